@@ -1,0 +1,260 @@
+"""Generate tests/golden/*.npz from the UNMODIFIED reference (TEST INFRASTRUCTURE).
+
+Run in the build container only (``python -m oracle.make_golden``): it imports
+graphBuilder.py, model.py, hybrid_model.py, dataset.py, embed_utils.py and
+train_hybrid_maml_v5.py straight from /root/reference over oracle/pyg_shim.py,
+executes them on seeded synthetic inputs, checks oracle/ref_port.py against
+them, and freezes the reference's outputs as fixtures.  /root/reference does
+not exist on the GPU box; only the fixtures travel.
+
+Dropout: the reference's training functions call ``.train()``; its three dropout
+sites cannot be RNG-matched by a batched implementation, so the
+reference models are *constructed* with dropout_rate=0 / lstm_dropout=0 -- the
+reference's own constructor arguments, no code changed.
+"""
+from __future__ import annotations
+
+import contextlib
+import io
+import os
+import sys
+
+import numpy as np
+import torch
+
+REF = "/root/reference"
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+
+SAMPLE_IDX_SEED = 1234
+
+
+def _import_reference():
+    from oracle import pyg_shim
+
+    pyg_shim.install()
+    if REF not in sys.path:
+        sys.path.insert(0, REF)
+    with contextlib.redirect_stdout(io.StringIO()):
+        import graphBuilder, model, hybrid_model, dataset, embed_utils  # noqa: E401
+        import train_hybrid_maml_v5 as train
+    return graphBuilder, model, hybrid_model, dataset, embed_utils, train
+
+
+def sample_indices(numel, count=64):
+    g = np.random.RandomState(SAMPLE_IDX_SEED + numel % 9973)
+    return np.sort(g.choice(numel, size=min(count, numel), replace=False))
+
+
+def summarize(t):
+    """(l2 norm, sum, sampled values) of a tensor -- a compact fixture for big tensors."""
+    a = t.detach().double().reshape(-1).numpy()
+    idx = sample_indices(a.size)
+    return np.array([np.sqrt((a * a).sum()), a.sum()]), a[idx].astype(np.float32)
+
+
+def build_ref_model(mods, sd, cfg):
+    _, model, hybrid_model, _, _, _ = mods
+    base = model.STGCN(cfg["in"], cfg["hidden"], out_channels=cfg["out"], window_size=cfg["T"],
+                       forecast_horizon=cfg["H"], dropout_rate=0.0)
+    hyb = hybrid_model.HybridSTGCN_LSTM(base, lstm_hidden_size=cfg["L"], lstm_num_layers=cfg["layers"],
+                                        lstm_dropout=0.0, out_channels=cfg["out"], forecast_horizon=cfg["H"],
+                                        freeze_base=False)
+    missing = hyb.load_state_dict(sd, strict=True)
+    assert not missing.missing_keys and not missing.unexpected_keys
+    return hyb
+
+
+def run_case(mods, name, cfg, nlat, nlon, k, seed, inner_steps, full_tensors):
+    from oracle import ref_port as P
+    from weatherforecast_stgcn_maml_b200 import synth
+
+    graphBuilder, model, hybrid_model, dataset, embed_utils, train = mods
+    T, H = cfg["T"], cfg["H"]
+    lats, lons = synth.region_grid(nlat, nlon)
+    with contextlib.redirect_stdout(io.StringIO()):
+        edge_index, n, pos = graphBuilder.build_spatial_graph(synth.GridCoords(lats, lons), k_neighbors=k)
+    assert torch.equal(edge_index, P.knn_edges_ckdtree(lats, lons, k))
+    sd = synth.init_v5_state_dict(seed, gcn_bias_scale=0.05, in_channels=cfg["in"], hidden=cfg["hidden"],
+                                  lstm_hidden=cfg["L"], lstm_layers=cfg["layers"], out_channels=cfg["out"],
+                                  horizon=H)
+    feats = synth.synth_features(T + H + 8, n, seed + 1, synth.koppen_table(seed)[3])
+    ds = dataset.WeatherGraphDataset(feats, edge_index, window_size=T, forecast_horizon=H)
+    assert len(ds) == P.num_windows(feats, T, H)
+    out = {"edge_index": edge_index.numpy().astype(np.int32), "k": k, "nlat": nlat, "nlon": nlon,
+           "seed": seed, "cfg": np.array([cfg[x] for x in ("in", "hidden", "L", "layers", "out", "T", "H")])}
+
+    hyb = build_ref_model(mods, sd, cfg)
+    assert sum(p.numel() for p in hyb.parameters()) == sum(v.numel() for v in sd.values())
+    out["state_dict_keys"] = np.array(list(hyb.state_dict().keys()))
+    assert list(hyb.state_dict().keys()) == list(sd.keys())
+
+    # ---- forward / loss / backward on window 0, eval mode (hybrid_model.py:80-117)
+    hyb.train()  # dropout p = 0 everywhere
+    d0 = ds[0]
+    x_p, y_p = P.window_xy(feats, 0, T, H)
+    assert torch.equal(d0.x, x_p) and torch.equal(d0.y, y_p)
+    pred = hyb(d0.x, d0.edge_index)
+    loss = torch.nn.MSELoss()(pred, d0.y)
+    loss.backward()
+    ref_grads = {k_: p.grad for k_, p in hyb.named_parameters()}
+    assert all(ref_grads[k_] is None for k_ in sd if k_.startswith("base_stgcn."))
+    p_loss, p_grads, p_pred = P.loss_and_grads(sd, x_p, y_p, edge_index, T, H, 1.0, cfg["layers"])
+    err = (p_pred - pred).abs().max().item() / pred.abs().max().item()
+    assert err < 2e-6, f"port forward vs reference: {err}"
+    for k_ in p_grads:
+        e = (p_grads[k_] - ref_grads[k_]).abs().max().item() / (ref_grads[k_].abs().max().item() + 1e-30)
+        assert e < 2e-5, f"port grad {k_}: {e}"
+    out["pred"] = pred.detach().numpy()
+    out["loss"] = np.float64(loss.item())
+
+    # base features (hybrid_model.py:60-78)
+    bf = hyb.extract_base_features(d0.x, d0.edge_index)
+    pf = P.gcn_stack(sd, x_p, edge_index)
+    assert (bf - pf).abs().max().item() <= 1e-6 * bf.abs().max().item()
+    out["base_features_summary"], out["base_features_samples"] = summarize(bf)
+    if full_tensors:
+        out["base_features"] = bf.numpy()
+
+    for k_, g in ref_grads.items():
+        if g is None:
+            continue
+        s, v = summarize(g)
+        out[f"grad_summary/{k_}"], out[f"grad_samples/{k_}"] = s, v
+        if full_tensors:
+            out[f"grad/{k_}"] = g.numpy()
+
+    # ---- STGCN.forward fwd+bwd (model.py:30-52): the only differentiable GCN use (D4)
+    base_sd = {k_[len("base_stgcn."):]: v for k_, v in sd.items() if k_.startswith("base_stgcn.")}
+    base = model.STGCN(cfg["in"], cfg["hidden"], out_channels=cfg["out"], window_size=T,
+                       forecast_horizon=H, dropout_rate=0.0)
+    base.load_state_dict(base_sd)
+    base.train()
+    xs = d0.x.clone().requires_grad_(True)
+    sp = base(xs, d0.edge_index)
+    sl = torch.nn.MSELoss()(sp, d0.y)
+    sl.backward()
+    leaf = {k_: v.clone().requires_grad_(True) for k_, v in base_sd.items()}
+    xs2 = d0.x.clone().requires_grad_(True)
+    pp = P.stgcn_forward(leaf, xs2, edge_index, T, H, cfg["out"])
+    pl = torch.nn.functional.mse_loss(pp, d0.y)
+    pg = torch.autograd.grad(pl, list(leaf.values()) + [xs2])
+    assert (pp - sp).abs().max().item() <= 2e-6 * sp.abs().max().item()
+    for (k_, _), g in zip(list(leaf.items()), pg):
+        rg = dict(base.named_parameters())[k_].grad
+        assert (g - rg).abs().max().item() <= 2e-5 * (rg.abs().max().item() + 1e-30), k_
+    assert (pg[-1] - xs.grad).abs().max().item() <= 2e-5 * xs.grad.abs().max().item()
+    out["stgcn_pred"] = sp.detach().numpy()
+    out["stgcn_loss"] = np.float64(sl.item())
+    for k_, p in base.named_parameters():
+        s, v = summarize(p.grad)
+        out[f"stgcn_grad_summary/{k_}"], out[f"stgcn_grad_samples/{k_}"] = s, v
+        if full_tensors:
+            out[f"stgcn_grad/{k_}"] = p.grad.numpy()
+    out["stgcn_dx_summary"], out["stgcn_dx_samples"] = summarize(xs.grad)
+    if full_tensors:
+        out["stgcn_dx"] = xs.grad.numpy()
+
+    # ---- reference inner_loop_v4 + query backward (train_hybrid_maml_v5.py:110-141,162-169)
+    from torch.utils.data import Subset
+
+    hyb2 = build_ref_model(mods, sd, cfg)
+    kop = embed_utils.KoppenEmbedding(8)
+    support = Subset(ds, list(range(inner_steps)))
+    query = Subset(ds, [inner_steps])
+    train.INNER_EPOCHS_PER_TASK = 1  # module constant; the loop body is untouched
+    adapted, _ = train.inner_loop_v4(hyb2, kop, support, "cpu")
+    adapted.train()
+    qb = next(iter(train.DataLoader(query, batch_size=1, shuffle=False)))
+    # The copy still carries the last inner step's clipped grads (zero_grad runs at the START of
+    # each inner step, train_hybrid_maml_v5.py:130), so the reference's query backward (:169)
+    # ACCUMULATES onto them.  Both readings are frozen: "literal" (stale + query) and "fomaml"
+    # (query only, the meta-gradient this build defines).
+    stale = {k_: p.grad.clone() for k_, p in adapted.named_parameters() if p.grad is not None}
+    qout = adapted(qb.x, qb.edge_index)
+    qloss = torch.nn.MSELoss()(qout, qb.y) / train.GRAD_ACCUMULATION_STEPS
+    qloss.backward()
+    literal = {k_: p.grad.clone() for k_, p in adapted.named_parameters() if p.grad is not None}
+    assert all(p.grad is None for p in hyb2.parameters())  # nothing reaches the meta-params
+    adapted.zero_grad()
+    qloss2 = torch.nn.MSELoss()(adapted(qb.x, qb.edge_index), qb.y) / train.GRAD_ACCUMULATION_STEPS
+    qloss2.backward()
+    for k_, g in literal.items():
+        pure = dict(adapted.named_parameters())[k_].grad
+        assert (g - (stale[k_] + pure)).abs().max().item() <= 1e-6 * (g.abs().max().item() + 1e-30)
+        s, v = summarize(g)
+        out[f"literal_summary/{k_}"], out[f"literal_samples/{k_}"] = s, v
+        s, v = summarize(stale[k_])
+        out[f"stale_summary/{k_}"], out[f"stale_samples/{k_}"] = s, v
+    p_q, p_qg, p_fast = P.fomaml_task(sd, feats, edge_index, list(range(inner_steps)), inner_steps,
+                                      train.GRAD_ACCUMULATION_STEPS, window=T, horizon=H, lr=train.INNER_LR,
+                                      lstm_layers=cfg["layers"])
+    ad_sd = adapted.state_dict()
+    for k_ in P.trainable(sd):
+        e = (p_fast[k_] - ad_sd[k_]).abs().max().item() / ad_sd[k_].abs().max().item()
+        assert e < 2e-5, f"port adapted {k_}: {e}"
+        g = dict(adapted.named_parameters())[k_].grad
+        e = (p_qg[k_] - g).abs().max().item() / (g.abs().max().item() + 1e-30)
+        assert e < 1e-4, f"port fomaml grad {k_}: {e}"
+        s, v = summarize(ad_sd[k_])
+        out[f"adapted_summary/{k_}"], out[f"adapted_samples/{k_}"] = s, v
+        s, v = summarize(g)
+        out[f"fomaml_summary/{k_}"], out[f"fomaml_samples/{k_}"] = s, v
+        if full_tensors:
+            out[f"adapted/{k_}"] = ad_sd[k_].numpy()
+            out[f"fomaml/{k_}"] = g.numpy()
+    for k_ in sd:
+        if k_.startswith("base_stgcn."):
+            assert torch.equal(ad_sd[k_], sd[k_])  # SGD skips grad=None params
+    out["inner_steps"] = inner_steps
+    out["accum"] = train.GRAD_ACCUMULATION_STEPS
+    out["inner_lr"] = train.INNER_LR
+    out["query_loss_scaled"] = np.float64(qloss.item())
+    assert abs(float(p_q) - qloss.item()) <= 1e-5 * abs(qloss.item())
+
+    if full_tensors:
+        for k_, v in sd.items():
+            out[f"sd/{k_}"] = v.numpy()
+        out["features"] = feats.numpy()
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
+    print(f"[golden] {name}: loss={loss.item():.6f} stgcn_loss={sl.item():.6f} qloss/accum={qloss.item():.6f}")
+
+
+def knn_cases(mods):
+    from oracle import ref_port as P
+    from weatherforecast_stgcn_maml_b200 import synth
+
+    graphBuilder = mods[0]
+    out = {}
+    for (nlat, nlon, k) in [(21, 21, 4), (21, 21, 8), (5, 7, 4), (3, 3, 2), (121, 121, 8), (40, 30, 4)]:
+        lats, lons = synth.region_grid(nlat, nlon)
+        with contextlib.redirect_stdout(io.StringIO()):
+            ei, n, pos = graphBuilder.build_spatial_graph(synth.GridCoords(lats, lons), k_neighbors=k)
+        assert n == nlat * nlon and ei.shape == (2, n * k) and ei.dtype == torch.int64
+        out[f"{nlat}x{nlon}_k{k}"] = ei.numpy().astype(np.int32)
+        if n <= 2000:
+            can = P.knn_edges_canonical(lats, lons, k)
+            d_ref = np.sort(P.knn_sq_distances(lats, lons, ei).reshape(n, k), axis=1)
+            d_can = np.sort(P.knn_sq_distances(lats, lons, can).reshape(n, k), axis=1)
+            assert np.array_equal(d_ref, d_can), "distance multisets must agree everywhere"
+    np.savez_compressed(os.path.join(OUT, "knn_ckdtree.npz"), **out)
+    print("[golden] knn_ckdtree:", {k_: v.shape for k_, v in out.items()})
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    torch.manual_seed(42)
+    np.random.seed(42)
+    torch.set_num_threads(os.cpu_count() or 1)
+    mods = _import_reference()
+    knn_cases(mods)
+    small = dict(T=6, H=2, hidden=32, L=32, layers=2, out=12)
+    small["in"] = 24
+    run_case(mods, "hybrid_small", small, nlat=3, nlon=4, k=4, seed=7, inner_steps=3, full_tensors=True)
+    full = dict(T=24, H=8, hidden=256, L=128, layers=4, out=12)
+    full["in"] = 24
+    run_case(mods, "hybrid_v5_k4", full, nlat=21, nlon=21, k=4, seed=42, inner_steps=3, full_tensors=False)
+    run_case(mods, "hybrid_v5_k8", full, nlat=21, nlon=21, k=8, seed=43, inner_steps=3, full_tensors=False)
+
+
+if __name__ == "__main__":
+    main()

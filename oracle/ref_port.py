@@ -1,0 +1,250 @@
+"""CPU restatement of the reference's v5 hot path (TEST INFRASTRUCTURE, see oracle/__init__.py).
+
+Functional style: every routine takes the weights as a plain ``dict`` of
+tensors keyed like the reference ``state_dict`` instead of
+``nn.Module`` objects.  Each function cites the reference lines it follows
+(paths are relative to /root/reference).  ``oracle/make_golden.py`` checks this
+file against the unmodified reference in the build container and freezes the
+results under tests/golden/; tests/test_oracle_golden.py re-checks it anywhere.
+
+Third-party arithmetic used natively (installed in the image): scipy cKDTree,
+torch CPU matmul / autograd / optimizers.  ``torch_geometric.GCNConv`` is absent
+and restated in ``gcn_norm`` / ``gcn_conv`` (PyG >= 2.0 defaults).
+"""
+from __future__ import annotations
+
+import copy
+import math
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+
+# --------------------------------------------------------------------------- graph
+def node_positions(lats, lons):
+    """graphBuilder.py:27-30 -- meshgrid(indexing='ij'), node id = ilat * nlon + ilon."""
+    la, lo = np.meshgrid(np.asarray(lats, np.float64), np.asarray(lons, np.float64), indexing="ij")
+    return np.c_[la.ravel(), lo.ravel()]
+
+
+def knn_edges_ckdtree(lats, lons, k):
+    """graphBuilder.py:34-44 -- cKDTree.query(k+1), drop column 0 (self), edges [node, nbr]."""
+    from scipy.spatial import cKDTree
+
+    pos = node_positions(lats, lons)
+    _, nb = cKDTree(pos).query(pos, k=k + 1)
+    n = len(pos)
+    src = np.repeat(np.arange(n, dtype=np.int64), k)
+    dst = nb[:, 1:].astype(np.int64).ravel()
+    return torch.from_numpy(np.stack([src, dst])).contiguous()
+
+
+def knn_edges_canonical(lats, lons, k):
+    """Brute-force k nearest by (squared distance, index) -- the deterministic tie rule.
+
+    Same metric as graphBuilder.py:34-35 (Euclidean on raw degrees, float64).  Where no
+    tie straddles the k-th place this equals cKDTree's neighbour *set*; the distance
+    multiset is equal everywhere.
+    """
+    pos = node_positions(lats, lons)
+    n = len(pos)
+    out = np.empty((n, k), dtype=np.int64)
+    for i in range(n):
+        dlat = pos[:, 0] - pos[i, 0]
+        dlon = pos[:, 1] - pos[i, 1]
+        d2 = dlat * dlat + dlon * dlon
+        d2[i] = -1.0
+        order = np.lexsort((np.arange(n), d2))
+        out[i] = order[1 : k + 1]
+    src = np.repeat(np.arange(n, dtype=np.int64), k)
+    return torch.from_numpy(np.stack([src, out.ravel()])).contiguous()
+
+
+def knn_sq_distances(lats, lons, edge_index):
+    pos = node_positions(lats, lons)
+    d = pos[edge_index[0].numpy()] - pos[edge_index[1].numpy()]
+    return (d * d).sum(1)
+
+
+def gcn_norm(edge_index, num_rows):
+    """PyG gcn_norm as invoked by every GCNConv.forward (model.py:31-40, hybrid_model.py:65-74).
+
+    num_rows = x.size(0) = window * N, NOT the N of the graph: rows >= N
+    only get their self loop, deg 1, weight 1.
+    """
+    row, col = edge_index[0], edge_index[1]
+    keep = row != col
+    loops = torch.arange(num_rows, dtype=torch.long)
+    row = torch.cat([row[keep], loops])
+    col = torch.cat([col[keep], loops])
+    deg = torch.zeros(num_rows, dtype=torch.float32).scatter_add_(0, col, torch.ones(row.numel()))
+    dis = deg.pow(-0.5)
+    dis[dis == float("inf")] = 0
+    w = dis[row] * torch.ones(row.numel()) * dis[col]
+    return row, col, w
+
+
+def gcn_conv(x, edge_index, weight, bias):
+    """PyG GCNConv.forward: out[i] = sum_{e: dst_e = i} w_e * (x W^T)[src_e] + b."""
+    row, col, w = gcn_norm(edge_index, x.size(0))
+    h = x @ weight.t()
+    out = torch.zeros_like(h).index_add_(0, col, w[:, None] * h[row])
+    return out + bias
+
+
+def gcn_stack(sd, x, edge_index, prefix="base_stgcn."):
+    """hybrid_model.py:60-78 / model.py:31-42 with dropout off: 4 x relu(GCNConv)."""
+    h = x
+    for i in range(1, 5):
+        h = torch.relu(gcn_conv(h, edge_index, sd[f"{prefix}conv{i}.lin.weight"], sd[f"{prefix}conv{i}.bias"]))
+    return h
+
+
+# --------------------------------------------------------------------------- LSTM + head
+def lstm_last_hidden(sd, seq, num_layers, prefix="lstm."):
+    """torch.nn.LSTM(batch_first, zero initial state) restated cell by cell.
+
+    hybrid_model.py:42-49 (definition) and :93-105 (use): gates ordered i, f, g, o;
+    c = f*c + i*g; h = o*tanh(c); returns the top layer's h at the last step,
+    i.e. ``lstm_out[:, -1, :]``.  ``seq`` is [batch, T, F]: the reference feeds one node
+    at a time (batch 1); batching over nodes is the same arithmetic per row.
+    """
+    inp = seq
+    for l in range(num_layers):
+        w_ih, w_hh = sd[f"{prefix}weight_ih_l{l}"], sd[f"{prefix}weight_hh_l{l}"]
+        b = sd[f"{prefix}bias_ih_l{l}"] + sd[f"{prefix}bias_hh_l{l}"]
+        hid = w_hh.shape[1]
+        h = seq.new_zeros(seq.shape[0], hid)
+        c = seq.new_zeros(seq.shape[0], hid)
+        outs = []
+        for t in range(inp.shape[1]):
+            g = inp[:, t] @ w_ih.t() + h @ w_hh.t() + b
+            i, f, gg, o = g.chunk(4, dim=1)
+            c = torch.sigmoid(f) * c + torch.sigmoid(i) * torch.tanh(gg)
+            h = torch.sigmoid(o) * torch.tanh(c)
+            outs.append(h)
+        inp = torch.stack(outs, dim=1)
+    return inp[:, -1]
+
+
+def hybrid_forward(sd, x, edge_index, window, horizon=8, out_channels=12, lstm_layers=4):
+    """hybrid_model.py:80-117 in eval mode (dropout off).  Returns f32[N*horizon, out]."""
+    with torch.no_grad():  # hybrid_model.py:63 -- unconditional, even when not frozen (D4)
+        feats = gcn_stack({k: v.detach() for k, v in sd.items() if k.startswith("base_stgcn.")}, x, edge_index)
+    n = feats.shape[0] // window
+    seq = feats.view(window, n, -1).permute(1, 0, 2)  # :89-90
+    last = lstm_last_hidden(sd, seq, lstm_layers)  # :93-105
+    pred = last @ sd["output_layer.weight"].t() + sd["output_layer.bias"]  # :111
+    return pred.view(n, horizon, out_channels).reshape(-1, out_channels)  # :114-115 (row = node*H + h)
+
+
+def stgcn_forward(sd, x, edge_index, window, horizon=8, out_channels=12, prefix=""):
+    """model.py:30-52 in eval mode: differentiable 4 x GCN, last N rows, Linear head."""
+    h = gcn_stack(sd, x, edge_index, prefix=prefix)
+    n = h.shape[0] // window
+    h = h[-n:]
+    out = h @ sd[f"{prefix}output_layer.weight"].t() + sd[f"{prefix}output_layer.bias"]
+    return out.view(n, horizon, out_channels).reshape(-1, out_channels)
+
+
+# --------------------------------------------------------------------------- windows
+def window_xy(features, idx, window=24, horizon=8, num_weather=12):
+    """dataset.py:30-48: x = features[idx : idx+W] flattened time-major; targets at
+    actual_idx + h for h = 1..H with actual_idx = idx + W (index actual_idx itself is skipped)."""
+    n = features.shape[1]
+    x = features[idx : idx + window].reshape(window * n, -1)
+    a = idx + window
+    y = torch.stack([features[a + h, :, :num_weather] for h in range(1, horizon + 1)], 0)
+    return x.clone(), y.reshape(horizon * n, num_weather).clone()
+
+
+def num_windows(features, window=24, horizon=8):
+    """dataset.py:25: len(range(window, T - horizon))."""
+    return features.shape[0] - window - horizon
+
+
+# --------------------------------------------------------------------------- training pieces
+def trainable(sd):
+    return [k for k in sd if k.startswith(("lstm.", "output_layer."))]
+
+
+def clip_grad_norm(grads, max_norm=1.0):
+    """torch.nn.utils.clip_grad_norm_ (train_hybrid_maml_v5.py:135-138): one global L2
+    norm over the non-None grads, scale by min(1, max_norm / (norm + 1e-6))."""
+    total = torch.linalg.vector_norm(torch.stack([torch.linalg.vector_norm(g) for g in grads]))
+    coef = torch.clamp(max_norm / (total + 1e-6), max=1.0)
+    for g in grads:
+        g.mul_(coef)
+    return total
+
+
+def loss_and_grads(sd, x, y, edge_index, window, horizon=8, scale=1.0, lstm_layers=4):
+    """forward + nn.MSELoss + backward (train_hybrid_maml_v5.py:132-134, 166-169).
+
+    Returns (loss, {name: grad}) over the 18 tensors autograd reaches (D4)."""
+    names = trainable(sd)
+    leaf = {k: (v.detach().clone().requires_grad_(True) if k in names else v.detach()) for k, v in sd.items()}
+    pred = hybrid_forward(leaf, x, edge_index, window, horizon, y.shape[1], lstm_layers)
+    loss = F.mse_loss(pred, y) * scale
+    grads = torch.autograd.grad(loss, [leaf[k] for k in names])
+    return loss.detach(), dict(zip(names, grads)), pred.detach()
+
+
+def inner_loop(sd, features, edge_index, steps, window=24, horizon=8, lr=0.01, lstm_layers=4):
+    """train_hybrid_maml_v5.py:110-141: deepcopy, then for each listed support window:
+    zero_grad, forward, MSE, backward, clip(1.0), plain SGD.  ``steps`` is the sequence of
+    support-window indices (reference: 6 x [0..14])."""
+    fast = {k: v.clone() for k, v in sd.items()}
+    losses = []
+    for idx in steps:
+        x, y = window_xy(features, idx, window, horizon)
+        loss, grads, _ = loss_and_grads(fast, x, y, edge_index, window, horizon, 1.0, lstm_layers)
+        gl = [grads[k].clone() for k in grads]
+        clip_grad_norm(gl, 1.0)
+        for k, g in zip(grads, gl):
+            fast[k] = fast[k] - lr * g
+        losses.append(float(loss))
+    return fast, losses
+
+
+def fomaml_task(sd, features, edge_index, support_steps, query_idx, accum, **kw):
+    """One task of meta_update_v4 (train_hybrid_maml_v5.py:151-170): inner loop, then the
+    first query window, loss / GRAD_ACCUMULATION_STEPS, backward INTO THE ADAPTED COPY.
+    Returns (query_loss/accum, grads on the adapted copy, adapted weights)."""
+    fast, _ = inner_loop(sd, features, edge_index, support_steps, **kw)
+    x, y = window_xy(features, query_idx, kw.get("window", 24), kw.get("horizon", 8))
+    loss, grads, _ = loss_and_grads(fast, x, y, edge_index, kw.get("window", 24), kw.get("horizon", 8),
+                                    1.0 / accum, kw.get("lstm_layers", 4))
+    return loss, grads, fast
+
+
+# --------------------------------------------------------------------------- literal-cost model
+def build_reference_like_module(sd, window, horizon=8, lstm_layers=4):
+    """An nn.LSTM + per-node Python loop with the reference's execution shape
+    (hybrid_model.py:93-105: one nn.LSTM call per node, batch 1).  Used by bench.py's
+    cpu_baseline leg so the timed CPU work has the reference's cost profile."""
+    hid = sd["lstm.weight_hh_l0"].shape[1]
+    lstm = torch.nn.LSTM(sd["lstm.weight_ih_l0"].shape[1], hid, lstm_layers, batch_first=True)
+    with torch.no_grad():
+        for l in range(lstm_layers):
+            for nm in ("weight_ih", "weight_hh", "bias_ih", "bias_hh"):
+                getattr(lstm, f"{nm}_l{l}").copy_(sd[f"lstm.{nm}_l{l}"])
+    head_w = sd["output_layer.weight"].clone().requires_grad_(True)
+    head_b = sd["output_layer.bias"].clone().requires_grad_(True)
+
+    def forward(x, edge_index):
+        with torch.no_grad():
+            feats = gcn_stack(sd, x, edge_index)
+        n = feats.shape[0] // window
+        seq = feats.view(window, n, -1).permute(1, 0, 2)
+        outs = []
+        for node in range(n):
+            o, _ = lstm(seq[node : node + 1])
+            outs.append(o[0, -1, :])
+        last = torch.stack(outs, 0)
+        pred = last @ head_w.t() + head_b
+        return pred.view(n, horizon, -1).reshape(-1, pred.shape[1] // horizon)
+
+    params = list(lstm.parameters()) + [head_w, head_b]
+    return forward, params
