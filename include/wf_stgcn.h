@@ -1,0 +1,128 @@
+/* wf_stgcn.h -- C ABI of libwf_stgcn.so, the sm_100a implementation of the
+ * Hybrid MAML-STGCN-LSTM v5 hot path (Yalt8826/WeatherForecast_STGCN_MAML).
+ *
+ * The reference has no FFI layer of its own (it is 13 Python files that call
+ * torch / torch_geometric / scipy); each entry point below names the reference
+ * lines whose work it replaces, and weatherforecast_stgcn_maml_b200/_lib.py is
+ * the ctypes binding a maintainer would add.
+ *
+ * Rules common to every launcher:
+ *   - all pointers are DEVICE pointers unless stated otherwise, f32 row-major;
+ *   - `stream` is a cudaStream_t passed as void*; work is enqueued, never synchronised;
+ *   - nothing is allocated: scratch comes from the caller, sized by *_workspace_bytes;
+ *   - returns 0, or <0 (WF_EINVAL -1, WF_ECUDA -2, WF_EWORKSPACE -3) with a message
+ *     available from wf_last_error() (thread-local);
+ *   - batching: G groups (MAML tasks: own graph + own fast weights) x Bw windows,
+ *     window w = g*Bw + b; a window has R = T*N rows, time-major (row = t*N + node),
+ *     the layout dataset.py:36-37 produces.
+ */
+#ifndef WF_STGCN_H
+#define WF_STGCN_H
+#include <stddef.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+int wf_abi_version(void);
+const char* wf_last_error(void);
+
+/* Number of trainable f32 values in the flat parameter buffer used by the LSTM/head entry
+ * points: per layer weight_ih[4L,Kin] weight_hh[4L,L] bias_ih[4L] bias_hh[4L] (Kin = F for
+ * layer 0, else L), then output_layer.weight[O,L], output_layer.bias[O] -- the order of the
+ * reference state_dict (hybrid_model.py:42-55).  606,304 for the v5 model. */
+long long wf_param_count(int layers, int F, int L, int O);
+
+/* graphBuilder.py:9-47 build_spatial_graph.  lats f64[nlat], lons f64[nlon] (device);
+ * node id = ilat*nlon + ilon.  Writes edge_index i64[2, N*k]: row 0 = node (each k times),
+ * row 1 = its k nearest neighbours ordered by (squared distance, index).  monotonic != 0
+ * (both axes strictly monotonic) enables the exhaustive (2k+1)^2 stencil search. */
+int wf_knn_grid_build(const double* lats, int nlat, const double* lons, int nlon, int k,
+                      int monotonic, long long* edge_index, void* stream);
+
+/* PyG gcn_norm (invoked by every GCNConv.forward: model.py:31-40, hybrid_model.py:65-74),
+ * computed once per region over R = window*N rows: self loops dropped, one added per row,
+ * deg = in-degree by target, w = deg[src]^-1/2 * deg[dst]^-1/2.  Emits A_hat as CSR by
+ * target (rowptr i32[R+1], col/val capacity E+R) and A_hat^T as CSR by source. */
+size_t wf_gcn_norm_workspace_bytes(long long E, int R);
+int wf_gcn_norm_csr(const long long* edge_index, long long E, int R, int* rowptr, int* col,
+                    float* val, int* rowptr_t, int* col_t, float* val_t, void* workspace,
+                    size_t workspace_bytes, void* stream);
+
+/* GCNConv + ReLU (model.py:31-42, hybrid_model.py:65-75): Y = relu((A_hat X) W^T + b).
+ * Window w of X starts at element x_win_off[w] (or w*x_win_stride), rows x_ld apart.
+ * rowptr == NULL means identity aggregation. */
+int wf_gcn_layer_fwd(const float* X, int x_ld, long long x_win_stride, const long long* x_win_off,
+                     const float* W, const float* bias, long long w_group_stride,
+                     long long b_group_stride, const int* rowptr, const int* col, const float* val,
+                     long long rowptr_group_stride, long long csr_group_stride, int R, int Cin,
+                     int Cout, int G, int Bw, int relu, float* Y, void* stream);
+
+/* Backward of the above (autograd through STGCN.forward, model.py:30-52).  dY is overwritten
+ * with dY*(Y>0).  dX/dW/db may be NULL. */
+size_t wf_gcn_layer_bwd_workspace_bytes(int R, int Cin, int Cout, int G, int Bw);
+int wf_gcn_layer_bwd(const float* X, int x_ld, long long x_win_stride, const long long* x_win_off,
+                     const float* Y, float* dY, const float* W, long long w_group_stride,
+                     const int* rowptr, const int* col, const float* val, const int* rowptr_t,
+                     const int* col_t, const float* val_t, long long rowptr_group_stride,
+                     long long csr_group_stride, int R, int Cin, int Cout, int G, int Bw, int relu,
+                     float* dX, float* dW, float* db, long long dw_group_stride,
+                     long long db_group_stride, void* workspace, size_t workspace_bytes, void* stream);
+
+/* nn.LSTM(F -> L, `layers`, batch_first) over every (task, window, node) sequence
+ * (hybrid_model.py:42-49, 93-105).  x [G*Bw*R, F]; gates [layers][G*Bw*R,4L],
+ * h, c [layers][G*Bw*R, L] are outputs kept for BPTT. */
+int wf_lstm_fwd(const float* x, const float* params, long long params_group_stride, int layers,
+                int F, int L, int O, int T, int N, int G, int Bw, float* gates, float* h, float* c,
+                void* stream);
+
+/* BPTT (loss.backward(): train_hybrid_maml_v5.py:134,169; adapt_hybrid_v5.py:198). */
+size_t wf_lstm_bwd_workspace_bytes(int layers, int F, int L, int T, int N, int G, int Bw);
+int wf_lstm_bwd(const float* x, const float* params, long long params_group_stride, int layers,
+                int F, int L, int O, int T, int N, int G, int Bw, float* gates, const float* h,
+                const float* c, const float* dlast, float* grads, long long grads_group_stride,
+                void* workspace, size_t workspace_bytes, void* stream);
+
+/* Linear head (hybrid_model.py:108-115): pred[G*Bw*N, O] = h_top[last step] W_o^T + b_o.
+ * Row n of a window's pred, viewed as [H, 12], is the reference's rows n*H .. n*H+H-1. */
+int wf_head_fwd(const float* h_top, const float* params, long long params_group_stride, int layers,
+                int F, int L, int O, int T, int N, int G, int Bw, float* pred, void* stream);
+
+/* nn.MSELoss per window (train_hybrid_maml_v5.py:133,167; adapt_hybrid_v5.py:197) and its
+ * gradient seed scaled by grad_scale.  Targets: y [windows, N*O] or, when y == NULL, read in
+ * place from feat with tgt_off[w] = element offset of features[idx+T+1] (dataset.py:40-48).
+ * The node-major prediction buffer is compared flat against the horizon-major target buffer,
+ * exactly as the reference does. */
+int wf_mse_fwd_bwd(const float* pred, const float* y, const float* feat, const long long* tgt_off,
+                   int feat_ld, int num_weather, int N, int O, int windows, float grad_scale,
+                   float* loss, float* dpred, void* stream);
+
+/* Head backward: dlast[G*Bw*N, L] = dpred W_o; grads (optional) gets dW_o, db_o. */
+size_t wf_head_workspace_bytes(int L, int O, int N, int G, int Bw);
+int wf_head_bwd(const float* dpred, const float* h_top, const float* params,
+                long long params_group_stride, int layers, int F, int L, int O, int T, int N, int G,
+                int Bw, float* dlast, float* grads, long long grads_group_stride, void* workspace,
+                size_t workspace_bytes, void* stream);
+
+/* clip_grad_norm_(max_norm) + SGD, one clip norm per task (train_hybrid_maml_v5.py:116-118,
+ * 135-139).  max_norm <= 0 disables clipping. */
+size_t wf_optim_workspace_bytes(int G);
+int wf_clip_sgd_step(float* theta, long long theta_group_stride, const float* grad,
+                     long long grad_group_stride, long long P, int G, float lr, float max_norm,
+                     float* norms, void* workspace, size_t workspace_bytes, void* stream);
+
+/* clip_grad_norm_ + AdamW (decoupled=1, train_hybrid_maml_v5.py:174-178,245-249) or Adam with
+ * L2 (decoupled=0, adaptive_scheduler.py:89-93; adapt_hybrid_v5.py:200-201).  hyper_dev: 8
+ * device floats {lr, beta1, beta2, eps, weight_decay, 1-beta1^t, 1-beta2^t, grad_scale}. */
+int wf_clip_adam_step(float* theta, const float* grad, float* exp_avg, float* exp_avg_sq,
+                      long long P, const float* hyper_dev, float max_norm, int decoupled,
+                      float* norm_out, void* workspace, size_t workspace_bytes, void* stream);
+
+/* dst[i] (+)= sum_g src[g*stride + i]: the per-task query gradients summed into the
+ * meta-gradient buffer (train_hybrid_maml_v5.py:169 accumulates .grad across tasks). */
+int wf_sum_groups(const float* src, long long src_group_stride, int G, long long P, float* dst,
+                  int accumulate, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,289 @@
+"""GPU parity of the training loops through the C ABI: fused clip+SGD / Adam(W), inner loop,
+FOMAML meta-gradient, meta_update_v4 (both readings of SURVEY.md D5), MetaTrainer, fine-tuning."""
+import copy
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import check_summary, golden_case, rel_err
+from oracle import ref_port as P
+from weatherforecast_stgcn_maml_b200 import synth
+
+pytestmark = pytest.mark.gpu
+FWD_TOL, GRAD_TOL = 1e-4, 1e-3
+
+
+def _small_cfg():
+    z, cfg, sd, feats, ei = golden_case("hybrid_small")
+    from weatherforecast_stgcn_maml_b200.engine import V5Dims
+
+    dims = V5Dims(num_nodes=cfg["nlat"] * cfg["nlon"], window=cfg["T"], horizon=cfg["H"], in_channels=cfg["cin"],
+                  hidden=cfg["hidden"], lstm_hidden=cfg["L"], lstm_layers=cfg["layers"], out_channels=cfg["out"])
+    return z, cfg, sd, feats, ei, dims
+
+
+def _hybrid(cfg, sd):
+    from weatherforecast_stgcn_maml_b200.hybrid_model import HybridSTGCN_LSTM
+    from weatherforecast_stgcn_maml_b200.model import STGCN
+
+    base = STGCN(cfg["cin"], cfg["hidden"], out_channels=cfg["out"], window_size=cfg["T"],
+                 forecast_horizon=cfg["H"], dropout_rate=0.0)
+    hyb = HybridSTGCN_LSTM(base, lstm_hidden_size=cfg["L"], lstm_num_layers=cfg["layers"], lstm_dropout=0.0,
+                           out_channels=cfg["out"], forecast_horizon=cfg["H"], freeze_base=False)
+    hyb.load_state_dict(sd)
+    return hyb.cuda()
+
+
+@pytest.mark.parametrize("scale", [0.01, 30.0])
+def test_clip_sgd_matches_torch(scale):
+    from weatherforecast_stgcn_maml_b200 import _lib
+
+    torch.manual_seed(0)
+    G, Pn = 3, 4096 + 64
+    theta = torch.randn(G, Pn)
+    grad = torch.randn(G, Pn) * scale
+    ref = theta.clone()
+    norms = []
+    for g in range(G):
+        p = torch.nn.Parameter(ref[g].clone())
+        p.grad = grad[g].clone()
+        norms.append(torch.nn.utils.clip_grad_norm_([p], 1.0))
+        torch.optim.SGD([p], lr=0.01).step()
+        ref[g] = p.detach()
+    th, gr = theta.cuda(), grad.cuda()
+    nr = torch.zeros(G, device="cuda")
+    nb = _lib.query("wf_optim_workspace_bytes", G)
+    ws = torch.empty(nb, dtype=torch.uint8, device="cuda")
+    _lib.call("wf_clip_sgd_step", _lib.ptr(th), Pn, _lib.ptr(gr), Pn, Pn, G, 0.01, 1.0, _lib.ptr(nr), _lib.ptr(ws), nb,
+              _lib.stream_ptr())
+    assert rel_err(th, ref) <= 1e-6
+    assert rel_err(nr, torch.stack(norms)) <= 1e-5
+
+
+@pytest.mark.parametrize("decoupled", [True, False])
+def test_clip_adam_matches_torch(decoupled):
+    from weatherforecast_stgcn_maml_b200.engine import AdamState
+
+    torch.manual_seed(1)
+    Pn = 10000
+    p = torch.nn.Parameter(torch.randn(Pn))
+    opt = (torch.optim.AdamW([p], lr=1e-3, weight_decay=1e-4) if decoupled
+           else torch.optim.Adam([p], lr=6e-4, weight_decay=1e-4))
+    theta = p.detach().clone().cuda()
+    st = AdamState(Pn, "cuda", 1e-3 if decoupled else 6e-4, weight_decay=1e-4, decoupled=decoupled)
+    for step in range(5):
+        g = torch.randn(Pn) * (5.0 if step % 2 else 0.001)
+        p.grad = g.clone()
+        torch.nn.utils.clip_grad_norm_([p], 1.0)
+        opt.step()
+        st.step(theta, g.cuda(), max_norm=1.0)
+        if step == 2:
+            for grp in opt.param_groups:
+                grp["lr"] = 3e-4
+            st.lr = 3e-4
+    assert rel_err(theta, p.detach()) <= 2e-6
+
+
+def test_inner_loop_and_fomaml_vs_reference_fixture():
+    """3 inner SGD steps + query backward on the v5 model, against the reference's own run."""
+    from weatherforecast_stgcn_maml_b200.engine import V5Dims, unflatten_trainable
+    from weatherforecast_stgcn_maml_b200.train_hybrid_maml_v5 import MetaTrainer
+
+    z, cfg, sd, feats, ei = golden_case("hybrid_v5_k4")
+    dims = V5Dims(num_nodes=441)
+    steps, accum = int(z["inner_steps"]), int(z["accum"])
+    mt = MetaTrainer(sd, [(feats, ei)], dims, "cuda", support_rows=tuple(range(steps)), query_row=steps,
+                     inner_lr=float(z["inner_lr"]), accum=accum, use_cuda_graph=False)
+    loss = mt.meta_step()
+    torch.cuda.synchronize()
+    assert abs(loss.item() - float(z["query_loss_scaled"])) <= FWD_TOL * float(z["query_loss_scaled"])
+    fast = unflatten_trainable(mt.fast[0].cpu(), dims)
+    mg = unflatten_trainable(mt.meta_gradient().cpu(), dims)
+    for k in fast:
+        check_summary(fast[k], z[f"adapted_summary/{k}"], z[f"adapted_samples/{k}"], GRAD_TOL, "adapted " + k)
+        check_summary(mg[k], z[f"fomaml_summary/{k}"], z[f"fomaml_samples/{k}"], GRAD_TOL, "fomaml " + k)
+
+
+def test_meta_trainer_two_tasks_vs_oracle_with_and_without_graph():
+    """Two tasks, different graphs; FOMAML gradient sum + fused AdamW vs oracle + torch.optim.AdamW."""
+    from weatherforecast_stgcn_maml_b200.train_hybrid_maml_v5 import MetaTrainer
+
+    z, cfg, sd, feats, ei, dims = _small_cfg()
+    lats, lons = synth.region_grid(cfg["nlat"], cfg["nlon"])
+    ei2 = P.knn_edges_canonical(lats, lons, cfg["k"])
+    feats2 = synth.synth_features(feats.shape[0], feats.shape[1], 77)
+    tasks = [(feats, ei), (feats2, ei2)]
+    kw = dict(window=cfg["T"], horizon=cfg["H"], lr=0.01, lstm_layers=cfg["layers"])
+    names = P.trainable(sd)
+    # oracle: two meta-steps, accum = 2, AdamW(lr 1e-3, wd 1e-4), clip 1.0
+    cur = {k: v.clone() for k, v in sd.items()}
+    params = [torch.nn.Parameter(cur[k].clone()) for k in names]
+    opt = torch.optim.AdamW(params, lr=1e-3, weight_decay=1e-4)
+    ref_losses = []
+    for it in range(2):
+        tot, gsum = 0.0, None
+        for f, e in tasks:
+            l, g, _ = P.fomaml_task(cur, f, e, [0, 1, 2], 3, 2, **kw)
+            tot += float(l)
+            gsum = g if gsum is None else {k: gsum[k] + g[k] for k in g}
+        for p, k in zip(params, names):
+            p.grad = gsum[k].clone()
+        torch.nn.utils.clip_grad_norm_(params, 1.0)
+        opt.step()
+        for p, k in zip(params, names):
+            cur[k] = p.detach().clone()
+        ref_losses.append(tot)
+    for use_graph in (False, True):
+        mt = MetaTrainer(sd, tasks, dims, "cuda", support_rows=(0, 1, 2), query_row=3, accum=2,
+                         use_cuda_graph=use_graph)
+        got = [mt.meta_step().item() for _ in range(2)]
+        torch.cuda.synchronize()
+        out = mt.state_dict()
+        assert np.allclose(got, ref_losses, rtol=FWD_TOL), (use_graph, got, ref_losses)
+        for k in names:
+            assert rel_err(out[k], cur[k]) <= 1e-4, (use_graph, k)
+        for k in sd:
+            if k.startswith("base_stgcn."):
+                assert torch.equal(out[k], sd[k])
+
+
+def _ref_tasks(cfg, feats_list, ei_list, n_support, dataset_mod):
+    from torch.utils.data import Subset
+
+    tasks = []
+    for f, e in zip(feats_list, ei_list):
+        ds = dataset_mod.WeatherGraphDataset(f, e, window_size=cfg["T"], forecast_horizon=cfg["H"])
+        tasks.append((Subset(ds, list(range(n_support))), Subset(ds, list(range(n_support, len(ds)))), {}))
+    return tasks
+
+
+def test_inner_loop_v4_dropin_signature_and_values():
+    """inner_loop_v4(model, koppen, support_ds, device): 6 epochs x first 15 windows (here 4 windows)."""
+    from weatherforecast_stgcn_maml_b200 import dataset as D
+    from weatherforecast_stgcn_maml_b200 import train_hybrid_maml_v5 as TR
+    from weatherforecast_stgcn_maml_b200.embed_utils import KoppenEmbedding
+
+    z, cfg, sd, feats, ei, dims = _small_cfg()
+    hyb, kop = _hybrid(cfg, sd), KoppenEmbedding(8).cuda()
+    support, query, _ = _ref_tasks(cfg, [feats], [ei], 4, D)[0]
+    adapted, akop = TR.inner_loop_v4(hyb, kop, support, "cuda")
+    assert adapted is not hyb and adapted.training and akop is not kop
+    steps = [0, 1, 2, 3] * TR.INNER_EPOCHS_PER_TASK
+    fast, _ = P.inner_loop(sd, feats, ei, steps, window=cfg["T"], horizon=cfg["H"], lr=TR.INNER_LR,
+                           lstm_layers=cfg["layers"])
+    asd = adapted.state_dict()
+    for k in sd:
+        if k.startswith("base_stgcn."):
+            assert torch.equal(asd[k].cpu(), sd[k])
+        else:
+            assert rel_err(asd[k], fast[k]) <= 2e-4, k
+    assert all(torch.equal(a, b) for a, b in zip(hyb.state_dict().values(), [v.cuda() for v in sd.values()]))
+
+
+def test_meta_update_v4_literal_reference_is_a_noop_and_fomaml_steps():
+    from weatherforecast_stgcn_maml_b200 import dataset as D
+    from weatherforecast_stgcn_maml_b200 import train_hybrid_maml_v5 as TR
+    from weatherforecast_stgcn_maml_b200.embed_utils import KoppenEmbedding
+
+    z, cfg, sd, feats, ei, dims = _small_cfg()
+    feats2 = synth.synth_features(feats.shape[0], feats.shape[1], 78)
+    tasks = _ref_tasks(cfg, [feats, feats2, feats], [ei, ei, ei], 3, D)
+    sched = lambda idx: list(idx[:15])  # one epoch keeps the oracle cheap
+    kw = dict(window=cfg["T"], horizon=cfg["H"], lr=TR.INNER_LR, lstm_layers=cfg["layers"])
+    # literal reading (D5): loss is reported, no parameter moves, optimiser state stays empty
+    hyb, kop = _hybrid(cfg, sd), KoppenEmbedding(8).cuda()
+    opt = torch.optim.AdamW(list(hyb.parameters()) + list(kop.parameters()), lr=TR.OUTER_LR, weight_decay=1e-4)
+    loss = TR.meta_update_v4(hyb, kop, tasks, "cuda", opt, literal_reference=True, support_schedule=sched)
+    ref = sum(float(P.fomaml_task(sd, f, ei, [0, 1, 2], 3, 2, **kw)[0]) for f in (feats, feats2, feats))
+    assert abs(loss - ref) <= FWD_TOL * ref
+    assert len(opt.state) == 0
+    assert all(torch.equal(v.cpu(), sd[k]) for k, v in hyb.state_dict().items())
+    # FOMAML reading: groups of 2 tasks, optimiser step after each group (train_hybrid_maml_v5.py:173-179)
+    hyb, kop = _hybrid(cfg, sd), KoppenEmbedding(8).cuda()
+    opt = torch.optim.AdamW(list(hyb.parameters()) + list(kop.parameters()), lr=TR.OUTER_LR, weight_decay=1e-4)
+    loss = TR.meta_update_v4(hyb, kop, tasks, "cuda", opt, support_schedule=sched)
+    names = P.trainable(sd)
+    cur = {k: v.clone() for k, v in sd.items()}
+    params = [torch.nn.Parameter(cur[k].clone()) for k in names]
+    ropt = torch.optim.AdamW(params, lr=TR.OUTER_LR, weight_decay=1e-4)
+    tot = 0.0
+    for group in ([feats, feats2], [feats]):
+        gsum = None
+        for f in group:
+            l, g, _ = P.fomaml_task(cur, f, ei, [0, 1, 2], 3, 2, **kw)
+            tot += float(l)
+            gsum = g if gsum is None else {k: gsum[k] + g[k] for k in g}
+        for p, k in zip(params, names):
+            p.grad = gsum[k].clone()
+        torch.nn.utils.clip_grad_norm_(params, 1.0)
+        ropt.step()
+        for p, k in zip(params, names):
+            cur[k] = p.detach().clone()
+    assert abs(loss - tot) <= FWD_TOL * tot
+    out = hyb.state_dict()
+    for k in names:
+        assert rel_err(out[k], cur[k]) <= 1e-4, k
+    assert all(p.grad is None for n, p in hyb.named_parameters() if n.startswith("base_stgcn."))
+    assert all(p.grad is None for p in kop.parameters())
+
+
+def test_fine_tune_steps_and_validation_vs_oracle():
+    """adapt_hybrid_v5.py:185-231 restated around synthetic data: Adam(L2), clip 1.0, batch-1 steps."""
+    from weatherforecast_stgcn_maml_b200.adapt_hybrid_v5 import FineTuner
+
+    z, cfg, sd, feats, ei, dims = _small_cfg()
+    feats = synth.synth_features(cfg["T"] + cfg["H"] + 12, feats.shape[1], 5)
+    n_win = P.num_windows(feats, cfg["T"], cfg["H"])
+    names = P.trainable(sd)
+    order = [3, 0, 5, 1, 7, 2]
+    for use_graph in (False, True):
+        ft = FineTuner(sd, feats, ei, dims, "cuda", region_name="Thailand", max_samples=n_win, train_frac=0.8,
+                       use_cuda_graph=use_graph, val_batch=2)
+        assert ft.train_size == int(0.8 * n_win) and abs(ft.initial_lr - 0.0006 * 0.9) < 1e-12
+        avg = ft.train_epoch(order)
+        val = ft.validate()
+        # oracle
+        cur = {k: v.clone() for k, v in sd.items()}
+        params = [torch.nn.Parameter(cur[k].clone()) for k in names]
+        opt = torch.optim.Adam(params, lr=0.0006 * 0.9, weight_decay=1e-5)
+        losses = []
+        for i in order:
+            x, y = P.window_xy(feats, i, cfg["T"], cfg["H"])
+            l, g, _ = P.loss_and_grads(cur, x, y, ei, cfg["T"], cfg["H"], 1.0, cfg["layers"])
+            for p, k in zip(params, names):
+                p.grad = g[k].clone()
+            torch.nn.utils.clip_grad_norm_(params, 1.0)
+            opt.step()
+            for p, k in zip(params, names):
+                cur[k] = p.detach().clone()
+            losses.append(float(l))
+        assert abs(avg - np.mean(losses)) <= FWD_TOL * np.mean(losses)
+        out = ft.state_dict()
+        for k in names:
+            assert rel_err(out[k], cur[k]) <= 2e-4, (use_graph, k)
+        vref = []
+        for i in ft.val_idx:
+            x, y = P.window_xy(feats, i, cfg["T"], cfg["H"])
+            vref.append(float(torch.nn.functional.mse_loss(P.hybrid_forward(cur, x, ei, cfg["T"], cfg["H"], 12, cfg["layers"]), y)))
+        assert abs(val - np.mean(vref)) <= 2e-4 * np.mean(vref)
+
+
+def test_adapt_region_checkpoint_contract():
+    from weatherforecast_stgcn_maml_b200.adapt_hybrid_v5 import adapt_region
+    from weatherforecast_stgcn_maml_b200.embed_utils import KoppenEmbedding
+
+    z, cfg, sd, feats, ei, dims = _small_cfg()
+    feats = synth.synth_features(cfg["T"] + cfg["H"] + 10, feats.shape[1], 6)
+    ckpt = {"hybrid_model_state_dict": sd, "koppen_embed_state_dict": KoppenEmbedding(8).state_dict(),
+            "config": {"input_channels": cfg["cin"], "hidden_channels": cfg["hidden"], "output_channels": cfg["out"],
+                       "window_size": cfg["T"], "forecast_horizon": cfg["H"]},
+            "hybrid_config": {"lstm_hidden_size": cfg["L"], "lstm_num_layers": cfg["layers"], "lstm_dropout": 0.2}}
+    out = adapt_region(ckpt, feats, ei, (18, 23, 75, 80), "India", stats={"mean": np.zeros(12), "std": np.ones(12)},
+                       epochs=2, verbose=False)
+    assert set(out) == {"hybrid_model_state_dict", "koppen_embed_state_dict", "region", "region_name", "climate_type",
+                        "stats", "config", "hybrid_config", "model_version", "adaptation_type", "val_loss",
+                        "base_model_loss", "total_params"}
+    assert list(out["hybrid_model_state_dict"].keys()) == list(sd.keys())
+    assert out["total_params"] == sum(v.numel() for v in sd.values()) and np.isfinite(out["val_loss"])
+    _hybrid(cfg, out["hybrid_model_state_dict"])  # loads back into the drop-in classes

@@ -1,0 +1,120 @@
+"""The oracle port (oracle/ref_port.py) against the fixtures frozen from the unmodified reference
+(oracle/make_golden.py).  CPU only; this is what pins the oracle outside the build container."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import check_summary, golden_case, load_golden, rel_err
+from oracle import ref_port as P
+from weatherforecast_stgcn_maml_b200 import synth
+
+
+@pytest.mark.parametrize("key", ["21x21_k4", "21x21_k8", "5x7_k4", "3x3_k2", "40x30_k4"])
+def test_knn_ckdtree_matches_fixture(key):
+    z = load_golden("knn_ckdtree")
+    grid, k = key.split("_k")
+    nlat, nlon = (int(v) for v in grid.split("x"))
+    lats, lons = synth.region_grid(nlat, nlon)
+    ei = P.knn_edges_ckdtree(lats, lons, int(k))
+    assert ei.dtype == torch.int64 and tuple(ei.shape) == (2, nlat * nlon * int(k))
+    assert np.array_equal(ei.numpy(), z[key].astype(np.int64))
+
+
+@pytest.mark.parametrize("key", ["21x21_k4", "21x21_k8", "5x7_k4", "3x3_k2"])
+def test_canonical_knn_vs_ckdtree_contract(key):
+    """Same distance multiset everywhere; same neighbour set wherever no tie straddles the k-th place."""
+    z = load_golden("knn_ckdtree")
+    grid, k = key.split("_k")
+    k = int(k)
+    nlat, nlon = (int(v) for v in grid.split("x"))
+    n = nlat * nlon
+    lats, lons = synth.region_grid(nlat, nlon)
+    ref = torch.from_numpy(z[key].astype(np.int64))
+    can = P.knn_edges_canonical(lats, lons, k)
+    d_ref = P.knn_sq_distances(lats, lons, ref).reshape(n, k)
+    d_can = P.knn_sq_distances(lats, lons, can).reshape(n, k)
+    assert np.array_equal(np.sort(d_ref, 1), d_can)  # canonical rows are already sorted
+    pos = P.node_positions(lats, lons)
+    differing = 0
+    for i in range(n):
+        d2 = ((pos - pos[i]) ** 2).sum(1)
+        d2[i] = np.inf
+        kth = np.sort(d2)[k - 1]
+        straddle = (d2 == kth).sum() > (d_can[i] == kth).sum()
+        same = set(ref[1, i * k:(i + 1) * k].tolist()) == set(can[1, i * k:(i + 1) * k].tolist())
+        assert same or straddle, f"node {i}: sets differ without a straddling tie"
+        differing += not same
+    if key == "21x21_k8":
+        assert differing <= 8  # only the edge nodes next to the corners
+
+
+def test_dataset_window_layout():
+    feats = synth.synth_features(60, 6, 0)
+    assert P.num_windows(feats, 24, 8) == 28
+    x, y = P.window_xy(feats, 3, 24, 8)
+    assert x.shape == (24 * 6, 24) and y.shape == (8 * 6, 12)
+    assert torch.equal(x[0], feats[3, 0]) and torch.equal(x[6 * 23 + 2], feats[26, 2])
+    assert torch.equal(y[0], feats[28, 0, :12]) and torch.equal(y[6 * 7 + 5], feats[35, 5, :12])
+
+
+@pytest.mark.parametrize("name", ["hybrid_small", "hybrid_v5_k4", "hybrid_v5_k8"])
+def test_port_forward_backward_matches_reference(name):
+    z, cfg, sd, feats, ei = golden_case(name)
+    T, H = cfg["T"], cfg["H"]
+    assert list(sd.keys()) == [str(k) for k in z["state_dict_keys"]]
+    x, y = P.window_xy(feats, 0, T, H)
+    loss, grads, pred = P.loss_and_grads(sd, x, y, ei, T, H, 1.0, cfg["layers"])
+    assert rel_err(pred, torch.from_numpy(z["pred"])) <= 5e-6
+    assert abs(float(loss) - float(z["loss"])) <= 1e-5 * float(z["loss"])
+    assert sorted(grads) == sorted(P.trainable(sd)) and len(grads) == 2 + 4 * cfg["layers"]
+    for k, g in grads.items():
+        check_summary(g, z[f"grad_summary/{k}"], z[f"grad_samples/{k}"], 5e-5, k)
+    bf = P.gcn_stack(sd, x, ei)
+    check_summary(bf, z["base_features_summary"], z["base_features_samples"], 1e-5, "base features")
+
+
+@pytest.mark.parametrize("name", ["hybrid_small", "hybrid_v5_k4"])
+def test_port_stgcn_forward_backward_matches_reference(name):
+    z, cfg, sd, feats, ei = golden_case(name)
+    T, H = cfg["T"], cfg["H"]
+    x, y = P.window_xy(feats, 0, T, H)
+    leaf = {k[len("base_stgcn."):]: v.clone().requires_grad_(True) for k, v in sd.items() if k.startswith("base_stgcn.")}
+    xs = x.clone().requires_grad_(True)
+    pred = P.stgcn_forward(leaf, xs, ei, T, H, cfg["out"])
+    loss = torch.nn.functional.mse_loss(pred, y)
+    grads = torch.autograd.grad(loss, list(leaf.values()) + [xs])
+    assert rel_err(pred, torch.from_numpy(z["stgcn_pred"])) <= 5e-6
+    for (k, _), g in zip(leaf.items(), grads):
+        check_summary(g, z[f"stgcn_grad_summary/{k}"], z[f"stgcn_grad_samples/{k}"], 5e-5, k)
+    check_summary(grads[-1], z["stgcn_dx_summary"], z["stgcn_dx_samples"], 5e-5, "dx")
+
+
+@pytest.mark.parametrize("name", ["hybrid_small", "hybrid_v5_k4"])
+def test_port_inner_loop_and_fomaml_match_reference(name):
+    z, cfg, sd, feats, ei = golden_case(name)
+    steps, accum = int(z["inner_steps"]), int(z["accum"])
+    kw = dict(window=cfg["T"], horizon=cfg["H"], lr=float(z["inner_lr"]), lstm_layers=cfg["layers"])
+    qloss, qgrads, fast = P.fomaml_task(sd, feats, ei, list(range(steps)), steps, accum, **kw)
+    assert abs(float(qloss) - float(z["query_loss_scaled"])) <= 2e-5 * float(z["query_loss_scaled"])
+    for k in P.trainable(sd):
+        check_summary(fast[k], z[f"adapted_summary/{k}"], z[f"adapted_samples/{k}"], 5e-5, "adapted " + k)
+        check_summary(qgrads[k], z[f"fomaml_summary/{k}"], z[f"fomaml_samples/{k}"], 2e-4, "fomaml " + k)
+    for k in sd:
+        if k.startswith("base_stgcn."):
+            assert torch.equal(fast[k], sd[k])  # SGD never touches grad=None parameters (D4)
+
+
+def test_literal_reference_grad_is_stale_plus_query():
+    """SURVEY.md D5 detail: the reference's copy keeps the last inner step's clipped grad."""
+    z, cfg, sd, feats, ei = golden_case("hybrid_small")
+    steps, accum = int(z["inner_steps"]), int(z["accum"])
+    kw = dict(window=cfg["T"], horizon=cfg["H"], lr=float(z["inner_lr"]), lstm_layers=cfg["layers"])
+    fast, _ = P.inner_loop(sd, feats, ei, list(range(steps - 1)), **kw)
+    x, y = P.window_xy(feats, steps - 1, cfg["T"], cfg["H"])
+    _, g_last, _ = P.loss_and_grads(fast, x, y, ei, cfg["T"], cfg["H"], 1.0, cfg["layers"])
+    gl = [g_last[k].clone() for k in g_last]
+    P.clip_grad_norm(gl, 1.0)
+    _, qgrads, _ = P.fomaml_task(sd, feats, ei, list(range(steps)), steps, accum, **kw)
+    for k, stale in zip(g_last, gl):
+        check_summary(stale, z[f"stale_summary/{k}"], z[f"stale_samples/{k}"], 1e-4, "stale " + k)
+        check_summary(stale + qgrads[k], z[f"literal_summary/{k}"], z[f"literal_samples/{k}"], 2e-4, "literal " + k)

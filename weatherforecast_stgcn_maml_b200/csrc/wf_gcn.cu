@@ -1,0 +1,112 @@
+// GCN layer forward / backward (C-ABI).
+//
+// Replaces PyG GCNConv.forward + F.relu as used at model.py:31-42 and
+// hybrid_model.py:65-75:  Y = relu( A_hat (X W^T) + b ).  Computed as
+// Y = relu( (A_hat X) W^T + b ): the neighbour aggregation is the A-operand loader of
+// the GEMM (CSR gather, 128-bit loads), bias + ReLU are its epilogue -- one launch per
+// layer, no [E, C] message tensor, no intermediate in HBM.
+//
+// Backward (only reachable through STGCN.forward, model.py:30-52; the hybrid path runs the
+// convolutions under no_grad, hybrid_model.py:63):
+//   dPre = dY * (Y > 0);  db = colsum(dPre);  dW = dPre^T (A_hat X);  dX = (A_hat^T dPre) W
+#include "wf_gemm.cuh"
+
+int wf_launch_spmm(const float* X, RowMap xm, long long gX, const int* rowptr, const int* col, const float* val,
+                   long long gRowptr, long long gCsr, int R, int rows, int C, float* Z, long long gZ, int groups,
+                   cudaStream_t st);
+
+__global__ void wf_relu_mask_kernel(float4* __restrict__ dY, const float4* __restrict__ Y, long long quads) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= quads) return;
+  float4 d = dY[i], y = Y[i];
+  d.x = y.x > 0.f ? d.x : 0.f; d.y = y.y > 0.f ? d.y : 0.f;
+  d.z = y.z > 0.f ? d.z : 0.f; d.w = y.w > 0.f ? d.w : 0.f;
+  dY[i] = d;
+}
+
+// X addressing: window w = g*Bw + b starts at element  (x_win_off ? x_win_off[w] : w * x_win_stride)
+// from X; rows inside a window are x_ld apart.  Y/dY/dX are dense [G*Bw*R, C].
+extern "C" int wf_gcn_layer_fwd(const float* X, int x_ld, long long x_win_stride, const long long* x_win_off,
+                                const float* W, const float* bias, long long w_group_stride,
+                                long long b_group_stride, const int* rowptr, const int* col, const float* val,
+                                long long rowptr_group_stride, long long csr_group_stride, int R, int Cin,
+                                int Cout, int G, int Bw, int relu, float* Y, void* stream) {
+  WF_REQUIRE(G > 0 && Bw > 0 && R > 0, "gcn_layer_fwd: bad batch G=%d Bw=%d R=%d", G, Bw, R);
+  GemmArgs a = {};
+  a.A = X;
+  a.am = make_rowmap(0, R, x_win_stride, x_ld, x_win_off);
+  a.gA = x_win_off ? 0 : (long long)Bw * x_win_stride;
+  a.gAmBlk = Bw;
+  a.B = W; a.ldb = Cin; a.gB = w_group_stride;
+  a.C = Y;
+  a.cm = make_rowmap(0, Bw * R, 0, Cout);
+  a.gC = (long long)Bw * R * Cout;
+  a.bias = bias; a.bias2 = nullptr; a.gBias = b_group_stride;
+  a.M = Bw * R; a.N = Cout; a.K = Cin;
+  a.relu = relu; a.accumulate = 0;
+  a.rowptr = rowptr; a.col = col; a.val = val;
+  a.gRowptr = rowptr_group_stride; a.gCsr = csr_group_stride; a.R = R;
+  return wf_launch_gemm_nt(a, G, rowptr != nullptr, (cudaStream_t)stream);
+}
+
+extern "C" size_t wf_gcn_layer_bwd_workspace_bytes(int R, int Cin, int Cout, int G, int Bw) {
+  size_t z = (size_t)G * Bw * R * Cin;                 // Z = A_hat X
+  size_t part = (size_t)64 * G * Cout * (Cin > 32 ? Cin : 32);  // split-K partials / colsum partials
+  return sizeof(float) * (z + part) + 256;
+}
+
+extern "C" int wf_gcn_layer_bwd(const float* X, int x_ld, long long x_win_stride, const long long* x_win_off,
+                                const float* Y, float* dY, const float* W, long long w_group_stride,
+                                const int* rowptr, const int* col, const float* val, const int* rowptr_t,
+                                const int* col_t, const float* val_t, long long rowptr_group_stride,
+                                long long csr_group_stride, int R, int Cin, int Cout, int G, int Bw, int relu,
+                                float* dX, float* dW, float* db, long long dw_group_stride,
+                                long long db_group_stride, void* workspace, size_t workspace_bytes, void* stream) {
+  WF_REQUIRE(G > 0 && Bw > 0 && R > 0, "gcn_layer_bwd: bad batch");
+  if (workspace_bytes < wf_gcn_layer_bwd_workspace_bytes(R, Cin, Cout, G, Bw))
+    return wf_fail(WF_EWORKSPACE, "gcn_layer_bwd: workspace too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long rows = (long long)Bw * R;
+  float* Z = (float*)workspace;
+  size_t zf = (size_t)G * Bw * R * Cin;
+  float* part = Z + zf;
+  size_t partf = (workspace_bytes - 256) / sizeof(float) - zf;
+  int rc;
+  if (relu) {
+    long long quads = (long long)G * rows * Cout / 4;
+    wf_relu_mask_kernel<<<wf_cdiv(quads, 256), 256, 0, st>>>((float4*)dY, (const float4*)Y, quads);
+    WF_CHECK_LAUNCH("relu_mask");
+  }
+  RowMap dym = make_rowmap(0, (int)rows, 0, Cout);
+  if (db) {
+    rc = wf_launch_colsum(dY, dym, rows * Cout, (int)rows, Cout, db, nullptr, db_group_stride, G, part, partf, st);
+    if (rc) return rc;
+  }
+  if (dW) {
+    RowMap xm = make_rowmap(0, R, x_win_stride, x_ld, x_win_off);
+    WF_REQUIRE(x_win_off == nullptr || G == 1, "gcn_layer_bwd: per-window offsets need G == 1");
+    rc = wf_launch_spmm(X, xm, (long long)Bw * x_win_stride, rowptr, col, val, rowptr_group_stride, csr_group_stride,
+                        R, (int)rows, Cin, Z, rows * Cin, G, st);
+    if (rc) return rc;
+    GemmArgs a = {};
+    a.A = dY; a.am = dym; a.gA = rows * Cout;
+    a.B = Z; a.bm = make_rowmap(0, (int)rows, 0, Cin); a.gB = rows * Cin;
+    a.C = dW; a.cm = make_rowmap(0, Cout, 0, Cin); a.gC = dw_group_stride;
+    a.M = Cout; a.N = Cin; a.K = (int)rows;
+    a.partial = part;
+    rc = wf_launch_gemm_tn(a, G, partf, st);
+    if (rc) return rc;
+  }
+  if (dX) {
+    GemmArgs a = {};
+    a.A = dY; a.am = make_rowmap(0, R, (long long)R * Cout, Cout); a.gA = rows * Cout;
+    a.B = W; a.bm = make_rowmap(0, Cout, 0, Cin); a.gB = w_group_stride;
+    a.C = dX; a.cm = make_rowmap(0, (int)rows, 0, Cin); a.gC = rows * Cin;
+    a.M = (int)rows; a.N = Cin; a.K = Cout;
+    a.rowptr = rowptr_t; a.col = col_t; a.val = val_t;
+    a.gRowptr = rowptr_group_stride; a.gCsr = csr_group_stride; a.R = R;
+    rc = wf_launch_gemm_nn(a, G, rowptr_t != nullptr, st);
+    if (rc) return rc;
+  }
+  return WF_OK;
+}

@@ -1,0 +1,221 @@
+"""Task-batched functional engine for the v5 hybrid model on flat device buffers.
+
+One ``HybridEngine`` owns every activation / workspace buffer for a fixed batch shape
+(G tasks x Bw windows x N nodes) and drives the C-ABI launchers of libwf_stgcn.so:
+
+    GCN stack (no grad, hybrid_model.py:60-78)  -> wf_gcn_layer_fwd x4
+    LSTM over all (task, window, node) sequences -> wf_lstm_fwd         (hybrid_model.py:93-105)
+    head + per-window MSE + backward seed        -> wf_head_fwd, wf_mse_fwd_bwd, wf_head_bwd
+    BPTT                                          -> wf_lstm_bwd        (loss.backward())
+    clip + SGD per task                           -> wf_clip_sgd_step   (train_hybrid_maml_v5.py:135-139)
+
+Nothing here allocates after construction, synchronises, or touches the host, so a whole MAML
+inner step (or meta-step) can be captured in a CUDA graph.  Weights are *flat*: the 18 tensors
+autograd reaches on the hybrid path, concatenated in state_dict order, one copy
+per task (the replacement for ``copy.deepcopy(model)`` at train_hybrid_maml_v5.py:111).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+
+import torch
+
+from . import _lib
+from .graph import RegionGraph, StackedGraphs
+
+
+@dataclass(frozen=True)
+class V5Dims:
+    """Model/config constants (train_hybrid_maml_v5.py:31-38)."""
+    num_nodes: int = 441
+    window: int = 24
+    horizon: int = 8
+    in_channels: int = 24
+    hidden: int = 256
+    lstm_hidden: int = 128
+    lstm_layers: int = 4
+    out_channels: int = 12
+    num_weather: int = 12
+
+    @property
+    def R(self):
+        return self.window * self.num_nodes
+
+    @property
+    def O(self):
+        return self.out_channels * self.horizon
+
+    @property
+    def P(self):
+        return int(_lib.query("wf_param_count", self.lstm_layers, self.hidden, self.lstm_hidden, self.O))
+
+
+def trainable_layout(dims: V5Dims):
+    """[(state_dict key, shape, offset)] of the flat trainable buffer."""
+    L, out, off = dims.lstm_hidden, [], 0
+    for l in range(dims.lstm_layers):
+        kin = dims.hidden if l == 0 else L
+        for name, shape in ((f"lstm.weight_ih_l{l}", (4 * L, kin)), (f"lstm.weight_hh_l{l}", (4 * L, L)),
+                            (f"lstm.bias_ih_l{l}", (4 * L,)), (f"lstm.bias_hh_l{l}", (4 * L,))):
+            out.append((name, shape, off))
+            off += int(torch.Size(shape).numel())
+    for name, shape in (("output_layer.weight", (dims.O, L)), ("output_layer.bias", (dims.O,))):
+        out.append((name, shape, off))
+        off += int(torch.Size(shape).numel())
+    return out
+
+
+def flatten_trainable(sd, dims: V5Dims, device=None, prefix=""):
+    parts = [sd[prefix + name].detach().reshape(-1).to(torch.float32) for name, _, _ in trainable_layout(dims)]
+    flat = torch.cat(parts)
+    return flat.to(device) if device is not None else flat
+
+
+def unflatten_trainable(flat, dims: V5Dims):
+    return {name: flat[off:off + int(torch.Size(shape).numel())].view(shape) for name, shape, off in trainable_layout(dims)}
+
+
+def gcn_weights_from_state_dict(sd, device, prefix="base_stgcn."):
+    """[(W [Cout, Cin], b [Cout])] x 4, contiguous on ``device``."""
+    return [(sd[f"{prefix}conv{i}.lin.weight"].detach().to(device, torch.float32).contiguous(),
+             sd[f"{prefix}conv{i}.bias"].detach().to(device, torch.float32).contiguous()) for i in range(1, 5)]
+
+
+class HybridEngine:
+    def __init__(self, dims: V5Dims, G: int, Bw: int, device="cuda", keep_gcn_activations=False):
+        self.dims, self.G, self.Bw = dims, int(G), int(Bw)
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError("HybridEngine needs a CUDA device; there is no CPU fallback")
+        _lib.load()
+        d = dims
+        self.rows = self.G * self.Bw * d.R
+        self.W = self.G * self.Bw
+        f32 = dict(dtype=torch.float32, device=self.device)
+        n_act = 4 if keep_gcn_activations else 2
+        self.act = [torch.empty(self.rows, d.hidden, **f32) for _ in range(n_act)]
+        self.keep_gcn = keep_gcn_activations
+        Ls, L = d.lstm_layers, d.lstm_hidden
+        self.gates = torch.empty(Ls, self.rows, 4 * L, **f32)
+        self.h = torch.empty(Ls, self.rows, L, **f32)
+        self.c = torch.empty(Ls, self.rows, L, **f32)
+        self.pred = torch.empty(self.W * d.num_nodes, d.O, **f32)
+        self.dpred = torch.empty(self.W * d.num_nodes, d.O, **f32)
+        self.loss = torch.zeros(self.W, **f32)
+        self.dlast = torch.empty(self.W * d.num_nodes, L, **f32)
+        self.P = d.P
+        self.grads = torch.zeros(self.G, self.P, **f32)
+        self.norms = torch.zeros(self.G, **f32)
+        ws = max(_lib.query("wf_lstm_bwd_workspace_bytes", Ls, d.hidden, L, d.window, d.num_nodes, self.G, self.Bw),
+                 _lib.query("wf_head_workspace_bytes", L, d.O, d.num_nodes, self.G, self.Bw),
+                 _lib.query("wf_optim_workspace_bytes", self.G))
+        self.ws_bytes = int(ws)
+        self.ws = torch.empty(self.ws_bytes, dtype=torch.uint8, device=self.device)
+        self.feats = None
+        self.launches = 0  # kernels enqueued by this engine (bench.py reports it)
+
+    # ------------------------------------------------------------------ GCN stack
+    def gcn_forward(self, X, x_ld, x_win_stride, x_win_off, gcn_weights, graphs):
+        """4 x relu(GCNConv) with dropout off; returns the [G*Bw*R, hidden] feature buffer."""
+        d, st = self.dims, _lib.stream_ptr()
+        if isinstance(graphs, RegionGraph):
+            rp, cl, vl, rps, cs = graphs.rowptr, graphs.col, graphs.val, 0, 0
+        elif isinstance(graphs, StackedGraphs):
+            rp, cl, vl, rps, cs = graphs.rowptr, graphs.col, graphs.val, graphs.rowptr_stride, graphs.csr_stride
+        else:
+            raise TypeError("graphs must be a RegionGraph or StackedGraphs")
+        if graphs.R != d.R:
+            raise ValueError(f"graph was normalised over {graphs.R} rows, engine window has {d.R}")
+        src, src_ld, src_stride, src_off, cin = X, x_ld, x_win_stride, x_win_off, d.in_channels
+        for i, (Wt, b) in enumerate(gcn_weights):
+            dst = self.act[i] if self.keep_gcn else self.act[i & 1]
+            _lib.call("wf_gcn_layer_fwd", _lib.ptr(src), src_ld, src_stride, _lib.ptr(src_off), _lib.ptr(Wt),
+                      _lib.ptr(b), 0, 0, _lib.ptr(rp), _lib.ptr(cl), _lib.ptr(vl), rps, cs, d.R, cin, d.hidden,
+                      self.G, self.Bw, 1, _lib.ptr(dst), st)
+            self.launches += 1
+            src, src_ld, src_stride, src_off, cin = dst, d.hidden, d.R * d.hidden, None, d.hidden
+        self.feats = src
+        return src
+
+    # ------------------------------------------------------------------ LSTM + head
+    def lstm_head_forward(self, params, params_stride, feats=None):
+        d, st = self.dims, _lib.stream_ptr()
+        feats = self.feats if feats is None else feats
+        _lib.call("wf_lstm_fwd", _lib.ptr(feats), _lib.ptr(params), params_stride, d.lstm_layers, d.hidden,
+                  d.lstm_hidden, d.O, d.window, d.num_nodes, self.G, self.Bw, _lib.ptr(self.gates), _lib.ptr(self.h),
+                  _lib.ptr(self.c), st)
+        _lib.call("wf_head_fwd", _lib.ptr(self.h[d.lstm_layers - 1]), _lib.ptr(params), params_stride,
+                  d.lstm_layers, d.hidden, d.lstm_hidden, d.O, d.window, d.num_nodes, self.G, self.Bw,
+                  _lib.ptr(self.pred), st)
+        self.launches += d.lstm_layers * (1 + d.window) + 1
+        return self.pred
+
+    def mse(self, y=None, feat=None, tgt_off=None, feat_ld=0, grad_scale=1.0, want_grad=True):
+        """Per-window nn.MSELoss (+ backward seed) against explicit y or in-place targets."""
+        d = self.dims
+        _lib.call("wf_mse_fwd_bwd", _lib.ptr(self.pred), _lib.ptr(y), _lib.ptr(feat), _lib.ptr(tgt_off), feat_ld,
+                  d.num_weather, d.num_nodes, d.O, self.W, float(grad_scale), _lib.ptr(self.loss),
+                  _lib.ptr(self.dpred) if want_grad else None, _lib.stream_ptr())
+        self.launches += 1
+        return self.loss
+
+    def backward(self, params, params_stride, feats=None, dpred=None):
+        """BPTT from ``dpred`` (default: the seed left by ``mse``) into ``self.grads`` [G, P]."""
+        d, st = self.dims, _lib.stream_ptr()
+        feats = self.feats if feats is None else feats
+        dpred = self.dpred if dpred is None else dpred
+        Ls = d.lstm_layers
+        _lib.call("wf_head_bwd", _lib.ptr(dpred), _lib.ptr(self.h[Ls - 1]), _lib.ptr(params), params_stride, Ls,
+                  d.hidden, d.lstm_hidden, d.O, d.window, d.num_nodes, self.G, self.Bw, _lib.ptr(self.dlast),
+                  _lib.ptr(self.grads), self.P, _lib.ptr(self.ws), self.ws_bytes, st)
+        _lib.call("wf_lstm_bwd", _lib.ptr(feats), _lib.ptr(params), params_stride, Ls, d.hidden, d.lstm_hidden, d.O,
+                  d.window, d.num_nodes, self.G, self.Bw, _lib.ptr(self.gates), _lib.ptr(self.h), _lib.ptr(self.c),
+                  _lib.ptr(self.dlast), _lib.ptr(self.grads), self.P, _lib.ptr(self.ws), self.ws_bytes, st)
+        self.launches += 6 + Ls * (d.window + 9)
+        return self.grads
+
+    def sgd_step(self, fast, lr, max_norm=1.0):
+        """fast[g] -= lr * clip(grads[g]) for every task (train_hybrid_maml_v5.py:135-139)."""
+        _lib.call("wf_clip_sgd_step", _lib.ptr(fast), self.P, _lib.ptr(self.grads), self.P, self.P, self.G, float(lr),
+                  float(max_norm), _lib.ptr(self.norms), _lib.ptr(self.ws), self.ws_bytes, _lib.stream_ptr())
+        self.launches += 2
+        return fast
+
+    # ------------------------------------------------------------------ convenience
+    def forward_backward(self, X, x_ld, x_win_stride, x_win_off, gcn_weights, graphs, params, params_stride,
+                         y=None, feat=None, tgt_off=None, feat_ld=0, grad_scale=1.0):
+        self.gcn_forward(X, x_ld, x_win_stride, x_win_off, gcn_weights, graphs)
+        self.lstm_head_forward(params, params_stride)
+        self.mse(y, feat, tgt_off, feat_ld, grad_scale)
+        self.backward(params, params_stride)
+        return self.loss, self.grads
+
+
+class AdamState:
+    """Flat Adam/AdamW state + the 8-float hyper-parameter block the kernel reads from HBM."""
+
+    def __init__(self, P, device, lr, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, decoupled=True):
+        self.P, self.device = int(P), torch.device(device)
+        self.exp_avg = torch.zeros(P, dtype=torch.float32, device=device)
+        self.exp_avg_sq = torch.zeros(P, dtype=torch.float32, device=device)
+        self.lr, self.betas, self.eps, self.weight_decay = float(lr), betas, float(eps), float(weight_decay)
+        self.decoupled, self.step_count = bool(decoupled), 0
+        # ring of pinned staging slots: the async H2D of step t must not be overwritten by the
+        # host preparing step t+1 while the stream still lags behind
+        self.hyper_host = torch.zeros(2048, 8, dtype=torch.float32).pin_memory()
+        self.hyper = torch.zeros(8, dtype=torch.float32, device=device)
+        self.norm = torch.zeros(1, dtype=torch.float32, device=device)
+        self.ws_bytes = int(_lib.query("wf_optim_workspace_bytes", 1))
+        self.ws = torch.empty(self.ws_bytes, dtype=torch.uint8, device=device)
+
+    def step(self, theta, grad, max_norm=1.0, grad_scale=1.0):
+        self.step_count += 1
+        b1, b2 = self.betas
+        slot = self.hyper_host[self.step_count % self.hyper_host.shape[0]]
+        slot.copy_(torch.tensor([self.lr, b1, b2, self.eps, self.weight_decay, 1.0 - b1 ** self.step_count,
+                                 1.0 - b2 ** self.step_count, grad_scale], dtype=torch.float32))
+        self.hyper.copy_(slot, non_blocking=True)
+        _lib.call("wf_clip_adam_step", _lib.ptr(theta), _lib.ptr(grad), _lib.ptr(self.exp_avg),
+                  _lib.ptr(self.exp_avg_sq), self.P, _lib.ptr(self.hyper), float(max_norm), int(self.decoupled),
+                  _lib.ptr(self.norm), _lib.ptr(self.ws), self.ws_bytes, _lib.stream_ptr())
+        return theta

@@ -1,0 +1,80 @@
+"""Drop-in for the reference's ``model`` module: ``GCNConv`` and ``STGCN`` (model.py:7-52).
+
+Same constructor signature, attribute names (``conv1..conv4``, ``dropout``, ``output_layer``,
+``window_size``), ``forward(x [T*N, C], edge_index [2, E]) -> [H*N, out]`` and ``state_dict``
+keys (``convN.bias``, ``convN.lin.weight``, ``output_layer.{weight,bias}``) as the reference
+class over PyG >= 2.0.  The four convolutions run on the fused CUDA GCN layer
+(functional.GCNConvReLU); the graph normalisation PyG recomputes on every call is cached per
+``edge_index`` tensor (graph.graph_for).
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+import torch.nn as nn
+
+from . import functional as WF
+from .graph import graph_for
+
+
+class _Lin(nn.Module):
+    """Bias-free linear holder -> state_dict key ``<conv>.lin.weight`` (PyG ``Linear``)."""
+
+    def __init__(self, in_channels, out_channels):
+        super().__init__()
+        self.in_channels, self.out_channels = in_channels, out_channels
+        self.weight = nn.Parameter(torch.empty(out_channels, in_channels))
+        self.reset_parameters()
+
+    def reset_parameters(self):
+        a = math.sqrt(6.0 / (self.in_channels + self.out_channels))  # PyG 'glorot'
+        with torch.no_grad():
+            self.weight.uniform_(-a, a)
+
+
+class GCNConv(nn.Module):
+    """PyG ``GCNConv(in, out)`` with its defaults (add_self_loops, normalize, bias, sum aggregation,
+    source -> target flow): ``out[i] = sum_{e: dst_e = i} w_e (x W^T)[src_e] + b``."""
+
+    def __init__(self, in_channels, out_channels):
+        super().__init__()
+        self.in_channels, self.out_channels = in_channels, out_channels
+        self.bias = nn.Parameter(torch.zeros(out_channels))  # registered before ``lin`` like PyG
+        self.lin = _Lin(in_channels, out_channels)
+
+    def reset_parameters(self):
+        self.lin.reset_parameters()
+        with torch.no_grad():
+            self.bias.zero_()
+
+    def forward(self, x, edge_index, _fuse_relu=False):
+        graph = graph_for(edge_index, x.shape[0], x.device)
+        return WF.gcn_conv(x, self.lin.weight, self.bias, graph, relu=_fuse_relu)
+
+
+class STGCN(nn.Module):
+    def __init__(self, in_channels, hidden_channels, out_channels=12, window_size=6, forecast_horizon=1,
+                 dropout_rate=0.3):
+        super().__init__()
+        self.window_size = window_size
+        self.out_channels = out_channels
+        self.forecast_horizon = forecast_horizon
+        self.dropout_rate = dropout_rate
+        self.conv1 = GCNConv(in_channels, hidden_channels)
+        self.conv2 = GCNConv(hidden_channels, hidden_channels)
+        self.conv3 = GCNConv(hidden_channels, hidden_channels)
+        self.conv4 = GCNConv(hidden_channels, hidden_channels)
+        self.dropout = nn.Dropout(p=dropout_rate)
+        self.output_layer = nn.Linear(hidden_channels, out_channels * forecast_horizon)
+
+    def forward(self, x, edge_index):
+        # conv -> relu (fused into the GEMM epilogue) -> dropout, four times (model.py:31-42)
+        for conv in (self.conv1, self.conv2, self.conv3, self.conv4):
+            x = conv(x, edge_index, _fuse_relu=True)
+            x = self.dropout(x)
+        num_nodes = x.shape[0] // self.window_size
+        x = x[-num_nodes:]  # last time slice (model.py:45-48)
+        x = self.output_layer(x)
+        x = x.view(num_nodes, self.forecast_horizon, self.out_channels)
+        return x.reshape(-1, self.out_channels)

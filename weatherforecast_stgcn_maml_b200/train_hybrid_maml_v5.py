@@ -1,0 +1,383 @@
+"""Drop-in for the hot-path functions of the reference's ``train_hybrid_maml_v5`` module.
+
+Reference surface kept (train_hybrid_maml_v5.py:21-38, 110-184):
+
+    inner_loop_v4(hybrid_model, koppen_embed, support_ds, device) -> (model, koppen)
+    meta_update_v4(hybrid_model, koppen_embed, tasks, device, meta_optimizer) -> float
+
+plus the module constants.  Underneath, tasks are processed in lock-step by one task-batched
+engine (engine.HybridEngine) instead of a Python loop per task, per window and per node.
+
+Where the reference code and its description disagree this module follows
+the code, with each quirk an explicit, defaulted switch:
+
+* D5  The reference back-propagates the query loss into the deep-copied model, so its
+  ``meta_optimizer.step()`` never changes a weight.  ``literal_reference=True`` reproduces
+  that no-op.  The default instead feeds the quantity the reference computes and discards --
+  the first-order MAML gradient d(L_query / accum)/d(theta') summed over the tasks of an
+  accumulation group -- to the outer optimiser.  (The copy's ``.grad`` additionally still holds
+  the last inner step's clipped gradient because ``zero_grad`` runs at the start of a step;
+  that stale term is not part of the meta-gradient here.  tests/test_oracle_golden.py pins
+  both readings.)
+* D8  Every loader is batch-1; "batch B" means B independent windows.
+* D4/D10  No gradient reaches ``base_stgcn`` or ``KoppenEmbedding``; their tensors are untouched.
+
+``MetaTrainer`` is the device-resident form of the same loop (features and graphs stay in HBM,
+windows are offsets, the meta-step is one CUDA graph, AdamW is the fused kernel, and with
+``torch.distributed`` initialised tasks are sharded over ranks with ONE all-reduce of the flat
+meta-gradient per meta-step).
+"""
+from __future__ import annotations
+
+import copy
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+from .dataset import unwrap_subset
+from .engine import (AdamState, HybridEngine, V5Dims, flatten_trainable, gcn_weights_from_state_dict,
+                     trainable_layout, unflatten_trainable)
+from .graph import RegionGraph, StackedGraphs
+
+# ========== MODEL 4.0 ULTRA SCALED CONFIG (train_hybrid_maml_v5.py:21-38) ==========
+SEED = 42
+NUM_EPOCHS = 40
+BATCH_SIZE = 4
+INNER_EPOCHS_PER_TASK = 6
+INNER_LR = 0.01
+OUTER_LR = 0.001
+GRAD_ACCUMULATION_STEPS = 2
+WINDOW_SIZE = 24
+FORECAST_HORIZON = 8
+HIDDEN_CHANNELS = 256
+LSTM_HIDDEN_SIZE = 128
+LSTM_NUM_LAYERS = 4
+INPUT_CHANNELS = 12 + 4 + 8
+OUTPUT_CHANNELS = 12
+INNER_BATCHES_PER_EPOCH = 15  # the ``batch_idx >= 15: break`` at train_hybrid_maml_v5.py:126
+
+
+def reference_support_schedule(indices, epochs=None, per_epoch=INNER_BATCHES_PER_EPOCH):
+    """Window order of inner_loop_v4: ``epochs`` passes over the first ``per_epoch`` support windows."""
+    epochs = INNER_EPOCHS_PER_TASK if epochs is None else epochs
+    return list(indices[:per_epoch]) * epochs
+
+
+# ------------------------------------------------------------------------------------------
+class HostTaskStager:
+    """Stages the windows a meta-step reads from (pinned) host features into HBM.
+
+    For every task only the time rows its support/query windows touch are uploaded, as at most
+    a few contiguous ``features[a:b]`` slices per step (the reference copies each sample with
+    ``batch.to(device)`` every step, train_hybrid_maml_v5.py:129,164).
+    """
+
+    def __init__(self, task_windows, dims: V5Dims, device):
+        # task_windows: [(features [time, N, C] host tensor, [window start rows ...])]
+        self.dims, self.device = dims, torch.device(device)
+        d = dims
+        self.per_step = d.num_nodes * d.in_channels
+        span = d.window + 1 + d.horizon
+        self.plans, rows_max = [], 0
+        for feats, starts in task_windows:
+            if feats.shape[1] != d.num_nodes or feats.shape[2] != d.in_channels:
+                raise ValueError(f"features {tuple(feats.shape)} do not match N={d.num_nodes}, C={d.in_channels}")
+            ivs = []
+            for s in sorted(set(int(s) for s in starts)):
+                if s < 0 or s + span > feats.shape[0]:
+                    raise IndexError(f"window starting at row {s} leaves the features tensor ({feats.shape[0]} rows)")
+                if ivs and s <= ivs[-1][1]:
+                    ivs[-1][1] = max(ivs[-1][1], s + span)
+                else:
+                    ivs.append([s, s + span])
+            pos, cmap = 0, []
+            for a, b in ivs:
+                cmap.append((a, b, pos))
+                pos += b - a
+            rows_max = max(rows_max, pos)
+            host = feats if feats.is_pinned() else feats.contiguous().pin_memory()
+            self.plans.append((host, cmap))
+        self.G, self.rows = len(self.plans), rows_max
+        self.buf = torch.empty(self.G, rows_max, d.num_nodes, d.in_channels, dtype=torch.float32, device=self.device)
+        self.h2d_bytes = sum((b - a) * self.per_step * 4 for _, cmap in self.plans for a, b, _ in cmap)
+
+    def upload(self):
+        for g, (host, cmap) in enumerate(self.plans):
+            for a, b, pos in cmap:
+                self.buf[g, pos:pos + (b - a)].copy_(host[a:b], non_blocking=True)
+        return self.buf
+
+    def offsets(self, g, start):
+        """(x offset, target offset) in elements into ``buf`` for the window of task g starting at row ``start``."""
+        for a, b, pos in self.plans[g][1]:
+            if a <= start < b:
+                row = g * self.rows + pos + (start - a)
+                return row * self.per_step, (row + self.dims.window + 1) * self.per_step
+        raise KeyError(start)
+
+
+def _task_graph(dataset, dims, device):
+    g = getattr(dataset, "_wf_graph", None)
+    if g is None or g.R != dims.R or g.device != torch.device(device):
+        g = RegionGraph(dataset.edge_index, dims.R, device)
+        try:
+            dataset._wf_graph = g
+        except AttributeError:
+            pass
+    return g
+
+
+def _model_dims(hybrid_model, num_nodes):
+    return hybrid_model.dims(num_nodes)
+
+
+class _GroupRunner:
+    """Inner loops + query pass of one accumulation group of tasks, in lock-step."""
+
+    def __init__(self, dims, G, device):
+        self.engine = HybridEngine(dims, G, 1, device)
+        self.dims, self.G, self.device = dims, G, torch.device(device)
+        self.fast = torch.empty(G, self.engine.P, dtype=torch.float32, device=device)
+
+    def run(self, theta, gcn_w, graphs, buf, sup_x, sup_t, qry_x, qry_t, inner_lr, accum, max_norm=1.0):
+        """sup_x/sup_t: i64 [steps, G] offset tables; qry_x/qry_t: i64 [G].  Leaves the per-task query
+        gradients in engine.grads, the adapted weights in self.fast, returns sum(query loss)/accum."""
+        e, d = self.engine, self.dims
+        self.fast.copy_(theta.unsqueeze(0).expand(self.G, -1))
+        for s in range(sup_x.shape[0]):
+            e.forward_backward(buf, d.in_channels, 0, sup_x[s], gcn_w, graphs, self.fast, e.P,
+                               feat=buf, tgt_off=sup_t[s], feat_ld=d.in_channels, grad_scale=1.0)
+            e.sgd_step(self.fast, inner_lr, max_norm)
+        e.forward_backward(buf, d.in_channels, 0, qry_x, gcn_w, graphs, self.fast, e.P,
+                           feat=buf, tgt_off=qry_t, feat_ld=d.in_channels, grad_scale=1.0 / accum)
+        return e.loss.sum() / accum
+
+
+_RUNNERS = {}
+
+
+def _runner(dims, G, device):
+    key = (dims, G, str(torch.device(device)))
+    if key not in _RUNNERS:
+        if len(_RUNNERS) > 4:
+            _RUNNERS.clear()
+        _RUNNERS[key] = _GroupRunner(dims, G, device)
+    return _RUNNERS[key]
+
+
+def _stage_group(group, dims, device, support_steps_fn, query_pick):
+    """group: [(support_ds, query_ds)] -> stager, graphs, offset tables."""
+    task_windows, graphs, sup_rows, qry_rows = [], [], [], []
+    for support_ds, query_ds in group:
+        sds, sidx = unwrap_subset(support_ds)
+        qds, qidx = unwrap_subset(query_ds)
+        if sds is not qds and sds.features is not qds.features:
+            raise ValueError("support and query sets of a task must share one features tensor")
+        steps = support_steps_fn(sidx)
+        srows = [sds.valid_indices[i] - sds.window_size for i in steps]
+        qrow = qds.valid_indices[query_pick(qidx)] - qds.window_size
+        task_windows.append((sds.features, srows + [qrow]))
+        graphs.append(_task_graph(sds, dims, device))
+        sup_rows.append(srows)
+        qry_rows.append(qrow)
+    n_steps = len(sup_rows[0])
+    if any(len(r) != n_steps for r in sup_rows):
+        raise ValueError("tasks of one accumulation group must take the same number of inner steps")
+    stager = HostTaskStager(task_windows, dims, device)
+    G = len(group)
+    sup_x = torch.empty(n_steps, G, dtype=torch.long)
+    sup_t = torch.empty(n_steps, G, dtype=torch.long)
+    qry_x = torch.empty(G, dtype=torch.long)
+    qry_t = torch.empty(G, dtype=torch.long)
+    for g in range(G):
+        for s, row in enumerate(sup_rows[g]):
+            sup_x[s, g], sup_t[s, g] = stager.offsets(g, row)
+        qry_x[g], qry_t[g] = stager.offsets(g, qry_rows[g])
+    dev = torch.device(device)
+    return stager, StackedGraphs(graphs), sup_x.to(dev), sup_t.to(dev), qry_x.to(dev), qry_t.to(dev)
+
+
+def _load_flat_into(model, flat, dims):
+    named = dict(model.named_parameters())
+    with torch.no_grad():
+        for name, t in unflatten_trainable(flat, dims).items():
+            named[name].copy_(t)
+
+
+# ------------------------------------------------------------------------------------------
+def inner_loop_v4(hybrid_model, koppen_embed, support_ds, device):
+    """train_hybrid_maml_v5.py:110-141 -- adapt a copy of the model on the support set.
+
+    INNER_EPOCHS_PER_TASK passes over the first 15 support windows, each step: forward, MSE,
+    backward, clip_grad_norm_(1.0), SGD(lr=INNER_LR).  Returns ``(temp_model, temp_koppen)``
+    (deep copies in train mode, like the reference)."""
+    sds, _ = unwrap_subset(support_ds)
+    dims = _model_dims(hybrid_model, sds.num_nodes)
+    sd = {k: v.detach() for k, v in hybrid_model.state_dict().items()}
+    stager, graphs, sup_x, sup_t, qry_x, qry_t = _stage_group(
+        [(support_ds, support_ds)], dims, device, reference_support_schedule, lambda q: q[0])
+    run = _runner(dims, 1, device)
+    theta = flatten_trainable(sd, dims, device)
+    gcn_w = gcn_weights_from_state_dict(sd, device)
+    buf = stager.upload()
+    e = run.engine
+    run.fast.copy_(theta.unsqueeze(0))
+    for s in range(sup_x.shape[0]):
+        e.forward_backward(buf, dims.in_channels, 0, sup_x[s], gcn_w, graphs, run.fast, e.P,
+                           feat=buf, tgt_off=sup_t[s], feat_ld=dims.in_channels, grad_scale=1.0)
+        e.sgd_step(run.fast, INNER_LR, 1.0)
+    temp_model = copy.deepcopy(hybrid_model)
+    temp_koppen = copy.deepcopy(koppen_embed)
+    _load_flat_into(temp_model, run.fast[0], dims)
+    temp_model.train()
+    temp_koppen.train()
+    return temp_model, temp_koppen
+
+
+def meta_update_v4(hybrid_model, koppen_embed, tasks, device, meta_optimizer, literal_reference=False,
+                   grad_accumulation_steps=None, support_schedule=None):
+    """train_hybrid_maml_v5.py:144-184 -- one meta-update over ``tasks``.
+
+    ``tasks`` is the reference's list of ``(support_ds, query_ds, stats)``.  Tasks are processed
+    in accumulation groups of GRAD_ACCUMULATION_STEPS (an optimiser step after each group, as
+    at :173-179); inside a group all tasks run in lock-step on one batched engine.  Returns the
+    reference's ``meta_loss`` (sum of query_loss / GRAD_ACCUMULATION_STEPS)."""
+    accum = GRAD_ACCUMULATION_STEPS if grad_accumulation_steps is None else int(grad_accumulation_steps)
+    schedule = reference_support_schedule if support_schedule is None else support_schedule
+    tasks = [t for t in tasks if t[0] is not None]
+    meta_loss = 0.0
+    meta_optimizer.zero_grad()
+    named = dict(hybrid_model.named_parameters())
+    all_params = list(hybrid_model.parameters()) + list(koppen_embed.parameters())
+    for start in range(0, len(tasks), accum):
+        group = tasks[start:start + accum]
+        sds, _ = unwrap_subset(group[0][0])
+        dims = _model_dims(hybrid_model, sds.num_nodes)
+        sd = {k: v.detach() for k, v in hybrid_model.state_dict().items()}
+        stager, graphs, sup_x, sup_t, qry_x, qry_t = _stage_group(
+            [(s, q) for s, q, *_ in group], dims, device, schedule, lambda q: q[0])
+        run = _runner(dims, len(group), device)
+        theta = flatten_trainable(sd, dims, device)
+        gcn_w = gcn_weights_from_state_dict(sd, device)
+        buf = stager.upload()
+        loss = run.run(theta, gcn_w, graphs, buf, sup_x, sup_t, qry_x, qry_t, INNER_LR, accum)
+        if not literal_reference:
+            meta_grad = run.engine.grads.sum(dim=0)
+            for name, g in unflatten_trainable(meta_grad, dims).items():
+                p = named[name]
+                p.grad = g.clone() if p.grad is None else p.grad + g
+        meta_loss += float(loss)  # the reference's .item() sync (train_hybrid_maml_v5.py:170)
+        torch.nn.utils.clip_grad_norm_(all_params, max_norm=1.0)
+        meta_optimizer.step()
+        meta_optimizer.zero_grad()
+    return meta_loss
+
+
+# ------------------------------------------------------------------------------------------
+class MetaTrainer:
+    """Device-resident, task-sharded FOMAML meta-training of the v5 hybrid model.
+
+    tasks: list of ``(features [time, N, C], edge_index [2, E])`` owned by THIS rank.
+    One ``meta_step()`` = every local task runs ``support_rows`` inner SGD steps and one query
+    pass (one CUDA graph), the per-task query gradients are summed, all-reduced over ranks (one
+    collective, if torch.distributed is initialised) and applied by the fused clip+AdamW kernel.
+    ``accum`` is the divisor of the query loss (default: global task count, i.e. the reference
+    with GRAD_ACCUMULATION_STEPS = number of tasks).
+    """
+
+    def __init__(self, state_dict, tasks, dims: V5Dims, device="cuda", support_rows=(0, 1, 2), query_row=None,
+                 inner_lr=INNER_LR, outer_lr=OUTER_LR, weight_decay=1e-4, accum=None, use_cuda_graph=True,
+                 process_group=None, distributed=None):
+        import torch.distributed as dist
+
+        self.dims, self.device = dims, torch.device(device)
+        self.dist = dist if (distributed if distributed is not None else dist.is_initialized()) else None
+        self.pg = process_group
+        self.world = self.dist.get_world_size(self.pg) if self.dist else 1
+        self.G = len(tasks)
+        d = dims
+        feats = [f for f, _ in tasks]
+        time_rows = feats[0].shape[0]
+        if any(tuple(f.shape) != (time_rows, d.num_nodes, d.in_channels) for f in feats):
+            raise ValueError("all tasks of a rank must share the features shape [time, N, C]")
+        self.features = torch.stack([f.to(self.device, torch.float32) for f in feats]).contiguous()
+        self.graphs = StackedGraphs([RegionGraph(ei, d.R, self.device) for _, ei in tasks])
+        span = d.window + 1 + d.horizon
+        if query_row is None:
+            query_row = int(0.75 * min(600, time_rows - d.window - d.horizon))  # first query window (:95-102)
+        rows = list(support_rows) + [query_row]
+        if max(rows) + span > time_rows:
+            raise IndexError("support/query window leaves the features tensor")
+        per_step, per_task = d.num_nodes * d.in_channels, time_rows * d.num_nodes * d.in_channels
+        base = torch.arange(self.G, dtype=torch.long) * per_task
+        r = torch.tensor(rows, dtype=torch.long)
+        self.x_off = (base[None, :] + r[:, None] * per_step).to(self.device)             # [steps+1, G]
+        self.t_off = (base[None, :] + (r[:, None] + d.window + 1) * per_step).to(self.device)
+        self.n_inner = len(support_rows)
+        self.inner_lr, self.accum = float(inner_lr), float(accum if accum is not None else self.G * self.world)
+        self.sd = {k: v.detach().clone() for k, v in state_dict.items()}
+        self.theta = flatten_trainable(self.sd, d, self.device)
+        self.gcn_w = gcn_weights_from_state_dict(self.sd, self.device)
+        self.engine = HybridEngine(d, self.G, 1, self.device)
+        self.P = self.engine.P
+        self.fast = torch.empty(self.G, self.P, dtype=torch.float32, device=self.device)
+        self.meta = torch.zeros(self.P + 4, dtype=torch.float32, device=self.device)  # grad + packed loss
+        self.adam = AdamState(self.P, self.device, outer_lr, weight_decay=weight_decay, decoupled=True)
+        self.use_graph, self.graph = bool(use_cuda_graph), None
+        self.launches_per_step = None
+
+    # the captured region: no host interaction, fixed pointers
+    def _body(self):
+        e, d = self.engine, self.dims
+        C = d.in_channels
+        self.fast.copy_(self.theta.unsqueeze(0).expand(self.G, -1))
+        for s in range(self.n_inner):
+            e.forward_backward(self.features, C, 0, self.x_off[s], self.gcn_w, self.graphs, self.fast, self.P,
+                               feat=self.features, tgt_off=self.t_off[s], feat_ld=C, grad_scale=1.0)
+            e.sgd_step(self.fast, self.inner_lr, 1.0)
+        q = self.n_inner
+        e.forward_backward(self.features, C, 0, self.x_off[q], self.gcn_w, self.graphs, self.fast, self.P,
+                           feat=self.features, tgt_off=self.t_off[q], feat_ld=C, grad_scale=1.0 / self.accum)
+        _lib.call("wf_sum_groups", _lib.ptr(e.grads), self.P, self.G, self.P, _lib.ptr(self.meta), 0,
+                  _lib.stream_ptr())
+        e.launches += 1
+        self.meta[self.P:self.P + 1].copy_((e.loss.sum() / self.accum).reshape(1))
+
+    def meta_step(self):
+        """Enqueue one meta-step; returns the (device) meta-loss tensor without synchronising."""
+        if self.use_graph:
+            if self.graph is None:
+                before = self.engine.launches
+                side = torch.cuda.Stream(self.device)
+                side.wait_stream(torch.cuda.current_stream(self.device))
+                with torch.cuda.stream(side):
+                    self._body()  # warm-up: module load + autotune-free, outside capture
+                torch.cuda.current_stream(self.device).wait_stream(side)
+                torch.cuda.synchronize(self.device)
+                self.launches_per_step = self.engine.launches - before
+                self.graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(self.graph):
+                    self._body()
+            self.graph.replay()
+        else:
+            before = self.engine.launches
+            self._body()
+            self.launches_per_step = self.engine.launches - before
+        if self.dist is not None and self.world > 1:
+            self.dist.all_reduce(self.meta, op=self.dist.ReduceOp.SUM, group=self.pg)
+        self.adam.step(self.theta, self.meta, max_norm=1.0)
+        return self.meta[self.P]
+
+    def set_lr(self, lr):
+        self.adam.lr = float(lr)
+
+    def meta_gradient(self):
+        return self.meta[:self.P]
+
+    def state_dict(self):
+        """Hybrid ``state_dict`` with the current meta-parameters (CPU tensors)."""
+        out = {k: v.clone() for k, v in self.sd.items()}
+        for name, t in unflatten_trainable(self.theta.detach().cpu(), self.dims).items():
+            out[name] = t.clone()
+        return out
