@@ -96,7 +96,7 @@ class HostTaskStager:
                 cmap.append((a, b, pos))
                 pos += b - a
             rows_max = max(rows_max, pos)
-            host = feats if feats.is_pinned() else feats.contiguous().pin_memory()
+            host = feats if (feats.is_cuda or feats.is_pinned()) else feats.contiguous().pin_memory()
             self.plans.append((host, cmap))
         self.G, self.rows = len(self.plans), rows_max
         self.buf = torch.empty(self.G, rows_max, d.num_nodes, d.in_channels, dtype=torch.float32, device=self.device)
@@ -126,6 +126,21 @@ def _task_graph(dataset, dims, device):
         except AttributeError:
             pass
     return g
+
+
+def _pinned_features(dataset):
+    """Page-locked view of a dataset's host features, made once per dataset (async H2D needs it)."""
+    f = dataset.features
+    if f.is_cuda or f.is_pinned():
+        return f
+    p = getattr(dataset, "_wf_pinned", None)
+    if p is None or p[0] is not f:
+        p = (f, f.contiguous().pin_memory())
+        try:
+            dataset._wf_pinned = p
+        except AttributeError:
+            pass
+    return p[1]
 
 
 def _model_dims(hybrid_model, num_nodes):
@@ -177,7 +192,7 @@ def _stage_group(group, dims, device, support_steps_fn, query_pick):
         steps = support_steps_fn(sidx)
         srows = [sds.valid_indices[i] - sds.window_size for i in steps]
         qrow = qds.valid_indices[query_pick(qidx)] - qds.window_size
-        task_windows.append((sds.features, srows + [qrow]))
+        task_windows.append((_pinned_features(sds), srows + [qrow]))
         graphs.append(_task_graph(sds, dims, device))
         sup_rows.append(srows)
         qry_rows.append(qrow)
@@ -288,7 +303,7 @@ class MetaTrainer:
 
     def __init__(self, state_dict, tasks, dims: V5Dims, device="cuda", support_rows=(0, 1, 2), query_row=None,
                  inner_lr=INNER_LR, outer_lr=OUTER_LR, weight_decay=1e-4, accum=None, use_cuda_graph=True,
-                 process_group=None, distributed=None):
+                 process_group=None, distributed=None, host_staging=False):
         import torch.distributed as dist
 
         self.dims, self.device = dims, torch.device(device)
@@ -301,7 +316,6 @@ class MetaTrainer:
         time_rows = feats[0].shape[0]
         if any(tuple(f.shape) != (time_rows, d.num_nodes, d.in_channels) for f in feats):
             raise ValueError("all tasks of a rank must share the features shape [time, N, C]")
-        self.features = torch.stack([f.to(self.device, torch.float32) for f in feats]).contiguous()
         self.graphs = StackedGraphs([RegionGraph(ei, d.R, self.device) for _, ei in tasks])
         span = d.window + 1 + d.horizon
         if query_row is None:
@@ -309,11 +323,22 @@ class MetaTrainer:
         rows = list(support_rows) + [query_row]
         if max(rows) + span > time_rows:
             raise IndexError("support/query window leaves the features tensor")
-        per_step, per_task = d.num_nodes * d.in_channels, time_rows * d.num_nodes * d.in_channels
-        base = torch.arange(self.G, dtype=torch.long) * per_task
-        r = torch.tensor(rows, dtype=torch.long)
-        self.x_off = (base[None, :] + r[:, None] * per_step).to(self.device)             # [steps+1, G]
-        self.t_off = (base[None, :] + (r[:, None] + d.window + 1) * per_step).to(self.device)
+        self.stager = None
+        if host_staging:
+            # features stay in (pinned) host memory; each meta-step uploads only the time rows its
+            # windows read -- the reference's per-sample batch.to(device) (train_hybrid_maml_v5.py:129,164)
+            self.stager = HostTaskStager([(f, rows) for f in feats], d, self.device)
+            self.features = self.stager.buf
+            off = [[self.stager.offsets(g, r) for g in range(self.G)] for r in rows]
+            self.x_off = torch.tensor([[o[0] for o in row] for row in off], dtype=torch.long, device=self.device)
+            self.t_off = torch.tensor([[o[1] for o in row] for row in off], dtype=torch.long, device=self.device)
+        else:
+            self.features = torch.stack([f.to(self.device, torch.float32) for f in feats]).contiguous()
+            per_step, per_task = d.num_nodes * d.in_channels, time_rows * d.num_nodes * d.in_channels
+            base = torch.arange(self.G, dtype=torch.long) * per_task
+            r = torch.tensor(rows, dtype=torch.long)
+            self.x_off = (base[None, :] + r[:, None] * per_step).to(self.device)             # [steps+1, G]
+            self.t_off = (base[None, :] + (r[:, None] + d.window + 1) * per_step).to(self.device)
         self.n_inner = len(support_rows)
         self.inner_lr, self.accum = float(inner_lr), float(accum if accum is not None else self.G * self.world)
         self.sd = {k: v.detach().clone() for k, v in state_dict.items()}
@@ -346,6 +371,8 @@ class MetaTrainer:
 
     def meta_step(self):
         """Enqueue one meta-step; returns the (device) meta-loss tensor without synchronising."""
+        if self.stager is not None:
+            self.stager.upload()
         if self.use_graph:
             if self.graph is None:
                 before = self.engine.launches
