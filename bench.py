@@ -1,0 +1,388 @@
+#!/usr/bin/env python
+"""Benchmark of the v5 hot path: MAML meta-steps/s (BASELINE.json metric, configs[1]).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+Workload: per GPU 15 synthetic 21x21 region tasks (441 nodes, k = 8 kNN,
+600 windows each), one meta-step = every task runs 3 inner SGD steps on support windows 0, 1, 2
+plus the first query window (60 window forward+backward passes, 45 clip+SGD steps), the query
+gradients are summed (one NCCL all-reduce when N > 1) and applied by one clip+AdamW step.
+Scaling is weak: 15 tasks per GPU, so `value` counts 15-task meta-steps per second over the job.
+
+One JSON line on stdout (rank 0); see the contract in the task statement.  `value`: features
+resident in HBM, CUDA-graphed meta-step, device-timed.  `e2e`: same loop with the features in
+pinned HOST memory -- every step uploads the rows its windows read and reads the loss back.
+`roofline`: the dominant kernel family of an instrumented (un-graphed) step, algorithmic bytes
+per launch / its CUDA-event time.  `cpu_baseline` / `--impl reference`: the oracle port with the
+reference's execution shape (per-node nn.LSTM loop) on the host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+TASKS_PER_GPU = 15
+NLAT = NLON = 21
+KNN = 8
+WINDOWS = 600
+SUPPORT_ROWS = (0, 1, 2)
+METRIC = "maml_meta_steps_per_sec"
+UNIT = "meta-steps/s"
+
+
+def workload_config(n_gpus):
+    return {
+        "workload": "config[1]: MAML meta-train step, 15 synthetic region tasks/GPU (441 nodes, k=8, ~600 windows, "
+                    "75/25 support/query), 3 inner SGD steps + 1 query pass per task, outer AdamW",
+        "tasks_per_gpu": TASKS_PER_GPU, "global_tasks": TASKS_PER_GPU * n_gpus, "nodes": NLAT * NLON, "k": KNN,
+        "window": 24, "horizon": 8, "inner_steps": len(SUPPORT_ROWS), "window_passes_per_meta_step": 60 * n_gpus,
+        "parallelism": f"task-sharded dp{n_gpus}, 1 all-reduce of 2.43 MB per meta-step" if n_gpus > 1 else "single GPU",
+        "l2_policy": "working set per step (~4 GB of activations) exceeds the 126 MB L2; no explicit flush",
+        "dropout": "off (parity configuration, SURVEY.md D11)",
+    }
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# ----------------------------------------------------------------------------- CPU reference arm
+def cpu_window_pass_seconds(steps, warmup, literal=True):
+    """Time forward + MSE + backward + clip + SGD of ONE window with the oracle port on the host.
+
+    literal=True reproduces the reference's execution shape: one nn.LSTM call per node
+    (hybrid_model.py:93-105).  Returns (median seconds per window pass, cores used)."""
+    import torch
+
+    from oracle import ref_port as P
+    from weatherforecast_stgcn_maml_b200 import synth
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    lats, lons, feats, _ = synth.synth_task(0, num_windows=8, nlat=NLAT, nlon=NLON)
+    ei = P.knn_edges_ckdtree(lats, lons, KNN)
+    sd = synth.init_v5_state_dict(42)
+    times = []
+    if literal:
+        fwd, params = P.build_reference_like_module(sd, 24, 8, 4)
+        opt = torch.optim.SGD(params, lr=0.01)
+    for it in range(warmup + steps):
+        x, y = P.window_xy(feats, it % 4, 24, 8)
+        t0 = time.perf_counter()
+        if literal:
+            opt.zero_grad()
+            loss = torch.nn.functional.mse_loss(fwd(x, ei), y)
+            loss.backward()
+            torch.nn.utils.clip_grad_norm_(params, 1.0)
+            opt.step()
+        else:
+            _, grads, _ = P.loss_and_grads(sd, x, y, ei, 24, 8, 1.0, 4)
+            P.clip_grad_norm([g.clone() for g in grads.values()], 1.0)
+        dt = time.perf_counter() - t0
+        if it >= warmup:
+            times.append(dt)
+    return statistics.median(times), cores
+
+
+def run_reference(args, rank):
+    """--impl reference: the reference's CPU path (oracle port, per-node LSTM loop) on the host cores.
+    A step is a bounded sample of the workload -- one window pass; a meta-step is 60 of them, strictly
+    serial in the reference (train_hybrid_maml_v5.py:124-127,151), so throughput extrapolates linearly."""
+    if rank != 0:
+        return
+    sec, cores = cpu_window_pass_seconds(args.steps, args.warmup, literal=True)
+    passes = 60 * args.gpus
+    value = args.gpus / (sec * passes)  # 15-task meta-steps per second for the whole (N x 15)-task job
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(args.gpus),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": "one window forward+MSE+backward+clip+SGD per step with the reference's per-node "
+                                   "nn.LSTM loop; meta-step = 60 serial passes per 15 tasks (extrapolated)"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx, self.proc = str(gpu_index), None
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=self.f, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.f.read().splitlines():
+            c = [x.strip() for x in ln.split(",")]
+            if len(c) < 8 or c[0] != self.idx:
+                continue
+            try:
+                sm.append(float(c[1]))
+                mx.append(float(c[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, c[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        os.unlink(self.f.name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ----------------------------------------------------------------------------- GPU arm
+def build_tasks(rank, world):
+    import torch  # noqa: F401
+
+    from weatherforecast_stgcn_maml_b200 import synth
+    from weatherforecast_stgcn_maml_b200.dist import shard_tasks
+    from weatherforecast_stgcn_maml_b200.graphBuilder import knn_edge_index_device
+
+    tasks = []
+    for t in shard_tasks(TASKS_PER_GPU * world, rank, world):
+        lats, lons, feats, _ = synth.synth_task(t, num_windows=WINDOWS, nlat=NLAT, nlon=NLON)
+        ei = knn_edge_index_device(lats, lons, KNN, "cuda")
+        tasks.append((feats, ei))
+    return tasks
+
+
+def timed_steps(trainer, steps, warmup, world, sync_loss):
+    """W untimed + K timed meta-steps; barrier + synchronize on both sides; device time, max over ranks."""
+    import torch
+    import torch.distributed as dist
+
+    for _ in range(warmup):
+        loss = trainer.meta_step()
+        if sync_loss:
+            loss.item()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    last = None
+    for _ in range(steps):
+        loss = trainer.meta_step()
+        if sync_loss:
+            last = loss.item()  # the step's result read back to the host (reference: .item() at :170)
+    e1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item()), (last if sync_loss else float(loss.item()))
+
+
+def stage_breakdown(trainer, reps=3):
+    """Un-graphed instrumented meta-steps: CUDA-event time of every launcher family."""
+    import torch
+
+    from weatherforecast_stgcn_maml_b200 import _lib
+
+    acc, counts = {}, {}
+    orig = _lib.call
+
+    def timed_call(name, *a):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        orig(name, *a)
+        e1.record()
+        acc.setdefault(name, []).append((e0, e1))
+
+    was = trainer.use_graph
+    trainer.use_graph = False
+    for mod in (sys.modules["weatherforecast_stgcn_maml_b200.engine"],
+                sys.modules["weatherforecast_stgcn_maml_b200.train_hybrid_maml_v5"]):
+        mod._lib.call = timed_call
+    try:
+        for _ in range(reps):
+            trainer.meta_step()
+        torch.cuda.synchronize()
+    finally:
+        _lib.call = orig
+        trainer.use_graph = was
+    out = {}
+    for name, evs in acc.items():
+        out[name] = {"ms_per_meta_step": sum(a.elapsed_time(b) for a, b in evs) / reps, "calls": len(evs) // reps}
+    return out
+
+
+def roofline_from_stages(stages, G, peak, peak_src):
+    """Algorithmic traffic of each launcher family per call (SURVEY.md 8d figures)."""
+    N, T, F, L, C = NLAT * NLON, 24, 256, 128, 24
+    R = T * N
+    E = N * KNN + R
+    csr = E * 8 + (R + 1) * 4
+    # GCN layer call (the 256->256 layers dominate): read X, write Y, W, bias, CSR -- per window x G windows
+    gcn_bytes = G * (R * (F + F) * 4 + csr) + F * F * 4
+    gcn1_bytes = G * (R * (C + F) * 4 + csr) + F * C * 4
+    gcn_avg = (gcn1_bytes + 3 * gcn_bytes) / 4
+    # LSTM forward call: all 4 layers; per layer read input, write+read x-projection, write gates, h, c
+    lstm_f = 0
+    for l in range(4):
+        kin = F if l == 0 else L
+        lstm_f += G * R * (kin + 4 * L + 4 * L + 4 * L + 3 * L + L) * 4 + G * (4 * L * (kin + L) + 8 * L) * 4
+    # BPTT call: per layer read gates, c, c_prev; write dG; read dG (next step GEMM) ; weight-grad GEMMs read dG, X, H
+    lstm_b = 0
+    for l in range(4):
+        kin = F if l == 0 else L
+        lstm_b += G * R * (4 * L + 2 * L + 4 * L + 4 * L + L) * 4 + G * R * (2 * 4 * L + kin + L + 4 * L + kin) * 4
+    table = {"wf_gcn_layer_fwd": gcn_avg, "wf_lstm_fwd": lstm_f, "wf_lstm_bwd": lstm_b}
+    best = max((k for k in stages if k in table), key=lambda k: stages[k]["ms_per_meta_step"])
+    st = stages[best]
+    per_call_ms = st["ms_per_meta_step"] / st["calls"]
+    achieved = table[best] / (per_call_ms * 1e-3) / 1e9
+    return {"bound": "hbm", "kernel": best, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+            "traffic": None, "peak_source": peak_src, "ms_per_call": per_call_ms, "algorithmic_bytes_per_call": table[best],
+            "graph_conv_GBps": gcn_avg / (stages["wf_gcn_layer_fwd"]["ms_per_meta_step"] / stages["wf_gcn_layer_fwd"]["calls"] * 1e-3) / 1e9,
+            "graph_conv_frac": gcn_avg / (stages["wf_gcn_layer_fwd"]["ms_per_meta_step"] / stages["wf_gcn_layer_fwd"]["calls"] * 1e-3) / 1e9 / peak}
+
+
+def run_gpu(args, rank, local, world):
+    import torch
+
+    import __graft_entry__ as entry
+
+    if rank == 0:
+        entry.build()
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.barrier()
+    from weatherforecast_stgcn_maml_b200 import _lib, synth
+    from weatherforecast_stgcn_maml_b200.engine import V5Dims
+    from weatherforecast_stgcn_maml_b200.train_hybrid_maml_v5 import MetaTrainer
+
+    _lib.load()
+    torch.cuda.set_device(local)
+    dims = V5Dims(num_nodes=NLAT * NLON)
+    sd = synth.init_v5_state_dict(42)
+    tasks = build_tasks(rank, world)
+    kw = dict(support_rows=SUPPORT_ROWS, accum=TASKS_PER_GPU * world)
+
+    # ---- headline: device-resident, CUDA-graphed
+    tr = MetaTrainer(sd, tasks, dims, "cuda", use_cuda_graph=True, **kw)
+    tr.meta_step()  # capture
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    ms, loss = timed_steps(tr, args.steps, args.warmup, world, sync_loss=False)
+    clocks = sampler.stop() if sampler else None
+    launches_per_step = tr.launches_per_step + 2  # + sumsq + AdamW kernels outside the graph
+    stages = stage_breakdown(tr) if rank == 0 else None
+    del tr
+    torch.cuda.empty_cache()
+
+    # ---- e2e: features in pinned host memory, upload per step, loss read back per step
+    tr2 = MetaTrainer(sd, tasks, dims, "cuda", use_cuda_graph=True, host_staging=True, **kw)
+    tr2.meta_step()
+    ms2, loss2 = timed_steps(tr2, args.steps, args.warmup, world, sync_loss=True)
+    h2d = tr2.stager.h2d_bytes + 32  # + the AdamW hyper-parameter block
+    del tr2
+
+    if rank != 0:
+        return
+    sec_step = ms * 1e-3 / args.steps
+    value = world / sec_step
+    peak, peak_src = peaks()
+    roof = roofline_from_stages(stages, TASKS_PER_GPU, peak, peak_src)
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": sec_step * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic", "config": workload_config(world),
+        "windows_per_sec": 60 * world / sec_step, "meta_loss": loss, "clocks": clocks,
+        "e2e": {"value": world / (ms2 * 1e-3 / args.steps), "unit": UNIT, "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": 4, "ms_per_step": ms2 / args.steps, "meta_loss": loss2},
+        "gpu_launches": launches_per_step * args.steps,
+        "gpu_launches_per_step": launches_per_step,
+        "roofline": roof,
+        "stages_ms_per_meta_step": {k: round(v["ms_per_meta_step"], 4) for k, v in stages.items()},
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        sec, cores = cpu_window_pass_seconds(3, 1, literal=True)
+        sec_b, _ = cpu_window_pass_seconds(3, 1, literal=False)
+        line["cpu_baseline"] = {
+            "value": 1.0 / (60 * sec), "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": "3 timed window passes (forward+MSE+backward+clip+SGD, reference per-node nn.LSTM loop); "
+                      "meta-step = 60 serial passes (extrapolated, tasks/windows are serial in the reference)",
+            "sec_per_window_pass": sec, "batched_port_sec_per_window_pass": sec_b}
+    else:
+        line["cpu_baseline"] = None
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="graft", choices=["graft", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "graft" else args.warmup
+    world_env = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    from weatherforecast_stgcn_maml_b200.dist import init_from_env
+
+    rank, local, world = init_from_env("nccl")
+    if world != args.gpus and world_env > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    if args.gpus > 1 and world == 1:
+        raise SystemExit("launch N>1 with torch.distributed.run (one process per GPU)")
+    try:
+        run_gpu(args, rank, local, world)
+    finally:
+        import torch.distributed as dist
+
+        if dist.is_initialized():
+            dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
