@@ -122,6 +122,17 @@ int wf_clip_adam_step(float* theta, const float* grad, float* exp_avg, float* ex
 int wf_sum_groups(const float* src, long long src_group_stride, int G, long long P, float* dst,
                   int accumulate, void* stream);
 
+/* dst = src - trunc_tf32(src): the `lo` half of the 3xTF32 operand split (csrc/wf_tc.cuh). */
+int wf_split_lo(const float* src, float* dst, long long n, void* stream);
+
+/* tcgen05 3xTF32 GEMM, C[g] = A[g] W[g]^T (+ bias + bias2, relu): A [G*rows_g, K], W/W_lo
+ * [G][N, K] (group stride w_group_stride), C [G*rows_g, N]; K % 32 == 0, N % 128 == 0.
+ * The dense contraction behind GCNConv.lin (model.py:23-26) and the LSTM input projections
+ * (hybrid_model.py:42-49).  err: one device int, non-zero if a pipeline wait timed out. */
+int wf_tc_gemm_nt(const float* A, int rows_g, int G, int K, const float* W, const float* W_lo,
+                  long long w_group_stride, int N, const float* bias, const float* bias2,
+                  long long bias_group_stride, int relu, float* C, int* err, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -47,6 +47,8 @@ SIGNATURES = {
     "wf_clip_sgd_step": (c_i, [c_p, c_ll, c_p, c_ll, c_ll, c_i, c_f, c_f, c_p, c_p, c_sz, c_p]),
     "wf_clip_adam_step": (c_i, [c_p, c_p, c_p, c_p, c_ll, c_p, c_f, c_i, c_p, c_p, c_sz, c_p]),
     "wf_sum_groups": (c_i, [c_p, c_ll, c_i, c_ll, c_p, c_i, c_p]),
+    "wf_split_lo": (c_i, [c_p, c_p, c_ll, c_p]),
+    "wf_tc_gemm_nt": (c_i, [c_p, c_i, c_i, c_i, c_p, c_p, c_ll, c_i, c_p, c_p, c_ll, c_i, c_p, c_p, c_p]),
 }
 
 _lib = None
