@@ -133,6 +133,52 @@ int wf_tc_gemm_nt(const float* A, int rows_g, int G, int K, const float* W, cons
                   long long w_group_stride, int N, const float* bias, const float* bias2,
                   long long bias_group_stride, int relu, float* C, int* err, void* stream);
 
+/* ---- tensor-core (tcgen05, 3xTF32) variants of the hot entry points -------------------------
+ * Same mathematics and buffers as the FP32 entry points above, FP32-class accuracy (~2e-6), plus
+ * transposed activation copies [(G*Bw)][channels][R] that turn the weight-gradient products into
+ * K-major contractions.  err: one device int, set non-zero if a pipeline wait timed out. */
+
+/* Size of the pre-transposed weight buffer (W_hh^T per layer, W_ih^T for layers >= 1). */
+long long wf_param_count_transposed(int layers, int F, int L, int O);
+
+/* Operand staging after every update of the (fast) weights: lo halves + transposed copies. */
+int wf_prep_weights_tc(const float* params, long long params_group_stride, int layers, int F, int L,
+                       int O, int G, float* params_lo, float* paramsT, float* paramsT_lo, void* stream);
+
+/* Row pitch RT of the transposed activation copies [(G*Bw)][channels][RT]: column (t, node) =
+ * t*Np + node with Np = N rounded up to 4 (TMA box starts must be 16-byte aligned -- an unaligned
+ * inner coordinate faults on B200), RT = T*Np.  Padding columns must be zero and are never written. */
+long long wf_transposed_pitch(int T, int N);
+
+/* GCNConv + ReLU (model.py:31-42, hybrid_model.py:65-75) with the neighbour aggregation fused
+ * into the A-operand path of the tcgen05 GEMM.  X dense [G*Bw*R, Cin], Cin % 32 == 0,
+ * Cout % 128 == 0, W shared by all groups, N nodes per time slice (R = T*N); YT / YT_lo optional. */
+int wf_gcn_layer_fwd_tc(const float* X, const float* W, const float* W_lo, const float* bias,
+                        const int* rowptr, const int* col, const float* val,
+                        long long rowptr_group_stride, long long csr_group_stride, int R, int N, int Cin,
+                        int Cout, int G, int Bw, int relu, float* Y, float* YT, float* YT_lo, int* err,
+                        void* stream);
+
+/* nn.LSTM forward (hybrid_model.py:42-49, 93-105); hT / hT_lo [layers][(G*Bw)][L][RT] optional. */
+int wf_lstm_fwd_tc(const float* x, const float* params, const float* params_lo,
+                   long long params_group_stride, int layers, int F, int L, int O, int T, int N, int G,
+                   int Bw, float* gates, float* h, float* c, float* hT, float* hT_lo, int* err,
+                   void* stream);
+
+/* BPTT (train_hybrid_maml_v5.py:134,169).  xT / xT_lo: transposed layer-0 input [(G*Bw)][F][RT];
+ * dgT: scratch [(G*Bw)][4L][RT] with zero padding columns. */
+size_t wf_lstm_bwd_tc_workspace_bytes(int layers, int F, int L, int T, int N, int G, int Bw);
+int wf_lstm_bwd_tc(const float* xT, const float* xT_lo, const float* paramsT, const float* paramsT_lo,
+                   int layers, int F, int L, int O, int T, int N, int G, int Bw, float* gates,
+                   const float* c, const float* hT, const float* hT_lo, float* dgT, const float* dlast,
+                   float* grads, long long grads_group_stride, void* workspace, size_t workspace_bytes,
+                   int* err, void* stream);
+
+/* dW[g][M, N] = sum_w sum_k AT[g*Bw+w][m, a_k0+k] * BT[g*Bw+w][n, b_k0+k], k < klen: the weight
+ * gradient dG^T X over transposed activation copies [(G*Bw)][rows][R] (test entry point). */
+int wf_tc_wgrad(const float* AT, int M, const float* BT, const float* BT_lo, int N, int R, int Bw, int G,
+                int a_k0, int b_k0, int klen, float* dW, long long dw_group_stride, int* err, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -48,3 +48,59 @@ def test_split_lo_is_exact():
     _lib.call("wf_split_lo", _lib.ptr(x), _lib.ptr(lo), x.numel(), _lib.stream_ptr())
     hi = (x.view(torch.int32) & ~0x1FFF).view(torch.float32)
     assert torch.equal(hi + lo, x) and torch.all(lo.abs() <= x.abs() * 2.0 ** -10)
+
+
+@pytest.mark.parametrize("nlat,nlon,T,G,Bw", [(5, 7, 6, 2, 2), (21, 21, 24, 1, 1), (12, 13, 5, 3, 1)])
+def test_engine_tensor_core_path_matches_fp32_path(nlat, nlon, T, G, Bw):
+    """Whole window pass (GCN -> LSTM -> head -> MSE -> BPTT) on the tcgen05 path vs the exact FP32 SIMT path
+    and vs the CPU oracle, v5 layer widths, ragged tiles (N not a multiple of 128), several tasks/windows."""
+    from oracle import ref_port as P
+    from weatherforecast_stgcn_maml_b200 import synth
+    from weatherforecast_stgcn_maml_b200.engine import (HybridEngine, V5Dims, flatten_trainable,
+                                                        gcn_weights_from_state_dict, unflatten_trainable)
+    from weatherforecast_stgcn_maml_b200.graph import RegionGraph, StackedGraphs
+
+    n, H = nlat * nlon, 3
+    dims = V5Dims(num_nodes=n, window=T, horizon=H)
+    lats, lons = synth.region_grid(nlat, nlon)
+    eis = [P.knn_edges_ckdtree(lats, lons, 4) if g % 2 == 0 else P.knn_edges_canonical(lats, lons, 4) for g in range(G)]
+    base = synth.init_v5_state_dict(9, gcn_bias_scale=0.05, horizon=H)
+    sds = [{k: (v + 0.02 * torch.randn_like(v) * (g > 0) if k.startswith(("lstm.", "output_layer.")) else v)
+            for k, v in base.items()} for g in range(G)]
+    time_rows = T + H + 1 + Bw + 2
+    feats = torch.stack([synth.synth_features(time_rows, n, 200 + g) for g in range(G)])
+    per, per_task = n * 24, time_rows * n * 24
+    starts = [[(g + 2 * b) % (Bw + 2) for b in range(Bw)] for g in range(G)]
+    xo = torch.tensor([g * per_task + s * per for g in range(G) for s in starts[g]], device="cuda")
+    to = xo + (T + 1) * per
+    theta = torch.stack([flatten_trainable(sd, dims) for sd in sds]).cuda()
+    graphs = StackedGraphs([RegionGraph(ei, dims.R, "cuda") for ei in eis])
+    fd = feats.cuda()
+    out = {}
+    for prec in ("fp32", "tf32x3"):
+        eng = HybridEngine(dims, G, Bw, "cuda", precision=prec)
+        assert eng.tc == (prec == "tf32x3")
+        eng.gcn_forward(fd, 24, 0, xo, gcn_weights_from_state_dict(base, "cuda"), graphs)
+        eng.check()
+        eng.lstm_head_forward(theta, eng.P)
+        eng.check()
+        loss = eng.mse(feat=fd, tgt_off=to, feat_ld=24, grad_scale=1.0)
+        grads = eng.backward(theta, eng.P)
+        eng.check()
+        out[prec] = (eng.feats.clone(), eng.pred.clone(), loss.clone(), grads.clone(), eng.h.clone())
+    f0, p0, l0, g0, h0 = out["fp32"]
+    f1, p1, l1, g1, h1 = out["tf32x3"]
+    rel = lambda a, b: float((a.double() - b.double()).abs().max() / b.double().abs().max())
+    assert rel(f1, f0) <= 2e-5, "GCN features"
+    assert rel(h1, h0) <= 5e-5, "LSTM hidden states"
+    assert rel(p1, p0) <= 1e-4 and rel(l1, l0) <= 1e-4
+    lay = unflatten_trainable(g0[0], dims)
+    for g in range(G):
+        a, b = unflatten_trainable(g1[g], dims), unflatten_trainable(g0[g], dims)
+        for k in lay:
+            assert rel(a[k], b[k]) <= 1e-3, (g, k, rel(a[k], b[k]))
+    # and against the CPU oracle for task 0, window 0
+    x, y = P.window_xy(feats[0], starts[0][0], T, H)
+    l_ref, g_ref, p_ref = P.loss_and_grads(sds[0], x, y, eis[0], T, H, 1.0, 4)
+    got = p1[:n].cpu().view(n, H, 12).reshape(-1, 12)
+    assert float((got - p_ref).abs().max() / p_ref.abs().max()) <= 1e-4

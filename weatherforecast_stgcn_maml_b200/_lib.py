@@ -47,6 +47,17 @@ SIGNATURES = {
     "wf_clip_sgd_step": (c_i, [c_p, c_ll, c_p, c_ll, c_ll, c_i, c_f, c_f, c_p, c_p, c_sz, c_p]),
     "wf_clip_adam_step": (c_i, [c_p, c_p, c_p, c_p, c_ll, c_p, c_f, c_i, c_p, c_p, c_sz, c_p]),
     "wf_sum_groups": (c_i, [c_p, c_ll, c_i, c_ll, c_p, c_i, c_p]),
+    "wf_param_count_transposed": (c_ll, [c_i, c_i, c_i, c_i]),
+    "wf_prep_weights_tc": (c_i, [c_p, c_ll, c_i, c_i, c_i, c_i, c_i, c_p, c_p, c_p, c_p]),
+    "wf_transposed_pitch": (c_ll, [c_i, c_i]),
+    "wf_gcn_layer_fwd_tc": (c_i, [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_ll, c_ll, c_i, c_i, c_i, c_i, c_i, c_i, c_i,
+                                  c_p, c_p, c_p, c_p, c_p]),
+    "wf_lstm_fwd_tc": (c_i, [c_p, c_p, c_p, c_ll, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_p, c_p, c_p, c_p, c_p,
+                             c_p, c_p]),
+    "wf_lstm_bwd_tc_workspace_bytes": (c_sz, [c_i, c_i, c_i, c_i, c_i, c_i, c_i]),
+    "wf_lstm_bwd_tc": (c_i, [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_p, c_p, c_p, c_p, c_p, c_p,
+                             c_p, c_ll, c_p, c_sz, c_p, c_p]),
+    "wf_tc_wgrad": (c_i, [c_p, c_i, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_p, c_ll, c_p, c_p]),
     "wf_split_lo": (c_i, [c_p, c_p, c_ll, c_p]),
     "wf_tc_gemm_nt": (c_i, [c_p, c_i, c_i, c_i, c_p, c_p, c_ll, c_i, c_p, c_p, c_ll, c_i, c_p, c_p, c_p]),
 }

@@ -19,25 +19,7 @@
 //   then output_layer.weight [O, L], output_layer.bias [O].
 #include "wf_gemm.cuh"
 
-struct LstmLayout {
-  long long w_ih[8], w_hh[8], b_ih[8], b_hh[8], head_w, head_b, total;
-};
-
-static LstmLayout lstm_layout(int layers, int F, int L, int O) {
-  LstmLayout p;
-  long long off = 0;
-  for (int l = 0; l < layers; ++l) {
-    int kin = l == 0 ? F : L;
-    p.w_ih[l] = off; off += 4LL * L * kin;
-    p.w_hh[l] = off; off += 4LL * L * L;
-    p.b_ih[l] = off; off += 4LL * L;
-    p.b_hh[l] = off; off += 4LL * L;
-  }
-  p.head_w = off; off += (long long)O * L;
-  p.head_b = off; off += O;
-  p.total = off;
-  return p;
-}
+#include "wf_layout.cuh"
 
 extern "C" long long wf_param_count(int layers, int F, int L, int O) {
   if (layers < 1 || layers > 8) return -1;

@@ -82,13 +82,23 @@ def gcn_weights_from_state_dict(sd, device, prefix="base_stgcn."):
 
 
 class HybridEngine:
-    def __init__(self, dims: V5Dims, G: int, Bw: int, device="cuda", keep_gcn_activations=False):
+    """precision="tf32x3": dense products on the tcgen05 tensor cores with the 3xTF32 split
+    (FP32-class accuracy, csrc/wf_tc.cuh); used when the model shape allows it (GCN width a
+    multiple of 128, LSTM hidden 128 -- the v5 configuration).  precision="fp32": every product
+    on the exact FP32 CUDA-core kernels (also the route for other shapes)."""
+
+    def __init__(self, dims: V5Dims, G: int, Bw: int, device="cuda", keep_gcn_activations=False, precision="tf32x3",
+                 training=True):
         self.dims, self.G, self.Bw = dims, int(G), int(Bw)
         self.device = torch.device(device)
         if self.device.type != "cuda":
             raise RuntimeError("HybridEngine needs a CUDA device; there is no CPU fallback")
+        if precision not in ("tf32x3", "fp32"):
+            raise ValueError("precision must be 'tf32x3' or 'fp32'")
         _lib.load()
         d = dims
+        self.tc = precision == "tf32x3" and d.lstm_hidden == 128 and d.hidden % 128 == 0
+        self.training = bool(training)
         self.rows = self.G * self.Bw * d.R
         self.W = self.G * self.Bw
         f32 = dict(dtype=torch.float32, device=self.device)
@@ -109,10 +119,47 @@ class HybridEngine:
         ws = max(_lib.query("wf_lstm_bwd_workspace_bytes", Ls, d.hidden, L, d.window, d.num_nodes, self.G, self.Bw),
                  _lib.query("wf_head_workspace_bytes", L, d.O, d.num_nodes, self.G, self.Bw),
                  _lib.query("wf_optim_workspace_bytes", self.G))
+        self.err = torch.zeros(1, dtype=torch.int32, device=self.device)
+        if self.tc:
+            ws = max(ws, _lib.query("wf_lstm_bwd_tc_workspace_bytes", Ls, d.hidden, L, d.window, d.num_nodes, self.G,
+                                    self.Bw))
+            self.PT = int(_lib.query("wf_param_count_transposed", Ls, d.hidden, L, d.O))
+            self.params_lo = torch.empty(self.G, self.P, **f32)
+            self.paramsT = torch.empty(self.G, self.PT, **f32)
+            self.paramsT_lo = torch.empty(self.G, self.PT, **f32)
+            if self.training:
+                # transposed activation copies [(G*Bw)][channels][RT] feed the weight-gradient products;
+                # their padding columns must be zero and are never written by the kernels
+                rt = int(_lib.query("wf_transposed_pitch", d.window, d.num_nodes))
+                self.hT = torch.zeros(Ls, self.W * L * rt, **f32)
+                self.hT_lo = torch.zeros(Ls, self.W * L * rt, **f32)
+                self.featsT = torch.zeros(self.W * d.hidden * rt, **f32)
+                self.featsT_lo = torch.zeros(self.W * d.hidden * rt, **f32)
+                self.dgT = torch.zeros(self.W * 4 * L * rt, **f32)
+            else:
+                self.hT = self.hT_lo = self.featsT = self.featsT_lo = self.dgT = None
+            self._gcn_lo = {}
         self.ws_bytes = int(ws)
         self.ws = torch.empty(self.ws_bytes, dtype=torch.uint8, device=self.device)
         self.feats = None
         self.launches = 0  # kernels enqueued by this engine (bench.py reports it)
+
+    def check(self):
+        """Synchronise and raise if a tensor-core pipeline wait timed out (never expected)."""
+        code = int(self.err.item())
+        if code != 0:
+            raise RuntimeError(f"tcgen05 pipeline timeout (role code {code})")
+
+    def _gcn_w_lo(self, Wt):
+        key = (Wt.data_ptr(), Wt._version)
+        lo = self._gcn_lo.get(key)
+        if lo is None:
+            lo = torch.empty_like(Wt)
+            _lib.call("wf_split_lo", _lib.ptr(Wt), _lib.ptr(lo), Wt.numel(), _lib.stream_ptr())
+            if len(self._gcn_lo) > 16:
+                self._gcn_lo.clear()
+            self._gcn_lo[key] = lo
+        return lo
 
     # ------------------------------------------------------------------ GCN stack
     def gcn_forward(self, X, x_ld, x_win_stride, x_win_off, gcn_weights, graphs):
@@ -127,11 +174,20 @@ class HybridEngine:
         if graphs.R != d.R:
             raise ValueError(f"graph was normalised over {graphs.R} rows, engine window has {d.R}")
         src, src_ld, src_stride, src_off, cin = X, x_ld, x_win_stride, x_win_off, d.in_channels
+        nlayers = len(gcn_weights)
         for i, (Wt, b) in enumerate(gcn_weights):
             dst = self.act[i] if self.keep_gcn else self.act[i & 1]
-            _lib.call("wf_gcn_layer_fwd", _lib.ptr(src), src_ld, src_stride, _lib.ptr(src_off), _lib.ptr(Wt),
-                      _lib.ptr(b), 0, 0, _lib.ptr(rp), _lib.ptr(cl), _lib.ptr(vl), rps, cs, d.R, cin, d.hidden,
-                      self.G, self.Bw, 1, _lib.ptr(dst), st)
+            dense = src_off is None and src_ld == cin and src_stride == d.R * cin
+            if self.tc and dense and cin % 32 == 0:
+                want_t = self.training and i == nlayers - 1
+                _lib.call("wf_gcn_layer_fwd_tc", _lib.ptr(src), _lib.ptr(Wt), _lib.ptr(self._gcn_w_lo(Wt)), _lib.ptr(b),
+                          _lib.ptr(rp), _lib.ptr(cl), _lib.ptr(vl), rps, cs, d.R, d.num_nodes, cin, d.hidden, self.G,
+                          self.Bw, 1, _lib.ptr(dst), _lib.ptr(self.featsT) if want_t else None,
+                          _lib.ptr(self.featsT_lo) if want_t else None, _lib.ptr(self.err), st)
+            else:
+                _lib.call("wf_gcn_layer_fwd", _lib.ptr(src), src_ld, src_stride, _lib.ptr(src_off), _lib.ptr(Wt),
+                          _lib.ptr(b), 0, 0, _lib.ptr(rp), _lib.ptr(cl), _lib.ptr(vl), rps, cs, d.R, cin, d.hidden,
+                          self.G, self.Bw, 1, _lib.ptr(dst), st)
             self.launches += 1
             src, src_ld, src_stride, src_off, cin = dst, d.hidden, d.R * d.hidden, None, d.hidden
         self.feats = src
@@ -141,13 +197,22 @@ class HybridEngine:
     def lstm_head_forward(self, params, params_stride, feats=None):
         d, st = self.dims, _lib.stream_ptr()
         feats = self.feats if feats is None else feats
-        _lib.call("wf_lstm_fwd", _lib.ptr(feats), _lib.ptr(params), params_stride, d.lstm_layers, d.hidden,
-                  d.lstm_hidden, d.O, d.window, d.num_nodes, self.G, self.Bw, _lib.ptr(self.gates), _lib.ptr(self.h),
-                  _lib.ptr(self.c), st)
-        _lib.call("wf_head_fwd", _lib.ptr(self.h[d.lstm_layers - 1]), _lib.ptr(params), params_stride,
-                  d.lstm_layers, d.hidden, d.lstm_hidden, d.O, d.window, d.num_nodes, self.G, self.Bw,
-                  _lib.ptr(self.pred), st)
-        self.launches += d.lstm_layers * (1 + d.window) + 1
+        Ls, L = d.lstm_layers, d.lstm_hidden
+        if self.tc:
+            # operand staging for 3xTF32: lo halves and transposed copies of the current weights
+            src_stride = params_stride if self.G > 1 else self.P
+            _lib.call("wf_prep_weights_tc", _lib.ptr(params), src_stride, Ls, d.hidden, L, d.O, self.G,
+                      _lib.ptr(self.params_lo), _lib.ptr(self.paramsT), _lib.ptr(self.paramsT_lo), st)
+            _lib.call("wf_lstm_fwd_tc", _lib.ptr(feats), _lib.ptr(params), _lib.ptr(self.params_lo), params_stride, Ls,
+                      d.hidden, L, d.O, d.window, d.num_nodes, self.G, self.Bw, _lib.ptr(self.gates), _lib.ptr(self.h),
+                      _lib.ptr(self.c), _lib.ptr(self.hT), _lib.ptr(self.hT_lo), _lib.ptr(self.err), st)
+            self.launches += 2 * Ls
+        else:
+            _lib.call("wf_lstm_fwd", _lib.ptr(feats), _lib.ptr(params), params_stride, Ls, d.hidden, L, d.O, d.window,
+                      d.num_nodes, self.G, self.Bw, _lib.ptr(self.gates), _lib.ptr(self.h), _lib.ptr(self.c), st)
+        _lib.call("wf_head_fwd", _lib.ptr(self.h[Ls - 1]), _lib.ptr(params), params_stride, Ls, d.hidden, L, d.O,
+                  d.window, d.num_nodes, self.G, self.Bw, _lib.ptr(self.pred), st)
+        self.launches += Ls * (1 + d.window) + 1
         return self.pred
 
     def mse(self, y=None, feat=None, tgt_off=None, feat_ld=0, grad_scale=1.0, want_grad=True):
@@ -164,14 +229,24 @@ class HybridEngine:
         d, st = self.dims, _lib.stream_ptr()
         feats = self.feats if feats is None else feats
         dpred = self.dpred if dpred is None else dpred
-        Ls = d.lstm_layers
+        Ls, L = d.lstm_layers, d.lstm_hidden
         _lib.call("wf_head_bwd", _lib.ptr(dpred), _lib.ptr(self.h[Ls - 1]), _lib.ptr(params), params_stride, Ls,
-                  d.hidden, d.lstm_hidden, d.O, d.window, d.num_nodes, self.G, self.Bw, _lib.ptr(self.dlast),
+                  d.hidden, L, d.O, d.window, d.num_nodes, self.G, self.Bw, _lib.ptr(self.dlast),
                   _lib.ptr(self.grads), self.P, _lib.ptr(self.ws), self.ws_bytes, st)
-        _lib.call("wf_lstm_bwd", _lib.ptr(feats), _lib.ptr(params), params_stride, Ls, d.hidden, d.lstm_hidden, d.O,
-                  d.window, d.num_nodes, self.G, self.Bw, _lib.ptr(self.gates), _lib.ptr(self.h), _lib.ptr(self.c),
-                  _lib.ptr(self.dlast), _lib.ptr(self.grads), self.P, _lib.ptr(self.ws), self.ws_bytes, st)
-        self.launches += 6 + Ls * (d.window + 9)
+        if self.tc:
+            if not self.training:
+                raise RuntimeError("engine was built with training=False")
+            _lib.call("wf_lstm_bwd_tc", _lib.ptr(self.featsT), _lib.ptr(self.featsT_lo), _lib.ptr(self.paramsT),
+                      _lib.ptr(self.paramsT_lo), Ls, d.hidden, L, d.O, d.window, d.num_nodes, self.G, self.Bw,
+                      _lib.ptr(self.gates), _lib.ptr(self.c), _lib.ptr(self.hT), _lib.ptr(self.hT_lo),
+                      _lib.ptr(self.dgT), _lib.ptr(self.dlast), _lib.ptr(self.grads), self.P, _lib.ptr(self.ws),
+                      self.ws_bytes, _lib.ptr(self.err), st)
+            self.launches += 6 + Ls * (d.window + 5)
+        else:
+            _lib.call("wf_lstm_bwd", _lib.ptr(feats), _lib.ptr(params), params_stride, Ls, d.hidden, L, d.O, d.window,
+                      d.num_nodes, self.G, self.Bw, _lib.ptr(self.gates), _lib.ptr(self.h), _lib.ptr(self.c),
+                      _lib.ptr(self.dlast), _lib.ptr(self.grads), self.P, _lib.ptr(self.ws), self.ws_bytes, st)
+            self.launches += 6 + Ls * (d.window + 9)
         return self.grads
 
     def sgd_step(self, fast, lr, max_norm=1.0):
