@@ -179,6 +179,40 @@ int wf_lstm_bwd_tc(const float* xT, const float* xT_lo, const float* paramsT, co
 int wf_tc_wgrad(const float* AT, int M, const float* BT, const float* BT_lo, int N, int R, int Bw, int G,
                 int a_k0, int b_k0, int klen, float* dW, long long dw_group_stride, int* err, void* stream);
 
+/* ---- persistent LSTM recurrence (csrc/wf_lstm_seq.cu) ------------------------------------------
+ * One launch per layer runs all T steps: a 2-CTA cluster owns a tile of 128 (task, window, node)
+ * sequences, keeps the task's W_hh in shared memory as 16-bit hi/lo operands and exchanges h / partial
+ * dh through distributed shared memory.  Activations private to this path (gates, cell state, dh
+ * between layers) use the TB4 layout: per (window, step, 128-node tile) a block
+ * [channels/4][128 rows][4 floats]. */
+
+/* f32 elements of a TB4 buffer with `channels` values per (window, step, node). */
+long long wf_tb4_elems(int channels, int T, int N, long long windows);
+
+/* 16-bit elements of EACH of the four operand buffers wf_prep_weights_seq writes. */
+long long wf_seq_weight_elems(int layers, int L, int G);
+
+/* W_hh of every (task, layer) -> fp16 hi/lo [G][layers][4L][L] (forward operand) and bf16 hi/lo
+ * [G][layers][2][L][2L] (backward operand, regrouped per CTA rank).  Run after every weight update. */
+int wf_prep_weights_seq(const float* params, long long params_group_stride, int layers, int F, int L,
+                        int O, int G, void* f16_hi, void* f16_lo, void* bf16_hi, void* bf16_lo, void* stream);
+
+/* nn.LSTM forward (hybrid_model.py:42-49, 93-105).  x [G*Bw*T*N, F] and h [layers][G*Bw*T*N, L] are
+ * row-major; gates (4L channels) and c (L channels) are TB4, [layers] of them; hT / hT_lo optional. */
+int wf_lstm_fwd_seq(const float* x, const float* params, const float* params_lo,
+                    long long params_group_stride, const void* f16_hi, const void* f16_lo, int layers,
+                    int F, int L, int O, int T, int N, int G, int Bw, float* gates, float* h, float* c,
+                    float* hT, float* hT_lo, int* err, void* stream);
+
+/* BPTT (train_hybrid_maml_v5.py:134,169; adapt_hybrid_v5.py:198) over the buffers of wf_lstm_fwd_seq;
+ * gates are overwritten with dL/d(pre-activation).  Other arguments as wf_lstm_bwd_tc. */
+size_t wf_lstm_bwd_seq_workspace_bytes(int layers, int F, int L, int T, int N, int G, int Bw);
+int wf_lstm_bwd_seq(const float* xT, const float* xT_lo, const float* paramsT, const float* paramsT_lo,
+                    const void* bf16_hi, const void* bf16_lo, int layers, int F, int L, int O, int T, int N,
+                    int G, int Bw, float* gates, const float* c, const float* hT, const float* hT_lo,
+                    float* dgT, const float* dlast, float* grads, long long grads_group_stride,
+                    void* workspace, size_t workspace_bytes, int* err, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

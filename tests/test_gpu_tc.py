@@ -77,9 +77,10 @@ def test_engine_tensor_core_path_matches_fp32_path(nlat, nlon, T, G, Bw):
     graphs = StackedGraphs([RegionGraph(ei, dims.R, "cuda") for ei in eis])
     fd = feats.cuda()
     out = {}
-    for prec in ("fp32", "tf32x3"):
-        eng = HybridEngine(dims, G, Bw, "cuda", precision=prec)
-        assert eng.tc == (prec == "tf32x3")
+    for prec in ("fp32", "tf32x3", "stepwise"):
+        eng = HybridEngine(dims, G, Bw, "cuda", precision="fp32" if prec == "fp32" else "tf32x3",
+                           lstm_mode="stepwise" if prec == "stepwise" else "persistent")
+        assert eng.tc == (prec != "fp32") and eng.seq == (prec == "tf32x3")
         eng.gcn_forward(fd, 24, 0, xo, gcn_weights_from_state_dict(base, "cuda"), graphs)
         eng.check()
         eng.lstm_head_forward(theta, eng.P)
@@ -89,16 +90,18 @@ def test_engine_tensor_core_path_matches_fp32_path(nlat, nlon, T, G, Bw):
         eng.check()
         out[prec] = (eng.feats.clone(), eng.pred.clone(), loss.clone(), grads.clone(), eng.h.clone())
     f0, p0, l0, g0, h0 = out["fp32"]
-    f1, p1, l1, g1, h1 = out["tf32x3"]
     rel = lambda a, b: float((a.double() - b.double()).abs().max() / b.double().abs().max())
-    assert rel(f1, f0) <= 2e-5, "GCN features"
-    assert rel(h1, h0) <= 5e-5, "LSTM hidden states"
-    assert rel(p1, p0) <= 1e-4 and rel(l1, l0) <= 1e-4
     lay = unflatten_trainable(g0[0], dims)
-    for g in range(G):
-        a, b = unflatten_trainable(g1[g], dims), unflatten_trainable(g0[g], dims)
-        for k in lay:
-            assert rel(a[k], b[k]) <= 1e-3, (g, k, rel(a[k], b[k]))
+    for mode in ("tf32x3", "stepwise"):  # persistent cluster kernels, then the per-step launches
+        f1, p1, l1, g1, h1 = out[mode]
+        assert rel(f1, f0) <= 2e-5, (mode, "GCN features")
+        assert rel(h1, h0) <= 5e-5, (mode, "LSTM hidden states", rel(h1, h0))
+        assert rel(p1, p0) <= 1e-4 and rel(l1, l0) <= 1e-4, mode
+        for g in range(G):
+            a, b = unflatten_trainable(g1[g], dims), unflatten_trainable(g0[g], dims)
+            for k in lay:
+                assert rel(a[k], b[k]) <= 1e-3, (mode, g, k, rel(a[k], b[k]))
+    f1, p1, l1, g1, h1 = out["tf32x3"]
     # and against the CPU oracle for task 0, window 0
     x, y = P.window_xy(feats[0], starts[0][0], T, H)
     l_ref, g_ref, p_ref = P.loss_and_grads(sds[0], x, y, eis[0], T, H, 1.0, 4)

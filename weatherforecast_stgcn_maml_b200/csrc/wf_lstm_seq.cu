@@ -1,0 +1,756 @@
+// Persistent LSTM recurrence kernels (sm_100a): one launch runs all T steps of one layer.
+//
+// Replaces the reference's per-node Python loop over nn.LSTM (hybrid_model.py:93-105: 441 calls
+// per window) and autograd's BPTT (train_hybrid_maml_v5.py:134,169).  Sequences are independent,
+// so a tile of 128 (task, window, node) sequences is owned by one 2-CTA cluster for the whole
+// window; the recurrent weights of the tile's task stay in shared memory for all T steps and the
+// per-step product runs on the tcgen05 tensor cores with 16-bit hi/lo operand splits
+//     a*b ~= a_hi*b_hi + a_lo*b_hi + a_hi*b_lo   (fp32 accumulate in TMEM)
+// fp16 in the forward pass (|h| < 1, |W| ~ 0.1: ~2^-20 relative), bf16 in the backward pass
+// (gradients span the fp32 exponent range; ~2^-16 relative against a 1e-3 gradient tolerance).
+//
+// Forward (N split): CTA r of the pair holds W_hh rows of units [64r, 64r+64) x 4 gates
+// (256 x 128, hi + lo = 128 KB), computes D[128 x 256] = h[t-1] W^T from shared memory (SS mode),
+// applies the cell non-linearities and writes its 64 units of h[t] as fp16 hi/lo straight into
+// the A-operand buffer of BOTH CTAs (st.shared::cluster), so the only per-step exchange is the
+// operand itself.
+// Backward (K split): CTA r holds W_hh^T restricted to its own gate rows (128 x 256, 128 KB), keeps
+// its own dG[t+1] (128 x 256) in TMEM as the A operand (TS mode) and produces a partial
+// dh[128 x 128]; the half belonging to the peer's units goes through distributed shared memory
+// (fp32, 32 KB per step, double buffered).
+//
+// Activation layout ("TB4", wf_layout.cuh): per (window, step, 128-node tile) a block of
+// [channels / 4][128 rows][4 floats], so a warp whose lanes are consecutive rows moves 512
+// contiguous bytes per float4 instruction in both the GEMM epilogues and the cell epilogues.
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+
+#include "wf_common.cuh"
+#include "wf_layout.cuh"
+#include "wf_tc.cuh"
+
+using namespace wftc;
+
+int wf_launch_tc_nodes(const float* A, int a_tb4, int K, const float* Whi, const float* Wlo, int ldb, long long b_gstride,
+                       int N, const float* bias, const float* bias2, long long bias_gstride, float* C, int T, int Nn, int Bw,
+                       int G, int* err, cudaStream_t st);
+int wf_launch_tc_wgrad(const float* AT, int M, const float* BT, const float* BT_lo, int N, int R, int Bw, int G,
+                       int a_k0, int b_k0, int klen, float* dW, long long dw_gstride, int* err, cudaStream_t st);
+
+namespace {
+
+constexpr int SEQ_THREADS = 256;  // 8 warps = 4 TMEM lane quarters x 2 unit halves; warp 0 also owns TMEM, TMA and MMA issue
+                                  // (9 warps would put 3 on one SM sub-partition and cap registers at 168)
+constexpr int SEQ_SMEM = 196608 + 1024;
+
+struct SeqArgs {
+  float* XG;          // TB4, 4L channels. fwd: input projection in, activated gates out; bwd: gates in, dG out
+  float* Cst;         // TB4, L channels: cell state
+  float* H;           // fwd out: row-major [Z*R, L]
+  float* HT;          // fwd out (optional): transposed copies [(z)][L][RT]
+  float* HT_lo;
+  float* DGT;         // bwd out: transposed dG [(z)][4L][RT]
+  const float* ext;   // bwd: dL/dh from above -- TB4 (L channels), or row-major dlast [Z*Nn, L] if ext_last_only
+  int ext_last_only;
+  int T, Nn, Bw, tpw, Np, RT;
+  int slab0, slab_g;  // weight map z coordinate = slab0 + g * slab_g (+ rank in the backward kernel)
+  int* err;
+};
+
+__device__ __forceinline__ uint32_t cluster_rank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;\n" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+}
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t saddr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;\n" : "=r"(r) : "r"(saddr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void st_cluster_v4(uint32_t caddr, uint4 v) {
+  asm volatile("st.shared::cluster.v4.b32 [%0], {%1, %2, %3, %4};\n" ::"r"(caddr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ void arrive_cluster(uint32_t cbar) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];\n" ::"r"(cbar) : "memory");
+}
+// bounded wait with cluster-scope acquire (the barrier receives arrivals from the peer CTA)
+__device__ __forceinline__ bool mbar_wait_cl(uint64_t* bar, uint32_t parity) {
+  for (uint32_t spin = 0; spin < (1u << 18); ++spin) {
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}\n"
+                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    if (ok) return true;
+  }
+  return false;
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;\n" ::: "memory"); }
+
+// kind::f16 instruction descriptor: D = F32, A/B = fmt (0 F16, 1 BF16), both K-major, M = 128
+__host__ __device__ constexpr uint32_t idesc_16(int n, uint32_t fmt) {
+  return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+}
+__device__ __forceinline__ void umma_ss_16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+               "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
+               ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void umma_ts_16(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+               "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}\n"
+               ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void tmem_st4(uint32_t taddr, const uint32_t* v) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};\n"
+               ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]) : "memory");
+}
+
+__device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+__device__ __forceinline__ float fast_tanh(float x) { return 2.0f * __fdividef(1.0f, 1.0f + __expf(-2.0f * x)) - 1.0f; }
+
+__device__ __forceinline__ uint32_t pack_f16(float a, float b, float& ra, float& rb) {
+  const __half ha = __float2half_rn(a), hb = __float2half_rn(b);
+  ra = a - __half2float(ha);
+  rb = b - __half2float(hb);
+  return (uint32_t)__half_as_ushort(ha) | ((uint32_t)__half_as_ushort(hb) << 16);
+}
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b, float& ra, float& rb) {
+  const __nv_bfloat16 ha = __float2bfloat16_rn(a), hb = __float2bfloat16_rn(b);
+  ra = a - __bfloat162float(ha);
+  rb = b - __bfloat162float(hb);
+  return (uint32_t)__bfloat16_as_ushort(ha) | ((uint32_t)__bfloat16_as_ushort(hb) << 16);
+}
+
+// ================================================================================= forward
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(SEQ_THREADS, 1)
+wf_lstm_seq_fwd_kernel(const __grid_constant__ CUtensorMap tmWhi, const __grid_constant__ CUtensorMap tmWlo, const SeqArgs a) {
+  constexpr int L = 128;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* b_hi = smem;            // [2 k-blocks][256 gate rows][128 B]
+  uint8_t* b_lo = smem + 65536;
+  uint8_t* a_hi = smem + 131072;   // [2 k-blocks][128 rows][128 B]
+  uint8_t* a_lo = smem + 163840;
+  __shared__ uint64_t wfull, a_ready, dfull, peer_done;
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t rank = cluster_rank(), peer = rank ^ 1u;
+  const int tile = blockIdx.x >> 1;
+  const int z = tile / a.tpw, nt = tile - z * a.tpw, node0 = nt * 128, g = z / a.Bw;
+  const int T = a.T;
+
+  if (tid == 0) {
+    mbar_init(&wfull, 1); mbar_init(&a_ready, 16); mbar_init(&dfull, 1); mbar_init(&peer_done, 1);
+    mbar_fence_init();
+    tma_prefetch_desc(&tmWhi); tma_prefetch_desc(&tmWlo);
+  }
+  if (warp == 0) tmem_alloc(&tmem_base_s, 256);
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();  // the peer's barriers exist before anybody arrives on them remotely
+  tc_fence_after();
+  const uint32_t tbase = tmem_base_s;
+
+  if (warp == 0 && lane == 0) {  // recurrent weights of this tile's task: resident for all T steps
+    const int slab = a.slab0 + g * a.slab_g;
+    mbar_expect_tx(&wfull, 131072);
+    for (int kb = 0; kb < 2; ++kb) {
+      tma_load_4d(b_hi + kb * 32768, &tmWhi, &wfull, kb * 64, 64 * (int)rank, 0, slab);
+      tma_load_4d(b_lo + kb * 32768, &tmWlo, &wfull, kb * 64, 64 * (int)rank, 0, slab);
+    }
+  }
+  {
+    // ---------------------------------------------------------------- cell epilogue
+    const int q = warp & 3, half = warp >> 2;
+    const int r = q * 32 + lane;            // tile row == TMEM lane
+    const int ub = half * 32;               // first of this thread's 32 units inside the CTA's 64
+    const int u0 = 64 * (int)rank + ub;     // ... as a global hidden-unit index
+    const int node = node0 + r;
+    const bool valid = node < a.Nn;
+    const uint32_t tlane = tbase + ((uint32_t)(q * 32) << 16);
+    const long long R = (long long)T * a.Nn;
+    float4* const xg4 = reinterpret_cast<float4*>(a.XG);
+    float4* const c4 = reinterpret_cast<float4*>(a.Cst);
+    const uint32_t pd_remote = mapa_u32(smem_u32(&peer_done), peer);
+    const uint32_t ar_local = smem_u32(&a_ready), ar_remote = mapa_u32(smem_u32(&a_ready), peer);
+    bool ok = true;
+
+    float cst[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) cst[j] = 0.f;
+    float4 xq[2][8];
+    // chunk (t, c): units u0 + 8c .. +8, all four gates -> 8 float4 (gate * 2 + half-of-8)
+    auto xg_index = [&](int t, int c, int gate, int hh) -> long long {
+      const long long blk = ((long long)z * T + t) * a.tpw + nt;
+      return (blk * 128 + gate * 32 + ((u0 + 8 * c) >> 2) + hh) * 128 + r;
+    };
+    auto load_chunk = [&](int t, int c, float4* dst) {
+#pragma unroll
+      for (int gate = 0; gate < 4; ++gate) {
+        dst[gate * 2] = xg4[xg_index(t, c, gate, 0)];
+        dst[gate * 2 + 1] = xg4[xg_index(t, c, gate, 1)];
+      }
+    };
+    load_chunk(0, 0, xq[0]);
+    load_chunk(0, 1, xq[1]);
+
+    for (int t = 0; t < T; ++t) {
+      if (t > 0) {
+        if (warp == 0) {  // MMA issue: D[128 x 256] = h[t-1] W_hh^T for this CTA's 64 units x 4 gates
+          if (ok && t == 1 && !mbar_wait(&wfull, 0)) { ok = false; if (lane == 0) atomicExch(a.err, 11); }
+          if (ok && !mbar_wait_cl(&a_ready, (t - 1) & 1)) { ok = false; if (lane == 0) atomicExch(a.err, 12); }
+          fence_proxy_async();
+          tc_fence_after();
+          if (lane == 0 && ok) {
+            const uint32_t idesc = idesc_16(256, 0);
+            uint32_t accf = 0;
+#pragma unroll
+            for (int p = 0; p < 3; ++p) {  // h_hi W_hi, h_lo W_hi, h_hi W_lo
+              const uint32_t as = smem_u32(p == 1 ? a_lo : a_hi), bs = smem_u32(p == 2 ? b_lo : b_hi);
+#pragma unroll
+              for (int kb = 0; kb < 2; ++kb)
+#pragma unroll
+                for (int k16 = 0; k16 < 4; ++k16) {
+                  umma_ss_16(tbase, umma_desc_k_sw128(as + kb * 16384 + k16 * 32),
+                             umma_desc_k_sw128(bs + kb * 32768 + k16 * 32), idesc, accf);
+                  accf = 1;
+                }
+            }
+            umma_commit(&dfull);
+          }
+          __syncwarp();
+        }
+        if (ok && !mbar_wait(&dfull, (t - 1) & 1)) { ok = false; if (lane == 0) atomicExch(a.err, 13); }
+        tc_fence_after();
+        if (warp == 0 && lane == 0) arrive_cluster(pd_remote);  // my MMA no longer reads my A buffer
+      }
+      const long long blk = ((long long)z * T + t) * a.tpw + nt;
+      const long long hrow = ((long long)z * R + (long long)t * a.Nn + node) * L + u0;
+      const long long tcol = (long long)t * a.Np + node;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint32_t acc[4][8];
+        if (t > 0) {
+          __syncwarp();
+#pragma unroll
+          for (int gate = 0; gate < 4; ++gate) tmem_ld8(tlane + gate * 64 + ub + 8 * c, acc[gate]);
+          tmem_wait_ld();
+        } else {
+#pragma unroll
+          for (int gate = 0; gate < 4; ++gate)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[gate][j] = 0u;
+        }
+        const float4* x = xq[c & 1];
+        float gi[8], gf[8], gg[8], go[8], hh[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int hsel = j >> 2, cmp = j & 3;
+          const float4 xi = x[0 + hsel], xf = x[2 + hsel], xgv = x[4 + hsel], xo = x[6 + hsel];
+          const float pi = (cmp == 0 ? xi.x : cmp == 1 ? xi.y : cmp == 2 ? xi.z : xi.w) + __uint_as_float(acc[0][j]);
+          const float pf = (cmp == 0 ? xf.x : cmp == 1 ? xf.y : cmp == 2 ? xf.z : xf.w) + __uint_as_float(acc[1][j]);
+          const float pg = (cmp == 0 ? xgv.x : cmp == 1 ? xgv.y : cmp == 2 ? xgv.z : xgv.w) + __uint_as_float(acc[2][j]);
+          const float po = (cmp == 0 ? xo.x : cmp == 1 ? xo.y : cmp == 2 ? xo.z : xo.w) + __uint_as_float(acc[3][j]);
+          gi[j] = fast_sigmoid(pi);
+          gf[j] = fast_sigmoid(pf);
+          gg[j] = fast_tanh(pg);
+          go[j] = fast_sigmoid(po);
+          const float cc = fmaf(gf[j], cst[8 * c + j], gi[j] * gg[j]);
+          cst[8 * c + j] = cc;
+          hh[j] = go[j] * fast_tanh(cc);
+        }
+        // activated gates overwrite the projection in place; cell state; hidden state
+#pragma unroll
+        for (int hsel = 0; hsel < 2; ++hsel) {
+          const int j = 4 * hsel;
+          xg4[xg_index(t, c, 0, hsel)] = make_float4(gi[j], gi[j + 1], gi[j + 2], gi[j + 3]);
+          xg4[xg_index(t, c, 1, hsel)] = make_float4(gf[j], gf[j + 1], gf[j + 2], gf[j + 3]);
+          xg4[xg_index(t, c, 2, hsel)] = make_float4(gg[j], gg[j + 1], gg[j + 2], gg[j + 3]);
+          xg4[xg_index(t, c, 3, hsel)] = make_float4(go[j], go[j + 1], go[j + 2], go[j + 3]);
+          c4[(blk * 32 + ((u0 + 8 * c) >> 2) + hsel) * 128 + r] =
+              make_float4(cst[8 * c + j], cst[8 * c + j + 1], cst[8 * c + j + 2], cst[8 * c + j + 3]);
+        }
+        if (valid) {
+          *reinterpret_cast<float4*>(a.H + hrow + 8 * c) = make_float4(hh[0], hh[1], hh[2], hh[3]);
+          *reinterpret_cast<float4*>(a.H + hrow + 8 * c + 4) = make_float4(hh[4], hh[5], hh[6], hh[7]);
+          if (a.HT != nullptr) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const long long ti = ((long long)z * L + u0 + 8 * c + j) * a.RT + tcol;
+              a.HT[ti] = hh[j];
+              a.HT_lo[ti] = hh[j] - __uint_as_float(__float_as_uint(hh[j]) & 0xFFFFE000u);
+            }
+          }
+        }
+        if (t + 1 < T) {
+          // h[t] as fp16 hi/lo -> the A operand of step t+1 in both CTAs (k-block `rank`, chunk (ub + 8c) / 8)
+          uint32_t hi[4], lo[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            float ra, rb, d0, d1;
+            hi[i] = pack_f16(hh[2 * i], hh[2 * i + 1], ra, rb);
+            lo[i] = pack_f16(ra, rb, d0, d1);
+          }
+          const uint32_t off = rank * 16384u + (uint32_t)(r >> 3) * 1024u + (uint32_t)(r & 7) * 128u +
+                               ((uint32_t)((((ub >> 3) + c)) ^ (r & 7)) << 4);
+          if (c == 0 && t > 0) {  // the peer's MMA of this step must be done with the peer's A buffer
+            if (ok && !mbar_wait_cl(&peer_done, (t - 1) & 1)) { ok = false; if (lane == 0) atomicExch(a.err, 14); }
+          }
+          const uint4 vhi = make_uint4(hi[0], hi[1], hi[2], hi[3]), vlo = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+          *reinterpret_cast<uint4*>(a_hi + off) = vhi;
+          *reinterpret_cast<uint4*>(a_lo + off) = vlo;
+          st_cluster_v4(mapa_u32(smem_u32(a_hi + off), peer), vhi);
+          st_cluster_v4(mapa_u32(smem_u32(a_lo + off), peer), vlo);
+        }
+        // prefetch two chunks ahead
+        {
+          const int cn = (c + 2) & 3, tn = t + ((c + 2) >> 2);
+          if (tn < T) load_chunk(tn, cn, xq[c & 1]);
+        }
+      }
+      if (t + 1 < T) {
+        fence_proxy_async();      // generic-proxy operand writes -> visible to the tensor core (async proxy)
+        tc_fence_before();        // my TMEM reads of D[t] are complete before MMA[t+1] may overwrite D
+        __syncwarp();
+        if (lane == 0) {
+          asm volatile("mbarrier.arrive.release.cluster.shared::cta.b64 _, [%0];\n" ::"r"(ar_local) : "memory");
+          arrive_cluster(ar_remote);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tbase, 256);
+  cluster_sync_all();  // nobody exits while the peer may still address this CTA's shared memory
+}
+
+// ================================================================================= backward
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(SEQ_THREADS, 1)
+wf_lstm_seq_bwd_kernel(const __grid_constant__ CUtensorMap tmWhi, const __grid_constant__ CUtensorMap tmWlo, const SeqArgs a) {
+  constexpr int L = 128;
+  constexpr uint32_t A_HI = 128, A_LO = 256;  // TMEM columns: D [0,128), dG hi [128,256), dG lo [256,384)
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* b_hi = smem;            // [4 k-blocks][128 unit rows][128 B]
+  uint8_t* b_lo = smem + 65536;
+  uint8_t* xbuf = smem + 131072;   // 2 x [2 halves][8 quads][128 rows][16 B]: the peer's partial dh for my units
+  __shared__ uint64_t wfull, a_ready, dfull, x_ready[2];
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t rank = cluster_rank(), peer = rank ^ 1u;
+  const int tile = blockIdx.x >> 1;
+  const int z = tile / a.tpw, nt = tile - z * a.tpw, node0 = nt * 128, g = z / a.Bw;
+  const int T = a.T;
+
+  if (tid == 0) {
+    mbar_init(&wfull, 1); mbar_init(&a_ready, 8); mbar_init(&dfull, 1); mbar_init(&x_ready[0], 8); mbar_init(&x_ready[1], 8);
+    mbar_fence_init();
+    tma_prefetch_desc(&tmWhi); tma_prefetch_desc(&tmWlo);
+  }
+  if (warp == 0) tmem_alloc(&tmem_base_s, 512);
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tbase = tmem_base_s;
+
+  if (warp == 0 && lane == 0) {
+    const int slab = a.slab0 + g * a.slab_g + (int)rank;
+    mbar_expect_tx(&wfull, 131072);
+    for (int kb = 0; kb < 4; ++kb) {
+      tma_load_3d(b_hi + kb * 16384, &tmWhi, &wfull, kb * 64, 0, slab);
+      tma_load_3d(b_lo + kb * 16384, &tmWlo, &wfull, kb * 64, 0, slab);
+    }
+  }
+  {
+    const int q = warp & 3, half = warp >> 2;
+    const int r = q * 32 + lane;
+    const int ub = half * 32;
+    const int u0 = 64 * (int)rank + ub;
+    const int node = node0 + r;
+    const bool valid = node < a.Nn;
+    const float vm = valid ? 1.0f : 0.0f;
+    const uint32_t tlane = tbase + ((uint32_t)(q * 32) << 16);
+    float4* const xg4 = reinterpret_cast<float4*>(a.XG);
+    const float4* const c4 = reinterpret_cast<const float4*>(a.Cst);
+    const float4* const e4 = reinterpret_cast<const float4*>(a.ext);
+    const uint32_t xr_remote0 = mapa_u32(smem_u32(&x_ready[0]), peer), xr_remote1 = mapa_u32(smem_u32(&x_ready[1]), peer);
+    const uint32_t xbuf_remote = mapa_u32(smem_u32(xbuf), peer);
+    bool ok = true;
+
+    float dcs[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) dcs[j] = 0.f;
+    // per chunk: gates 8 float4, c[t] 2, c[t-1] 2, ext 2
+    float4 ld[2][14];
+    auto blk_of = [&](int t) -> long long { return ((long long)z * T + t) * a.tpw + nt; };
+    auto load_chunk = [&](int t, int c, float4* dst) {
+      const long long blk = blk_of(t);
+      const int uq = (u0 + 8 * c) >> 2;
+#pragma unroll
+      for (int gate = 0; gate < 4; ++gate) {
+        dst[gate * 2] = xg4[(blk * 128 + gate * 32 + uq) * 128 + r];
+        dst[gate * 2 + 1] = xg4[(blk * 128 + gate * 32 + uq + 1) * 128 + r];
+      }
+      dst[8] = c4[(blk * 32 + uq) * 128 + r];
+      dst[9] = c4[(blk * 32 + uq + 1) * 128 + r];
+      const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (t > 0) {
+        const long long blkp = blk_of(t - 1);
+        dst[10] = c4[(blkp * 32 + uq) * 128 + r];
+        dst[11] = c4[(blkp * 32 + uq + 1) * 128 + r];
+      } else {
+        dst[10] = zero; dst[11] = zero;
+      }
+      if (a.ext_last_only) {
+        if (t == T - 1 && valid) {
+          const float4* p = reinterpret_cast<const float4*>(a.ext + ((long long)z * a.Nn + node) * L + u0 + 8 * c);
+          dst[12] = p[0]; dst[13] = p[1];
+        } else {
+          dst[12] = zero; dst[13] = zero;
+        }
+      } else {
+        dst[12] = e4[(blk * 32 + uq) * 128 + r];
+        dst[13] = e4[(blk * 32 + uq + 1) * 128 + r];
+      }
+    };
+    load_chunk(T - 1, 0, ld[0]);
+
+    for (int s = 0; s < T; ++s) {
+      const int t = T - 1 - s;
+      const int xb = s & 1;
+      if (s > 0) {
+        if (warp == 0) {  // MMA issue: partial dh[128 x 128] = dG[t+1][:, my gate rows] W_hh[my gate rows, :]
+          if (ok && s == 1 && !mbar_wait(&wfull, 0)) { ok = false; if (lane == 0) atomicExch(a.err, 21); }
+          if (ok && !mbar_wait(&a_ready, (s - 1) & 1)) { ok = false; if (lane == 0) atomicExch(a.err, 22); }
+          tc_fence_after();
+          if (lane == 0 && ok) {
+            const uint32_t idesc = idesc_16(128, 1);
+            uint32_t accf = 0;
+#pragma unroll
+            for (int p = 0; p < 3; ++p) {  // dG_hi W_hi, dG_lo W_hi, dG_hi W_lo
+              const uint32_t ac = tbase + (p == 1 ? A_LO : A_HI), bs = smem_u32(p == 2 ? b_lo : b_hi);
+#pragma unroll
+              for (int kb = 0; kb < 4; ++kb)
+#pragma unroll
+                for (int k16 = 0; k16 < 4; ++k16) {
+                  umma_ts_16(tbase, ac + kb * 32 + k16 * 8, umma_desc_k_sw128(bs + kb * 16384 + k16 * 32), idesc, accf);
+                  accf = 1;
+                }
+            }
+            umma_commit(&dfull);
+          }
+          __syncwarp();
+        }
+        if (ok && !mbar_wait(&dfull, (s - 1) & 1)) { ok = false; if (lane == 0) atomicExch(a.err, 23); }
+        tc_fence_after();
+        // ---- the partial dh of the peer's units -> peer (same (row, half, quad) slot the peer's twin thread reads)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          uint32_t v[8];
+          __syncwarp();
+          tmem_ld8(tlane + 64 * peer + ub + 8 * c, v);
+          tmem_wait_ld();
+          const uint32_t dst = xbuf_remote + (uint32_t)xb * 32768u + (uint32_t)(((half * 8 + 2 * c) * 128 + r) * 16);
+          st_cluster_v4(dst, make_uint4(v[0], v[1], v[2], v[3]));
+          st_cluster_v4(dst + 2048u, make_uint4(v[4], v[5], v[6], v[7]));
+        }
+        __syncwarp();
+        if (lane == 0) arrive_cluster(xb ? xr_remote1 : xr_remote0);
+        if (ok && !mbar_wait_cl(&x_ready[xb], ((s - 1) >> 1) & 1)) { ok = false; if (lane == 0) atomicExch(a.err, 24); }
+      }
+      const long long blk = blk_of(t);
+      const long long tcol = (long long)t * a.Np + node;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        // prefetch the next chunk (possibly of the next step) while this one is processed
+        {
+          const int cn = (c + 1) & 3, sn = s + ((c + 1) >> 2);
+          if (sn < T) load_chunk(T - 1 - sn, cn, ld[(c + 1) & 1]);
+        }
+        float dh[8];
+        if (s > 0) {
+          uint32_t v[8];
+          __syncwarp();
+          tmem_ld8(tlane + 64 * rank + ub + 8 * c, v);
+          tmem_wait_ld();
+          const uint8_t* src = xbuf + xb * 32768 + ((half * 8 + 2 * c) * 128 + r) * 16;
+          const float4 p0 = *reinterpret_cast<const float4*>(src), p1 = *reinterpret_cast<const float4*>(src + 2048);
+          dh[0] = __uint_as_float(v[0]) + p0.x; dh[1] = __uint_as_float(v[1]) + p0.y;
+          dh[2] = __uint_as_float(v[2]) + p0.z; dh[3] = __uint_as_float(v[3]) + p0.w;
+          dh[4] = __uint_as_float(v[4]) + p1.x; dh[5] = __uint_as_float(v[5]) + p1.y;
+          dh[6] = __uint_as_float(v[6]) + p1.z; dh[7] = __uint_as_float(v[7]) + p1.w;
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) dh[j] = 0.f;
+        }
+        const float4* x = ld[c & 1];
+        float di[8], df[8], dg[8], dO[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int hsel = j >> 2, cmp = j & 3;
+          auto pick = [&](const float4& v4) { return cmp == 0 ? v4.x : cmp == 1 ? v4.y : cmp == 2 ? v4.z : v4.w; };
+          const float vi = pick(x[0 + hsel]), vf = pick(x[2 + hsel]), vg = pick(x[4 + hsel]), vo = pick(x[6 + hsel]);
+          const float vc = pick(x[8 + hsel]), vp = pick(x[10 + hsel]), ve = pick(x[12 + hsel]);
+          const float dhj = (dh[j] + ve) * vm;
+          const float tc = fast_tanh(vc);
+          const float dc = dcs[8 * c + j] + dhj * vo * (1.f - tc * tc);
+          dO[j] = dhj * tc * vo * (1.f - vo);
+          di[j] = dc * vg * vi * (1.f - vi);
+          df[j] = dc * vp * vf * (1.f - vf);
+          dg[j] = dc * vi * (1.f - vg * vg);
+          dcs[8 * c + j] = dc * vf;
+        }
+        const int uq = (u0 + 8 * c) >> 2;
+#pragma unroll
+        for (int hsel = 0; hsel < 2; ++hsel) {
+          const int j = 4 * hsel;
+          xg4[(blk * 128 + 0 * 32 + uq + hsel) * 128 + r] = make_float4(di[j], di[j + 1], di[j + 2], di[j + 3]);
+          xg4[(blk * 128 + 1 * 32 + uq + hsel) * 128 + r] = make_float4(df[j], df[j + 1], df[j + 2], df[j + 3]);
+          xg4[(blk * 128 + 2 * 32 + uq + hsel) * 128 + r] = make_float4(dg[j], dg[j + 1], dg[j + 2], dg[j + 3]);
+          xg4[(blk * 128 + 3 * 32 + uq + hsel) * 128 + r] = make_float4(dO[j], dO[j + 1], dO[j + 2], dO[j + 3]);
+        }
+        if (valid) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float* base = a.DGT + ((long long)z * 4 * L + u0 + 8 * c + j) * a.RT + tcol;
+            base[0] = di[j];
+            base[(long long)L * a.RT] = df[j];
+            base[2LL * L * a.RT] = dg[j];
+            base[3LL * L * a.RT] = dO[j];
+          }
+        }
+        if (s + 1 < T) {
+          // dG[t] as bf16 hi/lo -> TMEM A operand of the next step: k = gate*64 + (ub + 8c + j), two k per column
+          const float* gsrc[4] = {di, df, dg, dO};
+#pragma unroll
+          for (int gate = 0; gate < 4; ++gate) {
+            uint32_t hi[4], lo[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              float ra, rb, d0, d1;
+              hi[i] = pack_bf16(gsrc[gate][2 * i], gsrc[gate][2 * i + 1], ra, rb);
+              lo[i] = pack_bf16(ra, rb, d0, d1);
+            }
+            const uint32_t col = (uint32_t)((gate * 64 + ub + 8 * c) >> 1);
+            tmem_st4(tlane + A_HI + col, hi);
+            tmem_st4(tlane + A_LO + col, lo);
+          }
+        }
+      }
+      if (s + 1 < T) {
+        tmem_wait_st();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&a_ready);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tbase, 512);
+  cluster_sync_all();
+}
+
+// ================================================================================= helpers
+// W_hh [4L, L] fp32 of every (task, layer) -> the operand copies the two kernels keep in shared memory:
+//   f16_hi / f16_lo [G][layers][4L][L]            (forward: rows = gate rows, K = hidden units)
+//   b16_hi / b16_lo [G][layers][2][L][2L]         (backward: per CTA rank, rows = hidden units n,
+//                                                  K = gate*64 + (unit - 64*rank) over the rank's own gate rows)
+__global__ void wf_prep_seq_kernel(const float* __restrict__ params, long long gstride, LstmLayout P, int layers, int L,
+                                   __half* __restrict__ f_hi, __half* __restrict__ f_lo, __nv_bfloat16* __restrict__ b_hi,
+                                   __nv_bfloat16* __restrict__ b_lo) {
+  const int g = blockIdx.z, l = blockIdx.y;
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;  // over [4L][L]
+  if (idx >= 4 * L * L) return;
+  const int j = idx / L, n = idx - j * L;
+  const float v = params[g * gstride + P.w_hh[l] + idx];
+  const long long slab = (long long)g * layers + l;
+  const __half h = __float2half_rn(v);
+  f_hi[slab * 4 * L * L + idx] = h;
+  f_lo[slab * 4 * L * L + idx] = __float2half_rn(v - __half2float(h));
+  const int gate = j / L, u = j - gate * L, rk = u >> 6, ul = u & 63;
+  const long long o = ((slab * 2 + rk) * L + n) * (2 * L) + gate * 64 + ul;
+  const __nv_bfloat16 b = __float2bfloat16_rn(v);
+  b_hi[o] = b;
+  b_lo[o] = __float2bfloat16_rn(v - __bfloat162float(b));
+}
+
+// Column sums of a TB4 buffer over all blocks of a group: out1[g][c] = out2[g][c] = sum over (window, step,
+// node) of X[.., c]  (the LSTM bias gradients: db_ih = db_hh = sum dG).  grid (C/4, G), 128 threads.
+__global__ void __launch_bounds__(128) wf_colsum_tb4_kernel(const float4* __restrict__ X, int C4, int blocks_g, float* out1,
+                                                            float* out2, long long out_gstride) {
+  const int cg = blockIdx.x, g = blockIdx.y, r = threadIdx.x;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int b = 0; b < blocks_g; ++b) {
+    const float4 v = X[(((long long)g * blocks_g + b) * C4 + cg) * 128 + r];
+    acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+  }
+  __shared__ float4 sh[4];
+  acc.x = warp_sum(acc.x); acc.y = warp_sum(acc.y); acc.z = warp_sum(acc.z); acc.w = warp_sum(acc.w);
+  if ((r & 31) == 0) sh[r >> 5] = acc;
+  __syncthreads();
+  if (r == 0) {
+    float4 t = sh[0];
+    for (int i = 1; i < 4; ++i) { t.x += sh[i].x; t.y += sh[i].y; t.z += sh[i].z; t.w += sh[i].w; }
+    float* o1 = out1 + g * out_gstride + cg * 4;
+    o1[0] = t.x; o1[1] = t.y; o1[2] = t.z; o1[3] = t.w;
+    if (out2) {
+      float* o2 = out2 + g * out_gstride + cg * 4;
+      o2[0] = t.x; o2[1] = t.y; o2[2] = t.z; o2[3] = t.w;
+    }
+  }
+}
+
+int seq_maps_fwd(CUtensorMap* hi, CUtensorMap* lo, const void* f_hi, const void* f_lo, int L, int slabs) {
+  uint64_t dims[4] = {(uint64_t)L, (uint64_t)L, 4, (uint64_t)slabs};
+  uint64_t str[3] = {(uint64_t)L * 2, (uint64_t)L * L * 2, (uint64_t)4 * L * L * 2};
+  uint32_t box[4] = {64, 64, 4, 1};
+  int rc = wf_encode_tensor_map(hi, f_hi, 4, dims, str, box, 1, 1);
+  if (rc) return rc;
+  return wf_encode_tensor_map(lo, f_lo, 4, dims, str, box, 1, 1);
+}
+int seq_maps_bwd(CUtensorMap* hi, CUtensorMap* lo, const void* b_hi, const void* b_lo, int L, int slabs) {
+  uint64_t dims[3] = {(uint64_t)2 * L, (uint64_t)L, (uint64_t)slabs * 2};
+  uint64_t str[2] = {(uint64_t)2 * L * 2, (uint64_t)L * 2 * L * 2};
+  uint32_t box[3] = {64, 128, 1};
+  int rc = wf_encode_tensor_map(hi, b_hi, 3, dims, str, box, 1, 2);
+  if (rc) return rc;
+  return wf_encode_tensor_map(lo, b_lo, 3, dims, str, box, 1, 2);
+}
+
+template <typename K>
+int seq_configure(K kernel) {
+  if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SEQ_SMEM) != cudaSuccess)
+    return wf_fail(WF_ECUDA, "lstm_seq: cannot raise dynamic shared memory to %d", SEQ_SMEM);
+  return WF_OK;
+}
+
+}  // namespace
+
+// Elements of a TB4 buffer with `channels` per (window, step, node): windows*T*ceil(N/128) blocks of channels*128.
+extern "C" long long wf_tb4_elems(int channels, int T, int N, long long windows) {
+  return windows * T * wf_cdiv(N, 128) * (long long)channels * 128;
+}
+
+// Elements (16-bit each) of ONE of the four recurrent-operand buffers written by wf_prep_weights_seq.
+extern "C" long long wf_seq_weight_elems(int layers, int L, int G) { return (long long)G * layers * 4 * L * L; }
+
+extern "C" int wf_prep_weights_seq(const float* params, long long params_group_stride, int layers, int F, int L, int O,
+                                   int G, void* f16_hi, void* f16_lo, void* bf16_hi, void* bf16_lo, void* stream) {
+  WF_REQUIRE(layers >= 1 && layers <= 8 && L == 128 && G > 0, "prep_weights_seq: needs L == 128");
+  const LstmLayout P = lstm_layout(layers, F, L, O);
+  dim3 grid(wf_cdiv(4 * L * L, 256), layers, G);
+  wf_prep_seq_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(params, params_group_stride, P, layers, L, (__half*)f16_hi,
+                                                             (__half*)f16_lo, (__nv_bfloat16*)bf16_hi, (__nv_bfloat16*)bf16_lo);
+  WF_CHECK_LAUNCH("prep_weights_seq");
+  return WF_OK;
+}
+
+// nn.LSTM forward (hybrid_model.py:42-49, 93-105) with one persistent launch per layer.
+//   x [G*Bw*T*N, F] row-major; params / params_lo: flat fp32 weights and their TF32 lo halves (input projections);
+//   f16_hi / f16_lo from wf_prep_weights_seq; gates TB4 [layers][4L ch], c TB4 [layers][L ch],
+//   h [layers][G*Bw*T*N, L] row-major, hT / hT_lo optional transposed copies (training).
+extern "C" int wf_lstm_fwd_seq(const float* x, const float* params, const float* params_lo, long long params_group_stride,
+                               const void* f16_hi, const void* f16_lo, int layers, int F, int L, int O, int T, int N,
+                               int G, int Bw, float* gates, float* h, float* c, float* hT, float* hT_lo, int* err,
+                               void* stream) {
+  WF_REQUIRE(layers >= 1 && layers <= 8 && L == 128 && F % 32 == 0, "lstm_fwd_seq: needs L == 128, F %% 32 == 0");
+  WF_REQUIRE(T > 0 && N > 0 && G > 0 && Bw > 0, "lstm_fwd_seq: empty batch");
+  cudaStream_t st = (cudaStream_t)stream;
+  static bool configured = false;
+  if (!configured) { int rc = seq_configure(wf_lstm_seq_fwd_kernel); if (rc) return rc; configured = true; }
+  const LstmLayout P = lstm_layout(layers, F, L, O);
+  const long long Z = (long long)G * Bw, rows = Z * T * N;
+  const int tpw = wf_cdiv(N, 128), Np = (N + 3) & ~3, RT = T * Np;
+  const long long g_elems = wf_tb4_elems(4 * L, T, N, Z), c_elems = wf_tb4_elems(L, T, N, Z);
+  const long long tsz = Z * L * RT;
+  CUtensorMap tmhi, tmlo;
+  int rc = seq_maps_fwd(&tmhi, &tmlo, f16_hi, f16_lo, L, G * layers);
+  if (rc) return rc;
+  for (int l = 0; l < layers; ++l) {
+    const int kin = l == 0 ? F : L;
+    float* XG = gates + l * g_elems;
+    const float* Xl = l == 0 ? x : h + (long long)(l - 1) * rows * L;
+    rc = wf_launch_tc_nodes(Xl, 0, kin, params + P.w_ih[l], params_lo + P.w_ih[l], kin, params_group_stride, 4 * L,
+                            params + P.b_ih[l], params + P.b_hh[l], params_group_stride, XG, T, N, Bw, G, err, st);
+    if (rc) return rc;
+    SeqArgs a;
+    memset(&a, 0, sizeof(a));
+    a.XG = XG; a.Cst = c + l * c_elems; a.H = h + (long long)l * rows * L;
+    a.HT = hT ? hT + l * tsz : nullptr; a.HT_lo = hT ? hT_lo + l * tsz : nullptr;
+    a.T = T; a.Nn = N; a.Bw = Bw; a.tpw = tpw; a.Np = Np; a.RT = RT;
+    a.slab0 = l; a.slab_g = layers; a.err = err;
+    wf_lstm_seq_fwd_kernel<<<dim3((unsigned)(2 * Z * tpw)), SEQ_THREADS, SEQ_SMEM, st>>>(tmhi, tmlo, a);
+    WF_CHECK_LAUNCH("lstm_seq_fwd");
+  }
+  return WF_OK;
+}
+
+extern "C" size_t wf_lstm_bwd_seq_workspace_bytes(int layers, int F, int L, int T, int N, int G, int Bw) {
+  (void)layers; (void)F;
+  return sizeof(float) * (size_t)wf_tb4_elems(L, T, N, (long long)G * Bw) + 256;
+}
+
+// BPTT (train_hybrid_maml_v5.py:134,169) with one persistent launch per layer.  gates / c from wf_lstm_fwd_seq
+// (gates are overwritten by dG); xT / xT_lo, hT / hT_lo, dgT as wf_lstm_bwd_tc; paramsT / paramsT_lo from
+// wf_prep_weights_tc (W_ih^T for dX); bf16_hi / bf16_lo from wf_prep_weights_seq; dlast [G*Bw*N, L].
+extern "C" int wf_lstm_bwd_seq(const float* xT, const float* xT_lo, const float* paramsT, const float* paramsT_lo,
+                               const void* bf16_hi, const void* bf16_lo, int layers, int F, int L, int O, int T, int N,
+                               int G, int Bw, float* gates, const float* c, const float* hT, const float* hT_lo,
+                               float* dgT, const float* dlast, float* grads, long long grads_group_stride, void* workspace,
+                               size_t workspace_bytes, int* err, void* stream) {
+  WF_REQUIRE(layers >= 1 && layers <= 8 && L == 128 && F % 128 == 0, "lstm_bwd_seq: needs L == 128 and F %% 128 == 0");
+  if (workspace_bytes < wf_lstm_bwd_seq_workspace_bytes(layers, F, L, T, N, G, Bw))
+    return wf_fail(WF_EWORKSPACE, "lstm_bwd_seq: workspace too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  static bool configured = false;
+  if (!configured) { int rc = seq_configure(wf_lstm_seq_bwd_kernel); if (rc) return rc; configured = true; }
+  const LstmLayout P = lstm_layout(layers, F, L, O);
+  const long long Z = (long long)G * Bw;
+  const int tpw = wf_cdiv(N, 128), Np = (N + 3) & ~3, RT = T * Np;
+  const long long g_elems = wf_tb4_elems(4 * L, T, N, Z), c_elems = wf_tb4_elems(L, T, N, Z);
+  const long long tsz = Z * L * RT;
+  float* DX = (float*)workspace;
+  CUtensorMap tmhi, tmlo;
+  int rc = seq_maps_bwd(&tmhi, &tmlo, bf16_hi, bf16_lo, L, G * layers);
+  if (rc) return rc;
+  for (int l = layers - 1; l >= 0; --l) {
+    const int kin = l == 0 ? F : L;
+    float* XG = gates + l * g_elems;
+    const float* HT = hT + l * tsz;
+    const float* HTlo = hT_lo + l * tsz;
+    const float* XT = l == 0 ? xT : hT + (l - 1) * tsz;
+    const float* XTlo = l == 0 ? xT_lo : hT_lo + (l - 1) * tsz;
+    SeqArgs a;
+    memset(&a, 0, sizeof(a));
+    a.XG = XG; a.Cst = const_cast<float*>(c) + l * c_elems; a.DGT = dgT;
+    a.ext = l == layers - 1 ? dlast : DX; a.ext_last_only = l == layers - 1 ? 1 : 0;
+    a.T = T; a.Nn = N; a.Bw = Bw; a.tpw = tpw; a.Np = Np; a.RT = RT;
+    a.slab0 = 2 * l; a.slab_g = 2 * layers; a.err = err;
+    wf_lstm_seq_bwd_kernel<<<dim3((unsigned)(2 * Z * tpw)), SEQ_THREADS, SEQ_SMEM, st>>>(tmhi, tmlo, a);
+    WF_CHECK_LAUNCH("lstm_seq_bwd");
+    wf_colsum_tb4_kernel<<<dim3(L, G), 128, 0, st>>>(reinterpret_cast<const float4*>(XG), L, Bw * T * tpw, grads + P.b_ih[l],
+                                                     grads + P.b_hh[l], grads_group_stride);
+    WF_CHECK_LAUNCH("colsum_tb4");
+    rc = wf_launch_tc_wgrad(dgT, 4 * L, XT, XTlo, kin, RT, Bw, G, 0, 0, RT, grads + P.w_ih[l], grads_group_stride, err, st);
+    if (rc) return rc;
+    if (T > 1) {
+      rc = wf_launch_tc_wgrad(dgT, 4 * L, HT, HTlo, L, RT, Bw, G, Np, 0, RT - Np, grads + P.w_hh[l], grads_group_stride, err, st);
+      if (rc) return rc;
+    } else {
+      for (int g = 0; g < G; ++g)
+        cudaMemsetAsync(grads + g * grads_group_stride + P.w_hh[l], 0, sizeof(float) * 4 * L * L, st);
+    }
+    if (l > 0) {  // dL/d(input of layer l) = dG W_ih -> ext of layer l-1 (TB4 in, TB4 out)
+      rc = wf_launch_tc_nodes(XG, 1, 4 * L, paramsT + P.wihT[l], paramsT_lo + P.wihT[l], 4 * L, P.totalT, L, nullptr, nullptr,
+                              0, DX, T, N, Bw, G, err, st);
+      if (rc) return rc;
+    }
+  }
+  return WF_OK;
+}

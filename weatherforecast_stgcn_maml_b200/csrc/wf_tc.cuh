@@ -102,6 +102,48 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* v) {
                : "r"(taddr) : "memory");
 }
 
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t* v) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];\n"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+               : "r"(taddr) : "memory");
+}
+
+// ---- per-warp staging blocks: 32 rows x 32 fp32 (128 B per row), 16-byte chunks XOR-swizzled by
+// (row & 7).  They turn the epilogue's "thread = row" view (what tcgen05.ld gives) into coalesced
+// global traffic: global <-> block moves touch 4 full 128-byte lines per warp instruction, the
+// thread = row side reads/writes its own row without bank conflicts.
+__device__ __forceinline__ uint32_t stg_off(int r, int ch) { return (uint32_t)(r * 128 + ((ch ^ (r & 7)) << 4)); }
+
+// global rows [0, nvalid) x 32 floats -> block, asynchronously (cp.async, no registers held)
+__device__ __forceinline__ void blk_load_async(uint8_t* stage, const float* g, long long ld, int nvalid, int lane) {
+#pragma unroll
+  for (int it = 0; it < 8; ++it) {
+    const int r = it * 4 + (lane >> 3), ch = lane & 7;
+    const int rc = r < nvalid ? r : (nvalid > 0 ? nvalid - 1 : 0);
+    const float* src = g + (long long)rc * ld + ch * 4;
+    const uint32_t bytes = r < nvalid ? 16u : 0u;  // src-size 0: destination is zero-filled
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(smem_u32(stage) + stg_off(r, ch)), "l"(src), "r"(bytes) : "memory");
+  }
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+  asm volatile("cp.async.commit_group;\n" ::: "memory");
+  asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+}
+// block -> global rows [0, nvalid) x 32 floats, 4 full lines per warp instruction
+__device__ __forceinline__ void blk_store(const uint8_t* stage, float* g, long long ld, int nvalid, int lane) {
+#pragma unroll
+  for (int it = 0; it < 8; ++it) {
+    const int r = it * 4 + (lane >> 3), ch = lane & 7;
+    if (r < nvalid) *reinterpret_cast<float4*>(g + (long long)r * ld + ch * 4) = *reinterpret_cast<const float4*>(stage + stg_off(r, ch));
+  }
+}
+__device__ __forceinline__ float4 row_ld(const uint8_t* stage, int lane, int ch) {
+  return *reinterpret_cast<const float4*>(stage + stg_off(lane, ch));
+}
+__device__ __forceinline__ void row_st(uint8_t* stage, int lane, int ch, float4 v) {
+  *reinterpret_cast<float4*>(stage + stg_off(lane, ch)) = v;
+}
+
 // ---- UMMA ----------------------------------------------------------------------------------
 // Shared-memory matrix descriptor, K-major, SWIZZLE_128B, 8-row atoms 1024 B apart.
 __device__ __forceinline__ uint64_t umma_desc_k_sw128(uint32_t saddr) {
@@ -134,5 +176,6 @@ __device__ __forceinline__ void split_tf32(float v, uint32_t& hi, uint32_t& lo) 
 }  // namespace wftc
 
 // Host side: encode a tiled tensor map without linking libcuda (driver entry point lookup).
+// dtype: 0 = f32, 1 = f16, 2 = bf16 (dims and box in elements, strides in bytes).
 int wf_encode_tensor_map(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                         const uint32_t* box, int swizzle_128b);
+                         const uint32_t* box, int swizzle_128b, int dtype = 0);

@@ -88,7 +88,7 @@ class HybridEngine:
     on the exact FP32 CUDA-core kernels (also the route for other shapes)."""
 
     def __init__(self, dims: V5Dims, G: int, Bw: int, device="cuda", keep_gcn_activations=False, precision="tf32x3",
-                 training=True):
+                 training=True, lstm_mode="persistent"):
         self.dims, self.G, self.Bw = dims, int(G), int(Bw)
         self.device = torch.device(device)
         if self.device.type != "cuda":
@@ -98,6 +98,11 @@ class HybridEngine:
         _lib.load()
         d = dims
         self.tc = precision == "tf32x3" and d.lstm_hidden == 128 and d.hidden % 128 == 0
+        if lstm_mode not in ("persistent", "stepwise"):
+            raise ValueError("lstm_mode must be 'persistent' or 'stepwise'")
+        # persistent: one cluster launch per LSTM layer runs all T steps (csrc/wf_lstm_seq.cu);
+        # stepwise: one tensor-core launch per (layer, step) (csrc/wf_tc_gemm.cu), kept as a cross-check
+        self.seq = self.tc and lstm_mode == "persistent"
         self.training = bool(training)
         self.rows = self.G * self.Bw * d.R
         self.W = self.G * self.Bw
@@ -106,9 +111,13 @@ class HybridEngine:
         self.act = [torch.empty(self.rows, d.hidden, **f32) for _ in range(n_act)]
         self.keep_gcn = keep_gcn_activations
         Ls, L = d.lstm_layers, d.lstm_hidden
-        self.gates = torch.empty(Ls, self.rows, 4 * L, **f32)
+        if self.seq:  # gates / cell state in the tile-blocked TB4 layout (padded to 128-node tiles)
+            self.gates = torch.empty(Ls, int(_lib.query("wf_tb4_elems", 4 * L, d.window, d.num_nodes, self.G * self.Bw)), **f32)
+            self.c = torch.empty(Ls, int(_lib.query("wf_tb4_elems", L, d.window, d.num_nodes, self.G * self.Bw)), **f32)
+        else:
+            self.gates = torch.empty(Ls, self.rows, 4 * L, **f32)
+            self.c = torch.empty(Ls, self.rows, L, **f32)
         self.h = torch.empty(Ls, self.rows, L, **f32)
-        self.c = torch.empty(Ls, self.rows, L, **f32)
         self.pred = torch.empty(self.W * d.num_nodes, d.O, **f32)
         self.dpred = torch.empty(self.W * d.num_nodes, d.O, **f32)
         self.loss = torch.zeros(self.W, **f32)
@@ -123,6 +132,11 @@ class HybridEngine:
         if self.tc:
             ws = max(ws, _lib.query("wf_lstm_bwd_tc_workspace_bytes", Ls, d.hidden, L, d.window, d.num_nodes, self.G,
                                     self.Bw))
+            if self.seq:
+                ws = max(ws, _lib.query("wf_lstm_bwd_seq_workspace_bytes", Ls, d.hidden, L, d.window, d.num_nodes, self.G,
+                                        self.Bw))
+                nw = int(_lib.query("wf_seq_weight_elems", Ls, L, self.G))
+                self.w16 = [torch.empty(nw, dtype=torch.int16, device=self.device) for _ in range(4)]
             self.PT = int(_lib.query("wf_param_count_transposed", Ls, d.hidden, L, d.O))
             self.params_lo = torch.empty(self.G, self.P, **f32)
             self.paramsT = torch.empty(self.G, self.PT, **f32)
@@ -203,16 +217,26 @@ class HybridEngine:
             src_stride = params_stride if self.G > 1 else self.P
             _lib.call("wf_prep_weights_tc", _lib.ptr(params), src_stride, Ls, d.hidden, L, d.O, self.G,
                       _lib.ptr(self.params_lo), _lib.ptr(self.paramsT), _lib.ptr(self.paramsT_lo), st)
-            _lib.call("wf_lstm_fwd_tc", _lib.ptr(feats), _lib.ptr(params), _lib.ptr(self.params_lo), params_stride, Ls,
-                      d.hidden, L, d.O, d.window, d.num_nodes, self.G, self.Bw, _lib.ptr(self.gates), _lib.ptr(self.h),
-                      _lib.ptr(self.c), _lib.ptr(self.hT), _lib.ptr(self.hT_lo), _lib.ptr(self.err), st)
-            self.launches += 2 * Ls
+            if self.seq:
+                _lib.call("wf_prep_weights_seq", _lib.ptr(params), src_stride, Ls, d.hidden, L, d.O, self.G,
+                          _lib.ptr(self.w16[0]), _lib.ptr(self.w16[1]), _lib.ptr(self.w16[2]), _lib.ptr(self.w16[3]), st)
+                _lib.call("wf_lstm_fwd_seq", _lib.ptr(feats), _lib.ptr(params), _lib.ptr(self.params_lo), params_stride,
+                          _lib.ptr(self.w16[0]), _lib.ptr(self.w16[1]), Ls, d.hidden, L, d.O, d.window, d.num_nodes,
+                          self.G, self.Bw, _lib.ptr(self.gates), _lib.ptr(self.h), _lib.ptr(self.c), _lib.ptr(self.hT),
+                          _lib.ptr(self.hT_lo), _lib.ptr(self.err), st)
+                self.launches += 2 * Ls + 1 + 2 * Ls  # operand staging, then (projection + recurrence) per layer
+            else:
+                _lib.call("wf_lstm_fwd_tc", _lib.ptr(feats), _lib.ptr(params), _lib.ptr(self.params_lo), params_stride, Ls,
+                          d.hidden, L, d.O, d.window, d.num_nodes, self.G, self.Bw, _lib.ptr(self.gates), _lib.ptr(self.h),
+                          _lib.ptr(self.c), _lib.ptr(self.hT), _lib.ptr(self.hT_lo), _lib.ptr(self.err), st)
+                self.launches += 2 * Ls + Ls * (1 + d.window)
         else:
             _lib.call("wf_lstm_fwd", _lib.ptr(feats), _lib.ptr(params), params_stride, Ls, d.hidden, L, d.O, d.window,
                       d.num_nodes, self.G, self.Bw, _lib.ptr(self.gates), _lib.ptr(self.h), _lib.ptr(self.c), st)
+            self.launches += Ls * (1 + d.window)
         _lib.call("wf_head_fwd", _lib.ptr(self.h[Ls - 1]), _lib.ptr(params), params_stride, Ls, d.hidden, L, d.O,
                   d.window, d.num_nodes, self.G, self.Bw, _lib.ptr(self.pred), st)
-        self.launches += Ls * (1 + d.window) + 1
+        self.launches += 1
         return self.pred
 
     def mse(self, y=None, feat=None, tgt_off=None, feat_ld=0, grad_scale=1.0, want_grad=True):
@@ -236,12 +260,20 @@ class HybridEngine:
         if self.tc:
             if not self.training:
                 raise RuntimeError("engine was built with training=False")
-            _lib.call("wf_lstm_bwd_tc", _lib.ptr(self.featsT), _lib.ptr(self.featsT_lo), _lib.ptr(self.paramsT),
-                      _lib.ptr(self.paramsT_lo), Ls, d.hidden, L, d.O, d.window, d.num_nodes, self.G, self.Bw,
-                      _lib.ptr(self.gates), _lib.ptr(self.c), _lib.ptr(self.hT), _lib.ptr(self.hT_lo),
-                      _lib.ptr(self.dgT), _lib.ptr(self.dlast), _lib.ptr(self.grads), self.P, _lib.ptr(self.ws),
-                      self.ws_bytes, _lib.ptr(self.err), st)
-            self.launches += 6 + Ls * (d.window + 5)
+            if self.seq:
+                _lib.call("wf_lstm_bwd_seq", _lib.ptr(self.featsT), _lib.ptr(self.featsT_lo), _lib.ptr(self.paramsT),
+                          _lib.ptr(self.paramsT_lo), _lib.ptr(self.w16[2]), _lib.ptr(self.w16[3]), Ls, d.hidden, L, d.O,
+                          d.window, d.num_nodes, self.G, self.Bw, _lib.ptr(self.gates), _lib.ptr(self.c), _lib.ptr(self.hT),
+                          _lib.ptr(self.hT_lo), _lib.ptr(self.dgT), _lib.ptr(self.dlast), _lib.ptr(self.grads), self.P,
+                          _lib.ptr(self.ws), self.ws_bytes, _lib.ptr(self.err), st)
+                self.launches += 6 + Ls * 5 - 1  # head bwd + per layer: recurrence, colsum, 2 wgrad, dX (layers >= 1)
+            else:
+                _lib.call("wf_lstm_bwd_tc", _lib.ptr(self.featsT), _lib.ptr(self.featsT_lo), _lib.ptr(self.paramsT),
+                          _lib.ptr(self.paramsT_lo), Ls, d.hidden, L, d.O, d.window, d.num_nodes, self.G, self.Bw,
+                          _lib.ptr(self.gates), _lib.ptr(self.c), _lib.ptr(self.hT), _lib.ptr(self.hT_lo),
+                          _lib.ptr(self.dgT), _lib.ptr(self.dlast), _lib.ptr(self.grads), self.P, _lib.ptr(self.ws),
+                          self.ws_bytes, _lib.ptr(self.err), st)
+                self.launches += 6 + Ls * (d.window + 5)
         else:
             _lib.call("wf_lstm_bwd", _lib.ptr(feats), _lib.ptr(params), params_stride, Ls, d.hidden, L, d.O, d.window,
                       d.num_nodes, self.G, self.Bw, _lib.ptr(self.gates), _lib.ptr(self.h), _lib.ptr(self.c),
