@@ -35,7 +35,8 @@ int wf_launch_tc_nodes(const float* A, int a_tb4, int K, const float* Whi, const
                        int N, const float* bias, const float* bias2, long long bias_gstride, float* C, int T, int Nn, int Bw,
                        int G, int* err, cudaStream_t st);
 int wf_launch_tc_wgrad(const float* AT, int M, const float* BT, const float* BT_lo, int N, int R, int Bw, int G,
-                       int a_k0, int b_k0, int klen, float* dW, long long dw_gstride, int* err, cudaStream_t st);
+                       int a_k0, int b_k0, int klen, float* dW, long long dw_gstride, int* err, cudaStream_t st,
+                       float* partials, size_t partial_floats);
 
 namespace {
 
@@ -77,6 +78,11 @@ __device__ __forceinline__ void st_cluster_v4(uint32_t caddr, uint4 v) {
 __device__ __forceinline__ void arrive_cluster(uint32_t cbar) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];\n" ::"r"(cbar) : "memory");
 }
+// no data is published with this arrival (it only says "my tensor core is done reading"): no memory barrier
+__device__ __forceinline__ void arrive_cluster_relaxed(uint32_t cbar) {
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];\n" ::"r"(cbar) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_cta() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
 // bounded wait with cluster-scope acquire (the barrier receives arrivals from the peer CTA)
 __device__ __forceinline__ bool mbar_wait_cl(uint64_t* bar, uint32_t parity) {
   for (uint32_t spin = 0; spin < (1u << 18); ++spin) {
@@ -87,7 +93,9 @@ __device__ __forceinline__ bool mbar_wait_cl(uint64_t* bar, uint32_t parity) {
   }
   return false;
 }
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;\n" ::: "memory"); }
+// generic-proxy writes to (distributed) shared memory -> visible to the async proxy (tensor core operand reads);
+// the unqualified form also fences global memory (MEMBAR.ALL.GPU: waits for every outstanding global store)
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cluster;\n" ::: "memory"); }
 
 // kind::f16 instruction descriptor: D = F32, A/B = fmt (0 F16, 1 BF16), both K-major, M = 128
 __host__ __device__ constexpr uint32_t idesc_16(int n, uint32_t fmt) {
@@ -175,7 +183,7 @@ wf_lstm_seq_fwd_kernel(const __grid_constant__ CUtensorMap tmWhi, const __grid_c
     float4* const xg4 = reinterpret_cast<float4*>(a.XG);
     float4* const c4 = reinterpret_cast<float4*>(a.Cst);
     const uint32_t pd_remote = mapa_u32(smem_u32(&peer_done), peer);
-    const uint32_t ar_local = smem_u32(&a_ready), ar_remote = mapa_u32(smem_u32(&a_ready), peer);
+    const uint32_t ar_remote = mapa_u32(smem_u32(&a_ready), peer);
     bool ok = true;
 
     float cst[32];
@@ -196,13 +204,25 @@ wf_lstm_seq_fwd_kernel(const __grid_constant__ CUtensorMap tmWhi, const __grid_c
     };
     load_chunk(0, 0, xq[0]);
     load_chunk(0, 1, xq[1]);
+    uint32_t acc[2][4][8];  // recurrent pre-activations of the current / next chunk (TMEM loads run one chunk ahead)
+#pragma unroll
+    for (int b = 0; b < 2; ++b)
+#pragma unroll
+      for (int gate = 0; gate < 4; ++gate)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[b][gate][j] = 0u;
+    auto issue_acc = [&](int c, uint32_t (*dst)[8]) {
+      __syncwarp();
+#pragma unroll
+      for (int gate = 0; gate < 4; ++gate) tmem_ld8(tlane + gate * 64 + ub + 8 * c, dst[gate]);
+    };
 
     for (int t = 0; t < T; ++t) {
       if (t > 0) {
         if (warp == 0) {  // MMA issue: D[128 x 256] = h[t-1] W_hh^T for this CTA's 64 units x 4 gates
           if (ok && t == 1 && !mbar_wait(&wfull, 0)) { ok = false; if (lane == 0) atomicExch(a.err, 11); }
           if (ok && !mbar_wait_cl(&a_ready, (t - 1) & 1)) { ok = false; if (lane == 0) atomicExch(a.err, 12); }
-          fence_proxy_async();
+          fence_proxy_async_cta();
           tc_fence_after();
           if (lane == 0 && ok) {
             const uint32_t idesc = idesc_16(256, 0);
@@ -225,44 +245,14 @@ wf_lstm_seq_fwd_kernel(const __grid_constant__ CUtensorMap tmWhi, const __grid_c
         }
         if (ok && !mbar_wait(&dfull, (t - 1) & 1)) { ok = false; if (lane == 0) atomicExch(a.err, 13); }
         tc_fence_after();
-        if (warp == 0 && lane == 0) arrive_cluster(pd_remote);  // my MMA no longer reads my A buffer
+        if (warp == 0 && lane == 0) arrive_cluster_relaxed(pd_remote);  // my MMA no longer reads my A buffer
+        issue_acc(0, acc[0]);
       }
       const long long blk = ((long long)z * T + t) * a.tpw + nt;
       const long long hrow = ((long long)z * R + (long long)t * a.Nn + node) * L + u0;
       const long long tcol = (long long)t * a.Np + node;
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        uint32_t acc[4][8];
-        if (t > 0) {
-          __syncwarp();
-#pragma unroll
-          for (int gate = 0; gate < 4; ++gate) tmem_ld8(tlane + gate * 64 + ub + 8 * c, acc[gate]);
-          tmem_wait_ld();
-        } else {
-#pragma unroll
-          for (int gate = 0; gate < 4; ++gate)
-#pragma unroll
-            for (int j = 0; j < 8; ++j) acc[gate][j] = 0u;
-        }
-        const float4* x = xq[c & 1];
-        float gi[8], gf[8], gg[8], go[8], hh[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const int hsel = j >> 2, cmp = j & 3;
-          const float4 xi = x[0 + hsel], xf = x[2 + hsel], xgv = x[4 + hsel], xo = x[6 + hsel];
-          const float pi = (cmp == 0 ? xi.x : cmp == 1 ? xi.y : cmp == 2 ? xi.z : xi.w) + __uint_as_float(acc[0][j]);
-          const float pf = (cmp == 0 ? xf.x : cmp == 1 ? xf.y : cmp == 2 ? xf.z : xf.w) + __uint_as_float(acc[1][j]);
-          const float pg = (cmp == 0 ? xgv.x : cmp == 1 ? xgv.y : cmp == 2 ? xgv.z : xgv.w) + __uint_as_float(acc[2][j]);
-          const float po = (cmp == 0 ? xo.x : cmp == 1 ? xo.y : cmp == 2 ? xo.z : xo.w) + __uint_as_float(acc[3][j]);
-          gi[j] = fast_sigmoid(pi);
-          gf[j] = fast_sigmoid(pf);
-          gg[j] = fast_tanh(pg);
-          go[j] = fast_sigmoid(po);
-          const float cc = fmaf(gf[j], cst[8 * c + j], gi[j] * gg[j]);
-          cst[8 * c + j] = cc;
-          hh[j] = go[j] * fast_tanh(cc);
-        }
-        // activated gates overwrite the projection in place; cell state; hidden state
+      // global stores of one finished chunk: activated gates (in place), cell state, hidden state (+ transposed copies)
+      auto store_chunk = [&](int c, const float* gi, const float* gf, const float* gg, const float* go, const float* hh) {
 #pragma unroll
         for (int hsel = 0; hsel < 2; ++hsel) {
           const int j = 4 * hsel;
@@ -277,13 +267,40 @@ wf_lstm_seq_fwd_kernel(const __grid_constant__ CUtensorMap tmWhi, const __grid_c
           *reinterpret_cast<float4*>(a.H + hrow + 8 * c) = make_float4(hh[0], hh[1], hh[2], hh[3]);
           *reinterpret_cast<float4*>(a.H + hrow + 8 * c + 4) = make_float4(hh[4], hh[5], hh[6], hh[7]);
           if (a.HT != nullptr) {
+            float* ht = a.HT + ((long long)z * L + u0 + 8 * c) * a.RT + tcol;
+            float* htl = a.HT_lo + ((long long)z * L + u0 + 8 * c) * a.RT + tcol;
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-              const long long ti = ((long long)z * L + u0 + 8 * c + j) * a.RT + tcol;
-              a.HT[ti] = hh[j];
-              a.HT_lo[ti] = hh[j] - __uint_as_float(__float_as_uint(hh[j]) & 0xFFFFE000u);
+              ht[(long long)j * a.RT] = hh[j];
+              htl[(long long)j * a.RT] = hh[j] - __uint_as_float(__float_as_uint(hh[j]) & 0xFFFFE000u);
             }
           }
+        }
+      };
+      float gi3[8], gf3[8], gg3[8], go3[8], hh3[8];  // the last chunk's outputs: stored after the hand-over below
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        if (t > 0) {
+          tmem_wait_ld();                          // chunk c's accumulators (issued one chunk ago) have landed
+          if (c < 3) issue_acc(c + 1, acc[(c + 1) & 1]);
+        }
+        const float4* x = xq[c & 1];
+        float gi[8], gf[8], gg[8], go[8], hh[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int hsel = j >> 2, cmp = j & 3;
+          const float4 xi = x[0 + hsel], xf = x[2 + hsel], xgv = x[4 + hsel], xo = x[6 + hsel];
+          const float pi = (cmp == 0 ? xi.x : cmp == 1 ? xi.y : cmp == 2 ? xi.z : xi.w) + __uint_as_float(acc[c & 1][0][j]);
+          const float pf = (cmp == 0 ? xf.x : cmp == 1 ? xf.y : cmp == 2 ? xf.z : xf.w) + __uint_as_float(acc[c & 1][1][j]);
+          const float pg = (cmp == 0 ? xgv.x : cmp == 1 ? xgv.y : cmp == 2 ? xgv.z : xgv.w) + __uint_as_float(acc[c & 1][2][j]);
+          const float po = (cmp == 0 ? xo.x : cmp == 1 ? xo.y : cmp == 2 ? xo.z : xo.w) + __uint_as_float(acc[c & 1][3][j]);
+          gi[j] = fast_sigmoid(pi);
+          gf[j] = fast_sigmoid(pf);
+          gg[j] = fast_tanh(pg);
+          go[j] = fast_sigmoid(po);
+          const float cc = fmaf(gf[j], cst[8 * c + j], gi[j] * gg[j]);
+          cst[8 * c + j] = cc;
+          hh[j] = go[j] * fast_tanh(cc);
         }
         if (t + 1 < T) {
           // h[t] as fp16 hi/lo -> the A operand of step t+1 in both CTAs (k-block `rank`, chunk (ub + 8c) / 8)
@@ -305,20 +322,30 @@ wf_lstm_seq_fwd_kernel(const __grid_constant__ CUtensorMap tmWhi, const __grid_c
           st_cluster_v4(mapa_u32(smem_u32(a_hi + off), peer), vhi);
           st_cluster_v4(mapa_u32(smem_u32(a_lo + off), peer), vlo);
         }
-        // prefetch two chunks ahead
-        {
-          const int cn = (c + 2) & 3, tn = t + ((c + 2) >> 2);
-          if (tn < T) load_chunk(tn, cn, xq[c & 1]);
+        if (c < 3) {
+          store_chunk(c, gi, gf, gg, go, hh);
+          if (c < 2) load_chunk(t, c + 2, xq[c & 1]);  // chunks 2, 3 of this step; consumed before the hand-over
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) { gi3[j] = gi[j]; gf3[j] = gf[j]; gg3[j] = gg[j]; go3[j] = go[j]; hh3[j] = hh[j]; }
         }
       }
       if (t + 1 < T) {
+        // Hand h[t] over.  The cluster-scope release below is a full memory barrier for this warp (MEMBAR.ALL.GPU in
+        // SASS), so nothing recent may be in flight here: the last chunk's global stores and the next step's input
+        // prefetch are issued after it and overlap the next step's MMA instead.
         fence_proxy_async();      // generic-proxy operand writes -> visible to the tensor core (async proxy)
         tc_fence_before();        // my TMEM reads of D[t] are complete before MMA[t+1] may overwrite D
         __syncwarp();
         if (lane == 0) {
-          asm volatile("mbarrier.arrive.release.cluster.shared::cta.b64 _, [%0];\n" ::"r"(ar_local) : "memory");
+          mbar_arrive(&a_ready);
           arrive_cluster(ar_remote);
         }
+      }
+      store_chunk(3, gi3, gf3, gg3, go3, hh3);
+      if (t + 1 < T) {
+        load_chunk(t + 1, 0, xq[0]);
+        load_chunk(t + 1, 1, xq[1]);
       }
     }
   }
@@ -691,9 +718,11 @@ extern "C" int wf_lstm_fwd_seq(const float* x, const float* params, const float*
   return WF_OK;
 }
 
+// workspace = dh between layers (TB4, L channels) + split-K partials of the weight gradients
+static size_t seq_partial_floats(int F, int L, int G) { return (size_t)8 * G * 4 * L * (F > L ? F : L); }
 extern "C" size_t wf_lstm_bwd_seq_workspace_bytes(int layers, int F, int L, int T, int N, int G, int Bw) {
-  (void)layers; (void)F;
-  return sizeof(float) * (size_t)wf_tb4_elems(L, T, N, (long long)G * Bw) + 256;
+  (void)layers;
+  return sizeof(float) * ((size_t)wf_tb4_elems(L, T, N, (long long)G * Bw) + seq_partial_floats(F, L, G)) + 256;
 }
 
 // BPTT (train_hybrid_maml_v5.py:134,169) with one persistent launch per layer.  gates / c from wf_lstm_fwd_seq
@@ -716,6 +745,8 @@ extern "C" int wf_lstm_bwd_seq(const float* xT, const float* xT_lo, const float*
   const long long g_elems = wf_tb4_elems(4 * L, T, N, Z), c_elems = wf_tb4_elems(L, T, N, Z);
   const long long tsz = Z * L * RT;
   float* DX = (float*)workspace;
+  float* partials = DX + wf_tb4_elems(L, T, N, Z);
+  const size_t partial_floats = seq_partial_floats(F, L, G);
   CUtensorMap tmhi, tmlo;
   int rc = seq_maps_bwd(&tmhi, &tmlo, bf16_hi, bf16_lo, L, G * layers);
   if (rc) return rc;
@@ -737,10 +768,12 @@ extern "C" int wf_lstm_bwd_seq(const float* xT, const float* xT_lo, const float*
     wf_colsum_tb4_kernel<<<dim3(L, G), 128, 0, st>>>(reinterpret_cast<const float4*>(XG), L, Bw * T * tpw, grads + P.b_ih[l],
                                                      grads + P.b_hh[l], grads_group_stride);
     WF_CHECK_LAUNCH("colsum_tb4");
-    rc = wf_launch_tc_wgrad(dgT, 4 * L, XT, XTlo, kin, RT, Bw, G, 0, 0, RT, grads + P.w_ih[l], grads_group_stride, err, st);
+    rc = wf_launch_tc_wgrad(dgT, 4 * L, XT, XTlo, kin, RT, Bw, G, 0, 0, RT, grads + P.w_ih[l], grads_group_stride, err, st,
+                            partials, partial_floats);
     if (rc) return rc;
     if (T > 1) {
-      rc = wf_launch_tc_wgrad(dgT, 4 * L, HT, HTlo, L, RT, Bw, G, Np, 0, RT - Np, grads + P.w_hh[l], grads_group_stride, err, st);
+      rc = wf_launch_tc_wgrad(dgT, 4 * L, HT, HTlo, L, RT, Bw, G, Np, 0, RT - Np, grads + P.w_hh[l], grads_group_stride, err, st,
+                              partials, partial_floats);
       if (rc) return rc;
     } else {
       for (int g = 0; g < G; ++g)

@@ -15,7 +15,8 @@ int wf_launch_tc_rows(const float* A, long long a_rows_total, int lda, int a_gro
                       long long g_rowptr, long long g_csr, int R, int Bw, float* ct, float* ct_lo, int Nn, int* err,
                       cudaStream_t st);
 int wf_launch_tc_wgrad(const float* AT, int M, const float* BT, const float* BT_lo, int N, int R, int Bw, int G,
-                       int a_k0, int b_k0, int klen, float* dW, long long dw_gstride, int* err, cudaStream_t st);
+                       int a_k0, int b_k0, int klen, float* dW, long long dw_gstride, int* err, cudaStream_t st,
+                       float* partials, size_t partial_floats);
 int wf_launch_tc_lstm_fwd(float* H, float* Cst, float* XG, float* HT, float* HT_lo, const float* Whh,
                           const float* Whh_lo, long long w_gstride, long long wlo_gstride, int L, int T, int Nn, int Bw,
                           int G, int t, int* err, cudaStream_t st);
@@ -156,11 +157,12 @@ extern "C" int wf_lstm_bwd_tc(const float* xT, const float* xT_lo, const float* 
                           grads_group_stride, G, part, partf, st);
     if (rc) return rc;
     // dW_ih = dG^T X_l  as  (dG^T)(X_l^T)^T over all columns of every window (padding columns are zero)
-    rc = wf_launch_tc_wgrad(dgT, 4 * L, XT, XTlo, kin, RT, Bw, G, 0, 0, RT, grads + P.w_ih[l], grads_group_stride, err, st);
+    rc = wf_launch_tc_wgrad(dgT, 4 * L, XT, XTlo, kin, RT, Bw, G, 0, 0, RT, grads + P.w_ih[l], grads_group_stride, err, st,
+                            nullptr, 0);
     if (rc) return rc;
     if (T > 1) {  // dW_hh = sum_{t>=1} dG[t]^T h[t-1]: dG^T columns [Np, RT) against h^T columns [0, RT-Np)
       rc = wf_launch_tc_wgrad(dgT, 4 * L, HT, HTlo, L, RT, Bw, G, Np, 0, RT - Np, grads + P.w_hh[l], grads_group_stride,
-                              err, st);
+                              err, st, nullptr, 0);
       if (rc) return rc;
     } else {
       for (int g = 0; g < G; ++g)
@@ -180,5 +182,5 @@ extern "C" int wf_lstm_bwd_tc(const float* xT, const float* xT_lo, const float* 
 extern "C" int wf_tc_wgrad(const float* AT, int M, const float* BT, const float* BT_lo, int N, int R, int Bw, int G,
                            int a_k0, int b_k0, int klen, float* dW, long long dw_group_stride, int* err, void* stream) {
   return wf_launch_tc_wgrad(AT, M, BT, BT_lo, N, R, Bw, G, a_k0, b_k0, klen, dW, dw_group_stride, err,
-                            (cudaStream_t)stream);
+                            (cudaStream_t)stream, nullptr, 0);
 }

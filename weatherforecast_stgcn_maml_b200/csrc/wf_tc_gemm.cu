@@ -44,6 +44,8 @@ struct TcArgs {
                         // up to 4 -- TMA needs 16-byte aligned box starts (an unaligned inner coordinate faults)
   int nkb;              // k-blocks per segment
   int nseg;             // K segments (windows) accumulated into one tile (TILE_WGRAD: Bw, else 1)
+  int nkb_split;        // TILE_WGRAD split-K: k-blocks per blockIdx.z slice (partials c_sstride apart)
+  long long c_sstride;
   int a_k0, b_k0;       // first K coordinate of a segment in the A / B maps
   int b_rank;           // 3: (k, n, z)   4: (k, unit, gate, group)
   int b_gmul;           // 0: B shared by all groups, 1: per-group B
@@ -70,8 +72,8 @@ template <int BN, int EPI>
 __global__ void __launch_bounds__(192, 1)
 wf_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmBhi,
              const __grid_constant__ CUtensorMap tmBlo, const TcArgs a) {
-  constexpr int A_BYTES = 128 * 128, B_BYTES = BN * 128, STAGE = A_BYTES + 2 * B_BYTES, NST = 2;
-  constexpr uint32_t TMEM_COLS = BN == 256 ? 512 : 256, A_COL = BN;
+  constexpr int A_BYTES = 128 * 128, B_BYTES = BN * 128, STAGE = A_BYTES + 2 * B_BYTES, NST = BN == 128 ? 4 : 2;
+  constexpr uint32_t TMEM_COLS = 512, A_COL = BN;  // D [0, BN), A stages (hi 32 + lo 32 columns each) behind it
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   __shared__ uint64_t full[NST], aready[NST], empty[NST], dfull;
@@ -103,7 +105,9 @@ wf_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     const int tt = EPI == EPI_LSTM_FWD ? a.t - 1 : a.t + 1;
     a_row = (g * a.Bw + win) * a.R + tt * a.Nn + node0;
   }
-  const int nkb_total = a.nkb * a.nseg;
+  const int kb0 = a.tile_mode == TILE_WGRAD ? (int)blockIdx.z * a.nkb_split : 0;
+  const int nkb_loc = a.tile_mode == TILE_WGRAD ? min(a.nkb - kb0, a.nkb_split) : a.nkb;
+  const int nkb_total = nkb_loc * a.nseg;
   __shared__ int abort_s;  // a pipeline already timed out somewhere: do not pile up waits (CTA-uniform decision)
   if (threadIdx.x == 0) abort_s = *reinterpret_cast<volatile int*>(a.err);
   __syncthreads();
@@ -125,8 +129,8 @@ wf_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     if (lane == 0) {
       int it = 0;
       for (int seg = 0; seg < a.nseg; ++seg)
-        for (int kb = 0; kb < a.nkb; ++kb, ++it) {
-          const int s = it & 1, ph = (it >> 1) & 1;
+        for (int kb = kb0; kb < kb0 + nkb_loc; ++kb, ++it) {
+          const int s = it % NST, ph = (it / NST) & 1;
           if (!mbar_wait(&empty[s], ph ^ 1)) { atomicExch(a.err, 1); seg = a.nseg; break; }
           uint8_t* st = smem + s * STAGE;
           mbar_expect_tx(&full[s], STAGE);
@@ -148,7 +152,7 @@ wf_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   } else if (warp == 1) {
     const uint32_t idesc = umma_idesc_tf32(BN);
     for (int it = 0; it < nkb_total; ++it) {
-      const int s = it & 1, ph = (it >> 1) & 1;
+      const int s = it % NST, ph = (it / NST) & 1;
       if (!mbar_wait(&full[s], ph) || !mbar_wait(&aready[s], ph)) { if (lane == 0) atomicExch(a.err, 2); break; }
       tc_fence_after();
       if (lane == 0) {
@@ -191,7 +195,7 @@ wf_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     }
 
     for (int it = 0; it < nkb_total && ok; ++it) {
-      const int s = it & 1, ph = (it >> 1) & 1;
+      const int s = it % NST, ph = (it / NST) & 1;
       if (!mbar_wait(&full[s], ph) || !mbar_wait(&empty[s], ph ^ 1)) { if (lane == 0) atomicExch(a.err, 3); ok = false; break; }
       uint32_t hi[32], lo[32];
       if (!gather) {
@@ -264,7 +268,7 @@ wf_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       } else if (EPI == EPI_STORE) {
         const int grow = tile * 128 + row;
         const bool valid = grow < a.rows_g;
-        float* crow = a.C + g * a.c_gstride + (long long)grow * a.ldc + n0;
+        float* crow = a.C + g * a.c_gstride + blockIdx.z * a.c_sstride + (long long)grow * a.ldc + n0;
         const float* b1 = a.bias ? a.bias + g * a.bias_gstride + n0 : nullptr;
         const float* b2 = a.bias2 ? a.bias2 + g * a.bias_gstride + n0 : nullptr;
         long long ctbase = 0;
@@ -540,7 +544,7 @@ static int map3(CUtensorMap* m, const float* base, uint64_t k, uint64_t rows, ui
 template <int BN, int EPI>
 static int launch_variant(const CUtensorMap& tmA, const CUtensorMap& tmBhi, const CUtensorMap& tmBlo, const TcArgs& a,
                           dim3 grid, cudaStream_t st) {
-  constexpr int smem = 2 * (128 * 128 + 2 * BN * 128) + 1024;
+  constexpr int smem = (BN == 128 ? 4 : 2) * (128 * 128 + 2 * BN * 128) + 1024;
   static bool configured = false;
   if (!configured) {
     if (cudaFuncSetAttribute(wf_tc_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
@@ -561,7 +565,7 @@ static int launch_variant(const CUtensorMap& tmA, const CUtensorMap& tmBhi, cons
 
 static void tc_defaults(TcArgs& a) {
   memset(&a, 0, sizeof(a));
-  a.nseg = 1; a.b_rank = 3; a.b_gmul = 1; a.Bw = 1; a.R = 1;
+  a.nseg = 1; a.b_rank = 3; a.b_gmul = 1; a.Bw = 1; a.R = 1; a.nkb_split = 1 << 30;
 }
 
 // ---- C[g] = (A_hat[g]) A[g] W[g]^T (+bias, +bias2, relu), rows tiled, optional CSR gather on A and
@@ -633,8 +637,35 @@ int wf_launch_tc_nodes(const float* A, int a_tb4, int K, const float* Whi, const
 
 // ---- weight gradient: dW[g][M, N] = sum over windows w and columns k of AT[g*Bw+w][m, a_k0+k] * BT[g*Bw+w][n, b_k0+k]
 // AT: [G*Bw][M][R], BT / BT_lo: [G*Bw][N][R];  klen columns are reduced per window.
+// Sum of split-K partials: out[g][i] = sum_s part[s][g][i], i < count (deterministic order).
+__global__ void wf_sum_splits_kernel(const float4* __restrict__ part, int splits, long long count4, long long part_sstride4,
+                                     float4* __restrict__ out, long long out_gstride4) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int g = blockIdx.y;
+  if (i >= count4) return;
+  float4 acc = part[g * count4 + i];
+  for (int sidx = 1; sidx < splits; ++sidx) {
+    const float4 v = part[sidx * part_sstride4 + g * count4 + i];
+    acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+  }
+  out[g * out_gstride4 + i] = acc;
+}
+
+// Split factor for the weight-gradient contraction: fill the SMs when there are few output tiles.
+int wf_wgrad_splits(int M, int N, int G, int klen) {
+  const int BN = (N % 256 == 0) ? 256 : 128;
+  const int tiles = (M / 128) * (N / BN) * G, nkb = wf_cdiv(klen, 32);
+  int splits = 148 / (tiles > 0 ? tiles : 1);
+  if (splits < 1) splits = 1;
+  if (splits > 8) splits = 8;
+  if (splits > nkb) splits = nkb;
+  const int per = wf_cdiv(nkb, splits);
+  return wf_cdiv(nkb, per);
+}
+
 int wf_launch_tc_wgrad(const float* AT, int M, const float* BT, const float* BT_lo, int N, int R, int Bw, int G,
-                       int a_k0, int b_k0, int klen, float* dW, long long dw_gstride, int* err, cudaStream_t st) {
+                       int a_k0, int b_k0, int klen, float* dW, long long dw_gstride, int* err, cudaStream_t st,
+                       float* partials, size_t partial_floats) {
   WF_REQUIRE(M % 128 == 0 && N % 128 == 0 && R % 4 == 0, "tc_wgrad: M=%d N=%d must be multiples of 128, R=%d of 4", M, N, R);
   // measured on B200: a TMA box whose inner start coordinate is not 16-byte aligned faults (illegal instruction)
   WF_REQUIRE(a_k0 % 4 == 0 && b_k0 % 4 == 0, "tc_wgrad: K offsets (%d, %d) must be multiples of 4", a_k0, b_k0);
@@ -646,14 +677,26 @@ int wf_launch_tc_wgrad(const float* AT, int M, const float* BT, const float* BT_
   if ((rc = map3(&tmA, AT, (uint64_t)a_k0 + klen, M, Z, R, (uint64_t)M * R, 128))) return rc;
   if ((rc = map3(&tmBhi, BT, (uint64_t)b_k0 + klen, N, Z, R, (uint64_t)N * R, BN))) return rc;
   if ((rc = map3(&tmBlo, BT_lo, (uint64_t)b_k0 + klen, N, Z, R, (uint64_t)N * R, BN))) return rc;
+  int splits = wf_wgrad_splits(M, N, G, klen);
+  const long long per_split = (long long)G * M * N;
+  if (partials == nullptr || (long long)partial_floats < per_split * splits || (dw_gstride % 4) != 0) splits = 1;
   TcArgs a;
   tc_defaults(a);
   a.tile_mode = TILE_WGRAD; a.tiles_g = M / 128; a.rows_g = M; a.Bw = Bw; a.R = R;
   a.nkb = wf_cdiv(klen, 32); a.nseg = Bw; a.a_k0 = a_k0; a.b_k0 = b_k0;
-  a.C = dW; a.ldc = N; a.c_gstride = dw_gstride; a.err = err;
-  dim3 grid(N / BN, a.tiles_g * G);
-  return BN == 256 ? launch_variant<256, EPI_STORE>(tmA, tmBhi, tmBlo, a, grid, st)
-                   : launch_variant<128, EPI_STORE>(tmA, tmBhi, tmBlo, a, grid, st);
+  a.nkb_split = wf_cdiv(a.nkb, splits);
+  a.ldc = N; a.err = err;
+  if (splits > 1) { a.C = partials; a.c_gstride = (long long)M * N; a.c_sstride = per_split; }
+  else { a.C = dW; a.c_gstride = dw_gstride; a.c_sstride = 0; }
+  dim3 grid(N / BN, a.tiles_g * G, splits);
+  rc = BN == 256 ? launch_variant<256, EPI_STORE>(tmA, tmBhi, tmBlo, a, grid, st)
+                 : launch_variant<128, EPI_STORE>(tmA, tmBhi, tmBlo, a, grid, st);
+  if (rc || splits == 1) return rc;
+  const long long count4 = (long long)M * N / 4;
+  wf_sum_splits_kernel<<<dim3(wf_cdiv(count4, 256), G), 256, 0, st>>>((const float4*)partials, splits, count4, per_split / 4,
+                                                                     (float4*)dW, dw_gstride / 4);
+  WF_CHECK_LAUNCH("sum_splits");
+  return WF_OK;
 }
 
 // ---- one LSTM time step, forward.  H [G*Bw*R, L] row-major; W_hh hi (raw) / lo: [G][4L, L].
