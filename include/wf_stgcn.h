@@ -189,27 +189,56 @@ int wf_tc_wgrad(const float* AT, int M, const float* BT, const float* BT_lo, int
 /* f32 elements of a TB4 buffer with `channels` values per (window, step, node). */
 long long wf_tb4_elems(int channels, int T, int N, long long windows);
 
-/* 16-bit elements of EACH of the four operand buffers wf_prep_weights_seq writes. */
+/* 16-bit elements of EACH of the four recurrent-operand buffers wf_prep_weights_seq writes. */
 long long wf_seq_weight_elems(int layers, int L, int G);
 
-/* W_hh of every (task, layer) -> fp16 hi/lo [G][layers][4L][L] (forward operand) and bf16 hi/lo
- * [G][layers][2][L][2L] (backward operand, regrouped per CTA rank).  Run after every weight update. */
+/* fp32 -> 16-bit hi / lo operand halves (fmt 0: fp16, 1: bf16): hi = rn(x), lo = rn(x - hi); n % 4 == 0. */
+int wf_split16(const float* src, void* hi, void* lo, long long n, int fmt, void* stream);
+
+/* Row pitch RT16 of the 16-bit transposed activation copies [(G*Bw)][channels][RT16] and of the fp32 dG^T
+ * scratch that pairs with them: column (t, node) = t*Np + node, Np = N rounded up to 8.  Padding columns zero. */
+long long wf_transposed_pitch16(int T, int N);
+
+/* Persistent tcgen05 GEMM with 16-bit hi/lo operand splits (csrc/wf_gemm16.cu), test / general entry point:
+ * C[g] = A[g] W[g]^T (+ bias + bias2, relu); A [G*rows_g, K] fp32, W16 hi/lo [G][N, K] from wf_split16(W, fmt);
+ * K % 64 == 0, N % 128 == 0. */
+int wf_g16_gemm_nt(const float* A, int rows_g, int G, int K, const void* W16_hi, const void* W16_lo,
+                   long long w_group_stride, int N, const float* bias, const float* bias2,
+                   long long bias_group_stride, int relu, int fmt, float* C, int* err, void* stream);
+
+/* GCNConv + ReLU (model.py:31-42, hybrid_model.py:65-75) on the fp16 hi/lo GEMM, neighbour aggregation fused into
+ * the A-operand path.  X dense [G*Bw*R, Cin], Cin % 64 == 0, Cout % 128 == 0; W16 hi/lo = wf_split16(W, 0), shared
+ * by all groups; YT hi/lo (optional): bf16 transposed copies [(G*Bw)][Cout][RT16] for the LSTM layer-0 dW. */
+int wf_gcn_layer_fwd_g16(const float* X, const void* W16_hi, const void* W16_lo, const float* bias,
+                         const int* rowptr, const int* col, const float* val, long long rowptr_group_stride,
+                         long long csr_group_stride, int R, int N, int Cin, int Cout, int G, int Bw, int relu,
+                         float* Y, void* YT_hi, void* YT_lo, int* err, void* stream);
+
+/* Group stride (16-bit elements) of the p16 (which = 0) / pT16 (which = 1) buffers below: the parameter counts
+ * rounded up to 8 so that every group starts 16-byte aligned. */
+long long wf_param_stride16(int layers, int F, int L, int O, int which);
+
+/* Operand staging after every weight update: p16 = fp16 hi/lo of the flat parameters [G][stride16(0)]; pT16 = bf16
+ * hi/lo of W_ih^T (layers >= 1) at the offsets of wf_param_count_transposed [G][stride16(1)]; f16 = W_hh fp16 hi/lo
+ * [G][layers][4L][L]; b16 = W_hh^T regrouped per CTA rank, bf16 hi/lo [G][layers][2][L][2L]. */
 int wf_prep_weights_seq(const float* params, long long params_group_stride, int layers, int F, int L,
-                        int O, int G, void* f16_hi, void* f16_lo, void* bf16_hi, void* bf16_lo, void* stream);
+                        int O, int G, void* p16_hi, void* p16_lo, void* pT16_hi, void* pT16_lo, void* f16_hi,
+                        void* f16_lo, void* b16_hi, void* b16_lo, void* stream);
 
 /* nn.LSTM forward (hybrid_model.py:42-49, 93-105).  x [G*Bw*T*N, F] and h [layers][G*Bw*T*N, L] are
- * row-major; gates (4L channels) and c (L channels) are TB4, [layers] of them; hT / hT_lo optional. */
-int wf_lstm_fwd_seq(const float* x, const float* params, const float* params_lo,
+ * row-major; gates (4L channels) and c (L channels) are TB4, [layers] of them; hT hi/lo optional (bf16). */
+int wf_lstm_fwd_seq(const float* x, const float* params, const void* p16_hi, const void* p16_lo,
                     long long params_group_stride, const void* f16_hi, const void* f16_lo, int layers,
                     int F, int L, int O, int T, int N, int G, int Bw, float* gates, float* h, float* c,
-                    float* hT, float* hT_lo, int* err, void* stream);
+                    void* hT_hi, void* hT_lo, int* err, void* stream);
 
 /* BPTT (train_hybrid_maml_v5.py:134,169; adapt_hybrid_v5.py:198) over the buffers of wf_lstm_fwd_seq;
- * gates are overwritten with dL/d(pre-activation).  Other arguments as wf_lstm_bwd_tc. */
+ * gates are overwritten with dL/d(pre-activation).  xT hi/lo: bf16 transposed layer-0 input [(G*Bw)][F][RT16]
+ * (wf_gcn_layer_fwd_g16); dgT: fp32 scratch [(G*Bw)][4L][RT16], padding columns zero; dlast [G*Bw*N, L]. */
 size_t wf_lstm_bwd_seq_workspace_bytes(int layers, int F, int L, int T, int N, int G, int Bw);
-int wf_lstm_bwd_seq(const float* xT, const float* xT_lo, const float* paramsT, const float* paramsT_lo,
-                    const void* bf16_hi, const void* bf16_lo, int layers, int F, int L, int O, int T, int N,
-                    int G, int Bw, float* gates, const float* c, const float* hT, const float* hT_lo,
+int wf_lstm_bwd_seq(const void* xT_hi, const void* xT_lo, const void* pT16_hi, const void* pT16_lo,
+                    const void* b16_hi, const void* b16_lo, int layers, int F, int L, int O, int T, int N,
+                    int G, int Bw, float* gates, const float* c, const void* hT_hi, const void* hT_lo,
                     float* dgT, const float* dlast, float* grads, long long grads_group_stride,
                     void* workspace, size_t workspace_bytes, int* err, void* stream);
 

@@ -42,6 +42,57 @@ def test_tc_gemm_bias_relu_epilogue():
     assert _run(200, 1, 128, 512, bias=True) <= 5e-6
 
 
+def _run16(rows_g, G, K, N, fmt, bias=False, relu=False, seed=0, scale=1.0):
+    torch.manual_seed(seed)
+    A = torch.randn(G * rows_g, K, device="cuda") * scale
+    W = torch.randn(G, N, K, device="cuda") / K ** 0.5
+    Whi = torch.empty(G, N, K, dtype=torch.int16, device="cuda")
+    Wlo = torch.empty_like(Whi)
+    b1 = torch.randn(G, N, device="cuda") * scale if bias else None
+    b2 = torch.randn(G, N, device="cuda") * scale if bias else None
+    C = torch.full((G * rows_g, N), float("nan"), device="cuda")
+    err = torch.zeros(1, dtype=torch.int32, device="cuda")
+    st = _lib.stream_ptr()
+    _lib.call("wf_split16", _lib.ptr(W), _lib.ptr(Whi), _lib.ptr(Wlo), W.numel(), fmt, st)
+    _lib.call("wf_g16_gemm_nt", _lib.ptr(A), rows_g, G, K, _lib.ptr(Whi), _lib.ptr(Wlo), N * K, N, _lib.ptr(b1), _lib.ptr(b2),
+              N, int(relu), fmt, _lib.ptr(C), _lib.ptr(err), st)
+    torch.cuda.synchronize()
+    assert int(err.item()) == 0, f"pipeline timeout code {int(err.item())}"
+    ref = torch.bmm(A.double().view(G, rows_g, K), W.double().transpose(1, 2))
+    if bias:
+        ref = ref + (b1 + b2).double()[:, None, :]
+    if relu:
+        ref = ref.clamp_min(0)
+    ref = ref.view(G * rows_g, N)
+    return float((C.double() - ref).abs().max() / ref.abs().max())
+
+
+@pytest.mark.parametrize("rows_g,G,K,N", [(128, 1, 64, 128), (441, 1, 128, 512), (300, 3, 256, 256), (1000, 2, 128, 128),
+                                          (10584, 2, 256, 512), (70000, 1, 64, 128)])
+def test_g16_gemm_matches_fp64(rows_g, G, K, N):
+    """Persistent 16-bit hi/lo GEMM: fp16 split ~2^-20, bf16 split ~2^-16 (many tiles per CTA at the larger sizes)."""
+    assert _run16(rows_g, G, K, N, 0) <= 5e-6
+    assert _run16(rows_g, G, K, N, 1) <= 5e-5
+    assert _run16(rows_g, G, K, N, 1, scale=1e-7) <= 5e-5   # gradient-sized operands keep their precision in bf16
+
+
+def test_g16_gemm_bias_relu_epilogue():
+    assert _run16(441, 2, 256, 256, 0, bias=True, relu=True) <= 5e-6
+    assert _run16(200, 1, 128, 512, 1, bias=True) <= 5e-5
+
+
+def test_split16_reconstructs():
+    x = torch.randn(4096, device="cuda") * 3.0
+    # fp16: 22 significant bits down to the fp16 subnormal spacing (2^-24 absolute); bf16: 16 bits, fp32 range
+    for fmt, dt, tol, floor in ((0, torch.float16, 2.0 ** -21, 2.0 ** -24), (1, torch.bfloat16, 2.0 ** -15, 0.0)):
+        hi = torch.empty(4096, dtype=torch.int16, device="cuda")
+        lo = torch.empty_like(hi)
+        _lib.call("wf_split16", _lib.ptr(x), _lib.ptr(hi), _lib.ptr(lo), x.numel(), fmt, _lib.stream_ptr())
+        rec = hi.view(dt).float() + lo.view(dt).float()
+        assert torch.equal(hi.view(dt), x.to(dt))
+        assert bool(((rec - x).abs() <= (x.abs() * tol).clamp_min(floor)).all())
+
+
 def test_split_lo_is_exact():
     x = torch.randn(4096, device="cuda") * 37.0
     lo = torch.empty_like(x)

@@ -1,0 +1,589 @@
+// Persistent tcgen05 GEMM with 16-bit hi/lo operand splits (sm_100a) -- the dense products around the LSTM:
+// GCN Theta transform with fused neighbour aggregation (model.py:23-26, hybrid_model.py:65-74), LSTM input
+// projections (hybrid_model.py:42-49), dX = dG W_ih and the weight gradients dW = dG^T X of loss.backward()
+// (train_hybrid_maml_v5.py:134,169).
+//
+//   D[128 x 128] (TMEM, fp32) += A[128 x 64] * B[128 x 64]^T   per k-block, as three kind::f16 products
+//   a*b ~= a_hi*b_hi + a_lo*b_hi + a_hi*b_lo  (fp16 hi/lo in the forward pass: ~2^-20; bf16 hi/lo for gradient
+//   operands, which need the fp32 exponent range: ~2^-16).  Twice the MMA rate and half the B bytes of 3xTF32.
+//
+// One CTA per SM, static round-robin over output tiles (n fastest, so the CTAs working on one A row block
+// at the same time share it in L2).  Warp roles:
+//   warp 0      TMA producer: A tile [128 x 64] fp32 (two SWIZZLE_128B boxes, or two TB4 boxes) + B_hi / B_lo
+//               [128 x 64] 16-bit into a 3-stage shared-memory ring
+//   warp 1      MMA issuer (TS mode: A from TMEM, B from smem); owns TMEM: 2 accumulator stages x 128 columns
+//               + 3 A stages x 64 columns
+//   warps 2..5  converters: thread = tile row; fp32 row from smem (or CSR gather-aggregate from global for GCN
+//               rows with neighbours) -> hi/lo 16-bit pairs -> tcgen05.st into the TMEM A stage
+//   warps 6..9  epilogue of the PREVIOUS tile while the next one is multiplied: tcgen05.ld -> bias / ReLU ->
+//               row-major, TB4, or split-K partial stores (+ transposed bf16 hi/lo copies for the weight gradients)
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+
+#include "wf_common.cuh"
+#include "wf_tc.cuh"
+
+using namespace wftc;
+
+namespace {
+
+enum { G16_ROWS = 0, G16_NODES = 1, G16_WGRAD = 2 };
+constexpr int G16_THREADS = 320;
+constexpr int G16_NST = 3;
+constexpr int G16_A_BYTES = 32768, G16_B_BYTES = 16384, G16_STAGE = G16_A_BYTES + 2 * G16_B_BYTES;
+constexpr int G16_SMEM = G16_NST * G16_STAGE + 1024;
+
+struct G16Args {
+  int mode;
+  int m_tiles, n_tiles, G, splits;   // tile id -> (split, g, m tile, n tile), n fastest
+  int rows_g, a_group_rows;          // ROWS: valid rows per group / row stride between groups in the A map
+  int Bw, R, Nn, T, tpw, Np, RT;
+  int nkb, nseg, nkb_split;          // k-blocks (64 wide) per segment; segments (wgrad: windows); split-K slice
+  int a_k0, b_k0;
+  int b_gmul;                        // 0: B shared by all groups
+  int a_tb4;
+  const float* a_raw; int lda;       // CSR gather on A (GCN aggregation), ROWS only
+  const int* rowptr; const int* col; const float* val; long long g_rowptr, g_csr;
+  float* C; int ldc; long long c_gstride, c_sstride; int c_cols;
+  const float* bias; const float* bias2; long long bias_gstride; int relu;
+  __nv_bfloat16* ct_hi; __nv_bfloat16* ct_lo;   // transposed copies [(g*Bw + w)][c_cols][RT]
+  int* err;
+};
+
+__host__ __device__ constexpr uint32_t g16_idesc(uint32_t fmt) {  // D = F32, A/B = fmt (0 F16, 1 BF16), K-major, M = N = 128
+  return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+}
+__device__ __forceinline__ void g16_mma(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+               "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}\n"
+               ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
+
+template <int FMT>
+__device__ __forceinline__ void split_pair(float a, float b, uint32_t& hi, uint32_t& lo) {
+  if (FMT == 0) {
+    const __half ha = __float2half_rn(a), hb = __float2half_rn(b);
+    const __half la = __float2half_rn(a - __half2float(ha)), lb = __float2half_rn(b - __half2float(hb));
+    hi = (uint32_t)__half_as_ushort(ha) | ((uint32_t)__half_as_ushort(hb) << 16);
+    lo = (uint32_t)__half_as_ushort(la) | ((uint32_t)__half_as_ushort(lb) << 16);
+  } else {
+    const __nv_bfloat16 ha = __float2bfloat16_rn(a), hb = __float2bfloat16_rn(b);
+    const __nv_bfloat16 la = __float2bfloat16_rn(a - __bfloat162float(ha)), lb = __float2bfloat16_rn(b - __bfloat162float(hb));
+    hi = (uint32_t)__bfloat16_as_ushort(ha) | ((uint32_t)__bfloat16_as_ushort(hb) << 16);
+    lo = (uint32_t)__bfloat16_as_ushort(la) | ((uint32_t)__bfloat16_as_ushort(lb) << 16);
+  }
+}
+
+struct TileCoord {
+  int g, mt, ntile, split;
+  int a_row, a_z0, b_z0, zstep;   // TMA coordinates
+  int zt, blk, node0;             // NODES
+  int kb0, nkb_loc;
+};
+
+__device__ __forceinline__ TileCoord decode_tile(const G16Args& a, int tile) {
+  TileCoord c;
+  c.ntile = tile % a.n_tiles; tile /= a.n_tiles;
+  c.mt = tile % a.m_tiles; tile /= a.m_tiles;
+  c.g = tile % a.G;
+  c.split = tile / a.G;
+  c.a_z0 = 0; c.zstep = 0; c.b_z0 = c.g * a.b_gmul; c.zt = 0; c.blk = 0; c.node0 = 0;
+  c.kb0 = 0; c.nkb_loc = a.nkb;
+  if (a.mode == G16_ROWS) {
+    c.a_row = c.g * a.a_group_rows + c.mt * 128;
+  } else if (a.mode == G16_NODES) {
+    const int ztl = c.mt / a.tpw, nt = c.mt - ztl * a.tpw;
+    c.node0 = nt * 128;
+    c.zt = c.g * a.Bw * a.T + ztl;
+    c.blk = c.zt * a.tpw + nt;
+    c.a_row = c.node0;
+  } else {
+    c.a_row = c.mt * 128;
+    c.a_z0 = c.g * a.Bw; c.b_z0 = c.g * a.Bw; c.zstep = 1;
+    c.kb0 = c.split * a.nkb_split;
+    c.nkb_loc = min(a.nkb - c.kb0, a.nkb_split);
+  }
+  return c;
+}
+
+template <int FMT>
+__global__ void __launch_bounds__(G16_THREADS, 1)
+wf_g16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmBhi,
+              const __grid_constant__ CUtensorMap tmBlo, const G16Args a) {
+  constexpr int NST = G16_NST, STAGE = G16_STAGE, A_BYTES = G16_A_BYTES, B_BYTES = G16_B_BYTES;
+  constexpr uint32_t A_COL = 256;  // TMEM: D stage ds at [128 ds, +128); A stage s at [256 + 64 s, +64) (hi 32 | lo 32)
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  __shared__ uint64_t full[NST], aready[NST], empty[NST], dfull[2], dempty[2];
+  __shared__ uint32_t tmem_base_s;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int total = a.n_tiles * a.m_tiles * a.G * a.splits;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < NST; ++s) { mbar_init(&full[s], 1); mbar_init(&aready[s], 4); mbar_init(&empty[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&dfull[s], 1); mbar_init(&dempty[s], 4); }
+    mbar_fence_init();
+    tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmBhi); tma_prefetch_desc(&tmBlo);
+  }
+  if (warp == 1) tmem_alloc(&tmem_base_s, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tbase = tmem_base_s;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int it = 0;
+      bool ok = true;
+      for (int tile = blockIdx.x; tile < total && ok; tile += gridDim.x) {
+        const TileCoord c = decode_tile(a, tile);
+        for (int seg = 0; seg < a.nseg && ok; ++seg)
+          for (int kb = c.kb0; kb < c.kb0 + c.nkb_loc; ++kb, ++it) {
+            const int s = it % NST, ph = (it / NST) & 1;
+            if (!mbar_wait(&empty[s], ph ^ 1)) { atomicExch(a.err, 31); ok = false; break; }
+            uint8_t* st = smem + s * STAGE;
+            mbar_expect_tx(&full[s], STAGE);
+            const int ka = a.a_k0 + kb * 64, kbb = a.b_k0 + kb * 64;
+            if (a.mode == G16_NODES && a.a_tb4) {
+              tma_load_4d(st, &tmA, &full[s], 0, 0, ka >> 2, c.blk);
+              tma_load_4d(st + 16384, &tmA, &full[s], 0, 0, (ka >> 2) + 8, c.blk);
+            } else {
+              const int zc = a.mode == G16_NODES ? c.zt : c.a_z0 + seg * c.zstep;
+              tma_load_3d(st, &tmA, &full[s], ka, c.a_row, zc);
+              tma_load_3d(st + 16384, &tmA, &full[s], ka + 32, c.a_row, zc);
+            }
+            const int zb = c.b_z0 + seg * c.zstep;
+            tma_load_3d(st + A_BYTES, &tmBhi, &full[s], kbb, c.ntile * 128, zb);
+            tma_load_3d(st + A_BYTES + B_BYTES, &tmBlo, &full[s], kbb, c.ntile * 128, zb);
+          }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    const uint32_t idesc = g16_idesc(FMT);
+    int it = 0, lt = 0;
+    bool ok = true;
+    for (int tile = blockIdx.x; tile < total && ok; tile += gridDim.x, ++lt) {
+      const TileCoord c = decode_tile(a, tile);
+      const int ds = lt & 1, nk = c.nkb_loc * a.nseg;
+      if (!mbar_wait(&dempty[ds], ((lt >> 1) & 1) ^ 1)) { if (lane == 0) atomicExch(a.err, 32); ok = false; break; }
+      tc_fence_after();
+      for (int k = 0; k < nk; ++k, ++it) {
+        const int s = it % NST, ph = (it / NST) & 1;
+        if (!mbar_wait(&full[s], ph) || !mbar_wait(&aready[s], ph)) { if (lane == 0) atomicExch(a.err, 33); ok = false; break; }
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t bhi = smem_u32(smem + s * STAGE + A_BYTES), blo = bhi + B_BYTES;
+          const uint32_t acol = tbase + A_COL + s * 64;
+#pragma unroll
+          for (int p = 0; p < 3; ++p) {  // A_hi B_hi, A_lo B_hi, A_hi B_lo
+            const uint32_t ac = acol + (p == 1 ? 32 : 0);
+            const uint32_t bs = p == 2 ? blo : bhi;
+#pragma unroll
+            for (int k16 = 0; k16 < 4; ++k16)
+              g16_mma(tbase + ds * 128, ac + k16 * 8, umma_desc_k_sw128(bs + k16 * 32), idesc, (k | p | k16) ? 1u : 0u);
+          }
+          umma_commit(&empty[s]);
+          if (k == nk - 1) umma_commit(&dfull[ds]);
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp < 6) {
+    // ------------------------------------------------------------------ converters (A: fp32 -> hi/lo 16-bit -> TMEM)
+    const int q = warp & 3, row = q * 32 + lane;
+    const uint32_t tlane = tbase + ((uint32_t)(q * 32) << 16);
+    int it = 0;
+    bool ok = true;
+    for (int tile = blockIdx.x; tile < total && ok; tile += gridDim.x) {
+      const TileCoord c = decode_tile(a, tile);
+      int p0 = 0, p1 = 0;
+      long long wbase = 0;
+      bool gather = false;
+      if (a.mode == G16_ROWS && a.rowptr != nullptr) {  // rows whose aggregation is not the unit self loop
+        const int grow = c.mt * 128 + row;
+        if (grow < a.rows_g) {
+          const int w = grow / a.R, rr = grow - w * a.R;
+          const int* rp = a.rowptr + c.g * a.g_rowptr;
+          p0 = rp[rr]; p1 = rp[rr + 1];
+          wbase = ((long long)c.g * a.a_group_rows + (long long)w * a.R) * a.lda;
+          gather = !(p1 - p0 == 1 && a.col[c.g * a.g_csr + p0] == rr && a.val[c.g * a.g_csr + p0] == 1.0f);
+        }
+      }
+      const int nk = c.nkb_loc * a.nseg;
+      for (int k = 0; k < nk; ++k, ++it) {
+        const int s = it % NST, ph = (it / NST) & 1;
+        if (!mbar_wait(&full[s], ph) || !mbar_wait(&empty[s], ph ^ 1)) { if (lane == 0) atomicExch(a.err, 34); ok = false; break; }
+        uint32_t hi[32], lo[32];
+        if (!gather) {
+          const uint8_t* st = smem + s * STAGE;
+#pragma unroll
+          for (int h = 0; h < 2; ++h)
+#pragma unroll
+            for (int ch = 0; ch < 8; ++ch) {
+              // TB4 stage: [channel group][row][4 floats]; otherwise two SWIZZLE_128B boxes of 32 floats per row
+              const uint8_t* p = st + h * 16384 + (a.a_tb4 ? ch * 2048 + row * 16 : row * 128 + ((ch ^ (row & 7)) << 4));
+              const float4 v = *reinterpret_cast<const float4*>(p);
+              split_pair<FMT>(v.x, v.y, hi[h * 16 + 2 * ch], lo[h * 16 + 2 * ch]);
+              split_pair<FMT>(v.z, v.w, hi[h * 16 + 2 * ch + 1], lo[h * 16 + 2 * ch + 1]);
+            }
+        } else {
+          const int* cl = a.col + c.g * a.g_csr;
+          const float* vl = a.val + c.g * a.g_csr;
+          const int k0 = a.a_k0 + (c.kb0 + k % c.nkb_loc) * 64;
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            float acc[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) acc[j] = 0.f;
+            for (int p = p0; p < p1; ++p) {
+              const float v = __ldg(vl + p);
+              const float4* src = reinterpret_cast<const float4*>(a.a_raw + wbase + (long long)__ldg(cl + p) * a.lda + k0 + 32 * h);
+#pragma unroll
+              for (int ch = 0; ch < 8; ++ch) {
+                const float4 x = __ldg(src + ch);
+                acc[4 * ch + 0] = fmaf(v, x.x, acc[4 * ch + 0]); acc[4 * ch + 1] = fmaf(v, x.y, acc[4 * ch + 1]);
+                acc[4 * ch + 2] = fmaf(v, x.z, acc[4 * ch + 2]); acc[4 * ch + 3] = fmaf(v, x.w, acc[4 * ch + 3]);
+              }
+            }
+#pragma unroll
+            for (int j = 0; j < 16; ++j) split_pair<FMT>(acc[2 * j], acc[2 * j + 1], hi[h * 16 + j], lo[h * 16 + j]);
+          }
+        }
+        __syncwarp();  // gather / non-gather lanes diverged above
+        tmem_st32(tlane + A_COL + s * 64, hi);
+        tmem_st32(tlane + A_COL + s * 64 + 32, lo);
+        tmem_wait_st();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&aready[s]);
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue
+    const int q = warp & 3, row = q * 32 + lane;
+    const uint32_t tlane = tbase + ((uint32_t)(q * 32) << 16);
+    int lt = 0;
+    bool ok = true;
+    for (int tile = blockIdx.x; tile < total && ok; tile += gridDim.x, ++lt) {
+      const TileCoord c = decode_tile(a, tile);
+      const int ds = lt & 1, n0 = c.ntile * 128;
+      if (!mbar_wait(&dfull[ds], (lt >> 1) & 1)) { if (lane == 0) atomicExch(a.err, 35); ok = false; break; }
+      tc_fence_after();
+      const float* b1 = a.bias ? a.bias + c.g * a.bias_gstride + n0 : nullptr;
+      const float* b2 = a.bias2 ? a.bias2 + c.g * a.bias_gstride + n0 : nullptr;
+      if (a.mode == G16_NODES) {
+        // TB4 block = [c_cols / 4 channel groups][128 rows][4 floats]: 512 contiguous bytes per warp store
+        float4* cblk = reinterpret_cast<float4*>(a.C) + ((long long)c.blk * (a.c_cols >> 2) + (n0 >> 2)) * 128 + row;
+#pragma unroll 1
+        for (int cc = 0; cc < 128; cc += 32) {
+          uint32_t v[32];
+          __syncwarp();
+          tmem_ld32(tlane + ds * 128 + cc, v);
+          tmem_wait_ld();
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            float4 o = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+            if (b1) { const float4 b = __ldg(reinterpret_cast<const float4*>(b1 + cc + j)); o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w; }
+            if (b2) { const float4 b = __ldg(reinterpret_cast<const float4*>(b2 + cc + j)); o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w; }
+            if (a.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+            cblk[(long long)((cc + j) >> 2) * 128] = o;
+          }
+        }
+      } else {
+        const int grow = c.mt * 128 + row;
+        const bool valid = grow < a.rows_g;
+        float* crow = a.C + c.g * a.c_gstride + c.split * a.c_sstride + (long long)grow * a.ldc + n0;
+        long long ctbase = 0;
+        if (a.ct_hi != nullptr && valid) {
+          const int w = grow / a.R, rr = grow - w * a.R;
+          const int tt = rr / a.Nn, nn = rr - tt * a.Nn;
+          ctbase = ((long long)(c.g * a.Bw + w) * a.c_cols + n0) * a.RT + (long long)tt * a.Np + nn;
+        }
+#pragma unroll 1
+        for (int cc = 0; cc < 128; cc += 32) {
+          uint32_t v[32];
+          __syncwarp();
+          tmem_ld32(tlane + ds * 128 + cc, v);
+          tmem_wait_ld();
+          if (valid) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              float4 o = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+              if (b1) { const float4 b = __ldg(reinterpret_cast<const float4*>(b1 + cc + j)); o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w; }
+              if (b2) { const float4 b = __ldg(reinterpret_cast<const float4*>(b2 + cc + j)); o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w; }
+              if (a.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+              *reinterpret_cast<float4*>(crow + cc + j) = o;
+              if (a.ct_hi != nullptr) {  // lanes of a warp hold consecutive rows -> contiguous transposed stores
+                const float ov[4] = {o.x, o.y, o.z, o.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const long long ti = ctbase + (long long)(cc + j + e) * a.RT;
+                  const __nv_bfloat16 h = __float2bfloat16_rn(ov[e]);
+                  a.ct_hi[ti] = h;
+                  a.ct_lo[ti] = __float2bfloat16_rn(ov[e] - __bfloat162float(h));
+                }
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&dempty[ds]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tbase, 512);
+}
+
+// fp32 -> 16-bit hi / lo (fmt 0: fp16, 1: bf16), elementwise; blockIdx.y = group (own source / destination stride)
+__global__ void wf_split16_kernel(const float4* __restrict__ src, long long src_gstride4, uint2* __restrict__ hi,
+                                  uint2* __restrict__ lo, long long dst_gstride4, long long quads, int fmt) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= quads) return;
+  const float4 v = src[blockIdx.y * src_gstride4 + i];
+  i += blockIdx.y * dst_gstride4;
+  uint2 h, l;
+  if (fmt == 0) { split_pair<0>(v.x, v.y, h.x, l.x); split_pair<0>(v.z, v.w, h.y, l.y); }
+  else { split_pair<1>(v.x, v.y, h.x, l.x); split_pair<1>(v.z, v.w, h.y, l.y); }
+  hi[i] = h;
+  lo[i] = l;
+}
+
+int map16(CUtensorMap* m, const void* base, uint64_t k, uint64_t rows, uint64_t z, uint64_t ld, uint64_t zstride, int fmt) {
+  uint64_t dims[3] = {k, rows, z};
+  uint64_t str[2] = {ld * 2, zstride * 2};
+  uint32_t box[3] = {64, 128, 1};
+  return wf_encode_tensor_map(m, base, 3, dims, str, box, 1, fmt == 0 ? 1 : 2);
+}
+int map32(CUtensorMap* m, const float* base, uint64_t k, uint64_t rows, uint64_t z, uint64_t ld, uint64_t zstride) {
+  uint64_t dims[3] = {k, rows, z};
+  uint64_t str[2] = {ld * 4, zstride * 4};
+  uint32_t box[3] = {32, 128, 1};
+  return wf_encode_tensor_map(m, base, 3, dims, str, box, 1, 0);
+}
+
+int g16_launch(int fmt, const CUtensorMap& tmA, const CUtensorMap& tmBhi, const CUtensorMap& tmBlo, const G16Args& a, cudaStream_t st) {
+  static bool configured = false;
+  static int sms = 148;
+  if (!configured) {
+    if (cudaFuncSetAttribute(wf_g16_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, G16_SMEM) != cudaSuccess ||
+        cudaFuncSetAttribute(wf_g16_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, G16_SMEM) != cudaSuccess)
+      return wf_fail(WF_ECUDA, "g16 kernel: cannot raise dynamic shared memory to %d", G16_SMEM);
+    int dev = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (sms <= 0) sms = 148;
+    configured = true;
+  }
+  const long long total = (long long)a.n_tiles * a.m_tiles * a.G * a.splits;
+  const int grid = (int)(total < sms ? total : sms);
+  if (fmt == 0) wf_g16_kernel<0><<<grid, G16_THREADS, G16_SMEM, st>>>(tmA, tmBhi, tmBlo, a);
+  else wf_g16_kernel<1><<<grid, G16_THREADS, G16_SMEM, st>>>(tmA, tmBhi, tmBlo, a);
+  WF_CHECK_LAUNCH("g16_kernel");
+  return WF_OK;
+}
+
+void g16_defaults(G16Args& a) {
+  memset(&a, 0, sizeof(a));
+  a.G = 1; a.splits = 1; a.nseg = 1; a.b_gmul = 1; a.Bw = 1; a.R = 1; a.Nn = 1; a.T = 1; a.tpw = 1; a.nkb_split = 1 << 30;
+}
+
+}  // namespace
+
+// Column pitch of one time slice in the transposed copies: N rounded up to 8, so 16-bit rows stay 16-byte aligned
+// for TMA whatever T is.
+int wf_np(int N) { return (N + 7) & ~7; }
+
+// G groups of n values each; group g reads src + g*src_gstride and writes hi/lo + g*dst_gstride (elements).
+int wf_launch_split16(const float* src, long long src_gstride, void* hi, void* lo, long long dst_gstride, long long n, int G,
+                      int fmt, cudaStream_t st) {
+  WF_REQUIRE(n > 0 && n % 4 == 0 && src_gstride % 4 == 0 && dst_gstride % 4 == 0, "split16: sizes must be multiples of 4");
+  wf_split16_kernel<<<dim3(wf_cdiv(n / 4, 256), G), 256, 0, st>>>((const float4*)src, src_gstride / 4, (uint2*)hi, (uint2*)lo,
+                                                                dst_gstride / 4, n / 4, fmt);
+  WF_CHECK_LAUNCH("split16");
+  return WF_OK;
+}
+
+// ---- C[g] = (A_hat[g]) A[g] W[g]^T (+bias, +bias2, relu): rows tiled, optional CSR gather on A and transposed
+// bf16 hi/lo copies of C.  W16 hi/lo: [Gb][N, K] 16-bit (fmt).
+int wf_launch_g16_rows(int fmt, const float* A, long long a_rows_total, int lda, int a_group_rows, int rows_g, int G, int K,
+                       const void* Whi, const void* Wlo, int ldb, long long b_gstride, int b_shared, int N, const float* bias,
+                       const float* bias2, long long bias_gstride, int relu, float* C, int ldc, long long c_gstride,
+                       const int* rowptr, const int* col, const float* val, long long g_rowptr, long long g_csr, int R, int Bw,
+                       void* ct_hi, void* ct_lo, int Nn, int* err, cudaStream_t st) {
+  WF_REQUIRE(K % 64 == 0 && K >= 64, "g16_rows: K=%d must be a multiple of 64", K);
+  WF_REQUIRE(N % 128 == 0, "g16_rows: N=%d must be a multiple of 128", N);
+  WF_REQUIRE(lda % 4 == 0 && ldb % 8 == 0 && ldc % 4 == 0, "g16_rows: leading dimensions must keep 16-byte alignment");
+  WF_REQUIRE(((uintptr_t)A | (uintptr_t)Whi | (uintptr_t)Wlo | (uintptr_t)C) % 16 == 0, "g16_rows: pointers must be 16-byte aligned");
+  const int Gb = b_shared ? 1 : G;
+  CUtensorMap tmA, tmBhi, tmBlo;
+  int rc;
+  if ((rc = map32(&tmA, A, K, a_rows_total, 1, lda, (uint64_t)a_rows_total * lda))) return rc;
+  if ((rc = map16(&tmBhi, Whi, K, N, Gb, ldb, Gb > 1 ? b_gstride : (long long)N * ldb, fmt))) return rc;
+  if ((rc = map16(&tmBlo, Wlo, K, N, Gb, ldb, Gb > 1 ? b_gstride : (long long)N * ldb, fmt))) return rc;
+  G16Args a;
+  g16_defaults(a);
+  a.mode = G16_ROWS; a.m_tiles = wf_cdiv(rows_g, 128); a.n_tiles = N / 128; a.G = G;
+  a.rows_g = rows_g; a.a_group_rows = a_group_rows; a.nkb = K / 64; a.b_gmul = b_shared ? 0 : 1;
+  a.a_raw = A; a.lda = lda; a.rowptr = rowptr; a.col = col; a.val = val; a.g_rowptr = g_rowptr; a.g_csr = g_csr;
+  a.R = R > 0 ? R : rows_g; a.Bw = Bw > 0 ? Bw : 1;
+  a.Nn = Nn > 0 ? Nn : a.R; a.Np = wf_np(a.Nn); a.RT = (a.R / a.Nn) * a.Np;
+  WF_REQUIRE(ct_hi == nullptr || a.R % a.Nn == 0, "g16_rows: transposed copies need R to be a multiple of the node count");
+  a.C = C; a.ldc = ldc; a.c_gstride = c_gstride; a.c_cols = N; a.bias = bias; a.bias2 = bias2; a.bias_gstride = bias_gstride;
+  a.relu = relu; a.ct_hi = (__nv_bfloat16*)ct_hi; a.ct_lo = (__nv_bfloat16*)ct_lo; a.err = err;
+  return g16_launch(fmt, tmA, tmBhi, tmBlo, a, st);
+}
+
+// ---- C = A W^T (+bias + bias2) tiled per (window, step, 128 nodes), output in the TB4 layout.
+// A: row-major [G*Bw*T*Nn, K] (a_tb4 == 0) or a TB4 buffer with K channels (a_tb4 == 1).
+int wf_launch_g16_nodes(int fmt, const float* A, int a_tb4, int K, const void* Whi, const void* Wlo, int ldb, long long b_gstride,
+                        int N, const float* bias, const float* bias2, long long bias_gstride, float* C, int T, int Nn, int Bw,
+                        int G, int* err, cudaStream_t st) {
+  WF_REQUIRE(K % 64 == 0 && K >= 64, "g16_nodes: K=%d must be a multiple of 64", K);
+  WF_REQUIRE(N % 128 == 0 && ldb % 8 == 0, "g16_nodes: N=%d must be a multiple of 128, ldb of 8", N);
+  WF_REQUIRE(((uintptr_t)A | (uintptr_t)Whi | (uintptr_t)Wlo | (uintptr_t)C) % 16 == 0, "g16_nodes: pointers must be 16-byte aligned");
+  const int tpw = wf_cdiv(Nn, 128);
+  const long long ZT = (long long)G * Bw * T;
+  CUtensorMap tmA, tmBhi, tmBlo;
+  int rc;
+  if (a_tb4) {
+    uint64_t dims[4] = {256, 2, (uint64_t)(K / 4), (uint64_t)(ZT * tpw)};
+    uint64_t str[3] = {256 * 4, 512 * 4, (uint64_t)K * 128 * 4};
+    uint32_t box[4] = {256, 2, 8, 1};
+    if ((rc = wf_encode_tensor_map(&tmA, A, 4, dims, str, box, 0, 0))) return rc;
+  } else {
+    if ((rc = map32(&tmA, A, K, Nn, ZT, K, (uint64_t)Nn * K))) return rc;
+  }
+  if ((rc = map16(&tmBhi, Whi, K, N, G, ldb, G > 1 ? b_gstride : (long long)N * ldb, fmt))) return rc;
+  if ((rc = map16(&tmBlo, Wlo, K, N, G, ldb, G > 1 ? b_gstride : (long long)N * ldb, fmt))) return rc;
+  G16Args a;
+  g16_defaults(a);
+  a.mode = G16_NODES; a.tpw = tpw; a.a_tb4 = a_tb4; a.m_tiles = Bw * T * tpw; a.n_tiles = N / 128; a.G = G;
+  a.Bw = Bw; a.T = T; a.Nn = Nn; a.nkb = K / 64;
+  a.C = C; a.c_cols = N; a.bias = bias; a.bias2 = bias2; a.bias_gstride = bias_gstride; a.err = err;
+  return g16_launch(fmt, tmA, tmBhi, tmBlo, a, st);
+}
+
+// Sum of split-K partials: out[g][i] = sum_s part[s][g][i] (fixed order: deterministic).
+static __global__ void wf_sum_splits16_kernel(const float4* __restrict__ part, int splits, long long count4, long long part_sstride4,
+                                              float4* __restrict__ out, long long out_gstride4) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int g = blockIdx.y;
+  if (i >= count4) return;
+  float4 acc = part[g * count4 + i];
+  for (int sidx = 1; sidx < splits; ++sidx) {
+    const float4 v = part[sidx * part_sstride4 + g * count4 + i];
+    acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+  }
+  out[g * out_gstride4 + i] = acc;
+}
+
+// ---- weight gradient: dW[g][M, N] = sum over windows w and columns k of AT[g*Bw+w][m, a_k0+k] * BT[g*Bw+w][n, b_k0+k]
+// AT: fp32 [G*Bw][M][R]; BT hi/lo: bf16 [G*Bw][N][R].  Split-K over `partials` when there are few output tiles.
+int wf_launch_g16_wgrad(const float* AT, int M, const void* BT_hi, const void* BT_lo, int N, int R, int Bw, int G, int a_k0,
+                        int b_k0, int klen, float* dW, long long dw_gstride, int* err, cudaStream_t st, float* partials,
+                        size_t partial_floats) {
+  WF_REQUIRE(M % 128 == 0 && N % 128 == 0 && R % 8 == 0, "g16_wgrad: M=%d N=%d must be multiples of 128, R=%d of 8", M, N, R);
+  WF_REQUIRE(a_k0 % 4 == 0 && b_k0 % 8 == 0, "g16_wgrad: K offsets (%d, %d) must keep 16-byte alignment", a_k0, b_k0);
+  CUtensorMap tmA, tmBhi, tmBlo;
+  int rc;
+  const uint64_t Z = (uint64_t)G * Bw;
+  // the K extent seen through the maps ends at a_k0 + klen / b_k0 + klen: everything beyond is zero-filled
+  if ((rc = map32(&tmA, AT, (uint64_t)a_k0 + klen, M, Z, R, (uint64_t)M * R))) return rc;
+  if ((rc = map16(&tmBhi, BT_hi, (uint64_t)b_k0 + klen, N, Z, R, (uint64_t)N * R, 1))) return rc;
+  if ((rc = map16(&tmBlo, BT_lo, (uint64_t)b_k0 + klen, N, Z, R, (uint64_t)N * R, 1))) return rc;
+  const int tiles = (M / 128) * (N / 128) * G, nkb = wf_cdiv(klen, 64);
+  int splits = 148 / (tiles > 0 ? tiles : 1);
+  if (splits < 1) splits = 1;
+  if (splits > 8) splits = 8;
+  if (splits > nkb) splits = nkb;
+  int per = wf_cdiv(nkb, splits);
+  splits = wf_cdiv(nkb, per);
+  const long long per_split = (long long)G * M * N;
+  if (partials == nullptr || (long long)partial_floats < per_split * splits || (dw_gstride % 4) != 0) { splits = 1; per = nkb; }
+  G16Args a;
+  g16_defaults(a);
+  a.mode = G16_WGRAD; a.m_tiles = M / 128; a.n_tiles = N / 128; a.G = G; a.splits = splits;
+  a.rows_g = M; a.Bw = Bw; a.R = R; a.nkb = nkb; a.nseg = Bw; a.nkb_split = per; a.a_k0 = a_k0; a.b_k0 = b_k0;
+  a.ldc = N; a.c_cols = N; a.err = err;
+  if (splits > 1) { a.C = partials; a.c_gstride = (long long)M * N; a.c_sstride = per_split; }
+  else { a.C = dW; a.c_gstride = dw_gstride; a.c_sstride = 0; }
+  rc = g16_launch(1, tmA, tmBhi, tmBlo, a, st);
+  if (rc || splits == 1) return rc;
+  const long long count4 = (long long)M * N / 4;
+  wf_sum_splits16_kernel<<<dim3(wf_cdiv(count4, 256), G), 256, 0, st>>>((const float4*)partials, splits, count4, per_split / 4,
+                                                                     (float4*)dW, dw_gstride / 4);
+  WF_CHECK_LAUNCH("sum_splits");
+  return WF_OK;
+}
+
+// out[g][c][r] = split16(in[g][r][c]): W[rows, cols] -> W^T[cols, rows] as bf16 hi / lo for every group.
+static __global__ void wf_transpose_split16_kernel(const float* __restrict__ in, long long in_gstride, int rows, int cols,
+                                                   __nv_bfloat16* __restrict__ out_hi, __nv_bfloat16* __restrict__ out_lo,
+                                                   long long out_gstride) {
+  __shared__ float t[32][33];
+  const int g = blockIdx.z;
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    int r = r0 + i, c = c0 + threadIdx.x;
+    t[i][threadIdx.x] = (r < rows && c < cols) ? in[g * in_gstride + (long long)r * cols + c] : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    int c = c0 + i, r = r0 + threadIdx.x;
+    if (c < cols && r < rows) {
+      const float v = t[threadIdx.x][i];
+      const long long o = g * out_gstride + (long long)c * rows + r;
+      const __nv_bfloat16 h = __float2bfloat16_rn(v);
+      out_hi[o] = h;
+      out_lo[o] = __float2bfloat16_rn(v - __bfloat162float(h));
+    }
+  }
+}
+
+int wf_launch_transpose_split16(const float* in, long long in_gstride, int rows, int cols, void* out_hi, void* out_lo,
+                                long long out_gstride, int G, cudaStream_t st) {
+  dim3 grid(wf_cdiv(cols, 32), wf_cdiv(rows, 32), G), block(32, 8);
+  wf_transpose_split16_kernel<<<grid, block, 0, st>>>(in, in_gstride, rows, cols, (__nv_bfloat16*)out_hi, (__nv_bfloat16*)out_lo,
+                                                      out_gstride);
+  WF_CHECK_LAUNCH("transpose_split16");
+  return WF_OK;
+}
+
+// fp32 -> 16-bit hi / lo operand halves (fmt 0: fp16, 1: bf16); n a multiple of 4.
+extern "C" int wf_split16(const float* src, void* hi, void* lo, long long n, int fmt, void* stream) {
+  WF_REQUIRE(fmt == 0 || fmt == 1, "split16: fmt must be 0 (fp16) or 1 (bf16)");
+  return wf_launch_split16(src, 0, hi, lo, 0, n, 1, fmt, (cudaStream_t)stream);
+}
+
+// Row pitch of the 16-bit transposed activation copies [(G*Bw)][channels][RT16] (and of the fp32 dG^T scratch that
+// pairs with them): column (t, node) = t*Np + node with Np = N rounded up to 8.  Padding columns must be zero.
+extern "C" long long wf_transposed_pitch16(int T, int N) { return (long long)T * wf_np(N); }
+
+// GCNConv + ReLU (model.py:31-42, hybrid_model.py:65-75): Y = relu((A_hat X) W^T + b) on the persistent fp16 hi/lo GEMM
+// with the neighbour aggregation fused into the A-operand path.  X dense [G*Bw*R, Cin], Cin % 64 == 0, Cout % 128 == 0,
+// W16 hi/lo = wf_split16(W, fmt 0), shared by all groups; YT hi/lo (optional): bf16 transposed copies [(G*Bw)][Cout][RT16].
+extern "C" int wf_gcn_layer_fwd_g16(const float* X, const void* W16_hi, const void* W16_lo, const float* bias, const int* rowptr,
+                                    const int* col, const float* val, long long rowptr_group_stride, long long csr_group_stride,
+                                    int R, int N, int Cin, int Cout, int G, int Bw, int relu, float* Y, void* YT_hi, void* YT_lo,
+                                    int* err, void* stream) {
+  WF_REQUIRE(G > 0 && Bw > 0 && R > 0 && N > 0, "gcn_layer_fwd_g16: bad batch");
+  const long long rows_g = (long long)Bw * R;
+  return wf_launch_g16_rows(0, X, rows_g * G, Cin, (int)rows_g, (int)rows_g, G, Cin, W16_hi, W16_lo, Cin, 0, 1, Cout, bias, nullptr,
+                            0, relu, Y, Cout, rows_g * Cout, rowptr, col, val, rowptr_group_stride, csr_group_stride, R, Bw, YT_hi,
+                            YT_lo, N, err, (cudaStream_t)stream);
+}
+
+// Test / general entry point: C[g] = A[g] W[g]^T (+ bias + bias2, relu), W16 hi/lo [G][N, K] from wf_split16(W, fmt).
+extern "C" int wf_g16_gemm_nt(const float* A, int rows_g, int G, int K, const void* W16_hi, const void* W16_lo,
+                              long long w_group_stride, int N, const float* bias, const float* bias2, long long bias_group_stride,
+                              int relu, int fmt, float* C, int* err, void* stream) {
+  WF_REQUIRE(rows_g > 0 && G > 0, "g16_gemm_nt: empty problem");
+  WF_REQUIRE(fmt == 0 || fmt == 1, "g16_gemm_nt: fmt must be 0 (fp16) or 1 (bf16)");
+  return wf_launch_g16_rows(fmt, A, (long long)rows_g * G, K, rows_g, rows_g, G, K, W16_hi, W16_lo, K, w_group_stride, 0, N, bias,
+                            bias2, bias_group_stride, relu, C, N, (long long)rows_g * N, nullptr, nullptr, nullptr, 0, 0, 0, 1,
+                            nullptr, nullptr, 0, err, (cudaStream_t)stream);
+}

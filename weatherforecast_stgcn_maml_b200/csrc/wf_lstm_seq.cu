@@ -31,12 +31,17 @@
 
 using namespace wftc;
 
-int wf_launch_tc_nodes(const float* A, int a_tb4, int K, const float* Whi, const float* Wlo, int ldb, long long b_gstride,
-                       int N, const float* bias, const float* bias2, long long bias_gstride, float* C, int T, int Nn, int Bw,
-                       int G, int* err, cudaStream_t st);
-int wf_launch_tc_wgrad(const float* AT, int M, const float* BT, const float* BT_lo, int N, int R, int Bw, int G,
-                       int a_k0, int b_k0, int klen, float* dW, long long dw_gstride, int* err, cudaStream_t st,
-                       float* partials, size_t partial_floats);
+int wf_launch_g16_nodes(int fmt, const float* A, int a_tb4, int K, const void* Whi, const void* Wlo, int ldb, long long b_gstride,
+                        int N, const float* bias, const float* bias2, long long bias_gstride, float* C, int T, int Nn, int Bw,
+                        int G, int* err, cudaStream_t st);
+int wf_launch_g16_wgrad(const float* AT, int M, const void* BT_hi, const void* BT_lo, int N, int R, int Bw, int G, int a_k0,
+                        int b_k0, int klen, float* dW, long long dw_gstride, int* err, cudaStream_t st, float* partials,
+                        size_t partial_floats);
+int wf_launch_split16(const float* src, long long src_gstride, void* hi, void* lo, long long dst_gstride, long long n, int G,
+                      int fmt, cudaStream_t st);
+int wf_launch_transpose_split16(const float* in, long long in_gstride, int rows, int cols, void* out_hi, void* out_lo,
+                                long long out_gstride, int G, cudaStream_t st);
+int wf_np(int N);
 
 namespace {
 
@@ -48,8 +53,8 @@ struct SeqArgs {
   float* XG;          // TB4, 4L channels. fwd: input projection in, activated gates out; bwd: gates in, dG out
   float* Cst;         // TB4, L channels: cell state
   float* H;           // fwd out: row-major [Z*R, L]
-  float* HT;          // fwd out (optional): transposed copies [(z)][L][RT]
-  float* HT_lo;
+  __nv_bfloat16* HT;  // fwd out (optional): transposed bf16 hi / lo copies [(z)][L][RT]
+  __nv_bfloat16* HT_lo;
   float* DGT;         // bwd out: transposed dG [(z)][4L][RT]
   const float* ext;   // bwd: dL/dh from above -- TB4 (L channels), or row-major dlast [Z*Nn, L] if ext_last_only
   int ext_last_only;
@@ -267,12 +272,13 @@ wf_lstm_seq_fwd_kernel(const __grid_constant__ CUtensorMap tmWhi, const __grid_c
           *reinterpret_cast<float4*>(a.H + hrow + 8 * c) = make_float4(hh[0], hh[1], hh[2], hh[3]);
           *reinterpret_cast<float4*>(a.H + hrow + 8 * c + 4) = make_float4(hh[4], hh[5], hh[6], hh[7]);
           if (a.HT != nullptr) {
-            float* ht = a.HT + ((long long)z * L + u0 + 8 * c) * a.RT + tcol;
-            float* htl = a.HT_lo + ((long long)z * L + u0 + 8 * c) * a.RT + tcol;
+            __nv_bfloat16* ht = a.HT + ((long long)z * L + u0 + 8 * c) * a.RT + tcol;
+            __nv_bfloat16* htl = a.HT_lo + ((long long)z * L + u0 + 8 * c) * a.RT + tcol;
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-              ht[(long long)j * a.RT] = hh[j];
-              htl[(long long)j * a.RT] = hh[j] - __uint_as_float(__float_as_uint(hh[j]) & 0xFFFFE000u);
+              const __nv_bfloat16 hb = __float2bfloat16_rn(hh[j]);
+              ht[(long long)j * a.RT] = hb;
+              htl[(long long)j * a.RT] = __float2bfloat16_rn(hh[j] - __bfloat162float(hb));
             }
           }
         }
@@ -664,36 +670,62 @@ extern "C" long long wf_tb4_elems(int channels, int T, int N, long long windows)
   return windows * T * wf_cdiv(N, 128) * (long long)channels * 128;
 }
 
+// Group stride (16-bit elements) of the p16 / pT16 operand buffers: the parameter counts rounded up to 8 so that every
+// group starts 16-byte aligned (TMA).  which = 0: flat parameters, 1: transposed W_ih buffer.
+static long long stride16(long long n) { return (n + 7) & ~7LL; }
+extern "C" long long wf_param_stride16(int layers, int F, int L, int O, int which) {
+  if (layers < 1 || layers > 8) return -1;
+  const LstmLayout P = lstm_layout(layers, F, L, O);
+  return stride16(which ? P.totalT : P.total);
+}
+
 // Elements (16-bit each) of ONE of the four recurrent-operand buffers written by wf_prep_weights_seq.
 extern "C" long long wf_seq_weight_elems(int layers, int L, int G) { return (long long)G * layers * 4 * L * L; }
 
+// Operand staging after every update of the (fast) weights -- it replaces nothing in the reference:
+//   p16_hi / p16_lo   fp16 hi/lo of the whole flat parameter buffer, [G][wf_param_stride16(.., 0)] (W_ih: projections)
+//   pT16_hi / pT16_lo bf16 hi/lo of W_ih^T, layers >= 1, at the offsets of wf_param_count_transposed,
+//                     [G][wf_param_stride16(.., 1)] (dX)
+//   f16_hi / f16_lo   W_hh as fp16 hi/lo [G][layers][4L][L] (forward recurrence)
+//   b16_hi / b16_lo   W_hh^T regrouped per CTA rank as bf16 hi/lo [G][layers][2][L][2L] (backward recurrence)
 extern "C" int wf_prep_weights_seq(const float* params, long long params_group_stride, int layers, int F, int L, int O,
-                                   int G, void* f16_hi, void* f16_lo, void* bf16_hi, void* bf16_lo, void* stream) {
+                                   int G, void* p16_hi, void* p16_lo, void* pT16_hi, void* pT16_lo, void* f16_hi, void* f16_lo,
+                                   void* b16_hi, void* b16_lo, void* stream) {
   WF_REQUIRE(layers >= 1 && layers <= 8 && L == 128 && G > 0, "prep_weights_seq: needs L == 128");
   const LstmLayout P = lstm_layout(layers, F, L, O);
+  WF_REQUIRE(G == 1 || params_group_stride == P.total, "prep_weights_seq: parameter sets must be contiguous");
+  WF_REQUIRE(P.total % 4 == 0, "prep_weights_seq: parameter count must be a multiple of 4");
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc = wf_launch_split16(params, params_group_stride, p16_hi, p16_lo, stride16(P.total), P.total, G, 0, st);
+  if (rc) return rc;
+  for (int l = 1; l < layers; ++l) {
+    rc = wf_launch_transpose_split16(params + P.w_ih[l], params_group_stride, 4 * L, L, (uint16_t*)pT16_hi + P.wihT[l],
+                                     (uint16_t*)pT16_lo + P.wihT[l], stride16(P.totalT), G, st);
+    if (rc) return rc;
+  }
   dim3 grid(wf_cdiv(4 * L * L, 256), layers, G);
-  wf_prep_seq_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(params, params_group_stride, P, layers, L, (__half*)f16_hi,
-                                                             (__half*)f16_lo, (__nv_bfloat16*)bf16_hi, (__nv_bfloat16*)bf16_lo);
+  wf_prep_seq_kernel<<<grid, 256, 0, st>>>(params, params_group_stride, P, layers, L, (__half*)f16_hi, (__half*)f16_lo,
+                                           (__nv_bfloat16*)b16_hi, (__nv_bfloat16*)b16_lo);
   WF_CHECK_LAUNCH("prep_weights_seq");
   return WF_OK;
 }
 
-// nn.LSTM forward (hybrid_model.py:42-49, 93-105) with one persistent launch per layer.
-//   x [G*Bw*T*N, F] row-major; params / params_lo: flat fp32 weights and their TF32 lo halves (input projections);
-//   f16_hi / f16_lo from wf_prep_weights_seq; gates TB4 [layers][4L ch], c TB4 [layers][L ch],
-//   h [layers][G*Bw*T*N, L] row-major, hT / hT_lo optional transposed copies (training).
-extern "C" int wf_lstm_fwd_seq(const float* x, const float* params, const float* params_lo, long long params_group_stride,
-                               const void* f16_hi, const void* f16_lo, int layers, int F, int L, int O, int T, int N,
-                               int G, int Bw, float* gates, float* h, float* c, float* hT, float* hT_lo, int* err,
-                               void* stream) {
-  WF_REQUIRE(layers >= 1 && layers <= 8 && L == 128 && F % 32 == 0, "lstm_fwd_seq: needs L == 128, F %% 32 == 0");
+// nn.LSTM forward (hybrid_model.py:42-49, 93-105): per layer one input-projection GEMM + one persistent launch.
+//   x [G*Bw*T*N, F] row-major; params: flat fp32 weights (biases); p16 / f16 operands from wf_prep_weights_seq;
+//   gates TB4 [layers][4L ch], c TB4 [layers][L ch], h [layers][G*Bw*T*N, L] row-major,
+//   hT_hi / hT_lo optional bf16 transposed copies [layers][(G*Bw)][L][RT16] (training).
+extern "C" int wf_lstm_fwd_seq(const float* x, const float* params, const void* p16_hi, const void* p16_lo,
+                               long long params_group_stride, const void* f16_hi, const void* f16_lo, int layers, int F, int L,
+                               int O, int T, int N, int G, int Bw, float* gates, float* h, float* c, void* hT_hi, void* hT_lo,
+                               int* err, void* stream) {
+  WF_REQUIRE(layers >= 1 && layers <= 8 && L == 128 && F % 64 == 0, "lstm_fwd_seq: needs L == 128, F %% 64 == 0");
   WF_REQUIRE(T > 0 && N > 0 && G > 0 && Bw > 0, "lstm_fwd_seq: empty batch");
   cudaStream_t st = (cudaStream_t)stream;
   static bool configured = false;
   if (!configured) { int rc = seq_configure(wf_lstm_seq_fwd_kernel); if (rc) return rc; configured = true; }
   const LstmLayout P = lstm_layout(layers, F, L, O);
   const long long Z = (long long)G * Bw, rows = Z * T * N;
-  const int tpw = wf_cdiv(N, 128), Np = (N + 3) & ~3, RT = T * Np;
+  const int tpw = wf_cdiv(N, 128), Np = wf_np(N), RT = T * Np;
   const long long g_elems = wf_tb4_elems(4 * L, T, N, Z), c_elems = wf_tb4_elems(L, T, N, Z);
   const long long tsz = Z * L * RT;
   CUtensorMap tmhi, tmlo;
@@ -703,13 +735,14 @@ extern "C" int wf_lstm_fwd_seq(const float* x, const float* params, const float*
     const int kin = l == 0 ? F : L;
     float* XG = gates + l * g_elems;
     const float* Xl = l == 0 ? x : h + (long long)(l - 1) * rows * L;
-    rc = wf_launch_tc_nodes(Xl, 0, kin, params + P.w_ih[l], params_lo + P.w_ih[l], kin, params_group_stride, 4 * L,
-                            params + P.b_ih[l], params + P.b_hh[l], params_group_stride, XG, T, N, Bw, G, err, st);
+    rc = wf_launch_g16_nodes(0, Xl, 0, kin, (const uint16_t*)p16_hi + P.w_ih[l], (const uint16_t*)p16_lo + P.w_ih[l], kin,
+                             stride16(P.total), 4 * L, params + P.b_ih[l], params + P.b_hh[l], params_group_stride, XG, T, N,
+                             Bw, G, err, st);
     if (rc) return rc;
     SeqArgs a;
     memset(&a, 0, sizeof(a));
     a.XG = XG; a.Cst = c + l * c_elems; a.H = h + (long long)l * rows * L;
-    a.HT = hT ? hT + l * tsz : nullptr; a.HT_lo = hT ? hT_lo + l * tsz : nullptr;
+    a.HT = hT_hi ? (__nv_bfloat16*)hT_hi + l * tsz : nullptr; a.HT_lo = hT_hi ? (__nv_bfloat16*)hT_lo + l * tsz : nullptr;
     a.T = T; a.Nn = N; a.Bw = Bw; a.tpw = tpw; a.Np = Np; a.RT = RT;
     a.slab0 = l; a.slab_g = layers; a.err = err;
     wf_lstm_seq_fwd_kernel<<<dim3((unsigned)(2 * Z * tpw)), SEQ_THREADS, SEQ_SMEM, st>>>(tmhi, tmlo, a);
@@ -726,12 +759,13 @@ extern "C" size_t wf_lstm_bwd_seq_workspace_bytes(int layers, int F, int L, int 
 }
 
 // BPTT (train_hybrid_maml_v5.py:134,169) with one persistent launch per layer.  gates / c from wf_lstm_fwd_seq
-// (gates are overwritten by dG); xT / xT_lo, hT / hT_lo, dgT as wf_lstm_bwd_tc; paramsT / paramsT_lo from
-// wf_prep_weights_tc (W_ih^T for dX); bf16_hi / bf16_lo from wf_prep_weights_seq; dlast [G*Bw*N, L].
-extern "C" int wf_lstm_bwd_seq(const float* xT, const float* xT_lo, const float* paramsT, const float* paramsT_lo,
-                               const void* bf16_hi, const void* bf16_lo, int layers, int F, int L, int O, int T, int N,
-                               int G, int Bw, float* gates, const float* c, const float* hT, const float* hT_lo,
-                               float* dgT, const float* dlast, float* grads, long long grads_group_stride, void* workspace,
+// (gates are overwritten by dG); xT_hi / xT_lo: bf16 transposed layer-0 input [(G*Bw)][F][RT16]; hT_hi / hT_lo from
+// wf_lstm_fwd_seq; dgT: fp32 scratch [(G*Bw)][4L][RT16] with zero padding columns; pT16 / b16 operands from
+// wf_prep_weights_seq; dlast [G*Bw*N, L].
+extern "C" int wf_lstm_bwd_seq(const void* xT_hi, const void* xT_lo, const void* pT16_hi, const void* pT16_lo,
+                               const void* b16_hi, const void* b16_lo, int layers, int F, int L, int O, int T, int N, int G,
+                               int Bw, float* gates, const float* c, const void* hT_hi, const void* hT_lo, float* dgT,
+                               const float* dlast, float* grads, long long grads_group_stride, void* workspace,
                                size_t workspace_bytes, int* err, void* stream) {
   WF_REQUIRE(layers >= 1 && layers <= 8 && L == 128 && F % 128 == 0, "lstm_bwd_seq: needs L == 128 and F %% 128 == 0");
   if (workspace_bytes < wf_lstm_bwd_seq_workspace_bytes(layers, F, L, T, N, G, Bw))
@@ -741,22 +775,21 @@ extern "C" int wf_lstm_bwd_seq(const float* xT, const float* xT_lo, const float*
   if (!configured) { int rc = seq_configure(wf_lstm_seq_bwd_kernel); if (rc) return rc; configured = true; }
   const LstmLayout P = lstm_layout(layers, F, L, O);
   const long long Z = (long long)G * Bw;
-  const int tpw = wf_cdiv(N, 128), Np = (N + 3) & ~3, RT = T * Np;
+  const int tpw = wf_cdiv(N, 128), Np = wf_np(N), RT = T * Np;
   const long long g_elems = wf_tb4_elems(4 * L, T, N, Z), c_elems = wf_tb4_elems(L, T, N, Z);
   const long long tsz = Z * L * RT;
   float* DX = (float*)workspace;
   float* partials = DX + wf_tb4_elems(L, T, N, Z);
   const size_t partial_floats = seq_partial_floats(F, L, G);
+  const uint16_t *hTh = (const uint16_t*)hT_hi, *hTl = (const uint16_t*)hT_lo;
   CUtensorMap tmhi, tmlo;
-  int rc = seq_maps_bwd(&tmhi, &tmlo, bf16_hi, bf16_lo, L, G * layers);
+  int rc = seq_maps_bwd(&tmhi, &tmlo, b16_hi, b16_lo, L, G * layers);
   if (rc) return rc;
   for (int l = layers - 1; l >= 0; --l) {
     const int kin = l == 0 ? F : L;
     float* XG = gates + l * g_elems;
-    const float* HT = hT + l * tsz;
-    const float* HTlo = hT_lo + l * tsz;
-    const float* XT = l == 0 ? xT : hT + (l - 1) * tsz;
-    const float* XTlo = l == 0 ? xT_lo : hT_lo + (l - 1) * tsz;
+    const void* XTh = l == 0 ? xT_hi : (const void*)(hTh + (l - 1) * tsz);
+    const void* XTl = l == 0 ? xT_lo : (const void*)(hTl + (l - 1) * tsz);
     SeqArgs a;
     memset(&a, 0, sizeof(a));
     a.XG = XG; a.Cst = const_cast<float*>(c) + l * c_elems; a.DGT = dgT;
@@ -768,20 +801,21 @@ extern "C" int wf_lstm_bwd_seq(const float* xT, const float* xT_lo, const float*
     wf_colsum_tb4_kernel<<<dim3(L, G), 128, 0, st>>>(reinterpret_cast<const float4*>(XG), L, Bw * T * tpw, grads + P.b_ih[l],
                                                      grads + P.b_hh[l], grads_group_stride);
     WF_CHECK_LAUNCH("colsum_tb4");
-    rc = wf_launch_tc_wgrad(dgT, 4 * L, XT, XTlo, kin, RT, Bw, G, 0, 0, RT, grads + P.w_ih[l], grads_group_stride, err, st,
-                            partials, partial_floats);
+    // dW_ih = dG^T X_l  as  (dG^T)(X_l^T)^T over all columns of every window (padding columns are zero)
+    rc = wf_launch_g16_wgrad(dgT, 4 * L, XTh, XTl, kin, RT, Bw, G, 0, 0, RT, grads + P.w_ih[l], grads_group_stride, err, st,
+                             partials, partial_floats);
     if (rc) return rc;
-    if (T > 1) {
-      rc = wf_launch_tc_wgrad(dgT, 4 * L, HT, HTlo, L, RT, Bw, G, Np, 0, RT - Np, grads + P.w_hh[l], grads_group_stride, err, st,
-                              partials, partial_floats);
+    if (T > 1) {  // dW_hh = sum_{t>=1} dG[t]^T h[t-1]: dG^T columns [Np, RT) against h^T columns [0, RT-Np)
+      rc = wf_launch_g16_wgrad(dgT, 4 * L, hTh + l * tsz, hTl + l * tsz, L, RT, Bw, G, Np, 0, RT - Np, grads + P.w_hh[l],
+                               grads_group_stride, err, st, partials, partial_floats);
       if (rc) return rc;
     } else {
       for (int g = 0; g < G; ++g)
         cudaMemsetAsync(grads + g * grads_group_stride + P.w_hh[l], 0, sizeof(float) * 4 * L * L, st);
     }
     if (l > 0) {  // dL/d(input of layer l) = dG W_ih -> ext of layer l-1 (TB4 in, TB4 out)
-      rc = wf_launch_tc_nodes(XG, 1, 4 * L, paramsT + P.wihT[l], paramsT_lo + P.wihT[l], 4 * L, P.totalT, L, nullptr, nullptr,
-                              0, DX, T, N, Bw, G, err, st);
+      rc = wf_launch_g16_nodes(1, XG, 1, 4 * L, (const uint16_t*)pT16_hi + P.wihT[l], (const uint16_t*)pT16_lo + P.wihT[l], 4 * L,
+                               stride16(P.totalT), L, nullptr, nullptr, 0, DX, T, N, Bw, G, err, st);
       if (rc) return rc;
     }
   }

@@ -129,21 +129,37 @@ class HybridEngine:
                  _lib.query("wf_head_workspace_bytes", L, d.O, d.num_nodes, self.G, self.Bw),
                  _lib.query("wf_optim_workspace_bytes", self.G))
         self.err = torch.zeros(1, dtype=torch.int32, device=self.device)
-        if self.tc:
+        i16 = dict(dtype=torch.int16, device=self.device)
+        if self.seq:
+            # persistent path: 16-bit hi/lo operands everywhere (fp16 forward, bf16 for gradient operands)
+            ws = max(ws, _lib.query("wf_lstm_bwd_seq_workspace_bytes", Ls, d.hidden, L, d.window, d.num_nodes, self.G,
+                                    self.Bw))
+            nw = int(_lib.query("wf_seq_weight_elems", Ls, L, self.G))
+            self.PT = int(_lib.query("wf_param_count_transposed", Ls, d.hidden, L, d.O))
+            self.w16 = [torch.empty(nw, **i16) for _ in range(4)]            # W_hh: fwd hi/lo, bwd hi/lo
+            s16 = [int(_lib.query("wf_param_stride16", Ls, d.hidden, L, d.O, w)) for w in (0, 1)]
+            self.p16 = [torch.empty(self.G, s16[0], **i16) for _ in range(2)]   # flat params as fp16 hi/lo
+            self.pT16 = [torch.empty(self.G, s16[1], **i16) for _ in range(2)]  # W_ih^T as bf16 hi/lo
+            if self.training:
+                # transposed activation copies [(G*Bw)][channels][RT16] feed the weight-gradient products;
+                # their padding columns must be zero and are never written by the kernels
+                rt = int(_lib.query("wf_transposed_pitch16", d.window, d.num_nodes))
+                self.hT = torch.zeros(Ls, self.W * L * rt, **i16)
+                self.hT_lo = torch.zeros(Ls, self.W * L * rt, **i16)
+                self.featsT = torch.zeros(self.W * d.hidden * rt, **i16)
+                self.featsT_lo = torch.zeros(self.W * d.hidden * rt, **i16)
+                self.dgT = torch.zeros(self.W * 4 * L * rt, **f32)
+            else:
+                self.hT = self.hT_lo = self.featsT = self.featsT_lo = self.dgT = None
+            self._gcn_lo = {}
+        elif self.tc:
             ws = max(ws, _lib.query("wf_lstm_bwd_tc_workspace_bytes", Ls, d.hidden, L, d.window, d.num_nodes, self.G,
                                     self.Bw))
-            if self.seq:
-                ws = max(ws, _lib.query("wf_lstm_bwd_seq_workspace_bytes", Ls, d.hidden, L, d.window, d.num_nodes, self.G,
-                                        self.Bw))
-                nw = int(_lib.query("wf_seq_weight_elems", Ls, L, self.G))
-                self.w16 = [torch.empty(nw, dtype=torch.int16, device=self.device) for _ in range(4)]
             self.PT = int(_lib.query("wf_param_count_transposed", Ls, d.hidden, L, d.O))
             self.params_lo = torch.empty(self.G, self.P, **f32)
             self.paramsT = torch.empty(self.G, self.PT, **f32)
             self.paramsT_lo = torch.empty(self.G, self.PT, **f32)
             if self.training:
-                # transposed activation copies [(G*Bw)][channels][RT] feed the weight-gradient products;
-                # their padding columns must be zero and are never written by the kernels
                 rt = int(_lib.query("wf_transposed_pitch", d.window, d.num_nodes))
                 self.hT = torch.zeros(Ls, self.W * L * rt, **f32)
                 self.hT_lo = torch.zeros(Ls, self.W * L * rt, **f32)
@@ -165,11 +181,17 @@ class HybridEngine:
             raise RuntimeError(f"tcgen05 pipeline timeout (role code {code})")
 
     def _gcn_w_lo(self, Wt):
+        """Cached operand staging of a GCN weight: TF32 lo half (stepwise path) or fp16 (hi, lo) (persistent path)."""
         key = (Wt.data_ptr(), Wt._version)
         lo = self._gcn_lo.get(key)
         if lo is None:
-            lo = torch.empty_like(Wt)
-            _lib.call("wf_split_lo", _lib.ptr(Wt), _lib.ptr(lo), Wt.numel(), _lib.stream_ptr())
+            if self.seq:
+                lo = (torch.empty(Wt.shape, dtype=torch.int16, device=Wt.device),
+                      torch.empty(Wt.shape, dtype=torch.int16, device=Wt.device))
+                _lib.call("wf_split16", _lib.ptr(Wt), _lib.ptr(lo[0]), _lib.ptr(lo[1]), Wt.numel(), 0, _lib.stream_ptr())
+            else:
+                lo = torch.empty_like(Wt)
+                _lib.call("wf_split_lo", _lib.ptr(Wt), _lib.ptr(lo), Wt.numel(), _lib.stream_ptr())
             if len(self._gcn_lo) > 16:
                 self._gcn_lo.clear()
             self._gcn_lo[key] = lo
@@ -192,7 +214,14 @@ class HybridEngine:
         for i, (Wt, b) in enumerate(gcn_weights):
             dst = self.act[i] if self.keep_gcn else self.act[i & 1]
             dense = src_off is None and src_ld == cin and src_stride == d.R * cin
-            if self.tc and dense and cin % 32 == 0:
+            if self.seq and dense and cin % 64 == 0:
+                want_t = self.training and i == nlayers - 1
+                w16 = self._gcn_w_lo(Wt)
+                _lib.call("wf_gcn_layer_fwd_g16", _lib.ptr(src), _lib.ptr(w16[0]), _lib.ptr(w16[1]), _lib.ptr(b),
+                          _lib.ptr(rp), _lib.ptr(cl), _lib.ptr(vl), rps, cs, d.R, d.num_nodes, cin, d.hidden, self.G,
+                          self.Bw, 1, _lib.ptr(dst), _lib.ptr(self.featsT) if want_t else None,
+                          _lib.ptr(self.featsT_lo) if want_t else None, _lib.ptr(self.err), st)
+            elif self.tc and not self.seq and dense and cin % 32 == 0:
                 want_t = self.training and i == nlayers - 1
                 _lib.call("wf_gcn_layer_fwd_tc", _lib.ptr(src), _lib.ptr(Wt), _lib.ptr(self._gcn_w_lo(Wt)), _lib.ptr(b),
                           _lib.ptr(rp), _lib.ptr(cl), _lib.ptr(vl), rps, cs, d.R, d.num_nodes, cin, d.hidden, self.G,
@@ -212,24 +241,26 @@ class HybridEngine:
         d, st = self.dims, _lib.stream_ptr()
         feats = self.feats if feats is None else feats
         Ls, L = d.lstm_layers, d.lstm_hidden
-        if self.tc:
+        if self.seq:
+            # operand staging: 16-bit hi/lo copies of the current (fast) weights
+            src_stride = params_stride if self.G > 1 else self.P
+            _lib.call("wf_prep_weights_seq", _lib.ptr(params), src_stride, Ls, d.hidden, L, d.O, self.G,
+                      _lib.ptr(self.p16[0]), _lib.ptr(self.p16[1]), _lib.ptr(self.pT16[0]), _lib.ptr(self.pT16[1]),
+                      _lib.ptr(self.w16[0]), _lib.ptr(self.w16[1]), _lib.ptr(self.w16[2]), _lib.ptr(self.w16[3]), st)
+            _lib.call("wf_lstm_fwd_seq", _lib.ptr(feats), _lib.ptr(params), _lib.ptr(self.p16[0]), _lib.ptr(self.p16[1]),
+                      params_stride if self.G > 1 else self.P, _lib.ptr(self.w16[0]), _lib.ptr(self.w16[1]), Ls, d.hidden,
+                      L, d.O, d.window, d.num_nodes, self.G, self.Bw, _lib.ptr(self.gates), _lib.ptr(self.h),
+                      _lib.ptr(self.c), _lib.ptr(self.hT), _lib.ptr(self.hT_lo), _lib.ptr(self.err), st)
+            self.launches += (1 + (Ls - 1) + 1) + 2 * Ls  # operand staging, then (projection + recurrence) per layer
+        elif self.tc:
             # operand staging for 3xTF32: lo halves and transposed copies of the current weights
             src_stride = params_stride if self.G > 1 else self.P
             _lib.call("wf_prep_weights_tc", _lib.ptr(params), src_stride, Ls, d.hidden, L, d.O, self.G,
                       _lib.ptr(self.params_lo), _lib.ptr(self.paramsT), _lib.ptr(self.paramsT_lo), st)
-            if self.seq:
-                _lib.call("wf_prep_weights_seq", _lib.ptr(params), src_stride, Ls, d.hidden, L, d.O, self.G,
-                          _lib.ptr(self.w16[0]), _lib.ptr(self.w16[1]), _lib.ptr(self.w16[2]), _lib.ptr(self.w16[3]), st)
-                _lib.call("wf_lstm_fwd_seq", _lib.ptr(feats), _lib.ptr(params), _lib.ptr(self.params_lo), params_stride,
-                          _lib.ptr(self.w16[0]), _lib.ptr(self.w16[1]), Ls, d.hidden, L, d.O, d.window, d.num_nodes,
-                          self.G, self.Bw, _lib.ptr(self.gates), _lib.ptr(self.h), _lib.ptr(self.c), _lib.ptr(self.hT),
-                          _lib.ptr(self.hT_lo), _lib.ptr(self.err), st)
-                self.launches += 2 * Ls + 1 + 2 * Ls  # operand staging, then (projection + recurrence) per layer
-            else:
-                _lib.call("wf_lstm_fwd_tc", _lib.ptr(feats), _lib.ptr(params), _lib.ptr(self.params_lo), params_stride, Ls,
-                          d.hidden, L, d.O, d.window, d.num_nodes, self.G, self.Bw, _lib.ptr(self.gates), _lib.ptr(self.h),
-                          _lib.ptr(self.c), _lib.ptr(self.hT), _lib.ptr(self.hT_lo), _lib.ptr(self.err), st)
-                self.launches += 2 * Ls + Ls * (1 + d.window)
+            _lib.call("wf_lstm_fwd_tc", _lib.ptr(feats), _lib.ptr(params), _lib.ptr(self.params_lo), params_stride, Ls,
+                      d.hidden, L, d.O, d.window, d.num_nodes, self.G, self.Bw, _lib.ptr(self.gates), _lib.ptr(self.h),
+                      _lib.ptr(self.c), _lib.ptr(self.hT), _lib.ptr(self.hT_lo), _lib.ptr(self.err), st)
+            self.launches += 2 * Ls + Ls * (1 + d.window)
         else:
             _lib.call("wf_lstm_fwd", _lib.ptr(feats), _lib.ptr(params), params_stride, Ls, d.hidden, L, d.O, d.window,
                       d.num_nodes, self.G, self.Bw, _lib.ptr(self.gates), _lib.ptr(self.h), _lib.ptr(self.c), st)
@@ -261,12 +292,12 @@ class HybridEngine:
             if not self.training:
                 raise RuntimeError("engine was built with training=False")
             if self.seq:
-                _lib.call("wf_lstm_bwd_seq", _lib.ptr(self.featsT), _lib.ptr(self.featsT_lo), _lib.ptr(self.paramsT),
-                          _lib.ptr(self.paramsT_lo), _lib.ptr(self.w16[2]), _lib.ptr(self.w16[3]), Ls, d.hidden, L, d.O,
+                _lib.call("wf_lstm_bwd_seq", _lib.ptr(self.featsT), _lib.ptr(self.featsT_lo), _lib.ptr(self.pT16[0]),
+                          _lib.ptr(self.pT16[1]), _lib.ptr(self.w16[2]), _lib.ptr(self.w16[3]), Ls, d.hidden, L, d.O,
                           d.window, d.num_nodes, self.G, self.Bw, _lib.ptr(self.gates), _lib.ptr(self.c), _lib.ptr(self.hT),
                           _lib.ptr(self.hT_lo), _lib.ptr(self.dgT), _lib.ptr(self.dlast), _lib.ptr(self.grads), self.P,
                           _lib.ptr(self.ws), self.ws_bytes, _lib.ptr(self.err), st)
-                self.launches += 6 + Ls * 5 - 1  # head bwd + per layer: recurrence, colsum, 2 wgrad, dX (layers >= 1)
+                self.launches += 6 + Ls * 7 - 1  # head bwd + per layer: recurrence, colsum, 2 x (wgrad + split sum), dX
             else:
                 _lib.call("wf_lstm_bwd_tc", _lib.ptr(self.featsT), _lib.ptr(self.featsT_lo), _lib.ptr(self.paramsT),
                           _lib.ptr(self.paramsT_lo), Ls, d.hidden, L, d.O, d.window, d.num_nodes, self.G, self.Bw,
