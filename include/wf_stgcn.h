@@ -208,11 +208,14 @@ int wf_g16_gemm_nt(const float* A, int rows_g, int G, int K, const void* W16_hi,
 
 /* GCNConv + ReLU (model.py:31-42, hybrid_model.py:65-75) on the fp16 hi/lo GEMM, neighbour aggregation fused into
  * the A-operand path.  X dense [G*Bw*R, Cin], Cin % 64 == 0, Cout % 128 == 0; W16 hi/lo = wf_split16(W, 0), shared
- * by all groups; YT hi/lo (optional): bf16 transposed copies [(G*Bw)][Cout][RT16] for the LSTM layer-0 dW. */
+ * by all groups; YT hi/lo (optional): bf16 transposed copies [(G*Bw)][Cout][RT16] for the LSTM layer-0 dW.
+ * gather_rows (optional, i32 [G][gather_max], -1 padded): rows of a window whose aggregation is not the unit self
+ * loop; with agg (scratch f32 [G*Bw*R, Cin]) they are aggregated by a pre-pass instead of inside the GEMM. */
 int wf_gcn_layer_fwd_g16(const float* X, const void* W16_hi, const void* W16_lo, const float* bias,
                          const int* rowptr, const int* col, const float* val, long long rowptr_group_stride,
-                         long long csr_group_stride, int R, int N, int Cin, int Cout, int G, int Bw, int relu,
-                         float* Y, void* YT_hi, void* YT_lo, int* err, void* stream);
+                         long long csr_group_stride, const int* gather_rows, int gather_max,
+                         long long gather_group_stride, float* agg, int R, int N, int Cin, int Cout, int G, int Bw,
+                         int relu, float* Y, void* YT_hi, void* YT_lo, int* err, void* stream);
 
 /* Group stride (16-bit elements) of the p16 (which = 0) / pT16 (which = 1) buffers below: the parameter counts
  * rounded up to 8 so that every group starts 16-byte aligned. */

@@ -13,9 +13,10 @@
 //               [128 x 64] 16-bit into a 3-stage shared-memory ring
 //   warp 1      MMA issuer (TS mode: A from TMEM, B from smem); owns TMEM: 2 accumulator stages x 128 columns
 //               + 3 A stages x 64 columns
-//   warps 2..5  converters: thread = tile row; fp32 row from smem (or CSR gather-aggregate from global for GCN
-//               rows with neighbours) -> hi/lo 16-bit pairs -> tcgen05.st into the TMEM A stage
-//   warps 6..9  epilogue of the PREVIOUS tile while the next one is multiplied: tcgen05.ld -> bias / ReLU ->
+//   warps 2..9  converters: thread = tile row x half a k-block; fp32 from smem (GCN rows with neighbours: the
+//               pre-aggregated row, or a CSR gather-aggregate from global) -> hi/lo 16-bit pairs (packed F2FP
+//               conversions) -> tcgen05.st into the TMEM A stage
+//   warps 10..13 epilogue of the PREVIOUS tile while the next one is multiplied: tcgen05.ld -> bias / ReLU ->
 //               row-major, TB4, or split-K partial stores (+ transposed bf16 hi/lo copies for the weight gradients)
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
@@ -28,7 +29,7 @@ using namespace wftc;
 namespace {
 
 enum { G16_ROWS = 0, G16_NODES = 1, G16_WGRAD = 2 };
-constexpr int G16_THREADS = 320;
+constexpr int G16_THREADS = 448;  // producer, MMA, 8 converter warps, 4 epilogue warps
 constexpr int G16_NST = 3;
 constexpr int G16_A_BYTES = 32768, G16_B_BYTES = 16384, G16_STAGE = G16_A_BYTES + 2 * G16_B_BYTES;
 constexpr int G16_SMEM = G16_NST * G16_STAGE + 1024;
@@ -44,6 +45,7 @@ struct G16Args {
   int a_tb4;
   const float* a_raw; int lda;       // CSR gather on A (GCN aggregation), ROWS only
   const int* rowptr; const int* col; const float* val; long long g_rowptr, g_csr;
+  const float* agg;                  // optional: pre-aggregated rows (same indexing as a_raw) for rows with neighbours
   float* C; int ldc; long long c_gstride, c_sstride; int c_cols;
   const float* bias; const float* bias2; long long bias_gstride; int relu;
   __nv_bfloat16* ct_hi; __nv_bfloat16* ct_lo;   // transposed copies [(g*Bw + w)][c_cols][RT]
@@ -59,18 +61,21 @@ __device__ __forceinline__ void g16_mma(uint32_t d_tmem, uint32_t a_tmem, uint64
                ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
 }
 
+// (a, b) -> packed 16-bit hi pair and lo pair (a in the low half).  Packed conversions (F2FP) run on the ALU pipe;
+// the scalar cvt.rn.f16.f32 goes through the quarter-rate conversion unit.
 template <int FMT>
 __device__ __forceinline__ void split_pair(float a, float b, uint32_t& hi, uint32_t& lo) {
   if (FMT == 0) {
-    const __half ha = __float2half_rn(a), hb = __float2half_rn(b);
-    const __half la = __float2half_rn(a - __half2float(ha)), lb = __float2half_rn(b - __half2float(hb));
-    hi = (uint32_t)__half_as_ushort(ha) | ((uint32_t)__half_as_ushort(hb) << 16);
-    lo = (uint32_t)__half_as_ushort(la) | ((uint32_t)__half_as_ushort(lb) << 16);
+    const __half2 h = __floats2half2_rn(a, b);
+    const float2 f = __half22float2(h);
+    const __half2 l = __floats2half2_rn(a - f.x, b - f.y);
+    hi = *reinterpret_cast<const uint32_t*>(&h);
+    lo = *reinterpret_cast<const uint32_t*>(&l);
   } else {
-    const __nv_bfloat16 ha = __float2bfloat16_rn(a), hb = __float2bfloat16_rn(b);
-    const __nv_bfloat16 la = __float2bfloat16_rn(a - __bfloat162float(ha)), lb = __float2bfloat16_rn(b - __bfloat162float(hb));
-    hi = (uint32_t)__bfloat16_as_ushort(ha) | ((uint32_t)__bfloat16_as_ushort(hb) << 16);
-    lo = (uint32_t)__bfloat16_as_ushort(la) | ((uint32_t)__bfloat16_as_ushort(lb) << 16);
+    const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    hi = *reinterpret_cast<const uint32_t*>(&h);
+    const __nv_bfloat162 l = __floats2bfloat162_rn(a - __uint_as_float(hi << 16), b - __uint_as_float(hi & 0xFFFF0000u));
+    lo = *reinterpret_cast<const uint32_t*>(&l);
   }
 }
 
@@ -120,7 +125,7 @@ wf_g16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
   const int total = a.n_tiles * a.m_tiles * a.G * a.splits;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < NST; ++s) { mbar_init(&full[s], 1); mbar_init(&aready[s], 4); mbar_init(&empty[s], 1); }
+    for (int s = 0; s < NST; ++s) { mbar_init(&full[s], 1); mbar_init(&aready[s], 8); mbar_init(&empty[s], 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(&dfull[s], 1); mbar_init(&dempty[s], 4); }
     mbar_fence_init();
     tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmBhi); tma_prefetch_desc(&tmBlo);
@@ -134,29 +139,36 @@ wf_g16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
     if (lane == 0) {
+      // cursor over this CTA's (tile, segment, k-block) sequence.  (An L2 prefetch cursor running ahead of it was
+      // measured and made things slightly slower: the ring is not waiting on HBM latency.)
+      struct Cursor { int tile, seg, kb; TileCoord c; };
+      auto cur_init = [&](Cursor& u, int tile) { u.tile = tile; u.seg = 0; if (tile < total) { u.c = decode_tile(a, tile); u.kb = u.c.kb0; } };
+      auto cur_next = [&](Cursor& u) {
+        if (++u.kb == u.c.kb0 + u.c.nkb_loc) { u.kb = u.c.kb0; if (++u.seg == a.nseg) cur_init(u, u.tile + gridDim.x); }
+      };
+      Cursor cu;
+      cur_init(cu, blockIdx.x);
       int it = 0;
-      bool ok = true;
-      for (int tile = blockIdx.x; tile < total && ok; tile += gridDim.x) {
-        const TileCoord c = decode_tile(a, tile);
-        for (int seg = 0; seg < a.nseg && ok; ++seg)
-          for (int kb = c.kb0; kb < c.kb0 + c.nkb_loc; ++kb, ++it) {
-            const int s = it % NST, ph = (it / NST) & 1;
-            if (!mbar_wait(&empty[s], ph ^ 1)) { atomicExch(a.err, 31); ok = false; break; }
-            uint8_t* st = smem + s * STAGE;
-            mbar_expect_tx(&full[s], STAGE);
-            const int ka = a.a_k0 + kb * 64, kbb = a.b_k0 + kb * 64;
-            if (a.mode == G16_NODES && a.a_tb4) {
-              tma_load_4d(st, &tmA, &full[s], 0, 0, ka >> 2, c.blk);
-              tma_load_4d(st + 16384, &tmA, &full[s], 0, 0, (ka >> 2) + 8, c.blk);
-            } else {
-              const int zc = a.mode == G16_NODES ? c.zt : c.a_z0 + seg * c.zstep;
-              tma_load_3d(st, &tmA, &full[s], ka, c.a_row, zc);
-              tma_load_3d(st + 16384, &tmA, &full[s], ka + 32, c.a_row, zc);
-            }
-            const int zb = c.b_z0 + seg * c.zstep;
-            tma_load_3d(st + A_BYTES, &tmBhi, &full[s], kbb, c.ntile * 128, zb);
-            tma_load_3d(st + A_BYTES + B_BYTES, &tmBlo, &full[s], kbb, c.ntile * 128, zb);
-          }
+      while (cu.tile < total) {
+        const int s = it % NST, ph = (it / NST) & 1;
+        if (!mbar_wait(&empty[s], ph ^ 1)) { atomicExch(a.err, 31); break; }
+        const TileCoord& c = cu.c;
+        uint8_t* st = smem + s * STAGE;
+        mbar_expect_tx(&full[s], STAGE);
+        const int ka = a.a_k0 + cu.kb * 64, kbb = a.b_k0 + cu.kb * 64;
+        if (a.mode == G16_NODES && a.a_tb4) {
+          tma_load_4d(st, &tmA, &full[s], 0, 0, ka >> 2, c.blk);
+          tma_load_4d(st + 16384, &tmA, &full[s], 0, 0, (ka >> 2) + 8, c.blk);
+        } else {
+          const int zc = a.mode == G16_NODES ? c.zt : c.a_z0 + cu.seg * c.zstep;
+          tma_load_3d(st, &tmA, &full[s], ka, c.a_row, zc);
+          tma_load_3d(st + 16384, &tmA, &full[s], ka + 32, c.a_row, zc);
+        }
+        const int zb = c.b_z0 + cu.seg * c.zstep;
+        tma_load_3d(st + A_BYTES, &tmBhi, &full[s], kbb, c.ntile * 128, zb);
+        tma_load_3d(st + A_BYTES + B_BYTES, &tmBlo, &full[s], kbb, c.ntile * 128, zb);
+        cur_next(cu);
+        ++it;
       }
     }
   } else if (warp == 1) {
@@ -190,70 +202,93 @@ wf_g16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
         __syncwarp();
       }
     }
-  } else if (warp < 6) {
+  } else if (warp < 10) {
     // ------------------------------------------------------------------ converters (A: fp32 -> hi/lo 16-bit -> TMEM)
-    const int q = warp & 3, row = q * 32 + lane;
+    // warps 2..5 take the first 32 k of every k-block, warps 6..9 the second 32 (TMEM lane quarter = warp & 3)
+    const int q = warp & 3, row = q * 32 + lane, h = (warp - 2) >> 2;
     const uint32_t tlane = tbase + ((uint32_t)(q * 32) << 16);
     int it = 0;
     bool ok = true;
+    // CSR row descriptor of this thread's row, fetched one tile ahead (two dependent global loads)
+    int n_p0 = 0, n_p1 = 0, n_col = -1;
+    float n_val = 0.f;
+    auto fetch_row = [&](int tile) {
+      n_p0 = 0; n_p1 = 0; n_col = -1; n_val = 0.f;
+      if (a.mode == G16_ROWS && a.rowptr != nullptr && tile < total) {
+        const TileCoord c = decode_tile(a, tile);
+        const int grow = c.mt * 128 + row;
+        if (grow < a.rows_g) {
+          const int rr = grow % a.R;
+          const int* rp = a.rowptr + c.g * a.g_rowptr;
+          n_p0 = __ldg(rp + rr); n_p1 = __ldg(rp + rr + 1);
+          n_col = __ldg(a.col + c.g * a.g_csr + n_p0);
+          n_val = __ldg(a.val + c.g * a.g_csr + n_p0);
+        }
+      }
+    };
+    fetch_row(blockIdx.x);
     for (int tile = blockIdx.x; tile < total && ok; tile += gridDim.x) {
       const TileCoord c = decode_tile(a, tile);
-      int p0 = 0, p1 = 0;
+      const int p0 = n_p0, p1 = n_p1;
       long long wbase = 0;
+      int grow_in_w = 0;
       bool gather = false;
       if (a.mode == G16_ROWS && a.rowptr != nullptr) {  // rows whose aggregation is not the unit self loop
         const int grow = c.mt * 128 + row;
         if (grow < a.rows_g) {
           const int w = grow / a.R, rr = grow - w * a.R;
-          const int* rp = a.rowptr + c.g * a.g_rowptr;
-          p0 = rp[rr]; p1 = rp[rr + 1];
+          grow_in_w = rr;
           wbase = ((long long)c.g * a.a_group_rows + (long long)w * a.R) * a.lda;
-          gather = !(p1 - p0 == 1 && a.col[c.g * a.g_csr + p0] == rr && a.val[c.g * a.g_csr + p0] == 1.0f);
+          gather = !(p1 - p0 == 1 && n_col == rr && n_val == 1.0f);
         }
       }
+      fetch_row(tile + gridDim.x);
       const int nk = c.nkb_loc * a.nseg;
       for (int k = 0; k < nk; ++k, ++it) {
         const int s = it % NST, ph = (it / NST) & 1;
         if (!mbar_wait(&full[s], ph) || !mbar_wait(&empty[s], ph ^ 1)) { if (lane == 0) atomicExch(a.err, 34); ok = false; break; }
-        uint32_t hi[32], lo[32];
+        uint32_t hi[16], lo[16];
         if (!gather) {
-          const uint8_t* st = smem + s * STAGE;
+          const uint8_t* st = smem + s * STAGE + h * 16384;
 #pragma unroll
-          for (int h = 0; h < 2; ++h)
-#pragma unroll
-            for (int ch = 0; ch < 8; ++ch) {
-              // TB4 stage: [channel group][row][4 floats]; otherwise two SWIZZLE_128B boxes of 32 floats per row
-              const uint8_t* p = st + h * 16384 + (a.a_tb4 ? ch * 2048 + row * 16 : row * 128 + ((ch ^ (row & 7)) << 4));
-              const float4 v = *reinterpret_cast<const float4*>(p);
-              split_pair<FMT>(v.x, v.y, hi[h * 16 + 2 * ch], lo[h * 16 + 2 * ch]);
-              split_pair<FMT>(v.z, v.w, hi[h * 16 + 2 * ch + 1], lo[h * 16 + 2 * ch + 1]);
-            }
+          for (int ch = 0; ch < 8; ++ch) {
+            // TB4 stage: [channel group][row][4 floats]; otherwise a SWIZZLE_128B box of 32 floats per row
+            const uint8_t* p = st + (a.a_tb4 ? ch * 2048 + row * 16 : row * 128 + ((ch ^ (row & 7)) << 4));
+            const float4 v = *reinterpret_cast<const float4*>(p);
+            split_pair<FMT>(v.x, v.y, hi[2 * ch], lo[2 * ch]);
+            split_pair<FMT>(v.z, v.w, hi[2 * ch + 1], lo[2 * ch + 1]);
+          }
         } else {
           const int* cl = a.col + c.g * a.g_csr;
           const float* vl = a.val + c.g * a.g_csr;
-          const int k0 = a.a_k0 + (c.kb0 + k % c.nkb_loc) * 64;
+          const int k0 = a.a_k0 + (c.kb0 + k % c.nkb_loc) * 64 + 32 * h;
+          float acc[32];
 #pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            float acc[32];
+          for (int j = 0; j < 32; ++j) acc[j] = 0.f;
+          if (a.agg != nullptr) {  // aggregated by wf_agg_rows_kernel beforehand: one row read
+            const float4* src = reinterpret_cast<const float4*>(a.agg + wbase + (long long)grow_in_w * a.lda + k0);
 #pragma unroll
-            for (int j = 0; j < 32; ++j) acc[j] = 0.f;
-            for (int p = p0; p < p1; ++p) {
-              const float v = __ldg(vl + p);
-              const float4* src = reinterpret_cast<const float4*>(a.a_raw + wbase + (long long)__ldg(cl + p) * a.lda + k0 + 32 * h);
-#pragma unroll
-              for (int ch = 0; ch < 8; ++ch) {
-                const float4 x = __ldg(src + ch);
-                acc[4 * ch + 0] = fmaf(v, x.x, acc[4 * ch + 0]); acc[4 * ch + 1] = fmaf(v, x.y, acc[4 * ch + 1]);
-                acc[4 * ch + 2] = fmaf(v, x.z, acc[4 * ch + 2]); acc[4 * ch + 3] = fmaf(v, x.w, acc[4 * ch + 3]);
-              }
+            for (int ch = 0; ch < 8; ++ch) {
+              const float4 x = __ldg(src + ch);
+              acc[4 * ch + 0] = x.x; acc[4 * ch + 1] = x.y; acc[4 * ch + 2] = x.z; acc[4 * ch + 3] = x.w;
             }
+          } else
+          for (int p = p0; p < p1; ++p) {
+            const float v = __ldg(vl + p);
+            const float4* src = reinterpret_cast<const float4*>(a.a_raw + wbase + (long long)__ldg(cl + p) * a.lda + k0);
 #pragma unroll
-            for (int j = 0; j < 16; ++j) split_pair<FMT>(acc[2 * j], acc[2 * j + 1], hi[h * 16 + j], lo[h * 16 + j]);
+            for (int ch = 0; ch < 8; ++ch) {
+              const float4 x = __ldg(src + ch);
+              acc[4 * ch + 0] = fmaf(v, x.x, acc[4 * ch + 0]); acc[4 * ch + 1] = fmaf(v, x.y, acc[4 * ch + 1]);
+              acc[4 * ch + 2] = fmaf(v, x.z, acc[4 * ch + 2]); acc[4 * ch + 3] = fmaf(v, x.w, acc[4 * ch + 3]);
+            }
           }
+#pragma unroll
+          for (int j = 0; j < 16; ++j) split_pair<FMT>(acc[2 * j], acc[2 * j + 1], hi[j], lo[j]);
         }
         __syncwarp();  // gather / non-gather lanes diverged above
-        tmem_st32(tlane + A_COL + s * 64, hi);
-        tmem_st32(tlane + A_COL + s * 64 + 32, lo);
+        tmem_st16(tlane + A_COL + s * 64 + 16 * h, hi);
+        tmem_st16(tlane + A_COL + s * 64 + 32 + 16 * h, lo);
         tmem_wait_st();
         tc_fence_before();
         __syncwarp();
@@ -320,9 +355,10 @@ wf_g16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
                   const long long ti = ctbase + (long long)(cc + j + e) * a.RT;
-                  const __nv_bfloat16 h = __float2bfloat16_rn(ov[e]);
-                  a.ct_hi[ti] = h;
-                  a.ct_lo[ti] = __float2bfloat16_rn(ov[e] - __bfloat162float(h));
+                  uint32_t ph, pl;
+                  split_pair<1>(ov[e], 0.f, ph, pl);
+                  reinterpret_cast<uint16_t*>(a.ct_hi)[ti] = (uint16_t)ph;
+                  reinterpret_cast<uint16_t*>(a.ct_lo)[ti] = (uint16_t)pl;
                 }
               }
             }
@@ -407,13 +443,37 @@ int wf_launch_split16(const float* src, long long src_gstride, void* hi, void* l
   return WF_OK;
 }
 
+// AGG[z][rr] = sum_p val[p] * X[z][col[p]] for the listed rows rr of every window z (rows whose aggregation is not
+// the unit self loop; -1 entries are padding).  grid (ceil(nlist / 8), G*Bw), one warp per (row, window).
+static __global__ void __launch_bounds__(256) wf_agg_rows_kernel(const float* __restrict__ X, float* __restrict__ AGG, int C, int R,
+                                                                 int Bw, const int* __restrict__ rowptr, const int* __restrict__ col,
+                                                                 const float* __restrict__ val, long long g_rowptr, long long g_csr,
+                                                                 const int* __restrict__ list, int nlist, long long g_list) {
+  const int z = blockIdx.y, g = z / Bw, i = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (i >= nlist) return;
+  const int rr = list[g * g_list + i];
+  if (rr < 0) return;
+  const int* rp = rowptr + g * g_rowptr;
+  const int p0 = rp[rr], p1 = rp[rr + 1];
+  const float* Xz = X + (long long)z * R * C;
+  for (int c4 = lane; c4 < (C >> 2); c4 += 32) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int p = p0; p < p1; ++p) {
+      const float v = __ldg(val + g * g_csr + p);
+      const float4 x = __ldg(reinterpret_cast<const float4*>(Xz + (long long)__ldg(col + g * g_csr + p) * C) + c4);
+      acc.x = fmaf(v, x.x, acc.x); acc.y = fmaf(v, x.y, acc.y); acc.z = fmaf(v, x.z, acc.z); acc.w = fmaf(v, x.w, acc.w);
+    }
+    reinterpret_cast<float4*>(AGG + ((long long)z * R + rr) * C)[c4] = acc;
+  }
+}
+
 // ---- C[g] = (A_hat[g]) A[g] W[g]^T (+bias, +bias2, relu): rows tiled, optional CSR gather on A and transposed
 // bf16 hi/lo copies of C.  W16 hi/lo: [Gb][N, K] 16-bit (fmt).
 int wf_launch_g16_rows(int fmt, const float* A, long long a_rows_total, int lda, int a_group_rows, int rows_g, int G, int K,
                        const void* Whi, const void* Wlo, int ldb, long long b_gstride, int b_shared, int N, const float* bias,
                        const float* bias2, long long bias_gstride, int relu, float* C, int ldc, long long c_gstride,
                        const int* rowptr, const int* col, const float* val, long long g_rowptr, long long g_csr, int R, int Bw,
-                       void* ct_hi, void* ct_lo, int Nn, int* err, cudaStream_t st) {
+                       void* ct_hi, void* ct_lo, int Nn, const float* agg, int* err, cudaStream_t st) {
   WF_REQUIRE(K % 64 == 0 && K >= 64, "g16_rows: K=%d must be a multiple of 64", K);
   WF_REQUIRE(N % 128 == 0, "g16_rows: N=%d must be a multiple of 128", N);
   WF_REQUIRE(lda % 4 == 0 && ldb % 8 == 0 && ldc % 4 == 0, "g16_rows: leading dimensions must keep 16-byte alignment");
@@ -428,7 +488,7 @@ int wf_launch_g16_rows(int fmt, const float* A, long long a_rows_total, int lda,
   g16_defaults(a);
   a.mode = G16_ROWS; a.m_tiles = wf_cdiv(rows_g, 128); a.n_tiles = N / 128; a.G = G;
   a.rows_g = rows_g; a.a_group_rows = a_group_rows; a.nkb = K / 64; a.b_gmul = b_shared ? 0 : 1;
-  a.a_raw = A; a.lda = lda; a.rowptr = rowptr; a.col = col; a.val = val; a.g_rowptr = g_rowptr; a.g_csr = g_csr;
+  a.a_raw = A; a.lda = lda; a.rowptr = rowptr; a.col = col; a.val = val; a.g_rowptr = g_rowptr; a.g_csr = g_csr; a.agg = agg;
   a.R = R > 0 ? R : rows_g; a.Bw = Bw > 0 ? Bw : 1;
   a.Nn = Nn > 0 ? Nn : a.R; a.Np = wf_np(a.Nn); a.RT = (a.R / a.Nn) * a.Np;
   WF_REQUIRE(ct_hi == nullptr || a.R % a.Nn == 0, "g16_rows: transposed copies need R to be a multiple of the node count");
@@ -566,15 +626,28 @@ extern "C" long long wf_transposed_pitch16(int T, int N) { return (long long)T *
 // GCNConv + ReLU (model.py:31-42, hybrid_model.py:65-75): Y = relu((A_hat X) W^T + b) on the persistent fp16 hi/lo GEMM
 // with the neighbour aggregation fused into the A-operand path.  X dense [G*Bw*R, Cin], Cin % 64 == 0, Cout % 128 == 0,
 // W16 hi/lo = wf_split16(W, fmt 0), shared by all groups; YT hi/lo (optional): bf16 transposed copies [(G*Bw)][Cout][RT16].
+// gather_rows (optional): per group the rows of a window whose aggregation is not the unit self loop, padded with -1 to
+// gather_max, with `agg` a scratch [G*Bw*R, Cin]: those rows are aggregated by a small pre-pass and the GEMM reads one
+// row instead of walking the CSR inside its operand pipeline.
 extern "C" int wf_gcn_layer_fwd_g16(const float* X, const void* W16_hi, const void* W16_lo, const float* bias, const int* rowptr,
                                     const int* col, const float* val, long long rowptr_group_stride, long long csr_group_stride,
-                                    int R, int N, int Cin, int Cout, int G, int Bw, int relu, float* Y, void* YT_hi, void* YT_lo,
+                                    const int* gather_rows, int gather_max, long long gather_group_stride, float* agg, int R,
+                                    int N, int Cin, int Cout, int G, int Bw, int relu, float* Y, void* YT_hi, void* YT_lo,
                                     int* err, void* stream) {
   WF_REQUIRE(G > 0 && Bw > 0 && R > 0 && N > 0, "gcn_layer_fwd_g16: bad batch");
   const long long rows_g = (long long)Bw * R;
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool pre = rowptr != nullptr && gather_rows != nullptr && agg != nullptr && gather_max > 0;
+  if (pre) {
+    WF_REQUIRE(Cin % 4 == 0, "gcn_layer_fwd_g16: Cin must be a multiple of 4");
+    wf_agg_rows_kernel<<<dim3(wf_cdiv(gather_max, 8), G * Bw), 256, 0, st>>>(X, agg, Cin, R, Bw, rowptr, col, val, rowptr_group_stride,
+                                                                            csr_group_stride, gather_rows, gather_max,
+                                                                            gather_group_stride);
+    WF_CHECK_LAUNCH("agg_rows");
+  }
   return wf_launch_g16_rows(0, X, rows_g * G, Cin, (int)rows_g, (int)rows_g, G, Cin, W16_hi, W16_lo, Cin, 0, 1, Cout, bias, nullptr,
                             0, relu, Y, Cout, rows_g * Cout, rowptr, col, val, rowptr_group_stride, csr_group_stride, R, Bw, YT_hi,
-                            YT_lo, N, err, (cudaStream_t)stream);
+                            YT_lo, N, pre ? agg : nullptr, err, st);
 }
 
 // Test / general entry point: C[g] = A[g] W[g]^T (+ bias + bias2, relu), W16 hi/lo [G][N, K] from wf_split16(W, fmt).
@@ -585,5 +658,5 @@ extern "C" int wf_g16_gemm_nt(const float* A, int rows_g, int G, int K, const vo
   WF_REQUIRE(fmt == 0 || fmt == 1, "g16_gemm_nt: fmt must be 0 (fp16) or 1 (bf16)");
   return wf_launch_g16_rows(fmt, A, (long long)rows_g * G, K, rows_g, rows_g, G, K, W16_hi, W16_lo, K, w_group_stride, 0, N, bias,
                             bias2, bias_group_stride, relu, C, N, (long long)rows_g * N, nullptr, nullptr, nullptr, 0, 0, 0, 1,
-                            nullptr, nullptr, 0, err, (cudaStream_t)stream);
+                            nullptr, nullptr, 0, nullptr, err, (cudaStream_t)stream);
 }

@@ -124,17 +124,20 @@ __device__ __forceinline__ void tmem_st4(uint32_t taddr, const uint32_t* v) {
 __device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
 __device__ __forceinline__ float fast_tanh(float x) { return 2.0f * __fdividef(1.0f, 1.0f + __expf(-2.0f * x)) - 1.0f; }
 
+// packed conversions (F2FP, ALU pipe); the residuals ra, rb feed the lo half
 __device__ __forceinline__ uint32_t pack_f16(float a, float b, float& ra, float& rb) {
-  const __half ha = __float2half_rn(a), hb = __float2half_rn(b);
-  ra = a - __half2float(ha);
-  rb = b - __half2float(hb);
-  return (uint32_t)__half_as_ushort(ha) | ((uint32_t)__half_as_ushort(hb) << 16);
+  const __half2 h = __floats2half2_rn(a, b);
+  const float2 f = __half22float2(h);
+  ra = a - f.x;
+  rb = b - f.y;
+  return *reinterpret_cast<const uint32_t*>(&h);
 }
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b, float& ra, float& rb) {
-  const __nv_bfloat16 ha = __float2bfloat16_rn(a), hb = __float2bfloat16_rn(b);
-  ra = a - __bfloat162float(ha);
-  rb = b - __bfloat162float(hb);
-  return (uint32_t)__bfloat16_as_ushort(ha) | ((uint32_t)__bfloat16_as_ushort(hb) << 16);
+  const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  const uint32_t u = *reinterpret_cast<const uint32_t*>(&h);
+  ra = a - __uint_as_float(u << 16);
+  rb = b - __uint_as_float(u & 0xFFFF0000u);
+  return u;
 }
 
 // ================================================================================= forward
@@ -275,10 +278,13 @@ wf_lstm_seq_fwd_kernel(const __grid_constant__ CUtensorMap tmWhi, const __grid_c
             __nv_bfloat16* ht = a.HT + ((long long)z * L + u0 + 8 * c) * a.RT + tcol;
             __nv_bfloat16* htl = a.HT_lo + ((long long)z * L + u0 + 8 * c) * a.RT + tcol;
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const __nv_bfloat16 hb = __float2bfloat16_rn(hh[j]);
-              ht[(long long)j * a.RT] = hb;
-              htl[(long long)j * a.RT] = __float2bfloat16_rn(hh[j] - __bfloat162float(hb));
+            for (int j = 0; j < 8; j += 2) {
+              float ra, rb, d0, d1;
+              const uint32_t uh = pack_bf16(hh[j], hh[j + 1], ra, rb), ul = pack_bf16(ra, rb, d0, d1);
+              reinterpret_cast<uint16_t*>(ht)[(long long)j * a.RT] = (uint16_t)uh;
+              reinterpret_cast<uint16_t*>(ht)[(long long)(j + 1) * a.RT] = (uint16_t)(uh >> 16);
+              reinterpret_cast<uint16_t*>(htl)[(long long)j * a.RT] = (uint16_t)ul;
+              reinterpret_cast<uint16_t*>(htl)[(long long)(j + 1) * a.RT] = (uint16_t)(ul >> 16);
             }
           }
         }

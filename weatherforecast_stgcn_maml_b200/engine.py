@@ -172,6 +172,7 @@ class HybridEngine:
         self.ws_bytes = int(ws)
         self.ws = torch.empty(self.ws_bytes, dtype=torch.uint8, device=self.device)
         self.feats = None
+        self.agg = None  # scratch of the GCN pre-aggregation pass (persistent path)
         self.launches = 0  # kernels enqueued by this engine (bench.py reports it)
 
     def check(self):
@@ -203,8 +204,10 @@ class HybridEngine:
         d, st = self.dims, _lib.stream_ptr()
         if isinstance(graphs, RegionGraph):
             rp, cl, vl, rps, cs = graphs.rowptr, graphs.col, graphs.val, 0, 0
+            gl, gmax, gls = graphs.gather_rows, int(graphs.gather_rows.numel()), 0
         elif isinstance(graphs, StackedGraphs):
             rp, cl, vl, rps, cs = graphs.rowptr, graphs.col, graphs.val, graphs.rowptr_stride, graphs.csr_stride
+            gl, gmax, gls = graphs.gather_rows, graphs.gather_max, graphs.gather_rows.shape[1]
         else:
             raise TypeError("graphs must be a RegionGraph or StackedGraphs")
         if graphs.R != d.R:
@@ -217,8 +220,11 @@ class HybridEngine:
             if self.seq and dense and cin % 64 == 0:
                 want_t = self.training and i == nlayers - 1
                 w16 = self._gcn_w_lo(Wt)
+                if self.agg is None:
+                    self.agg = torch.empty(self.rows, d.hidden, dtype=torch.float32, device=self.device)
                 _lib.call("wf_gcn_layer_fwd_g16", _lib.ptr(src), _lib.ptr(w16[0]), _lib.ptr(w16[1]), _lib.ptr(b),
-                          _lib.ptr(rp), _lib.ptr(cl), _lib.ptr(vl), rps, cs, d.R, d.num_nodes, cin, d.hidden, self.G,
+                          _lib.ptr(rp), _lib.ptr(cl), _lib.ptr(vl), rps, cs, _lib.ptr(gl) if gmax > 0 else None, gmax, gls,
+                          _lib.ptr(self.agg), d.R, d.num_nodes, cin, d.hidden, self.G,
                           self.Bw, 1, _lib.ptr(dst), _lib.ptr(self.featsT) if want_t else None,
                           _lib.ptr(self.featsT_lo) if want_t else None, _lib.ptr(self.err), st)
             elif self.tc and not self.seq and dense and cin % 32 == 0:

@@ -45,6 +45,20 @@ class RegionGraph:
                       _lib.ptr(self.val), _lib.ptr(self.rowptr_t), _lib.ptr(self.col_t), _lib.ptr(self.val_t),
                       _lib.ptr(ws), nbytes, _lib.stream_ptr())
         self._ws = ws  # keep alive until the stream has consumed it
+        self._gather_rows = None
+        _ = self.gather_rows  # computed eagerly (it synchronises): never inside a CUDA-graph capture
+
+    @property
+    def gather_rows(self):
+        """i32 list of the rows whose aggregation is NOT the unit self loop (the t = 0 slice for the reference's
+        graphs): the only rows the GCN pre-aggregation pass has to touch."""
+        if self._gather_rows is None:
+            first = self.rowptr[:-1].long()
+            deg = (self.rowptr[1:] - self.rowptr[:-1])
+            rows = torch.arange(self.R, device=self.device)
+            ident = (deg == 1) & (self.col[first].long() == rows) & (self.val[first] == 1.0)
+            self._gather_rows = torch.nonzero(~ident).flatten().to(torch.int32).contiguous()
+        return self._gather_rows
 
     @property
     def nnz(self):
@@ -65,6 +79,11 @@ class StackedGraphs:
         self.rowptr_t = torch.stack([g.rowptr_t for g in graphs]).contiguous()
         self.col_t = torch.stack([g.col_t for g in graphs]).contiguous()
         self.val_t = torch.stack([g.val_t for g in graphs]).contiguous()
+        lists = [g.gather_rows for g in graphs]
+        self.gather_max = max(int(l.numel()) for l in lists)
+        self.gather_rows = torch.full((self.G, max(self.gather_max, 1)), -1, dtype=torch.int32, device=self.device)
+        for i, l in enumerate(lists):
+            self.gather_rows[i, :l.numel()] = l
 
     @property
     def rowptr_stride(self):
