@@ -249,35 +249,79 @@ def stage_breakdown(trainer, reps=3):
     return out
 
 
-def roofline_from_stages(stages, G, peak, peak_src):
-    """Algorithmic traffic of each launcher family per call (SURVEY.md 8d figures)."""
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernels from `ncu --set full`
+# (profiles/r1_final_ncu_summary.md); None until a capture of the current kernels is committed
+NCU_TRAFFIC = {"wf_lstm_seq_fwd_kernel": None, "wf_lstm_seq_bwd_kernel": None}
+
+
+def time_recurrence_kernels(trainer, reps=10):
+    """CUDA-event time of ONE launch of each persistent LSTM kernel (layer 1: 128-wide input, as 3 of 4 layers) on the
+    trainer's own buffers, on the stream the kernels are launched on."""
+    import torch
+
+    from weatherforecast_stgcn_maml_b200 import _lib
+
+    e, d = trainer.engine, trainer.engine.dims
+    Ls, L, st = d.lstm_layers, d.lstm_hidden, _lib.stream_ptr()
+    out = {}
+
+    def fwd():
+        _lib.call("wf_lstm_seq_recur_fwd", _lib.ptr(e.gates[1]), _lib.ptr(e.c[1]), _lib.ptr(e.h[1]), _lib.ptr(e.hT[1]),
+                  _lib.ptr(e.hT_lo[1]), _lib.ptr(e.w16[0]), _lib.ptr(e.w16[1]), 1, Ls, L, d.window, d.num_nodes, e.G, e.Bw,
+                  _lib.ptr(e.err), st)
+
+    def bwd():
+        _lib.call("wf_lstm_seq_recur_bwd", _lib.ptr(e.gates[1]), _lib.ptr(e.c[1]), _lib.ptr(e.dgT), _lib.ptr(e.ws), 0,
+                  _lib.ptr(e.w16[2]), _lib.ptr(e.w16[3]), 1, Ls, L, d.window, d.num_nodes, e.G, e.Bw, _lib.ptr(e.err), st)
+
+    e.ws.zero_()  # dh from the layer above: zeros (timing does not depend on values)
+    for name, fn in (("wf_lstm_seq_fwd_kernel", fwd), ("wf_lstm_seq_bwd_kernel", bwd)):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        out[name] = e0.elapsed_time(e1) / reps
+    e.check()
+    return out
+
+
+def roofline_report(stages, kernel_ms, G, peak, peak_src):
+    """Roofline of the dominant kernels.  Algorithmic bytes = the saved-activation traffic a
+    (row, step) needs (SURVEY.md 8d figures for gates / c / h, plus this design's transposed bf16 copies), times the
+    G*N*T valid (row, step) pairs of one launch; TB4 tile padding is NOT counted."""
     N, T, F, L, C = NLAT * NLON, 24, 256, 128, 24
     R = T * N
     E = N * KNN + R
     csr = E * 8 + (R + 1) * 4
-    # GCN layer call (the 256->256 layers dominate): read X, write Y, W, bias, CSR -- per window x G windows
+    per_row_step = {
+        # read the input projection (4L f32); write gates (4L), c (L), h (L) f32 and h^T as bf16 hi + lo (2 x L x 2 B)
+        "wf_lstm_seq_fwd_kernel": 4 * L * 4 + (4 * L + L + L) * 4 + 2 * L * 2,
+        # read gates (4L), c[t], c[t-1] (2L), dh from above (L); write dG (4L) and dG^T (4L) f32
+        "wf_lstm_seq_bwd_kernel": (4 * L + 2 * L + L) * 4 + (4 * L + 4 * L) * 4,
+    }
+    calls_per_step = 16  # 4 layers x 4 window passes of a meta-step, each kernel
+    kern = {}
+    for name, ms in kernel_ms.items():
+        b = per_row_step[name] * G * R
+        kern[name] = {"ms_per_launch": ms, "algorithmic_bytes": b, "GBps": b / (ms * 1e-3) / 1e9,
+                      "frac": b / (ms * 1e-3) / 1e9 / peak, "share_of_step_ms": ms * calls_per_step,
+                      "traffic": NCU_TRAFFIC.get(name)}
+    best = max(kern, key=lambda k: kern[k]["ms_per_launch"])
+    # graph conv (BASELINE.json asks for it): one 256 -> 256 GCN layer call = read X, write Y, CSR, W
     gcn_bytes = G * (R * (F + F) * 4 + csr) + F * F * 4
-    gcn1_bytes = G * (R * (C + F) * 4 + csr) + F * C * 4
-    gcn_avg = (gcn1_bytes + 3 * gcn_bytes) / 4
-    # LSTM forward call: all 4 layers; per layer read input, write+read x-projection, write gates, h, c
-    lstm_f = 0
-    for l in range(4):
-        kin = F if l == 0 else L
-        lstm_f += G * R * (kin + 4 * L + 4 * L + 4 * L + 3 * L + L) * 4 + G * (4 * L * (kin + L) + 8 * L) * 4
-    # BPTT call: per layer read gates, c, c_prev; write dG; read dG (next step GEMM) ; weight-grad GEMMs read dG, X, H
-    lstm_b = 0
-    for l in range(4):
-        kin = F if l == 0 else L
-        lstm_b += G * R * (4 * L + 2 * L + 4 * L + 4 * L + L) * 4 + G * R * (2 * 4 * L + kin + L + 4 * L + kin) * 4
-    table = {"wf_gcn_layer_fwd": gcn_avg, "wf_lstm_fwd": lstm_f, "wf_lstm_bwd": lstm_b}
-    best = max((k for k in stages if k in table), key=lambda k: stages[k]["ms_per_meta_step"])
-    st = stages[best]
-    per_call_ms = st["ms_per_meta_step"] / st["calls"]
-    achieved = table[best] / (per_call_ms * 1e-3) / 1e9
-    return {"bound": "hbm", "kernel": best, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-            "traffic": None, "peak_source": peak_src, "ms_per_call": per_call_ms, "algorithmic_bytes_per_call": table[best],
-            "graph_conv_GBps": gcn_avg / (stages["wf_gcn_layer_fwd"]["ms_per_meta_step"] / stages["wf_gcn_layer_fwd"]["calls"] * 1e-3) / 1e9,
-            "graph_conv_frac": gcn_avg / (stages["wf_gcn_layer_fwd"]["ms_per_meta_step"] / stages["wf_gcn_layer_fwd"]["calls"] * 1e-3) / 1e9 / peak}
+    gname = "wf_gcn_layer_fwd_g16" if "wf_gcn_layer_fwd_g16" in stages else "wf_gcn_layer_fwd_tc"
+    g = stages.get(gname)
+    gcn_gbps = gcn_bytes / (g["ms_per_meta_step"] / g["calls"] * 1e-3) / 1e9 if g else None
+    return {"bound": "hbm", "kernel": best, "achieved": kern[best]["GBps"], "peak": peak, "unit": "GB/s",
+            "frac": kern[best]["frac"], "traffic": kern[best]["traffic"], "peak_source": peak_src,
+            "ms_per_launch": kern[best]["ms_per_launch"], "algorithmic_bytes_per_launch": kern[best]["algorithmic_bytes"],
+            "kernels": kern, "graph_conv_GBps": gcn_gbps, "graph_conv_frac": gcn_gbps / peak if gcn_gbps else None,
+            "graph_conv_note": "256->256 GCN layer incl. the pre-aggregation pass; the last layer also writes transposed copies"}
 
 
 def run_gpu(args, rank, local, world):
@@ -313,6 +357,7 @@ def run_gpu(args, rank, local, world):
     clocks = sampler.stop() if sampler else None
     launches_per_step = tr.launches_per_step + 2  # + sumsq + AdamW kernels outside the graph
     stages = stage_breakdown(tr) if rank == 0 else None
+    kernel_ms = time_recurrence_kernels(tr) if rank == 0 else None
     del tr
     torch.cuda.empty_cache()
 
@@ -328,7 +373,7 @@ def run_gpu(args, rank, local, world):
     sec_step = ms * 1e-3 / args.steps
     value = world / sec_step
     peak, peak_src = peaks()
-    roof = roofline_from_stages(stages, TASKS_PER_GPU, peak, peak_src)
+    roof = roofline_report(stages, kernel_ms, TASKS_PER_GPU, peak, peak_src)
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": sec_step * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,

@@ -245,6 +245,15 @@ int wf_lstm_bwd_seq(const void* xT_hi, const void* xT_lo, const void* pT16_hi, c
                     float* dgT, const float* dlast, float* grads, long long grads_group_stride,
                     void* workspace, size_t workspace_bytes, int* err, void* stream);
 
+/* Single-layer recurrence launches (the persistent kernels wf_lstm_fwd_seq / wf_lstm_bwd_seq issue per layer), for
+ * harnesses that time the dominant kernels alone or drive the layers themselves.  *_l pointers address ONE layer. */
+int wf_lstm_seq_recur_fwd(float* gates_l, float* c_l, float* h_l, void* hT_hi_l, void* hT_lo_l, const void* f16_hi,
+                          const void* f16_lo, int layer, int layers, int L, int T, int N, int G, int Bw, int* err,
+                          void* stream);
+int wf_lstm_seq_recur_bwd(float* gates_l, const float* c_l, float* dgT, const float* ext, int ext_is_dlast,
+                          const void* b16_hi, const void* b16_lo, int layer, int layers, int L, int T, int N, int G,
+                          int Bw, int* err, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

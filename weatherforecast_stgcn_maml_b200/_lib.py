@@ -74,6 +74,8 @@ SIGNATURES = {
     "wf_lstm_bwd_seq": (c_i, [c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_p, c_p, c_p,
                               c_p, c_p, c_p, c_p, c_ll, c_p, c_sz, c_p, c_p]),
     "wf_tc_gemm_nt": (c_i, [c_p, c_i, c_i, c_i, c_p, c_p, c_ll, c_i, c_p, c_p, c_ll, c_i, c_p, c_p, c_p]),
+    "wf_lstm_seq_recur_fwd": (c_i, [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_p, c_p]),
+    "wf_lstm_seq_recur_bwd": (c_i, [c_p, c_p, c_p, c_p, c_i, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_p, c_p]),
 }
 
 _lib = None

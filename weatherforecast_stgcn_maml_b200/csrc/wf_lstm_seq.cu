@@ -827,3 +827,45 @@ extern "C" int wf_lstm_bwd_seq(const void* xT_hi, const void* xT_lo, const void*
   }
   return WF_OK;
 }
+
+// ---- single-layer recurrence entry points: exactly the persistent launches the two functions above issue per layer,
+// exposed so that a harness can time the dominant kernels alone (bench.py roofline) or drive layers itself.
+extern "C" int wf_lstm_seq_recur_fwd(float* gates_l, float* c_l, float* h_l, void* hT_hi_l, void* hT_lo_l, const void* f16_hi,
+                                     const void* f16_lo, int layer, int layers, int L, int T, int N, int G, int Bw, int* err,
+                                     void* stream) {
+  WF_REQUIRE(layers >= 1 && layers <= 8 && layer >= 0 && layer < layers && L == 128, "lstm_seq_recur_fwd: bad layer / L");
+  static bool configured = false;
+  if (!configured) { int rc = seq_configure(wf_lstm_seq_fwd_kernel); if (rc) return rc; configured = true; }
+  const long long Z = (long long)G * Bw;
+  CUtensorMap tmhi, tmlo;
+  int rc = seq_maps_fwd(&tmhi, &tmlo, f16_hi, f16_lo, L, G * layers);
+  if (rc) return rc;
+  SeqArgs a;
+  memset(&a, 0, sizeof(a));
+  a.XG = gates_l; a.Cst = c_l; a.H = h_l; a.HT = (__nv_bfloat16*)hT_hi_l; a.HT_lo = (__nv_bfloat16*)hT_lo_l;
+  a.T = T; a.Nn = N; a.Bw = Bw; a.tpw = wf_cdiv(N, 128); a.Np = wf_np(N); a.RT = T * a.Np;
+  a.slab0 = layer; a.slab_g = layers; a.err = err;
+  wf_lstm_seq_fwd_kernel<<<dim3((unsigned)(2 * Z * a.tpw)), SEQ_THREADS, SEQ_SMEM, (cudaStream_t)stream>>>(tmhi, tmlo, a);
+  WF_CHECK_LAUNCH("lstm_seq_recur_fwd");
+  return WF_OK;
+}
+
+extern "C" int wf_lstm_seq_recur_bwd(float* gates_l, const float* c_l, float* dgT, const float* ext, int ext_is_dlast,
+                                     const void* b16_hi, const void* b16_lo, int layer, int layers, int L, int T, int N, int G,
+                                     int Bw, int* err, void* stream) {
+  WF_REQUIRE(layers >= 1 && layers <= 8 && layer >= 0 && layer < layers && L == 128, "lstm_seq_recur_bwd: bad layer / L");
+  static bool configured = false;
+  if (!configured) { int rc = seq_configure(wf_lstm_seq_bwd_kernel); if (rc) return rc; configured = true; }
+  const long long Z = (long long)G * Bw;
+  CUtensorMap tmhi, tmlo;
+  int rc = seq_maps_bwd(&tmhi, &tmlo, b16_hi, b16_lo, L, G * layers);
+  if (rc) return rc;
+  SeqArgs a;
+  memset(&a, 0, sizeof(a));
+  a.XG = gates_l; a.Cst = const_cast<float*>(c_l); a.DGT = dgT; a.ext = ext; a.ext_last_only = ext_is_dlast ? 1 : 0;
+  a.T = T; a.Nn = N; a.Bw = Bw; a.tpw = wf_cdiv(N, 128); a.Np = wf_np(N); a.RT = T * a.Np;
+  a.slab0 = 2 * layer; a.slab_g = 2 * layers; a.err = err;
+  wf_lstm_seq_bwd_kernel<<<dim3((unsigned)(2 * Z * a.tpw)), SEQ_THREADS, SEQ_SMEM, (cudaStream_t)stream>>>(tmhi, tmlo, a);
+  WF_CHECK_LAUNCH("lstm_seq_recur_bwd");
+  return WF_OK;
+}
