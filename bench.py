@@ -231,8 +231,9 @@ def stage_breakdown(trainer, reps=3):
         e1.record()
         acc.setdefault(name, []).append((e0, e1))
 
-    was = trainer.use_graph
+    was, was_dist = trainer.use_graph, trainer.dist
     trainer.use_graph = False
+    trainer.dist = None  # rank 0 only: an instrumented step must not enter a collective the other ranks do not
     for mod in (sys.modules["weatherforecast_stgcn_maml_b200.engine"],
                 sys.modules["weatherforecast_stgcn_maml_b200.train_hybrid_maml_v5"]):
         mod._lib.call = timed_call
@@ -242,7 +243,7 @@ def stage_breakdown(trainer, reps=3):
         torch.cuda.synchronize()
     finally:
         _lib.call = orig
-        trainer.use_graph = was
+        trainer.use_graph, trainer.dist = was, was_dist
     out = {}
     for name, evs in acc.items():
         out[name] = {"ms_per_meta_step": sum(a.elapsed_time(b) for a, b in evs) / reps, "calls": len(evs) // reps}
@@ -415,6 +416,11 @@ def main():
         return
     from weatherforecast_stgcn_maml_b200.dist import init_from_env
 
+    if world_env > 1:
+        # a rank stuck in a collective must not hang the job: dump every thread's stack and exit
+        import faulthandler
+
+        faulthandler.dump_traceback_later(int(os.environ.get("WF_BENCH_WATCHDOG_S", "900")), exit=True)
     rank, local, world = init_from_env("nccl")
     if world != args.gpus and world_env > 1:
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
