@@ -228,8 +228,9 @@ int wf_prep_weights_seq(const float* params, long long params_group_stride, int 
                         int O, int G, void* p16_hi, void* p16_lo, void* pT16_hi, void* pT16_lo, void* f16_hi,
                         void* f16_lo, void* b16_hi, void* b16_lo, void* stream);
 
-/* nn.LSTM forward (hybrid_model.py:42-49, 93-105).  x [G*Bw*T*N, F] and h [layers][G*Bw*T*N, L] are
- * row-major; gates (4L channels) and c (L channels) are TB4, [layers] of them; hT hi/lo optional (bf16). */
+/* nn.LSTM forward (hybrid_model.py:42-49, 93-105).  x [G*Bw*T*N, F] row-major; gates (4L channels) and c
+ * (L channels) are TB4, [layers] of them; h is [layers][wf_tb4_elems(L, T, N, G*Bw)]: the TOP layer row-major
+ * [G*Bw*T*N, L] (what the head reads), the layers below TB4; hT hi/lo optional (bf16). */
 int wf_lstm_fwd_seq(const float* x, const float* params, const void* p16_hi, const void* p16_lo,
                     long long params_group_stride, const void* f16_hi, const void* f16_lo, int layers,
                     int F, int L, int O, int T, int N, int G, int Bw, float* gates, float* h, float* c,

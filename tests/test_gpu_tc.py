@@ -137,9 +137,10 @@ def test_engine_tensor_core_path_matches_fp32_path(nlat, nlon, T, G, Bw):
         eng.lstm_head_forward(theta, eng.P)
         eng.check()
         loss = eng.mse(feat=fd, tgt_off=to, feat_ld=24, grad_scale=1.0)
+        hid = eng.hidden_states()
         grads = eng.backward(theta, eng.P)
         eng.check()
-        out[prec] = (eng.feats.clone(), eng.pred.clone(), loss.clone(), grads.clone(), eng.h.clone())
+        out[prec] = (eng.feats.clone(), eng.pred.clone(), loss.clone(), grads.clone(), hid)
     f0, p0, l0, g0, h0 = out["fp32"]
     rel = lambda a, b: float((a.double() - b.double()).abs().max() / b.double().abs().max())
     lay = unflatten_trainable(g0[0], dims)

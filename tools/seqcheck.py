@@ -28,7 +28,7 @@ def run(nlat, nlon, T, G, Bw):
         eng.lstm_head_forward(theta, eng.P)
         torch.cuda.synchronize(); print(prec, "fwd err flag", int(eng.err.item()))
         loss = eng.mse(feat=fd, tgt_off=to, feat_ld=24, grad_scale=1.0)
-        hcl = eng.h.clone()
+        hcl = eng.hidden_states()
         grads = eng.backward(theta, eng.P)
         torch.cuda.synchronize(); print(prec, "bwd err flag", int(eng.err.item()))
         out[prec] = (eng.pred.clone(), loss.clone(), grads.clone(), hcl)

@@ -49,6 +49,7 @@ struct G16Args {
   float* C; int ldc; long long c_gstride, c_sstride; int c_cols;
   const float* bias; const float* bias2; long long bias_gstride; int relu;
   __nv_bfloat16* ct_hi; __nv_bfloat16* ct_lo;   // transposed copies [(g*Bw + w)][c_cols][RT]
+  float* rowsum_part;                // WGRAD: per (split, k-half) partial row sums of A [parts][G][M] (bias gradients), or null
   int* err;
 };
 
@@ -244,6 +245,8 @@ wf_g16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
       }
       fetch_row(tile + gridDim.x);
       const int nk = c.nkb_loc * a.nseg;
+      const bool want_sum = a.rowsum_part != nullptr && c.ntile == 0;  // sum_k A[m, k]: the LSTM bias gradient, for free
+      float rsum = 0.f;
       for (int k = 0; k < nk; ++k, ++it) {
         const int s = it % NST, ph = (it / NST) & 1;
         if (!mbar_wait(&full[s], ph) || !mbar_wait(&empty[s], ph ^ 1)) { if (lane == 0) atomicExch(a.err, 34); ok = false; break; }
@@ -255,6 +258,7 @@ wf_g16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
             // TB4 stage: [channel group][row][4 floats]; otherwise a SWIZZLE_128B box of 32 floats per row
             const uint8_t* p = st + (a.a_tb4 ? ch * 2048 + row * 16 : row * 128 + ((ch ^ (row & 7)) << 4));
             const float4 v = *reinterpret_cast<const float4*>(p);
+            if (want_sum) rsum += (v.x + v.y) + (v.z + v.w);
             split_pair<FMT>(v.x, v.y, hi[2 * ch], lo[2 * ch]);
             split_pair<FMT>(v.z, v.w, hi[2 * ch + 1], lo[2 * ch + 1]);
           }
@@ -294,6 +298,8 @@ wf_g16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
         __syncwarp();
         if (lane == 0) mbar_arrive(&aready[s]);
       }
+      if (want_sum && ok)
+        a.rowsum_part[((long long)(c.split * 2 + h) * a.G + c.g) * a.rows_g + c.mt * 128 + row] = rsum;
     }
   } else {
     // ------------------------------------------------------------------ epilogue
@@ -387,6 +393,18 @@ __global__ void wf_split16_kernel(const float4* __restrict__ src, long long src_
   else { split_pair<1>(v.x, v.y, h.x, l.x); split_pair<1>(v.z, v.w, h.y, l.y); }
   hi[i] = h;
   lo[i] = l;
+}
+
+// out1[g][m] = out2[g][m] = sum over parts of part[p][g][m] (fixed order: deterministic)
+__global__ void wf_sum_rowsum_parts_kernel(const float* __restrict__ part, int parts, int G, int M, float* out1, float* out2,
+                                           long long out_gstride) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= G * M) return;
+  float acc = 0.f;
+  for (int p = 0; p < parts; ++p) acc += part[(long long)p * G * M + i];
+  const int g = i / M, m = i - g * M;
+  out1[g * out_gstride + m] = acc;
+  if (out2) out2[g * out_gstride + m] = acc;
 }
 
 int map16(CUtensorMap* m, const void* base, uint64_t k, uint64_t rows, uint64_t z, uint64_t ld, uint64_t zstride, int fmt) {
@@ -543,9 +561,11 @@ static __global__ void wf_sum_splits16_kernel(const float4* __restrict__ part, i
 
 // ---- weight gradient: dW[g][M, N] = sum over windows w and columns k of AT[g*Bw+w][m, a_k0+k] * BT[g*Bw+w][n, b_k0+k]
 // AT: fp32 [G*Bw][M][R]; BT hi/lo: bf16 [G*Bw][N][R].  Split-K over `partials` when there are few output tiles.
+// rowsum1 / rowsum2 (optional): sum over windows and k of AT[m, k] -> [g][M] (the two LSTM bias gradients), computed in
+// the converter path; needs 16*G*M extra floats at the end of `partials`.
 int wf_launch_g16_wgrad(const float* AT, int M, const void* BT_hi, const void* BT_lo, int N, int R, int Bw, int G, int a_k0,
                         int b_k0, int klen, float* dW, long long dw_gstride, int* err, cudaStream_t st, float* partials,
-                        size_t partial_floats) {
+                        size_t partial_floats, float* rowsum1, float* rowsum2, long long rowsum_gstride) {
   WF_REQUIRE(M % 128 == 0 && N % 128 == 0 && R % 8 == 0, "g16_wgrad: M=%d N=%d must be multiples of 128, R=%d of 8", M, N, R);
   WF_REQUIRE(a_k0 % 4 == 0 && b_k0 % 8 == 0, "g16_wgrad: K offsets (%d, %d) must keep 16-byte alignment", a_k0, b_k0);
   CUtensorMap tmA, tmBhi, tmBlo;
@@ -562,17 +582,25 @@ int wf_launch_g16_wgrad(const float* AT, int M, const void* BT_hi, const void* B
   if (splits > nkb) splits = nkb;
   int per = wf_cdiv(nkb, splits);
   splits = wf_cdiv(nkb, per);
-  const long long per_split = (long long)G * M * N;
-  if (partials == nullptr || (long long)partial_floats < per_split * splits || (dw_gstride % 4) != 0) { splits = 1; per = nkb; }
+  const long long per_split = (long long)G * M * N, rs_floats = rowsum1 ? 16LL * G * M : 0;
+  WF_REQUIRE(rowsum1 == nullptr || (partials != nullptr && (long long)partial_floats >= rs_floats),
+             "g16_wgrad: row sums need %lld floats of scratch", rs_floats);
+  if (partials == nullptr || (long long)partial_floats < per_split * splits + rs_floats || (dw_gstride % 4) != 0) { splits = 1; per = nkb; }
+  float* rs_part = rowsum1 ? partials + (partial_floats - rs_floats) : nullptr;
   G16Args a;
   g16_defaults(a);
   a.mode = G16_WGRAD; a.m_tiles = M / 128; a.n_tiles = N / 128; a.G = G; a.splits = splits;
   a.rows_g = M; a.Bw = Bw; a.R = R; a.nkb = nkb; a.nseg = Bw; a.nkb_split = per; a.a_k0 = a_k0; a.b_k0 = b_k0;
-  a.ldc = N; a.c_cols = N; a.err = err;
+  a.ldc = N; a.c_cols = N; a.err = err; a.rowsum_part = rs_part;
   if (splits > 1) { a.C = partials; a.c_gstride = (long long)M * N; a.c_sstride = per_split; }
   else { a.C = dW; a.c_gstride = dw_gstride; a.c_sstride = 0; }
   rc = g16_launch(1, tmA, tmBhi, tmBlo, a, st);
-  if (rc || splits == 1) return rc;
+  if (rc) return rc;
+  if (rs_part) {
+    wf_sum_rowsum_parts_kernel<<<wf_cdiv(G * M, 256), 256, 0, st>>>(rs_part, 2 * splits, G, M, rowsum1, rowsum2, rowsum_gstride);
+    WF_CHECK_LAUNCH("sum_rowsum_parts");
+  }
+  if (splits == 1) return WF_OK;
   const long long count4 = (long long)M * N / 4;
   wf_sum_splits16_kernel<<<dim3(wf_cdiv(count4, 256), G), 256, 0, st>>>((const float4*)partials, splits, count4, per_split / 4,
                                                                      (float4*)dW, dw_gstride / 4);

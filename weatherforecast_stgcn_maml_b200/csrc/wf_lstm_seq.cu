@@ -36,7 +36,7 @@ int wf_launch_g16_nodes(int fmt, const float* A, int a_tb4, int K, const void* W
                         int G, int* err, cudaStream_t st);
 int wf_launch_g16_wgrad(const float* AT, int M, const void* BT_hi, const void* BT_lo, int N, int R, int Bw, int G, int a_k0,
                         int b_k0, int klen, float* dW, long long dw_gstride, int* err, cudaStream_t st, float* partials,
-                        size_t partial_floats);
+                        size_t partial_floats, float* rowsum1, float* rowsum2, long long rowsum_gstride);
 int wf_launch_split16(const float* src, long long src_gstride, void* hi, void* lo, long long dst_gstride, long long n, int G,
                       int fmt, cudaStream_t st);
 int wf_launch_transpose_split16(const float* in, long long in_gstride, int rows, int cols, void* out_hi, void* out_lo,
@@ -52,7 +52,8 @@ constexpr int SEQ_SMEM = 196608 + 1024;
 struct SeqArgs {
   float* XG;          // TB4, 4L channels. fwd: input projection in, activated gates out; bwd: gates in, dG out
   float* Cst;         // TB4, L channels: cell state
-  float* H;           // fwd out: row-major [Z*R, L]
+  float* H;           // fwd out: row-major [Z*R, L], or TB4 (L channels) when h_tb4
+  int h_tb4;
   __nv_bfloat16* HT;  // fwd out (optional): transposed bf16 hi / lo copies [(z)][L][RT]
   __nv_bfloat16* HT_lo;
   float* DGT;         // bwd out: transposed dG [(z)][4L][RT]
@@ -271,9 +272,16 @@ wf_lstm_seq_fwd_kernel(const __grid_constant__ CUtensorMap tmWhi, const __grid_c
           c4[(blk * 32 + ((u0 + 8 * c) >> 2) + hsel) * 128 + r] =
               make_float4(cst[8 * c + j], cst[8 * c + j + 1], cst[8 * c + j + 2], cst[8 * c + j + 3]);
         }
+        if (a.h_tb4) {  // consumed only by the next layer's projection GEMM: coalesced tile-blocked stores
+          float4* h4 = reinterpret_cast<float4*>(a.H) + (blk * 32 + ((u0 + 8 * c) >> 2)) * 128 + r;
+          h4[0] = make_float4(hh[0], hh[1], hh[2], hh[3]);
+          h4[128] = make_float4(hh[4], hh[5], hh[6], hh[7]);
+        }
         if (valid) {
-          *reinterpret_cast<float4*>(a.H + hrow + 8 * c) = make_float4(hh[0], hh[1], hh[2], hh[3]);
-          *reinterpret_cast<float4*>(a.H + hrow + 8 * c + 4) = make_float4(hh[4], hh[5], hh[6], hh[7]);
+          if (!a.h_tb4) {
+            *reinterpret_cast<float4*>(a.H + hrow + 8 * c) = make_float4(hh[0], hh[1], hh[2], hh[3]);
+            *reinterpret_cast<float4*>(a.H + hrow + 8 * c + 4) = make_float4(hh[4], hh[5], hh[6], hh[7]);
+          }
           if (a.HT != nullptr) {
             __nv_bfloat16* ht = a.HT + ((long long)z * L + u0 + 8 * c) * a.RT + tcol;
             __nv_bfloat16* htl = a.HT_lo + ((long long)z * L + u0 + 8 * c) * a.RT + tcol;
@@ -619,32 +627,6 @@ __global__ void wf_prep_seq_kernel(const float* __restrict__ params, long long g
   b_lo[o] = __float2bfloat16_rn(v - __bfloat162float(b));
 }
 
-// Column sums of a TB4 buffer over all blocks of a group: out1[g][c] = out2[g][c] = sum over (window, step,
-// node) of X[.., c]  (the LSTM bias gradients: db_ih = db_hh = sum dG).  grid (C/4, G), 128 threads.
-__global__ void __launch_bounds__(128) wf_colsum_tb4_kernel(const float4* __restrict__ X, int C4, int blocks_g, float* out1,
-                                                            float* out2, long long out_gstride) {
-  const int cg = blockIdx.x, g = blockIdx.y, r = threadIdx.x;
-  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int b = 0; b < blocks_g; ++b) {
-    const float4 v = X[(((long long)g * blocks_g + b) * C4 + cg) * 128 + r];
-    acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
-  }
-  __shared__ float4 sh[4];
-  acc.x = warp_sum(acc.x); acc.y = warp_sum(acc.y); acc.z = warp_sum(acc.z); acc.w = warp_sum(acc.w);
-  if ((r & 31) == 0) sh[r >> 5] = acc;
-  __syncthreads();
-  if (r == 0) {
-    float4 t = sh[0];
-    for (int i = 1; i < 4; ++i) { t.x += sh[i].x; t.y += sh[i].y; t.z += sh[i].z; t.w += sh[i].w; }
-    float* o1 = out1 + g * out_gstride + cg * 4;
-    o1[0] = t.x; o1[1] = t.y; o1[2] = t.z; o1[3] = t.w;
-    if (out2) {
-      float* o2 = out2 + g * out_gstride + cg * 4;
-      o2[0] = t.x; o2[1] = t.y; o2[2] = t.z; o2[3] = t.w;
-    }
-  }
-}
-
 int seq_maps_fwd(CUtensorMap* hi, CUtensorMap* lo, const void* f_hi, const void* f_lo, int L, int slabs) {
   uint64_t dims[4] = {(uint64_t)L, (uint64_t)L, 4, (uint64_t)slabs};
   uint64_t str[3] = {(uint64_t)L * 2, (uint64_t)L * L * 2, (uint64_t)4 * L * L * 2};
@@ -718,7 +700,8 @@ extern "C" int wf_prep_weights_seq(const float* params, long long params_group_s
 
 // nn.LSTM forward (hybrid_model.py:42-49, 93-105): per layer one input-projection GEMM + one persistent launch.
 //   x [G*Bw*T*N, F] row-major; params: flat fp32 weights (biases); p16 / f16 operands from wf_prep_weights_seq;
-//   gates TB4 [layers][4L ch], c TB4 [layers][L ch], h [layers][G*Bw*T*N, L] row-major,
+//   gates TB4 [layers][4L ch], c TB4 [layers][L ch]; h [layers][wf_tb4_elems(L, ..)]: the top layer row-major
+//   [G*Bw*T*N, L] (read by the head), the layers below TB4 (read only by the next layer's projection);
 //   hT_hi / hT_lo optional bf16 transposed copies [layers][(G*Bw)][L][RT16] (training).
 extern "C" int wf_lstm_fwd_seq(const float* x, const float* params, const void* p16_hi, const void* p16_lo,
                                long long params_group_stride, const void* f16_hi, const void* f16_lo, int layers, int F, int L,
@@ -730,7 +713,7 @@ extern "C" int wf_lstm_fwd_seq(const float* x, const float* params, const void* 
   static bool configured = false;
   if (!configured) { int rc = seq_configure(wf_lstm_seq_fwd_kernel); if (rc) return rc; configured = true; }
   const LstmLayout P = lstm_layout(layers, F, L, O);
-  const long long Z = (long long)G * Bw, rows = Z * T * N;
+  const long long Z = (long long)G * Bw;
   const int tpw = wf_cdiv(N, 128), Np = wf_np(N), RT = T * Np;
   const long long g_elems = wf_tb4_elems(4 * L, T, N, Z), c_elems = wf_tb4_elems(L, T, N, Z);
   const long long tsz = Z * L * RT;
@@ -740,14 +723,14 @@ extern "C" int wf_lstm_fwd_seq(const float* x, const float* params, const void* 
   for (int l = 0; l < layers; ++l) {
     const int kin = l == 0 ? F : L;
     float* XG = gates + l * g_elems;
-    const float* Xl = l == 0 ? x : h + (long long)(l - 1) * rows * L;
-    rc = wf_launch_g16_nodes(0, Xl, 0, kin, (const uint16_t*)p16_hi + P.w_ih[l], (const uint16_t*)p16_lo + P.w_ih[l], kin,
+    const float* Xl = l == 0 ? x : h + (long long)(l - 1) * c_elems;
+    rc = wf_launch_g16_nodes(0, Xl, l == 0 ? 0 : 1, kin, (const uint16_t*)p16_hi + P.w_ih[l], (const uint16_t*)p16_lo + P.w_ih[l], kin,
                              stride16(P.total), 4 * L, params + P.b_ih[l], params + P.b_hh[l], params_group_stride, XG, T, N,
                              Bw, G, err, st);
     if (rc) return rc;
     SeqArgs a;
     memset(&a, 0, sizeof(a));
-    a.XG = XG; a.Cst = c + l * c_elems; a.H = h + (long long)l * rows * L;
+    a.XG = XG; a.Cst = c + l * c_elems; a.H = h + (long long)l * c_elems; a.h_tb4 = l + 1 < layers ? 1 : 0;
     a.HT = hT_hi ? (__nv_bfloat16*)hT_hi + l * tsz : nullptr; a.HT_lo = hT_hi ? (__nv_bfloat16*)hT_lo + l * tsz : nullptr;
     a.T = T; a.Nn = N; a.Bw = Bw; a.tpw = tpw; a.Np = Np; a.RT = RT;
     a.slab0 = l; a.slab_g = layers; a.err = err;
@@ -758,7 +741,7 @@ extern "C" int wf_lstm_fwd_seq(const float* x, const float* params, const void* 
 }
 
 // workspace = dh between layers (TB4, L channels) + split-K partials of the weight gradients
-static size_t seq_partial_floats(int F, int L, int G) { return (size_t)8 * G * 4 * L * (F > L ? F : L); }
+static size_t seq_partial_floats(int F, int L, int G) { return (size_t)8 * G * 4 * L * (F > L ? F : L) + (size_t)16 * G * 4 * L; }
 extern "C" size_t wf_lstm_bwd_seq_workspace_bytes(int layers, int F, int L, int T, int N, int G, int Bw) {
   (void)layers;
   return sizeof(float) * ((size_t)wf_tb4_elems(L, T, N, (long long)G * Bw) + seq_partial_floats(F, L, G)) + 256;
@@ -804,16 +787,14 @@ extern "C" int wf_lstm_bwd_seq(const void* xT_hi, const void* xT_lo, const void*
     a.slab0 = 2 * l; a.slab_g = 2 * layers; a.err = err;
     wf_lstm_seq_bwd_kernel<<<dim3((unsigned)(2 * Z * tpw)), SEQ_THREADS, SEQ_SMEM, st>>>(tmhi, tmlo, a);
     WF_CHECK_LAUNCH("lstm_seq_bwd");
-    wf_colsum_tb4_kernel<<<dim3(L, G), 128, 0, st>>>(reinterpret_cast<const float4*>(XG), L, Bw * T * tpw, grads + P.b_ih[l],
-                                                     grads + P.b_hh[l], grads_group_stride);
-    WF_CHECK_LAUNCH("colsum_tb4");
-    // dW_ih = dG^T X_l  as  (dG^T)(X_l^T)^T over all columns of every window (padding columns are zero)
+    // dW_ih = dG^T X_l  as  (dG^T)(X_l^T)^T over all columns of every window (padding columns are zero); the bias
+    // gradients db_ih = db_hh = row sums of dG^T fall out of the same pass over dG^T
     rc = wf_launch_g16_wgrad(dgT, 4 * L, XTh, XTl, kin, RT, Bw, G, 0, 0, RT, grads + P.w_ih[l], grads_group_stride, err, st,
-                             partials, partial_floats);
+                             partials, partial_floats, grads + P.b_ih[l], grads + P.b_hh[l], grads_group_stride);
     if (rc) return rc;
     if (T > 1) {  // dW_hh = sum_{t>=1} dG[t]^T h[t-1]: dG^T columns [Np, RT) against h^T columns [0, RT-Np)
       rc = wf_launch_g16_wgrad(dgT, 4 * L, hTh + l * tsz, hTl + l * tsz, L, RT, Bw, G, Np, 0, RT - Np, grads + P.w_hh[l],
-                               grads_group_stride, err, st, partials, partial_floats);
+                               grads_group_stride, err, st, partials, partial_floats, nullptr, nullptr, 0);
       if (rc) return rc;
     } else {
       for (int g = 0; g < G; ++g)
@@ -842,7 +823,8 @@ extern "C" int wf_lstm_seq_recur_fwd(float* gates_l, float* c_l, float* h_l, voi
   if (rc) return rc;
   SeqArgs a;
   memset(&a, 0, sizeof(a));
-  a.XG = gates_l; a.Cst = c_l; a.H = h_l; a.HT = (__nv_bfloat16*)hT_hi_l; a.HT_lo = (__nv_bfloat16*)hT_lo_l;
+  a.XG = gates_l; a.Cst = c_l; a.H = h_l; a.h_tb4 = layer + 1 < layers ? 1 : 0;
+  a.HT = (__nv_bfloat16*)hT_hi_l; a.HT_lo = (__nv_bfloat16*)hT_lo_l;
   a.T = T; a.Nn = N; a.Bw = Bw; a.tpw = wf_cdiv(N, 128); a.Np = wf_np(N); a.RT = T * a.Np;
   a.slab0 = layer; a.slab_g = layers; a.err = err;
   wf_lstm_seq_fwd_kernel<<<dim3((unsigned)(2 * Z * a.tpw)), SEQ_THREADS, SEQ_SMEM, (cudaStream_t)stream>>>(tmhi, tmlo, a);

@@ -114,10 +114,12 @@ class HybridEngine:
         if self.seq:  # gates / cell state in the tile-blocked TB4 layout (padded to 128-node tiles)
             self.gates = torch.empty(Ls, int(_lib.query("wf_tb4_elems", 4 * L, d.window, d.num_nodes, self.G * self.Bw)), **f32)
             self.c = torch.empty(Ls, int(_lib.query("wf_tb4_elems", L, d.window, d.num_nodes, self.G * self.Bw)), **f32)
+            # hidden states: top layer row-major (the head reads it), layers below TB4 (next layer's projection only)
+            self.h = torch.empty(Ls, self.c.shape[1], **f32)
         else:
             self.gates = torch.empty(Ls, self.rows, 4 * L, **f32)
             self.c = torch.empty(Ls, self.rows, L, **f32)
-        self.h = torch.empty(Ls, self.rows, L, **f32)
+            self.h = torch.empty(Ls, self.rows, L, **f32)
         self.pred = torch.empty(self.W * d.num_nodes, d.O, **f32)
         self.dpred = torch.empty(self.W * d.num_nodes, d.O, **f32)
         self.loss = torch.zeros(self.W, **f32)
@@ -174,6 +176,21 @@ class HybridEngine:
         self.feats = None
         self.agg = None  # scratch of the GCN pre-aggregation pass (persistent path)
         self.launches = 0  # kernels enqueued by this engine (bench.py reports it)
+
+    def hidden_states(self):
+        """[layers, G*Bw*R, L] row-major copy of the LSTM hidden states, whatever layout the kernels keep them in."""
+        d, Ls, L = self.dims, self.dims.lstm_layers, self.dims.lstm_hidden
+        if not self.seq:
+            return self.h.clone()
+        tpw = (d.num_nodes + 127) // 128
+        out = torch.empty(Ls, self.rows, L, dtype=torch.float32, device=self.device)
+        for l in range(Ls):
+            if l == Ls - 1:
+                out[l] = self.h[l, :self.rows * L].view(self.rows, L)
+            else:  # TB4: [window, step, node tile, L/4, 128 rows, 4]
+                t = self.h[l].view(self.W, d.window, tpw, L // 4, 128, 4).permute(0, 1, 2, 4, 3, 5)
+                out[l] = t.reshape(self.W, d.window, tpw * 128, L)[:, :, :d.num_nodes].reshape(self.rows, L)
+        return out
 
     def check(self):
         """Synchronise and raise if a tensor-core pipeline wait timed out (never expected)."""
