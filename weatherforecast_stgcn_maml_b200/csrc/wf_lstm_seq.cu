@@ -343,8 +343,9 @@ wf_lstm_seq_fwd_kernel(const __grid_constant__ CUtensorMap tmWhi, const __grid_c
           st_cluster_v4(mapa_u32(smem_u32(a_lo + off), peer), vlo);
         }
         if (c < 3) {
-          store_chunk(c, gi, gf, gg, go, hh);
+          // loads first: the memory pipeline is in order, a load queued behind a burst of stores waits for it
           if (c < 2) load_chunk(t, c + 2, xq[c & 1]);  // chunks 2, 3 of this step; consumed before the hand-over
+          store_chunk(c, gi, gf, gg, go, hh);
         } else {
 #pragma unroll
           for (int j = 0; j < 8; ++j) { gi3[j] = gi[j]; gf3[j] = gf[j]; gg3[j] = gg[j]; go3[j] = go[j]; hh3[j] = hh[j]; }
@@ -362,11 +363,11 @@ wf_lstm_seq_fwd_kernel(const __grid_constant__ CUtensorMap tmWhi, const __grid_c
           arrive_cluster(ar_remote);
         }
       }
-      store_chunk(3, gi3, gf3, gg3, go3, hh3);
       if (t + 1 < T) {
         load_chunk(t + 1, 0, xq[0]);
         load_chunk(t + 1, 1, xq[1]);
       }
+      store_chunk(3, gi3, gf3, gg3, go3, hh3);
     }
   }
   tc_fence_before();
