@@ -1,0 +1,134 @@
+"""Size-independent properties at BASELINE.json's full sizes, where the CPU oracle would take minutes:
+batching invariance (a batch is B independent batch-1 windows), task independence (MAML tasks only
+share theta), the identity rows of the graph convolution (rows >= N see their self loop only, D3) and
+one oracle spot check per case.  Tensor-core (persistent) path, v5 widths."""
+import pytest
+import torch
+
+from conftest import rel_err
+from oracle import ref_port as P
+from weatherforecast_stgcn_maml_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _setup(nlat, nlon, k, G, Bw, seed=11):
+    from weatherforecast_stgcn_maml_b200.engine import V5Dims, flatten_trainable, gcn_weights_from_state_dict
+    from weatherforecast_stgcn_maml_b200.graph import RegionGraph, StackedGraphs
+
+    n = nlat * nlon
+    dims = V5Dims(num_nodes=n)
+    lats, lons = synth.region_grid(nlat, nlon)
+    ei = P.knn_edges_canonical(lats, lons, k)
+    base = synth.init_v5_state_dict(seed, gcn_bias_scale=0.05)
+    sds = [{kk: (v + 0.02 * torch.randn_like(v) * (g > 0) if kk.startswith(("lstm.", "output_layer.")) else v)
+            for kk, v in base.items()} for g in range(G)]
+    time_rows = dims.window + dims.horizon + 1 + Bw + 2
+    feats = torch.stack([synth.synth_features(time_rows, n, 300 + g) for g in range(G)])
+    per, per_task = n * 24, time_rows * n * 24
+    starts = [[(g + b) % (Bw + 2) for b in range(Bw)] for g in range(G)]
+    xo = torch.tensor([g * per_task + s * per for g in range(G) for s in starts[g]], device="cuda")
+    to = xo + (dims.window + 1) * per
+    theta = torch.stack([flatten_trainable(sd, dims) for sd in sds]).cuda()
+    graphs = StackedGraphs([RegionGraph(ei, dims.R, "cuda") for _ in range(G)])
+    return dims, ei, base, sds, feats, starts, xo, to, theta, graphs, gcn_weights_from_state_dict(base, "cuda")
+
+
+def _run(dims, G, Bw, fd, xo, to, theta, graphs, gcn_w):
+    from weatherforecast_stgcn_maml_b200.engine import HybridEngine
+
+    eng = HybridEngine(dims, G, Bw, "cuda")
+    assert eng.seq, "full-size cases must run on the persistent tensor-core path"
+    loss, grads = eng.forward_backward(fd, 24, 0, xo, gcn_w, graphs, theta, eng.P, feat=fd, tgt_off=to, feat_ld=24)
+    eng.check()
+    return eng.pred.clone(), loss.clone(), grads.clone()
+
+
+def test_config1_batch16_equals_16_single_windows():
+    """configs[0]: 441 nodes, k = 8, 24 -> 8, batch 16 = sixteen batch-1 windows; gradients of a task's windows add."""
+    from weatherforecast_stgcn_maml_b200.engine import unflatten_trainable
+    from weatherforecast_stgcn_maml_b200.graph import StackedGraphs
+
+    Bw = 16
+    dims, ei, base, sds, feats, starts, xo, to, theta, graphs, gcn_w = _setup(21, 21, 8, 1, Bw)
+    fd = feats.cuda()
+    pred, loss, grads = _run(dims, 1, Bw, fd, xo, to, theta, graphs, gcn_w)
+    n = dims.num_nodes
+    gsum = torch.zeros_like(grads[0])
+    for b in (0, 7, 15):  # three windows individually through a batch-1 engine
+        p1, l1, g1 = _run(dims, 1, 1, fd, xo[b:b + 1], to[b:b + 1], theta, graphs, gcn_w)
+        assert rel_err(pred[b * n:(b + 1) * n], p1) <= 1e-5
+        assert abs(loss[b].item() - l1[0].item()) <= 1e-5 * abs(l1[0].item())
+    for b in range(Bw):
+        gsum += _run(dims, 1, 1, fd, xo[b:b + 1], to[b:b + 1], theta, graphs, gcn_w)[2][0]
+    a, r = unflatten_trainable(grads[0], dims), unflatten_trainable(gsum, dims)
+    for kk in a:
+        assert rel_err(a[kk], r[kk]) <= 1e-4, kk
+    # oracle spot check of window 0 (reference arithmetic, CPU)
+    x, y = P.window_xy(feats[0], starts[0][0], dims.window, dims.horizon)
+    l_ref, _, p_ref = P.loss_and_grads(sds[0], x, y, ei, dims.window, dims.horizon, 1.0, 4)
+    got = pred[:n].cpu().view(n, dims.horizon, 12).reshape(-1, 12)
+    assert rel_err(got, p_ref) <= 1e-4 and abs(loss[0].item() - float(l_ref)) <= 1e-4 * float(l_ref)
+
+
+def test_config2_tasks_are_independent():
+    """configs[1] shape: 15 tasks of 441 nodes in one launch; a task's result does not depend on its neighbours
+    in the batch (own graph, own fast weights) -- run alone it gives the same predictions, loss and gradients."""
+    from weatherforecast_stgcn_maml_b200.engine import unflatten_trainable
+    from weatherforecast_stgcn_maml_b200.graph import RegionGraph, StackedGraphs
+
+    G = 15
+    dims, ei, base, sds, feats, starts, xo, to, theta, graphs, gcn_w = _setup(21, 21, 8, G, 1)
+    fd = feats.cuda()
+    pred, loss, grads = _run(dims, G, 1, fd, xo, to, theta, graphs, gcn_w)
+    n = dims.num_nodes
+    assert torch.isfinite(grads).all() and torch.isfinite(pred).all()
+    for g in (0, 6, 14):
+        one = StackedGraphs([RegionGraph(ei, dims.R, "cuda")])
+        p1, l1, g1 = _run(dims, 1, 1, fd, xo[g:g + 1], to[g:g + 1], theta[g:g + 1].contiguous(), one, gcn_w)
+        assert rel_err(pred[g * n:(g + 1) * n], p1) <= 1e-5
+        assert abs(loss[g].item() - l1[0].item()) <= 1e-5 * abs(l1[0].item())
+        a, r = unflatten_trainable(grads[g], dims), unflatten_trainable(g1[0], dims)
+        for kk in a:
+            assert rel_err(a[kk], r[kk]) <= 1e-4, (g, kk)
+
+
+def test_config4_large_graph_gcn_stack():
+    """configs[3]: 121 x 121 = 14,641 nodes, k = 8: the four GCN layers on the tensor-core path.  Rows >= N only see
+    their self loop, so they must equal relu(x W^T + b) layer by layer; rows < N are checked against an explicit
+    sparse aggregation; the whole output against the exact-FP32 CUDA path."""
+    from weatherforecast_stgcn_maml_b200.engine import HybridEngine, V5Dims, gcn_weights_from_state_dict
+    from weatherforecast_stgcn_maml_b200.graph import RegionGraph
+
+    nlat = nlon = 121
+    n, T, Bw = nlat * nlon, 24, 2
+    dims = V5Dims(num_nodes=n)
+    lats, lons = synth.region_grid(nlat, nlon)
+    ei = P.knn_edges_canonical(lats, lons, 8)
+    sd = synth.init_v5_state_dict(3, gcn_bias_scale=0.05)
+    gcn_w = gcn_weights_from_state_dict(sd, "cuda")
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(Bw * T * n, 24, generator=g).cuda()
+    graph = RegionGraph(ei, dims.R, "cuda")
+    outs = {}
+    for prec in ("tf32x3", "fp32"):
+        eng = HybridEngine(dims, 1, Bw, "cuda", precision=prec, training=False)
+        outs[prec] = eng.gcn_forward(x, 24, dims.R * 24, None, gcn_w, graph).clone()
+        eng.check()
+        del eng
+        torch.cuda.empty_cache()
+    assert rel_err(outs["tf32x3"], outs["fp32"]) <= 2e-5
+    # explicit reference in torch on the GPU: A_hat from the same CSR, layer by layer
+    rp, col, val = graph.rowptr.long(), graph.col.long(), graph.val
+    rows = torch.repeat_interleave(torch.arange(dims.R, device="cuda"), rp[1:] - rp[:-1])
+    A = torch.sparse_coo_tensor(torch.stack([rows, col[:rows.numel()]]), val[:rows.numel()].double(), (dims.R, dims.R),
+                                check_invariants=False).coalesce()
+    h = x.view(Bw, dims.R, 24)
+    for W, b in gcn_w:
+        h = torch.stack([torch.relu(torch.sparse.mm(A, h[w].double()).float() @ W.t() + b) for w in range(Bw)])
+    ref = h.reshape(Bw * dims.R, -1)
+    assert rel_err(outs["tf32x3"], ref) <= 1e-4
+    ident = torch.relu(torch.relu(torch.relu(torch.relu(x @ gcn_w[0][0].t() + gcn_w[0][1]) @ gcn_w[1][0].t() + gcn_w[1][1])
+                                  @ gcn_w[2][0].t() + gcn_w[2][1]) @ gcn_w[3][0].t() + gcn_w[3][1])
+    tail = torch.arange(n, dims.R, device="cuda")  # rows of the slices t >= 1 of window 0
+    assert rel_err(outs["tf32x3"][tail], ident[tail]) <= 1e-4
