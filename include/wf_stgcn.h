@@ -210,9 +210,11 @@ int wf_g16_gemm_nt(const float* A, int rows_g, int G, int K, const void* W16_hi,
  * the A-operand path.  X dense [G*Bw*R, Cin], Cin % 64 == 0, Cout % 128 == 0; W16 hi/lo = wf_split16(W, 0), shared
  * by all groups; YT hi/lo (optional): bf16 transposed copies [(G*Bw)][Cout][RT16] for the LSTM layer-0 dW.
  * gather_rows (optional, i32 [G][gather_max], -1 padded): rows of a window whose aggregation is not the unit self
- * loop; with agg (scratch f32 [G*Bw*R, Cin]) they are aggregated by a pre-pass instead of inside the GEMM. */
-int wf_gcn_layer_fwd_g16(const float* X, const void* W16_hi, const void* W16_lo, const float* bias,
-                         const int* rowptr, const int* col, const float* val, long long rowptr_group_stride,
+ * loop; with agg (scratch f32 [G*Bw*R, Cin]) they are aggregated by a pre-pass instead of inside the GEMM.
+ * x_win_off (optional): element offset of every window in X = a resident features tensor with x_rows_total rows of
+ * Cin floats (dataset.py:36-37: a window is a contiguous slice); Cin % 8 == 0 suffices then (needs gather_rows + agg). */
+int wf_gcn_layer_fwd_g16(const float* X, const long long* x_win_off, long long x_rows_total,
+                         const void* W16_hi, const void* W16_lo, const float* bias, const int* rowptr, const int* col, const float* val, long long rowptr_group_stride,
                          long long csr_group_stride, const int* gather_rows, int gather_max,
                          long long gather_group_stride, float* agg, int R, int N, int Cin, int Cout, int G, int Bw,
                          int relu, float* Y, void* YT_hi, void* YT_lo, int* err, void* stream);

@@ -65,7 +65,7 @@ SIGNATURES = {
     "wf_split16": (c_i, [c_p, c_p, c_p, c_ll, c_i, c_p]),
     "wf_transposed_pitch16": (c_ll, [c_i, c_i]),
     "wf_g16_gemm_nt": (c_i, [c_p, c_i, c_i, c_i, c_p, c_p, c_ll, c_i, c_p, c_p, c_ll, c_i, c_i, c_p, c_p, c_p]),
-    "wf_gcn_layer_fwd_g16": (c_i, [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_ll, c_ll, c_p, c_i, c_ll, c_p, c_i, c_i, c_i, c_i,
+    "wf_gcn_layer_fwd_g16": (c_i, [c_p, c_p, c_ll, c_p, c_p, c_p, c_p, c_p, c_p, c_ll, c_ll, c_p, c_i, c_ll, c_p, c_i, c_i, c_i, c_i,
                                    c_i, c_i, c_i, c_p, c_p, c_p, c_p, c_p]),
     "wf_prep_weights_seq": (c_i, [c_p, c_ll, c_i, c_i, c_i, c_i, c_i, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p]),
     "wf_lstm_fwd_seq": (c_i, [c_p, c_p, c_p, c_p, c_ll, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_p, c_p, c_p,

@@ -38,12 +38,15 @@ struct G16Args {
   int mode;
   int m_tiles, n_tiles, G, splits;   // tile id -> (split, g, m tile, n tile), n fastest
   int rows_g, a_group_rows;          // ROWS: valid rows per group / row stride between groups in the A map
+  const long long* a_win_off;        // ROWS, optional: element offset of every window (g*Bw + w) in A -- windows read in place
+  int win_tiles;                     //   from a resident features tensor (dataset.py:36-37); tiles per window
   int Bw, R, Nn, T, tpw, Np, RT;
   int nkb, nseg, nkb_split;          // k-blocks (64 wide) per segment; segments (wgrad: windows); split-K slice
   int a_k0, b_k0;
   int b_gmul;                        // 0: B shared by all groups
   int a_tb4;
   const float* a_raw; int lda;       // CSR gather on A (GCN aggregation), ROWS only
+  int kreal;                         // real K of the operands (<= 64 * nkb; columns beyond are zero)
   const int* rowptr; const int* col; const float* val; long long g_rowptr, g_csr;
   const float* agg;                  // optional: pre-aggregated rows (same indexing as a_raw) for rows with neighbours
   float* C; int ldc; long long c_gstride, c_sstride; int c_cols;
@@ -84,6 +87,7 @@ struct TileCoord {
   int g, mt, ntile, split;
   int a_row, a_z0, b_z0, zstep;   // TMA coordinates
   int zt, blk, node0;             // NODES
+  int row0, rlim;                 // ROWS / WGRAD: first output row of the tile in its group, exclusive row limit
   int kb0, nkb_loc;
 };
 
@@ -95,7 +99,13 @@ __device__ __forceinline__ TileCoord decode_tile(const G16Args& a, int tile) {
   c.split = tile / a.G;
   c.a_z0 = 0; c.zstep = 0; c.b_z0 = c.g * a.b_gmul; c.zt = 0; c.blk = 0; c.node0 = 0;
   c.kb0 = 0; c.nkb_loc = a.nkb;
-  if (a.mode == G16_ROWS) {
+  c.row0 = c.mt * 128; c.rlim = a.rows_g;
+  if (a.mode == G16_ROWS && a.a_win_off != nullptr) {
+    const int w = c.mt / a.win_tiles, mtw = c.mt - w * a.win_tiles;
+    c.a_row = (int)(a.a_win_off[c.g * a.Bw + w] / a.lda) + mtw * 128;
+    c.row0 = w * a.R + mtw * 128;
+    c.rlim = w * a.R + a.R;
+  } else if (a.mode == G16_ROWS) {
     c.a_row = c.g * a.a_group_rows + c.mt * 128;
   } else if (a.mode == G16_NODES) {
     const int ztl = c.mt / a.tpw, nt = c.mt - ztl * a.tpw;
@@ -217,8 +227,8 @@ wf_g16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
       n_p0 = 0; n_p1 = 0; n_col = -1; n_val = 0.f;
       if (a.mode == G16_ROWS && a.rowptr != nullptr && tile < total) {
         const TileCoord c = decode_tile(a, tile);
-        const int grow = c.mt * 128 + row;
-        if (grow < a.rows_g) {
+        const int grow = c.row0 + row;
+        if (grow < c.rlim) {
           const int rr = grow % a.R;
           const int* rp = a.rowptr + c.g * a.g_rowptr;
           n_p0 = __ldg(rp + rr); n_p1 = __ldg(rp + rr + 1);
@@ -235,8 +245,8 @@ wf_g16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
       int grow_in_w = 0;
       bool gather = false;
       if (a.mode == G16_ROWS && a.rowptr != nullptr) {  // rows whose aggregation is not the unit self loop
-        const int grow = c.mt * 128 + row;
-        if (grow < a.rows_g) {
+        const int grow = c.row0 + row;
+        if (grow < c.rlim) {
           const int w = grow / a.R, rr = grow - w * a.R;
           grow_in_w = rr;
           wbase = ((long long)c.g * a.a_group_rows + (long long)w * a.R) * a.lda;
@@ -273,7 +283,7 @@ wf_g16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
             const float4* src = reinterpret_cast<const float4*>(a.agg + wbase + (long long)grow_in_w * a.lda + k0);
 #pragma unroll
             for (int ch = 0; ch < 8; ++ch) {
-              const float4 x = __ldg(src + ch);
+              const float4 x = k0 + 4 * ch < a.kreal ? __ldg(src + ch) : make_float4(0.f, 0.f, 0.f, 0.f);
               acc[4 * ch + 0] = x.x; acc[4 * ch + 1] = x.y; acc[4 * ch + 2] = x.z; acc[4 * ch + 3] = x.w;
             }
           } else
@@ -333,8 +343,8 @@ wf_g16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
           }
         }
       } else {
-        const int grow = c.mt * 128 + row;
-        const bool valid = grow < a.rows_g;
+        const int grow = c.row0 + row;
+        const bool valid = grow < c.rlim;
         float* crow = a.C + c.g * a.c_gstride + c.split * a.c_sstride + (long long)grow * a.ldc + n0;
         long long ctbase = 0;
         if (a.ct_hi != nullptr && valid) {
@@ -463,8 +473,9 @@ int wf_launch_split16(const float* src, long long src_gstride, void* hi, void* l
 
 // AGG[z][rr] = sum_p val[p] * X[z][col[p]] for the listed rows rr of every window z (rows whose aggregation is not
 // the unit self loop; -1 entries are padding).  grid (ceil(nlist / 8), G*Bw), one warp per (row, window).
-static __global__ void __launch_bounds__(256) wf_agg_rows_kernel(const float* __restrict__ X, float* __restrict__ AGG, int C, int R,
-                                                                 int Bw, const int* __restrict__ rowptr, const int* __restrict__ col,
+static __global__ void __launch_bounds__(256) wf_agg_rows_kernel(const float* __restrict__ X, const long long* __restrict__ x_win_off,
+                                                                 float* __restrict__ AGG, int C, int R, int Bw,
+                                                                 const int* __restrict__ rowptr, const int* __restrict__ col,
                                                                  const float* __restrict__ val, long long g_rowptr, long long g_csr,
                                                                  const int* __restrict__ list, int nlist, long long g_list) {
   const int z = blockIdx.y, g = z / Bw, i = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
@@ -473,7 +484,7 @@ static __global__ void __launch_bounds__(256) wf_agg_rows_kernel(const float* __
   if (rr < 0) return;
   const int* rp = rowptr + g * g_rowptr;
   const int p0 = rp[rr], p1 = rp[rr + 1];
-  const float* Xz = X + (long long)z * R * C;
+  const float* Xz = X + (x_win_off ? x_win_off[z] : (long long)z * R * C);
   for (int c4 = lane; c4 < (C >> 2); c4 += 32) {
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int p = p0; p < p1; ++p) {
@@ -491,8 +502,13 @@ int wf_launch_g16_rows(int fmt, const float* A, long long a_rows_total, int lda,
                        const void* Whi, const void* Wlo, int ldb, long long b_gstride, int b_shared, int N, const float* bias,
                        const float* bias2, long long bias_gstride, int relu, float* C, int ldc, long long c_gstride,
                        const int* rowptr, const int* col, const float* val, long long g_rowptr, long long g_csr, int R, int Bw,
-                       void* ct_hi, void* ct_lo, int Nn, const float* agg, int* err, cudaStream_t st) {
-  WF_REQUIRE(K % 64 == 0 && K >= 64, "g16_rows: K=%d must be a multiple of 64", K);
+                       void* ct_hi, void* ct_lo, int Nn, const float* agg, int* err, cudaStream_t st,
+                       const long long* a_win_off = nullptr, int kpad = 0) {
+  // kpad: the K extent seen by the k-loop when the operands' real K (their row length) is shorter and not a multiple of
+  // 64: TMA zero-fills the columns beyond K (the 24-channel first GCN layer)
+  if (kpad > 0) { WF_REQUIRE(K % 8 == 0 && kpad % 64 == 0 && kpad >= K, "g16_rows: bad K padding %d -> %d", K, kpad); }
+  else WF_REQUIRE(K % 64 == 0 && K >= 64, "g16_rows: K=%d must be a multiple of 64", K);
+  WF_REQUIRE(a_win_off == nullptr || (rowptr == nullptr || agg != nullptr), "g16_rows: windowed A needs pre-aggregated rows");
   WF_REQUIRE(N % 128 == 0, "g16_rows: N=%d must be a multiple of 128", N);
   WF_REQUIRE(lda % 4 == 0 && ldb % 8 == 0 && ldc % 4 == 0, "g16_rows: leading dimensions must keep 16-byte alignment");
   WF_REQUIRE(((uintptr_t)A | (uintptr_t)Whi | (uintptr_t)Wlo | (uintptr_t)C) % 16 == 0, "g16_rows: pointers must be 16-byte aligned");
@@ -505,11 +521,12 @@ int wf_launch_g16_rows(int fmt, const float* A, long long a_rows_total, int lda,
   G16Args a;
   g16_defaults(a);
   a.mode = G16_ROWS; a.m_tiles = wf_cdiv(rows_g, 128); a.n_tiles = N / 128; a.G = G;
-  a.rows_g = rows_g; a.a_group_rows = a_group_rows; a.nkb = K / 64; a.b_gmul = b_shared ? 0 : 1;
-  a.a_raw = A; a.lda = lda; a.rowptr = rowptr; a.col = col; a.val = val; a.g_rowptr = g_rowptr; a.g_csr = g_csr; a.agg = agg;
+  a.rows_g = rows_g; a.a_group_rows = a_group_rows; a.nkb = (kpad > 0 ? kpad : K) / 64; a.b_gmul = b_shared ? 0 : 1;
+  a.a_raw = A; a.lda = lda; a.kreal = K; a.rowptr = rowptr; a.col = col; a.val = val; a.g_rowptr = g_rowptr; a.g_csr = g_csr; a.agg = agg;
   a.R = R > 0 ? R : rows_g; a.Bw = Bw > 0 ? Bw : 1;
   a.Nn = Nn > 0 ? Nn : a.R; a.Np = wf_np(a.Nn); a.RT = (a.R / a.Nn) * a.Np;
   WF_REQUIRE(ct_hi == nullptr || a.R % a.Nn == 0, "g16_rows: transposed copies need R to be a multiple of the node count");
+  if (a_win_off != nullptr) { a.a_win_off = a_win_off; a.win_tiles = wf_cdiv(a.R, 128); a.m_tiles = a.Bw * a.win_tiles; }
   a.C = C; a.ldc = ldc; a.c_gstride = c_gstride; a.c_cols = N; a.bias = bias; a.bias2 = bias2; a.bias_gstride = bias_gstride;
   a.relu = relu; a.ct_hi = (__nv_bfloat16*)ct_hi; a.ct_lo = (__nv_bfloat16*)ct_lo; a.err = err;
   return g16_launch(fmt, tmA, tmBhi, tmBlo, a, st);
@@ -657,25 +674,30 @@ extern "C" long long wf_transposed_pitch16(int T, int N) { return (long long)T *
 // gather_rows (optional): per group the rows of a window whose aggregation is not the unit self loop, padded with -1 to
 // gather_max, with `agg` a scratch [G*Bw*R, Cin]: those rows are aggregated by a small pre-pass and the GEMM reads one
 // row instead of walking the CSR inside its operand pipeline.
-extern "C" int wf_gcn_layer_fwd_g16(const float* X, const void* W16_hi, const void* W16_lo, const float* bias, const int* rowptr,
-                                    const int* col, const float* val, long long rowptr_group_stride, long long csr_group_stride,
-                                    const int* gather_rows, int gather_max, long long gather_group_stride, float* agg, int R,
-                                    int N, int Cin, int Cout, int G, int Bw, int relu, float* Y, void* YT_hi, void* YT_lo,
-                                    int* err, void* stream) {
+// x_win_off (optional): element offset of every window in X, a resident features tensor of x_rows_total rows of Cin
+// floats (the first layer reads windows in place, dataset.py:36-37); Cin only has to be a multiple of 8 then (TMA
+// zero-fills the k-block).
+extern "C" int wf_gcn_layer_fwd_g16(const float* X, const long long* x_win_off, long long x_rows_total, const void* W16_hi,
+                                    const void* W16_lo, const float* bias, const int* rowptr, const int* col, const float* val,
+                                    long long rowptr_group_stride, long long csr_group_stride, const int* gather_rows,
+                                    int gather_max, long long gather_group_stride, float* agg, int R, int N, int Cin, int Cout,
+                                    int G, int Bw, int relu, float* Y, void* YT_hi, void* YT_lo, int* err, void* stream) {
   WF_REQUIRE(G > 0 && Bw > 0 && R > 0 && N > 0, "gcn_layer_fwd_g16: bad batch");
   const long long rows_g = (long long)Bw * R;
   cudaStream_t st = (cudaStream_t)stream;
   const bool pre = rowptr != nullptr && gather_rows != nullptr && agg != nullptr && gather_max > 0;
+  WF_REQUIRE(x_win_off == nullptr || rowptr == nullptr || pre, "gcn_layer_fwd_g16: windows read in place need gather_rows + agg");
   if (pre) {
     WF_REQUIRE(Cin % 4 == 0, "gcn_layer_fwd_g16: Cin must be a multiple of 4");
-    wf_agg_rows_kernel<<<dim3(wf_cdiv(gather_max, 8), G * Bw), 256, 0, st>>>(X, agg, Cin, R, Bw, rowptr, col, val, rowptr_group_stride,
-                                                                            csr_group_stride, gather_rows, gather_max,
-                                                                            gather_group_stride);
+    wf_agg_rows_kernel<<<dim3(wf_cdiv(gather_max, 8), G * Bw), 256, 0, st>>>(X, x_win_off, agg, Cin, R, Bw, rowptr, col, val,
+                                                                            rowptr_group_stride, csr_group_stride, gather_rows,
+                                                                            gather_max, gather_group_stride);
     WF_CHECK_LAUNCH("agg_rows");
   }
-  return wf_launch_g16_rows(0, X, rows_g * G, Cin, (int)rows_g, (int)rows_g, G, Cin, W16_hi, W16_lo, Cin, 0, 1, Cout, bias, nullptr,
-                            0, relu, Y, Cout, rows_g * Cout, rowptr, col, val, rowptr_group_stride, csr_group_stride, R, Bw, YT_hi,
-                            YT_lo, N, pre ? agg : nullptr, err, st);
+  const int kpad = Cin % 64 == 0 ? 0 : (Cin + 63) / 64 * 64;
+  return wf_launch_g16_rows(0, X, x_win_off ? x_rows_total : rows_g * G, Cin, (int)rows_g, (int)rows_g, G, Cin, W16_hi, W16_lo, Cin,
+                            0, 1, Cout, bias, nullptr, 0, relu, Y, Cout, rows_g * Cout, rowptr, col, val, rowptr_group_stride,
+                            csr_group_stride, R, Bw, YT_hi, YT_lo, N, pre ? agg : nullptr, err, st, x_win_off, kpad);
 }
 
 // Test / general entry point: C[g] = A[g] W[g]^T (+ bias + bias2, relu), W16 hi/lo [G][N, K] from wf_split16(W, fmt).

@@ -234,12 +234,14 @@ class HybridEngine:
         for i, (Wt, b) in enumerate(gcn_weights):
             dst = self.act[i] if self.keep_gcn else self.act[i & 1]
             dense = src_off is None and src_ld == cin and src_stride == d.R * cin
-            if self.seq and dense and cin % 64 == 0:
+            in_place = src_off is not None and src_ld == cin and gmax > 0  # windows read straight from the features
+            if self.seq and (dense or in_place) and cin % 8 == 0 and (cin % 64 == 0 or src.data_ptr() % 16 == 0):
                 want_t = self.training and i == nlayers - 1
                 w16 = self._gcn_w_lo(Wt)
                 if self.agg is None:
                     self.agg = torch.empty(self.rows, d.hidden, dtype=torch.float32, device=self.device)
-                _lib.call("wf_gcn_layer_fwd_g16", _lib.ptr(src), _lib.ptr(w16[0]), _lib.ptr(w16[1]), _lib.ptr(b),
+                _lib.call("wf_gcn_layer_fwd_g16", _lib.ptr(src), _lib.ptr(src_off) if in_place else None,
+                          src.numel() // cin, _lib.ptr(w16[0]), _lib.ptr(w16[1]), _lib.ptr(b),
                           _lib.ptr(rp), _lib.ptr(cl), _lib.ptr(vl), rps, cs, _lib.ptr(gl) if gmax > 0 else None, gmax, gls,
                           _lib.ptr(self.agg), d.R, d.num_nodes, cin, d.hidden, self.G,
                           self.Bw, 1, _lib.ptr(dst), _lib.ptr(self.featsT) if want_t else None,
