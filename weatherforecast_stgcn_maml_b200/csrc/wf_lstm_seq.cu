@@ -609,23 +609,35 @@ wf_lstm_seq_bwd_kernel(const __grid_constant__ CUtensorMap tmWhi, const __grid_c
 //   f16_hi / f16_lo [G][layers][4L][L]            (forward: rows = gate rows, K = hidden units)
 //   b16_hi / b16_lo [G][layers][2][L][2L]         (backward: per CTA rank, rows = hidden units n,
 //                                                  K = gate*64 + (unit - 64*rank) over the rank's own gate rows)
-__global__ void wf_prep_seq_kernel(const float* __restrict__ params, long long gstride, LstmLayout P, int layers, int L,
-                                   __half* __restrict__ f_hi, __half* __restrict__ f_lo, __nv_bfloat16* __restrict__ b_hi,
-                                   __nv_bfloat16* __restrict__ b_lo) {
+// One block = a 32 (gate rows j) x 32 (hidden units n) tile: the forward copy keeps the orientation, the backward copy
+// is its transpose, staged through shared memory so that both are written with consecutive lanes on consecutive addresses.
+__global__ void __launch_bounds__(256) wf_prep_seq_kernel(const float* __restrict__ params, long long gstride, LstmLayout P,
+                                                          int layers, int L, __half* __restrict__ f_hi, __half* __restrict__ f_lo,
+                                                          __nv_bfloat16* __restrict__ b_hi, __nv_bfloat16* __restrict__ b_lo) {
+  __shared__ float tile[32][33];
   const int g = blockIdx.z, l = blockIdx.y;
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;  // over [4L][L]
-  if (idx >= 4 * L * L) return;
-  const int j = idx / L, n = idx - j * L;
-  const float v = params[g * gstride + P.w_hh[l] + idx];
+  const int tiles_n = L / 32, j0 = (blockIdx.x / tiles_n) * 32, n0 = (blockIdx.x % tiles_n) * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
   const long long slab = (long long)g * layers + l;
-  const __half h = __float2half_rn(v);
-  f_hi[slab * 4 * L * L + idx] = h;
-  f_lo[slab * 4 * L * L + idx] = __float2half_rn(v - __half2float(h));
-  const int gate = j / L, u = j - gate * L, rk = u >> 6, ul = u & 63;
-  const long long o = ((slab * 2 + rk) * L + n) * (2 * L) + gate * 64 + ul;
-  const __nv_bfloat16 b = __float2bfloat16_rn(v);
-  b_hi[o] = b;
-  b_lo[o] = __float2bfloat16_rn(v - __bfloat162float(b));
+  const float* W = params + g * gstride + P.w_hh[l];
+  for (int i = ty; i < 32; i += 8) {
+    const int idx = (j0 + i) * L + n0 + tx;
+    const float v = W[idx];
+    tile[i][tx] = v;
+    const __half h = __float2half_rn(v);
+    f_hi[slab * 4 * L * L + idx] = h;
+    f_lo[slab * 4 * L * L + idx] = __float2half_rn(v - __half2float(h));
+  }
+  __syncthreads();
+  // 32 consecutive gate rows j0 .. j0+31 share gate and rank (j0 is a multiple of 32, gates / ranks change every 128 / 64)
+  const int gate = j0 / L, u0 = j0 - gate * L, rk = u0 >> 6, ul0 = u0 & 63;
+  for (int i = ty; i < 32; i += 8) {
+    const float v = tile[tx][i];                              // element (j0 + tx, n0 + i)
+    const long long o = ((slab * 2 + rk) * L + n0 + i) * (2 * L) + gate * 64 + ul0 + tx;
+    const __nv_bfloat16 b = __float2bfloat16_rn(v);
+    b_hi[o] = b;
+    b_lo[o] = __float2bfloat16_rn(v - __bfloat162float(b));
+  }
 }
 
 int seq_maps_fwd(CUtensorMap* hi, CUtensorMap* lo, const void* f_hi, const void* f_lo, int L, int slabs) {
@@ -692,7 +704,7 @@ extern "C" int wf_prep_weights_seq(const float* params, long long params_group_s
                                      (uint16_t*)pT16_lo + P.wihT[l], stride16(P.totalT), G, st);
     if (rc) return rc;
   }
-  dim3 grid(wf_cdiv(4 * L * L, 256), layers, G);
+  dim3 grid((4 * L / 32) * (L / 32), layers, G);
   wf_prep_seq_kernel<<<grid, 256, 0, st>>>(params, params_group_stride, P, layers, L, (__half*)f16_hi, (__half*)f16_lo,
                                            (__nv_bfloat16*)b16_hi, (__nv_bfloat16*)b16_lo);
   WF_CHECK_LAUNCH("prep_weights_seq");
