@@ -12,12 +12,13 @@
 // Forward (N split): CTA r of the pair holds W_hh rows of units [64r, 64r+64) x 4 gates
 // (256 x 128, hi + lo = 128 KB), computes D[128 x 256] = h[t-1] W^T from shared memory (SS mode),
 // applies the cell non-linearities and writes its 64 units of h[t] as fp16 hi/lo straight into
-// the A-operand buffer of BOTH CTAs (st.shared::cluster), so the only per-step exchange is the
-// operand itself.
+// the A-operand buffer of BOTH CTAs -- the peer's copy as st.async transactions that complete on the
+// peer's mbarrier (no cluster-scope release on the sending warp) -- so the only per-step exchange is
+// the operand itself.
 // Backward (K split): CTA r holds W_hh^T restricted to its own gate rows (128 x 256, 128 KB), keeps
 // its own dG[t+1] (128 x 256) in TMEM as the A operand (TS mode) and produces a partial
 // dh[128 x 128]; the half belonging to the peer's units goes through distributed shared memory
-// (fp32, 32 KB per step, double buffered).
+// (fp32, 32 KB per step as st.async transactions, double buffered).
 //
 // Activation layout ("TB4", wf_layout.cuh): per (window, step, 128-node tile) a block of
 // [channels / 4][128 rows][4 floats], so a warp whose lanes are consecutive rows moves 512
@@ -78,11 +79,11 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t saddr, uint32_t rank) {
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;\n" : "=r"(r) : "r"(saddr), "r"(rank));
   return r;
 }
-__device__ __forceinline__ void st_cluster_v4(uint32_t caddr, uint4 v) {
-  asm volatile("st.shared::cluster.v4.b32 [%0], {%1, %2, %3, %4};\n" ::"r"(caddr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
-}
-__device__ __forceinline__ void arrive_cluster(uint32_t cbar) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];\n" ::"r"(cbar) : "memory");
+// asynchronous 16-byte store into the peer CTA's shared memory that signals `cbar` (an mbarrier of the SAME peer CTA)
+// with the byte count when it lands: the data hand-over needs no release fence on the sending warp
+__device__ __forceinline__ void st_async_v4(uint32_t caddr, uint4 v, uint32_t cbar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];\n"
+               ::"r"(caddr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "r"(cbar) : "memory");
 }
 // no data is published with this arrival (it only says "my tensor core is done reading"): no memory barrier
 __device__ __forceinline__ void arrive_cluster_relaxed(uint32_t cbar) {
@@ -99,10 +100,6 @@ __device__ __forceinline__ bool mbar_wait_cl(uint64_t* bar, uint32_t parity) {
   }
   return false;
 }
-// generic-proxy writes to (distributed) shared memory -> visible to the async proxy (tensor core operand reads);
-// the unqualified form also fences global memory (MEMBAR.ALL.GPU: waits for every outstanding global store)
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cluster;\n" ::: "memory"); }
-
 // kind::f16 instruction descriptor: D = F32, A/B = fmt (0 F16, 1 BF16), both K-major, M = 128
 __host__ __device__ constexpr uint32_t idesc_16(int n, uint32_t fmt) {
   return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
@@ -160,7 +157,8 @@ wf_lstm_seq_fwd_kernel(const __grid_constant__ CUtensorMap tmWhi, const __grid_c
   const int T = a.T;
 
   if (tid == 0) {
-    mbar_init(&wfull, 1); mbar_init(&a_ready, 16); mbar_init(&dfull, 1); mbar_init(&peer_done, 1);
+    // a_ready: 8 local warps + the expect_tx arrival; the peer's half of h[t] arrives as 32 KB of st.async transactions
+    mbar_init(&wfull, 1); mbar_init(&a_ready, 9); mbar_init(&dfull, 1); mbar_init(&peer_done, 1);
     mbar_fence_init();
     tma_prefetch_desc(&tmWhi); tma_prefetch_desc(&tmWlo);
   }
@@ -172,6 +170,7 @@ wf_lstm_seq_fwd_kernel(const __grid_constant__ CUtensorMap tmWhi, const __grid_c
   const uint32_t tbase = tmem_base_s;
 
   if (warp == 0 && lane == 0) {  // recurrent weights of this tile's task: resident for all T steps
+    if (T > 1) mbar_expect_tx(&a_ready, 32768);  // phase 0: the peer's half of h[0]
     const int slab = a.slab0 + g * a.slab_g;
     mbar_expect_tx(&wfull, 131072);
     for (int kb = 0; kb < 2; ++kb) {
@@ -231,6 +230,7 @@ wf_lstm_seq_fwd_kernel(const __grid_constant__ CUtensorMap tmWhi, const __grid_c
         if (warp == 0) {  // MMA issue: D[128 x 256] = h[t-1] W_hh^T for this CTA's 64 units x 4 gates
           if (ok && t == 1 && !mbar_wait(&wfull, 0)) { ok = false; if (lane == 0) atomicExch(a.err, 11); }
           if (ok && !mbar_wait_cl(&a_ready, (t - 1) & 1)) { ok = false; if (lane == 0) atomicExch(a.err, 12); }
+          if (lane == 0 && t + 1 < T) mbar_expect_tx(&a_ready, 32768);  // phase t: the peer's half of h[t]
           fence_proxy_async_cta();
           tc_fence_after();
           if (lane == 0 && ok) {
@@ -339,8 +339,8 @@ wf_lstm_seq_fwd_kernel(const __grid_constant__ CUtensorMap tmWhi, const __grid_c
           const uint4 vhi = make_uint4(hi[0], hi[1], hi[2], hi[3]), vlo = make_uint4(lo[0], lo[1], lo[2], lo[3]);
           *reinterpret_cast<uint4*>(a_hi + off) = vhi;
           *reinterpret_cast<uint4*>(a_lo + off) = vlo;
-          st_cluster_v4(mapa_u32(smem_u32(a_hi + off), peer), vhi);
-          st_cluster_v4(mapa_u32(smem_u32(a_lo + off), peer), vlo);
+          st_async_v4(mapa_u32(smem_u32(a_hi + off), peer), vhi, ar_remote);
+          st_async_v4(mapa_u32(smem_u32(a_lo + off), peer), vlo, ar_remote);
         }
         if (c < 3) {
           // loads first: the memory pipeline is in order, a load queued behind a burst of stores waits for it
@@ -352,16 +352,13 @@ wf_lstm_seq_fwd_kernel(const __grid_constant__ CUtensorMap tmWhi, const __grid_c
         }
       }
       if (t + 1 < T) {
-        // Hand h[t] over.  The cluster-scope release below is a full memory barrier for this warp (MEMBAR.ALL.GPU in
-        // SASS), so nothing recent may be in flight here: the last chunk's global stores and the next step's input
-        // prefetch are issued after it and overlap the next step's MMA instead.
-        fence_proxy_async();      // generic-proxy operand writes -> visible to the tensor core (async proxy)
+        // Hand h[t] over.  The peer's copy travels as st.async transactions that complete on the peer's barrier by
+        // themselves; locally only a shared-memory proxy fence and a CTA-scope arrive are needed -- no cluster-scope
+        // release (MEMBAR.ALL.GPU, which waits for every outstanding global store of the warp) on the critical path.
+        fence_proxy_async_cta();  // my generic-proxy operand writes -> visible to the tensor core (async proxy)
         tc_fence_before();        // my TMEM reads of D[t] are complete before MMA[t+1] may overwrite D
         __syncwarp();
-        if (lane == 0) {
-          mbar_arrive(&a_ready);
-          arrive_cluster(ar_remote);
-        }
+        if (lane == 0) mbar_arrive(&a_ready);
       }
       if (t + 1 < T) {
         load_chunk(t + 1, 0, xq[0]);
@@ -395,7 +392,7 @@ wf_lstm_seq_bwd_kernel(const __grid_constant__ CUtensorMap tmWhi, const __grid_c
   const int T = a.T;
 
   if (tid == 0) {
-    mbar_init(&wfull, 1); mbar_init(&a_ready, 8); mbar_init(&dfull, 1); mbar_init(&x_ready[0], 8); mbar_init(&x_ready[1], 8);
+    mbar_init(&wfull, 1); mbar_init(&a_ready, 8); mbar_init(&dfull, 1); mbar_init(&x_ready[0], 1); mbar_init(&x_ready[1], 1);  // 1 = the expect_tx arrival; data = 32 KB of st.async
     mbar_fence_init();
     tma_prefetch_desc(&tmWhi); tma_prefetch_desc(&tmWlo);
   }
@@ -472,6 +469,8 @@ wf_lstm_seq_bwd_kernel(const __grid_constant__ CUtensorMap tmWhi, const __grid_c
       const int t = T - 1 - s;
       const int xb = s & 1;
       if (s > 0) {
+        // the peer's partial dh for my units arrives as st.async transactions on x_ready[xb] (phase (s - 1) / 2)
+        if (warp == 0 && lane == 0) mbar_expect_tx(&x_ready[xb], 32768);
         if (warp == 0) {  // MMA issue: partial dh[128 x 128] = dG[t+1][:, my gate rows] W_hh[my gate rows, :]
           if (ok && s == 1 && !mbar_wait(&wfull, 0)) { ok = false; if (lane == 0) atomicExch(a.err, 21); }
           if (ok && !mbar_wait(&a_ready, (s - 1) & 1)) { ok = false; if (lane == 0) atomicExch(a.err, 22); }
@@ -504,11 +503,9 @@ wf_lstm_seq_bwd_kernel(const __grid_constant__ CUtensorMap tmWhi, const __grid_c
           tmem_ld8(tlane + 64 * peer + ub + 8 * c, v);
           tmem_wait_ld();
           const uint32_t dst = xbuf_remote + (uint32_t)xb * 32768u + (uint32_t)(((half * 8 + 2 * c) * 128 + r) * 16);
-          st_cluster_v4(dst, make_uint4(v[0], v[1], v[2], v[3]));
-          st_cluster_v4(dst + 2048u, make_uint4(v[4], v[5], v[6], v[7]));
+          st_async_v4(dst, make_uint4(v[0], v[1], v[2], v[3]), xb ? xr_remote1 : xr_remote0);
+          st_async_v4(dst + 2048u, make_uint4(v[4], v[5], v[6], v[7]), xb ? xr_remote1 : xr_remote0);
         }
-        __syncwarp();
-        if (lane == 0) arrive_cluster(xb ? xr_remote1 : xr_remote0);
         if (ok && !mbar_wait_cl(&x_ready[xb], ((s - 1) >> 1) & 1)) { ok = false; if (lane == 0) atomicExch(a.err, 24); }
       }
       const long long blk = blk_of(t);
