@@ -325,6 +325,33 @@ def roofline_report(stages, kernel_ms, G, peak, peak_src):
             "graph_conv_note": "256->256 GCN layer incl. the pre-aggregation pass; the last layer also writes transposed copies"}
 
 
+def finetune_windows_per_sec(sd, dims, steps=96, warmup=16):
+    """configs[2] shape (regional adaptation, adapt_hybrid_v5.py:185-203): batch-1 Adam steps on one 441-node region,
+    windows visited in a shuffled order; device-timed.  Sequential by construction (one optimiser step per window), so
+    this is a latency number: 8 CTAs per LSTM launch."""
+    import torch
+
+    from weatherforecast_stgcn_maml_b200 import synth
+    from weatherforecast_stgcn_maml_b200.adapt_hybrid_v5 import FineTuner
+    from weatherforecast_stgcn_maml_b200.graphBuilder import knn_edge_index_device
+
+    lats, lons, feats, _ = synth.synth_task(7, num_windows=steps + warmup + 8, nlat=NLAT, nlon=NLON)
+    ei = knn_edge_index_device(lats, lons, KNN, "cuda")
+    ft = FineTuner(sd, feats, ei, dims, "cuda", region_name="bench", max_samples=steps + warmup, train_frac=1.0)
+    order = torch.randperm(steps + warmup, generator=torch.Generator().manual_seed(0)).tolist()
+    for i in order[:warmup]:
+        ft.step(i)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in order[warmup:]:
+        ft.step(i)
+    e1.record()
+    torch.cuda.synchronize()
+    ft.engine.check()
+    return steps / (e0.elapsed_time(e1) * 1e-3)
+
+
 def run_gpu(args, rank, local, world):
     import torch
 
@@ -387,6 +414,9 @@ def run_gpu(args, rank, local, world):
         "roofline": roof,
         "stages_ms_per_meta_step": {k: round(v["ms_per_meta_step"], 4) for k, v in stages.items()},
     }
+    line["finetune"] = {"windows_per_sec": finetune_windows_per_sec(sd, dims), "unit": "windows/s",
+                        "workload": "configs[2]: batch-1 Adam fine-tuning steps on one 441-node region (k=8), "
+                                    "forward + MSE + backward + clip + Adam per window, 1 GPU"}
     if world == 1 and not args.no_cpu_baseline:
         sec, cores = cpu_window_pass_seconds(3, 1, literal=True)
         sec_b, _ = cpu_window_pass_seconds(3, 1, literal=False)
