@@ -408,7 +408,9 @@ def run_gpu(args, rank, local, world):
         "dtype": "f32", "data": "synthetic", "config": workload_config(world),
         "windows_per_sec": 60 * world / sec_step, "meta_loss": loss, "clocks": clocks,
         "e2e": {"value": world / (ms2 * 1e-3 / args.steps), "unit": UNIT, "h2d_bytes_per_step": h2d,
-                "d2h_bytes_per_step": 4, "ms_per_step": ms2 / args.steps, "meta_loss": loss2},
+                "d2h_bytes_per_step": 4, "ms_per_step": ms2 / args.steps, "meta_loss": loss2,
+                "note": "features in pinned host memory; every step uploads the rows its windows read (double buffered: the "
+                        "copy for step t+1 runs on a copy stream while step t computes) and reads the loss back (.item())"},
         "gpu_launches": launches_per_step * args.steps,
         "gpu_launches_per_step": launches_per_step,
         "roofline": roof,

@@ -99,14 +99,19 @@ class HostTaskStager:
             host = feats if (feats.is_cuda or feats.is_pinned()) else feats.contiguous().pin_memory()
             self.plans.append((host, cmap))
         self.G, self.rows = len(self.plans), rows_max
-        self.buf = torch.empty(self.G, rows_max, d.num_nodes, d.in_channels, dtype=torch.float32, device=self.device)
+        # two device staging buffers: the upload of step t+1 overlaps the compute of step t
+        self.bufs = [torch.empty(self.G, rows_max, d.num_nodes, d.in_channels, dtype=torch.float32, device=self.device)
+                     for _ in range(2)]
+        self.buf = self.bufs[0]
         self.h2d_bytes = sum((b - a) * self.per_step * 4 for _, cmap in self.plans for a, b, _ in cmap)
 
-    def upload(self):
+    def upload(self, k=0):
+        """Enqueue (on the current stream) the host -> device copies of one step's windows into staging buffer k."""
+        buf = self.bufs[k]
         for g, (host, cmap) in enumerate(self.plans):
             for a, b, pos in cmap:
-                self.buf[g, pos:pos + (b - a)].copy_(host[a:b], non_blocking=True)
-        return self.buf
+                buf[g, pos:pos + (b - a)].copy_(host[a:b], non_blocking=True)
+        return buf
 
     def offsets(self, g, start):
         """(x offset, target offset) in elements into ``buf`` for the window of task g starting at row ``start``."""
@@ -349,7 +354,8 @@ class MetaTrainer:
         self.fast = torch.empty(self.G, self.P, dtype=torch.float32, device=self.device)
         self.meta = torch.zeros(self.P + 4, dtype=torch.float32, device=self.device)  # grad + packed loss
         self.adam = AdamState(self.P, self.device, outer_lr, weight_decay=weight_decay, decoupled=True)
-        self.use_graph, self.graph = bool(use_cuda_graph), None
+        self.use_graph, self.cuda_graphs = bool(use_cuda_graph), [None, None]
+        self._copy = None
         self.launches_per_step = None
 
     # the captured region: no host interaction, fixed pointers
@@ -369,28 +375,62 @@ class MetaTrainer:
         e.launches += 1
         self.meta[self.P:self.P + 1].copy_((e.loss.sum() / self.accum).reshape(1))
 
-    def meta_step(self):
-        """Enqueue one meta-step; returns the (device) meta-loss tensor without synchronising."""
-        if self.stager is not None:
-            self.stager.upload()
-        if self.use_graph:
-            if self.graph is None:
-                before = self.engine.launches
-                side = torch.cuda.Stream(self.device)
-                side.wait_stream(torch.cuda.current_stream(self.device))
-                with torch.cuda.stream(side):
-                    self._body()  # warm-up: module load + autotune-free, outside capture
-                torch.cuda.current_stream(self.device).wait_stream(side)
-                torch.cuda.synchronize(self.device)
-                self.launches_per_step = self.engine.launches - before
-                self.graph = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(self.graph):
-                    self._body()
-            self.graph.replay()
-        else:
+    def _run_body(self, k=0):
+        """Replay (capturing on first use) the CUDA graph of the meta-step body that reads staging buffer k."""
+        if not self.use_graph:
             before = self.engine.launches
             self._body()
             self.launches_per_step = self.engine.launches - before
+            return
+        if self.cuda_graphs[k] is None:
+            before = self.engine.launches
+            side = torch.cuda.Stream(self.device)
+            side.wait_stream(torch.cuda.current_stream(self.device))
+            with torch.cuda.stream(side):
+                self._body()  # warm-up: module load + autotune-free, outside capture
+            torch.cuda.current_stream(self.device).wait_stream(side)
+            torch.cuda.synchronize(self.device)
+            self.launches_per_step = self.engine.launches - before
+            self.cuda_graphs[k] = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.cuda_graphs[k]):
+                self._body()
+        self.cuda_graphs[k].replay()
+
+    def meta_step(self):
+        """Enqueue one meta-step; returns the (device) meta-loss tensor without synchronising."""
+        if self.stager is None:
+            self._run_body(0)
+        elif not self.use_graph:
+            self.features = self.stager.upload(0)
+            self._run_body(0)
+        else:
+            # host-resident features: every step uploads the rows its windows read.  Double buffered: the copy for
+            # step t+1 runs on a copy stream while the graph of step t computes (one upload per step, shifted by one).
+            main = torch.cuda.current_stream(self.device)
+            if self._copy is None:
+                self._copy = torch.cuda.Stream(self.device)
+                self._up_done, self._comp_done, self._t = [None, None], [None, None], 0
+                for k in (0, 1):  # first call: both buffers filled synchronously, both graphs captured
+                    self.features = self.stager.upload(k)
+                    torch.cuda.synchronize(self.device)
+                    if self.cuda_graphs[k] is None:
+                        self._run_body(k)
+                        torch.cuda.synchronize(self.device)
+            k = self._t & 1
+            if self._up_done[k] is not None:
+                main.wait_event(self._up_done[k])
+            self.features = self.stager.bufs[k]
+            self._run_body(k)
+            self._comp_done[k] = torch.cuda.Event()
+            self._comp_done[k].record(main)
+            kn = k ^ 1
+            if self._comp_done[kn] is not None:
+                self._copy.wait_event(self._comp_done[kn])  # the graph that read buffer kn has finished
+            with torch.cuda.stream(self._copy):
+                self.stager.upload(kn)
+                self._up_done[kn] = torch.cuda.Event()
+                self._up_done[kn].record(self._copy)
+            self._t += 1
         if self.dist is not None and self.world > 1:
             self.dist.all_reduce(self.meta, op=self.dist.ReduceOp.SUM, group=self.pg)
         self.adam.step(self.theta, self.meta, max_norm=1.0)
