@@ -93,3 +93,61 @@ def test_task_sharding_round_robin():
     assert shard_tasks(5, 1, 2) == [1, 3]
     with pytest.raises(ValueError):
         shard_tasks(3, 0, 4, require_even=True)
+
+
+def test_cosine_warm_restarts_matches_torch():
+    from weatherforecast_stgcn_maml_b200.schedule import CosineWarmRestarts
+
+    p = torch.nn.Parameter(torch.zeros(1))
+    opt = torch.optim.AdamW([p], lr=1e-3)
+    ref = torch.optim.lr_scheduler.CosineAnnealingWarmRestarts(opt, T_0=10, T_mult=2, eta_min=1e-6)
+    mine = CosineWarmRestarts(1e-3, T_0=10, T_mult=2, eta_min=1e-6)
+    for _ in range(75):  # 40 epochs in the reference (train_hybrid_maml_v5.py:24); run through three restarts
+        opt.step()
+        ref.step()
+        assert mine.step() == pytest.approx(ref.get_last_lr()[0], rel=1e-12, abs=1e-18)
+
+
+def test_adaptive_task_sampler_follows_the_reference_draws():
+    from weatherforecast_stgcn_maml_b200.schedule import AdaptiveTaskSampler
+
+    np.random.seed(42)
+    s = AdaptiveTaskSampler(15, 4)
+    got = []
+    for loss in (0.9, 0.7, 0.65):
+        got.append(s.sample())
+        s.update(loss)
+    # the same sequence written out the way train_hybrid_maml_v5.py:264-292 does it
+    np.random.seed(42)
+    losses, want = [], []
+    for loss in (0.9, 0.7, 0.65):
+        if losses:
+            want.append(list(np.random.choice(15, 4, replace=False, p=np.array(losses) / sum(losses))))
+        else:
+            want.append(list(np.random.choice(15, 4, replace=False)))
+        losses = [loss] * 15 if len(losses) < 15 else [0.9 * t + 0.1 * loss for t in losses]
+    assert got == [[int(i) for i in w] for w in want]
+    assert len(set(s.task_losses)) == 1  # every task carries the same "difficulty": the draw is uniform
+    assert AdaptiveTaskSampler(3, 4).sample() == [0, 1, 2]
+
+
+def test_denormalisation_and_forecast_metrics():
+    from weatherforecast_stgcn_maml_b200.featurePreprocessor import (denormalize_all_predictions, denormalize_predictions,
+                                                                      forecast_metrics)
+
+    rng = np.random.default_rng(0)
+    stats = {"mean": rng.normal(size=12) * 10, "std": rng.uniform(0.5, 3.0, size=12)}
+    pred = rng.normal(size=(40, 12))
+    assert np.allclose(denormalize_all_predictions(pred, stats), pred * stats["std"] + stats["mean"])
+    assert np.allclose(denormalize_all_predictions(pred[0], stats), pred[0] * stats["std"] + stats["mean"])
+    t = torch.tensor(pred[:, 2], dtype=torch.float32)
+    assert torch.allclose(denormalize_predictions(t, stats), t * float(stats["std"][2]) + float(stats["mean"][2]))
+    assert denormalize_predictions(t, {}) is t
+    H, N = 8, 5
+    yp, yt = rng.normal(size=(H * N, 12)), rng.normal(size=(H * N, 12))
+    m = forecast_metrics(torch.tensor(yp), yt, stats, N, H)
+    a = (yp.reshape(H, N, 12).mean(1) * stats["std"] + stats["mean"])
+    b = (yt.reshape(H, N, 12).mean(1) * stats["std"] + stats["mean"])
+    assert m["t2m"]["mse"] == pytest.approx(np.mean((a[:, 2] - b[:, 2]) ** 2))
+    assert m["sp"]["mae"] == pytest.approx(np.mean(np.abs(a[:, 4] - b[:, 4])))   # sp is channel 4 (featurePreprocessor.py:42-55)
+    assert m["average_mse"] == pytest.approx(np.mean([np.mean((a[:, v] - b[:, v]) ** 2) for v in (0, 1, 2, 3, 5)]))

@@ -2,7 +2,8 @@
 
 Drop-in modules (same names, signatures and ``state_dict`` layout as the reference files):
 ``graphBuilder``, ``model``, ``hybrid_model``, ``embed_utils``, ``dataset``,
-``train_hybrid_maml_v5``, ``adapt_hybrid_v5``, ``adaptive_scheduler``.  Every compute call goes
+``train_hybrid_maml_v5``, ``adapt_hybrid_v5``, ``adaptive_scheduler``, plus ``schedule`` (outer LR schedule, task
+sampler) and ``featurePreprocessor`` (de-normalisation, forecast metrics).  Every compute call goes
 through the C ABI of ``libwf_stgcn.so`` (include/wf_stgcn.h, sm_100a CUDA); there is no CPU or
 eager-PyTorch fallback -- a missing library or a CPU tensor raises.
 """
