@@ -40,6 +40,25 @@ METRIC = "maml_meta_steps_per_sec"
 UNIT = "meta-steps/s"
 
 
+_REAL_STDOUT = None
+
+
+def claim_stdout():
+    """Keep stdout for the ONE JSON line: everything else that writes to file descriptor 1 (NCCL's version banner, build
+    messages, library chatter) is sent to stderr from here on."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line):
+    out = _REAL_STDOUT if _REAL_STDOUT is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def workload_config(n_gpus):
     return {
         "workload": "config[1]: MAML meta-train step, 15 synthetic region tasks/GPU (441 nodes, k=8, ~600 windows, "
@@ -117,7 +136,7 @@ def run_reference(args, rank):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ----------------------------------------------------------------------------- clocks
@@ -429,7 +448,7 @@ def run_gpu(args, rank, local, world):
             "sec_per_window_pass": sec, "batched_port_sec_per_window_pass": sec_b}
     else:
         line["cpu_baseline"] = None
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def main():
@@ -440,6 +459,7 @@ def main():
     ap.add_argument("--impl", default="graft", choices=["graft", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    claim_stdout()
     args.warmup = max(args.warmup, 3) if args.impl == "graft" else args.warmup
     world_env = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
