@@ -132,3 +132,29 @@ def test_config4_large_graph_gcn_stack():
                                   @ gcn_w[2][0].t() + gcn_w[2][1]) @ gcn_w[3][0].t() + gcn_w[3][1])
     tail = torch.arange(n, dims.R, device="cuda")  # rows of the slices t >= 1 of window 0
     assert rel_err(outs["tf32x3"][tail], ident[tail]) <= 1e-4
+
+
+def test_config4_large_graph_full_hybrid_pass():
+    """configs[3] graph (14,641 nodes, k = 8) through the WHOLE hybrid pass (GCN -> LSTM -> head -> MSE -> BPTT), two
+    windows: 115 node tiles per time slice, 230 clusters per LSTM launch (more than one wave), 64-bit indexing.
+    Tensor-core persistent path against the exact-FP32 CUDA path."""
+    from weatherforecast_stgcn_maml_b200.engine import unflatten_trainable
+    from weatherforecast_stgcn_maml_b200.engine import HybridEngine
+
+    Bw = 2
+    dims, ei, base, sds, feats, starts, xo, to, theta, graphs, gcn_w = _setup(121, 121, 8, 1, Bw)
+    fd = feats.cuda()
+    out = {}
+    for prec in ("tf32x3", "fp32"):
+        eng = HybridEngine(dims, 1, Bw, "cuda", precision=prec)
+        loss, grads = eng.forward_backward(fd, 24, 0, xo, gcn_w, graphs, theta, eng.P, feat=fd, tgt_off=to, feat_ld=24)
+        eng.check()
+        out[prec] = (eng.pred.clone(), loss.clone(), grads.clone())
+        del eng
+        torch.cuda.empty_cache()
+    (p1, l1, g1), (p0, l0, g0) = out["tf32x3"], out["fp32"]
+    assert torch.isfinite(g1).all()
+    assert rel_err(p1, p0) <= 1e-4 and rel_err(l1, l0) <= 1e-4
+    a, r = unflatten_trainable(g1[0], dims), unflatten_trainable(g0[0], dims)
+    for kk in a:
+        assert rel_err(a[kk], r[kk]) <= 1e-3, (kk, rel_err(a[kk], r[kk]))
