@@ -31,7 +31,7 @@
 using namespace wftc;
 
 enum { EPI_STORE = 0, EPI_LSTM_FWD = 1, EPI_LSTM_BWD = 2 };
-enum { TILE_ROWS = 0, TILE_WGRAD = 1, TILE_STEP = 2, TILE_NODES = 3 };
+enum { TILE_ROWS = 0, TILE_WGRAD = 1, TILE_STEP = 2 };
 
 struct TcArgs {
   // ---- tiling
@@ -49,10 +49,6 @@ struct TcArgs {
   int a_k0, b_k0;       // first K coordinate of a segment in the A / B maps
   int b_rank;           // 3: (k, n, z)   4: (k, unit, gate, group)
   int b_gmul;           // 0: B shared by all groups, 1: per-group B
-  // ---- TILE_NODES: one tile = 128 nodes of one (window, step); output (and optionally A) in the TB4
-  // tile-blocked layout of wf_layout.cuh
-  int tpw;              // node tiles per time slice
-  int a_tb4;            // A is a TB4 buffer (read through a 4-D map: 256 floats, 2, channel group, block)
   // ---- CSR gather on A (GCN aggregation), TILE_ROWS only
   const float* a_raw; int lda;
   const int* rowptr; const int* col; const float* val; long long g_rowptr, g_csr;
@@ -85,14 +81,7 @@ wf_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   // ---- tile -> operand coordinates
   int a_row, a_z0 = 0, a_zstep = 0, b_z0 = g * a.b_gmul, b_zstep = 0;
   int win = 0, node0 = 0;  // TILE_STEP
-  int zt = 0, blk = 0;     // TILE_NODES
-  if (a.tile_mode == TILE_NODES) {
-    const int ztl = tile / a.tpw;
-    node0 = (tile - ztl * a.tpw) * 128;
-    zt = g * a.Bw * a.T + ztl;
-    blk = zt * a.tpw + (tile - ztl * a.tpw);
-    a_row = node0;
-  } else if (a.tile_mode == TILE_ROWS) {
+  if (a.tile_mode == TILE_ROWS) {
     a_row = g * a.a_group_rows + tile * 128;
   } else if (a.tile_mode == TILE_WGRAD) {
     a_row = tile * 128;           // gate rows of dG^T
@@ -134,12 +123,7 @@ wf_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           if (!mbar_wait(&empty[s], ph ^ 1)) { atomicExch(a.err, 1); seg = a.nseg; break; }
           uint8_t* st = smem + s * STAGE;
           mbar_expect_tx(&full[s], STAGE);
-          if (a.tile_mode == TILE_NODES) {
-            if (a.a_tb4) tma_load_4d(st, &tmA, &full[s], 0, 0, (a.a_k0 + kb * 32) >> 2, blk);
-            else tma_load_3d(st, &tmA, &full[s], a.a_k0 + kb * 32, node0, zt);
-          } else {
-            tma_load_3d(st, &tmA, &full[s], a.a_k0 + kb * 32, a_row, a_z0 + seg * a_zstep);
-          }
+          tma_load_3d(st, &tmA, &full[s], a.a_k0 + kb * 32, a_row, a_z0 + seg * a_zstep);
           if (a.b_rank == 4) {
             tma_load_4d(st + A_BYTES, &tmBhi, &full[s], a.b_k0 + kb * 32, blockIdx.x * (BN / 4), 0, g);
             tma_load_4d(st + A_BYTES + B_BYTES, &tmBlo, &full[s], a.b_k0 + kb * 32, blockIdx.x * (BN / 4), 0, g);
@@ -199,11 +183,10 @@ wf_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       if (!mbar_wait(&full[s], ph) || !mbar_wait(&empty[s], ph ^ 1)) { if (lane == 0) atomicExch(a.err, 3); ok = false; break; }
       uint32_t hi[32], lo[32];
       if (!gather) {
-        const uint8_t* arow = smem + s * STAGE + (a.a_tb4 ? row * 16 : row * 128);
+        const uint8_t* arow = smem + s * STAGE + row * 128;
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
-          // TB4 stage: [channel group c][row][4 floats]; otherwise a SWIZZLE_128B row of 32 floats
-          const float4 v = *reinterpret_cast<const float4*>(arow + (a.a_tb4 ? c * 2048 : ((c ^ (row & 7)) << 4)));
+          const float4 v = *reinterpret_cast<const float4*>(arow + ((c ^ (row & 7)) << 4));
           split_tf32(v.x, hi[4 * c + 0], lo[4 * c + 0]);
           split_tf32(v.y, hi[4 * c + 1], lo[4 * c + 1]);
           split_tf32(v.z, hi[4 * c + 2], lo[4 * c + 2]);
@@ -243,29 +226,7 @@ wf_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     if (ok && have_acc && !mbar_wait(&dfull, 0)) { if (lane == 0) atomicExch(a.err, 4); ok = false; }
     if (ok) {
       tc_fence_after();
-      if (EPI == EPI_STORE && a.tile_mode == TILE_NODES) {
-        // TB4 output: block `blk` = [ct_cols / 4 channel groups][128 rows][4 floats]; lanes are consecutive
-        // rows, so every float4 store instruction of a warp covers 512 contiguous bytes
-        float4* cblk = reinterpret_cast<float4*>(a.C) + ((long long)blk * (a.ct_cols >> 2) + (n0 >> 2)) * 128 + row;
-        const float* b1 = a.bias ? a.bias + g * a.bias_gstride + n0 : nullptr;
-        const float* b2 = a.bias2 ? a.bias2 + g * a.bias_gstride + n0 : nullptr;
-#pragma unroll 1
-        for (int c = 0; c < BN; c += 32) {
-          uint32_t v[32];
-          __syncwarp();
-          tmem_ld32(tlane + c, v);
-          tmem_wait_ld();
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            float4 o = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
-                                   __uint_as_float(v[j + 3]));
-            if (b1) { const float4 b = __ldg(reinterpret_cast<const float4*>(b1 + c + j)); o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w; }
-            if (b2) { const float4 b = __ldg(reinterpret_cast<const float4*>(b2 + c + j)); o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w; }
-            if (a.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
-            cblk[(long long)((c + j) >> 2) * 128] = o;
-          }
-        }
-      } else if (EPI == EPI_STORE) {
+      if (EPI == EPI_STORE) {
         const int grow = tile * 128 + row;
         const bool valid = grow < a.rows_g;
         float* crow = a.C + g * a.c_gstride + blockIdx.z * a.c_sstride + (long long)grow * a.ldc + n0;
@@ -602,41 +563,6 @@ int wf_launch_tc_rows(const float* A, long long a_rows_total, int lda, int a_gro
                    : launch_variant<128, EPI_STORE>(tmA, tmBhi, tmBlo, a, grid, st);
 }
 
-// ---- C[g] = A[g] W[g]^T (+bias + bias2) tiled per (window, step, 128 nodes), output in the TB4 layout.
-// A: row-major [G*Bw*T*Nn, K] (a_tb4 == 0) or a TB4 buffer with K channels (a_tb4 == 1).
-int wf_launch_tc_nodes(const float* A, int a_tb4, int K, const float* Whi, const float* Wlo, int ldb, long long b_gstride,
-                       int N, const float* bias, const float* bias2, long long bias_gstride, float* C, int T, int Nn, int Bw,
-                       int G, int* err, cudaStream_t st) {
-  WF_REQUIRE(K % 32 == 0 && K >= 32, "tc_nodes: K=%d must be a multiple of 32", K);
-  WF_REQUIRE(N % 128 == 0, "tc_nodes: N=%d must be a multiple of 128", N);
-  WF_REQUIRE(((uintptr_t)A | (uintptr_t)Whi | (uintptr_t)Wlo | (uintptr_t)C) % 16 == 0, "tc_nodes: pointers must be 16-byte aligned");
-  const int BN = (N % 256 == 0) ? 256 : 128;
-  const int tpw = wf_cdiv(Nn, 128);
-  const long long ZT = (long long)G * Bw * T;
-  CUtensorMap tmA, tmBhi, tmBlo;
-  int rc;
-  if (a_tb4) {
-    uint64_t dims[4] = {256, 2, (uint64_t)(K / 4), (uint64_t)(ZT * tpw)};
-    uint64_t str[3] = {256 * 4, 512 * 4, (uint64_t)K * 128 * 4};
-    uint32_t box[4] = {256, 2, 8, 1};
-    if ((rc = wf_encode_tensor_map(&tmA, A, 4, dims, str, box, 0))) return rc;
-  } else {
-    if ((rc = map3(&tmA, A, K, Nn, ZT, K, (uint64_t)Nn * K, 128))) return rc;
-  }
-  if ((rc = map3(&tmBhi, Whi, K, N, G, ldb, G > 1 ? b_gstride : (long long)N * ldb, BN))) return rc;
-  if ((rc = map3(&tmBlo, Wlo, K, N, G, ldb, G > 1 ? b_gstride : (long long)N * ldb, BN))) return rc;
-  TcArgs a;
-  tc_defaults(a);
-  a.tile_mode = TILE_NODES; a.tpw = tpw; a.a_tb4 = a_tb4; a.tiles_g = Bw * T * tpw; a.Bw = Bw; a.T = T; a.Nn = Nn;
-  a.nkb = K / 32;
-  a.C = C; a.ct_cols = N; a.bias = bias; a.bias2 = bias2; a.bias_gstride = bias_gstride; a.err = err;
-  dim3 grid(N / BN, a.tiles_g * G);
-  return BN == 256 ? launch_variant<256, EPI_STORE>(tmA, tmBhi, tmBlo, a, grid, st)
-                   : launch_variant<128, EPI_STORE>(tmA, tmBhi, tmBlo, a, grid, st);
-}
-
-// ---- weight gradient: dW[g][M, N] = sum over windows w and columns k of AT[g*Bw+w][m, a_k0+k] * BT[g*Bw+w][n, b_k0+k]
-// AT: [G*Bw][M][R], BT / BT_lo: [G*Bw][N][R];  klen columns are reduced per window.
 // Sum of split-K partials: out[g][i] = sum_s part[s][g][i], i < count (deterministic order).
 __global__ void wf_sum_splits_kernel(const float4* __restrict__ part, int splits, long long count4, long long part_sstride4,
                                      float4* __restrict__ out, long long out_gstride4) {
