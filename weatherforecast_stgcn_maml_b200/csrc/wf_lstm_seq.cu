@@ -373,6 +373,276 @@ wf_lstm_seq_fwd_kernel(const __grid_constant__ CUtensorMap tmWhi, const __grid_c
   cluster_sync_all();  // nobody exits while the peer may still address this CTA's shared memory
 }
 
+// ================================================================================= forward, 16 warps
+// Same algorithm and buffers as wf_lstm_seq_fwd_kernel, rearranged around the measured per-SM limits:
+// an SM writes at most ~62 GB/s to L2 whatever the path (LSU or bulk copy), so the 224 KB a CTA stores per step cost
+// 3.6 us and must not sit between the cell mathematics and the hand-over of h[t].  Per step:
+//   phase A  D[t] (TMEM) + input projection -> gates, c, h;  h[t] -> both CTAs' A operand;  h / h^T stores;  the
+//            activated gates go back into the accumulator columns they came from (tcgen05.st, 256 B/clk);
+//   hand-over, MMA[t+1] into the OTHER accumulator buffer;
+//   phase B  (under MMA[t+1] and the hand-over latency) gates TMEM -> global in place, cell state -> global.
+// 16 warps: 4 TMEM lane quarters x 4 unit groups of 16, chunks of 4 units (one TB4 float4 per gate), <= 128 registers.
+#ifdef WF_SEQ_TRACE
+__device__ long long wf_seq_trace_buf[32 * 16 * 24];  // [step][warp][point], CTA 0 (tools/trace_fwd.py)
+#define WF_TR(pt) do { if (blockIdx.x == 0 && lane == 0 && t < 32) wf_seq_trace_buf[(t * 16 + warp) * 24 + (pt)] = clock64(); } while (0)
+#else
+#define WF_TR(pt) do { } while (0)
+#endif
+__device__ __forceinline__ void st_async_v2(uint32_t caddr, uint32_t x, uint32_t y, uint32_t cbar) {
+  asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.b32 [%0], {%1, %2}, [%3];\n"
+               ::"r"(caddr), "r"(x), "r"(y), "r"(cbar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld4(uint32_t taddr, uint32_t* v) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];\n"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]) : "r"(taddr) : "memory");
+}
+// 2^(-x * scale), exponent clamped to 29: a product of four denominators 1 + 2^29 stays finite, and sigmoid(-20) = 2e-9
+// is below the arithmetic's resolution anyway.  .ftz forms: one MUFU each, no denormal pre-scaling.
+constexpr float kLog2e = 1.4426950408889634f;
+__device__ __forceinline__ float exp2_neg(float x, float scale) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;\n" : "=f"(y) : "f"(fminf(-x * scale, 29.0f)));
+  return y;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;\n" : "=f"(y) : "f"(x));
+  return y;
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(512, 1)
+wf_lstm_seq_fwd16_kernel(const __grid_constant__ CUtensorMap tmWhi, const __grid_constant__ CUtensorMap tmWlo, const SeqArgs a) {
+  constexpr int L = 128;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* b_hi = smem;            // [2 k-blocks][256 gate rows][128 B]
+  uint8_t* b_lo = smem + 65536;
+  uint8_t* a_hi = smem + 131072;   // [2 k-blocks][128 rows][128 B]
+  uint8_t* a_lo = smem + 163840;
+  __shared__ uint64_t wfull, a_ready, dfull, peer_done;
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t rank = cluster_rank(), peer = rank ^ 1u;
+  const int tile = blockIdx.x >> 1;
+  const int z = tile / a.tpw, nt = tile - z * a.tpw, node0 = nt * 128, g = z / a.Bw;
+  const int T = a.T;
+
+  if (tid == 0) {
+    // a_ready: 16 local warps + the expect_tx arrival; the peer's half of h[t] arrives as 32 KB of st.async transactions
+    mbar_init(&wfull, 1); mbar_init(&a_ready, 17); mbar_init(&dfull, 1); mbar_init(&peer_done, 1);
+    mbar_fence_init();
+    tma_prefetch_desc(&tmWhi); tma_prefetch_desc(&tmWlo);
+  }
+  if (warp == 0) tmem_alloc(&tmem_base_s, 512);  // two accumulator buffers of 256 columns
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();  // the peer's barriers exist before anybody arrives on them remotely
+  tc_fence_after();
+  const uint32_t tbase = tmem_base_s;
+
+  if (warp == 0 && lane == 0) {  // recurrent weights of this tile's task: resident for all T steps
+    if (T > 1) mbar_expect_tx(&a_ready, 32768);  // phase 0: the peer's half of h[0]
+    const int slab = a.slab0 + g * a.slab_g;
+    mbar_expect_tx(&wfull, 131072);
+    for (int kb = 0; kb < 2; ++kb) {
+      tma_load_4d(b_hi + kb * 32768, &tmWhi, &wfull, kb * 64, 64 * (int)rank, 0, slab);
+      tma_load_4d(b_lo + kb * 32768, &tmWlo, &wfull, kb * 64, 64 * (int)rank, 0, slab);
+    }
+  }
+  const int q = warp & 3, ug = warp >> 2;
+  const int r = q * 32 + lane;            // tile row == TMEM lane
+  const int ub = ug * 16;                 // first of this thread's 16 units inside the CTA's 64
+  const int u0 = 64 * (int)rank + ub;     // ... as a global hidden-unit index
+  const int node = node0 + r;
+  const bool valid = node < a.Nn;
+  const uint32_t tlane = tbase + ((uint32_t)(q * 32) << 16) + (uint32_t)ub;
+  const long long R = (long long)T * a.Nn;
+  float4* const xg4 = reinterpret_cast<float4*>(a.XG);
+  float4* const c4 = reinterpret_cast<float4*>(a.Cst);
+  const uint32_t pd_remote = mapa_u32(smem_u32(&peer_done), peer);
+  const uint32_t ar_remote = mapa_u32(smem_u32(&a_ready), peer);
+  bool ok = true;
+
+  float cst[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) cst[j] = 0.f;
+  float4 xq[2][4];  // two chunks of 4 units in flight: one float4 per gate
+  auto xg_index = [&](int t, int c, int gate) -> long long {
+    const long long blk = ((long long)z * T + t) * a.tpw + nt;
+    return (blk * 128 + gate * 32 + (u0 >> 2) + c) * 128 + r;
+  };
+  auto load_chunk = [&](int t, int c, float4* dst) {
+#pragma unroll
+    for (int gate = 0; gate < 4; ++gate) dst[gate] = xg4[xg_index(t, c, gate)];
+  };
+  load_chunk(0, 0, xq[0]);
+  load_chunk(0, 1, xq[1]);
+
+  for (int t = 0; t < T; ++t) {
+    const uint32_t dcol = tlane + (uint32_t)(t & 1) * 256u;  // this step's accumulator buffer (and gate staging)
+    if (t > 0) {
+      if (ok && !mbar_wait(&dfull, (t - 1) & 1)) { ok = false; if (lane == 0) atomicExch(a.err, 13); }
+      tc_fence_after();
+      if (warp == 0 && lane == 0) arrive_cluster_relaxed(pd_remote);  // my MMA no longer reads my A buffer
+    }
+    WF_TR(0);
+    const long long blk = ((long long)z * T + t) * a.tpw + nt;
+    const long long hrow = ((long long)z * R + (long long)t * a.Nn + node) * L + u0;
+    const long long tcol = (long long)t * a.Np + node;
+    // ------------------------------------------------------------ phase A: cell mathematics, h[t] out
+    uint32_t acc[4][4];
+    auto issue_acc = [&](int c) {
+      __syncwarp();
+#pragma unroll
+      for (int gate = 0; gate < 4; ++gate) tmem_ld4(dcol + gate * 64 + 4 * c, acc[gate]);
+    };
+    if (t > 0) issue_acc(0);
+    else {
+#pragma unroll
+      for (int gate = 0; gate < 4; ++gate)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[gate][j] = 0u;
+    }
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      if (t > 0) tmem_wait_ld();
+      WF_TR(8 + 4 * c);
+      const float4* x = xq[c & 1];
+      const float xi[4] = {x[0].x, x[0].y, x[0].z, x[0].w}, xf[4] = {x[1].x, x[1].y, x[1].z, x[1].w};
+      const float xgv[4] = {x[2].x, x[2].y, x[2].z, x[2].w}, xo[4] = {x[3].x, x[3].y, x[3].z, x[3].w};
+      uint32_t gt[4][4];
+      float hh[4], go[4], dc[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        // i, f, o = 1 / (1 + e^-p), g = 2 / (1 + e^-2p) - 1 with ONE reciprocal for the four denominators
+        const float di = 1.0f + exp2_neg(xi[j] + __uint_as_float(acc[0][j]), kLog2e);
+        const float df = 1.0f + exp2_neg(xf[j] + __uint_as_float(acc[1][j]), kLog2e);
+        const float dg = 1.0f + exp2_neg(xgv[j] + __uint_as_float(acc[2][j]), 2.0f * kLog2e);
+        const float dq = 1.0f + exp2_neg(xo[j] + __uint_as_float(acc[3][j]), kLog2e);
+        const float p1 = di * df, p2 = dg * dq, rr = rcp_approx(p1 * p2);
+        const float r1 = rr * p2, r2 = rr * p1;  // 1 / (di df), 1 / (dg dq)
+        const float gi = r1 * df, gf = r1 * di, gg = fmaf(2.0f, r2 * dq, -1.0f);
+        go[j] = r2 * dg;
+        const float cc = fmaf(gf, cst[4 * c + j], gi * gg);
+        cst[4 * c + j] = cc;
+        dc[j] = 1.0f + exp2_neg(cc, 2.0f * kLog2e);
+        gt[0][j] = __float_as_uint(gi); gt[1][j] = __float_as_uint(gf);
+        gt[2][j] = __float_as_uint(gg); gt[3][j] = __float_as_uint(go[j]);
+      }
+      {
+        // tanh(c) of the four units: one reciprocal again
+        const float p1 = dc[0] * dc[1], p2 = dc[2] * dc[3], rr = rcp_approx(p1 * p2);
+        const float r1 = rr * p2, r2 = rr * p1;
+        hh[0] = go[0] * fmaf(2.0f, r1 * dc[1], -1.0f);
+        hh[1] = go[1] * fmaf(2.0f, r1 * dc[0], -1.0f);
+        hh[2] = go[2] * fmaf(2.0f, r2 * dc[3], -1.0f);
+        hh[3] = go[3] * fmaf(2.0f, r2 * dc[2], -1.0f);
+      }
+      __syncwarp();
+#pragma unroll
+      for (int gate = 0; gate < 4; ++gate) tmem_st4(dcol + gate * 64 + 4 * c, gt[gate]);
+      if (t > 0 && c < 3) issue_acc(c + 1);  // in flight under this chunk's stores
+      WF_TR(9 + 4 * c);
+      if (c < 2) load_chunk(t, c + 2, xq[c & 1]);  // chunks 2, 3 of this step
+      if (t + 1 < T) {
+        // h[t] as fp16 hi/lo -> the A operand of step t+1 in both CTAs (k-block `rank`, 16-byte chunk (ub + 4c) / 8)
+        float ra, rb, rc, rd, d0, d1;
+        const uint32_t h0 = pack_f16(hh[0], hh[1], ra, rb), h1 = pack_f16(hh[2], hh[3], rc, rd);
+        const uint32_t l0 = pack_f16(ra, rb, d0, d1), l1 = pack_f16(rc, rd, d0, d1);
+        const uint32_t off = rank * 16384u + (uint32_t)(r >> 3) * 1024u + (uint32_t)(r & 7) * 128u +
+                             ((uint32_t)(((ub >> 3) + (c >> 1)) ^ (r & 7)) << 4) + 8u * (uint32_t)(c & 1);
+        if (c == 0 && t > 0) {  // the peer's MMA of this step must be done with the peer's A buffer (no data is
+          // acquired here, so a CTA-scope wait: the cluster-scope form costs a CCTL.IVALL per warp and step)
+          if (ok && !mbar_wait(&peer_done, (t - 1) & 1)) { ok = false; if (lane == 0) atomicExch(a.err, 14); }
+        }
+        *reinterpret_cast<uint2*>(a_hi + off) = make_uint2(h0, h1);
+        *reinterpret_cast<uint2*>(a_lo + off) = make_uint2(l0, l1);
+        st_async_v2(mapa_u32(smem_u32(a_hi + off), peer), h0, h1, ar_remote);
+        st_async_v2(mapa_u32(smem_u32(a_lo + off), peer), l0, l1, ar_remote);
+      }
+      WF_TR(10 + 4 * c);
+      if (a.h_tb4) reinterpret_cast<float4*>(a.H)[(blk * 32 + (u0 >> 2) + c) * 128 + r] = make_float4(hh[0], hh[1], hh[2], hh[3]);
+      if (valid) {
+        if (!a.h_tb4) *reinterpret_cast<float4*>(a.H + hrow + 4 * c) = make_float4(hh[0], hh[1], hh[2], hh[3]);
+        if (a.HT != nullptr) {
+          __nv_bfloat16* ht = a.HT + ((long long)z * L + u0 + 4 * c) * a.RT + tcol;
+          __nv_bfloat16* htl = a.HT_lo + ((long long)z * L + u0 + 4 * c) * a.RT + tcol;
+#pragma unroll
+          for (int j = 0; j < 4; j += 2) {
+            float ra, rb, d0, d1;
+            const uint32_t uh = pack_bf16(hh[j], hh[j + 1], ra, rb), ul = pack_bf16(ra, rb, d0, d1);
+            reinterpret_cast<uint16_t*>(ht)[(long long)j * a.RT] = (uint16_t)uh;
+            reinterpret_cast<uint16_t*>(ht)[(long long)(j + 1) * a.RT] = (uint16_t)(uh >> 16);
+            reinterpret_cast<uint16_t*>(htl)[(long long)j * a.RT] = (uint16_t)ul;
+            reinterpret_cast<uint16_t*>(htl)[(long long)(j + 1) * a.RT] = (uint16_t)(ul >> 16);
+          }
+        }
+      }
+    }
+    tmem_wait_st();  // the staged gates are in TMEM before phase B reads them back
+    WF_TR(1);
+    if (t + 1 < T) {
+      // Hand h[t] over: the peer's copy completes on the peer's barrier by itself (st.async); locally a shared-memory
+      // proxy fence and a CTA-scope arrive -- no cluster-scope release on the critical path.
+      fence_proxy_async_cta();  // my generic-proxy operand writes -> visible to the tensor core (async proxy)
+      tc_fence_before();        // my TMEM accesses of the other buffer (phase B of step t-1) precede MMA[t+1]
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&a_ready);
+      load_chunk(t + 1, 0, xq[0]);  // ahead of phase B's stores: the memory pipeline is in order
+      load_chunk(t + 1, 1, xq[1]);
+      WF_TR(2);
+      if (warp == 0) {  // MMA issue: D[128 x 256] = h[t] W_hh^T for this CTA's 64 units x 4 gates, other buffer
+        if (ok && t == 0 && !mbar_wait(&wfull, 0)) { ok = false; if (lane == 0) atomicExch(a.err, 11); }
+        // the peer's half arrived as st.async transactions counted by this barrier: a CTA-scope acquire is enough
+        if (ok && !mbar_wait(&a_ready, t & 1)) { ok = false; if (lane == 0) atomicExch(a.err, 12); }
+        WF_TR(3);
+        if (lane == 0 && t + 2 < T) mbar_expect_tx(&a_ready, 32768);  // next phase: the peer's half of h[t+1]
+        fence_proxy_async_cta();
+        tc_fence_after();
+        if (lane == 0 && ok) {
+          const uint32_t idesc = idesc_16(256, 0);
+          const uint32_t dnext = tbase + (uint32_t)((t + 1) & 1) * 256u;
+          uint32_t accf = 0;
+#pragma unroll
+          for (int p = 0; p < 3; ++p) {  // h_hi W_hi, h_lo W_hi, h_hi W_lo
+            const uint32_t as = smem_u32(p == 1 ? a_lo : a_hi), bs = smem_u32(p == 2 ? b_lo : b_hi);
+#pragma unroll
+            for (int kb = 0; kb < 2; ++kb)
+#pragma unroll
+              for (int k16 = 0; k16 < 4; ++k16) {
+                umma_ss_16(dnext, umma_desc_k_sw128(as + kb * 16384 + k16 * 32), umma_desc_k_sw128(bs + kb * 32768 + k16 * 32),
+                           idesc, accf);
+                accf = 1;
+              }
+          }
+          umma_commit(&dfull);
+        }
+        __syncwarp();
+        WF_TR(4);
+      }
+    }
+    // ------------------------------------------------------------ phase B: gates (TMEM) and cell state -> global
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      uint32_t gt[4][4];
+      __syncwarp();
+#pragma unroll
+      for (int gate = 0; gate < 4; ++gate) tmem_ld4(dcol + gate * 64 + 4 * c, gt[gate]);
+      tmem_wait_ld();
+#pragma unroll
+      for (int gate = 0; gate < 4; ++gate)
+        xg4[xg_index(t, c, gate)] = make_float4(__uint_as_float(gt[gate][0]), __uint_as_float(gt[gate][1]),
+                                                __uint_as_float(gt[gate][2]), __uint_as_float(gt[gate][3]));
+      c4[(blk * 32 + (u0 >> 2) + c) * 128 + r] = make_float4(cst[4 * c], cst[4 * c + 1], cst[4 * c + 2], cst[4 * c + 3]);
+    }
+    WF_TR(5);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tbase, 512);
+  cluster_sync_all();  // nobody exits while the peer may still address this CTA's shared memory
+}
+
 // ================================================================================= backward
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(SEQ_THREADS, 1)
 wf_lstm_seq_bwd_kernel(const __grid_constant__ CUtensorMap tmWhi, const __grid_constant__ CUtensorMap tmWlo, const SeqArgs a) {
@@ -744,6 +1014,12 @@ extern "C" int wf_lstm_fwd_seq(const float* x, const float* params, const void* 
     a.HT = hT_hi ? (__nv_bfloat16*)hT_hi + l * tsz : nullptr; a.HT_lo = hT_hi ? (__nv_bfloat16*)hT_lo + l * tsz : nullptr;
     a.T = T; a.Nn = N; a.Bw = Bw; a.tpw = tpw; a.Np = Np; a.RT = RT;
     a.slab0 = l; a.slab_g = layers; a.err = err;
+    static const bool fwd16 = getenv("WF_SEQ_FWD16") != nullptr;
+    if (fwd16) {
+      static bool c16 = false;
+      if (!c16) { int rc16 = seq_configure(wf_lstm_seq_fwd16_kernel); if (rc16) return rc16; c16 = true; }
+      wf_lstm_seq_fwd16_kernel<<<dim3((unsigned)(2 * Z * tpw)), 512, SEQ_SMEM, st>>>(tmhi, tmlo, a);
+    } else
     wf_lstm_seq_fwd_kernel<<<dim3((unsigned)(2 * Z * tpw)), SEQ_THREADS, SEQ_SMEM, st>>>(tmhi, tmlo, a);
     WF_CHECK_LAUNCH("lstm_seq_fwd");
   }
@@ -861,3 +1137,9 @@ extern "C" int wf_lstm_seq_recur_bwd(float* gates_l, const float* c_l, float* dg
   WF_CHECK_LAUNCH("lstm_seq_recur_bwd");
   return WF_OK;
 }
+
+#ifdef WF_SEQ_TRACE
+extern "C" int wf_seq_trace_read(long long* host) {
+  return (int)cudaMemcpyFromSymbol(host, wf_seq_trace_buf, sizeof(long long) * 32 * 16 * 24);
+}
+#endif
