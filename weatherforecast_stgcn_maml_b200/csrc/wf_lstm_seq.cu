@@ -90,6 +90,13 @@ __device__ __forceinline__ void arrive_cluster_relaxed(uint32_t cbar) {
   asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];\n" ::"r"(cbar) : "memory");
 }
 __device__ __forceinline__ void fence_proxy_async_cta() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
+// non-blocking phase test (CTA-scope acquire)
+__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}\n"
+               : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  return ok != 0;
+}
 // bounded wait with cluster-scope acquire (the barrier receives arrivals from the peer CTA)
 __device__ __forceinline__ bool mbar_wait_cl(uint64_t* bar, uint32_t parity) {
   for (uint32_t spin = 0; spin < (1u << 18); ++spin) {
@@ -419,7 +426,7 @@ wf_lstm_seq_fwd16_kernel(const __grid_constant__ CUtensorMap tmWhi, const __grid
   uint8_t* b_lo = smem + 65536;
   uint8_t* a_hi = smem + 131072;   // [2 k-blocks][128 rows][128 B]
   uint8_t* a_lo = smem + 163840;
-  __shared__ uint64_t wfull, a_ready, dfull, peer_done;
+  __shared__ uint64_t wfull, a_ready[4], dfull, peer_done;
   __shared__ uint32_t tmem_base_s;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t rank = cluster_rank(), peer = rank ^ 1u;
@@ -428,8 +435,10 @@ wf_lstm_seq_fwd16_kernel(const __grid_constant__ CUtensorMap tmWhi, const __grid
   const int T = a.T;
 
   if (tid == 0) {
-    // a_ready: 16 local warps + the expect_tx arrival; the peer's half of h[t] arrives as 32 KB of st.async transactions
-    mbar_init(&wfull, 1); mbar_init(&a_ready, 17); mbar_init(&dfull, 1); mbar_init(&peer_done, 1);
+    // a_ready[c], one per chunk of 16 units (= one K step of 16 per k-block): 16 local warps + the expect_tx arrival;
+    // the peer's 16 units of h[t] arrive as 8 KB of st.async transactions
+    mbar_init(&wfull, 1); mbar_init(&dfull, 1); mbar_init(&peer_done, 1);
+    for (int c = 0; c < 4; ++c) mbar_init(&a_ready[c], 17);
     mbar_fence_init();
     tma_prefetch_desc(&tmWhi); tma_prefetch_desc(&tmWlo);
   }
@@ -441,7 +450,8 @@ wf_lstm_seq_fwd16_kernel(const __grid_constant__ CUtensorMap tmWhi, const __grid
   const uint32_t tbase = tmem_base_s;
 
   if (warp == 0 && lane == 0) {  // recurrent weights of this tile's task: resident for all T steps
-    if (T > 1) mbar_expect_tx(&a_ready, 32768);  // phase 0: the peer's half of h[0]
+    if (T > 1)
+      for (int c = 0; c < 4; ++c) mbar_expect_tx(&a_ready[c], 8192);  // phase 0: the peer's half of h[0]
     const int slab = a.slab0 + g * a.slab_g;
     mbar_expect_tx(&wfull, 131072);
     for (int kb = 0; kb < 2; ++kb) {
@@ -451,8 +461,8 @@ wf_lstm_seq_fwd16_kernel(const __grid_constant__ CUtensorMap tmWhi, const __grid
   }
   const int q = warp & 3, ug = warp >> 2;
   const int r = q * 32 + lane;            // tile row == TMEM lane
-  const int ub = ug * 16;                 // first of this thread's 16 units inside the CTA's 64
-  const int u0 = 64 * (int)rank + ub;     // ... as a global hidden-unit index
+  const int ub = ug * 4;                  // chunk c: units 16 c + ub .. + 4 of the CTA's 64, so that ALL warps finish
+  const int u0 = 64 * (int)rank + ub;     // K step c of h[t] together and MMA[t+1] can start behind chunk 0
   const int node = node0 + r;
   const bool valid = node < a.Nn;
   const uint32_t tlane = tbase + ((uint32_t)(q * 32) << 16) + (uint32_t)ub;
@@ -460,7 +470,7 @@ wf_lstm_seq_fwd16_kernel(const __grid_constant__ CUtensorMap tmWhi, const __grid
   float4* const xg4 = reinterpret_cast<float4*>(a.XG);
   float4* const c4 = reinterpret_cast<float4*>(a.Cst);
   const uint32_t pd_remote = mapa_u32(smem_u32(&peer_done), peer);
-  const uint32_t ar_remote = mapa_u32(smem_u32(&a_ready), peer);
+  const uint32_t ar_remote = mapa_u32(smem_u32(&a_ready[0]), peer);
   bool ok = true;
 
   float cst[16];
@@ -469,7 +479,7 @@ wf_lstm_seq_fwd16_kernel(const __grid_constant__ CUtensorMap tmWhi, const __grid
   float4 xq[2][4];  // two chunks of 4 units in flight: one float4 per gate
   auto xg_index = [&](int t, int c, int gate) -> long long {
     const long long blk = ((long long)z * T + t) * a.tpw + nt;
-    return (blk * 128 + gate * 32 + (u0 >> 2) + c) * 128 + r;
+    return (blk * 128 + gate * 32 + (u0 >> 2) + 4 * c) * 128 + r;
   };
   auto load_chunk = [&](int t, int c, float4* dst) {
 #pragma unroll
@@ -477,6 +487,40 @@ wf_lstm_seq_fwd16_kernel(const __grid_constant__ CUtensorMap tmWhi, const __grid
   };
   load_chunk(0, 0, xq[0]);
   load_chunk(0, 1, xq[1]);
+
+  // MMA[t+1] = h[t] W_hh^T, issued by warp 0 one K step of 16 units (x 2 k-blocks x 3 hi/lo products) at a time, as
+  // soon as that slice of h[t] is complete in BOTH CTAs: only the last K step is left when phase A ends.
+  int kdone = 0;  // K steps of the pending MMA already issued (warp 0)
+  auto mma_steps = [&](int t, int climit, bool block) {
+    while (kdone < climit) {
+      if (kdone == 0 && t == 0 && ok && !mbar_wait(&wfull, 0)) { ok = false; if (lane == 0) atomicExch(a.err, 11); }
+      if (block) {
+        // the peer's slice arrived as st.async transactions counted by this barrier: a CTA-scope acquire is enough
+        if (ok && !mbar_wait(&a_ready[kdone], t & 1)) { ok = false; if (lane == 0) atomicExch(a.err, 12); }
+      } else if (!__all_sync(0xffffffffu, mbar_test(&a_ready[kdone], t & 1))) {
+        return;
+      }
+      if (lane == 0 && t + 2 < T) mbar_expect_tx(&a_ready[kdone], 8192);  // next phase: the peer's slice of h[t+1]
+      fence_proxy_async_cta();
+      tc_fence_after();
+      if (lane == 0 && ok) {
+        const uint32_t idesc = idesc_16(256, 0);
+        const uint32_t dnext = tbase + (uint32_t)((t + 1) & 1) * 256u;
+#pragma unroll
+        for (int p = 0; p < 3; ++p) {  // h_hi W_hi, h_lo W_hi, h_hi W_lo
+          const uint32_t as = smem_u32(p == 1 ? a_lo : a_hi), bs = smem_u32(p == 2 ? b_lo : b_hi);
+#pragma unroll
+          for (int kb = 0; kb < 2; ++kb)
+            umma_ss_16(dnext, umma_desc_k_sw128(as + kb * 16384 + kdone * 32), umma_desc_k_sw128(bs + kb * 32768 + kdone * 32),
+                       idesc, (kdone | p | kb) != 0 ? 1u : 0u);
+        }
+        if (kdone == 3) umma_commit(&dfull);
+      }
+      __syncwarp();
+      ++kdone;
+    }
+    if (kdone == 4 && block) kdone = 0;
+  };
 
   for (int t = 0; t < T; ++t) {
     const uint32_t dcol = tlane + (uint32_t)(t & 1) * 256u;  // this step's accumulator buffer (and gate staging)
@@ -494,7 +538,7 @@ wf_lstm_seq_fwd16_kernel(const __grid_constant__ CUtensorMap tmWhi, const __grid
     auto issue_acc = [&](int c) {
       __syncwarp();
 #pragma unroll
-      for (int gate = 0; gate < 4; ++gate) tmem_ld4(dcol + gate * 64 + 4 * c, acc[gate]);
+      for (int gate = 0; gate < 4; ++gate) tmem_ld4(dcol + gate * 64 + 16 * c, acc[gate]);
     };
     if (t > 0) issue_acc(0);
     else {
@@ -540,33 +584,40 @@ wf_lstm_seq_fwd16_kernel(const __grid_constant__ CUtensorMap tmWhi, const __grid
       }
       __syncwarp();
 #pragma unroll
-      for (int gate = 0; gate < 4; ++gate) tmem_st4(dcol + gate * 64 + 4 * c, gt[gate]);
+      for (int gate = 0; gate < 4; ++gate) tmem_st4(dcol + gate * 64 + 16 * c, gt[gate]);
       if (t > 0 && c < 3) issue_acc(c + 1);  // in flight under this chunk's stores
       WF_TR(9 + 4 * c);
       if (c < 2) load_chunk(t, c + 2, xq[c & 1]);  // chunks 2, 3 of this step
       if (t + 1 < T) {
-        // h[t] as fp16 hi/lo -> the A operand of step t+1 in both CTAs (k-block `rank`, 16-byte chunk (ub + 4c) / 8)
+        // h[t] as fp16 hi/lo -> the A operand of step t+1 in both CTAs (k-block `rank`, 16-byte chunk (16c + ub) / 8)
         float ra, rb, rc, rd, d0, d1;
         const uint32_t h0 = pack_f16(hh[0], hh[1], ra, rb), h1 = pack_f16(hh[2], hh[3], rc, rd);
         const uint32_t l0 = pack_f16(ra, rb, d0, d1), l1 = pack_f16(rc, rd, d0, d1);
         const uint32_t off = rank * 16384u + (uint32_t)(r >> 3) * 1024u + (uint32_t)(r & 7) * 128u +
-                             ((uint32_t)(((ub >> 3) + (c >> 1)) ^ (r & 7)) << 4) + 8u * (uint32_t)(c & 1);
+                             ((uint32_t)((2 * c + (ug >> 1)) ^ (r & 7)) << 4) + 8u * (uint32_t)(ug & 1);
         if (c == 0 && t > 0) {  // the peer's MMA of this step must be done with the peer's A buffer (no data is
           // acquired here, so a CTA-scope wait: the cluster-scope form costs a CCTL.IVALL per warp and step)
           if (ok && !mbar_wait(&peer_done, (t - 1) & 1)) { ok = false; if (lane == 0) atomicExch(a.err, 14); }
         }
         *reinterpret_cast<uint2*>(a_hi + off) = make_uint2(h0, h1);
         *reinterpret_cast<uint2*>(a_lo + off) = make_uint2(l0, l1);
-        st_async_v2(mapa_u32(smem_u32(a_hi + off), peer), h0, h1, ar_remote);
-        st_async_v2(mapa_u32(smem_u32(a_lo + off), peer), l0, l1, ar_remote);
+        st_async_v2(mapa_u32(smem_u32(a_hi + off), peer), h0, h1, ar_remote + 8u * c);
+        st_async_v2(mapa_u32(smem_u32(a_lo + off), peer), l0, l1, ar_remote + 8u * c);
+        // K step c of h[t] is complete in this warp: my generic-proxy operand writes -> visible to the tensor core
+        // (async proxy), my TMEM reads of the other accumulator buffer (phase B of step t-1) precede MMA[t+1]
+        fence_proxy_async_cta();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&a_ready[c]);
+        if (warp == 0 && c > 0) mma_steps(t, c, false);  // K steps whose operands have already arrived everywhere
       }
       WF_TR(10 + 4 * c);
-      if (a.h_tb4) reinterpret_cast<float4*>(a.H)[(blk * 32 + (u0 >> 2) + c) * 128 + r] = make_float4(hh[0], hh[1], hh[2], hh[3]);
+      if (a.h_tb4) reinterpret_cast<float4*>(a.H)[(blk * 32 + (u0 >> 2) + 4 * c) * 128 + r] = make_float4(hh[0], hh[1], hh[2], hh[3]);
       if (valid) {
-        if (!a.h_tb4) *reinterpret_cast<float4*>(a.H + hrow + 4 * c) = make_float4(hh[0], hh[1], hh[2], hh[3]);
+        if (!a.h_tb4) *reinterpret_cast<float4*>(a.H + hrow + 16 * c) = make_float4(hh[0], hh[1], hh[2], hh[3]);
         if (a.HT != nullptr) {
-          __nv_bfloat16* ht = a.HT + ((long long)z * L + u0 + 4 * c) * a.RT + tcol;
-          __nv_bfloat16* htl = a.HT_lo + ((long long)z * L + u0 + 4 * c) * a.RT + tcol;
+          __nv_bfloat16* ht = a.HT + ((long long)z * L + u0 + 16 * c) * a.RT + tcol;
+          __nv_bfloat16* htl = a.HT_lo + ((long long)z * L + u0 + 16 * c) * a.RT + tcol;
 #pragma unroll
           for (int j = 0; j < 4; j += 2) {
             float ra, rb, d0, d1;
@@ -582,44 +633,11 @@ wf_lstm_seq_fwd16_kernel(const __grid_constant__ CUtensorMap tmWhi, const __grid
     tmem_wait_st();  // the staged gates are in TMEM before phase B reads them back
     WF_TR(1);
     if (t + 1 < T) {
-      // Hand h[t] over: the peer's copy completes on the peer's barrier by itself (st.async); locally a shared-memory
-      // proxy fence and a CTA-scope arrive -- no cluster-scope release on the critical path.
-      fence_proxy_async_cta();  // my generic-proxy operand writes -> visible to the tensor core (async proxy)
-      tc_fence_before();        // my TMEM accesses of the other buffer (phase B of step t-1) precede MMA[t+1]
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&a_ready);
       load_chunk(t + 1, 0, xq[0]);  // ahead of phase B's stores: the memory pipeline is in order
       load_chunk(t + 1, 1, xq[1]);
       WF_TR(2);
-      if (warp == 0) {  // MMA issue: D[128 x 256] = h[t] W_hh^T for this CTA's 64 units x 4 gates, other buffer
-        if (ok && t == 0 && !mbar_wait(&wfull, 0)) { ok = false; if (lane == 0) atomicExch(a.err, 11); }
-        // the peer's half arrived as st.async transactions counted by this barrier: a CTA-scope acquire is enough
-        if (ok && !mbar_wait(&a_ready, t & 1)) { ok = false; if (lane == 0) atomicExch(a.err, 12); }
-        WF_TR(3);
-        if (lane == 0 && t + 2 < T) mbar_expect_tx(&a_ready, 32768);  // next phase: the peer's half of h[t+1]
-        fence_proxy_async_cta();
-        tc_fence_after();
-        if (lane == 0 && ok) {
-          const uint32_t idesc = idesc_16(256, 0);
-          const uint32_t dnext = tbase + (uint32_t)((t + 1) & 1) * 256u;
-          uint32_t accf = 0;
-#pragma unroll
-          for (int p = 0; p < 3; ++p) {  // h_hi W_hi, h_lo W_hi, h_hi W_lo
-            const uint32_t as = smem_u32(p == 1 ? a_lo : a_hi), bs = smem_u32(p == 2 ? b_lo : b_hi);
-#pragma unroll
-            for (int kb = 0; kb < 2; ++kb)
-#pragma unroll
-              for (int k16 = 0; k16 < 4; ++k16) {
-                umma_ss_16(dnext, umma_desc_k_sw128(as + kb * 16384 + k16 * 32), umma_desc_k_sw128(bs + kb * 32768 + k16 * 32),
-                           idesc, accf);
-                accf = 1;
-              }
-          }
-          umma_commit(&dfull);
-        }
-        __syncwarp();
-        WF_TR(4);
-      }
+      if (warp == 0) mma_steps(t, 4, true);  // the remaining K steps of MMA[t+1], then the commit
+      WF_TR(4);
     }
     // ------------------------------------------------------------ phase B: gates (TMEM) and cell state -> global
 #pragma unroll
@@ -627,13 +645,13 @@ wf_lstm_seq_fwd16_kernel(const __grid_constant__ CUtensorMap tmWhi, const __grid
       uint32_t gt[4][4];
       __syncwarp();
 #pragma unroll
-      for (int gate = 0; gate < 4; ++gate) tmem_ld4(dcol + gate * 64 + 4 * c, gt[gate]);
+      for (int gate = 0; gate < 4; ++gate) tmem_ld4(dcol + gate * 64 + 16 * c, gt[gate]);
       tmem_wait_ld();
 #pragma unroll
       for (int gate = 0; gate < 4; ++gate)
         xg4[xg_index(t, c, gate)] = make_float4(__uint_as_float(gt[gate][0]), __uint_as_float(gt[gate][1]),
                                                 __uint_as_float(gt[gate][2]), __uint_as_float(gt[gate][3]));
-      c4[(blk * 32 + (u0 >> 2) + c) * 128 + r] = make_float4(cst[4 * c], cst[4 * c + 1], cst[4 * c + 2], cst[4 * c + 3]);
+      c4[(blk * 32 + (u0 >> 2) + 4 * c) * 128 + r] = make_float4(cst[4 * c], cst[4 * c + 1], cst[4 * c + 2], cst[4 * c + 3]);
     }
     WF_TR(5);
   }
