@@ -121,6 +121,10 @@ __device__ __forceinline__ void umma_ts_16(uint32_t d_tmem, uint32_t a_tmem, uin
                "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}\n"
                ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
 }
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t* v) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};\n"
+               ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]) : "memory");
+}
 __device__ __forceinline__ void tmem_st4(uint32_t taddr, const uint32_t* v) {
   asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};\n"
                ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]) : "memory");
@@ -753,34 +757,37 @@ wf_lstm_seq_bwd_kernel(const __grid_constant__ CUtensorMap tmWhi, const __grid_c
     };
     load_chunk(T - 1, 0, ld[0]);
 
+    // MMA of step s (warp 0): partial dh[128 x 128] = dG[t+1][:, my gate rows] W_hh[my gate rows, :]; also arms the barrier
+    // on which the peer's partial dh for my units will arrive as st.async transactions (phase (s - 1) / 2 of x_ready[s & 1])
+    auto issue_mma = [&](int s) {
+      if (lane == 0) mbar_expect_tx(&x_ready[s & 1], 32768);
+      if (ok && s == 1 && !mbar_wait(&wfull, 0)) { ok = false; if (lane == 0) atomicExch(a.err, 21); }
+      if (ok && !mbar_wait(&a_ready, (s - 1) & 1)) { ok = false; if (lane == 0) atomicExch(a.err, 22); }
+      tc_fence_after();
+      if (lane == 0 && ok) {
+        const uint32_t idesc = idesc_16(128, 1);
+        uint32_t accf = 0;
+#pragma unroll
+        for (int p = 0; p < 3; ++p) {  // dG_hi W_hi, dG_lo W_hi, dG_hi W_lo
+          const uint32_t ac = tbase + (p == 1 ? A_LO : A_HI), bs = smem_u32(p == 2 ? b_lo : b_hi);
+#pragma unroll
+          for (int kb = 0; kb < 4; ++kb)
+#pragma unroll
+            for (int k16 = 0; k16 < 4; ++k16) {
+              umma_ts_16(tbase, ac + kb * 32 + k16 * 8, umma_desc_k_sw128(bs + kb * 16384 + k16 * 32), idesc, accf);
+              accf = 1;
+            }
+        }
+        umma_commit(&dfull);
+      }
+      __syncwarp();
+    };
+
     for (int s = 0; s < T; ++s) {
       const int t = T - 1 - s;
       const int xb = s & 1;
       if (s > 0) {
         // the peer's partial dh for my units arrives as st.async transactions on x_ready[xb] (phase (s - 1) / 2)
-        if (warp == 0 && lane == 0) mbar_expect_tx(&x_ready[xb], 32768);
-        if (warp == 0) {  // MMA issue: partial dh[128 x 128] = dG[t+1][:, my gate rows] W_hh[my gate rows, :]
-          if (ok && s == 1 && !mbar_wait(&wfull, 0)) { ok = false; if (lane == 0) atomicExch(a.err, 21); }
-          if (ok && !mbar_wait(&a_ready, (s - 1) & 1)) { ok = false; if (lane == 0) atomicExch(a.err, 22); }
-          tc_fence_after();
-          if (lane == 0 && ok) {
-            const uint32_t idesc = idesc_16(128, 1);
-            uint32_t accf = 0;
-#pragma unroll
-            for (int p = 0; p < 3; ++p) {  // dG_hi W_hi, dG_lo W_hi, dG_hi W_lo
-              const uint32_t ac = tbase + (p == 1 ? A_LO : A_HI), bs = smem_u32(p == 2 ? b_lo : b_hi);
-#pragma unroll
-              for (int kb = 0; kb < 4; ++kb)
-#pragma unroll
-                for (int k16 = 0; k16 < 4; ++k16) {
-                  umma_ts_16(tbase, ac + kb * 32 + k16 * 8, umma_desc_k_sw128(bs + kb * 16384 + k16 * 32), idesc, accf);
-                  accf = 1;
-                }
-            }
-            umma_commit(&dfull);
-          }
-          __syncwarp();
-        }
         if (ok && !mbar_wait(&dfull, (s - 1) & 1)) { ok = false; if (lane == 0) atomicExch(a.err, 23); }
         tc_fence_after();
         // ---- the partial dh of the peer's units -> peer (same (row, half, quad) slot the peer's twin thread reads)
@@ -838,27 +845,11 @@ wf_lstm_seq_bwd_kernel(const __grid_constant__ CUtensorMap tmWhi, const __grid_c
           dg[j] = dc * vi * (1.f - vg * vg);
           dcs[8 * c + j] = dc * vf;
         }
-        const int uq = (u0 + 8 * c) >> 2;
-#pragma unroll
-        for (int hsel = 0; hsel < 2; ++hsel) {
-          const int j = 4 * hsel;
-          xg4[(blk * 128 + 0 * 32 + uq + hsel) * 128 + r] = make_float4(di[j], di[j + 1], di[j + 2], di[j + 3]);
-          xg4[(blk * 128 + 1 * 32 + uq + hsel) * 128 + r] = make_float4(df[j], df[j + 1], df[j + 2], df[j + 3]);
-          xg4[(blk * 128 + 2 * 32 + uq + hsel) * 128 + r] = make_float4(dg[j], dg[j + 1], dg[j + 2], dg[j + 3]);
-          xg4[(blk * 128 + 3 * 32 + uq + hsel) * 128 + r] = make_float4(dO[j], dO[j + 1], dO[j + 2], dO[j + 3]);
-        }
-        if (valid) {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            float* base = a.DGT + ((long long)z * 4 * L + u0 + 8 * c + j) * a.RT + tcol;
-            base[0] = di[j];
-            base[(long long)L * a.RT] = df[j];
-            base[2LL * L * a.RT] = dg[j];
-            base[3LL * L * a.RT] = dO[j];
-          }
-        }
-        if (s + 1 < T) {
-          // dG[t] as bf16 hi/lo -> TMEM A operand of the next step: k = gate*64 + (ub + 8c + j), two k per column
+        {
+          // dG[t] as bf16 hi/lo -> TMEM A operand of the next step: k = gate*64 + (ub + 8c + j), two k per column.
+          // The global copies of dG[t] are read back from here AFTER the hand-over (hi + lo is exactly what the GEMMs
+          // downstream split it into again), so nothing is stored to global memory in this loop: an SM writes ~62 GB/s
+          // at most, and the 256 KB of a step would otherwise sit on the recurrence's critical path for 4 us.
           const float* gsrc[4] = {di, df, dg, dO};
 #pragma unroll
           for (int gate = 0; gate < 4; ++gate) {
@@ -875,11 +866,46 @@ wf_lstm_seq_bwd_kernel(const __grid_constant__ CUtensorMap tmWhi, const __grid_c
           }
         }
       }
+      tmem_wait_st();
       if (s + 1 < T) {
-        tmem_wait_st();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&a_ready);
+        if (warp == 0) issue_mma(s + 1);  // warp 0 feeds the tensor core first, then stores like everybody else
+      }
+      // ---- deferred stores of step t (under MMA[s+1]): dG in place (TB4) and transposed fp32 for the weight gradients
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        float v[4][8];
+        __syncwarp();
+#pragma unroll
+        for (int gate = 0; gate < 4; ++gate) {
+          uint32_t hi[4], lo[4];
+          const uint32_t col = (uint32_t)((gate * 64 + ub + 8 * c) >> 1);
+          tmem_ld4(tlane + A_HI + col, hi);
+          tmem_ld4(tlane + A_LO + col, lo);
+          tmem_wait_ld();
+#pragma unroll
+          for (int i2 = 0; i2 < 4; ++i2) {
+            v[gate][2 * i2] = __uint_as_float(hi[i2] << 16) + __uint_as_float(lo[i2] << 16);
+            v[gate][2 * i2 + 1] = __uint_as_float(hi[i2] & 0xFFFF0000u) + __uint_as_float(lo[i2] & 0xFFFF0000u);
+          }
+        }
+        const int uq = (u0 + 8 * c) >> 2;
+#pragma unroll
+        for (int gate = 0; gate < 4; ++gate)
+#pragma unroll
+          for (int hsel = 0; hsel < 2; ++hsel)
+            xg4[(blk * 128 + gate * 32 + uq + hsel) * 128 + r] =
+                make_float4(v[gate][4 * hsel], v[gate][4 * hsel + 1], v[gate][4 * hsel + 2], v[gate][4 * hsel + 3]);
+        if (valid) {
+#pragma unroll
+          for (int jj = 0; jj < 8; ++jj) {
+            float* base = a.DGT + ((long long)z * 4 * L + u0 + 8 * c + jj) * a.RT + tcol;
+#pragma unroll
+            for (int gate = 0; gate < 4; ++gate) base[(long long)gate * L * a.RT] = v[gate][jj];
+          }
+        }
       }
     }
   }
@@ -1032,7 +1058,7 @@ extern "C" int wf_lstm_fwd_seq(const float* x, const float* params, const void* 
     a.HT = hT_hi ? (__nv_bfloat16*)hT_hi + l * tsz : nullptr; a.HT_lo = hT_hi ? (__nv_bfloat16*)hT_lo + l * tsz : nullptr;
     a.T = T; a.Nn = N; a.Bw = Bw; a.tpw = tpw; a.Np = Np; a.RT = RT;
     a.slab0 = l; a.slab_g = layers; a.err = err;
-    static const bool fwd16 = getenv("WF_SEQ_FWD16") != nullptr;
+    static const bool fwd16 = getenv("WF_SEQ_FWD8") == nullptr;  // WF_SEQ_FWD8=1: the first-generation 8-warp kernel (A/B timing)
     if (fwd16) {
       static bool c16 = false;
       if (!c16) { int rc16 = seq_configure(wf_lstm_seq_fwd16_kernel); if (rc16) return rc16; c16 = true; }
@@ -1131,6 +1157,12 @@ extern "C" int wf_lstm_seq_recur_fwd(float* gates_l, float* c_l, float* h_l, voi
   a.HT = (__nv_bfloat16*)hT_hi_l; a.HT_lo = (__nv_bfloat16*)hT_lo_l;
   a.T = T; a.Nn = N; a.Bw = Bw; a.tpw = wf_cdiv(N, 128); a.Np = wf_np(N); a.RT = T * a.Np;
   a.slab0 = layer; a.slab_g = layers; a.err = err;
+  static const bool fwd16 = getenv("WF_SEQ_FWD8") == nullptr;
+  if (fwd16) {
+    static bool c16 = false;
+    if (!c16) { int rc16 = seq_configure(wf_lstm_seq_fwd16_kernel); if (rc16) return rc16; c16 = true; }
+    wf_lstm_seq_fwd16_kernel<<<dim3((unsigned)(2 * Z * a.tpw)), 512, SEQ_SMEM, (cudaStream_t)stream>>>(tmhi, tmlo, a);
+  } else
   wf_lstm_seq_fwd_kernel<<<dim3((unsigned)(2 * Z * a.tpw)), SEQ_THREADS, SEQ_SMEM, (cudaStream_t)stream>>>(tmhi, tmlo, a);
   WF_CHECK_LAUNCH("lstm_seq_recur_fwd");
   return WF_OK;
