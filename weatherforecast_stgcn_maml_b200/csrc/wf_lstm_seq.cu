@@ -430,7 +430,7 @@ wf_lstm_seq_fwd16_kernel(const __grid_constant__ CUtensorMap tmWhi, const __grid
   uint8_t* b_lo = smem + 65536;
   uint8_t* a_hi = smem + 131072;   // [2 k-blocks][128 rows][128 B]
   uint8_t* a_lo = smem + 163840;
-  __shared__ uint64_t wfull, a_ready[4], dfull, peer_done;
+  __shared__ uint64_t wfull, a_ready[4], issued[3], dfull, peer_done;
   __shared__ uint32_t tmem_base_s;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t rank = cluster_rank(), peer = rank ^ 1u;
@@ -441,8 +441,9 @@ wf_lstm_seq_fwd16_kernel(const __grid_constant__ CUtensorMap tmWhi, const __grid
   if (tid == 0) {
     // a_ready[c], one per chunk of 16 units (= one K step of 16 per k-block): 16 local warps + the expect_tx arrival;
     // the peer's 16 units of h[t] arrive as 8 KB of st.async transactions
-    mbar_init(&wfull, 1); mbar_init(&dfull, 1); mbar_init(&peer_done, 1);
+    mbar_init(&wfull, 1); mbar_init(&dfull, 4); mbar_init(&peer_done, 1);  // dfull: one commit per K-step issuer
     for (int c = 0; c < 4; ++c) mbar_init(&a_ready[c], 17);
+    for (int c = 0; c < 3; ++c) mbar_init(&issued[c], 1);
     mbar_fence_init();
     tma_prefetch_desc(&tmWhi); tma_prefetch_desc(&tmWlo);
   }
@@ -492,38 +493,43 @@ wf_lstm_seq_fwd16_kernel(const __grid_constant__ CUtensorMap tmWhi, const __grid
   load_chunk(0, 0, xq[0]);
   load_chunk(0, 1, xq[1]);
 
-  // MMA[t+1] = h[t] W_hh^T, issued by warp 0 one K step of 16 units (x 2 k-blocks x 3 hi/lo products) at a time, as
-  // soon as that slice of h[t] is complete in BOTH CTAs: only the last K step is left when phase A ends.
-  int kdone = 0;  // K steps of the pending MMA already issued (warp 0)
-  auto mma_steps = [&](int t, int climit, bool block) {
-    while (kdone < climit) {
-      if (kdone == 0 && t == 0 && ok && !mbar_wait(&wfull, 0)) { ok = false; if (lane == 0) atomicExch(a.err, 11); }
-      if (block) {
-        // the peer's slice arrived as st.async transactions counted by this barrier: a CTA-scope acquire is enough
-        if (ok && !mbar_wait(&a_ready[kdone], t & 1)) { ok = false; if (lane == 0) atomicExch(a.err, 12); }
-      } else if (!__all_sync(0xffffffffu, mbar_test(&a_ready[kdone], t & 1))) {
-        return;
-      }
-      if (lane == 0 && t + 2 < T) mbar_expect_tx(&a_ready[kdone], 8192);  // next phase: the peer's slice of h[t+1]
-      fence_proxy_async_cta();
-      tc_fence_after();
-      if (lane == 0 && ok) {
-        const uint32_t idesc = idesc_16(256, 0);
-        const uint32_t dnext = tbase + (uint32_t)((t + 1) & 1) * 256u;
-#pragma unroll
-        for (int p = 0; p < 3; ++p) {  // h_hi W_hi, h_lo W_hi, h_hi W_lo
-          const uint32_t as = smem_u32(p == 1 ? a_lo : a_hi), bs = smem_u32(p == 2 ? b_lo : b_hi);
-#pragma unroll
-          for (int kb = 0; kb < 2; ++kb)
-            umma_ss_16(dnext, umma_desc_k_sw128(as + kb * 16384 + kdone * 32), umma_desc_k_sw128(bs + kb * 32768 + kdone * 32),
-                       idesc, (kdone | p | kb) != 0 ? 1u : 0u);
-        }
-        if (kdone == 3) umma_commit(&dfull);
-      }
-      __syncwarp();
-      ++kdone;
+  // MMA[t+1] = h[t] W_hh^T, one K step of 16 units (x 2 k-blocks x 3 hi/lo products = 6 instructions) at a time, as soon
+  // as that slice of h[t] is complete in BOTH CTAs: only the last K step is left when phase A ends.  tcgen05.mma blocks
+  // the issuing thread while the pipe is busy (~128 cycles per instruction here), so the four K steps are issued by four
+  // different warps (K step j by warp j), chained through issued[j] so that they enter the pipe in order.
+  bool mdone = true;  // warps 0-3: my K step of the pending MMA has been issued (or none is pending)
+  auto mma_step = [&](int t, bool block) {
+    if (mdone) return;
+    const int ks = warp;
+    if (ks == 0 && t == 0 && ok && !mbar_wait(&wfull, 0)) { ok = false; if (lane == 0) atomicExch(a.err, 11); }
+    if (block) {
+      // the peer's slice arrived as st.async transactions counted by this barrier: a CTA-scope acquire is enough
+      if (ok && !mbar_wait(&a_ready[ks], t & 1)) { ok = false; if (lane == 0) atomicExch(a.err, 12); }
+      if (ks > 0 && ok && !mbar_wait(&issued[ks - 1], t & 1)) { ok = false; if (lane == 0) atomicExch(a.err, 15); }
+    } else {
+      bool rdy = mbar_test(&a_ready[ks], t & 1);
+      if (ks > 0) rdy = rdy && mbar_test(&issued[ks - 1], t & 1);
+      if (!__all_sync(0xffffffffu, rdy)) return;
     }
-    if (kdone == 4 && block) kdone = 0;
+    if (lane == 0 && t + 2 < T) mbar_expect_tx(&a_ready[ks], 8192);  // next phase: the peer's slice of h[t+1]
+    fence_proxy_async_cta();
+    tc_fence_after();
+    if (lane == 0 && ok) {
+      const uint32_t idesc = idesc_16(256, 0);
+      const uint32_t dnext = tbase + (uint32_t)((t + 1) & 1) * 256u;
+#pragma unroll
+      for (int p = 0; p < 3; ++p) {  // h_hi W_hi, h_lo W_hi, h_hi W_lo
+        const uint32_t as = smem_u32(p == 1 ? a_lo : a_hi), bs = smem_u32(p == 2 ? b_lo : b_hi);
+#pragma unroll
+        for (int kb = 0; kb < 2; ++kb)
+          umma_ss_16(dnext, umma_desc_k_sw128(as + kb * 16384 + ks * 32), umma_desc_k_sw128(bs + kb * 32768 + ks * 32),
+                     idesc, (ks | p | kb) != 0 ? 1u : 0u);
+      }
+      umma_commit(&dfull);  // a commit tracks the issuing thread's own instructions: D[t+1] is complete after all four
+      if (ks < 3) { tc_fence_before(); mbar_arrive(&issued[ks]); }
+    }
+    __syncwarp();
+    mdone = true;
   };
 
   for (int t = 0; t < T; ++t) {
@@ -534,6 +540,7 @@ wf_lstm_seq_fwd16_kernel(const __grid_constant__ CUtensorMap tmWhi, const __grid
       if (warp == 0 && lane == 0) arrive_cluster_relaxed(pd_remote);  // my MMA no longer reads my A buffer
     }
     WF_TR(0);
+    mdone = !(warp < 4 && t + 1 < T);
     const long long blk = ((long long)z * T + t) * a.tpw + nt;
     const long long hrow = ((long long)z * R + (long long)t * a.Nn + node) * L + u0;
     const long long tcol = (long long)t * a.Np + node;
@@ -613,7 +620,7 @@ wf_lstm_seq_fwd16_kernel(const __grid_constant__ CUtensorMap tmWhi, const __grid
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&a_ready[c]);
-        if (warp == 0 && c > 0) mma_steps(t, c, false);  // K steps whose operands have already arrived everywhere
+        if (warp < 4 && c > warp) mma_step(t, false);  // my K step, if its operands have arrived everywhere
       }
       WF_TR(10 + 4 * c);
       if (a.h_tb4) reinterpret_cast<float4*>(a.H)[(blk * 32 + (u0 >> 2) + 4 * c) * 128 + r] = make_float4(hh[0], hh[1], hh[2], hh[3]);
@@ -640,7 +647,7 @@ wf_lstm_seq_fwd16_kernel(const __grid_constant__ CUtensorMap tmWhi, const __grid
       load_chunk(t + 1, 0, xq[0]);  // ahead of phase B's stores: the memory pipeline is in order
       load_chunk(t + 1, 1, xq[1]);
       WF_TR(2);
-      if (warp == 0) mma_steps(t, 4, true);  // the remaining K steps of MMA[t+1], then the commit
+      if (warp < 4) mma_step(t, true);
       WF_TR(4);
     }
     // ------------------------------------------------------------ phase B: gates (TMEM) and cell state -> global
