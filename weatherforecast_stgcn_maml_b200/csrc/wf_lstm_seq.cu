@@ -421,6 +421,16 @@ __device__ __forceinline__ float rcp_approx(float x) {
   return y;
 }
 
+// h = o tanh(c) for four units from d = 1 + e^(-2c): tanh = 2 / d - 1 with one reciprocal for the four denominators
+__device__ __forceinline__ void hidden4(const float* go, const float* dc, float* hh) {
+  const float p1 = dc[0] * dc[1], p2 = dc[2] * dc[3], rr = rcp_approx(p1 * p2);
+  const float r1 = rr * p2, r2 = rr * p1;
+  hh[0] = go[0] * fmaf(2.0f, r1 * dc[1], -1.0f);
+  hh[1] = go[1] * fmaf(2.0f, r1 * dc[0], -1.0f);
+  hh[2] = go[2] * fmaf(2.0f, r2 * dc[3], -1.0f);
+  hh[3] = go[3] * fmaf(2.0f, r2 * dc[2], -1.0f);
+}
+
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(512, 1)
 wf_lstm_seq_fwd16_kernel(const __grid_constant__ CUtensorMap tmWhi, const __grid_constant__ CUtensorMap tmWlo, const SeqArgs a) {
   constexpr int L = 128;
@@ -584,15 +594,7 @@ wf_lstm_seq_fwd16_kernel(const __grid_constant__ CUtensorMap tmWhi, const __grid
         gt[0][j] = __float_as_uint(gi); gt[1][j] = __float_as_uint(gf);
         gt[2][j] = __float_as_uint(gg); gt[3][j] = __float_as_uint(go[j]);
       }
-      {
-        // tanh(c) of the four units: one reciprocal again
-        const float p1 = dc[0] * dc[1], p2 = dc[2] * dc[3], rr = rcp_approx(p1 * p2);
-        const float r1 = rr * p2, r2 = rr * p1;
-        hh[0] = go[0] * fmaf(2.0f, r1 * dc[1], -1.0f);
-        hh[1] = go[1] * fmaf(2.0f, r1 * dc[0], -1.0f);
-        hh[2] = go[2] * fmaf(2.0f, r2 * dc[3], -1.0f);
-        hh[3] = go[3] * fmaf(2.0f, r2 * dc[2], -1.0f);
-      }
+      hidden4(go, dc, hh);
       __syncwarp();
 #pragma unroll
       for (int gate = 0; gate < 4; ++gate) tmem_st4(dcol + gate * 64 + 16 * c, gt[gate]);
@@ -623,23 +625,6 @@ wf_lstm_seq_fwd16_kernel(const __grid_constant__ CUtensorMap tmWhi, const __grid
         if (warp < 4 && c > warp) mma_step(t, false);  // my K step, if its operands have arrived everywhere
       }
       WF_TR(10 + 4 * c);
-      if (a.h_tb4) reinterpret_cast<float4*>(a.H)[(blk * 32 + (u0 >> 2) + 4 * c) * 128 + r] = make_float4(hh[0], hh[1], hh[2], hh[3]);
-      if (valid) {
-        if (!a.h_tb4) *reinterpret_cast<float4*>(a.H + hrow + 16 * c) = make_float4(hh[0], hh[1], hh[2], hh[3]);
-        if (a.HT != nullptr) {
-          __nv_bfloat16* ht = a.HT + ((long long)z * L + u0 + 16 * c) * a.RT + tcol;
-          __nv_bfloat16* htl = a.HT_lo + ((long long)z * L + u0 + 16 * c) * a.RT + tcol;
-#pragma unroll
-          for (int j = 0; j < 4; j += 2) {
-            float ra, rb, d0, d1;
-            const uint32_t uh = pack_bf16(hh[j], hh[j + 1], ra, rb), ul = pack_bf16(ra, rb, d0, d1);
-            reinterpret_cast<uint16_t*>(ht)[(long long)j * a.RT] = (uint16_t)uh;
-            reinterpret_cast<uint16_t*>(ht)[(long long)(j + 1) * a.RT] = (uint16_t)(uh >> 16);
-            reinterpret_cast<uint16_t*>(htl)[(long long)j * a.RT] = (uint16_t)ul;
-            reinterpret_cast<uint16_t*>(htl)[(long long)(j + 1) * a.RT] = (uint16_t)(ul >> 16);
-          }
-        }
-      }
     }
     tmem_wait_st();  // the staged gates are in TMEM before phase B reads them back
     WF_TR(1);
@@ -658,11 +643,39 @@ wf_lstm_seq_fwd16_kernel(const __grid_constant__ CUtensorMap tmWhi, const __grid
 #pragma unroll
       for (int gate = 0; gate < 4; ++gate) tmem_ld4(dcol + gate * 64 + 16 * c, gt[gate]);
       tmem_wait_ld();
+      // h[t] = o tanh(c[t]) again (bit-identical to phase A: same function, same inputs) instead of 16 more registers
+      float hh[4];
+      {
+        float go[4], dc[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          go[j] = __uint_as_float(gt[3][j]);
+          dc[j] = 1.0f + exp2_neg(cst[4 * c + j], 2.0f * kLog2e);
+        }
+        hidden4(go, dc, hh);
+      }
 #pragma unroll
       for (int gate = 0; gate < 4; ++gate)
         xg4[xg_index(t, c, gate)] = make_float4(__uint_as_float(gt[gate][0]), __uint_as_float(gt[gate][1]),
                                                 __uint_as_float(gt[gate][2]), __uint_as_float(gt[gate][3]));
       c4[(blk * 32 + (u0 >> 2) + 4 * c) * 128 + r] = make_float4(cst[4 * c], cst[4 * c + 1], cst[4 * c + 2], cst[4 * c + 3]);
+      if (a.h_tb4) reinterpret_cast<float4*>(a.H)[(blk * 32 + (u0 >> 2) + 4 * c) * 128 + r] = make_float4(hh[0], hh[1], hh[2], hh[3]);
+      if (valid) {
+        if (!a.h_tb4) *reinterpret_cast<float4*>(a.H + hrow + 16 * c) = make_float4(hh[0], hh[1], hh[2], hh[3]);
+        if (a.HT != nullptr) {
+          __nv_bfloat16* ht = a.HT + ((long long)z * L + u0 + 16 * c) * a.RT + tcol;
+          __nv_bfloat16* htl = a.HT_lo + ((long long)z * L + u0 + 16 * c) * a.RT + tcol;
+#pragma unroll
+          for (int j = 0; j < 4; j += 2) {
+            float ra, rb, d0, d1;
+            const uint32_t uh = pack_bf16(hh[j], hh[j + 1], ra, rb), ul = pack_bf16(ra, rb, d0, d1);
+            reinterpret_cast<uint16_t*>(ht)[(long long)j * a.RT] = (uint16_t)uh;
+            reinterpret_cast<uint16_t*>(ht)[(long long)(j + 1) * a.RT] = (uint16_t)(uh >> 16);
+            reinterpret_cast<uint16_t*>(htl)[(long long)j * a.RT] = (uint16_t)ul;
+            reinterpret_cast<uint16_t*>(htl)[(long long)(j + 1) * a.RT] = (uint16_t)(ul >> 16);
+          }
+        }
+      }
     }
     WF_TR(5);
   }
