@@ -271,7 +271,7 @@ def stage_breakdown(trainer, reps=3):
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernels from `ncu --set full`
 # (profiles/r1_final_ncu_summary.md); None until a capture of the current kernels is committed
-NCU_TRAFFIC = {"wf_lstm_seq_fwd_kernel": 974.7e6, "wf_lstm_seq_bwd_kernel": 1230.1e6}
+NCU_TRAFFIC = {"wf_lstm_seq_fwd16_kernel": 974.7e6, "wf_lstm_seq_bwd_kernel": 1230.1e6}
 
 
 def time_recurrence_kernels(trainer, reps=10):
@@ -295,7 +295,7 @@ def time_recurrence_kernels(trainer, reps=10):
                   _lib.ptr(e.w16[2]), _lib.ptr(e.w16[3]), 1, Ls, L, d.window, d.num_nodes, e.G, e.Bw, _lib.ptr(e.err), st)
 
     e.ws.zero_()  # dh from the layer above: zeros (timing does not depend on values)
-    for name, fn in (("wf_lstm_seq_fwd_kernel", fwd), ("wf_lstm_seq_bwd_kernel", bwd)):
+    for name, fn in (("wf_lstm_seq_fwd16_kernel", fwd), ("wf_lstm_seq_bwd_kernel", bwd)):
         for _ in range(3):
             fn()
         torch.cuda.synchronize()
@@ -320,7 +320,7 @@ def roofline_report(stages, kernel_ms, G, peak, peak_src):
     csr = E * 8 + (R + 1) * 4
     per_row_step = {
         # read the input projection (4L f32); write gates (4L), c (L), h (L) f32 and h^T as bf16 hi + lo (2 x L x 2 B)
-        "wf_lstm_seq_fwd_kernel": 4 * L * 4 + (4 * L + L + L) * 4 + 2 * L * 2,
+        "wf_lstm_seq_fwd16_kernel": 4 * L * 4 + (4 * L + L + L) * 4 + 2 * L * 2,
         # read gates (4L), c[t], c[t-1] (2L), dh from above (L); write dG (4L) and dG^T (4L) f32
         "wf_lstm_seq_bwd_kernel": (4 * L + 2 * L + L) * 4 + (4 * L + 4 * L) * 4,
     }
