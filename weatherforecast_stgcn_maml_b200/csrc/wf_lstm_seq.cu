@@ -396,8 +396,10 @@ wf_lstm_seq_fwd_kernel(const __grid_constant__ CUtensorMap tmWhi, const __grid_c
 #ifdef WF_SEQ_TRACE
 __device__ long long wf_seq_trace_buf[32 * 16 * 24];  // [step][warp][point], CTA 0 (tools/trace_fwd.py)
 #define WF_TR(pt) do { if (blockIdx.x == 0 && lane == 0 && t < 32) wf_seq_trace_buf[(t * 16 + warp) * 24 + (pt)] = clock64(); } while (0)
+#define WF_TRS(pt) do { if (blockIdx.x == 0 && lane == 0 && s < 32) wf_seq_trace_buf[(s * 16 + warp) * 24 + (pt)] = clock64(); } while (0)
 #else
 #define WF_TR(pt) do { } while (0)
+#define WF_TRS(pt) do { } while (0)
 #endif
 __device__ __forceinline__ void st_async_v2(uint32_t caddr, uint32_t x, uint32_t y, uint32_t cbar) {
   asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.b32 [%0], {%1, %2}, [%3];\n"
@@ -810,6 +812,7 @@ wf_lstm_seq_bwd_kernel(const __grid_constant__ CUtensorMap tmWhi, const __grid_c
         // the peer's partial dh for my units arrives as st.async transactions on x_ready[xb] (phase (s - 1) / 2)
         if (ok && !mbar_wait(&dfull, (s - 1) & 1)) { ok = false; if (lane == 0) atomicExch(a.err, 23); }
         tc_fence_after();
+        WF_TRS(0);
         // ---- the partial dh of the peer's units -> peer (same (row, half, quad) slot the peer's twin thread reads)
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
@@ -821,7 +824,10 @@ wf_lstm_seq_bwd_kernel(const __grid_constant__ CUtensorMap tmWhi, const __grid_c
           st_async_v4(dst, make_uint4(v[0], v[1], v[2], v[3]), xb ? xr_remote1 : xr_remote0);
           st_async_v4(dst + 2048u, make_uint4(v[4], v[5], v[6], v[7]), xb ? xr_remote1 : xr_remote0);
         }
-        if (ok && !mbar_wait_cl(&x_ready[xb], ((s - 1) >> 1) & 1)) { ok = false; if (lane == 0) atomicExch(a.err, 24); }
+        WF_TRS(1);
+        // the data arrive as st.async transactions counted by this barrier: a CTA-scope acquire is enough
+        if (ok && !mbar_wait(&x_ready[xb], ((s - 1) >> 1) & 1)) { ok = false; if (lane == 0) atomicExch(a.err, 24); }
+        WF_TRS(2);
       }
       const long long blk = blk_of(t);
       const long long tcol = (long long)t * a.Np + node;
@@ -885,13 +891,16 @@ wf_lstm_seq_bwd_kernel(const __grid_constant__ CUtensorMap tmWhi, const __grid_c
             tmem_st4(tlane + A_LO + col, lo);
           }
         }
+        WF_TRS(3 + c);
       }
       tmem_wait_st();
+      WF_TRS(7);
       if (s + 1 < T) {
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&a_ready);
-        if (warp == 0) issue_mma(s + 1);  // warp 0 feeds the tensor core first, then stores like everybody else
+        if (warp == 0) issue_mma(s + 1);
+        WF_TRS(8);  // warp 0 feeds the tensor core first, then stores like everybody else
       }
       // ---- deferred stores of step t (under MMA[s+1]): dG in place (TB4) and transposed fp32 for the weight gradients
 #pragma unroll
@@ -927,6 +936,7 @@ wf_lstm_seq_bwd_kernel(const __grid_constant__ CUtensorMap tmWhi, const __grid_c
           }
         }
       }
+      WF_TRS(9);
     }
   }
   tc_fence_before();
