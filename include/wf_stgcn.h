@@ -257,6 +257,22 @@ int wf_lstm_seq_recur_bwd(float* gates_l, const float* c_l, float* dgT, const fl
                           const void* b16_hi, const void* b16_lo, int layer, int layers, int L, int T, int N, int G,
                           int Bw, int* err, void* stream);
 
+/* ---- feature assembly: prepare_model_input, featurePreprocessor.py:84-177 ----
+ * weather: device f32 [time * N, 12] (time-major rows, the reference's reshape at :121-122), may hold NaN.
+ * wf_feature_stats: per variable the NaN fill value (f32 nanmean, 0 if all NaN; :104-109), the mean and the population
+ * standard deviation of the FILLED array over (time, nodes) in f64 (:133-136; the caller adds the 1e-8) and the NaN
+ * count.  Outputs are DEVICE buffers fill[12], mean[12], stdev[12], nan_count[12]. */
+size_t wf_feature_stats_workspace_bytes(long long rows);
+int wf_feature_stats(const float* weather, long long rows, float* fill, double* mean, double* stdev,
+                     long long* nan_count, void* workspace, size_t workspace_bytes, void* stream);
+/* out[time * N, 24] = [ (x or fill - mean) / std | time features of the step | Koppen embedding row ], NaN -> 0
+ * (:146, :164-180).  fill / mean / std / koppen are HOST arrays (12, 12, 12, 8 values); timefeat is device f32 [time, 4]
+ * (embed_utils.py:9-27).  f64_arith = 1 reproduces the reference with statistics passed in (f64 arrays), 0 the
+ * statistics it derives itself (f32 arrays). */
+int wf_assemble_features(const float* weather, long long time_steps, int N, const float* fill_host,
+                         const double* mean_host, const double* std_host, int normalize, int f64_arith,
+                         const float* timefeat, const float* koppen_host, float* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -240,8 +240,71 @@ def knn_cases(mods):
     print("[golden] knn_ckdtree:", {k_: v.shape for k_, v in out.items()})
 
 
+class _Var:
+    def __init__(self, values):
+        self.values = values
+
+
+def synth_raw_weather(seed, time, nlat, nlon, nan_frac=0.01, all_nan_var=None):
+    """Raw (un-normalised) ERA5-like fields f32 [time, lat, lon, 12] with physical offsets and scales, NaNs sprinkled in
+    three variables (and optionally one variable entirely NaN), plus day-of-year / hour-of-day of hourly steps."""
+    g = np.random.RandomState(seed)
+    loc = np.array([1.5, -0.7, 288.0, 281.0, 98000.0, 2e-4, 2.5, -1.1, -6.0e4, 0.35, 0.45, -8e-5], dtype=np.float64)
+    scale = np.array([3.0, 3.0, 9.0, 8.0, 2500.0, 5e-4, 4.5, 4.5, 3.0e4, 0.3, 0.3, 6e-5], dtype=np.float64)
+    w = (loc + scale * g.standard_normal((time, nlat, nlon, 12))).astype(np.float32)
+    for v in (2, 5, 9):
+        w[..., v][g.random_sample((time, nlat, nlon)) < nan_frac] = np.nan
+    if all_nan_var is not None:
+        w[..., all_nan_var] = np.nan
+    hours = 17 + np.arange(time)
+    return w, 200 + hours // 24, (hours % 24).astype(np.float64)
+
+
+def feature_cases():
+    """prepare_model_input of the UNMODIFIED reference (featurePreprocessor.py:66-182) on a dict-like stand-in for the
+    xarray Dataset; embed_utils.add_time_embeddings needs a real Dataset, so the time features come from the restated
+    formula (ref_port.time_features, embed_utils.py:12-26).  Freezes inputs, outputs and statistics."""
+    from oracle import pyg_shim, ref_port
+
+    pyg_shim.install()
+    if REF not in sys.path:
+        sys.path.insert(0, REF)
+    with contextlib.redirect_stdout(io.StringIO()):
+        import featurePreprocessor as fp
+        import embed_utils
+    torch.manual_seed(42)
+    kop = embed_utils.KoppenEmbedding(8)
+    out = {"koppen_weight": kop.embedding.weight.detach().numpy().copy()}
+    given = {"mean": [float(x) for x in np.linspace(-2.0, 3.0, 12)], "std": [float(x) for x in np.linspace(0.5, 4.0, 12)]}
+    for name, kw, code, stats in (("nan", dict(), 7, None), ("allnan", dict(all_nan_var=4), 12, None),
+                                  ("clean", dict(nan_frac=0.0), 3, None), ("given", dict(), 21, given),
+                                  ("raw", dict(), 5, "raw")):
+        w, doy, tod = synth_raw_weather(11 + code, 40, 5, 7, **kw)
+        tf = ref_port.time_features(doy, tod)
+        ds = {v: _Var(w[..., i].copy()) for i, v in enumerate(fp.WEATHER_VARS)}
+        ds.update({v: _Var(tf[:, i]) for i, v in enumerate(fp.TIME_VARS)})
+        normalize = stats != "raw"
+        with contextlib.redirect_stdout(io.StringIO()):
+            feats, st = fp.prepare_model_input(ds, code, kop, normalize=normalize, stats=stats if normalize else None)
+        mine, st2 = ref_port.prepare_features(w.copy(), tf, kop(torch.tensor([code])), normalize=normalize,
+                                              stats=stats if normalize else None)
+        assert torch.equal(feats, mine), name
+        if normalize:
+            assert np.array_equal(np.asarray(st["mean"]), np.asarray(st2["mean"])), name
+        out[f"{name}_weather"], out[f"{name}_doy"], out[f"{name}_tod"] = w, doy, tod
+        out[f"{name}_code"] = np.array(code)
+        out[f"{name}_features"] = feats.detach().numpy()
+        if normalize:
+            out[f"{name}_mean"], out[f"{name}_std"] = np.asarray(st["mean"]), np.asarray(st["std"])
+    np.savez_compressed(os.path.join(OUT, "features_prepare.npz"), **out)
+    print("features_prepare.npz:", {k: v.shape for k, v in out.items() if k.endswith("_features")})
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
+    if len(sys.argv) > 1 and sys.argv[1] == "features":  # only this fixture (the model cases take minutes)
+        feature_cases()
+        return
     torch.manual_seed(42)
     np.random.seed(42)
     torch.set_num_threads(os.cpu_count() or 1)
@@ -254,6 +317,7 @@ def main():
     full["in"] = 24
     run_case(mods, "hybrid_v5_k4", full, nlat=21, nlon=21, k=4, seed=42, inner_steps=3, full_tensors=False)
     run_case(mods, "hybrid_v5_k8", full, nlat=21, nlon=21, k=8, seed=43, inner_steps=3, full_tensors=False)
+    feature_cases()
 
 
 if __name__ == "__main__":

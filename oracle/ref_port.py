@@ -248,3 +248,51 @@ def build_reference_like_module(sd, window, horizon=8, lstm_layers=4):
 
     params = list(lstm.parameters()) + [head_w, head_b]
     return forward, params
+
+
+# ------------------------------------------------------------------ feature assembly
+WEATHER_VARS = ["u10", "v10", "t2m", "d2m", "sp", "tp", "u100", "v100", "str", "hcc", "lcc", "e"]
+TIME_VARS = ["year_progress_sin", "year_progress_cos", "day_progress_sin", "day_progress_cos"]
+
+
+def time_features(day_of_year, time_of_day):
+    """embed_utils.py:12-26 on plain arrays: [time, 4] f64 in TIME_VARS order."""
+    year = 2 * np.pi * np.asarray(day_of_year) / 365.25
+    day = 2 * np.pi * np.asarray(time_of_day, dtype=np.float64) / 24.0
+    return np.stack([np.sin(year), np.cos(year), np.sin(day), np.cos(day)], axis=-1)
+
+
+def prepare_features(weather, time_data, koppen_row, normalize=True, stats=None):
+    """featurePreprocessor.py:84-182 on plain arrays, statement by statement: ``weather`` [time, lat, lon, 12] (NaN
+    allowed, modified in place like the reference does), ``time_data`` [time, 4], ``koppen_row`` [1, 8] torch tensor.
+    Returns (combined f32 [time, nodes, 24], stats)."""
+    weather_data = weather
+    if np.isnan(weather_data).sum() > 0:  # :97-109
+        for i in range(weather_data.shape[-1]):
+            var_data = weather_data[..., i]
+            var_mean = np.nanmean(var_data) if not np.all(np.isnan(var_data)) else np.nan
+            if np.isnan(var_mean):
+                var_mean = 0.0
+            weather_data[..., i] = np.nan_to_num(var_data, nan=var_mean)
+    num_time, num_lat, num_lon, num_weather = weather_data.shape  # :117-122
+    num_nodes = num_lat * num_lon
+    weather_features = weather_data.reshape(num_time, num_nodes, num_weather)
+    if normalize:  # :125-146
+        if stats is not None:
+            mean, std = np.array(stats["mean"]), np.array(stats["std"])
+        else:
+            mean = weather_features.mean(axis=(0, 1))
+            std = weather_features.std(axis=(0, 1)) + 1e-8
+            if np.any(np.isnan(mean)) or np.any(np.isnan(std)):
+                mean, std = np.nan_to_num(mean, nan=0.0), np.nan_to_num(std, nan=1.0)
+            stats = {"mean": mean, "std": std}
+        weather_features = (weather_features - mean) / std
+    elif stats is None:
+        stats = {}
+    weather_tensor = torch.tensor(weather_features, dtype=torch.float32)  # :161-176
+    time_tensor = torch.tensor(np.tile(time_data[:, np.newaxis, :], (1, num_nodes, 1)), dtype=torch.float32)
+    koppen_expanded = koppen_row.detach().cpu().unsqueeze(0).expand(num_time, num_nodes, -1)
+    combined = torch.cat([weather_tensor, time_tensor, koppen_expanded], dim=-1)
+    if torch.isnan(combined).any():  # :178-180
+        combined = torch.nan_to_num(combined, nan=0.0)
+    return combined, stats

@@ -118,3 +118,44 @@ def test_literal_reference_grad_is_stale_plus_query():
     for k, stale in zip(g_last, gl):
         check_summary(stale, z[f"stale_summary/{k}"], z[f"stale_samples/{k}"], 1e-4, "stale " + k)
         check_summary(stale + qgrads[k], z[f"literal_summary/{k}"], z[f"literal_samples/{k}"], 2e-4, "literal " + k)
+
+
+FEATURE_CASES = ("nan", "allnan", "clean", "given", "raw")
+GIVEN_STATS = {"mean": [float(x) for x in np.linspace(-2.0, 3.0, 12)], "std": [float(x) for x in np.linspace(0.5, 4.0, 12)]}
+
+
+def feature_case_inputs(z, name):
+    """(weather copy, time features, Koppen row, normalize, stats) of one features_prepare.npz case."""
+    w = z[f"{name}_weather"].copy()
+    tf = P.time_features(z[f"{name}_doy"], z[f"{name}_tod"])
+    row = torch.from_numpy(z["koppen_weight"])[int(z[f"{name}_code"])][None, :]
+    return w, tf, row, name != "raw", (GIVEN_STATS if name == "given" else None)
+
+
+@pytest.mark.parametrize("name", FEATURE_CASES)
+def test_port_prepare_features_matches_reference(name):
+    """oracle restatement of prepare_model_input (featurePreprocessor.py:84-182) == the reference's own output, bit for
+    bit (numpy and torch are the same libraries on both sides), incl. NaN fill, an all-NaN variable, given statistics
+    (f64 arithmetic) and normalize=False."""
+    import warnings
+
+    z = load_golden("features_prepare")
+    w, tf, row, normalize, stats = feature_case_inputs(z, name)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        feats, st = P.prepare_features(w, tf, row, normalize=normalize, stats=stats)
+    assert feats.dtype == torch.float32 and tuple(feats.shape) == (40, 35, 24)
+    assert np.array_equal(feats.numpy(), z[f"{name}_features"])
+    if normalize:
+        assert np.array_equal(np.asarray(st["mean"]), z[f"{name}_mean"]) and np.array_equal(np.asarray(st["std"]), z[f"{name}_std"])
+    assert not np.isnan(feats.numpy()).any()
+
+
+def test_time_features_formula():
+    """embed_utils.py:12-26: year phase over 365.25 days, day phase over 24 h, order sin/cos year, sin/cos day."""
+    from weatherforecast_stgcn_maml_b200.embed_utils import time_features
+
+    tf = time_features([1, 100, 366], [0.0, 6.0, 23.5])
+    assert tf.shape == (3, 4) and tf.dtype == np.float64
+    assert np.allclose(tf[1], [np.sin(2 * np.pi * 100 / 365.25), np.cos(2 * np.pi * 100 / 365.25), 1.0, 0.0], atol=1e-15)
+    assert np.array_equal(tf, P.time_features([1, 100, 366], [0.0, 6.0, 23.5]))

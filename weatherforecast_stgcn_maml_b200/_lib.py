@@ -47,6 +47,9 @@ SIGNATURES = {
     "wf_clip_sgd_step": (c_i, [c_p, c_ll, c_p, c_ll, c_ll, c_i, c_f, c_f, c_p, c_p, c_sz, c_p]),
     "wf_clip_adam_step": (c_i, [c_p, c_p, c_p, c_p, c_ll, c_p, c_f, c_i, c_p, c_p, c_sz, c_p]),
     "wf_sum_groups": (c_i, [c_p, c_ll, c_i, c_ll, c_p, c_i, c_p]),
+    "wf_feature_stats_workspace_bytes": (c_sz, [c_ll]),
+    "wf_feature_stats": (c_i, [c_p, c_ll, c_p, c_p, c_p, c_p, c_p, c_sz, c_p]),
+    "wf_assemble_features": (c_i, [c_p, c_ll, c_i, c_p, c_p, c_p, c_i, c_i, c_p, c_p, c_p, c_p]),
     "wf_param_count_transposed": (c_ll, [c_i, c_i, c_i, c_i]),
     "wf_prep_weights_tc": (c_i, [c_p, c_ll, c_i, c_i, c_i, c_i, c_i, c_p, c_p, c_p, c_p]),
     "wf_transposed_pitch": (c_ll, [c_i, c_i]),

@@ -4,10 +4,19 @@ Same constructor, attributes and ``state_dict`` (``embedding.weight [31, 8]``). 
 reference path the embedding row is concatenated into the input features once per task at
 dataset-build time and detached (featurePreprocessor.py:170-177, dataset.py:50-53), so it never
 receives a gradient; the lookup itself is an ordinary ``nn.Embedding``.
-``add_time_embeddings`` (embed_utils.py:10-27) is host-side xarray preprocessing and out of
-scope; synth.synth_features restates its four phase features for synthetic inputs.
+``time_features`` restates the arithmetic of ``add_time_embeddings`` (embed_utils.py:9-27) on plain arrays
+(the xarray bookkeeping around it is ingest and out of scope).
 """
+import numpy as np
 import torch.nn as nn
+
+
+def time_features(day_of_year, time_of_day):
+    """[time, 4] f64: sin / cos of ``2 pi day_of_year / 365.25`` and of ``2 pi time_of_day / 24`` (hours, fractional), in
+    the order featurePreprocessor.TIME_VARS reads them (embed_utils.py:12-26)."""
+    year = 2 * np.pi * np.asarray(day_of_year) / 365.25
+    day = 2 * np.pi * np.asarray(time_of_day, dtype=np.float64) / 24.0
+    return np.stack([np.sin(year), np.cos(year), np.sin(day), np.cos(day)], axis=-1)
 
 
 class KoppenEmbedding(nn.Module):
