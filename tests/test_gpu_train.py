@@ -287,3 +287,60 @@ def test_adapt_region_checkpoint_contract():
     assert list(out["hybrid_model_state_dict"].keys()) == list(sd.keys())
     assert out["total_params"] == sum(v.numel() for v in sd.values()) and np.isfinite(out["val_loss"])
     _hybrid(cfg, out["hybrid_model_state_dict"])  # loads back into the drop-in classes
+
+
+def test_meta_checkpoint_layout_and_real_resume():
+    """the meta-training checkpoint carries the reference's keys (train_hybrid_maml_v5.py:311-335),
+    its optimiser / scheduler entries load into torch.optim.AdamW / CosineAnnealingWarmRestarts built the reference's way,
+    and a trainer resumed from it continues bit-identically (weights, AdamW moments, step count, learning rate)."""
+    from weatherforecast_stgcn_maml_b200 import checkpoint as ck
+    from weatherforecast_stgcn_maml_b200.embed_utils import KoppenEmbedding
+    from weatherforecast_stgcn_maml_b200.schedule import CosineWarmRestarts
+    from weatherforecast_stgcn_maml_b200.train_hybrid_maml_v5 import MetaTrainer
+
+    z, cfg, sd, feats, ei, dims = _small_cfg()
+    feats2 = synth.synth_features(feats.shape[0], feats.shape[1], 78)
+    tasks = [(feats, ei), (feats2, ei)]
+    kop = KoppenEmbedding(8)
+    mk = lambda state: MetaTrainer(state, tasks, dims, "cuda", support_rows=(0, 1, 2), query_row=3, accum=2)
+    a, sched_a = mk(sd), CosineWarmRestarts(1e-3, 10, 2, 1e-6)
+    for _ in range(3):  # three "epochs" of one meta-step each, the schedule stepped per epoch (:294)
+        a.meta_step()
+        a.set_lr(sched_a.step())
+    ckpt = ck.meta_checkpoint(a, kop.state_dict(), sched_a, epoch=3, best_loss=0.5)
+    assert set(ckpt) == {"hybrid_model_state_dict", "koppen_embed_state_dict", "meta_optimizer_state_dict", "scheduler_state_dict",
+                         "epoch", "best_loss", "model_version", "total_params", "config", "hybrid_config"}
+    assert ckpt["model_version"] == "5.0" and ckpt["total_params"] == sum(v.numel() for v in sd.values())
+    assert ckpt["config"] == {"input_channels": cfg["cin"], "hidden_channels": cfg["hidden"], "output_channels": cfg["out"],
+                              "window_size": cfg["T"], "forecast_horizon": cfg["H"]}
+    assert list(ckpt["hybrid_model_state_dict"]) == list(sd)
+    # survives torch.save / torch.load the way the reference reads it (adapt_hybrid_v5.py:84)
+    import io
+    buf = io.BytesIO()
+    torch.save(ckpt, buf)
+    buf.seek(0)
+    ckpt = torch.load(buf, weights_only=False)
+    # loads into the reference's optimiser and scheduler objects
+    module = _hybrid(cfg, ckpt["hybrid_model_state_dict"])  # same parameter order as the reference's class (SURVEY.md 8b)
+    assert [k for k, _ in module.named_parameters()] == list(sd)
+    opt = torch.optim.AdamW(list(module.parameters()) + list(kop.parameters()), lr=1e-3, weight_decay=1e-4)
+    opt.load_state_dict(ckpt["meta_optimizer_state_dict"])
+    ref_sched = torch.optim.lr_scheduler.CosineAnnealingWarmRestarts(opt, T_0=10, T_mult=2, eta_min=1e-6)
+    ref_sched.load_state_dict({**ref_sched.state_dict(), **ckpt["scheduler_state_dict"]})
+    assert abs(ref_sched.get_last_lr()[0] - sched_a.lr) <= 1e-15
+    n_state = sum(1 for p in module.parameters() if p in opt.state)
+    assert n_state == len(P.trainable(sd))
+    # real resume: a fresh trainer from the ORIGINAL weights, then the checkpoint; both continue for two more epochs
+    b, sched_b = mk(sd), CosineWarmRestarts(1e-3, 10, 2, 1e-6)
+    epoch, best = ck.resume(b, sched_b, ckpt)
+    assert (epoch, best) == (3, 0.5) and b.adam.step_count == 3 and b.adam.lr == a.adam.lr
+    for _ in range(2):
+        la, lb = a.meta_step().item(), b.meta_step().item()
+        assert la == lb
+        a.set_lr(sched_a.step())
+        b.set_lr(sched_b.step())
+    torch.cuda.synchronize()
+    assert torch.equal(a.theta, b.theta) and torch.equal(a.adam.exp_avg, b.adam.exp_avg)
+    assert torch.equal(a.adam.exp_avg_sq, b.adam.exp_avg_sq)
+    with pytest.raises(ValueError):
+        ck.resume(b, sched_b, {**ckpt, "config": {**ckpt["config"], "window_size": 7}})

@@ -151,3 +151,78 @@ def test_denormalisation_and_forecast_metrics():
     assert m["t2m"]["mse"] == pytest.approx(np.mean((a[:, 2] - b[:, 2]) ** 2))
     assert m["sp"]["mae"] == pytest.approx(np.mean(np.abs(a[:, 4] - b[:, 4])))   # sp is channel 4 (featurePreprocessor.py:42-55)
     assert m["average_mse"] == pytest.approx(np.mean([np.mean((a[:, v] - b[:, v]) ** 2) for v in (0, 1, 2, 3, 5)]))
+
+
+def test_scheduler_state_roundtrips_with_torch():
+    """checkpoint.scheduler_state_dict / load_scheduler_state_dict against torch's CosineAnnealingWarmRestarts (the
+    object the reference saves, train_hybrid_maml_v5.py:250-252,318): a state written by either side resumes on the
+    other and the learning rates stay equal."""
+    from weatherforecast_stgcn_maml_b200 import checkpoint as ck
+    from weatherforecast_stgcn_maml_b200.schedule import CosineWarmRestarts
+
+    p = torch.nn.Parameter(torch.zeros(1))
+    opt = torch.optim.AdamW([p], lr=1e-3)
+    ref = torch.optim.lr_scheduler.CosineAnnealingWarmRestarts(opt, T_0=10, T_mult=2, eta_min=1e-6)
+    mine = CosineWarmRestarts(1e-3, 10, 2, 1e-6)
+    for _ in range(13):
+        opt.step(); ref.step(); mine.step()
+    # torch -> here
+    resumed = CosineWarmRestarts(5.0, 3, 1, 0.0)
+    ck.load_scheduler_state_dict(resumed, ref.state_dict())
+    # here -> torch
+    opt2 = torch.optim.AdamW([p], lr=1e-3)
+    ref2 = torch.optim.lr_scheduler.CosineAnnealingWarmRestarts(opt2, T_0=10, T_mult=2, eta_min=1e-6)
+    ref2.load_state_dict({**ref2.state_dict(), **ck.scheduler_state_dict(mine)})
+    for _ in range(25):
+        opt.step(); opt2.step(); ref.step(); ref2.step()
+        a, b = mine.step(), resumed.step()
+        assert abs(a - ref.get_last_lr()[0]) <= 1e-12 and abs(b - a) <= 1e-15 and abs(ref2.get_last_lr()[0] - a) <= 1e-12
+
+
+def test_optimizer_state_dict_loads_into_torch_adamw():
+    """The fused optimiser's flat moments, written in torch.optim.AdamW's state_dict format over the reference's parameter
+    list (hybrid parameters then the Koppen table, train_hybrid_maml_v5.py:245-249), load into a real AdamW; entries land
+    on the right parameters; frozen parameters have no state; the inverse conversion returns the flat buffers; one more
+    torch step from the loaded state equals the AdamW recurrence applied to the flat buffers."""
+    from types import SimpleNamespace
+
+    from weatherforecast_stgcn_maml_b200 import checkpoint as ck, synth
+    from weatherforecast_stgcn_maml_b200.engine import V5Dims, flatten_trainable, trainable_layout
+
+    dims = V5Dims(num_nodes=12, window=6, horizon=2, hidden=32, lstm_hidden=32, lstm_layers=2)
+    sd = synth.init_v5_state_dict(7, hidden=32, lstm_hidden=32, lstm_layers=2, horizon=2)
+    layout = trainable_layout(dims)
+    P = layout[-1][2] + int(torch.Size(layout[-1][1]).numel())
+    g = torch.Generator().manual_seed(1)
+    adam = SimpleNamespace(exp_avg=torch.randn(P, generator=g), exp_avg_sq=torch.rand(P, generator=g), step_count=5, lr=7e-4,
+                           betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-4, decoupled=True)
+    osd = ck.optimizer_state_dict(adam, sd.keys(), dims, num_extra_params=1)
+    names = [n for n, _, _ in layout]
+    keys = list(sd.keys())
+    assert sorted(osd["state"]) == sorted(keys.index(n) for n in names)           # only trainable parameters carry state
+    assert osd["param_groups"][0]["params"] == list(range(len(keys) + 1))          # + embedding.weight
+    params = [torch.nn.Parameter(v.clone().float()) for v in sd.values()] + [torch.nn.Parameter(torch.zeros(31, 8))]
+    opt = torch.optim.AdamW(params, lr=1e-3, weight_decay=1e-4)
+    opt.load_state_dict(osd)
+    assert opt.param_groups[0]["lr"] == 7e-4
+    for n, shape, off in layout:
+        st = opt.state[params[keys.index(n)]]
+        assert float(st["step"]) == 5 and torch.equal(st["exp_avg"].reshape(-1), adam.exp_avg[off:off + st["exp_avg"].numel()])
+    # one torch step from the loaded state == the AdamW recurrence on the flat buffers
+    grads = torch.randn(P, generator=g) * 1e-2
+    theta = flatten_trainable(sd, dims).clone()
+    for n, shape, off in layout:
+        params[keys.index(n)].grad = grads[off:off + int(torch.Size(shape).numel())].view(shape).clone()
+    opt.step()
+    b1, b2, t = 0.9, 0.999, 6
+    m = b1 * adam.exp_avg + (1 - b1) * grads
+    v = b2 * adam.exp_avg_sq + (1 - b2) * grads * grads
+    want = theta * (1 - 7e-4 * 1e-4) - 7e-4 * (m / (1 - b1 ** t)) / ((v / (1 - b2 ** t)).sqrt() + 1e-8)
+    got = torch.cat([params[keys.index(n)].detach().reshape(-1) for n in names])
+    assert float((got - want).abs().max()) <= 1e-6 * float(want.abs().max())
+    # inverse conversion (what a resume does), also from torch's own state_dict
+    back = SimpleNamespace(exp_avg=torch.zeros(P), exp_avg_sq=torch.zeros(P), step_count=0, lr=0.0, betas=None, eps=0.0,
+                           weight_decay=0.0, decoupled=True)
+    ck.load_optimizer_state_dict(back, opt.state_dict(), sd.keys(), dims)
+    assert back.step_count == 6 and back.lr == 7e-4 and tuple(back.betas) == (0.9, 0.999)
+    assert float((back.exp_avg - m).abs().max()) <= 1e-6 and float((back.exp_avg_sq - v).abs().max()) <= 1e-6  # torch lerps

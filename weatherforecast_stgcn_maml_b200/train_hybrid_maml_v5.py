@@ -448,3 +448,18 @@ class MetaTrainer:
         for name, t in unflatten_trainable(self.theta.detach().cpu(), self.dims).items():
             out[name] = t.clone()
         return out
+
+    def load_state_dict(self, state_dict):
+        """Replace the meta-parameters (and the frozen GCN weights) by those of a hybrid ``state_dict``, in place."""
+        missing = [k for k in self.sd if k not in state_dict]
+        if missing:
+            raise KeyError(f"state_dict lacks {missing[:3]}{'...' if len(missing) > 3 else ''}")
+        self.sd = {k: state_dict[k].detach().clone().cpu() for k in self.sd}
+        self.theta.copy_(flatten_trainable(self.sd, self.dims, self.device))
+        for (W, b), (W2, b2) in zip(self.gcn_w, gcn_weights_from_state_dict(self.sd, self.device)):
+            W.copy_(W2)
+            b.copy_(b2)
+        cache = getattr(self.engine, "_gcn_lo", None)  # 16-bit operand staging of the frozen GCN weights (tensor-core path)
+        if cache is not None:
+            cache.clear()
+        self.cuda_graphs = [None, None]                # ... which the captured graphs read: capture again
