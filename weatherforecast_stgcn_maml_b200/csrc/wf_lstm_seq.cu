@@ -14,11 +14,15 @@
 // applies the cell non-linearities and writes its 64 units of h[t] as fp16 hi/lo straight into
 // the A-operand buffer of BOTH CTAs -- the peer's copy as st.async transactions that complete on the
 // peer's mbarrier (no cluster-scope release on the sending warp) -- so the only per-step exchange is
-// the operand itself.
+// the operand itself.  The default kernel (wf_lstm_seq_fwd16_kernel, 16 cell warps) keeps every global
+// store out of the dependent part of a step: results are staged in TMEM and written under the next
+// step's MMA, which is itself issued K step by K step behind the cell mathematics (see the comment on
+// that kernel and DESIGN.md section 4); wf_lstm_seq_fwd_kernel is the first, 8-warp version (WF_SEQ_FWD8=1).
 // Backward (K split): CTA r holds W_hh^T restricted to its own gate rows (128 x 256, 128 KB), keeps
 // its own dG[t+1] (128 x 256) in TMEM as the A operand (TS mode) and produces a partial
 // dh[128 x 128]; the half belonging to the peer's units goes through distributed shared memory
-// (fp32, 32 KB per step as st.async transactions, double buffered).
+// (fp32, 32 KB per step as st.async transactions, double buffered).  The global copies of dG[t] are written
+// after the hand-over, read back from the TMEM operand.
 //
 // Activation layout ("TB4", wf_layout.cuh): per (window, step, 128-node tile) a block of
 // [channels / 4][128 rows][4 floats], so a warp whose lanes are consecutive rows moves 512
