@@ -262,12 +262,11 @@ wf_g16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
         if (!mbar_wait(&full[s], ph) || !mbar_wait(&empty[s], ph ^ 1)) { if (lane == 0) atomicExch(a.err, 34); ok = false; break; }
         uint32_t hi[16], lo[16];
         if (!gather) {
-          const uint8_t* st = smem + s * STAGE + h * 16384;
+          const uint32_t st = smem_u32(smem + s * STAGE + h * 16384);
 #pragma unroll
           for (int ch = 0; ch < 8; ++ch) {
             // TB4 stage: [channel group][row][4 floats]; otherwise a SWIZZLE_128B box of 32 floats per row
-            const uint8_t* p = st + (a.a_tb4 ? ch * 2048 + row * 16 : row * 128 + ((ch ^ (row & 7)) << 4));
-            const float4 v = *reinterpret_cast<const float4*>(p);
+            const float4 v = lds128(st + (a.a_tb4 ? ch * 2048 + row * 16 : row * 128 + ((ch ^ (row & 7)) << 4)));
             if (want_sum) rsum += (v.x + v.y) + (v.z + v.w);
             split_pair<FMT>(v.x, v.y, hi[2 * ch], lo[2 * ch]);
             split_pair<FMT>(v.z, v.w, hi[2 * ch + 1], lo[2 * ch + 1]);

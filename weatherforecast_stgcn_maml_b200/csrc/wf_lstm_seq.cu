@@ -348,8 +348,8 @@ wf_lstm_seq_fwd_kernel(const __grid_constant__ CUtensorMap tmWhi, const __grid_c
             if (ok && !mbar_wait_cl(&peer_done, (t - 1) & 1)) { ok = false; if (lane == 0) atomicExch(a.err, 14); }
           }
           const uint4 vhi = make_uint4(hi[0], hi[1], hi[2], hi[3]), vlo = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-          *reinterpret_cast<uint4*>(a_hi + off) = vhi;
-          *reinterpret_cast<uint4*>(a_lo + off) = vlo;
+          sts128(smem_u32(a_hi + off), vhi);
+          sts128(smem_u32(a_lo + off), vlo);
           st_async_v4(mapa_u32(smem_u32(a_hi + off), peer), vhi, ar_remote);
           st_async_v4(mapa_u32(smem_u32(a_lo + off), peer), vlo, ar_remote);
         }
@@ -614,8 +614,8 @@ wf_lstm_seq_fwd16_kernel(const __grid_constant__ CUtensorMap tmWhi, const __grid
           // acquired here, so a CTA-scope wait: the cluster-scope form costs a CCTL.IVALL per warp and step)
           if (ok && !mbar_wait(&peer_done, (t - 1) & 1)) { ok = false; if (lane == 0) atomicExch(a.err, 14); }
         }
-        *reinterpret_cast<uint2*>(a_hi + off) = make_uint2(h0, h1);
-        *reinterpret_cast<uint2*>(a_lo + off) = make_uint2(l0, l1);
+        sts64(smem_u32(a_hi + off), h0, h1);
+        sts64(smem_u32(a_lo + off), l0, l1);
         st_async_v2(mapa_u32(smem_u32(a_hi + off), peer), h0, h1, ar_remote + 8u * c);
         st_async_v2(mapa_u32(smem_u32(a_lo + off), peer), l0, l1, ar_remote + 8u * c);
         // K step c of h[t] is complete in this warp: my generic-proxy operand writes -> visible to the tensor core
@@ -844,8 +844,8 @@ wf_lstm_seq_bwd_kernel(const __grid_constant__ CUtensorMap tmWhi, const __grid_c
           __syncwarp();
           tmem_ld8(tlane + 64 * rank + ub + 8 * c, v);
           tmem_wait_ld();
-          const uint8_t* src = xbuf + xb * 32768 + ((half * 8 + 2 * c) * 128 + r) * 16;
-          const float4 p0 = *reinterpret_cast<const float4*>(src), p1 = *reinterpret_cast<const float4*>(src + 2048);
+          const uint32_t src = smem_u32(xbuf + xb * 32768 + ((half * 8 + 2 * c) * 128 + r) * 16);
+          const float4 p0 = lds128(src), p1 = lds128(src + 2048);
           dh[0] = __uint_as_float(v[0]) + p0.x; dh[1] = __uint_as_float(v[1]) + p0.y;
           dh[2] = __uint_as_float(v[2]) + p0.z; dh[3] = __uint_as_float(v[3]) + p0.w;
           dh[4] = __uint_as_float(v[4]) + p1.x; dh[5] = __uint_as_float(v[5]) + p1.y;
