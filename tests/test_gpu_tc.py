@@ -68,7 +68,7 @@ def _run16(rows_g, G, K, N, fmt, bias=False, relu=False, seed=0, scale=1.0):
 
 
 @pytest.mark.parametrize("rows_g,G,K,N", [(128, 1, 64, 128), (441, 1, 128, 512), (300, 3, 256, 256), (1000, 2, 128, 128),
-                                          (10584, 2, 256, 512), (70000, 1, 64, 128)])
+                                          (10584, 2, 256, 512), (20000, 1, 256, 256), (70000, 1, 64, 128), (40000, 1, 128, 384)])
 def test_g16_gemm_matches_fp64(rows_g, G, K, N):
     """Persistent 16-bit hi/lo GEMM: fp16 split ~2^-20, bf16 split ~2^-16 (many tiles per CTA at the larger sizes)."""
     assert _run16(rows_g, G, K, N, 0) <= 5e-6
