@@ -217,7 +217,7 @@ int wf_launch_gemm_nn(const GemmArgs& a, int groups, bool csr, cudaStream_t st) 
 int wf_tn_splits(int M, int N, int K, int groups) {
   long long tiles = (long long)wf_cdiv(M, WF_BM) * wf_cdiv(N, WF_BN) * groups;
   long long want = (296 + tiles - 1) / tiles;
-  long long maxs = K / 256;
+  long long maxs = K / 64;  // >= 64 rows of K per split (the head gradient has K = Bw * N = 441 and 15 tiles)
   if (maxs < 1) maxs = 1;
   if (want > maxs) want = maxs;
   if (want > 64) want = 64;

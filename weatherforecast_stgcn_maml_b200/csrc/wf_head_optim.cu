@@ -11,34 +11,49 @@
 #include "wf_gemm.cuh"
 
 // ------------------------------------------------------------------ MSE
-// One CTA per window.  Targets either come from an explicit y buffer [G*Bw, N*O] or are read in
+// One cluster of CTAs per window.  Targets either come from an explicit y buffer [G*Bw, N*O] or are read in
 // place from the resident features tensor: y_flat[(h*N + n)*nw + c] = feat[tgt_off[w] + h*N*feat_ld
 // + n*feat_ld + c], tgt_off[w] = element offset of features[idx + W + 1, 0, 0] (dataset.py:40-44).
-__global__ void wf_mse_kernel(const float* __restrict__ pred, const float* __restrict__ y,
-                              const float* __restrict__ feat, const long long* __restrict__ tgt_off, int feat_ld,
-                              int N, int O, int nw, float grad_scale, float* __restrict__ dpred,
-                              float* __restrict__ loss) {
+// One cluster of MSE_CTAS blocks per window (a single block per window left 133 SMs idle for 32 us): every block sums a
+// slice, the partial sums meet in rank 0's shared memory through DSMEM and are added in rank order (deterministic).
+constexpr int MSE_CTAS = 8, MSE_THREADS = 256;
+__global__ void __cluster_dims__(MSE_CTAS, 1, 1) __launch_bounds__(MSE_THREADS)
+wf_mse_kernel(const float* __restrict__ pred, const float* __restrict__ y, const float* __restrict__ feat,
+              const long long* __restrict__ tgt_off, int feat_ld, int N, int O, int nw, float grad_scale,
+              float* __restrict__ dpred, float* __restrict__ loss) {
   __shared__ float sh[33];
-  const int w = blockIdx.x;
-  const long long per = (long long)N * O;
-  const float* p = pred + w * per;
+  __shared__ float part[MSE_CTAS];
+  const int w = blockIdx.x / MSE_CTAS, rank = blockIdx.x % MSE_CTAS;
+  const int per = N * O;
+  const float* p = pred + (long long)w * per;
   const float inv = 1.0f / (float)per;
+  const long long toff = y ? 0 : tgt_off[w];
   float s = 0.f;
-  for (long long i = threadIdx.x; i < per; i += blockDim.x) {
+  for (int i = rank * MSE_THREADS + threadIdx.x; i < per; i += MSE_CTAS * MSE_THREADS) {
     float t;
     if (y) {
-      t = y[w * per + i];
+      t = y[(long long)w * per + i];
     } else {
-      long long ry = i / nw;
-      int c = (int)(i - ry * nw);
-      t = feat[tgt_off[w] + ry * feat_ld + c];  // ry = h*N + n and time rows are N*feat_ld apart
+      const int ry = i / nw, c = i - ry * nw;
+      t = feat[toff + (long long)ry * feat_ld + c];  // ry = h*N + n and time rows are N*feat_ld apart
     }
-    float d = p[i] - t;
+    const float d = p[i] - t;
     s = fmaf(d, d, s);
-    if (dpred) dpred[w * per + i] = 2.0f * d * inv * grad_scale;
+    if (dpred) dpred[(long long)w * per + i] = 2.0f * d * inv * grad_scale;
   }
   s = block_sum(s, sh);
-  if (threadIdx.x == 0) loss[w] = s * inv;
+  if (threadIdx.x == 0) {  // partial -> rank 0's shared memory
+    uint32_t local = (uint32_t)__cvta_generic_to_shared(&part[rank]), remote;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;\n" : "=r"(remote) : "r"(local), "r"(0));
+    asm volatile("st.shared::cluster.f32 [%0], %1;\n" ::"r"(remote), "f"(s) : "memory");
+  }
+  asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+  if (rank == 0 && threadIdx.x == 0) {
+    float tot = 0.f;
+    for (int r = 0; r < MSE_CTAS; ++r) tot += part[r];
+    loss[w] = tot * inv;
+  }
 }
 
 static void head_offsets(int layers, int F, int L, int O, long long* hw, long long* hb) {
@@ -84,8 +99,9 @@ extern "C" int wf_mse_fwd_bwd(const float* pred, const float* y, const float* fe
                               float* loss, float* dpred, void* stream) {
   WF_REQUIRE(y != nullptr || (feat != nullptr && tgt_off != nullptr), "mse: no targets given");
   WF_REQUIRE(num_weather > 0 && O % num_weather == 0 && windows > 0, "mse: bad dims");
-  wf_mse_kernel<<<windows, 1024, 0, (cudaStream_t)stream>>>(pred, y, feat, tgt_off, feat_ld, N, O, num_weather,
-                                                            grad_scale, dpred, loss);
+  WF_REQUIRE((long long)N * O < (1LL << 31), "mse: N * O must fit 32 bits");
+  wf_mse_kernel<<<windows * MSE_CTAS, MSE_THREADS, 0, (cudaStream_t)stream>>>(pred, y, feat, tgt_off, feat_ld, N, O,
+                                                                              num_weather, grad_scale, dpred, loss);
   WF_CHECK_LAUNCH("mse");
   return WF_OK;
 }
