@@ -257,6 +257,11 @@ int wf_lstm_seq_recur_bwd(float* gates_l, const float* c_l, float* dgT, const fl
                           const void* b16_hi, const void* b16_lo, int layer, int layers, int L, int T, int N, int G,
                           int Bw, int* err, void* stream);
 
+/* Nodes per node tile of the TB4 activation layout (<= 128 rows per tile in memory; the N nodes of a window are dealt
+ * evenly over ceil(N / 128) tiles, rounded up to 8: 441 -> 112).  Node n of a window lives in tile n / wf_tile_rows(N),
+ * row n % wf_tile_rows(N). */
+int wf_tile_rows(int N);
+
 /* ---- feature assembly: prepare_model_input, featurePreprocessor.py:84-177 ----
  * weather: device f32 [time * N, 12] (time-major rows, the reference's reshape at :121-122), may hold NaN.
  * wf_feature_stats: per variable the NaN fill value (f32 nanmean, 0 if all NaN; :104-109), the mean and the population

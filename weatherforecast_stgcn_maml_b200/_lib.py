@@ -63,6 +63,7 @@ SIGNATURES = {
     "wf_tc_wgrad": (c_i, [c_p, c_i, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_p, c_ll, c_p, c_p]),
     "wf_split_lo": (c_i, [c_p, c_p, c_ll, c_p]),
     "wf_tb4_elems": (c_ll, [c_i, c_i, c_i, c_ll]),
+    "wf_tile_rows": (c_i, [c_i]),
     "wf_seq_weight_elems": (c_ll, [c_i, c_i, c_i]),
     "wf_param_stride16": (c_ll, [c_i, c_i, c_i, c_i, c_i]),
     "wf_split16": (c_i, [c_p, c_p, c_p, c_ll, c_i, c_p]),

@@ -40,7 +40,7 @@ struct G16Args {
   int rows_g, a_group_rows;          // ROWS: valid rows per group / row stride between groups in the A map
   const long long* a_win_off;        // ROWS, optional: element offset of every window (g*Bw + w) in A -- windows read in place
   int win_tiles;                     //   from a resident features tensor (dataset.py:36-37); tiles per window
-  int Bw, R, Nn, T, tpw, Np, RT;
+  int Bw, R, Nn, T, tpw, rpt, Np, RT;  // rpt: nodes per TB4 node tile (wf_tile_rows)
   int nkb, nseg, nkb_split;          // k-blocks (64 wide) per segment; segments (wgrad: windows); split-K slice
   int a_k0, b_k0;
   int b_gmul;                        // 0: B shared by all groups
@@ -109,7 +109,7 @@ __device__ __forceinline__ TileCoord decode_tile(const G16Args& a, int tile) {
     c.a_row = c.g * a.a_group_rows + c.mt * 128;
   } else if (a.mode == G16_NODES) {
     const int ztl = c.mt / a.tpw, nt = c.mt - ztl * a.tpw;
-    c.node0 = nt * 128;
+    c.node0 = nt * a.rpt;
     c.zt = c.g * a.Bw * a.T + ztl;
     c.blk = c.zt * a.tpw + nt;
     c.a_row = c.node0;
@@ -460,6 +460,17 @@ void g16_defaults(G16Args& a) {
 // for TMA whatever T is.
 int wf_np(int N) { return (N + 7) & ~7; }
 
+// Nodes per TB4 node tile.  A window's N nodes occupy ceil(N / 128) tiles of 128 ROWS each in memory; the nodes are dealt
+// evenly (rounded up to 8) instead of 128 per tile with a short last one: 441 nodes = 4 x 112 (- 7), so every CTA of the
+// recurrence kernels moves 12.5 % fewer bytes per step and none waits for a full-tile neighbour.  Rows >= wf_tile_rows of
+// a tile are padding: never read as data, written only by GEMM epilogues that store whole tiles.
+extern "C" int wf_tile_rows(int N) {
+  const int tiles = (N + 127) / 128;
+  if (tiles <= 0) return 128;
+  const int r = (((N + tiles - 1) / tiles) + 7) & ~7;
+  return r < 128 ? r : 128;
+}
+
 // G groups of n values each; group g reads src + g*src_gstride and writes hi/lo + g*dst_gstride (elements).
 int wf_launch_split16(const float* src, long long src_gstride, void* hi, void* lo, long long dst_gstride, long long n, int G,
                       int fmt, cudaStream_t st) {
@@ -555,7 +566,7 @@ int wf_launch_g16_nodes(int fmt, const float* A, int a_tb4, int K, const void* W
   if ((rc = map16(&tmBlo, Wlo, K, N, G, ldb, G > 1 ? b_gstride : (long long)N * ldb, fmt))) return rc;
   G16Args a;
   g16_defaults(a);
-  a.mode = G16_NODES; a.tpw = tpw; a.a_tb4 = a_tb4; a.m_tiles = Bw * T * tpw; a.n_tiles = N / 128; a.G = G;
+  a.mode = G16_NODES; a.tpw = tpw; a.rpt = wf_tile_rows(Nn); a.a_tb4 = a_tb4; a.m_tiles = Bw * T * tpw; a.n_tiles = N / 128; a.G = G;
   a.Bw = Bw; a.T = T; a.Nn = Nn; a.nkb = K / 64;
   a.C = C; a.c_cols = N; a.bias = bias; a.bias2 = bias2; a.bias_gstride = bias_gstride; a.err = err;
   return g16_launch(fmt, tmA, tmBhi, tmBlo, a, st);

@@ -47,6 +47,7 @@ int wf_launch_split16(const float* src, long long src_gstride, void* hi, void* l
 int wf_launch_transpose_split16(const float* in, long long in_gstride, int rows, int cols, void* out_hi, void* out_lo,
                                 long long out_gstride, int G, cudaStream_t st);
 int wf_np(int N);
+extern "C" int wf_tile_rows(int N);
 
 namespace {
 
@@ -64,7 +65,7 @@ struct SeqArgs {
   float* DGT;         // bwd out: transposed dG [(z)][4L][RT]
   const float* ext;   // bwd: dL/dh from above -- TB4 (L channels), or row-major dlast [Z*Nn, L] if ext_last_only
   int ext_last_only;
-  int T, Nn, Bw, tpw, Np, RT;
+  int T, Nn, Bw, tpw, rpt, Np, RT;  // rpt: nodes per node tile (wf_tile_rows)
   int slab0, slab_g;  // weight map z coordinate = slab0 + g * slab_g (+ rank in the backward kernel)
   int* err;
 };
@@ -164,7 +165,7 @@ wf_lstm_seq_fwd_kernel(const __grid_constant__ CUtensorMap tmWhi, const __grid_c
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t rank = cluster_rank(), peer = rank ^ 1u;
   const int tile = blockIdx.x >> 1;
-  const int z = tile / a.tpw, nt = tile - z * a.tpw, node0 = nt * 128, g = z / a.Bw;
+  const int z = tile / a.tpw, nt = tile - z * a.tpw, node0 = nt * a.rpt, g = z / a.Bw;
   const int T = a.T;
 
   if (tid == 0) {
@@ -196,7 +197,7 @@ wf_lstm_seq_fwd_kernel(const __grid_constant__ CUtensorMap tmWhi, const __grid_c
     const int ub = half * 32;               // first of this thread's 32 units inside the CTA's 64
     const int u0 = 64 * (int)rank + ub;     // ... as a global hidden-unit index
     const int node = node0 + r;
-    const bool valid = node < a.Nn;
+    const bool valid = r < a.rpt && node < a.Nn;
     const uint32_t tlane = tbase + ((uint32_t)(q * 32) << 16);
     const long long R = (long long)T * a.Nn;
     float4* const xg4 = reinterpret_cast<float4*>(a.XG);
@@ -447,7 +448,7 @@ wf_lstm_seq_fwd16_kernel(const __grid_constant__ CUtensorMap tmWhi, const __grid
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t rank = cluster_rank(), peer = rank ^ 1u;
   const int tile = blockIdx.x >> 1;
-  const int z = tile / a.tpw, nt = tile - z * a.tpw, node0 = nt * 128, g = z / a.Bw;
+  const int z = tile / a.tpw, nt = tile - z * a.tpw, node0 = nt * a.rpt, g = z / a.Bw;
   const int T = a.T;
 
   if (tid == 0) {
@@ -481,7 +482,7 @@ wf_lstm_seq_fwd16_kernel(const __grid_constant__ CUtensorMap tmWhi, const __grid
   const int ub = ug * 4;                  // chunk c: units 16 c + ub .. + 4 of the CTA's 64, so that ALL warps finish
   const int u0 = 64 * (int)rank + ub;     // K step c of h[t] together and MMA[t+1] can start behind chunk 0
   const int node = node0 + r;
-  const bool valid = node < a.Nn;
+  const bool valid = r < a.rpt && node < a.Nn;
   const uint32_t tlane = tbase + ((uint32_t)(q * 32) << 16) + (uint32_t)ub;
   const long long R = (long long)T * a.Nn;
   float4* const xg4 = reinterpret_cast<float4*>(a.XG);
@@ -500,7 +501,8 @@ wf_lstm_seq_fwd16_kernel(const __grid_constant__ CUtensorMap tmWhi, const __grid
   };
   auto load_chunk = [&](int t, int c, float4* dst) {
 #pragma unroll
-    for (int gate = 0; gate < 4; ++gate) dst[gate] = xg4[xg_index(t, c, gate)];
+    for (int gate = 0; gate < 4; ++gate)  // padding rows of a tile: no traffic
+      dst[gate] = valid ? xg4[xg_index(t, c, gate)] : make_float4(0.f, 0.f, 0.f, 0.f);
   };
   load_chunk(0, 0, xq[0]);
   load_chunk(0, 1, xq[1]);
@@ -656,13 +658,13 @@ wf_lstm_seq_fwd16_kernel(const __grid_constant__ CUtensorMap tmWhi, const __grid
         }
         hidden4(go, dc, hh);
       }
-#pragma unroll
-      for (int gate = 0; gate < 4; ++gate)
-        xg4[xg_index(t, c, gate)] = make_float4(__uint_as_float(gt[gate][0]), __uint_as_float(gt[gate][1]),
-                                                __uint_as_float(gt[gate][2]), __uint_as_float(gt[gate][3]));
-      c4[(blk * 32 + (u0 >> 2) + 4 * c) * 128 + r] = make_float4(cst[4 * c], cst[4 * c + 1], cst[4 * c + 2], cst[4 * c + 3]);
-      if (a.h_tb4) reinterpret_cast<float4*>(a.H)[(blk * 32 + (u0 >> 2) + 4 * c) * 128 + r] = make_float4(hh[0], hh[1], hh[2], hh[3]);
       if (valid) {
+#pragma unroll
+        for (int gate = 0; gate < 4; ++gate)
+          xg4[xg_index(t, c, gate)] = make_float4(__uint_as_float(gt[gate][0]), __uint_as_float(gt[gate][1]),
+                                                  __uint_as_float(gt[gate][2]), __uint_as_float(gt[gate][3]));
+        c4[(blk * 32 + (u0 >> 2) + 4 * c) * 128 + r] = make_float4(cst[4 * c], cst[4 * c + 1], cst[4 * c + 2], cst[4 * c + 3]);
+        if (a.h_tb4) reinterpret_cast<float4*>(a.H)[(blk * 32 + (u0 >> 2) + 4 * c) * 128 + r] = make_float4(hh[0], hh[1], hh[2], hh[3]);
         if (!a.h_tb4) *reinterpret_cast<float4*>(a.H + hrow + 16 * c) = make_float4(hh[0], hh[1], hh[2], hh[3]);
         if (a.HT != nullptr) {
           __nv_bfloat16* ht = a.HT + ((long long)z * L + u0 + 16 * c) * a.RT + tcol;
@@ -702,7 +704,7 @@ wf_lstm_seq_bwd_kernel(const __grid_constant__ CUtensorMap tmWhi, const __grid_c
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t rank = cluster_rank(), peer = rank ^ 1u;
   const int tile = blockIdx.x >> 1;
-  const int z = tile / a.tpw, nt = tile - z * a.tpw, node0 = nt * 128, g = z / a.Bw;
+  const int z = tile / a.tpw, nt = tile - z * a.tpw, node0 = nt * a.rpt, g = z / a.Bw;
   const int T = a.T;
 
   if (tid == 0) {
@@ -731,7 +733,7 @@ wf_lstm_seq_bwd_kernel(const __grid_constant__ CUtensorMap tmWhi, const __grid_c
     const int ub = half * 32;
     const int u0 = 64 * (int)rank + ub;
     const int node = node0 + r;
-    const bool valid = node < a.Nn;
+    const bool valid = r < a.rpt && node < a.Nn;
     const float vm = valid ? 1.0f : 0.0f;
     const uint32_t tlane = tbase + ((uint32_t)(q * 32) << 16);
     float4* const xg4 = reinterpret_cast<float4*>(a.XG);
@@ -750,6 +752,11 @@ wf_lstm_seq_bwd_kernel(const __grid_constant__ CUtensorMap tmWhi, const __grid_c
     auto load_chunk = [&](int t, int c, float4* dst) {
       const long long blk = blk_of(t);
       const int uq = (u0 + 8 * c) >> 2;
+      if (!valid) {  // padding rows of a tile: no traffic, zero gates (their dG is masked by vm anyway)
+#pragma unroll
+        for (int i2 = 0; i2 < 14; ++i2) dst[i2] = make_float4(0.f, 0.f, 0.f, 0.f);
+        return;
+      }
 #pragma unroll
       for (int gate = 0; gate < 4; ++gate) {
         dst[gate * 2] = xg4[(blk * 128 + gate * 32 + uq) * 128 + r];
@@ -921,13 +928,13 @@ wf_lstm_seq_bwd_kernel(const __grid_constant__ CUtensorMap tmWhi, const __grid_c
           }
         }
         const int uq = (u0 + 8 * c) >> 2;
-#pragma unroll
-        for (int gate = 0; gate < 4; ++gate)
-#pragma unroll
-          for (int hsel = 0; hsel < 2; ++hsel)
-            xg4[(blk * 128 + gate * 32 + uq + hsel) * 128 + r] =
-                make_float4(v[gate][4 * hsel], v[gate][4 * hsel + 1], v[gate][4 * hsel + 2], v[gate][4 * hsel + 3]);
         if (valid) {
+#pragma unroll
+          for (int gate = 0; gate < 4; ++gate)
+#pragma unroll
+            for (int hsel = 0; hsel < 2; ++hsel)
+              xg4[(blk * 128 + gate * 32 + uq + hsel) * 128 + r] =
+                  make_float4(v[gate][4 * hsel], v[gate][4 * hsel + 1], v[gate][4 * hsel + 2], v[gate][4 * hsel + 3]);
 #pragma unroll
           for (int jj = 0; jj < 8; ++jj) {
             float* base = a.DGT + ((long long)z * 4 * L + u0 + 8 * c + jj) * a.RT + tcol;
@@ -1086,7 +1093,7 @@ extern "C" int wf_lstm_fwd_seq(const float* x, const float* params, const void* 
     memset(&a, 0, sizeof(a));
     a.XG = XG; a.Cst = c + l * c_elems; a.H = h + (long long)l * c_elems; a.h_tb4 = l + 1 < layers ? 1 : 0;
     a.HT = hT_hi ? (__nv_bfloat16*)hT_hi + l * tsz : nullptr; a.HT_lo = hT_hi ? (__nv_bfloat16*)hT_lo + l * tsz : nullptr;
-    a.T = T; a.Nn = N; a.Bw = Bw; a.tpw = tpw; a.Np = Np; a.RT = RT;
+    a.T = T; a.Nn = N; a.Bw = Bw; a.tpw = tpw; a.rpt = wf_tile_rows(N); a.Np = Np; a.RT = RT;
     a.slab0 = l; a.slab_g = layers; a.err = err;
     static const bool fwd16 = getenv("WF_SEQ_FWD8") == nullptr;  // WF_SEQ_FWD8=1: the first-generation 8-warp kernel (A/B timing)
     if (fwd16) {
@@ -1143,7 +1150,7 @@ extern "C" int wf_lstm_bwd_seq(const void* xT_hi, const void* xT_lo, const void*
     memset(&a, 0, sizeof(a));
     a.XG = XG; a.Cst = const_cast<float*>(c) + l * c_elems; a.DGT = dgT;
     a.ext = l == layers - 1 ? dlast : DX; a.ext_last_only = l == layers - 1 ? 1 : 0;
-    a.T = T; a.Nn = N; a.Bw = Bw; a.tpw = tpw; a.Np = Np; a.RT = RT;
+    a.T = T; a.Nn = N; a.Bw = Bw; a.tpw = tpw; a.rpt = wf_tile_rows(N); a.Np = Np; a.RT = RT;
     a.slab0 = 2 * l; a.slab_g = 2 * layers; a.err = err;
     wf_lstm_seq_bwd_kernel<<<dim3((unsigned)(2 * Z * tpw)), SEQ_THREADS, SEQ_SMEM, st>>>(tmhi, tmlo, a);
     WF_CHECK_LAUNCH("lstm_seq_bwd");
@@ -1185,7 +1192,7 @@ extern "C" int wf_lstm_seq_recur_fwd(float* gates_l, float* c_l, float* h_l, voi
   memset(&a, 0, sizeof(a));
   a.XG = gates_l; a.Cst = c_l; a.H = h_l; a.h_tb4 = layer + 1 < layers ? 1 : 0;
   a.HT = (__nv_bfloat16*)hT_hi_l; a.HT_lo = (__nv_bfloat16*)hT_lo_l;
-  a.T = T; a.Nn = N; a.Bw = Bw; a.tpw = wf_cdiv(N, 128); a.Np = wf_np(N); a.RT = T * a.Np;
+  a.T = T; a.Nn = N; a.Bw = Bw; a.tpw = wf_cdiv(N, 128); a.rpt = wf_tile_rows(N); a.Np = wf_np(N); a.RT = T * a.Np;
   a.slab0 = layer; a.slab_g = layers; a.err = err;
   static const bool fwd16 = getenv("WF_SEQ_FWD8") == nullptr;
   if (fwd16) {
@@ -1211,7 +1218,7 @@ extern "C" int wf_lstm_seq_recur_bwd(float* gates_l, const float* c_l, float* dg
   SeqArgs a;
   memset(&a, 0, sizeof(a));
   a.XG = gates_l; a.Cst = const_cast<float*>(c_l); a.DGT = dgT; a.ext = ext; a.ext_last_only = ext_is_dlast ? 1 : 0;
-  a.T = T; a.Nn = N; a.Bw = Bw; a.tpw = wf_cdiv(N, 128); a.Np = wf_np(N); a.RT = T * a.Np;
+  a.T = T; a.Nn = N; a.Bw = Bw; a.tpw = wf_cdiv(N, 128); a.rpt = wf_tile_rows(N); a.Np = wf_np(N); a.RT = T * a.Np;
   a.slab0 = 2 * layer; a.slab_g = 2 * layers; a.err = err;
   wf_lstm_seq_bwd_kernel<<<dim3((unsigned)(2 * Z * a.tpw)), SEQ_THREADS, SEQ_SMEM, (cudaStream_t)stream>>>(tmhi, tmlo, a);
   WF_CHECK_LAUNCH("lstm_seq_recur_bwd");

@@ -188,8 +188,10 @@ class HybridEngine:
             if l == Ls - 1:
                 out[l] = self.h[l, :self.rows * L].view(self.rows, L)
             else:  # TB4: [window, step, node tile, L/4, 128 rows, 4]
+                rpt = int(_lib.query("wf_tile_rows", d.num_nodes))  # nodes per tile; rows beyond are padding
                 t = self.h[l].view(self.W, d.window, tpw, L // 4, 128, 4).permute(0, 1, 2, 4, 3, 5)
-                out[l] = t.reshape(self.W, d.window, tpw * 128, L)[:, :, :d.num_nodes].reshape(self.rows, L)
+                t = t.reshape(self.W, d.window, tpw, 128, L)[:, :, :, :rpt]
+                out[l] = t.reshape(self.W, d.window, tpw * rpt, L)[:, :, :d.num_nodes].reshape(self.rows, L)
         return out
 
     def check(self):
