@@ -271,7 +271,7 @@ def stage_breakdown(trainer, reps=3):
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernels from `ncu --set full`
 # (profiles/r1b_ncu_summary.md); None until a capture of the current kernels is committed
-NCU_TRAFFIC = {"wf_lstm_seq_fwd16_kernel": 973.1e6, "wf_lstm_seq_bwd_kernel": 1233.8e6}
+NCU_TRAFFIC = {"wf_lstm_seq_fwd16_kernel": 851.1e6, "wf_lstm_seq_bwd_kernel": 1109.3e6}
 
 
 def time_recurrence_kernels(trainer, reps=10):
