@@ -338,7 +338,7 @@ wf_g16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
             if (b1) { const float4 b = __ldg(reinterpret_cast<const float4*>(b1 + cc + j)); o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w; }
             if (b2) { const float4 b = __ldg(reinterpret_cast<const float4*>(b2 + cc + j)); o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w; }
             if (a.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
-            cblk[(long long)((cc + j) >> 2) * 128] = o;
+            if (row < a.rpt) cblk[(long long)((cc + j) >> 2) * 128] = o;  // rows >= rpt of a node tile are padding
           }
         }
       } else {
