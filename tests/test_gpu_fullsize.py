@@ -158,3 +158,25 @@ def test_config4_large_graph_full_hybrid_pass():
     a, r = unflatten_trainable(g1[0], dims), unflatten_trainable(g0[0], dims)
     for kk in a:
         assert rel_err(a[kk], r[kk]) <= 1e-3, (kk, rel_err(a[kk], r[kk]))
+
+
+@pytest.mark.parametrize("nlat,nlon,G,Bw", [(21, 21, 15, 1), (3, 43, 2, 2)])
+def test_repeated_passes_are_bit_identical(nlat, nlon, G, Bw):
+    """The hybrid pass has no atomics on data and reduces in fixed orders, so repeated runs must be BIT-identical: a race
+    in the persistent kernels' barrier protocols (cluster hand-over, TMEM staging, distributed MMA issue) would show up as
+    a differing bit (tools/determinism_stress.py runs the long version)."""
+    from weatherforecast_stgcn_maml_b200.engine import HybridEngine
+
+    dims, ei, base, sds, feats, starts, xo, to, theta, graphs, gcn_w = _setup(nlat, nlon, 8, G, Bw)
+    fd = feats.cuda()
+    eng = HybridEngine(dims, G, Bw, "cuda")
+    first = None
+    for _ in range(8):
+        loss, grads = eng.forward_backward(fd, 24, 0, xo, gcn_w, graphs, theta, eng.P, feat=fd, tgt_off=to, feat_ld=24)
+        eng.check()
+        cur = (eng.pred.clone(), loss.clone(), grads.clone())
+        if first is None:
+            first = cur
+        else:
+            assert all(torch.equal(a, b) for a, b in zip(first, cur))
+    assert torch.isfinite(first[2]).all()
