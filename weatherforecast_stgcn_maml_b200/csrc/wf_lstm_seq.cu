@@ -699,7 +699,7 @@ wf_lstm_seq_bwd_kernel(const __grid_constant__ CUtensorMap tmWhi, const __grid_c
   uint8_t* b_hi = smem;            // [4 k-blocks][128 unit rows][128 B]
   uint8_t* b_lo = smem + 65536;
   uint8_t* xbuf = smem + 131072;   // 2 x [2 halves][8 quads][128 rows][16 B]: the peer's partial dh for my units
-  __shared__ uint64_t wfull, a_ready, dfull, x_ready[2];
+  __shared__ uint64_t wfull, a_ready, issued, dfull, x_ready[2];
   __shared__ uint32_t tmem_base_s;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t rank = cluster_rank(), peer = rank ^ 1u;
@@ -708,7 +708,7 @@ wf_lstm_seq_bwd_kernel(const __grid_constant__ CUtensorMap tmWhi, const __grid_c
   const int T = a.T;
 
   if (tid == 0) {
-    mbar_init(&wfull, 1); mbar_init(&a_ready, 8); mbar_init(&dfull, 1); mbar_init(&x_ready[0], 1); mbar_init(&x_ready[1], 1);  // 1 = the expect_tx arrival; data = 32 KB of st.async
+    mbar_init(&wfull, 1); mbar_init(&a_ready, 8); mbar_init(&dfull, 2); mbar_init(&issued, 1); mbar_init(&x_ready[0], 1); mbar_init(&x_ready[1], 1);  // 1 = the expect_tx arrival; data = 32 KB of st.async
     mbar_fence_init();
     tma_prefetch_desc(&tmWhi); tma_prefetch_desc(&tmWlo);
   }
@@ -786,28 +786,34 @@ wf_lstm_seq_bwd_kernel(const __grid_constant__ CUtensorMap tmWhi, const __grid_c
     };
     load_chunk(T - 1, 0, ld[0]);
 
-    // MMA of step s (warp 0): partial dh[128 x 128] = dG[t+1][:, my gate rows] W_hh[my gate rows, :]; also arms the barrier
-    // on which the peer's partial dh for my units will arrive as st.async transactions (phase (s - 1) / 2 of x_ready[s & 1])
-    auto issue_mma = [&](int s) {
-      if (lane == 0) mbar_expect_tx(&x_ready[s & 1], 32768);
+    // MMA of step s: partial dh[128 x 128] = dG[t+1][:, my gate rows] W_hh[my gate rows, :], 48 instructions.  tcgen05.mma
+    // blocks the issuing thread for about as long as the queued instructions run, and the issuer is a cell warp with its
+    // own deferred stores still to do, so the work is split: warp 0 issues the k-blocks of gates i, f right after the
+    // hand-over, warp 4 (the other warp on TMEM lanes 0-31) those of g, o after the first half of ITS stores, chained
+    // through `issued` so that they enter the pipe in order; both commit on dfull (count 2).  Warp 0 also arms the barrier
+    // on which the peer's partial dh for my units will arrive as st.async transactions (phase (s - 1) / 2 of x_ready[s & 1]).
+    auto issue_mma = [&](int s, int part) {
+      if (part == 0 && lane == 0) mbar_expect_tx(&x_ready[s & 1], 32768);
       if (ok && s == 1 && !mbar_wait(&wfull, 0)) { ok = false; if (lane == 0) atomicExch(a.err, 21); }
       if (ok && !mbar_wait(&a_ready, (s - 1) & 1)) { ok = false; if (lane == 0) atomicExch(a.err, 22); }
+      if (part == 1 && ok && !mbar_wait(&issued, (s - 1) & 1)) { ok = false; if (lane == 0) atomicExch(a.err, 25); }
       tc_fence_after();
       if (lane == 0 && ok) {
         const uint32_t idesc = idesc_16(128, 1);
-        uint32_t accf = 0;
 #pragma unroll
         for (int p = 0; p < 3; ++p) {  // dG_hi W_hi, dG_lo W_hi, dG_hi W_lo
           const uint32_t ac = tbase + (p == 1 ? A_LO : A_HI), bs = smem_u32(p == 2 ? b_lo : b_hi);
 #pragma unroll
-          for (int kb = 0; kb < 4; ++kb)
+          for (int kk = 0; kk < 2; ++kk) {
+            const int kb = 2 * part + kk;
 #pragma unroll
-            for (int k16 = 0; k16 < 4; ++k16) {
-              umma_ts_16(tbase, ac + kb * 32 + k16 * 8, umma_desc_k_sw128(bs + kb * 16384 + k16 * 32), idesc, accf);
-              accf = 1;
-            }
+            for (int k16 = 0; k16 < 4; ++k16)
+              umma_ts_16(tbase, ac + kb * 32 + k16 * 8, umma_desc_k_sw128(bs + kb * 16384 + k16 * 32), idesc,
+                         (part | p | kk | k16) != 0 ? 1u : 0u);
+          }
         }
         umma_commit(&dfull);
+        if (part == 0) { tc_fence_before(); mbar_arrive(&issued); }
       }
       __syncwarp();
     };
@@ -906,7 +912,7 @@ wf_lstm_seq_bwd_kernel(const __grid_constant__ CUtensorMap tmWhi, const __grid_c
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&a_ready);
-        if (warp == 0) issue_mma(s + 1);
+        if (warp == 0) issue_mma(s + 1, 0);  // the first half of the MMA before warp 0's own stores
         WF_TRS(8);  // warp 0 feeds the tensor core first, then stores like everybody else
       }
       // ---- deferred stores of step t (under MMA[s+1]): dG in place (TB4) and transposed fp32 for the weight gradients
@@ -942,6 +948,7 @@ wf_lstm_seq_bwd_kernel(const __grid_constant__ CUtensorMap tmWhi, const __grid_c
             for (int gate = 0; gate < 4; ++gate) base[(long long)gate * L * a.RT] = v[gate][jj];
           }
         }
+        if (c == 1 && warp == 4 && s + 1 < T) issue_mma(s + 1, 1);  // the second half, between warp 4's store halves
       }
       WF_TRS(9);
     }
