@@ -226,3 +226,14 @@ def test_optimizer_state_dict_loads_into_torch_adamw():
     ck.load_optimizer_state_dict(back, opt.state_dict(), sd.keys(), dims)
     assert back.step_count == 6 and back.lr == 7e-4 and tuple(back.betas) == (0.9, 0.999)
     assert float((back.exp_avg - m).abs().max()) <= 1e-6 and float((back.exp_avg_sq - v).abs().max()) <= 1e-6  # torch lerps
+
+
+def test_feature_assembly_has_no_cpu_fallback():
+    """The product path fails loudly without a CUDA tensor (no silent numpy / torch fallback)."""
+    from weatherforecast_stgcn_maml_b200.featurePreprocessor import assemble_features, feature_stats
+
+    w = torch.zeros(4, 3, 12)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        feature_stats(w)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        assemble_features(w, np.zeros((4, 4), dtype=np.float32), np.zeros(8, dtype=np.float32))
