@@ -344,7 +344,7 @@ def roofline_report(stages, kernel_ms, G, peak, peak_src):
             "graph_conv_note": "256->256 GCN layer incl. the pre-aggregation pass; the last layer also writes transposed copies"}
 
 
-def finetune_windows_per_sec(sd, dims, steps=96, warmup=16):
+def finetune_windows_per_sec(sd, dims, steps=96, warmup=16, dropout=(0.0, 0.0, 0.0)):
     """configs[2] shape (regional adaptation, adapt_hybrid_v5.py:185-203): batch-1 Adam steps on one 441-node region,
     windows visited in a shuffled order; device-timed.  Sequential by construction (one optimiser step per window), so
     this is a latency number: 8 CTAs per LSTM launch."""
@@ -356,7 +356,8 @@ def finetune_windows_per_sec(sd, dims, steps=96, warmup=16):
 
     lats, lons, feats, _ = synth.synth_task(7, num_windows=steps + warmup + 8, nlat=NLAT, nlon=NLON)
     ei = knn_edge_index_device(lats, lons, KNN, "cuda")
-    ft = FineTuner(sd, feats, ei, dims, "cuda", region_name="bench", max_samples=steps + warmup, train_frac=1.0)
+    ft = FineTuner(sd, feats, ei, dims, "cuda", region_name="bench", max_samples=steps + warmup, train_frac=1.0,
+                   dropout=dropout)
     order = torch.randperm(steps + warmup, generator=torch.Generator().manual_seed(0)).tolist()
     for i in order[:warmup]:
         ft.step(i)
@@ -391,7 +392,9 @@ def run_gpu(args, rank, local, world):
     dims = V5Dims(num_nodes=NLAT * NLON)
     sd = synth.init_v5_state_dict(42)
     tasks = build_tasks(rank, world)
-    kw = dict(support_rows=SUPPORT_ROWS, accum=TASKS_PER_GPU * world)
+    # headline = the deterministic parity configuration (dropout off); the reference's training
+    # configuration (p = 0.2 at its three sites) is measured beside it as `dropout_on`
+    kw = dict(support_rows=SUPPORT_ROWS, accum=TASKS_PER_GPU * world, dropout=(0.0, 0.0, 0.0))
 
     # ---- headline: device-resident, CUDA-graphed
     tr = MetaTrainer(sd, tasks, dims, "cuda", use_cuda_graph=True, **kw)

@@ -70,16 +70,19 @@ int wf_gcn_layer_bwd(const float* X, int x_ld, long long x_win_stride, const lon
 
 /* nn.LSTM(F -> L, `layers`, batch_first) over every (task, window, node) sequence
  * (hybrid_model.py:42-49, 93-105).  x [G*Bw*R, F]; gates [layers][G*Bw*R,4L],
- * h, c [layers][G*Bw*R, L] are outputs kept for BPTT. */
+ * h, c [layers][G*Bw*R, L] are outputs kept for BPTT.  p_drop > 0: inter-layer dropout
+ * (hybrid_model.py:47) with the masks of wf_dropout_apply (site 16 + layer); h_masked
+ * [layers-1][G*Bw*R, L] receives the masked outputs the next layer reads (kept for BPTT). */
 int wf_lstm_fwd(const float* x, const float* params, long long params_group_stride, int layers,
                 int F, int L, int O, int T, int N, int G, int Bw, float* gates, float* h, float* c,
-                void* stream);
+                float p_drop, const unsigned long long* rng, float* h_masked, void* stream);
 
 /* BPTT (loss.backward(): train_hybrid_maml_v5.py:134,169; adapt_hybrid_v5.py:198). */
 size_t wf_lstm_bwd_workspace_bytes(int layers, int F, int L, int T, int N, int G, int Bw);
 int wf_lstm_bwd(const float* x, const float* params, long long params_group_stride, int layers,
                 int F, int L, int O, int T, int N, int G, int Bw, float* gates, const float* h,
                 const float* c, const float* dlast, float* grads, long long grads_group_stride,
+                float p_drop, const unsigned long long* rng, const float* h_masked,
                 void* workspace, size_t workspace_bytes, void* stream);
 
 /* Linear head (hybrid_model.py:108-115): pred[G*Bw*N, O] = h_top[last step] W_o^T + b_o.
@@ -195,6 +198,12 @@ long long wf_seq_weight_elems(int layers, int L, int G);
 /* fp32 -> 16-bit hi / lo operand halves (fmt 0: fp16, 1: bf16): hi = rn(x), lo = rn(x - hi); n % 4 == 0. */
 int wf_split16(const float* src, void* hi, void* lo, long long n, int fmt, void* stream);
 
+/* X [windows*T*N, C] row-major f32 -> bf16 hi / lo transposed copies [windows][C][RT16] (column (t, node) = t*Np + node):
+ * the layer-0 input operand xT of wf_lstm_bwd_seq for features that did not come out of wf_gcn_layer_fwd_g16 (the drop-in
+ * nn.Module path, hybrid_model.py:80-117, hands the LSTM any features tensor).  Padding columns are not written. */
+int wf_transpose_split16_rows(const float* X, int T, int N, int C, int windows, void* out_hi, void* out_lo,
+                              void* stream);
+
 /* Row pitch RT16 of the 16-bit transposed activation copies [(G*Bw)][channels][RT16] and of the fp32 dG^T
  * scratch that pairs with them: column (t, node) = t*Np + node, Np = N rounded up to 8.  Padding columns zero. */
 long long wf_transposed_pitch16(int T, int N);
@@ -212,12 +221,16 @@ int wf_g16_gemm_nt(const float* A, int rows_g, int G, int K, const void* W16_hi,
  * gather_rows (optional, i32 [G][gather_max], -1 padded): rows of a window whose aggregation is not the unit self
  * loop; with agg (scratch f32 [G*Bw*R, Cin]) they are aggregated by a pre-pass instead of inside the GEMM.
  * x_win_off (optional): element offset of every window in X = a resident features tensor with x_rows_total rows of
- * Cin floats (dataset.py:36-37: a window is a contiguous slice); Cin % 8 == 0 suffices then (needs gather_rows + agg). */
+ * Cin floats (dataset.py:36-37: a window is a contiguous slice); Cin % 8 == 0 suffices then (needs gather_rows + agg).
+ * p_drop > 0: nn.Dropout after the ReLU (hybrid_model.py:67-73, model.py:33-42) fused into the epilogue, masks of
+ * wf_dropout_apply for site `site` (the layer index) over Y [G*Bw*R, Cout].  err is also set (code 41) when an output
+ * reaches the fp16 operand range limit of the next layer (|y| >= 32768 or non-finite). */
 int wf_gcn_layer_fwd_g16(const float* X, const long long* x_win_off, long long x_rows_total,
                          const void* W16_hi, const void* W16_lo, const float* bias, const int* rowptr, const int* col, const float* val, long long rowptr_group_stride,
                          long long csr_group_stride, const int* gather_rows, int gather_max,
                          long long gather_group_stride, float* agg, int R, int N, int Cin, int Cout, int G, int Bw,
-                         int relu, float* Y, void* YT_hi, void* YT_lo, int* err, void* stream);
+                         int relu, float* Y, void* YT_hi, void* YT_lo, float p_drop,
+                         const unsigned long long* rng, int site, int* err, void* stream);
 
 /* Group stride (16-bit elements) of the p16 (which = 0) / pT16 (which = 1) buffers below: the parameter counts
  * rounded up to 8 so that every group starts 16-byte aligned. */
@@ -232,11 +245,14 @@ int wf_prep_weights_seq(const float* params, long long params_group_stride, int 
 
 /* nn.LSTM forward (hybrid_model.py:42-49, 93-105).  x [G*Bw*T*N, F] row-major; gates (4L channels) and c
  * (L channels) are TB4, [layers] of them; h is [layers][wf_tb4_elems(L, T, N, G*Bw)]: the TOP layer row-major
- * [G*Bw*T*N, L] (what the head reads), the layers below TB4; hT hi/lo optional (bf16). */
+ * [G*Bw*T*N, L] (what the head reads), the layers below TB4; hT hi/lo optional (bf16).
+ * p_drop > 0: inter-layer dropout (hybrid_model.py:47) applied by the recurrence kernel to what the next layer reads
+ * (site 16 + layer, element ((z*T + t)*N + node)*L + unit); hTm hi/lo [layers-1][...]: transposed copies of the masked h. */
 int wf_lstm_fwd_seq(const float* x, const float* params, const void* p16_hi, const void* p16_lo,
                     long long params_group_stride, const void* f16_hi, const void* f16_lo, int layers,
                     int F, int L, int O, int T, int N, int G, int Bw, float* gates, float* h, float* c,
-                    void* hT_hi, void* hT_lo, int* err, void* stream);
+                    void* hT_hi, void* hT_lo, float p_drop, const unsigned long long* rng,
+                    void* hTm_hi, void* hTm_lo, int* err, void* stream);
 
 /* BPTT (train_hybrid_maml_v5.py:134,169; adapt_hybrid_v5.py:198) over the buffers of wf_lstm_fwd_seq;
  * gates are overwritten with dL/d(pre-activation).  xT hi/lo: bf16 transposed layer-0 input [(G*Bw)][F][RT16]
@@ -246,6 +262,7 @@ int wf_lstm_bwd_seq(const void* xT_hi, const void* xT_lo, const void* pT16_hi, c
                     const void* b16_hi, const void* b16_lo, int layers, int F, int L, int O, int T, int N,
                     int G, int Bw, float* gates, const float* c, const void* hT_hi, const void* hT_lo,
                     float* dgT, const float* dlast, float* grads, long long grads_group_stride,
+                    float p_drop, const unsigned long long* rng, const void* hTm_hi, const void* hTm_lo,
                     void* workspace, size_t workspace_bytes, int* err, void* stream);
 
 /* Single-layer recurrence launches (the persistent kernels wf_lstm_fwd_seq / wf_lstm_bwd_seq issue per layer), for
@@ -261,6 +278,18 @@ int wf_lstm_seq_recur_bwd(float* gates_l, const float* c_l, float* dgT, const fl
  * evenly over ceil(N / 128) tiles, rounded up to 8: 441 -> 112).  Node n of a window lives in tile n / wf_tile_rows(N),
  * row n % wf_tile_rows(N). */
 int wf_tile_rows(int N);
+
+/* ---- dropout (hybrid_model.py:47,58,67-73,108; model.py:27,33-42) ---------------------------------------------------
+ * Counter-based masks (Philox4x32-10, csrc/wf_rng.cuh): element e of site s in forward pass c is kept with probability
+ * 1 - p and scaled by 1 / (1 - p); nothing is stored, backward kernels regenerate the mask.  rng: two device words
+ * {seed, pass counter}.  Sites: GCN layer i = i, LSTM layer l output = 16 + l, head input = 32.
+ * wf_dropout_apply: out[r, c] = in[row r][c] * mask(site, r*cols + c); input row r lives at
+ * in + (r / rows_per_blk)*in_blk_stride + (r % rows_per_blk)*in_ld; out dense [rows, cols] (may alias a dense input).
+ * Applied to ones it returns the mask itself (tests). */
+int wf_dropout_apply(const float* in, long long in_blk_stride, int rows_per_blk, int in_ld, long long rows,
+                     int cols, float p, const unsigned long long* rng, int site, float* out, void* stream);
+/* rng[1] += 1 on the stream (after a forward + backward pair): fresh masks for the next pass, also under graph replay. */
+int wf_rng_advance(unsigned long long* rng, void* stream);
 
 /* ---- feature assembly: prepare_model_input, featurePreprocessor.py:84-177 ----
  * weather: device f32 [time * N, 12] (time-major rows, the reference's reshape at :121-122), may hold NaN.

@@ -93,22 +93,27 @@ def gcn_conv(x, edge_index, weight, bias):
     return out + bias
 
 
-def gcn_stack(sd, x, edge_index, prefix="base_stgcn."):
-    """hybrid_model.py:60-78 / model.py:31-42 with dropout off: 4 x relu(GCNConv)."""
+def gcn_stack(sd, x, edge_index, prefix="base_stgcn.", masks=None):
+    """hybrid_model.py:60-78 / model.py:31-42: 4 x relu(GCNConv), each followed by nn.Dropout when ``masks`` gives
+    the layer a keep-mask already scaled by 1/(1-p) (``F.dropout(h) == h * mask``); None / missing entries = no dropout
+    (eval mode, or the hybrid path's last layer :76)."""
     h = x
     for i in range(1, 5):
         h = torch.relu(gcn_conv(h, edge_index, sd[f"{prefix}conv{i}.lin.weight"], sd[f"{prefix}conv{i}.bias"]))
+        if masks is not None and i - 1 < len(masks) and masks[i - 1] is not None:
+            h = h * masks[i - 1]
     return h
 
 
 # --------------------------------------------------------------------------- LSTM + head
-def lstm_last_hidden(sd, seq, num_layers, prefix="lstm."):
+def lstm_last_hidden(sd, seq, num_layers, prefix="lstm.", masks=None):
     """torch.nn.LSTM(batch_first, zero initial state) restated cell by cell.
 
     hybrid_model.py:42-49 (definition) and :93-105 (use): gates ordered i, f, g, o;
     c = f*c + i*g; h = o*tanh(c); returns the top layer's h at the last step,
     i.e. ``lstm_out[:, -1, :]``.  ``seq`` is [batch, T, F]: the reference feeds one node
-    at a time (batch 1); batching over nodes is the same arithmetic per row.
+    at a time (batch 1); batching over nodes is the same arithmetic per row.  ``masks[l]`` ([batch, T, hid], scaled
+    keep-mask): nn.LSTM's inter-layer dropout on the output of layer l < num_layers - 1 (hybrid_model.py:47).
     """
     inp = seq
     for l in range(num_layers):
@@ -125,23 +130,32 @@ def lstm_last_hidden(sd, seq, num_layers, prefix="lstm."):
             h = torch.sigmoid(o) * torch.tanh(c)
             outs.append(h)
         inp = torch.stack(outs, dim=1)
+        if masks is not None and l < num_layers - 1 and masks[l] is not None:
+            inp = inp * masks[l]
     return inp[:, -1]
 
 
-def hybrid_forward(sd, x, edge_index, window, horizon=8, out_channels=12, lstm_layers=4):
-    """hybrid_model.py:80-117 in eval mode (dropout off).  Returns f32[N*horizon, out]."""
+def hybrid_forward(sd, x, edge_index, window, horizon=8, out_channels=12, lstm_layers=4, masks=None):
+    """hybrid_model.py:80-117.  ``masks`` = None: eval mode (dropout off).  Train mode with KNOWN masks (each already
+    scaled by 1/(1-p)): {"gcn": [3 x [T*N, hidden]] (:67-73), "lstm": [layers-1 x [N, T, L]] (:47), "head": [N, L] (:108)}.
+    Returns f32[N*horizon, out]."""
+    masks = masks or {}
     with torch.no_grad():  # hybrid_model.py:63 -- unconditional, even when not frozen (D4)
-        feats = gcn_stack({k: v.detach() for k, v in sd.items() if k.startswith("base_stgcn.")}, x, edge_index)
+        feats = gcn_stack({k: v.detach() for k, v in sd.items() if k.startswith("base_stgcn.")}, x, edge_index,
+                          masks=masks.get("gcn"))
     n = feats.shape[0] // window
     seq = feats.view(window, n, -1).permute(1, 0, 2)  # :89-90
-    last = lstm_last_hidden(sd, seq, lstm_layers)  # :93-105
+    last = lstm_last_hidden(sd, seq, lstm_layers, masks=masks.get("lstm"))  # :93-105
+    if masks.get("head") is not None:
+        last = last * masks["head"]  # :108
     pred = last @ sd["output_layer.weight"].t() + sd["output_layer.bias"]  # :111
     return pred.view(n, horizon, out_channels).reshape(-1, out_channels)  # :114-115 (row = node*H + h)
 
 
-def stgcn_forward(sd, x, edge_index, window, horizon=8, out_channels=12, prefix=""):
-    """model.py:30-52 in eval mode: differentiable 4 x GCN, last N rows, Linear head."""
-    h = gcn_stack(sd, x, edge_index, prefix=prefix)
+def stgcn_forward(sd, x, edge_index, window, horizon=8, out_channels=12, prefix="", masks=None):
+    """model.py:30-52: differentiable 4 x GCN (+ dropout after each when ``masks`` lists four scaled keep-masks; None =
+    eval mode), last N rows, Linear head."""
+    h = gcn_stack(sd, x, edge_index, prefix=prefix, masks=masks)
     n = h.shape[0] // window
     h = h[-n:]
     out = h @ sd[f"{prefix}output_layer.weight"].t() + sd[f"{prefix}output_layer.bias"]
@@ -179,13 +193,13 @@ def clip_grad_norm(grads, max_norm=1.0):
     return total
 
 
-def loss_and_grads(sd, x, y, edge_index, window, horizon=8, scale=1.0, lstm_layers=4):
+def loss_and_grads(sd, x, y, edge_index, window, horizon=8, scale=1.0, lstm_layers=4, masks=None):
     """forward + nn.MSELoss + backward (train_hybrid_maml_v5.py:132-134, 166-169).
 
     Returns (loss, {name: grad}) over the 18 tensors autograd reaches (D4)."""
     names = trainable(sd)
     leaf = {k: (v.detach().clone().requires_grad_(True) if k in names else v.detach()) for k, v in sd.items()}
-    pred = hybrid_forward(leaf, x, edge_index, window, horizon, y.shape[1], lstm_layers)
+    pred = hybrid_forward(leaf, x, edge_index, window, horizon, y.shape[1], lstm_layers, masks=masks)
     loss = F.mse_loss(pred, y) * scale
     grads = torch.autograd.grad(loss, [leaf[k] for k in names])
     return loss.detach(), dict(zip(names, grads)), pred.detach()

@@ -21,7 +21,7 @@ def test_library_exports_every_symbol():
     lib = _lib.load()
     for name in parse_header():
         assert hasattr(lib, name), name
-    assert lib.wf_abi_version() == 1
+    assert lib.wf_abi_version() == 2
 
 
 def test_param_count_matches_reference_model():

@@ -13,6 +13,18 @@ pytestmark = pytest.mark.gpu
 FWD_TOL, GRAD_TOL = 1e-4, 1e-3
 
 
+@pytest.fixture(params=["tf32x3", "fp32"])
+def precision(request):
+    """The drop-in modules on both kernel families: tcgen05 (16-bit hi/lo operand splits, what the benchmark runs,
+    taken whenever the shapes allow) and exact FP32 CUDA cores."""
+    from weatherforecast_stgcn_maml_b200 import functional as WF
+
+    WF.set_precision(request.param)
+    yield request.param
+    WF.check()
+    WF.set_precision("tf32x3")
+
+
 def _models(cfg, sd, dropout=0.0):
     from weatherforecast_stgcn_maml_b200.hybrid_model import HybridSTGCN_LSTM
     from weatherforecast_stgcn_maml_b200.model import STGCN
@@ -28,7 +40,7 @@ def _models(cfg, sd, dropout=0.0):
 
 @pytest.mark.parametrize("relu", [False, True])
 @pytest.mark.parametrize("cin,cout", [(24, 256), (256, 256), (24, 32), (40, 72)])
-def test_gcn_layer_forward(relu, cin, cout):
+def test_gcn_layer_forward(relu, cin, cout, precision):
     from weatherforecast_stgcn_maml_b200 import functional as WF
     from weatherforecast_stgcn_maml_b200.graph import RegionGraph
 
@@ -43,11 +55,12 @@ def test_gcn_layer_forward(relu, cin, cout):
     ref = torch.relu(ref) if relu else ref
     g = RegionGraph(ei, T * n, "cuda")
     got = WF.gcn_conv(x.cuda(), W.cuda(), b.cuda(), g, relu=relu)
-    assert rel_err(got, ref) <= 1e-5
+    tol = 1e-5 if precision == "fp32" or cout % 128 else 2e-5  # fp16 hi/lo operand split: ~2^-20 per product
+    assert rel_err(got, ref) <= tol
     # rows >= N see only their self loop: out = x W^T + b
     lin = x[n:] @ W.t() + b
     lin = torch.relu(lin) if relu else lin
-    assert rel_err(got[n:], lin) <= 1e-5
+    assert rel_err(got[n:], lin) <= tol
 
 
 def test_gcn_layer_edges_at_every_row():
@@ -64,7 +77,7 @@ def test_gcn_layer_edges_at_every_row():
 
 
 @pytest.mark.parametrize("name", ["hybrid_small", "hybrid_v5_k4", "hybrid_v5_k8"])
-def test_hybrid_forward_and_backward_vs_reference_fixture(name):
+def test_hybrid_forward_and_backward_vs_reference_fixture(name, precision):
     z, cfg, sd, feats, ei = golden_case(name)
     T, H = cfg["T"], cfg["H"]
     hyb = _models(cfg, sd)
@@ -89,7 +102,7 @@ def test_hybrid_forward_and_backward_vs_reference_fixture(name):
 
 
 @pytest.mark.parametrize("name", ["hybrid_small", "hybrid_v5_k4"])
-def test_stgcn_forward_backward_vs_reference_fixture(name):
+def test_stgcn_forward_backward_vs_reference_fixture(name, precision):
     """model.py:30-52 end to end: the only differentiable use of the graph convolution (D4)."""
     from weatherforecast_stgcn_maml_b200.model import STGCN
 
@@ -111,7 +124,7 @@ def test_stgcn_forward_backward_vs_reference_fixture(name):
     check_summary(xs.grad, z["stgcn_dx_summary"], z["stgcn_dx_samples"], GRAD_TOL, "dx")
 
 
-def test_stgcn_backward_general_graph_vs_oracle():
+def test_stgcn_backward_general_graph_vs_oracle(precision):
     """dX = A_hat^T path with real neighbour mixing in every layer (window_size = 1 -> all rows have edges)."""
     from weatherforecast_stgcn_maml_b200.model import STGCN
 

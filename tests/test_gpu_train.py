@@ -93,7 +93,7 @@ def test_inner_loop_and_fomaml_vs_reference_fixture():
     z, cfg, sd, feats, ei = golden_case("hybrid_v5_k4")
     dims = V5Dims(num_nodes=441)
     steps, accum = int(z["inner_steps"]), int(z["accum"])
-    mt = MetaTrainer(sd, [(feats, ei)], dims, "cuda", support_rows=tuple(range(steps)), query_row=steps,
+    mt = MetaTrainer(sd, [(feats, ei)], dims, "cuda", dropout=(0, 0, 0), support_rows=tuple(range(steps)), query_row=steps,
                      inner_lr=float(z["inner_lr"]), accum=accum, use_cuda_graph=False)
     loss = mt.meta_step()
     torch.cuda.synchronize()
@@ -135,7 +135,7 @@ def test_meta_trainer_two_tasks_vs_oracle_with_and_without_graph():
             cur[k] = p.detach().clone()
         ref_losses.append(tot)
     for use_graph in (False, True):
-        mt = MetaTrainer(sd, tasks, dims, "cuda", support_rows=(0, 1, 2), query_row=3, accum=2,
+        mt = MetaTrainer(sd, tasks, dims, "cuda", dropout=(0, 0, 0), support_rows=(0, 1, 2), query_row=3, accum=2,
                          use_cuda_graph=use_graph)
         got = [mt.meta_step().item() for _ in range(2)]
         torch.cuda.synchronize()
@@ -238,7 +238,7 @@ def test_fine_tune_steps_and_validation_vs_oracle():
     names = P.trainable(sd)
     order = [3, 0, 5, 1, 7, 2]
     for use_graph in (False, True):
-        ft = FineTuner(sd, feats, ei, dims, "cuda", region_name="Thailand", max_samples=n_win, train_frac=0.8,
+        ft = FineTuner(sd, feats, ei, dims, "cuda", dropout=(0, 0, 0), region_name="Thailand", max_samples=n_win, train_frac=0.8,
                        use_cuda_graph=use_graph, val_batch=2)
         assert ft.train_size == int(0.8 * n_win) and abs(ft.initial_lr - 0.0006 * 0.9) < 1e-12
         avg = ft.train_epoch(order)
@@ -302,7 +302,7 @@ def test_meta_checkpoint_layout_and_real_resume():
     feats2 = synth.synth_features(feats.shape[0], feats.shape[1], 78)
     tasks = [(feats, ei), (feats2, ei)]
     kop = KoppenEmbedding(8)
-    mk = lambda state: MetaTrainer(state, tasks, dims, "cuda", support_rows=(0, 1, 2), query_row=3, accum=2)
+    mk = lambda state: MetaTrainer(state, tasks, dims, "cuda", dropout=(0, 0, 0), support_rows=(0, 1, 2), query_row=3, accum=2)
     a, sched_a = mk(sd), CosineWarmRestarts(1e-3, 10, 2, 1e-6)
     for _ in range(3):  # three "epochs" of one meta-step each, the schedule stepped per epoch (:294)
         a.meta_step()

@@ -41,6 +41,6 @@ rt = int(_lib.query("wf_transposed_pitch16", T, N))
 YT = torch.zeros(G * 256 * rt, dtype=torch.int16, device="cuda"); YTl = torch.zeros_like(YT)
 AGG = torch.empty(rows, 256, device="cuda")
 for ct, pre in ((False, False), (False, True), (True, True)):
-    t = timeit(lambda: _lib.call("wf_gcn_layer_fwd_g16", _lib.ptr(A), None, 0, _lib.ptr(hi), _lib.ptr(lo), _lib.ptr(b), _lib.ptr(graphs.rowptr), _lib.ptr(graphs.col), _lib.ptr(graphs.val), graphs.rowptr_stride, graphs.csr_stride, _lib.ptr(graphs.gather_rows) if pre else None, graphs.gather_max, graphs.gather_rows.shape[1], _lib.ptr(AGG), R, N, 256, 256, G, 1, 1, _lib.ptr(Y), _lib.ptr(YT) if ct else None, _lib.ptr(YTl) if ct else None, _lib.ptr(err), st))
+    t = timeit(lambda: _lib.call("wf_gcn_layer_fwd_g16", _lib.ptr(A), None, 0, _lib.ptr(hi), _lib.ptr(lo), _lib.ptr(b), _lib.ptr(graphs.rowptr), _lib.ptr(graphs.col), _lib.ptr(graphs.val), graphs.rowptr_stride, graphs.csr_stride, _lib.ptr(graphs.gather_rows) if pre else None, graphs.gather_max, graphs.gather_rows.shape[1], _lib.ptr(AGG), R, N, 256, 256, G, 1, 1, _lib.ptr(Y), _lib.ptr(YT) if ct else None, _lib.ptr(YTl) if ct else None, 0.0, None, 0, _lib.ptr(err), st))
     print(f"gcn layer (CSR, bias, relu, transposed={ct}, pre-aggregation={pre}): {t:7.1f} us")
 print("err flag", int(err.item()))

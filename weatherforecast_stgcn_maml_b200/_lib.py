@@ -34,10 +34,10 @@ SIGNATURES = {
     "wf_gcn_layer_bwd": (c_i, [c_p, c_i, c_ll, c_p, c_p, c_p, c_p, c_ll, c_p, c_p, c_p, c_p, c_p, c_p,
                                c_ll, c_ll, c_i, c_i, c_i, c_i, c_i, c_i, c_p, c_p, c_p, c_ll, c_ll,
                                c_p, c_sz, c_p]),
-    "wf_lstm_fwd": (c_i, [c_p, c_p, c_ll, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_p, c_p, c_p, c_p]),
+    "wf_lstm_fwd": (c_i, [c_p, c_p, c_ll, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_p, c_p, c_p, c_f, c_p, c_p, c_p]),
     "wf_lstm_bwd_workspace_bytes": (c_sz, [c_i, c_i, c_i, c_i, c_i, c_i, c_i]),
     "wf_lstm_bwd": (c_i, [c_p, c_p, c_ll, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_p, c_p, c_p, c_p, c_p,
-                          c_ll, c_p, c_sz, c_p]),
+                          c_ll, c_f, c_p, c_p, c_p, c_sz, c_p]),
     "wf_head_fwd": (c_i, [c_p, c_p, c_ll, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_p, c_p]),
     "wf_mse_fwd_bwd": (c_i, [c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_f, c_p, c_p, c_p]),
     "wf_head_workspace_bytes": (c_sz, [c_i, c_i, c_i, c_i, c_i]),
@@ -50,6 +50,8 @@ SIGNATURES = {
     "wf_feature_stats_workspace_bytes": (c_sz, [c_ll]),
     "wf_feature_stats": (c_i, [c_p, c_ll, c_p, c_p, c_p, c_p, c_p, c_sz, c_p]),
     "wf_assemble_features": (c_i, [c_p, c_ll, c_i, c_p, c_p, c_p, c_i, c_i, c_p, c_p, c_p, c_p]),
+    "wf_dropout_apply": (c_i, [c_p, c_ll, c_i, c_i, c_ll, c_i, c_f, c_p, c_i, c_p, c_p]),
+    "wf_rng_advance": (c_i, [c_p, c_p]),
     "wf_param_count_transposed": (c_ll, [c_i, c_i, c_i, c_i]),
     "wf_prep_weights_tc": (c_i, [c_p, c_ll, c_i, c_i, c_i, c_i, c_i, c_p, c_p, c_p, c_p]),
     "wf_transposed_pitch": (c_ll, [c_i, c_i]),
@@ -68,15 +70,16 @@ SIGNATURES = {
     "wf_param_stride16": (c_ll, [c_i, c_i, c_i, c_i, c_i]),
     "wf_split16": (c_i, [c_p, c_p, c_p, c_ll, c_i, c_p]),
     "wf_transposed_pitch16": (c_ll, [c_i, c_i]),
+    "wf_transpose_split16_rows": (c_i, [c_p, c_i, c_i, c_i, c_i, c_p, c_p, c_p]),
     "wf_g16_gemm_nt": (c_i, [c_p, c_i, c_i, c_i, c_p, c_p, c_ll, c_i, c_p, c_p, c_ll, c_i, c_i, c_p, c_p, c_p]),
     "wf_gcn_layer_fwd_g16": (c_i, [c_p, c_p, c_ll, c_p, c_p, c_p, c_p, c_p, c_p, c_ll, c_ll, c_p, c_i, c_ll, c_p, c_i, c_i, c_i, c_i,
-                                   c_i, c_i, c_i, c_p, c_p, c_p, c_p, c_p]),
+                                   c_i, c_i, c_i, c_p, c_p, c_p, c_f, c_p, c_i, c_p, c_p]),
     "wf_prep_weights_seq": (c_i, [c_p, c_ll, c_i, c_i, c_i, c_i, c_i, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p]),
     "wf_lstm_fwd_seq": (c_i, [c_p, c_p, c_p, c_p, c_ll, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_p, c_p, c_p,
-                              c_p, c_p, c_p, c_p]),
+                              c_p, c_p, c_f, c_p, c_p, c_p, c_p, c_p]),
     "wf_lstm_bwd_seq_workspace_bytes": (c_sz, [c_i, c_i, c_i, c_i, c_i, c_i, c_i]),
     "wf_lstm_bwd_seq": (c_i, [c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_p, c_p, c_p,
-                              c_p, c_p, c_p, c_p, c_ll, c_p, c_sz, c_p, c_p]),
+                              c_p, c_p, c_p, c_p, c_ll, c_f, c_p, c_p, c_p, c_p, c_sz, c_p, c_p]),
     "wf_tc_gemm_nt": (c_i, [c_p, c_i, c_i, c_i, c_p, c_p, c_ll, c_i, c_p, c_p, c_ll, c_i, c_p, c_p, c_p]),
     "wf_lstm_seq_recur_fwd": (c_i, [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_p, c_p]),
     "wf_lstm_seq_recur_bwd": (c_i, [c_p, c_p, c_p, c_p, c_i, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_p, c_p]),

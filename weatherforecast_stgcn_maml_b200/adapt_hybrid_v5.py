@@ -22,8 +22,8 @@ import torch
 
 from . import _lib
 from .adaptive_scheduler import ClimateAwareLRScheduler, climate_hyperparameters
-from .engine import (AdamState, HybridEngine, V5Dims, flatten_trainable, gcn_weights_from_state_dict,
-                     unflatten_trainable)
+from .engine import (REFERENCE_DROPOUT, AdamState, HybridEngine, V5Dims, flatten_trainable, gcn_weights_from_state_dict,
+                     raise_on_error_code, unflatten_trainable)
 from .graph import RegionGraph
 
 EPOCHS = 15  # adapt_hybrid_v5.py:185
@@ -31,7 +31,11 @@ EPOCHS = 15  # adapt_hybrid_v5.py:185
 
 class FineTuner:
     def __init__(self, state_dict, features, edge_index, dims: V5Dims, device="cuda", region_name="",
-                 base_lr=0.0006, max_samples=1200, train_frac=0.8, use_cuda_graph=True, val_batch=16):
+                 base_lr=0.0006, max_samples=1200, train_frac=0.8, use_cuda_graph=True, val_batch=16,
+                 dropout=REFERENCE_DROPOUT, seed=0):
+        """``dropout`` = (p_gcn, p_lstm, p_head): the reference fine-tunes in ``.train()`` mode (adapt_hybrid_v5.py:168)
+        on a model rebuilt with ``dropout_rate=0.2`` and the checkpoint's ``lstm_dropout`` (:99-117); validation runs in
+        ``.eval()`` mode (:214).  Pass ``(0, 0, 0)`` for the deterministic parity configuration."""
         self.dims, self.device = dims, torch.device(device)
         d = dims
         self.features = features.to(self.device, torch.float32).contiguous()
@@ -43,7 +47,7 @@ class FineTuner:
         self.sd = {k: v.detach().clone() for k, v in state_dict.items()}
         self.theta = flatten_trainable(self.sd, d, self.device)
         self.gcn_w = gcn_weights_from_state_dict(self.sd, self.device)
-        self.engine = HybridEngine(d, 1, 1, self.device)
+        self.engine = HybridEngine(d, 1, 1, self.device, dropout=dropout, seed=seed)
         self.P = self.engine.P
         lr, wd = climate_hyperparameters(region_name, base_lr)
         self.initial_lr = lr
@@ -56,6 +60,7 @@ class FineTuner:
         self.cur_x = torch.zeros(1, dtype=torch.long, device=self.device)
         self.cur_t = torch.zeros(1, dtype=torch.long, device=self.device)
         self.loss_sum = torch.zeros(1, dtype=torch.float32, device=self.device)
+        self.err_seen = torch.zeros(1, dtype=torch.int32, device=self.device)  # kernel error flags, read with the loss
         self.use_graph, self.graph = bool(use_cuda_graph), None
         self.val_batch = val_batch
         self._val_engine = None
@@ -67,6 +72,7 @@ class FineTuner:
         e.forward_backward(self.features, C, 0, self.cur_x, self.gcn_w, self.graph_csr, self.theta, 0,
                            feat=self.features, tgt_off=self.cur_t, feat_ld=C, grad_scale=1.0)
         self.loss_sum += e.loss
+        self.err_seen.copy_(torch.maximum(self.err_seen, e.err))
 
     def step(self, window_index):
         """One batch-1 training step on window ``window_index`` (adapt_hybrid_v5.py:193-201)."""
@@ -99,7 +105,16 @@ class FineTuner:
         self.loss_sum.zero_()
         for i in order:
             self.step(int(i))
-        return float(self.loss_sum.item()) / max(1, len(order))
+        total = float(self.loss_sum.item())
+        self.check()
+        return total / max(1, len(order))
+
+    def check(self):
+        """Raise if a kernel flagged an error since the last check (read at points that synchronise anyway)."""
+        code = max(int(self.err_seen.item()), int(self.engine.err.item()))
+        if self._val_engine is not None:
+            code = max(code, int(self._val_engine.err.item()))
+        raise_on_error_code(code)
 
     def fit(self, epochs=EPOCHS, orders=None, verbose=False):
         history = []
@@ -125,16 +140,19 @@ class FineTuner:
             chunk = indices[pos:pos + self.val_batch]
             pos += len(chunk)
             if self._val_engine is None or self._val_engine.Bw != len(chunk):
-                self._val_engine = HybridEngine(d, 1, len(chunk), self.device)
+                self._val_engine = HybridEngine(d, 1, len(chunk), self.device, training=False)  # eval mode: no dropout
             e = self._val_engine
             sel = torch.tensor(chunk, dtype=torch.long, device=self.device)
             e.gcn_forward(self.features, C, 0, self.x_table[sel].contiguous(), self.gcn_w, self.graph_csr)
             e.lstm_head_forward(self.theta, 0)
             e.mse(feat=self.features, tgt_off=self.t_table[sel].contiguous(), feat_ld=C, want_grad=False)
             total += e.loss.sum()
-        return float(total.item()) / len(indices)
+        out = float(total.item()) / len(indices)
+        self.check()
+        return out
 
     def state_dict(self):
+        self.check()
         out = {k: v.clone() for k, v in self.sd.items()}
         for name, t in unflatten_trainable(self.theta.detach().cpu(), self.dims).items():
             out[name] = t.clone()
@@ -142,7 +160,7 @@ class FineTuner:
 
 
 def adapt_region(checkpoint, features, edge_index, region_coords, region_name, stats=None, device="cuda",
-                 epochs=EPOCHS, orders=None, verbose=True):
+                 epochs=EPOCHS, orders=None, verbose=True, dropout=None):
     """The compute part of ``adaptModel`` (adapt_hybrid_v5.py:84-257) on in-memory inputs.
 
     ``checkpoint`` is a meta-training checkpoint dict (keys of train_hybrid_maml_v5.py:311-335);
@@ -152,7 +170,11 @@ def adapt_region(checkpoint, features, edge_index, region_coords, region_name, s
                   in_channels=config["input_channels"], hidden=config["hidden_channels"],
                   lstm_hidden=hybrid_config["lstm_hidden_size"], lstm_layers=hybrid_config["lstm_num_layers"],
                   out_channels=config["output_channels"], num_weather=config["output_channels"])
-    tuner = FineTuner(checkpoint["hybrid_model_state_dict"], features, edge_index, dims, device, region_name)
+    if dropout is None:  # adapt_hybrid_v5.py:99-117: STGCN(dropout_rate=0.2), lstm_dropout from the checkpoint
+        p = float(hybrid_config.get("lstm_dropout", REFERENCE_DROPOUT[1]))
+        dropout = (REFERENCE_DROPOUT[0], p, p)
+    tuner = FineTuner(checkpoint["hybrid_model_state_dict"], features, edge_index, dims, device, region_name,
+                      dropout=dropout)
     tuner.fit(epochs, orders, verbose)
     val = tuner.validate()
     sd = tuner.state_dict()

@@ -51,7 +51,7 @@ def load_optimizer_state_dict(adam, osd, hybrid_keys, dims: V5Dims):
             continue
         if tuple(entry["exp_avg"].shape) != tuple(shape):
             raise ValueError(f"optimizer state of {name}: shape {tuple(entry['exp_avg'].shape)} != {tuple(shape)}")
-        m[name], v[name] = entry["exp_avg"], entry["exp_avg_sq"]
+        m[name], v[name] = entry["exp_avg"].detach().cpu(), entry["exp_avg_sq"].detach().cpu()
         steps.add(int(float(entry["step"])))
     if len(steps) > 1:
         raise ValueError(f"parameters disagree on the step count: {sorted(steps)}")

@@ -85,12 +85,15 @@ extern "C" int wf_gcn_layer_bwd(const float* X, int x_ld, long long x_win_stride
   if (dW) {
     RowMap xm = make_rowmap(0, R, x_win_stride, x_ld, x_win_off);
     WF_REQUIRE(x_win_off == nullptr || G == 1, "gcn_layer_bwd: per-window offsets need G == 1");
-    rc = wf_launch_spmm(X, xm, (long long)Bw * x_win_stride, rowptr, col, val, rowptr_group_stride, csr_group_stride,
-                        R, (int)rows, Cin, Z, rows * Cin, G, st);
-    if (rc) return rc;
+    if (rowptr != nullptr) {
+      rc = wf_launch_spmm(X, xm, (long long)Bw * x_win_stride, rowptr, col, val, rowptr_group_stride, csr_group_stride,
+                          R, (int)rows, Cin, Z, rows * Cin, G, st);
+      if (rc) return rc;
+    }
     GemmArgs a = {};
     a.A = dY; a.am = dym; a.gA = rows * Cout;
-    a.B = Z; a.bm = make_rowmap(0, (int)rows, 0, Cin); a.gB = rows * Cin;
+    if (rowptr != nullptr) { a.B = Z; a.bm = make_rowmap(0, (int)rows, 0, Cin); a.gB = rows * Cin; }
+    else { a.B = X; a.bm = xm; a.gB = (long long)Bw * x_win_stride; }  // identity aggregation (a plain Linear layer)
     a.C = dW; a.cm = make_rowmap(0, Cout, 0, Cin); a.gC = dw_group_stride;
     a.M = Cout; a.N = Cin; a.K = (int)rows;
     a.partial = part;

@@ -22,6 +22,7 @@
 #include <cuda_fp16.h>
 
 #include "wf_common.cuh"
+#include "wf_rng.cuh"
 #include "wf_tc.cuh"
 
 using namespace wftc;
@@ -33,6 +34,9 @@ constexpr int G16_THREADS = 448;  // producer, MMA, 8 converter warps, 4 epilogu
 constexpr int G16_NST = 3;
 constexpr int G16_A_BYTES = 32768, G16_B_BYTES = 16384, G16_STAGE = G16_A_BYTES + 2 * G16_B_BYTES;
 constexpr int G16_SMEM = G16_NST * G16_STAGE + 1024;
+// fp16 hi/lo operand splits hold |x| < 65520 (beyond, hi rounds to inf and lo = x - inf is NaN).  Layer outputs are
+// flagged from 32768 up: the next layer's aggregation may still add neighbours of the same size.
+constexpr float WF_F16_RANGE_LIMIT = 32768.0f;
 
 struct G16Args {
   int mode;
@@ -53,6 +57,8 @@ struct G16Args {
   const float* bias; const float* bias2; long long bias_gstride; int relu;
   __nv_bfloat16* ct_hi; __nv_bfloat16* ct_lo;   // transposed copies [(g*Bw + w)][c_cols][RT]
   float* rowsum_part;                // WGRAD: per (split, k-half) partial row sums of A [parts][G][M] (bias gradients), or null
+  DropCfg drop;                      // ROWS: dropout on the output (GCN sites); NODES: on the TB4 output (dX = mask of the LSTM site)
+  float range_limit;                 // ROWS: > 0 flags |output| >= limit in err (the next layer splits it into fp16 hi/lo)
   int* err;
 };
 
@@ -122,7 +128,7 @@ __device__ __forceinline__ TileCoord decode_tile(const G16Args& a, int tile) {
   return c;
 }
 
-template <int FMT>
+template <int FMT, bool DROP>
 __global__ void __launch_bounds__(G16_THREADS, 1)
 wf_g16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmBhi,
               const __grid_constant__ CUtensorMap tmBlo, const G16Args a) {
@@ -326,6 +332,12 @@ wf_g16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
       if (a.mode == G16_NODES) {
         // TB4 block = [c_cols / 4 channel groups][128 rows][4 floats]: 512 contiguous bytes per warp store
         float4* cblk = reinterpret_cast<float4*>(a.C) + ((long long)c.blk * (a.c_cols >> 2) + (n0 >> 2)) * 128 + row;
+        DropState dst;
+        unsigned long long e4row = 0;  // (element index of this row's column n0) / 4 in the canonical [G*Bw, T, N, c_cols] tensor
+        if (DROP) {
+          dst = wf_drop_state(a.drop);
+          e4row = (((unsigned long long)c.zt * a.Nn + (unsigned)(c.node0 + row)) * (unsigned)a.c_cols + (unsigned)n0) >> 2;
+        }
 #pragma unroll 1
         for (int cc = 0; cc < 128; cc += 32) {
           uint32_t v[32];
@@ -338,6 +350,11 @@ wf_g16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
             if (b1) { const float4 b = __ldg(reinterpret_cast<const float4*>(b1 + cc + j)); o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w; }
             if (b2) { const float4 b = __ldg(reinterpret_cast<const float4*>(b2 + cc + j)); o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w; }
             if (a.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+            if (DROP) {
+              float m[4];
+              wf_drop4(dst, e4row + (unsigned)((cc + j) >> 2), m);
+              o.x *= m[0]; o.y *= m[1]; o.z *= m[2]; o.w *= m[3];
+            }
             if (row < a.rpt) cblk[(long long)((cc + j) >> 2) * 128] = o;  // rows >= rpt of a node tile are padding
           }
         }
@@ -351,6 +368,13 @@ wf_g16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
           const int tt = rr / a.Nn, nn = rr - tt * a.Nn;
           ctbase = ((long long)(c.g * a.Bw + w) * a.c_cols + n0) * a.RT + (long long)tt * a.Np + nn;
         }
+        DropState dst;
+        unsigned long long e4row = 0;  // (element index of this row's column n0) / 4 in the canonical [G*rows_g, c_cols] tensor
+        if (DROP) {
+          dst = wf_drop_state(a.drop);
+          e4row = (((unsigned long long)c.g * (unsigned)a.rows_g + (unsigned)grow) * (unsigned)a.c_cols + (unsigned)n0) >> 2;
+        }
+        float amax = 0.f;
 #pragma unroll 1
         for (int cc = 0; cc < 128; cc += 32) {
           uint32_t v[32];
@@ -364,6 +388,12 @@ wf_g16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
               if (b1) { const float4 b = __ldg(reinterpret_cast<const float4*>(b1 + cc + j)); o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w; }
               if (b2) { const float4 b = __ldg(reinterpret_cast<const float4*>(b2 + cc + j)); o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w; }
               if (a.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+              if (DROP) {
+                float m[4];
+                wf_drop4(dst, e4row + (unsigned)((cc + j) >> 2), m);
+                o.x *= m[0]; o.y *= m[1]; o.z *= m[2]; o.w *= m[3];
+              }
+              amax = fmaxf(amax, fmaxf(fmaxf(fabsf(o.x), fabsf(o.y)), fmaxf(fabsf(o.z), fabsf(o.w))));
               *reinterpret_cast<float4*>(crow + cc + j) = o;
               if (a.ct_hi != nullptr) {  // lanes of a warp hold consecutive rows -> contiguous transposed stores
                 const float ov[4] = {o.x, o.y, o.z, o.w};
@@ -379,6 +409,9 @@ wf_g16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
             }
           }
         }
+        // an activation the next layer cannot split into fp16 hi/lo (|x| >= 65520 rounds to inf), or a non-finite one:
+        // flag it instead of propagating NaN silently (engine.check() reports it; precision="fp32" has no such limit)
+        if (a.range_limit > 0.f && valid && !(amax < a.range_limit)) atomicExch(a.err, 41);
       }
       tc_fence_before();
       __syncwarp();
@@ -433,8 +466,10 @@ int g16_launch(int fmt, const CUtensorMap& tmA, const CUtensorMap& tmBhi, const 
   static bool configured = false;
   static int sms = 148;
   if (!configured) {
-    if (cudaFuncSetAttribute(wf_g16_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, G16_SMEM) != cudaSuccess ||
-        cudaFuncSetAttribute(wf_g16_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, G16_SMEM) != cudaSuccess)
+    if (cudaFuncSetAttribute(wf_g16_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, G16_SMEM) != cudaSuccess ||
+        cudaFuncSetAttribute(wf_g16_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, G16_SMEM) != cudaSuccess ||
+        cudaFuncSetAttribute(wf_g16_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, G16_SMEM) != cudaSuccess ||
+        cudaFuncSetAttribute(wf_g16_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, G16_SMEM) != cudaSuccess)
       return wf_fail(WF_ECUDA, "g16 kernel: cannot raise dynamic shared memory to %d", G16_SMEM);
     int dev = 0;
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -443,8 +478,11 @@ int g16_launch(int fmt, const CUtensorMap& tmA, const CUtensorMap& tmBhi, const 
   }
   const long long total = (long long)a.n_tiles * a.m_tiles * a.G * a.splits;
   const int grid = (int)(total < sms ? total : sms);
-  if (fmt == 0) wf_g16_kernel<0><<<grid, G16_THREADS, G16_SMEM, st>>>(tmA, tmBhi, tmBlo, a);
-  else wf_g16_kernel<1><<<grid, G16_THREADS, G16_SMEM, st>>>(tmA, tmBhi, tmBlo, a);
+  const bool drop = a.drop.rng != nullptr && a.mode != G16_WGRAD;
+  if (fmt == 0 && !drop) wf_g16_kernel<0, false><<<grid, G16_THREADS, G16_SMEM, st>>>(tmA, tmBhi, tmBlo, a);
+  else if (fmt == 0) wf_g16_kernel<0, true><<<grid, G16_THREADS, G16_SMEM, st>>>(tmA, tmBhi, tmBlo, a);
+  else if (!drop) wf_g16_kernel<1, false><<<grid, G16_THREADS, G16_SMEM, st>>>(tmA, tmBhi, tmBlo, a);
+  else wf_g16_kernel<1, true><<<grid, G16_THREADS, G16_SMEM, st>>>(tmA, tmBhi, tmBlo, a);
   WF_CHECK_LAUNCH("g16_kernel");
   return WF_OK;
 }
@@ -513,7 +551,8 @@ int wf_launch_g16_rows(int fmt, const float* A, long long a_rows_total, int lda,
                        const float* bias2, long long bias_gstride, int relu, float* C, int ldc, long long c_gstride,
                        const int* rowptr, const int* col, const float* val, long long g_rowptr, long long g_csr, int R, int Bw,
                        void* ct_hi, void* ct_lo, int Nn, const float* agg, int* err, cudaStream_t st,
-                       const long long* a_win_off = nullptr, int kpad = 0) {
+                       const long long* a_win_off = nullptr, int kpad = 0, const DropCfg* drop = nullptr,
+                       float range_limit = 0.f) {
   // kpad: the K extent seen by the k-loop when the operands' real K (their row length) is shorter and not a multiple of
   // 64: TMA zero-fills the columns beyond K (the 24-channel first GCN layer)
   if (kpad > 0) { WF_REQUIRE(K % 8 == 0 && kpad % 64 == 0 && kpad >= K, "g16_rows: bad K padding %d -> %d", K, kpad); }
@@ -539,6 +578,8 @@ int wf_launch_g16_rows(int fmt, const float* A, long long a_rows_total, int lda,
   if (a_win_off != nullptr) { a.a_win_off = a_win_off; a.win_tiles = wf_cdiv(a.R, 128); a.m_tiles = a.Bw * a.win_tiles; }
   a.C = C; a.ldc = ldc; a.c_gstride = c_gstride; a.c_cols = N; a.bias = bias; a.bias2 = bias2; a.bias_gstride = bias_gstride;
   a.relu = relu; a.ct_hi = (__nv_bfloat16*)ct_hi; a.ct_lo = (__nv_bfloat16*)ct_lo; a.err = err;
+  if (drop != nullptr) a.drop = *drop;
+  a.range_limit = range_limit;
   return g16_launch(fmt, tmA, tmBhi, tmBlo, a, st);
 }
 
@@ -546,7 +587,7 @@ int wf_launch_g16_rows(int fmt, const float* A, long long a_rows_total, int lda,
 // A: row-major [G*Bw*T*Nn, K] (a_tb4 == 0) or a TB4 buffer with K channels (a_tb4 == 1).
 int wf_launch_g16_nodes(int fmt, const float* A, int a_tb4, int K, const void* Whi, const void* Wlo, int ldb, long long b_gstride,
                         int N, const float* bias, const float* bias2, long long bias_gstride, float* C, int T, int Nn, int Bw,
-                        int G, int* err, cudaStream_t st) {
+                        int G, int* err, cudaStream_t st, const DropCfg* drop) {
   WF_REQUIRE(K % 64 == 0 && K >= 64, "g16_nodes: K=%d must be a multiple of 64", K);
   WF_REQUIRE(N % 128 == 0 && ldb % 8 == 0, "g16_nodes: N=%d must be a multiple of 128, ldb of 8", N);
   WF_REQUIRE(((uintptr_t)A | (uintptr_t)Whi | (uintptr_t)Wlo | (uintptr_t)C) % 16 == 0, "g16_nodes: pointers must be 16-byte aligned");
@@ -569,6 +610,7 @@ int wf_launch_g16_nodes(int fmt, const float* A, int a_tb4, int K, const void* W
   a.mode = G16_NODES; a.tpw = tpw; a.rpt = wf_tile_rows(Nn); a.a_tb4 = a_tb4; a.m_tiles = Bw * T * tpw; a.n_tiles = N / 128; a.G = G;
   a.Bw = Bw; a.T = T; a.Nn = Nn; a.nkb = K / 64;
   a.C = C; a.c_cols = N; a.bias = bias; a.bias2 = bias2; a.bias_gstride = bias_gstride; a.err = err;
+  if (drop != nullptr) a.drop = *drop;
   return g16_launch(fmt, tmA, tmBhi, tmBlo, a, st);
 }
 
@@ -668,6 +710,43 @@ int wf_launch_transpose_split16(const float* in, long long in_gstride, int rows,
   return WF_OK;
 }
 
+// X [Z*T*N, C] row-major fp32 -> bf16 hi / lo transposed copies [Z][C][RT16], column (t, node) = t*Np + node: the K-major
+// operand of the weight-gradient product dW_ih = dG^T X for activations that were not produced by the GCN epilogue
+// (the drop-in nn.Module path hands the LSTM an arbitrary features tensor).  Padding columns are left untouched (zero).
+static __global__ void wf_transpose_rows16_kernel(const float* __restrict__ X, int T, int N, int C, int Np,
+                                                  __nv_bfloat16* __restrict__ out_hi, __nv_bfloat16* __restrict__ out_lo) {
+  __shared__ float t[32][33];
+  const int zt = blockIdx.z, z = zt / T, tt = zt - z * T;
+  const int n0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    const int n = n0 + i, c = c0 + threadIdx.x;
+    t[i][threadIdx.x] = (n < N && c < C) ? X[((long long)zt * N + n) * C + c] : 0.f;
+  }
+  __syncthreads();
+  const long long RT = (long long)T * Np;
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    const int c = c0 + i, n = n0 + threadIdx.x;
+    if (c < C && n < N) {
+      const float v = t[threadIdx.x][i];
+      const long long o = ((long long)z * C + c) * RT + (long long)tt * Np + n;
+      const __nv_bfloat16 h = __float2bfloat16_rn(v);
+      out_hi[o] = h;
+      out_lo[o] = __float2bfloat16_rn(v - __bfloat162float(h));
+    }
+  }
+}
+
+extern "C" int wf_transpose_split16_rows(const float* X, int T, int N, int C, int windows, void* out_hi, void* out_lo,
+                                         void* stream) {
+  WF_REQUIRE(T > 0 && N > 0 && C > 0 && windows > 0, "transpose_split16_rows: empty input");
+  WF_REQUIRE((long long)windows * T < 65536, "transpose_split16_rows: windows * T must stay below 65536");
+  dim3 grid(wf_cdiv(N, 32), wf_cdiv(C, 32), windows * T), block(32, 8);
+  wf_transpose_rows16_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(X, T, N, C, wf_np(N), (__nv_bfloat16*)out_hi,
+                                                                       (__nv_bfloat16*)out_lo);
+  WF_CHECK_LAUNCH("transpose_split16_rows");
+  return WF_OK;
+}
+
 // fp32 -> 16-bit hi / lo operand halves (fmt 0: fp16, 1: bf16); n a multiple of 4.
 extern "C" int wf_split16(const float* src, void* hi, void* lo, long long n, int fmt, void* stream) {
   WF_REQUIRE(fmt == 0 || fmt == 1, "split16: fmt must be 0 (fp16) or 1 (bf16)");
@@ -691,8 +770,12 @@ extern "C" int wf_gcn_layer_fwd_g16(const float* X, const long long* x_win_off, 
                                     const void* W16_lo, const float* bias, const int* rowptr, const int* col, const float* val,
                                     long long rowptr_group_stride, long long csr_group_stride, const int* gather_rows,
                                     int gather_max, long long gather_group_stride, float* agg, int R, int N, int Cin, int Cout,
-                                    int G, int Bw, int relu, float* Y, void* YT_hi, void* YT_lo, int* err, void* stream) {
+                                    int G, int Bw, int relu, float* Y, void* YT_hi, void* YT_lo, float p_drop,
+                                    const unsigned long long* rng, int site, int* err, void* stream) {
   WF_REQUIRE(G > 0 && Bw > 0 && R > 0 && N > 0, "gcn_layer_fwd_g16: bad batch");
+  WF_REQUIRE(p_drop >= 0.f && p_drop < 1.f, "gcn_layer_fwd_g16: p_drop=%f outside [0, 1)", (double)p_drop);
+  WF_REQUIRE(p_drop == 0.f || rng != nullptr, "gcn_layer_fwd_g16: dropout needs the rng state");
+  const DropCfg drop = wf_drop_cfg(p_drop, rng, WF_SITE_GCN + site);
   const long long rows_g = (long long)Bw * R;
   cudaStream_t st = (cudaStream_t)stream;
   const bool pre = rowptr != nullptr && gather_rows != nullptr && agg != nullptr && gather_max > 0;
@@ -707,7 +790,8 @@ extern "C" int wf_gcn_layer_fwd_g16(const float* X, const long long* x_win_off, 
   const int kpad = Cin % 64 == 0 ? 0 : (Cin + 63) / 64 * 64;
   return wf_launch_g16_rows(0, X, x_win_off ? x_rows_total : rows_g * G, Cin, (int)rows_g, (int)rows_g, G, Cin, W16_hi, W16_lo, Cin,
                             0, 1, Cout, bias, nullptr, 0, relu, Y, Cout, rows_g * Cout, rowptr, col, val, rowptr_group_stride,
-                            csr_group_stride, R, Bw, YT_hi, YT_lo, N, pre ? agg : nullptr, err, st, x_win_off, kpad);
+                            csr_group_stride, R, Bw, YT_hi, YT_lo, N, pre ? agg : nullptr, err, st, x_win_off, kpad, &drop,
+                            WF_F16_RANGE_LIMIT);
 }
 
 // Test / general entry point: C[g] = A[g] W[g]^T (+ bias + bias2, relu), W16 hi/lo [G][N, K] from wf_split16(W, fmt).

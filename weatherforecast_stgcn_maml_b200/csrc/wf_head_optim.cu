@@ -284,4 +284,4 @@ int wf_fail(int code, const char* fmt, ...) {
   return code;
 }
 extern "C" const char* wf_last_error(void) { return wf_err_msg; }
-extern "C" int wf_abi_version(void) { return 1; }
+extern "C" int wf_abi_version(void) { return 2; }

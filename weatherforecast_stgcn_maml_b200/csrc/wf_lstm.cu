@@ -18,6 +18,7 @@
 //   per layer  weight_ih [4L, Kin], weight_hh [4L, L], bias_ih [4L], bias_hh [4L];
 //   then output_layer.weight [O, L], output_layer.bias [O].
 #include "wf_gemm.cuh"
+#include "wf_rng.cuh"
 
 #include "wf_layout.cuh"
 
@@ -184,11 +185,17 @@ static int check_dims(const char* fn, int layers, int F, int L, int T, int N, in
   return WF_OK;
 }
 
+extern "C" int wf_dropout_apply(const float* in, long long in_blk_stride, int rows_per_blk, int in_ld, long long rows,
+                                int cols, float p, const unsigned long long* rng, int site, float* out, void* stream);
+
 extern "C" int wf_lstm_fwd(const float* x, const float* params, long long params_group_stride, int layers, int F,
                            int L, int O, int T, int N, int G, int Bw, float* gates, float* h, float* c,
-                           void* stream) {
+                           float p_drop, const unsigned long long* rng, float* h_masked, void* stream) {
   int rc = check_dims("lstm_fwd", layers, F, L, T, N, G, Bw);
   if (rc) return rc;
+  WF_REQUIRE(p_drop >= 0.f && p_drop < 1.f, "lstm_fwd: p_drop=%f outside [0, 1)", (double)p_drop);
+  WF_REQUIRE(p_drop == 0.f || layers == 1 || (rng != nullptr && h_masked != nullptr), "lstm_fwd: dropout needs rng and h_masked");
+  const bool drop = p_drop > 0.f && layers > 1;
   cudaStream_t st = (cudaStream_t)stream;
   const LstmLayout P = lstm_layout(layers, F, L, O);
   const long long R = (long long)T * N, rows = (long long)Bw * R, allrows = rows * G;
@@ -198,7 +205,8 @@ extern "C" int wf_lstm_fwd(const float* x, const float* params, long long params
     float* H = h + (long long)l * allrows * L;
     float* C = c + (long long)l * allrows * L;
     GemmArgs a = {};
-    a.A = l == 0 ? x : h + (long long)(l - 1) * allrows * L;
+    // inter-layer dropout (hybrid_model.py:47): layer l >= 1 reads mask * h[l-1] / (1 - p), kept in h_masked for BPTT
+    a.A = l == 0 ? x : (drop ? h_masked : h) + (long long)(l - 1) * allrows * L;
     a.am = make_rowmap(0, (int)rows, 0, kin); a.gA = rows * kin;
     a.B = params + P.w_ih[l]; a.ldb = kin; a.gB = params_group_stride;
     a.C = XG; a.cm = make_rowmap(0, (int)rows, 0, 4 * L); a.gC = rows * 4 * L;
@@ -215,6 +223,11 @@ extern "C" int wf_lstm_fwd(const float* x, const float* params, long long params
       wf_lstm_step_fwd_kernel<<<grid, WF_GEMM_THREADS, 0, st>>>(s);
     }
     WF_CHECK_LAUNCH("lstm_step_fwd");
+    if (drop && l + 1 < layers) {
+      rc = wf_dropout_apply(H, 0, (int)(allrows > 0x7fffffff ? 0x7fffffff : allrows), L, allrows, L, p_drop, rng, WF_SITE_LSTM + l,
+                            h_masked + (long long)l * allrows * L, stream);
+      if (rc) return rc;
+    }
   }
   return WF_OK;
 }
@@ -239,10 +252,14 @@ extern "C" size_t wf_lstm_bwd_workspace_bytes(int layers, int F, int L, int T, i
 // (hybrid_model.py:63).
 extern "C" int wf_lstm_bwd(const float* x, const float* params, long long params_group_stride, int layers, int F,
                            int L, int O, int T, int N, int G, int Bw, float* gates, const float* h, const float* c,
-                           const float* dlast, float* grads, long long grads_group_stride, void* workspace,
+                           const float* dlast, float* grads, long long grads_group_stride, float p_drop,
+                           const unsigned long long* rng, const float* h_masked, void* workspace,
                            size_t workspace_bytes, void* stream) {
   int rc = check_dims("lstm_bwd", layers, F, L, T, N, G, Bw);
   if (rc) return rc;
+  WF_REQUIRE(p_drop >= 0.f && p_drop < 1.f, "lstm_bwd: p_drop=%f outside [0, 1)", (double)p_drop);
+  WF_REQUIRE(p_drop == 0.f || layers == 1 || (rng != nullptr && h_masked != nullptr), "lstm_bwd: dropout needs rng and h_masked");
+  const bool drop = p_drop > 0.f && layers > 1;
   if (workspace_bytes < wf_lstm_bwd_workspace_bytes(layers, F, L, T, N, G, Bw))
     return wf_fail(WF_EWORKSPACE, "lstm_bwd: workspace too small");
   cudaStream_t st = (cudaStream_t)stream;
@@ -257,7 +274,7 @@ extern "C" int wf_lstm_bwd(const float* x, const float* params, long long params
     float* XG = gates + (long long)l * allrows * 4 * L;
     const float* H = h + (long long)l * allrows * L;
     const float* C = c + (long long)l * allrows * L;
-    const float* Xl = l == 0 ? x : h + (long long)(l - 1) * allrows * L;
+    const float* Xl = l == 0 ? x : (drop ? h_masked : h) + (long long)(l - 1) * allrows * L;
     LstmStepArgs s = {};
     s.H = const_cast<float*>(H); s.C = const_cast<float*>(C); s.XG = XG;
     s.Whh = params + P.w_hh[l]; s.gW = params_group_stride;
@@ -308,6 +325,11 @@ extern "C" int wf_lstm_bwd(const float* x, const float* params, long long params
       a.M = (int)rows; a.N = kin; a.K = 4 * L;
       rc = wf_launch_gemm_nn(a, G, false, st);
       if (rc) return rc;
+      if (drop) {  // ... through the mask of layer l-1's output
+        rc = wf_dropout_apply(DX, 0, (int)(allrows > 0x7fffffff ? 0x7fffffff : allrows), L, allrows, L, p_drop, rng,
+                              WF_SITE_LSTM + l - 1, DX, stream);
+        if (rc) return rc;
+      }
     }
   }
   return WF_OK;

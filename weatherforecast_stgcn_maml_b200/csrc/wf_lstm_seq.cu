@@ -17,7 +17,7 @@
 // the operand itself.  The default kernel (wf_lstm_seq_fwd16_kernel, 16 cell warps) keeps every global
 // store out of the dependent part of a step: results are staged in TMEM and written under the next
 // step's MMA, which is itself issued K step by K step behind the cell mathematics (see the comment on
-// that kernel and DESIGN.md section 4); wf_lstm_seq_fwd_kernel is the first, 8-warp version (WF_SEQ_FWD8=1).
+// that kernel and DESIGN.md section 4).
 // Backward (K split): CTA r holds W_hh^T restricted to its own gate rows (128 x 256, 128 KB), keeps
 // its own dG[t+1] (128 x 256) in TMEM as the A operand (TS mode) and produces a partial
 // dh[128 x 128]; the half belonging to the peer's units goes through distributed shared memory
@@ -32,13 +32,14 @@
 
 #include "wf_common.cuh"
 #include "wf_layout.cuh"
+#include "wf_rng.cuh"
 #include "wf_tc.cuh"
 
 using namespace wftc;
 
 int wf_launch_g16_nodes(int fmt, const float* A, int a_tb4, int K, const void* Whi, const void* Wlo, int ldb, long long b_gstride,
                         int N, const float* bias, const float* bias2, long long bias_gstride, float* C, int T, int Nn, int Bw,
-                        int G, int* err, cudaStream_t st);
+                        int G, int* err, cudaStream_t st, const DropCfg* drop);
 int wf_launch_g16_wgrad(const float* AT, int M, const void* BT_hi, const void* BT_lo, int N, int R, int Bw, int G, int a_k0,
                         int b_k0, int klen, float* dW, long long dw_gstride, int* err, cudaStream_t st, float* partials,
                         size_t partial_floats, float* rowsum1, float* rowsum2, long long rowsum_gstride);
@@ -62,6 +63,9 @@ struct SeqArgs {
   int h_tb4;
   __nv_bfloat16* HT;  // fwd out (optional): transposed bf16 hi / lo copies [(z)][L][RT]
   __nv_bfloat16* HT_lo;
+  __nv_bfloat16* HTm;  // fwd out (dropout on): transposed copies of the MASKED h, the next layer's input (dW_ih of layer l+1)
+  __nv_bfloat16* HTm_lo;
+  DropCfg drop;        // fwd: inter-layer dropout on this layer's output (hybrid_model.py:47); rng == nullptr: off
   float* DGT;         // bwd out: transposed dG [(z)][4L][RT]
   const float* ext;   // bwd: dL/dh from above -- TB4 (L channels), or row-major dlast [Z*Nn, L] if ext_last_only
   int ext_last_only;
@@ -102,16 +106,6 @@ __device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
                : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
   return ok != 0;
 }
-// bounded wait with cluster-scope acquire (the barrier receives arrivals from the peer CTA)
-__device__ __forceinline__ bool mbar_wait_cl(uint64_t* bar, uint32_t parity) {
-  for (uint32_t spin = 0; spin < (1u << 18); ++spin) {
-    uint32_t ok;
-    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}\n"
-                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
-    if (ok) return true;
-  }
-  return false;
-}
 // kind::f16 instruction descriptor: D = F32, A/B = fmt (0 F16, 1 BF16), both K-major, M = 128
 __host__ __device__ constexpr uint32_t idesc_16(int n, uint32_t fmt) {
   return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
@@ -131,7 +125,6 @@ __device__ __forceinline__ void tmem_st4(uint32_t taddr, const uint32_t* v) {
                ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]) : "memory");
 }
 
-__device__ __forceinline__ float fast_sigmoid(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
 __device__ __forceinline__ float fast_tanh(float x) { return 2.0f * __fdividef(1.0f, 1.0f + __expf(-2.0f * x)) - 1.0f; }
 
 // packed conversions (F2FP, ALU pipe); the residuals ra, rb feed the lo half
@@ -150,243 +143,8 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b, float& ra, float
   return u;
 }
 
-// ================================================================================= forward
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(SEQ_THREADS, 1)
-wf_lstm_seq_fwd_kernel(const __grid_constant__ CUtensorMap tmWhi, const __grid_constant__ CUtensorMap tmWlo, const SeqArgs a) {
-  constexpr int L = 128;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* b_hi = smem;            // [2 k-blocks][256 gate rows][128 B]
-  uint8_t* b_lo = smem + 65536;
-  uint8_t* a_hi = smem + 131072;   // [2 k-blocks][128 rows][128 B]
-  uint8_t* a_lo = smem + 163840;
-  __shared__ uint64_t wfull, a_ready, dfull, peer_done;
-  __shared__ uint32_t tmem_base_s;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const uint32_t rank = cluster_rank(), peer = rank ^ 1u;
-  const int tile = blockIdx.x >> 1;
-  const int z = tile / a.tpw, nt = tile - z * a.tpw, node0 = nt * a.rpt, g = z / a.Bw;
-  const int T = a.T;
-
-  if (tid == 0) {
-    // a_ready: 8 local warps + the expect_tx arrival; the peer's half of h[t] arrives as 32 KB of st.async transactions
-    mbar_init(&wfull, 1); mbar_init(&a_ready, 9); mbar_init(&dfull, 1); mbar_init(&peer_done, 1);
-    mbar_fence_init();
-    tma_prefetch_desc(&tmWhi); tma_prefetch_desc(&tmWlo);
-  }
-  if (warp == 0) tmem_alloc(&tmem_base_s, 256);
-  tc_fence_before();
-  __syncthreads();
-  cluster_sync_all();  // the peer's barriers exist before anybody arrives on them remotely
-  tc_fence_after();
-  const uint32_t tbase = tmem_base_s;
-
-  if (warp == 0 && lane == 0) {  // recurrent weights of this tile's task: resident for all T steps
-    if (T > 1) mbar_expect_tx(&a_ready, 32768);  // phase 0: the peer's half of h[0]
-    const int slab = a.slab0 + g * a.slab_g;
-    mbar_expect_tx(&wfull, 131072);
-    for (int kb = 0; kb < 2; ++kb) {
-      tma_load_4d(b_hi + kb * 32768, &tmWhi, &wfull, kb * 64, 64 * (int)rank, 0, slab);
-      tma_load_4d(b_lo + kb * 32768, &tmWlo, &wfull, kb * 64, 64 * (int)rank, 0, slab);
-    }
-  }
-  {
-    // ---------------------------------------------------------------- cell epilogue
-    const int q = warp & 3, half = warp >> 2;
-    const int r = q * 32 + lane;            // tile row == TMEM lane
-    const int ub = half * 32;               // first of this thread's 32 units inside the CTA's 64
-    const int u0 = 64 * (int)rank + ub;     // ... as a global hidden-unit index
-    const int node = node0 + r;
-    const bool valid = r < a.rpt && node < a.Nn;
-    const uint32_t tlane = tbase + ((uint32_t)(q * 32) << 16);
-    const long long R = (long long)T * a.Nn;
-    float4* const xg4 = reinterpret_cast<float4*>(a.XG);
-    float4* const c4 = reinterpret_cast<float4*>(a.Cst);
-    const uint32_t pd_remote = mapa_u32(smem_u32(&peer_done), peer);
-    const uint32_t ar_remote = mapa_u32(smem_u32(&a_ready), peer);
-    bool ok = true;
-
-    float cst[32];
-#pragma unroll
-    for (int j = 0; j < 32; ++j) cst[j] = 0.f;
-    float4 xq[2][8];
-    // chunk (t, c): units u0 + 8c .. +8, all four gates -> 8 float4 (gate * 2 + half-of-8)
-    auto xg_index = [&](int t, int c, int gate, int hh) -> long long {
-      const long long blk = ((long long)z * T + t) * a.tpw + nt;
-      return (blk * 128 + gate * 32 + ((u0 + 8 * c) >> 2) + hh) * 128 + r;
-    };
-    auto load_chunk = [&](int t, int c, float4* dst) {
-#pragma unroll
-      for (int gate = 0; gate < 4; ++gate) {
-        dst[gate * 2] = xg4[xg_index(t, c, gate, 0)];
-        dst[gate * 2 + 1] = xg4[xg_index(t, c, gate, 1)];
-      }
-    };
-    load_chunk(0, 0, xq[0]);
-    load_chunk(0, 1, xq[1]);
-    uint32_t acc[2][4][8];  // recurrent pre-activations of the current / next chunk (TMEM loads run one chunk ahead)
-#pragma unroll
-    for (int b = 0; b < 2; ++b)
-#pragma unroll
-      for (int gate = 0; gate < 4; ++gate)
-#pragma unroll
-        for (int j = 0; j < 8; ++j) acc[b][gate][j] = 0u;
-    auto issue_acc = [&](int c, uint32_t (*dst)[8]) {
-      __syncwarp();
-#pragma unroll
-      for (int gate = 0; gate < 4; ++gate) tmem_ld8(tlane + gate * 64 + ub + 8 * c, dst[gate]);
-    };
-
-    for (int t = 0; t < T; ++t) {
-      if (t > 0) {
-        if (warp == 0) {  // MMA issue: D[128 x 256] = h[t-1] W_hh^T for this CTA's 64 units x 4 gates
-          if (ok && t == 1 && !mbar_wait(&wfull, 0)) { ok = false; if (lane == 0) atomicExch(a.err, 11); }
-          if (ok && !mbar_wait_cl(&a_ready, (t - 1) & 1)) { ok = false; if (lane == 0) atomicExch(a.err, 12); }
-          if (lane == 0 && t + 1 < T) mbar_expect_tx(&a_ready, 32768);  // phase t: the peer's half of h[t]
-          fence_proxy_async_cta();
-          tc_fence_after();
-          if (lane == 0 && ok) {
-            const uint32_t idesc = idesc_16(256, 0);
-            uint32_t accf = 0;
-#pragma unroll
-            for (int p = 0; p < 3; ++p) {  // h_hi W_hi, h_lo W_hi, h_hi W_lo
-              const uint32_t as = smem_u32(p == 1 ? a_lo : a_hi), bs = smem_u32(p == 2 ? b_lo : b_hi);
-#pragma unroll
-              for (int kb = 0; kb < 2; ++kb)
-#pragma unroll
-                for (int k16 = 0; k16 < 4; ++k16) {
-                  umma_ss_16(tbase, umma_desc_k_sw128(as + kb * 16384 + k16 * 32),
-                             umma_desc_k_sw128(bs + kb * 32768 + k16 * 32), idesc, accf);
-                  accf = 1;
-                }
-            }
-            umma_commit(&dfull);
-          }
-          __syncwarp();
-        }
-        if (ok && !mbar_wait(&dfull, (t - 1) & 1)) { ok = false; if (lane == 0) atomicExch(a.err, 13); }
-        tc_fence_after();
-        if (warp == 0 && lane == 0) arrive_cluster_relaxed(pd_remote);  // my MMA no longer reads my A buffer
-        issue_acc(0, acc[0]);
-      }
-      const long long blk = ((long long)z * T + t) * a.tpw + nt;
-      const long long hrow = ((long long)z * R + (long long)t * a.Nn + node) * L + u0;
-      const long long tcol = (long long)t * a.Np + node;
-      // global stores of one finished chunk: activated gates (in place), cell state, hidden state (+ transposed copies)
-      auto store_chunk = [&](int c, const float* gi, const float* gf, const float* gg, const float* go, const float* hh) {
-#pragma unroll
-        for (int hsel = 0; hsel < 2; ++hsel) {
-          const int j = 4 * hsel;
-          xg4[xg_index(t, c, 0, hsel)] = make_float4(gi[j], gi[j + 1], gi[j + 2], gi[j + 3]);
-          xg4[xg_index(t, c, 1, hsel)] = make_float4(gf[j], gf[j + 1], gf[j + 2], gf[j + 3]);
-          xg4[xg_index(t, c, 2, hsel)] = make_float4(gg[j], gg[j + 1], gg[j + 2], gg[j + 3]);
-          xg4[xg_index(t, c, 3, hsel)] = make_float4(go[j], go[j + 1], go[j + 2], go[j + 3]);
-          c4[(blk * 32 + ((u0 + 8 * c) >> 2) + hsel) * 128 + r] =
-              make_float4(cst[8 * c + j], cst[8 * c + j + 1], cst[8 * c + j + 2], cst[8 * c + j + 3]);
-        }
-        if (a.h_tb4) {  // consumed only by the next layer's projection GEMM: coalesced tile-blocked stores
-          float4* h4 = reinterpret_cast<float4*>(a.H) + (blk * 32 + ((u0 + 8 * c) >> 2)) * 128 + r;
-          h4[0] = make_float4(hh[0], hh[1], hh[2], hh[3]);
-          h4[128] = make_float4(hh[4], hh[5], hh[6], hh[7]);
-        }
-        if (valid) {
-          if (!a.h_tb4) {
-            *reinterpret_cast<float4*>(a.H + hrow + 8 * c) = make_float4(hh[0], hh[1], hh[2], hh[3]);
-            *reinterpret_cast<float4*>(a.H + hrow + 8 * c + 4) = make_float4(hh[4], hh[5], hh[6], hh[7]);
-          }
-          if (a.HT != nullptr) {
-            __nv_bfloat16* ht = a.HT + ((long long)z * L + u0 + 8 * c) * a.RT + tcol;
-            __nv_bfloat16* htl = a.HT_lo + ((long long)z * L + u0 + 8 * c) * a.RT + tcol;
-#pragma unroll
-            for (int j = 0; j < 8; j += 2) {
-              float ra, rb, d0, d1;
-              const uint32_t uh = pack_bf16(hh[j], hh[j + 1], ra, rb), ul = pack_bf16(ra, rb, d0, d1);
-              reinterpret_cast<uint16_t*>(ht)[(long long)j * a.RT] = (uint16_t)uh;
-              reinterpret_cast<uint16_t*>(ht)[(long long)(j + 1) * a.RT] = (uint16_t)(uh >> 16);
-              reinterpret_cast<uint16_t*>(htl)[(long long)j * a.RT] = (uint16_t)ul;
-              reinterpret_cast<uint16_t*>(htl)[(long long)(j + 1) * a.RT] = (uint16_t)(ul >> 16);
-            }
-          }
-        }
-      };
-      float gi3[8], gf3[8], gg3[8], go3[8], hh3[8];  // the last chunk's outputs: stored after the hand-over below
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        if (t > 0) {
-          tmem_wait_ld();                          // chunk c's accumulators (issued one chunk ago) have landed
-          if (c < 3) issue_acc(c + 1, acc[(c + 1) & 1]);
-        }
-        const float4* x = xq[c & 1];
-        float gi[8], gf[8], gg[8], go[8], hh[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const int hsel = j >> 2, cmp = j & 3;
-          const float4 xi = x[0 + hsel], xf = x[2 + hsel], xgv = x[4 + hsel], xo = x[6 + hsel];
-          const float pi = (cmp == 0 ? xi.x : cmp == 1 ? xi.y : cmp == 2 ? xi.z : xi.w) + __uint_as_float(acc[c & 1][0][j]);
-          const float pf = (cmp == 0 ? xf.x : cmp == 1 ? xf.y : cmp == 2 ? xf.z : xf.w) + __uint_as_float(acc[c & 1][1][j]);
-          const float pg = (cmp == 0 ? xgv.x : cmp == 1 ? xgv.y : cmp == 2 ? xgv.z : xgv.w) + __uint_as_float(acc[c & 1][2][j]);
-          const float po = (cmp == 0 ? xo.x : cmp == 1 ? xo.y : cmp == 2 ? xo.z : xo.w) + __uint_as_float(acc[c & 1][3][j]);
-          gi[j] = fast_sigmoid(pi);
-          gf[j] = fast_sigmoid(pf);
-          gg[j] = fast_tanh(pg);
-          go[j] = fast_sigmoid(po);
-          const float cc = fmaf(gf[j], cst[8 * c + j], gi[j] * gg[j]);
-          cst[8 * c + j] = cc;
-          hh[j] = go[j] * fast_tanh(cc);
-        }
-        if (t + 1 < T) {
-          // h[t] as fp16 hi/lo -> the A operand of step t+1 in both CTAs (k-block `rank`, chunk (ub + 8c) / 8)
-          uint32_t hi[4], lo[4];
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            float ra, rb, d0, d1;
-            hi[i] = pack_f16(hh[2 * i], hh[2 * i + 1], ra, rb);
-            lo[i] = pack_f16(ra, rb, d0, d1);
-          }
-          const uint32_t off = rank * 16384u + (uint32_t)(r >> 3) * 1024u + (uint32_t)(r & 7) * 128u +
-                               ((uint32_t)((((ub >> 3) + c)) ^ (r & 7)) << 4);
-          if (c == 0 && t > 0) {  // the peer's MMA of this step must be done with the peer's A buffer
-            if (ok && !mbar_wait_cl(&peer_done, (t - 1) & 1)) { ok = false; if (lane == 0) atomicExch(a.err, 14); }
-          }
-          const uint4 vhi = make_uint4(hi[0], hi[1], hi[2], hi[3]), vlo = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-          sts128(smem_u32(a_hi + off), vhi);
-          sts128(smem_u32(a_lo + off), vlo);
-          st_async_v4(mapa_u32(smem_u32(a_hi + off), peer), vhi, ar_remote);
-          st_async_v4(mapa_u32(smem_u32(a_lo + off), peer), vlo, ar_remote);
-        }
-        if (c < 3) {
-          // loads first: the memory pipeline is in order, a load queued behind a burst of stores waits for it
-          if (c < 2) load_chunk(t, c + 2, xq[c & 1]);  // chunks 2, 3 of this step; consumed before the hand-over
-          store_chunk(c, gi, gf, gg, go, hh);
-        } else {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) { gi3[j] = gi[j]; gf3[j] = gf[j]; gg3[j] = gg[j]; go3[j] = go[j]; hh3[j] = hh[j]; }
-        }
-      }
-      if (t + 1 < T) {
-        // Hand h[t] over.  The peer's copy travels as st.async transactions that complete on the peer's barrier by
-        // themselves; locally only a shared-memory proxy fence and a CTA-scope arrive are needed -- no cluster-scope
-        // release (MEMBAR.ALL.GPU, which waits for every outstanding global store of the warp) on the critical path.
-        fence_proxy_async_cta();  // my generic-proxy operand writes -> visible to the tensor core (async proxy)
-        tc_fence_before();        // my TMEM reads of D[t] are complete before MMA[t+1] may overwrite D
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&a_ready);
-      }
-      if (t + 1 < T) {
-        load_chunk(t + 1, 0, xq[0]);
-        load_chunk(t + 1, 1, xq[1]);
-      }
-      store_chunk(3, gi3, gf3, gg3, go3, hh3);
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 0) tmem_dealloc(tbase, 256);
-  cluster_sync_all();  // nobody exits while the peer may still address this CTA's shared memory
-}
-
 // ================================================================================= forward, 16 warps
-// Same algorithm and buffers as wf_lstm_seq_fwd_kernel, rearranged around the measured per-SM limits:
+// Arranged around the measured per-SM limits:
 // an SM writes at most ~62 GB/s to L2 whatever the path (LSU or bulk copy), so the 224 KB a CTA stores per step cost
 // 3.6 us and must not sit between the cell mathematics and the hand-over of h[t].  Per step:
 //   phase A  D[t] (TMEM) + input projection -> gates, c, h;  h[t] -> both CTAs' A operand;  h / h^T stores;  the
@@ -434,6 +192,7 @@ __device__ __forceinline__ void hidden4(const float* go, const float* dc, float*
   hh[3] = go[3] * fmaf(2.0f, r2 * dc[2], -1.0f);
 }
 
+template <bool DROP>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(512, 1)
 wf_lstm_seq_fwd16_kernel(const __grid_constant__ CUtensorMap tmWhi, const __grid_constant__ CUtensorMap tmWlo, const SeqArgs a) {
   constexpr int L = 128;
@@ -494,6 +253,8 @@ wf_lstm_seq_fwd16_kernel(const __grid_constant__ CUtensorMap tmWhi, const __grid
   float cst[16];
 #pragma unroll
   for (int j = 0; j < 16; ++j) cst[j] = 0.f;
+  DropState dstate;
+  if (DROP) dstate = wf_drop_state(a.drop);
   float4 xq[2][4];  // two chunks of 4 units in flight: one float4 per gate
   auto xg_index = [&](int t, int c, int gate) -> long long {
     const long long blk = ((long long)z * T + t) * a.tpw + nt;
@@ -664,8 +425,30 @@ wf_lstm_seq_fwd16_kernel(const __grid_constant__ CUtensorMap tmWhi, const __grid
           xg4[xg_index(t, c, gate)] = make_float4(__uint_as_float(gt[gate][0]), __uint_as_float(gt[gate][1]),
                                                   __uint_as_float(gt[gate][2]), __uint_as_float(gt[gate][3]));
         c4[(blk * 32 + (u0 >> 2) + 4 * c) * 128 + r] = make_float4(cst[4 * c], cst[4 * c + 1], cst[4 * c + 2], cst[4 * c + 3]);
-        if (a.h_tb4) reinterpret_cast<float4*>(a.H)[(blk * 32 + (u0 >> 2) + 4 * c) * 128 + r] = make_float4(hh[0], hh[1], hh[2], hh[3]);
+        // Inter-layer dropout (hybrid_model.py:47): the NEXT layer reads mask * h / (1 - p); the recurrence of this layer
+        // (the A operand handed over in phase A) and dW_hh (the unmasked transposed copy below) keep the plain h.
+        float hm[4] = {hh[0], hh[1], hh[2], hh[3]};
+        if (DROP) {
+          float m[4];
+          wf_drop4(dstate, (unsigned long long)(hrow + 16 * c) >> 2, m);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) hm[j] *= m[j];
+        }
+        if (a.h_tb4) reinterpret_cast<float4*>(a.H)[(blk * 32 + (u0 >> 2) + 4 * c) * 128 + r] = make_float4(hm[0], hm[1], hm[2], hm[3]);
         if (!a.h_tb4) *reinterpret_cast<float4*>(a.H + hrow + 16 * c) = make_float4(hh[0], hh[1], hh[2], hh[3]);
+        if (DROP && a.HTm != nullptr) {
+          __nv_bfloat16* ht = a.HTm + ((long long)z * L + u0 + 16 * c) * a.RT + tcol;
+          __nv_bfloat16* htl = a.HTm_lo + ((long long)z * L + u0 + 16 * c) * a.RT + tcol;
+#pragma unroll
+          for (int j = 0; j < 4; j += 2) {
+            float ra, rb, d0, d1;
+            const uint32_t uh = pack_bf16(hm[j], hm[j + 1], ra, rb), ul = pack_bf16(ra, rb, d0, d1);
+            reinterpret_cast<uint16_t*>(ht)[(long long)j * a.RT] = (uint16_t)uh;
+            reinterpret_cast<uint16_t*>(ht)[(long long)(j + 1) * a.RT] = (uint16_t)(uh >> 16);
+            reinterpret_cast<uint16_t*>(htl)[(long long)j * a.RT] = (uint16_t)ul;
+            reinterpret_cast<uint16_t*>(htl)[(long long)(j + 1) * a.RT] = (uint16_t)(ul >> 16);
+          }
+        }
         if (a.HT != nullptr) {
           __nv_bfloat16* ht = a.HT + ((long long)z * L + u0 + 16 * c) * a.RT + tcol;
           __nv_bfloat16* htl = a.HT_lo + ((long long)z * L + u0 + 16 * c) * a.RT + tcol;
@@ -1074,12 +857,21 @@ extern "C" int wf_prep_weights_seq(const float* params, long long params_group_s
 extern "C" int wf_lstm_fwd_seq(const float* x, const float* params, const void* p16_hi, const void* p16_lo,
                                long long params_group_stride, const void* f16_hi, const void* f16_lo, int layers, int F, int L,
                                int O, int T, int N, int G, int Bw, float* gates, float* h, float* c, void* hT_hi, void* hT_lo,
-                               int* err, void* stream) {
+                               float p_drop, const unsigned long long* rng, void* hTm_hi, void* hTm_lo, int* err,
+                               void* stream) {
   WF_REQUIRE(layers >= 1 && layers <= 8 && L == 128 && F % 64 == 0, "lstm_fwd_seq: needs L == 128, F %% 64 == 0");
   WF_REQUIRE(T > 0 && N > 0 && G > 0 && Bw > 0, "lstm_fwd_seq: empty batch");
+  WF_REQUIRE(p_drop >= 0.f && p_drop < 1.f, "lstm_fwd_seq: p_drop=%f outside [0, 1)", (double)p_drop);
+  WF_REQUIRE(p_drop == 0.f || rng != nullptr, "lstm_fwd_seq: dropout needs the rng state");
+  WF_REQUIRE(p_drop == 0.f || hT_hi == nullptr || hTm_hi != nullptr, "lstm_fwd_seq: training with dropout needs hTm");
   cudaStream_t st = (cudaStream_t)stream;
   static bool configured = false;
-  if (!configured) { int rc = seq_configure(wf_lstm_seq_fwd_kernel); if (rc) return rc; configured = true; }
+  if (!configured) {
+    int rc = seq_configure(wf_lstm_seq_fwd16_kernel<false>);
+    if (rc == WF_OK) rc = seq_configure(wf_lstm_seq_fwd16_kernel<true>);
+    if (rc) return rc;
+    configured = true;
+  }
   const LstmLayout P = lstm_layout(layers, F, L, O);
   const long long Z = (long long)G * Bw;
   const int tpw = wf_cdiv(N, 128), Np = wf_np(N), RT = T * Np;
@@ -1094,7 +886,7 @@ extern "C" int wf_lstm_fwd_seq(const float* x, const float* params, const void* 
     const float* Xl = l == 0 ? x : h + (long long)(l - 1) * c_elems;
     rc = wf_launch_g16_nodes(0, Xl, l == 0 ? 0 : 1, kin, (const uint16_t*)p16_hi + P.w_ih[l], (const uint16_t*)p16_lo + P.w_ih[l], kin,
                              stride16(P.total), 4 * L, params + P.b_ih[l], params + P.b_hh[l], params_group_stride, XG, T, N,
-                             Bw, G, err, st);
+                             Bw, G, err, st, nullptr);
     if (rc) return rc;
     SeqArgs a;
     memset(&a, 0, sizeof(a));
@@ -1102,13 +894,14 @@ extern "C" int wf_lstm_fwd_seq(const float* x, const float* params, const void* 
     a.HT = hT_hi ? (__nv_bfloat16*)hT_hi + l * tsz : nullptr; a.HT_lo = hT_hi ? (__nv_bfloat16*)hT_lo + l * tsz : nullptr;
     a.T = T; a.Nn = N; a.Bw = Bw; a.tpw = tpw; a.rpt = wf_tile_rows(N); a.Np = Np; a.RT = RT;
     a.slab0 = l; a.slab_g = layers; a.err = err;
-    static const bool fwd16 = getenv("WF_SEQ_FWD8") == nullptr;  // WF_SEQ_FWD8=1: the first-generation 8-warp kernel (A/B timing)
-    if (fwd16) {
-      static bool c16 = false;
-      if (!c16) { int rc16 = seq_configure(wf_lstm_seq_fwd16_kernel); if (rc16) return rc16; c16 = true; }
-      wf_lstm_seq_fwd16_kernel<<<dim3((unsigned)(2 * Z * tpw)), 512, SEQ_SMEM, st>>>(tmhi, tmlo, a);
-    } else
-    wf_lstm_seq_fwd_kernel<<<dim3((unsigned)(2 * Z * tpw)), SEQ_THREADS, SEQ_SMEM, st>>>(tmhi, tmlo, a);
+    const bool drop = p_drop > 0.f && l + 1 < layers;  // nn.LSTM: dropout on the outputs of every layer but the last
+    if (drop) {
+      a.drop = wf_drop_cfg(p_drop, rng, WF_SITE_LSTM + l);
+      a.HTm = hTm_hi ? (__nv_bfloat16*)hTm_hi + l * tsz : nullptr; a.HTm_lo = hTm_hi ? (__nv_bfloat16*)hTm_lo + l * tsz : nullptr;
+      wf_lstm_seq_fwd16_kernel<true><<<dim3((unsigned)(2 * Z * tpw)), 512, SEQ_SMEM, st>>>(tmhi, tmlo, a);
+    } else {
+      wf_lstm_seq_fwd16_kernel<false><<<dim3((unsigned)(2 * Z * tpw)), 512, SEQ_SMEM, st>>>(tmhi, tmlo, a);
+    }
     WF_CHECK_LAUNCH("lstm_seq_fwd");
   }
   return WF_OK;
@@ -1128,9 +921,14 @@ extern "C" size_t wf_lstm_bwd_seq_workspace_bytes(int layers, int F, int L, int 
 extern "C" int wf_lstm_bwd_seq(const void* xT_hi, const void* xT_lo, const void* pT16_hi, const void* pT16_lo,
                                const void* b16_hi, const void* b16_lo, int layers, int F, int L, int O, int T, int N, int G,
                                int Bw, float* gates, const float* c, const void* hT_hi, const void* hT_lo, float* dgT,
-                               const float* dlast, float* grads, long long grads_group_stride, void* workspace,
+                               const float* dlast, float* grads, long long grads_group_stride, float p_drop,
+                               const unsigned long long* rng, const void* hTm_hi, const void* hTm_lo, void* workspace,
                                size_t workspace_bytes, int* err, void* stream) {
   WF_REQUIRE(layers >= 1 && layers <= 8 && L == 128 && F % 128 == 0, "lstm_bwd_seq: needs L == 128 and F %% 128 == 0");
+  WF_REQUIRE(p_drop >= 0.f && p_drop < 1.f, "lstm_bwd_seq: p_drop=%f outside [0, 1)", (double)p_drop);
+  WF_REQUIRE(p_drop == 0.f || (rng != nullptr && hTm_hi != nullptr && hTm_lo != nullptr), "lstm_bwd_seq: dropout needs rng and hTm");
+  const bool drop = p_drop > 0.f;
+  const uint16_t *hTmh = (const uint16_t*)hTm_hi, *hTml = (const uint16_t*)hTm_lo;
   if (workspace_bytes < wf_lstm_bwd_seq_workspace_bytes(layers, F, L, T, N, G, Bw))
     return wf_fail(WF_EWORKSPACE, "lstm_bwd_seq: workspace too small");
   cudaStream_t st = (cudaStream_t)stream;
@@ -1151,8 +949,9 @@ extern "C" int wf_lstm_bwd_seq(const void* xT_hi, const void* xT_lo, const void*
   for (int l = layers - 1; l >= 0; --l) {
     const int kin = l == 0 ? F : L;
     float* XG = gates + l * g_elems;
-    const void* XTh = l == 0 ? xT_hi : (const void*)(hTh + (l - 1) * tsz);
-    const void* XTl = l == 0 ? xT_lo : (const void*)(hTl + (l - 1) * tsz);
+    // the input of layer l >= 1 is the (masked, when dropout is on) output of layer l - 1
+    const void* XTh = l == 0 ? xT_hi : (const void*)((drop ? hTmh : hTh) + (l - 1) * tsz);
+    const void* XTl = l == 0 ? xT_lo : (const void*)((drop ? hTml : hTl) + (l - 1) * tsz);
     SeqArgs a;
     memset(&a, 0, sizeof(a));
     a.XG = XG; a.Cst = const_cast<float*>(c) + l * c_elems; a.DGT = dgT;
@@ -1174,9 +973,10 @@ extern "C" int wf_lstm_bwd_seq(const void* xT_hi, const void* xT_lo, const void*
       for (int g = 0; g < G; ++g)
         cudaMemsetAsync(grads + g * grads_group_stride + P.w_hh[l], 0, sizeof(float) * 4 * L * L, st);
     }
-    if (l > 0) {  // dL/d(input of layer l) = dG W_ih -> ext of layer l-1 (TB4 in, TB4 out)
+    if (l > 0) {  // dL/d(input of layer l) = dG W_ih -> ext of layer l-1 (TB4 in, TB4 out), through layer l-1's mask
+      const DropCfg dc = wf_drop_cfg(p_drop, rng, WF_SITE_LSTM + l - 1);
       rc = wf_launch_g16_nodes(1, XG, 1, 4 * L, (const uint16_t*)pT16_hi + P.wihT[l], (const uint16_t*)pT16_lo + P.wihT[l], 4 * L,
-                               stride16(P.totalT), L, nullptr, nullptr, 0, DX, T, N, Bw, G, err, st);
+                               stride16(P.totalT), L, nullptr, nullptr, 0, DX, T, N, Bw, G, err, st, drop ? &dc : nullptr);
       if (rc) return rc;
     }
   }
@@ -1190,7 +990,7 @@ extern "C" int wf_lstm_seq_recur_fwd(float* gates_l, float* c_l, float* h_l, voi
                                      void* stream) {
   WF_REQUIRE(layers >= 1 && layers <= 8 && layer >= 0 && layer < layers && L == 128, "lstm_seq_recur_fwd: bad layer / L");
   static bool configured = false;
-  if (!configured) { int rc = seq_configure(wf_lstm_seq_fwd_kernel); if (rc) return rc; configured = true; }
+  if (!configured) { int rc = seq_configure(wf_lstm_seq_fwd16_kernel<false>); if (rc) return rc; configured = true; }
   const long long Z = (long long)G * Bw;
   CUtensorMap tmhi, tmlo;
   int rc = seq_maps_fwd(&tmhi, &tmlo, f16_hi, f16_lo, L, G * layers);
@@ -1201,13 +1001,7 @@ extern "C" int wf_lstm_seq_recur_fwd(float* gates_l, float* c_l, float* h_l, voi
   a.HT = (__nv_bfloat16*)hT_hi_l; a.HT_lo = (__nv_bfloat16*)hT_lo_l;
   a.T = T; a.Nn = N; a.Bw = Bw; a.tpw = wf_cdiv(N, 128); a.rpt = wf_tile_rows(N); a.Np = wf_np(N); a.RT = T * a.Np;
   a.slab0 = layer; a.slab_g = layers; a.err = err;
-  static const bool fwd16 = getenv("WF_SEQ_FWD8") == nullptr;
-  if (fwd16) {
-    static bool c16 = false;
-    if (!c16) { int rc16 = seq_configure(wf_lstm_seq_fwd16_kernel); if (rc16) return rc16; c16 = true; }
-    wf_lstm_seq_fwd16_kernel<<<dim3((unsigned)(2 * Z * a.tpw)), 512, SEQ_SMEM, (cudaStream_t)stream>>>(tmhi, tmlo, a);
-  } else
-  wf_lstm_seq_fwd_kernel<<<dim3((unsigned)(2 * Z * a.tpw)), SEQ_THREADS, SEQ_SMEM, (cudaStream_t)stream>>>(tmhi, tmlo, a);
+  wf_lstm_seq_fwd16_kernel<false><<<dim3((unsigned)(2 * Z * a.tpw)), 512, SEQ_SMEM, (cudaStream_t)stream>>>(tmhi, tmlo, a);
   WF_CHECK_LAUNCH("lstm_seq_recur_fwd");
   return WF_OK;
 }

@@ -16,6 +16,7 @@ per task (the replacement for ``copy.deepcopy(model)`` at train_hybrid_maml_v5.p
 """
 from __future__ import annotations
 
+import functools
 from dataclasses import dataclass
 
 import torch
@@ -81,6 +82,30 @@ def gcn_weights_from_state_dict(sd, device, prefix="base_stgcn."):
              sd[f"{prefix}conv{i}.bias"].detach().to(device, torch.float32).contiguous()) for i in range(1, 5)]
 
 
+# Dropout probabilities of the reference's training configuration: (GCN, LSTM inter-layer, head input) =
+# (STGCN dropout_rate, lstm_dropout, lstm_dropout) at train_hybrid_maml_v5.py:197,205.
+REFERENCE_DROPOUT = (0.2, 0.2, 0.2)
+
+ERR_MESSAGES = {41: "a GCN activation left the fp16 operand range (|x| >= 32768 or non-finite): normalise the input features "
+                    "(prepare_model_input(normalize=True)) or build the engine with precision='fp32'"}
+
+
+def model_dropout(hybrid_model):
+    """(p_gcn, p_lstm, p_head) of a HybridSTGCN_LSTM as the reference applies them (hybrid_model.py:47,58,67-73,108)."""
+    lstm = hybrid_model.lstm
+    p_lstm = float(getattr(lstm, "dropout", 0.0)) if getattr(lstm, "num_layers", 1) > 1 else 0.0
+    return (float(hybrid_model.base_stgcn.dropout.p), p_lstm, float(hybrid_model.dropout.p))
+
+
+def _on_device(fn):
+    """Run a launcher method with the engine's device current (streams and launches follow the current device)."""
+    @functools.wraps(fn)
+    def wrapped(self, *a, **kw):
+        with torch.cuda.device(self.device):
+            return fn(self, *a, **kw)
+    return wrapped
+
+
 class HybridEngine:
     """precision="tf32x3": dense products on the tcgen05 tensor cores with the 3xTF32 split
     (FP32-class accuracy, csrc/wf_tc.cuh); used when the model shape allows it (GCN width a
@@ -88,11 +113,22 @@ class HybridEngine:
     on the exact FP32 CUDA-core kernels (also the route for other shapes)."""
 
     def __init__(self, dims: V5Dims, G: int, Bw: int, device="cuda", keep_gcn_activations=False, precision="tf32x3",
-                 training=True, lstm_mode="persistent"):
+                 training=True, lstm_mode="persistent", dropout=(0.0, 0.0, 0.0), seed=0):
+        """dropout = (p_gcn, p_lstm, p_head): train-mode nn.Dropout at the reference's three sites (after GCN layers
+        1-3, between the LSTM layers, on the head input), as counter-based masks regenerated in the backward pass
+        (csrc/wf_rng.cuh); active while ``self.stochastic`` is set (``train()`` / ``eval()``)."""
         self.dims, self.G, self.Bw = dims, int(G), int(Bw)
         self.device = torch.device(device)
         if self.device.type != "cuda":
             raise RuntimeError("HybridEngine needs a CUDA device; there is no CPU fallback")
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
+        self.dropout = tuple(float(p) for p in dropout)
+        if len(self.dropout) != 3 or any(not (0.0 <= p < 1.0) for p in self.dropout):
+            raise ValueError("dropout must be three probabilities in [0, 1): (GCN, LSTM inter-layer, head)")
+        if dims.lstm_layers < 2:
+            self.dropout = (self.dropout[0], 0.0, self.dropout[2])  # nn.LSTM ignores dropout for a single layer
+        self.stochastic = bool(training) and any(p > 0 for p in self.dropout)
         if precision not in ("tf32x3", "fp32"):
             raise ValueError("precision must be 'tf32x3' or 'fp32'")
         _lib.load()
@@ -100,6 +136,8 @@ class HybridEngine:
         self.tc = precision == "tf32x3" and d.lstm_hidden == 128 and d.hidden % 128 == 0
         if lstm_mode not in ("persistent", "stepwise"):
             raise ValueError("lstm_mode must be 'persistent' or 'stepwise'")
+        if self.tc and lstm_mode == "stepwise" and (self.dropout[1] > 0 or self.dropout[2] > 0):
+            raise ValueError("lstm_mode='stepwise' (the 3xTF32 cross-check path) has no dropout; use 'persistent' or precision='fp32'")
         # persistent: one cluster launch per LSTM layer runs all T steps (csrc/wf_lstm_seq.cu);
         # stepwise: one tensor-core launch per (layer, step) (csrc/wf_tc_gemm.cu), kept as a cross-check
         self.seq = self.tc and lstm_mode == "persistent"
@@ -120,6 +158,13 @@ class HybridEngine:
             self.gates = torch.empty(Ls, self.rows, 4 * L, **f32)
             self.c = torch.empty(Ls, self.rows, L, **f32)
             self.h = torch.empty(Ls, self.rows, L, **f32)
+        # dropout state: {seed, forward-pass counter} on the device (kernels read it, wf_rng_advance bumps it on the stream)
+        self.rng = torch.tensor([int(seed), 0], dtype=torch.int64, device=self.device)
+        p_lstm, p_head = self.dropout[1], self.dropout[2]
+        self.hlast_m = torch.empty(self.W * d.num_nodes, L, **f32) if p_head > 0 else None
+        self.h_masked = None
+        if p_lstm > 0 and not self.tc:
+            self.h_masked = torch.empty(Ls - 1, self.rows, L, **f32)
         self.pred = torch.empty(self.W * d.num_nodes, d.O, **f32)
         self.dpred = torch.empty(self.W * d.num_nodes, d.O, **f32)
         self.loss = torch.zeros(self.W, **f32)
@@ -151,8 +196,11 @@ class HybridEngine:
                 self.featsT = torch.zeros(self.W * d.hidden * rt, **i16)
                 self.featsT_lo = torch.zeros(self.W * d.hidden * rt, **i16)
                 self.dgT = torch.zeros(self.W * 4 * L * rt, **f32)
+                # dropout on: transposed copies of the MASKED layer outputs (the next layer's input, for its dW_ih)
+                self.hTm = torch.zeros(Ls - 1, self.W * L * rt, **i16) if p_lstm > 0 else None
+                self.hTm_lo = torch.zeros(Ls - 1, self.W * L * rt, **i16) if p_lstm > 0 else None
             else:
-                self.hT = self.hT_lo = self.featsT = self.featsT_lo = self.dgT = None
+                self.hT = self.hT_lo = self.featsT = self.featsT_lo = self.dgT = self.hTm = self.hTm_lo = None
             self._gcn_lo = {}
         elif self.tc:
             ws = max(ws, _lib.query("wf_lstm_bwd_tc_workspace_bytes", Ls, d.hidden, L, d.window, d.num_nodes, self.G,
@@ -194,12 +242,29 @@ class HybridEngine:
                 out[l] = t.reshape(self.W, d.window, tpw * rpt, L)[:, :, :d.num_nodes].reshape(self.rows, L)
         return out
 
-    def check(self):
-        """Synchronise and raise if a tensor-core pipeline wait timed out (never expected)."""
-        code = int(self.err.item())
-        if code != 0:
-            raise RuntimeError(f"tcgen05 pipeline timeout (role code {code})")
+    def train(self, mode=True):
+        """Dropout on (if any p > 0) / off, like ``nn.Module.train()``."""
+        self.stochastic = bool(mode) and any(p > 0 for p in self.dropout)
+        return self
 
+    def eval(self):
+        return self.train(False)
+
+    def _p(self, site):
+        return self.dropout[site] if self.stochastic else 0.0
+
+    @_on_device
+    def advance_rng(self):
+        """Next forward pass draws fresh masks (enqueued on the stream: also advances under CUDA-graph replay)."""
+        _lib.call("wf_rng_advance", _lib.ptr(self.rng), _lib.stream_ptr())
+        self.launches += 1
+
+    def check(self):
+        """Synchronise and raise if a kernel flagged an error: a tensor-core pipeline wait that timed out (never
+        expected) or an activation outside the fp16 operand range."""
+        raise_on_error_code(int(self.err.item()))
+
+    @_on_device
     def _gcn_w_lo(self, Wt):
         """Cached operand staging of a GCN weight: TF32 lo half (stepwise path) or fp16 (hi, lo) (persistent path)."""
         key = (Wt.data_ptr(), Wt._version)
@@ -218,8 +283,10 @@ class HybridEngine:
         return lo
 
     # ------------------------------------------------------------------ GCN stack
+    @_on_device
     def gcn_forward(self, X, x_ld, x_win_stride, x_win_off, gcn_weights, graphs):
-        """4 x relu(GCNConv) with dropout off; returns the [G*Bw*R, hidden] feature buffer."""
+        """4 x relu(GCNConv), dropout after all layers but the last (hybrid_model.py:65-76); returns the
+        [G*Bw*R, hidden] feature buffer."""
         d, st = self.dims, _lib.stream_ptr()
         if isinstance(graphs, RegionGraph):
             rp, cl, vl, rps, cs = graphs.rowptr, graphs.col, graphs.val, 0, 0
@@ -237,6 +304,7 @@ class HybridEngine:
             dst = self.act[i] if self.keep_gcn else self.act[i & 1]
             dense = src_off is None and src_ld == cin and src_stride == d.R * cin
             in_place = src_off is not None and src_ld == cin and gmax > 0  # windows read straight from the features
+            p_drop = self._p(0) if i < nlayers - 1 else 0.0
             if self.seq and (dense or in_place) and cin % 8 == 0 and (cin % 64 == 0 or src.data_ptr() % 16 == 0):
                 want_t = self.training and i == nlayers - 1
                 w16 = self._gcn_w_lo(Wt)
@@ -247,7 +315,8 @@ class HybridEngine:
                           _lib.ptr(rp), _lib.ptr(cl), _lib.ptr(vl), rps, cs, _lib.ptr(gl) if gmax > 0 else None, gmax, gls,
                           _lib.ptr(self.agg), d.R, d.num_nodes, cin, d.hidden, self.G,
                           self.Bw, 1, _lib.ptr(dst), _lib.ptr(self.featsT) if want_t else None,
-                          _lib.ptr(self.featsT_lo) if want_t else None, _lib.ptr(self.err), st)
+                          _lib.ptr(self.featsT_lo) if want_t else None, p_drop, _lib.ptr(self.rng), i, _lib.ptr(self.err), st)
+                p_drop = 0.0  # fused into the epilogue
             elif self.tc and not self.seq and dense and cin % 32 == 0:
                 want_t = self.training and i == nlayers - 1
                 _lib.call("wf_gcn_layer_fwd_tc", _lib.ptr(src), _lib.ptr(Wt), _lib.ptr(self._gcn_w_lo(Wt)), _lib.ptr(b),
@@ -259,15 +328,21 @@ class HybridEngine:
                           _lib.ptr(b), 0, 0, _lib.ptr(rp), _lib.ptr(cl), _lib.ptr(vl), rps, cs, d.R, cin, d.hidden,
                           self.G, self.Bw, 1, _lib.ptr(dst), st)
             self.launches += 1
+            if p_drop > 0:  # paths without a fused epilogue mask: the same mask as a separate pass
+                _lib.call("wf_dropout_apply", _lib.ptr(dst), 0, self.rows, d.hidden, self.rows, d.hidden, p_drop,
+                          _lib.ptr(self.rng), i, _lib.ptr(dst), st)
+                self.launches += 1
             src, src_ld, src_stride, src_off, cin = dst, d.hidden, d.R * d.hidden, None, d.hidden
         self.feats = src
         return src
 
     # ------------------------------------------------------------------ LSTM + head
+    @_on_device
     def lstm_head_forward(self, params, params_stride, feats=None):
         d, st = self.dims, _lib.stream_ptr()
         feats = self.feats if feats is None else feats
         Ls, L = d.lstm_layers, d.lstm_hidden
+        p_lstm, p_head = self._p(1), self._p(2)
         if self.seq:
             # operand staging: 16-bit hi/lo copies of the current (fast) weights
             src_stride = params_stride if self.G > 1 else self.P
@@ -277,7 +352,8 @@ class HybridEngine:
             _lib.call("wf_lstm_fwd_seq", _lib.ptr(feats), _lib.ptr(params), _lib.ptr(self.p16[0]), _lib.ptr(self.p16[1]),
                       params_stride if self.G > 1 else self.P, _lib.ptr(self.w16[0]), _lib.ptr(self.w16[1]), Ls, d.hidden,
                       L, d.O, d.window, d.num_nodes, self.G, self.Bw, _lib.ptr(self.gates), _lib.ptr(self.h),
-                      _lib.ptr(self.c), _lib.ptr(self.hT), _lib.ptr(self.hT_lo), _lib.ptr(self.err), st)
+                      _lib.ptr(self.c), _lib.ptr(self.hT), _lib.ptr(self.hT_lo), p_lstm, _lib.ptr(self.rng),
+                      _lib.ptr(self.hTm), _lib.ptr(self.hTm_lo), _lib.ptr(self.err), st)
             self.launches += (1 + (Ls - 1) + 1) + 2 * Ls  # operand staging, then (projection + recurrence) per layer
         elif self.tc:
             # operand staging for 3xTF32: lo halves and transposed copies of the current weights
@@ -290,13 +366,25 @@ class HybridEngine:
             self.launches += 2 * Ls + Ls * (1 + d.window)
         else:
             _lib.call("wf_lstm_fwd", _lib.ptr(feats), _lib.ptr(params), params_stride, Ls, d.hidden, L, d.O, d.window,
-                      d.num_nodes, self.G, self.Bw, _lib.ptr(self.gates), _lib.ptr(self.h), _lib.ptr(self.c), st)
-            self.launches += Ls * (1 + d.window)
-        _lib.call("wf_head_fwd", _lib.ptr(self.h[Ls - 1]), _lib.ptr(params), params_stride, Ls, d.hidden, L, d.O,
-                  d.window, d.num_nodes, self.G, self.Bw, _lib.ptr(self.pred), st)
+                      d.num_nodes, self.G, self.Bw, _lib.ptr(self.gates), _lib.ptr(self.h), _lib.ptr(self.c), p_lstm,
+                      _lib.ptr(self.rng), _lib.ptr(self.h_masked), st)
+            self.launches += Ls * (1 + d.window) + (Ls - 1 if p_lstm > 0 else 0)
+        if p_head > 0:
+            # head-input dropout (hybrid_model.py:108): mask the last step of the top layer into a compact [W*N, L]
+            # buffer, which the head then reads as a window of ONE step
+            _lib.call("wf_dropout_apply", _lib.ptr(self.h[Ls - 1].view(-1)[(d.window - 1) * d.num_nodes * L:]), d.R * L,
+                      d.num_nodes, L, self.W * d.num_nodes, L, p_head, _lib.ptr(self.rng), SITE_HEAD,
+                      _lib.ptr(self.hlast_m), st)
+            _lib.call("wf_head_fwd", _lib.ptr(self.hlast_m), _lib.ptr(params), params_stride, Ls, d.hidden, L, d.O,
+                      1, d.num_nodes, self.G, self.Bw, _lib.ptr(self.pred), st)
+            self.launches += 1
+        else:
+            _lib.call("wf_head_fwd", _lib.ptr(self.h[Ls - 1]), _lib.ptr(params), params_stride, Ls, d.hidden, L, d.O,
+                      d.window, d.num_nodes, self.G, self.Bw, _lib.ptr(self.pred), st)
         self.launches += 1
         return self.pred
 
+    @_on_device
     def mse(self, y=None, feat=None, tgt_off=None, feat_ld=0, grad_scale=1.0, want_grad=True):
         """Per-window nn.MSELoss (+ backward seed) against explicit y or in-place targets."""
         d = self.dims
@@ -306,15 +394,26 @@ class HybridEngine:
         self.launches += 1
         return self.loss
 
+    @_on_device
     def backward(self, params, params_stride, feats=None, dpred=None):
-        """BPTT from ``dpred`` (default: the seed left by ``mse``) into ``self.grads`` [G, P]."""
+        """BPTT from ``dpred`` (default: the seed left by ``mse``) into ``self.grads`` [G, P].  With dropout on, the
+        masks of the forward pass are regenerated from (seed, pass counter): call before ``advance_rng()``."""
         d, st = self.dims, _lib.stream_ptr()
         feats = self.feats if feats is None else feats
         dpred = self.dpred if dpred is None else dpred
         Ls, L = d.lstm_layers, d.lstm_hidden
-        _lib.call("wf_head_bwd", _lib.ptr(dpred), _lib.ptr(self.h[Ls - 1]), _lib.ptr(params), params_stride, Ls,
-                  d.hidden, L, d.O, d.window, d.num_nodes, self.G, self.Bw, _lib.ptr(self.dlast),
-                  _lib.ptr(self.grads), self.P, _lib.ptr(self.ws), self.ws_bytes, st)
+        p_lstm, p_head = self._p(1), self._p(2)
+        if p_head > 0:
+            _lib.call("wf_head_bwd", _lib.ptr(dpred), _lib.ptr(self.hlast_m), _lib.ptr(params), params_stride, Ls,
+                      d.hidden, L, d.O, 1, d.num_nodes, self.G, self.Bw, _lib.ptr(self.dlast),
+                      _lib.ptr(self.grads), self.P, _lib.ptr(self.ws), self.ws_bytes, st)
+            _lib.call("wf_dropout_apply", _lib.ptr(self.dlast), 0, self.W * d.num_nodes, L, self.W * d.num_nodes, L, p_head,
+                      _lib.ptr(self.rng), SITE_HEAD, _lib.ptr(self.dlast), st)
+            self.launches += 1
+        else:
+            _lib.call("wf_head_bwd", _lib.ptr(dpred), _lib.ptr(self.h[Ls - 1]), _lib.ptr(params), params_stride, Ls,
+                      d.hidden, L, d.O, d.window, d.num_nodes, self.G, self.Bw, _lib.ptr(self.dlast),
+                      _lib.ptr(self.grads), self.P, _lib.ptr(self.ws), self.ws_bytes, st)
         if self.tc:
             if not self.training:
                 raise RuntimeError("engine was built with training=False")
@@ -323,6 +422,7 @@ class HybridEngine:
                           _lib.ptr(self.pT16[1]), _lib.ptr(self.w16[2]), _lib.ptr(self.w16[3]), Ls, d.hidden, L, d.O,
                           d.window, d.num_nodes, self.G, self.Bw, _lib.ptr(self.gates), _lib.ptr(self.c), _lib.ptr(self.hT),
                           _lib.ptr(self.hT_lo), _lib.ptr(self.dgT), _lib.ptr(self.dlast), _lib.ptr(self.grads), self.P,
+                          p_lstm, _lib.ptr(self.rng), _lib.ptr(self.hTm), _lib.ptr(self.hTm_lo),
                           _lib.ptr(self.ws), self.ws_bytes, _lib.ptr(self.err), st)
                 self.launches += 6 + Ls * 7 - 1  # head bwd + per layer: recurrence, colsum, 2 x (wgrad + split sum), dX
             else:
@@ -335,10 +435,12 @@ class HybridEngine:
         else:
             _lib.call("wf_lstm_bwd", _lib.ptr(feats), _lib.ptr(params), params_stride, Ls, d.hidden, L, d.O, d.window,
                       d.num_nodes, self.G, self.Bw, _lib.ptr(self.gates), _lib.ptr(self.h), _lib.ptr(self.c),
-                      _lib.ptr(self.dlast), _lib.ptr(self.grads), self.P, _lib.ptr(self.ws), self.ws_bytes, st)
-            self.launches += 6 + Ls * (d.window + 9)
+                      _lib.ptr(self.dlast), _lib.ptr(self.grads), self.P, p_lstm, _lib.ptr(self.rng),
+                      _lib.ptr(self.h_masked), _lib.ptr(self.ws), self.ws_bytes, st)
+            self.launches += 6 + Ls * (d.window + 9) + (Ls - 1 if p_lstm > 0 else 0)
         return self.grads
 
+    @_on_device
     def sgd_step(self, fast, lr, max_norm=1.0):
         """fast[g] -= lr * clip(grads[g]) for every task (train_hybrid_maml_v5.py:135-139)."""
         _lib.call("wf_clip_sgd_step", _lib.ptr(fast), self.P, _lib.ptr(self.grads), self.P, self.P, self.G, float(lr),
@@ -353,7 +455,21 @@ class HybridEngine:
         self.lstm_head_forward(params, params_stride)
         self.mse(y, feat, tgt_off, feat_ld, grad_scale)
         self.backward(params, params_stride)
+        if self.stochastic:
+            self.advance_rng()
         return self.loss, self.grads
+
+
+SITE_HEAD = 32  # csrc/wf_rng.cuh: GCN layer i = i, LSTM layer l = 16 + l, head input = 32
+SITE_LSTM = 16
+
+
+def raise_on_error_code(code):
+    if code == 0:
+        return
+    if code in ERR_MESSAGES:
+        raise RuntimeError(f"wf_stgcn device error {code}: {ERR_MESSAGES[code]}")
+    raise RuntimeError(f"tcgen05 pipeline timeout (role code {code})")
 
 
 class AdamState:
@@ -367,12 +483,15 @@ class AdamState:
         self.decoupled, self.step_count = bool(decoupled), 0
         # ring of pinned staging slots: the async H2D of step t must not be overwritten by the
         # host preparing step t+1 while the stream still lags behind
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
         self.hyper_host = torch.zeros(2048, 8, dtype=torch.float32).pin_memory()
         self.hyper = torch.zeros(8, dtype=torch.float32, device=device)
         self.norm = torch.zeros(1, dtype=torch.float32, device=device)
         self.ws_bytes = int(_lib.query("wf_optim_workspace_bytes", 1))
         self.ws = torch.empty(self.ws_bytes, dtype=torch.uint8, device=device)
 
+    @_on_device
     def step(self, theta, grad, max_norm=1.0, grad_scale=1.0):
         self.step_count += 1
         b1, b2 = self.betas

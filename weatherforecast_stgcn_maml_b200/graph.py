@@ -47,6 +47,10 @@ class RegionGraph:
         self._ws = ws  # keep alive until the stream has consumed it
         self._gather_rows = None
         _ = self.gather_rows  # computed eagerly (it synchronises): never inside a CUDA-graph capture
+        # wf_csr_count_kernel flags an edge outside [0, R) in workspace int[4R] (csrc/wf_graph.cu); the host check above
+        # makes that unreachable, but a corrupted graph must not be normalised silently
+        if int(ws.view(torch.int32)[4 * self.R].item()) != 0:
+            raise IndexError("wf_gcn_norm_csr: edge_index references a row outside the window")
 
     @property
     def gather_rows(self):

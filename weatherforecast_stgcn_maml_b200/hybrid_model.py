@@ -9,10 +9,10 @@ configuration).  ``forward(x, edge_index)`` reproduces the referen
   batched recurrence over all nodes (functional.LSTMHead -> wf_lstm_fwd / wf_lstm_bwd);
 * predictions come back as ``[N*H, out]`` with row = node*H + h (hybrid_model.py:114-115).
 
-Dropout: the fused kernels implement the deterministic path (eval mode, or p = 0 as in the
-parity configuration).  In train mode with p > 0 the three dropout sites (GCN, LSTM inter-layer,
-head input) fall back to sampling masks with torch and applying them between launches, which
-costs extra passes but keeps the reference's training semantics.
+Dropout: in train mode the three sites of the reference (after GCN layers 1-3 at
+hybrid_model.py:67-73, between the LSTM layers :47, on the head input :108) are fused into the
+kernels as counter-based masks (csrc/wf_rng.cuh) that the backward pass regenerates; torch's
+generator stream cannot be matched by a batched kernel, the distribution is.
 """
 from __future__ import annotations
 
@@ -23,7 +23,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from . import functional as WF
-from .engine import V5Dims, trainable_layout
+from .engine import V5Dims, model_dropout, trainable_layout
 from .model import STGCN  # noqa: F401  (same import as the reference module)
 
 
@@ -82,19 +82,14 @@ class HybridSTGCN_LSTM(nn.Module):
         sd = dict(self.named_parameters())
         return torch.cat([sd[name].reshape(-1) for name, _, _ in trainable_layout(dims)])
 
-    def _stochastic(self):
-        return self.training and (self.dropout.p > 0 or self.lstm.dropout > 0 or self.base_stgcn.dropout.p > 0)
-
     # -- reference API -------------------------------------------------------------------
     def extract_base_features(self, x, edge_index):
         with torch.no_grad():
             b = self.base_stgcn
-            h = b.conv1(x, edge_index, _fuse_relu=True)
-            h = b.dropout(h)
-            h = b.conv2(h, edge_index, _fuse_relu=True)
-            h = b.dropout(h)
-            h = b.conv3(h, edge_index, _fuse_relu=True)
-            h = b.dropout(h)
+            p = float(b.dropout.p) if b.dropout.training else 0.0  # nn.Dropout follows its own .training flag
+            h = b.conv1(x, edge_index, _fuse_relu=True, _dropout=p, _site=0)
+            h = b.conv2(h, edge_index, _fuse_relu=True, _dropout=p, _site=1)
+            h = b.conv3(h, edge_index, _fuse_relu=True, _dropout=p, _site=2)
             h = b.conv4(h, edge_index, _fuse_relu=True)  # no final dropout (hybrid_model.py:76)
         return h
 
@@ -103,11 +98,9 @@ class HybridSTGCN_LSTM(nn.Module):
         window = self.base_stgcn.window_size
         num_nodes = base_features.shape[0] // window
         dims = self.dims(num_nodes)
-        if self.training and (self.dropout.p > 0 or self.lstm.dropout > 0):
-            raise NotImplementedError(
-                "train-mode LSTM/head dropout is not implemented by the fused kernels yet; construct the model "
-                "with lstm_dropout=0.0 or call .eval() (the parity configuration, SURVEY.md D11)")
-        pred = WF.lstm_head(base_features, self.flat_trainable(dims), dims, 1)  # [N, H*out]
+        _, p_lstm, p_head = model_dropout(self)
+        drop = (p_lstm if self.lstm.training else 0.0, p_head if self.dropout.training else 0.0)
+        pred = WF.lstm_head(base_features, self.flat_trainable(dims), dims, 1, dropout=drop)  # [N, H*out]
         return pred.view(num_nodes, self.forecast_horizon, self.out_channels).reshape(-1, self.out_channels)
 
     def get_trainable_parameters(self):

@@ -4,8 +4,10 @@ Same constructor signature, attribute names (``conv1..conv4``, ``dropout``, ``ou
 ``window_size``), ``forward(x [T*N, C], edge_index [2, E]) -> [H*N, out]`` and ``state_dict``
 keys (``convN.bias``, ``convN.lin.weight``, ``output_layer.{weight,bias}``) as the reference
 class over PyG >= 2.0.  The four convolutions run on the fused CUDA GCN layer
-(functional.GCNConvReLU); the graph normalisation PyG recomputes on every call is cached per
-``edge_index`` tensor (graph.graph_for).
+(functional.GCNConvReLU: tensor cores where the widths allow, ReLU and train-mode dropout in the
+epilogue); the graph normalisation PyG recomputes on every call is cached per ``edge_index``
+tensor (graph.graph_for); the Linear head of ``STGCN.forward`` is the C-ABI head kernel
+(functional.LinearRows), not cuBLAS.
 """
 from __future__ import annotations
 
@@ -48,9 +50,11 @@ class GCNConv(nn.Module):
         with torch.no_grad():
             self.bias.zero_()
 
-    def forward(self, x, edge_index, _fuse_relu=False):
+    def forward(self, x, edge_index, _fuse_relu=False, _dropout=0.0, _site=0):
+        """``_fuse_relu`` / ``_dropout`` / ``_site``: ReLU and nn.Dropout(p) (mask site = layer index) fused into the
+        layer's epilogue -- what STGCN.forward and HybridSTGCN_LSTM.extract_base_features do right after the conv."""
         graph = graph_for(edge_index, x.shape[0], x.device)
-        return WF.gcn_conv(x, self.lin.weight, self.bias, graph, relu=_fuse_relu)
+        return WF.gcn_conv(x, self.lin.weight, self.bias, graph, relu=_fuse_relu, p_drop=_dropout, site=_site)
 
 
 class STGCN(nn.Module):
@@ -68,13 +72,17 @@ class STGCN(nn.Module):
         self.dropout = nn.Dropout(p=dropout_rate)
         self.output_layer = nn.Linear(hidden_channels, out_channels * forecast_horizon)
 
+    def _p(self):
+        """Probability of ``self.dropout`` (an nn.Dropout kept for attribute / state compatibility) when it is active."""
+        return float(self.dropout.p) if self.training else 0.0
+
     def forward(self, x, edge_index):
-        # conv -> relu (fused into the GEMM epilogue) -> dropout, four times (model.py:31-42)
-        for conv in (self.conv1, self.conv2, self.conv3, self.conv4):
-            x = conv(x, edge_index, _fuse_relu=True)
-            x = self.dropout(x)
+        # conv -> relu -> dropout, four times (model.py:31-42), each as ONE fused layer launch
+        p = self._p()
+        for i, conv in enumerate((self.conv1, self.conv2, self.conv3, self.conv4)):
+            x = conv(x, edge_index, _fuse_relu=True, _dropout=p, _site=i)
         num_nodes = x.shape[0] // self.window_size
         x = x[-num_nodes:]  # last time slice (model.py:45-48)
-        x = self.output_layer(x)
+        x = WF.linear_rows(x, self.output_layer.weight, self.output_layer.bias)
         x = x.view(num_nodes, self.forecast_horizon, self.out_channels)
         return x.reshape(-1, self.out_channels)

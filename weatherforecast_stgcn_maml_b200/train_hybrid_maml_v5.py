@@ -21,6 +21,11 @@ the code, with each quirk an explicit, defaulted switch:
   both readings.)
 * D8  Every loader is batch-1; "batch B" means B independent windows.
 * D4/D10  No gradient reaches ``base_stgcn`` or ``KoppenEmbedding``; their tensors are untouched.
+* D11 Dropout.  The reference trains with it ON: the copies are put in ``.train()`` mode (:113,:159) and the model
+  is built with ``dropout_rate=0.2, lstm_dropout=0.2`` (:197,:205).  ``inner_loop_v4`` / ``meta_update_v4`` therefore
+  take the three probabilities from the model they are given (``engine.model_dropout``) and ``MetaTrainer`` defaults to
+  the reference's values; the masks are fused, counter-based and regenerated in backward (csrc/wf_rng.cuh).  Parity
+  tests build their models with p = 0 (torch's generator stream cannot be matched by a batched kernel).
 
 ``MetaTrainer`` is the device-resident form of the same loop (features and graphs stay in HBM,
 windows are offsets, the meta-step is one CUDA graph, AdamW is the fused kernel, and with
@@ -36,8 +41,8 @@ import torch.nn as nn
 
 from . import _lib
 from .dataset import unwrap_subset
-from .engine import (AdamState, HybridEngine, V5Dims, flatten_trainable, gcn_weights_from_state_dict,
-                     trainable_layout, unflatten_trainable)
+from .engine import (REFERENCE_DROPOUT, AdamState, HybridEngine, V5Dims, flatten_trainable, gcn_weights_from_state_dict,
+                     model_dropout, raise_on_error_code, trainable_layout, unflatten_trainable)
 from .graph import RegionGraph, StackedGraphs
 
 # ========== MODEL 4.0 ULTRA SCALED CONFIG (train_hybrid_maml_v5.py:21-38) ==========
@@ -155,8 +160,8 @@ def _model_dims(hybrid_model, num_nodes):
 class _GroupRunner:
     """Inner loops + query pass of one accumulation group of tasks, in lock-step."""
 
-    def __init__(self, dims, G, device):
-        self.engine = HybridEngine(dims, G, 1, device)
+    def __init__(self, dims, G, device, dropout=(0.0, 0.0, 0.0), seed=SEED):
+        self.engine = HybridEngine(dims, G, 1, device, dropout=dropout, seed=seed)
         self.dims, self.G, self.device = dims, G, torch.device(device)
         self.fast = torch.empty(G, self.engine.P, dtype=torch.float32, device=device)
 
@@ -177,12 +182,13 @@ class _GroupRunner:
 _RUNNERS = {}
 
 
-def _runner(dims, G, device):
-    key = (dims, G, str(torch.device(device)))
+def _runner(dims, G, device, dropout=(0.0, 0.0, 0.0)):
+    dropout = tuple(float(p) for p in dropout)
+    key = (dims, G, str(torch.device(device)), dropout)
     if key not in _RUNNERS:
         if len(_RUNNERS) > 4:
             _RUNNERS.clear()
-        _RUNNERS[key] = _GroupRunner(dims, G, device)
+        _RUNNERS[key] = _GroupRunner(dims, G, device, dropout)
     return _RUNNERS[key]
 
 
@@ -231,22 +237,25 @@ def inner_loop_v4(hybrid_model, koppen_embed, support_ds, device):
 
     INNER_EPOCHS_PER_TASK passes over the first 15 support windows, each step: forward, MSE,
     backward, clip_grad_norm_(1.0), SGD(lr=INNER_LR).  Returns ``(temp_model, temp_koppen)``
-    (deep copies in train mode, like the reference)."""
+    (deep copies in train mode, like the reference).  The copy trains in ``.train()`` mode (:113): dropout runs
+    with the model's own probabilities."""
     sds, _ = unwrap_subset(support_ds)
     dims = _model_dims(hybrid_model, sds.num_nodes)
     sd = {k: v.detach() for k, v in hybrid_model.state_dict().items()}
     stager, graphs, sup_x, sup_t, qry_x, qry_t = _stage_group(
         [(support_ds, support_ds)], dims, device, reference_support_schedule, lambda q: q[0])
-    run = _runner(dims, 1, device)
+    run = _runner(dims, 1, device, model_dropout(hybrid_model))
     theta = flatten_trainable(sd, dims, device)
     gcn_w = gcn_weights_from_state_dict(sd, device)
     buf = stager.upload()
     e = run.engine
+    e.train()
     run.fast.copy_(theta.unsqueeze(0))
     for s in range(sup_x.shape[0]):
         e.forward_backward(buf, dims.in_channels, 0, sup_x[s], gcn_w, graphs, run.fast, e.P,
                            feat=buf, tgt_off=sup_t[s], feat_ld=dims.in_channels, grad_scale=1.0)
         e.sgd_step(run.fast, INNER_LR, 1.0)
+    e.check()  # a kernel-side error must not end up in the returned weights
     temp_model = copy.deepcopy(hybrid_model)
     temp_koppen = copy.deepcopy(koppen_embed)
     _load_flat_into(temp_model, run.fast[0], dims)
@@ -277,11 +286,13 @@ def meta_update_v4(hybrid_model, koppen_embed, tasks, device, meta_optimizer, li
         sd = {k: v.detach() for k, v in hybrid_model.state_dict().items()}
         stager, graphs, sup_x, sup_t, qry_x, qry_t = _stage_group(
             [(s, q) for s, q, *_ in group], dims, device, schedule, lambda q: q[0])
-        run = _runner(dims, len(group), device)
+        run = _runner(dims, len(group), device, model_dropout(hybrid_model))
+        run.engine.train()  # :113, :159 -- both the inner loop and the query pass run in train mode
         theta = flatten_trainable(sd, dims, device)
         gcn_w = gcn_weights_from_state_dict(sd, device)
         buf = stager.upload()
         loss = run.run(theta, gcn_w, graphs, buf, sup_x, sup_t, qry_x, qry_t, INNER_LR, accum)
+        run.engine.check()
         if not literal_reference:
             meta_grad = run.engine.grads.sum(dim=0)
             for name, g in unflatten_trainable(meta_grad, dims).items():
@@ -304,11 +315,15 @@ class MetaTrainer:
     collective, if torch.distributed is initialised) and applied by the fused clip+AdamW kernel.
     ``accum`` is the divisor of the query loss (default: global task count, i.e. the reference
     with GRAD_ACCUMULATION_STEPS = number of tasks).
+    ``dropout`` = (p_gcn, p_lstm, p_head), default the reference's training configuration (0.2 at each site:
+    train_hybrid_maml_v5.py:197,205); pass ``(0, 0, 0)`` for the deterministic parity configuration.  Ranks draw
+    different masks (``seed + rank``).  ``meta_step()`` returns the device loss without synchronising; kernel-side
+    error flags travel with it and are raised by ``read_loss()``, ``state_dict()`` and ``check()``.
     """
 
     def __init__(self, state_dict, tasks, dims: V5Dims, device="cuda", support_rows=(0, 1, 2), query_row=None,
                  inner_lr=INNER_LR, outer_lr=OUTER_LR, weight_decay=1e-4, accum=None, use_cuda_graph=True,
-                 process_group=None, distributed=None, host_staging=False):
+                 process_group=None, distributed=None, host_staging=False, dropout=REFERENCE_DROPOUT, seed=SEED):
         import torch.distributed as dist
 
         self.dims, self.device = dims, torch.device(device)
@@ -349,7 +364,8 @@ class MetaTrainer:
         self.sd = {k: v.detach().clone() for k, v in state_dict.items()}
         self.theta = flatten_trainable(self.sd, d, self.device)
         self.gcn_w = gcn_weights_from_state_dict(self.sd, self.device)
-        self.engine = HybridEngine(d, self.G, 1, self.device)
+        rank = self.dist.get_rank(self.pg) if self.dist else 0
+        self.engine = HybridEngine(d, self.G, 1, self.device, dropout=dropout, seed=int(seed) + rank)
         self.P = self.engine.P
         self.fast = torch.empty(self.G, self.P, dtype=torch.float32, device=self.device)
         self.meta = torch.zeros(self.P + 4, dtype=torch.float32, device=self.device)  # grad + packed loss
@@ -374,6 +390,7 @@ class MetaTrainer:
                   _lib.stream_ptr())
         e.launches += 1
         self.meta[self.P:self.P + 1].copy_((e.loss.sum() / self.accum).reshape(1))
+        self.meta[self.P + 1:self.P + 2].copy_(e.err.to(torch.float32))  # error flag rides with the loss (summed over ranks)
 
     def _run_body(self, k=0):
         """Replay (capturing on first use) the CUDA graph of the meta-step body that reads staging buffer k."""
@@ -436,6 +453,16 @@ class MetaTrainer:
         self.adam.step(self.theta, self.meta, max_norm=1.0)
         return self.meta[self.P]
 
+    def read_loss(self):
+        """Synchronise, raise if any rank's kernels flagged an error during the last step, return the meta-loss."""
+        loss, err = self.meta[self.P:self.P + 2].tolist()
+        if err != 0.0:
+            raise_on_error_code(int(self.engine.err.item()) or int(err))
+        return loss
+
+    def check(self):
+        self.read_loss()
+
     def set_lr(self, lr):
         self.adam.lr = float(lr)
 
@@ -444,6 +471,7 @@ class MetaTrainer:
 
     def state_dict(self):
         """Hybrid ``state_dict`` with the current meta-parameters (CPU tensors)."""
+        self.check()  # never hand out (or checkpoint) weights a failed kernel may have corrupted
         out = {k: v.clone() for k, v in self.sd.items()}
         for name, t in unflatten_trainable(self.theta.detach().cpu(), self.dims).items():
             out[name] = t.clone()
