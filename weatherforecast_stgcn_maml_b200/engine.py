@@ -267,8 +267,10 @@ class HybridEngine:
     @_on_device
     def _gcn_w_lo(self, Wt):
         """Cached operand staging of a GCN weight: TF32 lo half (stepwise path) or fp16 (hi, lo) (persistent path)."""
+        # the entry keeps the weight tensor alive: an address can then not be reused by another tensor while it is cached
         key = (Wt.data_ptr(), Wt._version)
-        lo = self._gcn_lo.get(key)
+        hit = self._gcn_lo.get(key)
+        lo = hit[1] if hit is not None and hit[0] is Wt else None
         if lo is None:
             if self.seq:
                 lo = (torch.empty(Wt.shape, dtype=torch.int16, device=Wt.device),
@@ -279,7 +281,7 @@ class HybridEngine:
                 _lib.call("wf_split_lo", _lib.ptr(Wt), _lib.ptr(lo), Wt.numel(), _lib.stream_ptr())
             if len(self._gcn_lo) > 16:
                 self._gcn_lo.clear()
-            self._gcn_lo[key] = lo
+            self._gcn_lo[key] = (Wt, lo)
         return lo
 
     # ------------------------------------------------------------------ GCN stack

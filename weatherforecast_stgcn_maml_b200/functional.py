@@ -56,7 +56,6 @@ class _DeviceState:
         self.rng = torch.tensor([seed, 0], dtype=torch.int64, device=device)
         self.err = torch.zeros(1, dtype=torch.int32, device=device)
         self.err_host = torch.zeros(1, dtype=torch.int32).pin_memory()
-        self.w16 = {}
         self.engines = {}
 
     def rng_snapshot(self):
@@ -76,16 +75,17 @@ class _DeviceState:
     def publish_errors(self):
         self.err_host.copy_(self.err, non_blocking=True)
 
-    def split_weight(self, w):
-        key = (w.data_ptr(), w._version, tuple(w.shape))
-        hit = self.w16.get(key)
-        if hit is None:
-            hit = (torch.empty(w.shape, dtype=torch.int16, device=w.device), torch.empty(w.shape, dtype=torch.int16, device=w.device))
-            _lib.call("wf_split16", _lib.ptr(w), _lib.ptr(hit[0]), _lib.ptr(hit[1]), w.numel(), 0, _lib.stream_ptr())
-            if len(self.w16) > 32:
-                self.w16.clear()
-            self.w16[key] = hit
-        return hit
+
+
+def split_weight16(w):
+    """fp16 (hi, lo) operand halves of a weight matrix (wf_split16).  Callers that own the weight cache the pair
+    themselves, keyed by (data_ptr, _version) -- see model.GCNConv; a device-wide cache keyed by address would hand a
+    new tensor allocated at a freed address somebody else's operands."""
+    with torch.cuda.device(w.device):
+        hi = torch.empty(w.shape, dtype=torch.int16, device=w.device)
+        lo = torch.empty(w.shape, dtype=torch.int16, device=w.device)
+        _lib.call("wf_split16", _lib.ptr(w), _lib.ptr(hi), _lib.ptr(lo), w.numel(), 0, _lib.stream_ptr())
+    return hi, lo
 
 
 _STATES = {}
@@ -120,7 +120,7 @@ class GCNConvReLU(torch.autograd.Function):
     ``p_drop`` > 0 applies nn.Dropout after the ReLU (model.py:33-42) as site ``site`` (the layer index)."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, graph: RegionGraph, relu: bool, p_drop: float = 0.0, site: int = 0):
+    def forward(ctx, x, weight, bias, graph: RegionGraph, relu: bool, p_drop: float = 0.0, site: int = 0, w16=None):
         _lib.require_cuda(x, weight, bias)
         x, weight, bias = _f32c(x), _f32c(weight), _f32c(bias)
         rows, cin = x.shape
@@ -137,7 +137,7 @@ class GCNConvReLU(torch.autograd.Function):
             s = _lib.stream_ptr()
             fast = _PRECISION == "tf32x3" and cout % 128 == 0 and cin % 8 == 0 and x.data_ptr() % 16 == 0
             if fast:
-                hi, lo = st.split_weight(weight.detach())
+                hi, lo = w16 if w16 is not None else split_weight16(weight.detach())
                 gl = graph.gather_rows
                 gmax = int(gl.numel())
                 agg = torch.empty(rows, cin, dtype=torch.float32, device=x.device) if gmax > 0 else None
@@ -179,7 +179,7 @@ class GCNConvReLU(torch.autograd.Function):
                       _lib.ptr(weight), 0, _lib.ptr(graph.rowptr), _lib.ptr(graph.col), _lib.ptr(graph.val),
                       _lib.ptr(graph.rowptr_t), _lib.ptr(graph.col_t), _lib.ptr(graph.val_t), 0, 0, graph.R, cin, cout,
                       1, bw, int(ctx.relu), _lib.ptr(dx), _lib.ptr(dw), _lib.ptr(db), 0, 0, _lib.ptr(ws), nbytes, s)
-        return dx, dw, db, None, None, None, None
+        return dx, dw, db, None, None, None, None, None
 
 
 # ------------------------------------------------------------------------------------------ LSTM + head
@@ -229,7 +229,7 @@ class LSTMHead(torch.autograd.Function):
         if feats.shape != (rows, d.hidden):
             raise ValueError(f"features {tuple(feats.shape)} do not match [{rows}, {d.hidden}]")
         dropout = (float(dropout[0]), float(dropout[1]))
-        need_grad = flat.requires_grad and torch.is_grad_enabled()
+        need_grad = bool(ctx.needs_input_grad[1])  # False under torch.no_grad() and for detached weights
         with torch.cuda.device(feats.device):
             st = _state(feats.device)
             st.poll_errors()
@@ -307,8 +307,9 @@ def linear_rows(x, weight, bias):
     return LinearRows.apply(x, weight, bias)
 
 
-def gcn_conv(x, weight, bias, graph, relu=False, p_drop=0.0, site=0):
-    return GCNConvReLU.apply(x, weight, bias, graph, relu, p_drop, site)
+def gcn_conv(x, weight, bias, graph, relu=False, p_drop=0.0, site=0, w16=None):
+    """``w16``: cached ``split_weight16(weight)`` of the CURRENT weight values (optional)."""
+    return GCNConvReLU.apply(x, weight, bias, graph, relu, p_drop, site, w16)
 
 
 def lstm_head(feats, flat, dims, bw=1, dropout=(0.0, 0.0)):

@@ -44,6 +44,7 @@ class GCNConv(nn.Module):
         self.in_channels, self.out_channels = in_channels, out_channels
         self.bias = nn.Parameter(torch.zeros(out_channels))  # registered before ``lin`` like PyG
         self.lin = _Lin(in_channels, out_channels)
+        self._w16 = None  # ((data_ptr, version, device), (hi, lo)): fp16 operand halves of lin.weight
 
     def reset_parameters(self):
         self.lin.reset_parameters()
@@ -54,7 +55,27 @@ class GCNConv(nn.Module):
         """``_fuse_relu`` / ``_dropout`` / ``_site``: ReLU and nn.Dropout(p) (mask site = layer index) fused into the
         layer's epilogue -- what STGCN.forward and HybridSTGCN_LSTM.extract_base_features do right after the conv."""
         graph = graph_for(edge_index, x.shape[0], x.device)
-        return WF.gcn_conv(x, self.lin.weight, self.bias, graph, relu=_fuse_relu, p_drop=_dropout, site=_site)
+        w16 = None
+        w = self.lin.weight
+        if w.is_cuda and WF.precision() == "tf32x3" and self.out_channels % 128 == 0 and self.in_channels % 8 == 0:
+            # tensor-core operand halves of the weight, recomputed whenever it changes (optimiser steps and
+            # load_state_dict bump _version; .to() / .cuda() move the storage)
+            key = (w.data_ptr(), w._version, w.device)
+            if self._w16 is None or self._w16[0] != key:
+                self._w16 = (key, WF.split_weight16(w.detach()))
+            w16 = self._w16[1]
+        return WF.gcn_conv(x, w, self.bias, graph, relu=_fuse_relu, p_drop=_dropout, site=_site, w16=w16)
+
+    def __deepcopy__(self, memo):
+        # the operand cache belongs to THIS module's storage: a copy starts without one
+        import copy
+
+        cls = self.__class__
+        new = cls.__new__(cls)
+        memo[id(self)] = new
+        for k, v in self.__dict__.items():
+            new.__dict__[k] = None if k == "_w16" else copy.deepcopy(v, memo)
+        return new
 
 
 class STGCN(nn.Module):
