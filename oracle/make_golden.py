@@ -29,15 +29,10 @@ SAMPLE_IDX_SEED = 1234
 
 
 def _import_reference():
-    from oracle import pyg_shim
+    from oracle import build_ref
 
-    pyg_shim.install()
-    if REF not in sys.path:
-        sys.path.insert(0, REF)
-    with contextlib.redirect_stdout(io.StringIO()):
-        import graphBuilder, model, hybrid_model, dataset, embed_utils  # noqa: E401
-        import train_hybrid_maml_v5 as train
-    return graphBuilder, model, hybrid_model, dataset, embed_utils, train
+    m = build_ref.reference_modules()
+    return (m["graphBuilder"], m["model"], m["hybrid_model"], m["dataset"], m["embed_utils"], m["train_hybrid_maml_v5"])
 
 
 def sample_indices(numel, count=64):
@@ -300,10 +295,168 @@ def feature_cases():
     print("features_prepare.npz:", {k: v.shape for k, v in out.items() if k.endswith("_features")})
 
 
+def inner90_case(mods, name="hybrid_v5_k8_inner90", nlat=21, nlon=21, k=8, seed=43):
+    """The reference's REAL inner-loop shape (train_hybrid_maml_v5.py:124-127): INNER_EPOCHS_PER_TASK = 6 passes over the
+    first 15 support windows = 90 sequential SGD steps with the unmodified ``inner_loop_v4``, then the query backward
+    (:162-169).  Freezes the adapted weights and the first-order meta-gradient so that the drift of a reduced-precision
+    path over the full loop is pinned (about 6 minutes of CPU)."""
+    from torch.utils.data import Subset
+
+    from oracle import ref_port as P
+    from weatherforecast_stgcn_maml_b200 import synth
+
+    graphBuilder, model, hybrid_model, dataset, embed_utils, train = mods
+    cfg = dict(T=24, H=8, hidden=256, L=128, layers=4, out=12)
+    cfg["in"] = 24
+    T, H = cfg["T"], cfg["H"]
+    lats, lons = synth.region_grid(nlat, nlon)
+    with contextlib.redirect_stdout(io.StringIO()):
+        edge_index, n, pos = graphBuilder.build_spatial_graph(synth.GridCoords(lats, lons), k_neighbors=k)
+    sd = synth.init_v5_state_dict(seed, gcn_bias_scale=0.05, in_channels=24, hidden=256, lstm_hidden=128, lstm_layers=4,
+                                  out_channels=12, horizon=H)
+    nsup = train_per_epoch = 15
+    feats = synth.synth_features(T + H + nsup + 4, n, seed + 1, synth.koppen_table(seed)[3])
+    ds = dataset.WeatherGraphDataset(feats, edge_index, window_size=T, forecast_horizon=H)
+    hyb = build_ref_model(mods, sd, cfg)
+    kop = embed_utils.KoppenEmbedding(8)
+    train.INNER_EPOCHS_PER_TASK = 6  # the reference's own value (:24); set explicitly because run_case lowers it
+    support = Subset(ds, list(range(nsup + 2)))  # more than 15 windows: the loop's own `break` at 15 (:126) cuts it
+    query = Subset(ds, [nsup])
+    adapted, _ = train.inner_loop_v4(hyb, kop, support, "cpu")
+    adapted.train()
+    qb = next(iter(train.DataLoader(query, batch_size=1, shuffle=False)))
+    adapted.zero_grad()
+    qloss = torch.nn.MSELoss()(adapted(qb.x, qb.edge_index), qb.y) / train.GRAD_ACCUMULATION_STEPS
+    qloss.backward()
+    steps = P.reference_support_schedule_indices(nsup + 2, 6, train_per_epoch)
+    assert len(steps) == 90
+    p_q, p_qg, p_fast = P.fomaml_task(sd, feats, edge_index, steps, nsup, train.GRAD_ACCUMULATION_STEPS, window=T,
+                                      horizon=H, lr=train.INNER_LR, lstm_layers=4)
+    out = {"edge_index": edge_index.numpy().astype(np.int32), "k": k, "nlat": nlat, "nlon": nlon, "seed": seed,
+           "cfg": np.array([cfg[x] for x in ("in", "hidden", "L", "layers", "out", "T", "H")]),
+           "inner_steps": 90, "support_windows": nsup, "query_window": nsup, "accum": train.GRAD_ACCUMULATION_STEPS,
+           "inner_lr": train.INNER_LR, "query_loss_scaled": np.float64(qloss.item()), "feature_rows": feats.shape[0]}
+    ad_sd = adapted.state_dict()
+    for k_ in P.trainable(sd):
+        e = (p_fast[k_] - ad_sd[k_]).abs().max().item() / ad_sd[k_].abs().max().item()
+        assert e < 1e-4, f"port adapted (90 steps) {k_}: {e}"
+        g = dict(adapted.named_parameters())[k_].grad
+        e = (p_qg[k_] - g).abs().max().item() / (g.abs().max().item() + 1e-30)
+        assert e < 1e-3, f"port fomaml grad (90 steps) {k_}: {e}"
+        out[f"adapted_summary/{k_}"], out[f"adapted_samples/{k_}"] = summarize(ad_sd[k_])
+        out[f"fomaml_summary/{k_}"], out[f"fomaml_samples/{k_}"] = summarize(g)
+        out[f"delta_summary/{k_}"], out[f"delta_samples/{k_}"] = summarize(ad_sd[k_] - sd[k_])  # what 90 steps moved
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
+    print(f"[golden] {name}: 90 inner steps, qloss/accum={qloss.item():.6f}")
+
+
+def _replay_masks(shapes, p):
+    """The keep-masks ATen's CPU dropout draws, in call order: ``at::dropout`` = ``empty_like(x).bernoulli_(1 - p)
+    .div_(1 - p)`` on the default generator -- used both by nn.Dropout / F.dropout and between nn.LSTM layers."""
+    return [torch.empty(s).bernoulli_(1 - p).div_(1 - p) for s in shapes]
+
+
+def dropout_case(mods, name="hybrid_small_dropout", nlat=3, nlon=4, k=4, seed=7, p=0.2, rng_seed=2024):
+    """TRAIN-MODE reference (dropout_rate = lstm_dropout = p > 0, ``.train()``) with torch's generator seeded: the masks
+    the unmodified reference draws are replayed from the same seed in the same order -- three GCN sites
+    (hybrid_model.py:67-73), per node the nn.LSTM inter-layer sites (:47, one call per node, :98), the head site (:108)
+    -- and ``ref_port.hybrid_forward(masks=...)`` must reproduce the reference's predictions, loss and gradients.  This
+    pins the PLACEMENT and SCALING of every dropout site of the restatement (and so of the CUDA path, which is tested
+    against the restatement on masks read back from the kernels) against the reference itself."""
+    from oracle import ref_port as P
+    from weatherforecast_stgcn_maml_b200 import synth
+
+    graphBuilder, model, hybrid_model, dataset, embed_utils, train = mods
+    cfg = dict(T=6, H=2, hidden=32, L=32, layers=3, out=12)
+    cfg["in"] = 24
+    T, H, L, Ls = cfg["T"], cfg["H"], cfg["L"], cfg["layers"]
+    lats, lons = synth.region_grid(nlat, nlon)
+    with contextlib.redirect_stdout(io.StringIO()):
+        edge_index, n, pos = graphBuilder.build_spatial_graph(synth.GridCoords(lats, lons), k_neighbors=k)
+    sd = synth.init_v5_state_dict(seed, gcn_bias_scale=0.05, in_channels=24, hidden=cfg["hidden"], lstm_hidden=L,
+                                  lstm_layers=Ls, out_channels=12, horizon=H)
+    feats = synth.synth_features(T + H + 8, n, seed + 1, synth.koppen_table(seed)[3])
+    x, y = P.window_xy(feats, 0, T, H)
+    base = model.STGCN(24, cfg["hidden"], out_channels=12, window_size=T, forecast_horizon=H, dropout_rate=p)
+    hyb = hybrid_model.HybridSTGCN_LSTM(base, lstm_hidden_size=L, lstm_num_layers=Ls, lstm_dropout=p, out_channels=12,
+                                        forecast_horizon=H, freeze_base=False)
+    hyb.load_state_dict(sd)
+    hyb.train()
+    torch.set_num_threads(1)  # the replay must consume the generator exactly as the reference run does
+    torch.manual_seed(rng_seed)
+    pred = hyb(x, edge_index)
+    loss = torch.nn.MSELoss()(pred, y)
+    loss.backward()
+    torch.manual_seed(rng_seed)
+    R = T * n
+    gcn = _replay_masks([(R, cfg["hidden"])] * 3, p)
+    lstm = [torch.empty(n, T, L) for _ in range(Ls - 1)]
+    for node in range(n):
+        for l, m in enumerate(_replay_masks([(1, T, L)] * (Ls - 1), p)):  # batch_first input [1, T, L] of one node
+            lstm[l][node] = m[0]
+    head = _replay_masks([(n, L)], p)[0]
+    masks = {"gcn": gcn, "lstm": lstm, "head": head}
+    l_p, g_p, p_p = P.loss_and_grads(sd, x, y, edge_index, T, H, 1.0, Ls, masks=masks)
+    err = (p_p - pred).abs().max().item() / pred.abs().max().item()
+    assert err < 2e-6, f"masked port vs train-mode reference: forward {err} (mask replay out of step?)"
+    out = {"edge_index": edge_index.numpy().astype(np.int32), "k": k, "nlat": nlat, "nlon": nlon, "seed": seed, "p": p,
+           "cfg": np.array([cfg[x_] for x_ in ("in", "hidden", "L", "layers", "out", "T", "H")]),
+           "pred": pred.detach().numpy(), "loss": np.float64(loss.item()), "features": feats.numpy(),
+           "mask_head": head.numpy()}
+    for i, m in enumerate(gcn):
+        out[f"mask_gcn{i}"] = m.numpy()
+    for l, m in enumerate(lstm):
+        out[f"mask_lstm{l}"] = m.numpy()
+    for k_, v in sd.items():
+        out[f"sd/{k_}"] = v.numpy()
+    for k_, q in hyb.named_parameters():
+        if k_.startswith("base_stgcn."):
+            assert q.grad is None
+            continue
+        e = (g_p[k_] - q.grad).abs().max().item() / (q.grad.abs().max().item() + 1e-30)
+        assert e < 2e-5, f"masked port grad {k_}: {e}"
+        out[f"grad/{k_}"] = q.grad.numpy()
+    # STGCN.forward in train mode: dropout after all four convolutions (model.py:31-42), differentiable
+    base_sd = {k_[len("base_stgcn."):]: v for k_, v in sd.items() if k_.startswith("base_stgcn.")}
+    b2 = model.STGCN(24, cfg["hidden"], out_channels=12, window_size=T, forecast_horizon=H, dropout_rate=p)
+    b2.load_state_dict(base_sd)
+    b2.train()
+    torch.manual_seed(rng_seed + 1)
+    xs = x.clone().requires_grad_(True)
+    sp = b2(xs, edge_index)
+    sl = torch.nn.MSELoss()(sp, y)
+    sl.backward()
+    torch.manual_seed(rng_seed + 1)
+    m4 = _replay_masks([(R, cfg["hidden"])] * 4, p)
+    leaf = {k_: v.clone().requires_grad_(True) for k_, v in base_sd.items()}
+    xs2 = x.clone().requires_grad_(True)
+    pp = P.stgcn_forward(leaf, xs2, edge_index, T, H, 12, masks=m4)
+    pg = torch.autograd.grad(torch.nn.functional.mse_loss(pp, y), list(leaf.values()) + [xs2])
+    assert (pp - sp).abs().max().item() <= 2e-6 * sp.abs().max().item(), "masked STGCN port vs train-mode reference"
+    assert (pg[-1] - xs.grad).abs().max().item() <= 2e-5 * xs.grad.abs().max().item()
+    out["stgcn_pred"], out["stgcn_loss"], out["stgcn_dx"] = sp.detach().numpy(), np.float64(sl.item()), xs.grad.numpy()
+    for i, m in enumerate(m4):
+        out[f"stgcn_mask{i}"] = m.numpy()
+    for k_, q in b2.named_parameters():
+        out[f"stgcn_grad/{k_}"] = q.grad.numpy()
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
+    print(f"[golden] {name}: train-mode loss={loss.item():.6f} stgcn_loss={sl.item():.6f} (p={p})")
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     if len(sys.argv) > 1 and sys.argv[1] == "features":  # only this fixture (the model cases take minutes)
         feature_cases()
+        return
+    if len(sys.argv) > 1 and sys.argv[1] in ("inner90", "dropout"):
+        torch.manual_seed(42)
+        np.random.seed(42)
+        mods = _import_reference()
+        if sys.argv[1] == "inner90":
+            torch.set_num_threads(os.cpu_count() or 1)
+            inner90_case(mods)
+        else:
+            dropout_case(mods)
         return
     torch.manual_seed(42)
     np.random.seed(42)
@@ -318,6 +471,8 @@ def main():
     run_case(mods, "hybrid_v5_k4", full, nlat=21, nlon=21, k=4, seed=42, inner_steps=3, full_tensors=False)
     run_case(mods, "hybrid_v5_k8", full, nlat=21, nlon=21, k=8, seed=43, inner_steps=3, full_tensors=False)
     feature_cases()
+    dropout_case(mods)
+    inner90_case(mods)
 
 
 if __name__ == "__main__":

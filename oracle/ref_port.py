@@ -222,6 +222,12 @@ def inner_loop(sd, features, edge_index, steps, window=24, horizon=8, lr=0.01, l
     return fast, losses
 
 
+def reference_support_schedule_indices(num_support, epochs=6, per_epoch=15):
+    """Window order of inner_loop_v4 (train_hybrid_maml_v5.py:124-127): ``epochs`` passes over the first ``per_epoch``
+    support windows, in order (shuffle=False, ``break`` at batch 15)."""
+    return list(range(min(num_support, per_epoch))) * epochs
+
+
 def fomaml_task(sd, features, edge_index, support_steps, query_idx, accum, **kw):
     """One task of meta_update_v4 (train_hybrid_maml_v5.py:151-170): inner loop, then the
     first query window, loss / GRAD_ACCUMULATION_STEPS, backward INTO THE ADAPTED COPY.

@@ -159,3 +159,63 @@ def test_time_features_formula():
     assert tf.shape == (3, 4) and tf.dtype == np.float64
     assert np.allclose(tf[1], [np.sin(2 * np.pi * 100 / 365.25), np.cos(2 * np.pi * 100 / 365.25), 1.0, 0.0], atol=1e-15)
     assert np.array_equal(tf, P.time_features([1, 100, 366], [0.0, 6.0, 23.5]))
+
+
+def test_masked_port_reproduces_the_reference_in_train_mode():
+    """hybrid_small_dropout.npz: the UNMODIFIED reference in ``.train()`` mode with dropout_rate = lstm_dropout = 0.2, its
+    masks replayed from torch's generator (oracle/make_golden.py:dropout_case).  The restatement with those masks as
+    explicit inputs must give the reference's predictions, loss and gradients: this pins where each of the three dropout
+    sites sits (after GCN layers 1-3, between LSTM layers, on the head input) and its 1/(1-p) scaling."""
+    z = load_golden("hybrid_small_dropout")
+    cin, hidden, L, layers, out, T, H = (int(v) for v in z["cfg"])
+    sd = {k[3:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("sd/")}
+    feats, ei = torch.from_numpy(z["features"]), torch.from_numpy(z["edge_index"].astype(np.int64))
+    p = float(z["p"])
+    masks = {"gcn": [torch.from_numpy(z[f"mask_gcn{i}"]) for i in range(3)],
+             "lstm": [torch.from_numpy(z[f"mask_lstm{l}"]) for l in range(layers - 1)],
+             "head": torch.from_numpy(z["mask_head"])}
+    for m in masks["gcn"] + masks["lstm"] + [masks["head"]]:
+        vals = torch.unique(m)
+        assert vals.numel() == 2 and vals[0] == 0 and abs(vals[1].item() - 1 / (1 - p)) < 1e-6
+    x, y = P.window_xy(feats, 0, T, H)
+    loss, grads, pred = P.loss_and_grads(sd, x, y, ei, T, H, 1.0, layers, masks=masks)
+    assert rel_err(pred, torch.from_numpy(z["pred"])) <= 2e-6
+    assert abs(float(loss) - float(z["loss"])) <= 1e-6 * float(z["loss"])
+    for k, g in grads.items():
+        assert rel_err(g, torch.from_numpy(z[f"grad/{k}"])) <= 2e-5, k
+    # without the masks (eval mode) the result is a different one: the fixture really exercises dropout
+    assert rel_err(P.hybrid_forward(sd, x, ei, T, H, out, layers), torch.from_numpy(z["pred"])) > 1e-2
+    # STGCN.forward: dropout after all four convolutions, differentiable (model.py:31-42)
+    base_sd = {k[len("base_stgcn."):]: v for k, v in sd.items() if k.startswith("base_stgcn.")}
+    leaf = {k: v.clone().requires_grad_(True) for k, v in base_sd.items()}
+    xr = x.clone().requires_grad_(True)
+    m4 = [torch.from_numpy(z[f"stgcn_mask{i}"]) for i in range(4)]
+    pr = P.stgcn_forward(leaf, xr, ei, T, H, out, masks=m4)
+    gr = torch.autograd.grad(torch.nn.functional.mse_loss(pr, y), list(leaf.values()) + [xr])
+    assert rel_err(pr, torch.from_numpy(z["stgcn_pred"])) <= 2e-6
+    for (k, _), g in zip(leaf.items(), gr):
+        assert rel_err(g, torch.from_numpy(z[f"stgcn_grad/{k}"])) <= 2e-5, k
+    assert rel_err(gr[-1], torch.from_numpy(z["stgcn_dx"])) <= 2e-5
+
+
+def test_reference_archive_recipe_round_trips(tmp_path):
+    """oracle/build_ref.py: what travels to the GPU box as the reference arm is the reference's own files, unchanged."""
+    import os
+
+    from oracle import build_ref
+
+    src = tmp_path / "src"
+    src.mkdir()
+    (src / "a.py").write_text("x = 1\n")
+    (src / "b.py").write_text("import a\ny = a.x + 1\n")
+    arc = tmp_path / "out" / "ref.tar.gz"
+    assert build_ref.build(str(src), str(arc)) == ["a.py", "b.py"]
+    first = arc.read_bytes()
+    assert build_ref.build(str(src), str(arc)) == ["a.py", "b.py"] and arc.read_bytes() == first  # idempotent
+    assert build_ref.build(str(tmp_path / "missing"), str(arc)) == []
+    if os.path.isdir(build_ref.REF_SRC) and os.path.exists(build_ref.ARCHIVE):
+        import tarfile
+
+        with tarfile.open(build_ref.ARCHIVE) as tar:
+            for m in tar.getmembers():
+                assert tar.extractfile(m).read() == open(os.path.join(build_ref.REF_SRC, m.name), "rb").read(), m.name

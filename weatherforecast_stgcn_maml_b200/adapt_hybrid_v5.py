@@ -193,3 +193,56 @@ def adapt_region(checkpoint, features, edge_index, region_coords, region_name, s
         "base_model_loss": checkpoint.get("meta_loss", "N/A"),
         "total_params": sum(v.numel() for v in sd.values()),
     }
+
+
+MODEL_PATH = "./Out_Data/SavedModels/hybrid_maml_model_v5_best.pt"   # adapt_hybrid_v5.py:17
+SAVE_DIR = "./Out_Data/AdaptedModels"                                # adapt_hybrid_v5.py:236
+
+
+def adaptModel(region_coords, region_name, loader=None, model_path=None, save_dir=None, device="cuda", epochs=EPOCHS,
+               orders=None, verbose=True, dropout=None):
+    """Adapt Model V5 to a specific region -- the reference's entry point (adapt_hybrid_v5.py:65-271), same positional
+    signature and return value (the path of the saved adapted checkpoint).
+
+    What the reference does around the compute is disk I/O against hard-coded paths (``load_adaptation_data``: NetCDF
+    files under ``E:/Study/...``, :22-62), which is out of scope; ``loader(region_coords)`` supplies the region's data
+    instead and must return what that function returns: a dataset-like object exposing ``.latitude.values``,
+    ``.longitude.values`` and, by name, the 12 ERA5 variables plus the four time features (``ds[name].values``; see
+    featurePreprocessor.WEATHER_VARS / TIME_VARS) -- or, for data that is already assembled, a tuple
+    ``(features [time, N, 24], edge_index [2, E], stats)``.  Everything else follows the reference line by line:
+    checkpoint from ``MODEL_PATH`` (:84), kNN graph with k = 4 (:139), ``prepare_model_input(ds, 0, koppen_embed,
+    normalize=True)`` (:140), 80/20 split of the first 1,200 windows, 15 epochs of batch-1 Adam fine-tuning in train mode,
+    eval-mode validation (:152-231), checkpoint dict and file name of :236-257."""
+    import os
+
+    from .embed_utils import KoppenEmbedding
+    from .featurePreprocessor import prepare_model_input
+    from .graphBuilder import build_spatial_graph
+
+    if loader is None:
+        raise ValueError("adaptModel needs loader(region_coords): the reference's NetCDF reader (adapt_hybrid_v5.py:30-62, "
+                         "hard-coded E:/ paths) is not part of this package")
+    model_path = MODEL_PATH if model_path is None else model_path
+    save_dir = SAVE_DIR if save_dir is None else save_dir
+    if verbose:
+        print("=" * 80)
+        print(f"MODEL 5.0 REGIONAL ADAPTATION: {region_name}")
+        print(f"Device: {device}  Region: {region_coords}  Base Model: {model_path}")
+        print("=" * 80)
+    checkpoint = torch.load(model_path, map_location="cpu", weights_only=False)
+    data = loader(region_coords)
+    if isinstance(data, tuple):
+        features, edge_index, stats = data
+    else:
+        koppen_embed = KoppenEmbedding(embedding_dim=8)
+        koppen_embed.load_state_dict(checkpoint["koppen_embed_state_dict"])
+        edge_index, _, _ = build_spatial_graph(data, k_neighbors=4, device=device)
+        features, stats = prepare_model_input(data, 0, koppen_embed.to(device), normalize=True, device=device)
+    out = adapt_region(checkpoint, features, edge_index, region_coords, region_name, stats=stats, device=device,
+                       epochs=epochs, orders=orders, verbose=verbose, dropout=dropout)
+    os.makedirs(save_dir, exist_ok=True)
+    save_path = os.path.join(save_dir, f"hybrid_v5_adapted_{region_name}_{region_coords}.pt")
+    torch.save(out, save_path)
+    if verbose:
+        print(f"Final validation loss: {out['val_loss']:.6f}\nModel saved: {save_path}")
+    return save_path
