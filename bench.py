@@ -38,6 +38,9 @@ WINDOWS = 600
 SUPPORT_ROWS = (0, 1, 2)
 METRIC = "maml_meta_steps_per_sec"
 UNIT = "meta-steps/s"
+# what the path computes in: f32 storage and accumulation; every tensor-core product is a 3-term split of its operands into
+# 16-bit hi/lo pairs (fp16 forward, bf16 where an operand is a gradient) -- FP32-class accuracy, not an FP32 FMA pipeline
+DTYPE = "f32 (storage + accumulate; products = 3x 16-bit hi/lo operand splits: fp16 forward, bf16 backward)"
 
 
 _REAL_STDOUT = None
@@ -77,6 +80,15 @@ def peaks():
         d = json.load(open(p))
         return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def tensor_peak():
+    """Sustained dense bf16 TFLOP/s (the step runs for many milliseconds): measured, else the recipe's fallback."""
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d.get("bf16_tflops_sustained", d.get("bf16_tflops", 0.0))) or None
+    return 1500.0
 
 
 # ----------------------------------------------------------------------------- CPU reference arm
@@ -327,9 +339,24 @@ def stage_breakdown(trainer, reps=3):
     return out
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernels from `ncu --set full`
-# (profiles/r1b_ncu_summary.md); None until a capture of the current kernels is committed
-NCU_TRAFFIC = {"wf_lstm_seq_fwd16_kernel": 851.1e6, "wf_lstm_seq_bwd_kernel": 1109.3e6}
+def load_ncu_traffic():
+    """{kernel name: dram__bytes_read.sum + dram__bytes_write.sum per launch} parsed from the newest committed
+    `profiles/*_ncu_traffic.csv` (written by tools/ncu_traffic.py from an `ncu --set full` capture of this command);
+    empty if no capture of the current kernels is committed -- `traffic` is then null, never a stale constant."""
+    import csv
+    import glob
+
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "*_ncu_traffic.csv")))
+    if not files:
+        return {}, None
+    out = {}
+    with open(files[-1]) as fh:
+        for row in csv.DictReader(fh):
+            try:
+                out[row["kernel"]] = (float(row["dram_read_bytes"]) + float(row["dram_write_bytes"])) / max(1.0, float(row["launches"]))
+            except (KeyError, ValueError):
+                continue
+    return out, os.path.relpath(files[-1], ROOT)
 
 
 def time_recurrence_kernels(trainer, reps=10):
@@ -368,38 +395,192 @@ def time_recurrence_kernels(trainer, reps=10):
     return out
 
 
-def roofline_report(stages, kernel_ms, G, peak, peak_src):
-    """Roofline of the dominant kernels.  Algorithmic bytes = the saved-activation traffic a
-    (row, step) needs (SURVEY.md 8d figures for gates / c / h, plus this design's transposed bf16 copies), times the
-    G*N*T valid (row, step) pairs of one launch; TB4 tile padding is NOT counted."""
-    N, T, F, L, C = NLAT * NLON, 24, 256, 128, 24
+# Bytes per (row, step) of the two persistent LSTM kernels, L = 128 hidden units, f32 unless noted.
+#   minimum = what ANY implementation of the step must move: forward writes the gates (4L), c (L) and h (L)
+#             BPTT needs and reads its input x_t (L, for 3 of 4 layers); backward reads gates (4L), c[t] (L; c[t-1] is the
+#             previous step's line), dh from above (L) and writes dG (4L).
+#   design  = what THIS design moves: the input projection is a separate GEMM, so the forward reads 4L of pre-activations
+#             instead of L of x_t and also writes h^T as bf16 hi/lo (2 x L x 2 B) for the weight gradients; the backward
+#             reads c[t-1] again and writes dG twice (in place + a transposed f32 copy for the weight-gradient GEMM).
+KERNEL_BYTES = {
+    "wf_lstm_seq_fwd16_kernel": {"minimum": (4 * 128 + 128 + 128) * 4 + 128 * 4,
+                                 "design": 4 * 128 * 4 + (4 * 128 + 128 + 128) * 4 + 2 * 128 * 2},
+    "wf_lstm_seq_bwd_kernel": {"minimum": (4 * 128 + 128 + 128) * 4 + 4 * 128 * 4,
+                               "design": (4 * 128 + 2 * 128 + 128) * 4 + (4 * 128 + 4 * 128) * 4},
+}
+
+
+def roofline_report(stages, kernel_ms, G, peak, peak_src, ms_per_step, tf_peak):
+    """Roofline of the dominant kernel (the slower of the two persistent LSTM kernels; both are reported).
+    achieved = ALGORITHMIC bytes per launch (the minimum any implementation must move) / the kernel's
+    CUDA-event time; the bytes this design actually asks for are reported beside it as design_bytes."""
+    N, T, F, L = NLAT * NLON, 24, 256, 128
     R = T * N
     E = N * KNN + R
     csr = E * 8 + (R + 1) * 4
-    per_row_step = {
-        # read the input projection (4L f32); write gates (4L), c (L), h (L) f32 and h^T as bf16 hi + lo (2 x L x 2 B)
-        "wf_lstm_seq_fwd16_kernel": 4 * L * 4 + (4 * L + L + L) * 4 + 2 * L * 2,
-        # read gates (4L), c[t], c[t-1] (2L), dh from above (L); write dG (4L) and dG^T (4L) f32
-        "wf_lstm_seq_bwd_kernel": (4 * L + 2 * L + L) * 4 + (4 * L + 4 * L) * 4,
-    }
+    traffic, traffic_src = load_ncu_traffic()
     calls_per_step = 16  # 4 layers x 4 window passes of a meta-step, each kernel
     kern = {}
     for name, ms in kernel_ms.items():
-        b = per_row_step[name] * G * R
-        kern[name] = {"ms_per_launch": ms, "algorithmic_bytes": b, "GBps": b / (ms * 1e-3) / 1e9,
-                      "frac": b / (ms * 1e-3) / 1e9 / peak, "share_of_step_ms": ms * calls_per_step,
-                      "traffic": NCU_TRAFFIC.get(name)}
+        b = KERNEL_BYTES[name]["minimum"] * G * R
+        bd = KERNEL_BYTES[name]["design"] * G * R
+        kern[name] = {"ms_per_launch": ms, "algorithmic_bytes": b, "design_bytes": bd, "GBps": b / (ms * 1e-3) / 1e9,
+                      "frac": b / (ms * 1e-3) / 1e9 / peak, "design_frac": bd / (ms * 1e-3) / 1e9 / peak,
+                      "share_of_step_ms": ms * calls_per_step, "traffic": traffic.get(name)}
     best = max(kern, key=lambda k: kern[k]["ms_per_launch"])
     # graph conv (BASELINE.json asks for it): one 256 -> 256 GCN layer call = read X, write Y, CSR, W
     gcn_bytes = G * (R * (F + F) * 4 + csr) + F * F * 4
     gname = "wf_gcn_layer_fwd_g16" if "wf_gcn_layer_fwd_g16" in stages else "wf_gcn_layer_fwd_tc"
     g = stages.get(gname)
     gcn_gbps = gcn_bytes / (g["ms_per_meta_step"] / g["calls"] * 1e-3) / 1e9 if g else None
+    # whole meta-step against both roofs (SURVEY.md 8d: ~262 MB and 41.81 GFLOP algorithmic per window pass)
+    passes = 4 * G
+    step_bytes, step_flop = passes * 262e6, passes * 41.81e9
+    step = {"algorithmic_bytes": step_bytes, "algorithmic_flop": step_flop,
+            "GBps": step_bytes / (ms_per_step * 1e-3) / 1e9, "hbm_frac": step_bytes / (ms_per_step * 1e-3) / 1e9 / peak,
+            "TFLOPs": step_flop / (ms_per_step * 1e-3) / 1e12,
+            "tensor_frac": (step_flop / (ms_per_step * 1e-3) / 1e12 / tf_peak) if tf_peak else None,
+            "tensor_peak_TFLOPs": tf_peak,
+            "note": "the step is bound by neither roof: 24 sequential recurrence steps x 32 layer launches of per-step "
+                    "latency; every tensor-core product is issued three times (hi/lo operand splits)"}
     return {"bound": "hbm", "kernel": best, "achieved": kern[best]["GBps"], "peak": peak, "unit": "GB/s",
-            "frac": kern[best]["frac"], "traffic": kern[best]["traffic"], "peak_source": peak_src,
-            "ms_per_launch": kern[best]["ms_per_launch"], "algorithmic_bytes_per_launch": kern[best]["algorithmic_bytes"],
+            "frac": kern[best]["frac"], "traffic": kern[best]["traffic"], "traffic_source": traffic_src,
+            "peak_source": peak_src, "ms_per_launch": kern[best]["ms_per_launch"],
+            "algorithmic_bytes_per_launch": kern[best]["algorithmic_bytes"],
+            "design_bytes_per_launch": kern[best]["design_bytes"], "design_frac": kern[best]["design_frac"],
             "kernels": kern, "graph_conv_GBps": gcn_gbps, "graph_conv_frac": gcn_gbps / peak if gcn_gbps else None,
-            "graph_conv_note": "256->256 GCN layer incl. the pre-aggregation pass; the last layer also writes transposed copies"}
+            "graph_conv_note": "256->256 GCN layer incl. the pre-aggregation pass; the last layer also writes transposed copies",
+            "step_roofline": step}
+
+
+def config1_windows_per_sec(sd, dims, batch=16, reps=5):
+    """configs[0] shape on the GPU: forward + MSE + backward of a batch of 16 independent windows (batch-1 semantics,
+    SURVEY.md D8) of one 441-node region, k = 8; device-timed."""
+    import torch
+
+    from weatherforecast_stgcn_maml_b200 import synth
+    from weatherforecast_stgcn_maml_b200.engine import HybridEngine, flatten_trainable, gcn_weights_from_state_dict
+    from weatherforecast_stgcn_maml_b200.graph import RegionGraph
+    from weatherforecast_stgcn_maml_b200.graphBuilder import knn_edge_index_device
+
+    lats, lons, feats, _ = synth.synth_task(3, num_windows=batch + 8, nlat=NLAT, nlon=NLON)
+    ei = knn_edge_index_device(lats, lons, KNN, "cuda")
+    eng = HybridEngine(dims, 1, batch, "cuda")
+    graph = RegionGraph(ei, dims.R, "cuda")
+    fd = feats.cuda()
+    per = dims.num_nodes * dims.in_channels
+    xo = (torch.arange(batch, dtype=torch.long) * per).cuda()
+    to = xo + (dims.window + 1) * per
+    theta = flatten_trainable(sd, dims, "cuda")
+    gw = gcn_weights_from_state_dict(sd, "cuda")
+    run = lambda: eng.forward_backward(fd, dims.in_channels, 0, xo, gw, graph, theta, 0, feat=fd, tgt_off=to,
+                                       feat_ld=dims.in_channels)
+    for _ in range(3):
+        run()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        run()
+    e1.record()
+    torch.cuda.synchronize()
+    eng.check()
+    ms = e0.elapsed_time(e1) / reps
+    return {"windows_per_sec": batch / (ms * 1e-3), "ms_per_batch": ms, "batch": batch,
+            "workload": "configs[0] on the GPU: v5 hybrid forward + MSE + backward, batch of 16 independent windows of one "
+                        "441-node region (k=8), features resident, tensor-core path"}
+
+
+def config4_record(peak, tf_peak, batch=32, chunk=8, reps=2):
+    """configs[3]: 121 x 121 = 14,641 nodes, k = 8, the graph-conv stack forward AND backward (STGCN.forward through the
+    drop-in module API, model.py:30-52 -- the only differentiable use of the convolution), batch 32 as 4 chunks of 8
+    windows (gradients accumulate in .grad).  GB/s and TFLOP/s on algorithmic bytes / FLOPs."""
+    import torch
+
+    from weatherforecast_stgcn_maml_b200 import functional as WF
+    from weatherforecast_stgcn_maml_b200 import synth
+    from weatherforecast_stgcn_maml_b200.graphBuilder import knn_edge_index_device
+    from weatherforecast_stgcn_maml_b200.model import STGCN
+
+    nlat = nlon = 121
+    n, T, H, F = nlat * nlon, 24, 8, 256
+    lats, lons = synth.region_grid(nlat, nlon)
+    ei = knn_edge_index_device(lats, lons, KNN, "cuda")
+    sd = synth.init_v5_state_dict(3, gcn_bias_scale=0.05)
+    base = STGCN(24, F, out_channels=12, window_size=T, forecast_horizon=H, dropout_rate=0.0)
+    base.load_state_dict({k[len("base_stgcn."):]: v for k, v in sd.items() if k.startswith("base_stgcn.")})
+    base = base.cuda().train()
+    g = torch.Generator(device="cuda").manual_seed(1)
+    x = torch.randn(chunk * T * n, 24, device="cuda", generator=g)
+
+    def run():
+        for _ in range(batch // chunk):
+            out = base(x, ei)
+            out.backward(torch.ones_like(out) / out.numel())
+
+    run()
+    torch.cuda.synchronize()
+    base.zero_grad(set_to_none=True)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        run()
+    e1.record()
+    torch.cuda.synchronize()
+    WF.check()
+    ms = e0.elapsed_time(e1) / reps
+    rows = batch * T * n
+    # per layer: forward read X + write Y; backward read dY, Y (ReLU mask), X (dW) and write dX -- f32
+    byts = rows * 4 * ((24 + F) + 3 * (F + F) + (F + F + 24) + 3 * (F + F + F + F))
+    flop = 3 * 2 * rows * (24 * F + 3 * F * F)  # forward + dX + dW
+    del x, base
+    torch.cuda.empty_cache()
+    return {"ms_per_batch32": ms, "windows_per_sec": batch / (ms * 1e-3), "algorithmic_bytes": byts, "algorithmic_flop": flop,
+            "GBps": byts / (ms * 1e-3) / 1e9, "hbm_frac": byts / (ms * 1e-3) / 1e9 / peak,
+            "TFLOPs": flop / (ms * 1e-3) / 1e12, "tensor_frac": flop / (ms * 1e-3) / 1e12 / tf_peak if tf_peak else None,
+            "workload": "configs[3]: 121x121 = 14,641 nodes, k=8, 4 x GCNConv(256)+ReLU forward+backward (STGCN.forward via "
+                        "the drop-in modules), batch 32 = 4 chunks of 8 windows, 351,384 rows per window"}
+
+
+def module_api_ms(sd, dims, reps=10):
+    """The drop-in nn.Module route (``out = model(x, edge_index); loss.backward()``, hybrid_model.py:80-117) on one
+    window: milliseconds per forward + MSE + backward, to set beside the task-batched engine's per-window time."""
+    import torch
+
+    from weatherforecast_stgcn_maml_b200 import functional as WF
+    from weatherforecast_stgcn_maml_b200 import synth
+    from weatherforecast_stgcn_maml_b200.graphBuilder import knn_edge_index_device
+    from weatherforecast_stgcn_maml_b200.hybrid_model import HybridSTGCN_LSTM
+    from weatherforecast_stgcn_maml_b200.model import STGCN
+
+    T, H, N = dims.window, dims.horizon, dims.num_nodes
+    lats, lons, feats, _ = synth.synth_task(5, num_windows=8, nlat=NLAT, nlon=NLON)
+    ei = knn_edge_index_device(lats, lons, KNN, "cuda")
+    base = STGCN(24, 256, out_channels=12, window_size=T, forecast_horizon=H, dropout_rate=0.0)
+    hyb = HybridSTGCN_LSTM(base, lstm_hidden_size=128, lstm_num_layers=4, lstm_dropout=0.0, out_channels=12,
+                           forecast_horizon=H, freeze_base=False)
+    hyb.load_state_dict(sd)
+    hyb = hyb.cuda().train()
+    fd = feats.cuda()
+    x = fd[0:T].reshape(T * N, -1).contiguous()                                   # dataset.py:36-37
+    y = torch.stack([fd[T + h, :, :12] for h in range(1, H + 1)]).reshape(H * N, 12)  # dataset.py:40-48
+    crit = torch.nn.MSELoss()
+
+    def run():
+        hyb.zero_grad(set_to_none=True)
+        crit(hyb(x, ei), y).backward()
+
+    for _ in range(3):
+        run()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        run()
+    e1.record()
+    torch.cuda.synchronize()
+    WF.check()
+    return e0.elapsed_time(e1) / reps
 
 
 def finetune_windows_per_sec(sd, dims, steps=96, warmup=16, dropout=(0.0, 0.0, 0.0)):
@@ -469,24 +650,66 @@ def run_gpu(args, rank, local, world):
     del tr
     torch.cuda.empty_cache()
 
+    # ---- the reference's TRAINING configuration: dropout 0.2 at its three sites (train_hybrid_maml_v5.py:197,205)
+    from weatherforecast_stgcn_maml_b200.engine import REFERENCE_DROPOUT
+
+    kw_on = dict(kw, dropout=REFERENCE_DROPOUT)
+    tr_on = MetaTrainer(sd, tasks, dims, "cuda", use_cuda_graph=True, **kw_on)
+    tr_on.meta_step()
+    ms_on, loss_on = timed_steps(tr_on, max(3, args.steps // 2), 3, world, sync_loss=False)
+    steps_on = max(3, args.steps // 2)
+    tr_on.check()
+    del tr_on
+    torch.cuda.empty_cache()
+
     # ---- e2e: features in pinned host memory, upload per step, loss read back per step
     tr2 = MetaTrainer(sd, tasks, dims, "cuda", use_cuda_graph=True, host_staging=True, **kw)
     tr2.meta_step()
     ms2, loss2 = timed_steps(tr2, args.steps, args.warmup, world, sync_loss=True)
     h2d = tr2.stager.h2d_bytes + 32  # + the AdamW hyper-parameter block
+    tr2.check()
     del tr2
+    torch.cuda.empty_cache()
+
+    # ---- configs[4] as BASELINE.json words it: 120 tasks in total over the N GPUs (strong scaling; N >= 2 only)
+    config5 = None
+    if world > 1 and 120 % world == 0:
+        from weatherforecast_stgcn_maml_b200.dist import shard_tasks
+        from weatherforecast_stgcn_maml_b200.graphBuilder import knn_edge_index_device
+
+        tasks5 = []
+        for t in shard_tasks(120, rank, world):
+            lats, lons, feats, _ = synth.synth_task(t, num_windows=64, nlat=NLAT, nlon=NLON)
+            tasks5.append((feats, knn_edge_index_device(lats, lons, KNN, "cuda")))
+        tr5 = MetaTrainer(sd, tasks5, dims, "cuda", use_cuda_graph=True, support_rows=SUPPORT_ROWS, accum=120,
+                          dropout=(0.0, 0.0, 0.0), query_row=40)
+        tr5.meta_step()
+        ms5, _ = timed_steps(tr5, 5, 3, world, sync_loss=False)
+        tr5.check()
+        config5 = {"global_tasks": 120, "tasks_per_gpu": 120 // world, "ms_per_step": ms5 / 5,
+                   "meta_steps_per_sec": 1.0 / (ms5 * 1e-3 / 5), "task_passes_per_sec": 120 / (ms5 * 1e-3 / 5),
+                   "scaling": "strong", "workload": "configs[4]: 120 synthetic region tasks across the N GPUs, NCCL "
+                                                    "all-reduce of the meta-gradient, one 120-task meta-step"}
+        del tr5, tasks5
+        torch.cuda.empty_cache()
 
     if rank != 0:
         return
     sec_step = ms * 1e-3 / args.steps
     value = world / sec_step
     peak, peak_src = peaks()
-    roof = roofline_report(stages, kernel_ms, TASKS_PER_GPU, peak, peak_src)
+    tf_peak = tensor_peak()
+    roof = roofline_report(stages, kernel_ms, TASKS_PER_GPU, peak, peak_src, sec_step * 1e3, tf_peak)
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": sec_step * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic", "config": workload_config(world),
+        "dtype": DTYPE, "data": "synthetic", "config": workload_config(world),
         "windows_per_sec": 60 * world / sec_step, "meta_loss": loss, "clocks": clocks,
+        "dropout_on": {"value": world / (ms_on * 1e-3 / steps_on), "unit": UNIT, "ms_per_step": ms_on / steps_on,
+                       "meta_loss": loss_on, "p": list(REFERENCE_DROPOUT),
+                       "note": "same workload with the reference's training configuration: dropout 0.2 after GCN layers "
+                               "1-3, between the LSTM layers and on the head input (fused counter-based masks, "
+                               "regenerated in backward); the headline value keeps dropout off (parity configuration)"},
         "e2e": {"value": world / (ms2 * 1e-3 / args.steps), "unit": UNIT, "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": 4, "ms_per_step": ms2 / args.steps, "meta_loss": loss2,
                 "note": "features in pinned host memory; every step uploads the rows its windows read (double buffered: the "
@@ -497,8 +720,19 @@ def run_gpu(args, rank, local, world):
         "stages_ms_per_meta_step": {k: round(v["ms_per_meta_step"], 4) for k, v in stages.items()},
     }
     line["finetune"] = {"windows_per_sec": finetune_windows_per_sec(sd, dims), "unit": "windows/s",
+                        "windows_per_sec_dropout_on": finetune_windows_per_sec(sd, dims, dropout=REFERENCE_DROPOUT),
                         "workload": "configs[2]: batch-1 Adam fine-tuning steps on one 441-node region (k=8), "
                                     "forward + MSE + backward + clip + Adam per window, 1 GPU"}
+    if config5 is not None:
+        line["config5"] = config5
+    if world == 1:
+        line["config1"] = config1_windows_per_sec(sd, dims)
+        ms_mod = module_api_ms(sd, dims)
+        line["module_api"] = {"ms_per_window_fwd_bwd": ms_mod, "engine_ms_per_window_fwd_bwd": sec_step * 1e3 / 60,
+                              "note": "drop-in nn.Module route (HybridSTGCN_LSTM.forward + loss.backward(), one window, "
+                                      "autograd, same tcgen05 kernels through a leased engine) vs the task-batched engine "
+                                      "(meta-step time / 60 window passes)"}
+        line["config4"] = config4_record(peak, tf_peak)
     if world == 1 and not args.no_cpu_baseline:
         sec, cores, kind = cpu_window_pass(3, 1)
         sec_p, _ = port_window_pass_seconds(2, 1, literal=True)
