@@ -318,6 +318,8 @@ def stage_breakdown(trainer, reps=3):
         e0.record()
         orig(name, *a)
         e1.record()
+        if name == "wf_gcn_layer_fwd_ss":  # the 24-channel first layer and the three 256 -> 256 layers separately
+            name += "_wide" if a[15] >= 128 else "_first"
         acc.setdefault(name, []).append((e0, e1))
 
     was, was_dist = trainer.use_graph, trainer.dist
@@ -371,12 +373,11 @@ def time_recurrence_kernels(trainer, reps=10):
     out = {}
 
     def fwd():
-        _lib.call("wf_lstm_seq_recur_fwd", _lib.ptr(e.gates[1]), _lib.ptr(e.c[1]), _lib.ptr(e.h[1]), _lib.ptr(e.hT[1]),
-                  _lib.ptr(e.hT_lo[1]), _lib.ptr(e.w16[0]), _lib.ptr(e.w16[1]), 1, Ls, L, d.window, d.num_nodes, e.G, e.Bw,
-                  _lib.ptr(e.err), st)
+        _lib.call("wf_lstm_seq_recur_fwd", _lib.ptr(e.gates[1]), _lib.ptr(e.c[1]), _lib.ptr(e.h16[1]), _lib.ptr(e.hb16[1]), None,
+                  _lib.ptr(e.w16[0]), _lib.ptr(e.w16[1]), 1, Ls, L, d.window, d.num_nodes, e.G, e.Bw, _lib.ptr(e.err), st)
 
     def bwd():
-        _lib.call("wf_lstm_seq_recur_bwd", _lib.ptr(e.gates[1]), _lib.ptr(e.c[1]), _lib.ptr(e.dgT), _lib.ptr(e.ws), 0,
+        _lib.call("wf_lstm_seq_recur_bwd", _lib.ptr(e.gates[1]), _lib.ptr(e.c[1]), _lib.ptr(e.dg16), _lib.ptr(e.ws), 0,
                   _lib.ptr(e.w16[2]), _lib.ptr(e.w16[3]), 1, Ls, L, d.window, d.num_nodes, e.G, e.Bw, _lib.ptr(e.err), st)
 
     e.ws.zero_()  # dh from the layer above: zeros (timing does not depend on values)
@@ -400,13 +401,14 @@ def time_recurrence_kernels(trainer, reps=10):
 #             BPTT needs and reads its input x_t (L, for 3 of 4 layers); backward reads gates (4L), c[t] (L; c[t-1] is the
 #             previous step's line), dh from above (L) and writes dG (4L).
 #   design  = what THIS design moves: the input projection is a separate GEMM, so the forward reads 4L of pre-activations
-#             instead of L of x_t and also writes h^T as bf16 hi/lo (2 x L x 2 B) for the weight gradients; the backward
-#             reads c[t-1] again and writes dG twice (in place + a transposed f32 copy for the weight-gradient GEMM).
+#             instead of L of x_t, and h leaves twice as 16-bit hi/lo planes (fp16 for the next layer's projection, bf16 for
+#             the weight gradients: 2 x L x 4 bytes); the backward reads c[t-1] again (dG leaves as bf16 hi/lo planes: the
+#             same 4L x 4 bytes; no transposed copies since round 2).
 KERNEL_BYTES = {
     "wf_lstm_seq_fwd16_kernel": {"minimum": (4 * 128 + 128 + 128) * 4 + 128 * 4,
-                                 "design": 4 * 128 * 4 + (4 * 128 + 128 + 128) * 4 + 2 * 128 * 2},
+                                 "design": 4 * 128 * 4 + (4 * 128 + 128 + 2 * 128) * 4},
     "wf_lstm_seq_bwd_kernel": {"minimum": (4 * 128 + 128 + 128) * 4 + 4 * 128 * 4,
-                               "design": (4 * 128 + 2 * 128 + 128) * 4 + (4 * 128 + 4 * 128) * 4},
+                               "design": (4 * 128 + 2 * 128 + 128) * 4 + 4 * 128 * 4},
 }
 
 
@@ -430,8 +432,7 @@ def roofline_report(stages, kernel_ms, G, peak, peak_src, ms_per_step, tf_peak):
     best = max(kern, key=lambda k: kern[k]["ms_per_launch"])
     # graph conv (BASELINE.json asks for it): one 256 -> 256 GCN layer call = read X, write Y, CSR, W
     gcn_bytes = G * (R * (F + F) * 4 + csr) + F * F * 4
-    gname = "wf_gcn_layer_fwd_g16" if "wf_gcn_layer_fwd_g16" in stages else "wf_gcn_layer_fwd_tc"
-    g = stages.get(gname)
+    g = stages.get("wf_gcn_layer_fwd_ss_wide")
     gcn_gbps = gcn_bytes / (g["ms_per_meta_step"] / g["calls"] * 1e-3) / 1e9 if g else None
     # whole meta-step against both roofs (~262 MB and 41.81 GFLOP algorithmic per window pass)
     passes = 4 * G
@@ -449,7 +450,8 @@ def roofline_report(stages, kernel_ms, G, peak, peak_src, ms_per_step, tf_peak):
             "algorithmic_bytes_per_launch": kern[best]["algorithmic_bytes"],
             "design_bytes_per_launch": kern[best]["design_bytes"], "design_frac": kern[best]["design_frac"],
             "kernels": kern, "graph_conv_GBps": gcn_gbps, "graph_conv_frac": gcn_gbps / peak if gcn_gbps else None,
-            "graph_conv_note": "256->256 GCN layer incl. the pre-aggregation pass; the last layer also writes transposed copies",
+            "graph_conv_note": "one 256->256 GCN layer call (aggregation of the rows with neighbours + the resident-weight SS GEMM "
+                               "with TMA-store epilogue), algorithmic bytes = read X + write Y as fp16 hi/lo planes (4 B/value)",
             "step_roofline": step}
 
 

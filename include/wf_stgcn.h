@@ -198,12 +198,6 @@ long long wf_seq_weight_elems(int layers, int L, int G);
 /* fp32 -> 16-bit hi / lo operand halves (fmt 0: fp16, 1: bf16): hi = rn(x), lo = rn(x - hi); n % 4 == 0. */
 int wf_split16(const float* src, void* hi, void* lo, long long n, int fmt, void* stream);
 
-/* X [windows*T*N, C] row-major f32 -> bf16 hi / lo transposed copies [windows][C][RT16] (column (t, node) = t*Np + node):
- * the layer-0 input operand xT of wf_lstm_bwd_seq for features that did not come out of wf_gcn_layer_fwd_g16 (the drop-in
- * nn.Module path, hybrid_model.py:80-117, hands the LSTM any features tensor).  Padding columns are not written. */
-int wf_transpose_split16_rows(const float* X, int T, int N, int C, int windows, void* out_hi, void* out_lo,
-                              void* stream);
-
 /* Row pitch RT16 of the 16-bit transposed activation copies [(G*Bw)][channels][RT16] and of the fp32 dG^T
  * scratch that pairs with them: column (t, node) = t*Np + node, Np = N rounded up to 8.  Padding columns zero. */
 long long wf_transposed_pitch16(int T, int N);
@@ -243,36 +237,86 @@ int wf_prep_weights_seq(const float* params, long long params_group_stride, int 
                         int O, int G, void* p16_hi, void* p16_lo, void* pT16_hi, void* pT16_lo, void* f16_hi,
                         void* f16_lo, void* b16_hi, void* b16_lo, void* stream);
 
-/* nn.LSTM forward (hybrid_model.py:42-49, 93-105).  x [G*Bw*T*N, F] row-major; gates (4L channels) and c
- * (L channels) are TB4, [layers] of them; h is [layers][wf_tb4_elems(L, T, N, G*Bw)]: the TOP layer row-major
- * [G*Bw*T*N, L] (what the head reads), the layers below TB4; hT hi/lo optional (bf16).
- * p_drop > 0: inter-layer dropout (hybrid_model.py:47) applied by the recurrence kernel to what the next layer reads
- * (site 16 + layer, element ((z*T + t)*N + node)*L + unit); hTm hi/lo [layers-1][...]: transposed copies of the masked h. */
-int wf_lstm_fwd_seq(const float* x, const float* params, const void* p16_hi, const void* p16_lo,
-                    long long params_group_stride, const void* f16_hi, const void* f16_lo, int layers,
-                    int F, int L, int O, int T, int N, int G, int Bw, float* gates, float* h, float* c,
-                    void* hT_hi, void* hT_lo, float p_drop, const unsigned long long* rng,
-                    void* hTm_hi, void* hTm_lo, int* err, void* stream);
+/* 16-bit elements of ONE plane of a TB8 buffer with `channels` values per (window, step, node).  TB8 is the layout of the
+ * 16-bit hi / lo activations of the LSTM path: per (window, step, 128-node tile) a block [channels/8][128 rows][8 values];
+ * an activation is two such planes (hi, lo) back to back.  The same bytes serve as a K-major operand (rows = M: input
+ * projections, dX) and as an MN-major operand (rows = K: weight gradients) of the tensor cores -- nothing is transposed. */
+long long wf_tb8_elems(int channels, int T, int N, long long windows);
 
-/* BPTT (train_hybrid_maml_v5.py:134,169; adapt_hybrid_v5.py:198) over the buffers of wf_lstm_fwd_seq;
- * gates are overwritten with dL/d(pre-activation).  xT hi/lo: bf16 transposed layer-0 input [(G*Bw)][F][RT16]
- * (wf_gcn_layer_fwd_g16); dgT: fp32 scratch [(G*Bw)][4L][RT16], padding columns zero; dlast [G*Bw*N, L]. */
+/* nn.LSTM forward (hybrid_model.py:42-49, 93-105).  x16: layer-0 input as fp16 hi / lo planes, row-major
+ * [2][G*Bw*T*N][F] (wf_gcn_layer_fwd_ss output, or wf_split16 of an fp32 tensor); gates (4L channels) and c (L channels)
+ * are TB4 fp32, [layers] of them.  Hidden states leave as 16-bit hi / lo plane pairs in the TB8 layout:
+ *   h16  [layers-1][2][wf_tb8_elems(L, ..)]  fp16: what the NEXT layer's input projection reads (masked when p_drop > 0);
+ *   hb16 [layers][2][...]   (optional: training)  bf16: the plain h, operand of the weight gradients (tcgen05 kind::f16
+ *        takes one format for both operands and dG needs bf16's exponent range);
+ *   hb16m [layers-1][2][...] (p_drop > 0, training)  bf16: the masked h (dW_ih of the next layer).
+ * ZERO-INITIALISE all three once: the padding rows of a node tile are never written and are contracted by the weight
+ * gradients.  hlast [G*Bw*N, L] fp32: the top layer's last step (what the head reads).
+ * p_drop > 0: inter-layer dropout (hybrid_model.py:47) applied by the recurrence kernel to what the next layer reads
+ * (site 16 + layer, element ((z*T + t)*N + node)*L + unit). */
+int wf_lstm_fwd_seq(const void* x16, const float* params, const void* p16_hi, const void* p16_lo,
+                    long long params_group_stride, const void* f16_hi, const void* f16_lo, int layers,
+                    int F, int L, int O, int T, int N, int G, int Bw, float* gates, void* h16, float* c,
+                    float* hlast, void* hb16, float p_drop, const unsigned long long* rng, void* hb16m,
+                    int* err, void* stream);
+
+/* BPTT (train_hybrid_maml_v5.py:134,169; adapt_hybrid_v5.py:198) over the buffers of wf_lstm_fwd_seq.  xb16: the layer-0
+ * input as BF16 hi / lo planes, row-major [2][G*Bw*T*N][F] (wf_gcn_layer_fwd_ss's Yb16, or wf_split16(.., fmt 1)).  dg16: scratch
+ * [2][wf_tb8_elems(4L, ..)] holding one layer's dL/d(pre-activation) as bf16 hi / lo planes (TB8; zero-initialise once).
+ * Per layer: one persistent recurrence launch, ONE pass over dG for [dW_ih | dW_hh] and both bias gradients
+ * (contraction over rows, operands read MN-major from the activations' own layouts), dX for the layer below. */
 size_t wf_lstm_bwd_seq_workspace_bytes(int layers, int F, int L, int T, int N, int G, int Bw);
-int wf_lstm_bwd_seq(const void* xT_hi, const void* xT_lo, const void* pT16_hi, const void* pT16_lo,
-                    const void* b16_hi, const void* b16_lo, int layers, int F, int L, int O, int T, int N,
-                    int G, int Bw, float* gates, const float* c, const void* hT_hi, const void* hT_lo,
-                    float* dgT, const float* dlast, float* grads, long long grads_group_stride,
-                    float p_drop, const unsigned long long* rng, const void* hTm_hi, const void* hTm_lo,
-                    void* workspace, size_t workspace_bytes, int* err, void* stream);
+int wf_lstm_bwd_seq(const void* xb16, const void* pT16_hi, const void* pT16_lo, const void* b16_hi,
+                    const void* b16_lo, int layers, int F, int L, int O, int T, int N, int G, int Bw,
+                    const float* gates, const float* c, const void* hb16, void* dg16, const float* dlast,
+                    float* grads, long long grads_group_stride, float p_drop, const unsigned long long* rng,
+                    const void* hb16m, void* workspace, size_t workspace_bytes, int* err, void* stream);
 
 /* Single-layer recurrence launches (the persistent kernels wf_lstm_fwd_seq / wf_lstm_bwd_seq issue per layer), for
  * harnesses that time the dominant kernels alone or drive the layers themselves.  *_l pointers address ONE layer. */
-int wf_lstm_seq_recur_fwd(float* gates_l, float* c_l, float* h_l, void* hT_hi_l, void* hT_lo_l, const void* f16_hi,
+int wf_lstm_seq_recur_fwd(float* gates_l, float* c_l, void* h16_l, void* hb16_l, float* hlast, const void* f16_hi,
                           const void* f16_lo, int layer, int layers, int L, int T, int N, int G, int Bw, int* err,
                           void* stream);
-int wf_lstm_seq_recur_bwd(float* gates_l, const float* c_l, float* dgT, const float* ext, int ext_is_dlast,
+int wf_lstm_seq_recur_bwd(const float* gates_l, const float* c_l, void* dg16, const float* ext, int ext_is_dlast,
                           const void* b16_hi, const void* b16_lo, int layer, int layers, int L, int T, int N, int G,
                           int Bw, int* err, void* stream);
+
+/* GCNConv + ReLU (+ train-mode dropout) on PRE-SPLIT fp16 hi / lo activations (model.py:31-42, hybrid_model.py:65-75;
+ * csrc/wf_gemm_ss.cu): Y16 = split(dropout(relu((A_hat X) W^T + b))) with X16 / Y16 as planes [2][G*Bw][R][C].  The first
+ * layer passes the fp32 windows instead (X32 with x_win_off[w] = element offset of window w in a resident features tensor,
+ * dataset.py:36-37, or dense when x_win_off == NULL) plus a scratch xsplit16 [2][G*Bw][R][Cin].  Every row whose
+ * aggregation is not the unit self loop must lie in the leading agg_rows rows of its window (a multiple of 128; the t = 0
+ * slice for the reference's graphs): they are aggregated into side16 [2][G*Bw][agg_rows][Cin] first.
+ * The weight slice stays resident in shared memory, activations stream through TMA, the output leaves through TMA stores.
+ * Cin % 8 == 0, Cout % 128 == 0; W16 hi/lo = wf_split16(W, 0), shared by all groups; dropout / err as wf_gcn_layer_fwd_g16.
+ * Yb16 (optional): the same output once more as bf16 hi / lo planes (xb16 of wf_lstm_bwd_seq). */
+int wf_gcn_layer_fwd_ss(const float* X32, const long long* x_win_off, const void* X16, void* xsplit16,
+                        const void* W16_hi, const void* W16_lo, const float* bias, const int* rowptr,
+                        const int* col, const float* val, long long rowptr_group_stride,
+                        long long csr_group_stride, int agg_rows, void* side16, int R, int Cin, int Cout, int G,
+                        int Bw, int relu, void* Y16, void* Yb16, float p_drop, const unsigned long long* rng,
+                        int site, int* err, void* stream);
+
+/* The two SS-mode kernels on operands given as plain 16-bit planes (test / general entry points).
+ * wf_ss_nodes_gemm: C (TB4 fp32: per (window, step, node tile) a block [Ntot/4][128 rows][4]) = A W^T (+ bias + bias2);
+ *   avar 0: A16 row-major planes [2][G*Bw*T][Nn][K], 1: TB8 planes; W16 hi / lo [G][Ntot][K]; bn = 64 / 128 / 256 columns
+ *   per CTA with bn * K <= 32768 (the weight slice is resident in shared memory); afmt / bfmt 0 fp16, 1 bf16.
+ * wf_ss_wgrad: dst0 [G][512][w0] (+ dst1 [G][512][w1], db [G][512]) = dG^T [B0 | B1] summed over all blocks of a group;
+ *   dg16: TB8 bf16 planes with 512 channels; half h of 128 columns: bvar 0 = TB8 bf16 planes with bC channels (bcol0:
+ *   first channel), 1 = row-major bf16 planes [2][G*Bw*T][Nn][bC] (bcol0: first column); bshift 1 = pair dG of step t
+ *   with B of step t - 1 (dW_hh).  part: scratch, part_floats >= 513 * 512 * G floats per split-K slice. */
+int wf_ss_nodes_gemm(int bn, int avar, const void* A16, long long a_plane, int K, int afmt, const void* W16_hi,
+                     const void* W16_lo, long long w_group_stride, int Ntot, int bfmt, const float* bias,
+                     const float* bias2, long long bias_group_stride, float* C, int T, int Nn, int Bw, int G,
+                     int* err, void* stream);
+int wf_ss_wgrad(const void* dg16, long long dg_plane, int nh, const void* b0, long long b0_plane, int b0var,
+                int b0shift, int b0col0, int b0C, const void* b1, long long b1_plane, int b1var, int b1shift,
+                int b1col0, int b1C, int T, int Nn, int Bw, int G, float* part, long long part_floats, float* dst0,
+                int ld0, int w0, float* dst1, int ld1, int w1, float* db, long long gstride, int* err,
+                void* stream);
+
+/* out[i] = float(hi[i]) + float(lo[i]) (fmt 0: fp16, 1: bf16): the fp32 value of a pair of operand planes. */
+int wf_join16(const void* hi, const void* lo, long long n, int fmt, float* out, void* stream);
 
 /* Nodes per node tile of the TB4 activation layout (<= 128 rows per tile in memory; the N nodes of a window are dealt
  * evenly over ceil(N / 128) tiles, rounded up to 8: 441 -> 112).  Node n of a window lives in tile n / wf_tile_rows(N),

@@ -142,7 +142,7 @@ def test_engine_tensor_core_path_matches_fp32_path(nlat, nlon, T, G, Bw):
         hid = eng.hidden_states()
         grads = eng.backward(theta, eng.P)
         eng.check()
-        out[prec] = (eng.feats.clone(), eng.pred.clone(), loss.clone(), grads.clone(), hid)
+        out[prec] = (eng.gcn_features(), eng.pred.clone(), loss.clone(), grads.clone(), hid)
     f0, p0, l0, g0, h0 = out["fp32"]
     rel = lambda a, b: float((a.double() - b.double()).abs().max() / (b.double().abs().max() + 1e-30))  # 0/0 -> 0 (T = 1: dW_hh = 0)
     lay = unflatten_trainable(g0[0], dims)

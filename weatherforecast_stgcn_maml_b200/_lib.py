@@ -70,19 +70,26 @@ SIGNATURES = {
     "wf_param_stride16": (c_ll, [c_i, c_i, c_i, c_i, c_i]),
     "wf_split16": (c_i, [c_p, c_p, c_p, c_ll, c_i, c_p]),
     "wf_transposed_pitch16": (c_ll, [c_i, c_i]),
-    "wf_transpose_split16_rows": (c_i, [c_p, c_i, c_i, c_i, c_i, c_p, c_p, c_p]),
     "wf_g16_gemm_nt": (c_i, [c_p, c_i, c_i, c_i, c_p, c_p, c_ll, c_i, c_p, c_p, c_ll, c_i, c_i, c_p, c_p, c_p]),
     "wf_gcn_layer_fwd_g16": (c_i, [c_p, c_p, c_ll, c_p, c_p, c_p, c_p, c_p, c_p, c_ll, c_ll, c_p, c_i, c_ll, c_p, c_i, c_i, c_i, c_i,
                                    c_i, c_i, c_i, c_p, c_p, c_p, c_f, c_p, c_i, c_p, c_p]),
     "wf_prep_weights_seq": (c_i, [c_p, c_ll, c_i, c_i, c_i, c_i, c_i, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p]),
+    "wf_tb8_elems": (c_ll, [c_i, c_i, c_i, c_ll]),
     "wf_lstm_fwd_seq": (c_i, [c_p, c_p, c_p, c_p, c_ll, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_p, c_p, c_p,
-                              c_p, c_p, c_f, c_p, c_p, c_p, c_p, c_p]),
+                              c_p, c_p, c_f, c_p, c_p, c_p, c_p]),
     "wf_lstm_bwd_seq_workspace_bytes": (c_sz, [c_i, c_i, c_i, c_i, c_i, c_i, c_i]),
-    "wf_lstm_bwd_seq": (c_i, [c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_p, c_p, c_p,
-                              c_p, c_p, c_p, c_p, c_ll, c_f, c_p, c_p, c_p, c_p, c_sz, c_p, c_p]),
+    "wf_lstm_bwd_seq": (c_i, [c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_p, c_p, c_p, c_p, c_p,
+                              c_p, c_ll, c_f, c_p, c_p, c_p, c_sz, c_p, c_p]),
     "wf_tc_gemm_nt": (c_i, [c_p, c_i, c_i, c_i, c_p, c_p, c_ll, c_i, c_p, c_p, c_ll, c_i, c_p, c_p, c_p]),
     "wf_lstm_seq_recur_fwd": (c_i, [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_p, c_p]),
     "wf_lstm_seq_recur_bwd": (c_i, [c_p, c_p, c_p, c_p, c_i, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_p, c_p]),
+    "wf_gcn_layer_fwd_ss": (c_i, [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_ll, c_ll, c_i, c_p, c_i, c_i, c_i,
+                                  c_i, c_i, c_i, c_p, c_p, c_f, c_p, c_i, c_p, c_p]),
+    "wf_join16": (c_i, [c_p, c_p, c_ll, c_i, c_p, c_p]),
+    "wf_ss_nodes_gemm": (c_i, [c_i, c_i, c_p, c_ll, c_i, c_i, c_p, c_p, c_ll, c_i, c_i, c_p, c_p, c_ll, c_p, c_i, c_i, c_i, c_i,
+                               c_p, c_p]),
+    "wf_ss_wgrad": (c_i, [c_p, c_ll, c_i, c_p, c_ll, c_i, c_i, c_i, c_i, c_p, c_ll, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i,
+                          c_p, c_ll, c_p, c_i, c_i, c_p, c_i, c_i, c_p, c_ll, c_p, c_p]),
 }
 
 _lib = None

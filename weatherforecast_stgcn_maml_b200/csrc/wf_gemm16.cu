@@ -710,43 +710,6 @@ int wf_launch_transpose_split16(const float* in, long long in_gstride, int rows,
   return WF_OK;
 }
 
-// X [Z*T*N, C] row-major fp32 -> bf16 hi / lo transposed copies [Z][C][RT16], column (t, node) = t*Np + node: the K-major
-// operand of the weight-gradient product dW_ih = dG^T X for activations that were not produced by the GCN epilogue
-// (the drop-in nn.Module path hands the LSTM an arbitrary features tensor).  Padding columns are left untouched (zero).
-static __global__ void wf_transpose_rows16_kernel(const float* __restrict__ X, int T, int N, int C, int Np,
-                                                  __nv_bfloat16* __restrict__ out_hi, __nv_bfloat16* __restrict__ out_lo) {
-  __shared__ float t[32][33];
-  const int zt = blockIdx.z, z = zt / T, tt = zt - z * T;
-  const int n0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
-  for (int i = threadIdx.y; i < 32; i += 8) {
-    const int n = n0 + i, c = c0 + threadIdx.x;
-    t[i][threadIdx.x] = (n < N && c < C) ? X[((long long)zt * N + n) * C + c] : 0.f;
-  }
-  __syncthreads();
-  const long long RT = (long long)T * Np;
-  for (int i = threadIdx.y; i < 32; i += 8) {
-    const int c = c0 + i, n = n0 + threadIdx.x;
-    if (c < C && n < N) {
-      const float v = t[threadIdx.x][i];
-      const long long o = ((long long)z * C + c) * RT + (long long)tt * Np + n;
-      const __nv_bfloat16 h = __float2bfloat16_rn(v);
-      out_hi[o] = h;
-      out_lo[o] = __float2bfloat16_rn(v - __bfloat162float(h));
-    }
-  }
-}
-
-extern "C" int wf_transpose_split16_rows(const float* X, int T, int N, int C, int windows, void* out_hi, void* out_lo,
-                                         void* stream) {
-  WF_REQUIRE(T > 0 && N > 0 && C > 0 && windows > 0, "transpose_split16_rows: empty input");
-  WF_REQUIRE((long long)windows * T < 65536, "transpose_split16_rows: windows * T must stay below 65536");
-  dim3 grid(wf_cdiv(N, 32), wf_cdiv(C, 32), windows * T), block(32, 8);
-  wf_transpose_rows16_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(X, T, N, C, wf_np(N), (__nv_bfloat16*)out_hi,
-                                                                       (__nv_bfloat16*)out_lo);
-  WF_CHECK_LAUNCH("transpose_split16_rows");
-  return WF_OK;
-}
-
 // fp32 -> 16-bit hi / lo operand halves (fmt 0: fp16, 1: bf16); n a multiple of 4.
 extern "C" int wf_split16(const float* src, void* hi, void* lo, long long n, int fmt, void* stream) {
   WF_REQUIRE(fmt == 0 || fmt == 1, "split16: fmt must be 0 (fp16) or 1 (bf16)");

@@ -1,0 +1,910 @@
+// SS-mode tcgen05 GEMMs on PRE-SPLIT 16-bit hi/lo operands (sm_100a) -- second generation of the dense products around
+// the LSTM and of the GCN Theta transform (model.py:23-26, hybrid_model.py:42-49,65-74; loss.backward()).
+//
+//   D[128 x BN] (TMEM, fp32) += A[128 x 32] * B[BN x 32]^T  per k-block, three kind::f16 products
+//   a*b ~= a_hi*b_hi + a_lo*b_hi + a_hi*b_lo   (fp16 pairs forward, bf16 pairs where an operand is a gradient)
+//
+// What changed against csrc/wf_gemm16.cu, and why:
+//  * every producer kernel writes its output already split (two 16-bit planes, the same bytes as one fp32), so both
+//    operands go TMA -> shared memory -> tensor core: no converter warps, no TMEM operand hop, a pipeline of two barriers
+//    per stage instead of four;
+//  * the weight operand B is RESIDENT in shared memory (BN x K x hi/lo = 128 KB) for all tiles of a CTA: the L2 -> SM path
+//    (~42 B/clk/SM) carries the activations once per n-part and nothing else -- re-streaming B per tile was 50 % of the
+//    bytes through L2 in the first generation;
+//  * CTAs own CONTIGUOUS ranges of row tiles of ONE n-part, so a CTA changes task (reloads B) at most once or twice;
+//  * GCN outputs leave through shared memory and cp.async.bulk.tensor stores (UTMASTG), full 128-byte lines.
+//
+// Activation layouts the operands are read from:
+//   row-major hl16   [2 planes][rows][K]                     GCN activations (fp16): K-major, SWIZZLE_64B boxes
+//   TB8              [2 planes][block][K/8][128 rows][8]     LSTM h (fp16), dG (bf16); block = (window, step, node tile):
+//                    no-swizzle canonical layouts -- K-major for the projections / dX (rows = M), and the SAME bytes
+//                    MN-major for the weight gradients (rows = K), so nothing is ever transposed in memory.
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+
+#include "wf_common.cuh"
+#include "wf_layout.cuh"
+#include "wf_rng.cuh"
+#include "wf_tc.cuh"
+
+using namespace wftc;
+
+int wf_np(int N);
+extern "C" int wf_tile_rows(int N);
+
+namespace {
+
+constexpr int SS_THREADS = 192;  // warp 0: TMA producer; warp 1: MMA issue + TMEM owner; warps 2-5: epilogue (lane quarters 2,3,0,1)
+constexpr int SS_BK = 32;
+constexpr int SS_A_PLANE = 128 * SS_BK * 2;   // 8 KB: one 16-bit plane of an A stage
+constexpr int SS_A_STAGE = 2 * SS_A_PLANE;    // hi + lo
+constexpr int SS_B_BYTES = 131072;            // resident B: BN x K x 2 B x 2 planes
+constexpr int SS_STG_BYTES = 32768;           // GCN epilogue staging: 4 warps x (hi + lo) x 32 rows x 128 B
+constexpr int SS_MAX_STAGES = 6;
+
+enum { SS_A_KS = 0, SS_A_KT = 1 };    // A: K-major SWIZZLE_64B from row-major hl16 / K-major no-swizzle from TB8
+enum { SS_E_TB4 = 0, SS_E_HL = 1 };   // epilogue: fp32 TB4 block (+bias) / row-major hl16 through TMA stores (+bias, ReLU)
+enum { SS_ROWS = 0, SS_NODES = 1 };   // row tiles: 128 rows of a window / the node tile of one (window, step)
+
+struct SsArgs {
+  int mode, avar, epi;
+  int n_parts;          // N_total / BN
+  int m_tiles_g, G;     // row tiles per group, groups
+  int nkb;              // K / 32
+  int nst;              // A ring depth
+  int b_per_group;      // weights differ per group: reload the resident B when a CTA's range crosses into the next group
+  int afmt, bfmt;       // 0 fp16, 1 bf16
+  // ROWS: windows of R rows; the first agg_rows rows of every window come from the side buffer (aggregated rows)
+  int R, Bw, win_tiles, agg_tiles;
+  // NODES
+  int T, Nn, tpw, rpt;
+  // epilogue
+  float* C; int c_cols;
+  const float* bias; const float* bias2; long long bias_gstride; int relu;
+  DropCfg drop; float range_limit;
+  int out2;             // E_HL: also write bf16 planes through tmOut2
+  int* err;
+};
+
+__host__ __device__ constexpr uint32_t ss_idesc(int n, uint32_t afmt, uint32_t bfmt, uint32_t a_mn, uint32_t b_mn) {
+  return (1u << 4) | (afmt << 7) | (bfmt << 10) | (a_mn << 15) | (b_mn << 16) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+}
+// shared-memory matrix descriptor: start address, leading / stride byte offsets, layout (0 none, 2 SWIZZLE_128B, 4 SWIZZLE_64B)
+__device__ __forceinline__ uint64_t ss_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo, uint32_t layout) {
+  return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo >> 4) & 0x3FFF) << 16) | ((uint64_t)((sbo >> 4) & 0x3FFF) << 32) |
+         ((uint64_t)1 << 46) | ((uint64_t)layout << 61);
+}
+__device__ __forceinline__ void ss_mma(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+               "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
+               ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void tma_load_5d(void* dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2, int c3, int c4) {
+  asm volatile("cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];\n"
+               ::"r"(smem_u32(dst)), "l"(m), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
+}
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* m, const void* src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];\n"
+               ::"l"(m), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;\n" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;\n" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
+
+__device__ __forceinline__ void ss_split_bf16(float a, float b, uint32_t& hi, uint32_t& lo) {
+  const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  const __nv_bfloat162 l = __floats2bfloat162_rn(a - __uint_as_float(hi << 16), b - __uint_as_float(hi & 0xFFFF0000u));
+  lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+__device__ __forceinline__ void ss_split_f16(float a, float b, uint32_t& hi, uint32_t& lo) {
+  const __half2 h = __floats2half2_rn(a, b);
+  const float2 f = __half22float2(h);
+  const __half2 l = __floats2half2_rn(a - f.x, b - f.y);
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+
+struct SsTile { int g, mtg, z, mtw, zt, nt, blk, node0; bool side; };
+
+// row tile `mt` of the flattened (group, tile-in-group) space
+__device__ __forceinline__ SsTile ss_decode(const SsArgs& a, int mt) {
+  SsTile t;
+  t.g = mt / a.m_tiles_g;
+  t.mtg = mt - t.g * a.m_tiles_g;
+  t.z = 0; t.mtw = 0; t.zt = 0; t.nt = 0; t.blk = 0; t.node0 = 0; t.side = false;
+  if (a.mode == SS_ROWS) {
+    const int w = t.mtg / a.win_tiles;
+    t.mtw = t.mtg - w * a.win_tiles;
+    t.z = t.g * a.Bw + w;
+    t.side = t.mtw < a.agg_tiles;
+  } else {
+    const int ztl = t.mtg / a.tpw;
+    t.nt = t.mtg - ztl * a.tpw;
+    t.node0 = t.nt * a.rpt;
+    t.zt = t.g * a.Bw * a.T + ztl;
+    t.blk = t.zt * a.tpw + t.nt;
+  }
+  return t;
+}
+
+// D[row tile][n-part] = A B^T with B resident.  tmA: main A source; tmA2: ROWS side buffer (aggregated leading rows);
+// tmBhi / tmBlo: weights [G or 1][N_total][K] as two planes; tmOut: E_HL output [2 planes][Z][R][N_total] (fp16);
+// tmOut2 (a.out2): the same values once more as bf16 planes (the weight gradients' operand format).
+template <int BN, bool DROP>
+__global__ void __launch_bounds__(SS_THREADS, 1)
+wf_ss_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
+             const __grid_constant__ CUtensorMap tmBhi, const __grid_constant__ CUtensorMap tmBlo,
+             const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmOut2, const SsArgs a) {
+  constexpr int NH = BN > 128 ? 2 : 1;          // MMA instructions per product and K step (N = 128 each, or one of N = BN)
+  constexpr int NI = BN > 128 ? 128 : BN;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sB = smem;                           // [plane][k-block][BN rows][64 B]
+  uint8_t* sA = smem + SS_B_BYTES;              // ring of A stages: [plane][...]
+  uint8_t* sStg = sA + a.nst * SS_A_STAGE;
+  __shared__ uint64_t full[SS_MAX_STAGES], empty[SS_MAX_STAGES], dfull[2], dempty[2], bfull, bempty;
+  __shared__ uint32_t tmem_base_s;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int NST = a.nst;
+
+  // this CTA: one n-part, a contiguous range of row tiles
+  const int npart = blockIdx.x % a.n_parts, slot = blockIdx.x / a.n_parts, slots = gridDim.x / a.n_parts;
+  const int total_mt = a.m_tiles_g * a.G;
+  const int per = (total_mt + slots - 1) / slots;
+  const int mt0 = slot * per, mt1 = min(total_mt, mt0 + per);
+  const int n0 = npart * BN;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < NST; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&dfull[s], 1); mbar_init(&dempty[s], 4); }
+    mbar_init(&bfull, 1); mbar_init(&bempty, 1);
+    mbar_fence_init();
+    tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmBhi); tma_prefetch_desc(&tmBlo);
+  }
+  if (warp == 1) tmem_alloc(&tmem_base_s, 2 * BN);   // two accumulator stages: 128 / 256 / 512 columns
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tbase = tmem_base_s;
+  const uint32_t b_plane = (uint32_t)a.nkb * BN * 64u;   // bytes of one resident B plane
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int it = 0, bload = 0, gprev = -1;
+      for (int mt = mt0; mt < mt1; ++mt) {
+        const SsTile t = ss_decode(a, mt);
+        const int gb = a.b_per_group ? t.g : 0;
+        if (gb != gprev) {  // (re)load the resident weight slice of this group
+          if (bload > 0 && !mbar_wait(&bempty, (bload - 1) & 1)) { atomicExch(a.err, 51); break; }
+          mbar_expect_tx(&bfull, 2 * b_plane);
+          for (int kb = 0; kb < a.nkb; ++kb) {
+            tma_load_3d(sB + kb * BN * 64, &tmBhi, &bfull, kb * SS_BK, n0, gb);
+            tma_load_3d(sB + b_plane + kb * BN * 64, &tmBlo, &bfull, kb * SS_BK, n0, gb);
+          }
+          gprev = gb; ++bload;
+        }
+        for (int kb = 0; kb < a.nkb; ++kb, ++it) {
+          const int s = it % NST, ph = (it / NST) & 1;
+          if (!mbar_wait(&empty[s], ph ^ 1)) { atomicExch(a.err, 52); mt = mt1; break; }
+          uint8_t* st = sA + s * SS_A_STAGE;
+          mbar_expect_tx(&full[s], SS_A_STAGE);
+          if (a.avar == SS_A_KT) {   // TB8 block: [plane][block][K/8][128 rows][8]
+            tma_load_5d(st, &tmA, &full[s], 0, 0, kb * 4, t.blk, 0);
+            tma_load_5d(st + SS_A_PLANE, &tmA, &full[s], 0, 0, kb * 4, t.blk, 1);
+          } else if (a.mode == SS_NODES) {  // row-major [plane][(window, step)][node][K]
+            tma_load_4d(st, &tmA, &full[s], kb * SS_BK, t.node0, t.zt, 0);
+            tma_load_4d(st + SS_A_PLANE, &tmA, &full[s], kb * SS_BK, t.node0, t.zt, 1);
+          } else {                          // row-major [plane][window][row][K]; leading rows from the side buffer
+            const CUtensorMap* m = t.side ? &tmA2 : &tmA;
+            tma_load_4d(st, m, &full[s], kb * SS_BK, t.mtw * 128, t.z, 0);
+            tma_load_4d(st + SS_A_PLANE, m, &full[s], kb * SS_BK, t.mtw * 128, t.z, 1);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    const uint32_t idesc = ss_idesc(NI, (uint32_t)a.afmt, (uint32_t)a.bfmt, 0, 0);
+    int it = 0, lt = 0, bload = 0, gprev = -1;
+    bool ok = true;
+    for (int mt = mt0; mt < mt1 && ok; ++mt, ++lt) {
+      const SsTile t = ss_decode(a, mt);
+      const int gb = a.b_per_group ? t.g : 0;
+      const int ds = lt & 1;
+      if (!mbar_wait(&dempty[ds], ((lt >> 1) & 1) ^ 1)) { if (lane == 0) atomicExch(a.err, 53); ok = false; break; }
+      if (gb != gprev) {
+        if (!mbar_wait(&bfull, bload & 1)) { if (lane == 0) atomicExch(a.err, 54); ok = false; break; }
+        gprev = gb; ++bload;
+      }
+      tc_fence_after();
+      for (int kb = 0; kb < a.nkb; ++kb, ++it) {
+        const int s = it % NST, ph = (it / NST) & 1;
+        if (!mbar_wait(&full[s], ph)) { if (lane == 0) atomicExch(a.err, 55); ok = false; break; }
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t ahi = smem_u32(sA + s * SS_A_STAGE), bhi = smem_u32(sB + kb * BN * 64);
+#pragma unroll
+          for (int k16 = 0; k16 < 2; ++k16) {
+#pragma unroll
+            for (int p = 0; p < 3; ++p) {  // A_hi B_hi, A_lo B_hi, A_hi B_lo
+              const uint32_t as = ahi + (p == 1 ? SS_A_PLANE : 0), bs = bhi + (p == 2 ? b_plane : 0);
+              const uint64_t ad = a.avar == SS_A_KT ? ss_desc(as + k16 * 4096, 2048, 128, 0) : ss_desc(as + k16 * 32, 16, 512, 4);
+#pragma unroll
+              for (int h = 0; h < NH; ++h)
+                ss_mma(tbase + ds * BN + h * 128, ad, ss_desc(bs + h * 8192 + k16 * 32, 16, 512, 4), idesc,
+                       (kb | k16 | p) ? 1u : 0u);
+            }
+          }
+          umma_commit(&empty[s]);
+          if (kb == a.nkb - 1) {
+            umma_commit(&dfull[ds]);
+            // last tile of this group in my range: the resident B may be replaced once these MMAs have completed
+            const int gnext = mt + 1 < mt1 ? (a.b_per_group ? (mt + 1) / a.m_tiles_g : 0) : -2;
+            if (gnext != gb && gnext != -2) umma_commit(&bempty);
+          }
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue
+    const int q = warp & 3, row = q * 32 + lane;
+    const uint32_t tlane = tbase + ((uint32_t)(q * 32) << 16);
+    uint8_t* stg = sStg + (warp - 2) * 8192;   // [plane][32 rows][128 B], 16-byte chunks XOR-swizzled by (row & 7)
+    int lt = 0;
+    bool ok = true;
+    for (int mt = mt0; mt < mt1 && ok; ++mt, ++lt) {
+      const SsTile t = ss_decode(a, mt);
+      const int ds = lt & 1;
+      if (!mbar_wait(&dfull[ds], (lt >> 1) & 1)) { if (lane == 0) atomicExch(a.err, 56); ok = false; break; }
+      tc_fence_after();
+      const float* b1 = a.bias ? a.bias + t.g * a.bias_gstride + n0 : nullptr;
+      const float* b2 = a.bias2 ? a.bias2 + t.g * a.bias_gstride + n0 : nullptr;
+      DropState dst;
+      if (DROP) dst = wf_drop_state(a.drop);
+      if (a.epi == SS_E_TB4) {
+        // TB4 block = [c_cols / 4 channel groups][128 rows][4 floats]: 512 contiguous bytes per warp store
+        float4* cblk = reinterpret_cast<float4*>(a.C) + ((long long)t.blk * (a.c_cols >> 2) + (n0 >> 2)) * 128 + row;
+        unsigned long long e4row = 0;
+        if (DROP) e4row = (((unsigned long long)t.zt * a.Nn + (unsigned)(t.node0 + row)) * (unsigned)a.c_cols + (unsigned)n0) >> 2;
+#pragma unroll 1
+        for (int cc = 0; cc < BN; cc += 32) {
+          uint32_t v[32];
+          __syncwarp();
+          tmem_ld32(tlane + ds * BN + cc, v);
+          tmem_wait_ld();
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            float4 o = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+            if (b1) { const float4 b = __ldg(reinterpret_cast<const float4*>(b1 + cc + j)); o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w; }
+            if (b2) { const float4 b = __ldg(reinterpret_cast<const float4*>(b2 + cc + j)); o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w; }
+            if (DROP) {
+              float m[4];
+              wf_drop4(dst, e4row + (unsigned)((cc + j) >> 2), m);
+              o.x *= m[0]; o.y *= m[1]; o.z *= m[2]; o.w *= m[3];
+            }
+            if (row < a.rpt) cblk[(long long)((cc + j) >> 2) * 128] = o;  // rows >= rpt of a node tile are padding
+          }
+        }
+      } else {
+        // row-major hl16 through shared memory + TMA stores: per 64 columns and plane a [32 rows][128 B] box per warp;
+        // the stores clip at the window's R rows (3-D map), so partial tiles need no masking
+        const int grow = t.mtw * 128 + row;
+        const bool valid = grow < a.R;
+        unsigned long long e4row = 0;
+        if (DROP) e4row = ((((unsigned long long)t.z * (unsigned)a.R) + (unsigned)grow) * (unsigned)a.c_cols + (unsigned)n0) >> 2;
+        float amax = 0.f;
+        const int npass = a.out2 ? 2 : 1;   // pass 1: the same values again as bf16 planes
+#pragma unroll 1
+        for (int c64p = 0; c64p < (BN / 64) * npass; ++c64p) {
+          const int c64 = (c64p / npass) * 64, pass = c64p % npass;
+          if (lane == 0) tma_store_wait_read();   // the previous boxes have been read out of the staging buffer
+          __syncwarp();
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {
+            const int cc = c64 + 32 * half;
+            uint32_t v[32];
+            tmem_ld32(tlane + ds * BN + cc, v);
+            tmem_wait_ld();
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              uint32_t hi[4], lo[4];
+#pragma unroll
+              for (int e = 0; e < 8; e += 4) {
+                float4 o = make_float4(__uint_as_float(v[j + e]), __uint_as_float(v[j + e + 1]), __uint_as_float(v[j + e + 2]),
+                                       __uint_as_float(v[j + e + 3]));
+                if (b1) { const float4 b = __ldg(reinterpret_cast<const float4*>(b1 + cc + j + e)); o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w; }
+                if (a.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+                if (DROP) {
+                  float m[4];
+                  wf_drop4(dst, e4row + (unsigned)((cc + j + e) >> 2), m);
+                  o.x *= m[0]; o.y *= m[1]; o.z *= m[2]; o.w *= m[3];
+                }
+                if (valid) amax = fmaxf(amax, fmaxf(fmaxf(fabsf(o.x), fabsf(o.y)), fmaxf(fabsf(o.z), fabsf(o.w))));
+                if (pass == 0) {
+                  ss_split_f16(o.x, o.y, hi[e >> 1], lo[e >> 1]);
+                  ss_split_f16(o.z, o.w, hi[(e >> 1) + 1], lo[(e >> 1) + 1]);
+                } else {
+                  ss_split_bf16(o.x, o.y, hi[e >> 1], lo[e >> 1]);
+                  ss_split_bf16(o.z, o.w, hi[(e >> 1) + 1], lo[(e >> 1) + 1]);
+                }
+              }
+              const int ch = (32 * half + j) >> 3;   // 16-byte chunk of this row's 128-byte line
+              const uint32_t off = (uint32_t)(lane * 128 + ((ch ^ (lane & 7)) << 4));
+              sts128(smem_u32(stg + off), make_uint4(hi[0], hi[1], hi[2], hi[3]));
+              sts128(smem_u32(stg + 4096 + off), make_uint4(lo[0], lo[1], lo[2], lo[3]));
+            }
+          }
+          fence_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            const CUtensorMap* om = pass == 0 ? &tmOut : &tmOut2;
+            tma_store_4d(om, stg, n0 + c64, t.mtw * 128 + q * 32, t.z, 0);
+            tma_store_4d(om, stg + 4096, n0 + c64, t.mtw * 128 + q * 32, t.z, 1);
+            tma_store_commit();
+          }
+        }
+        // an activation the next layer cannot hold as fp16 hi/lo (|x| >= 65520 rounds to inf), or a non-finite one
+        if (a.range_limit > 0.f && valid && !(amax < a.range_limit)) atomicExch(a.err, 41);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&dempty[ds]);
+    }
+    if (a.epi == SS_E_HL && lane == 0) tma_store_wait_all();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tbase, 2 * BN);
+}
+
+
+// ================================================================================= weight gradients
+// dW[g][512 gate rows][nh * 128] = sum over the task's (window, step, node tile) blocks of dG^T [X | H_prev]
+// (loss.backward() through nn.LSTM: dW_ih = dG^T x, dW_hh = sum_{t >= 1} dG[t]^T h[t-1]; train_hybrid_maml_v5.py:134,169).
+// Both operands are read MN-major straight from the activations' own layouts -- the contraction runs over ROWS:
+//   A   = dG, TB8 bf16 hi/lo: block [64 channel groups][128 rows][8]  -> [16 groups of this m tile][32 rows][16 B] per stage
+//   B_h = half h of the N range, either TB8 fp16 (h of the layer below at the same step, or this layer's h one step
+//         EARLIER: `shift`; step 0 has no such term and is skipped) or row-major fp16 features (SWIZZLE_128B boxes).
+// Rows >= rpt of a block are padding: never written by any kernel, zero since allocation, so they add nothing.
+// The bias gradients (row sums of dG^T) come out of the same pass as a 16-column product with a tile of ones.
+// Split-K over blocks; partial tiles go to `part`, summed in fixed order by wf_wg_reduce_kernel (deterministic).
+constexpr int WG_THREADS = 192;
+struct WgArgs {
+  int G, Bw, T, tpw, rpt, Nn;
+  int splits, bps;              // blocks per split
+  int nh;                       // B halves of 128 columns
+  int bvar[2];                  // 0: TB8 (MN-major, no swizzle), 1: row-major hl16 (MN-major, SWIZZLE_128B)
+  int bshift[2];                // 1: the block of the previous step (t - 1)
+  int bcol0[2];                 // TB8: first channel group of the half; row-major: first column
+  int afmt, bfmt;
+  int nst;
+  float* part; float* bias_part;   // [splits][G][512][nh * 128], [splits][G][512]
+  int* err;
+};
+
+__global__ void __launch_bounds__(WG_THREADS, 1)
+wf_wg_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB0,
+             const __grid_constant__ CUtensorMap tmB1, const WgArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int STAGE = SS_A_STAGE * (1 + a.nh);   // A (hi, lo) then each B half (hi, lo)
+  uint8_t* ones = smem + a.nst * STAGE;        // [2 column groups][16 rows][16 B] of 1.0 in B's format
+  __shared__ uint64_t full[SS_MAX_STAGES], empty[SS_MAX_STAGES], dfull, dempty;
+  __shared__ uint32_t tmem_base_s;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, NST = a.nst;
+  const int blocks_g = a.Bw * a.T * a.tpw;
+  const int total = a.splits * a.G * 4;
+  const int kb_n = (a.rpt + 31) / 32;          // 32-row k-blocks that hold data
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < NST; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    mbar_init(&dfull, 1); mbar_init(&dempty, 4);
+    mbar_fence_init();
+    tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmB0); tma_prefetch_desc(&tmB1);
+  }
+  if (threadIdx.x < 128) reinterpret_cast<uint32_t*>(ones)[threadIdx.x] = a.bfmt == 0 ? 0x3C003C00u : 0x3F803F80u;
+  if (warp == 1) tmem_alloc(&tmem_base_s, 512);
+  fence_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tbase = tmem_base_s;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int it = 0;
+      for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+        const int mtile = tile & 3, g = (tile >> 2) % a.G, split = (tile >> 2) / a.G;
+        const int b0 = split * a.bps, b1 = min(blocks_g, b0 + a.bps);
+        for (int b = b0; b < b1; ++b) {
+          const int t = (b / a.tpw) % a.T, nt = b % a.tpw;
+          const int blk = g * blocks_g + b;
+          for (int kb = 0; kb < kb_n; ++kb, ++it) {
+            const int s = it % NST, ph = (it / NST) & 1;
+            if (!mbar_wait(&empty[s], ph ^ 1)) { atomicExch(a.err, 61); tile = total; b = b1; break; }
+            uint8_t* st = smem + s * STAGE;
+            int bytes = SS_A_STAGE;
+            for (int h = 0; h < a.nh; ++h) if (!(a.bshift[h] && t == 0)) bytes += SS_A_STAGE;
+            mbar_expect_tx(&full[s], bytes);
+            tma_load_5d(st, &tmA, &full[s], 0, kb, mtile * 16, blk, 0);
+            tma_load_5d(st + SS_A_PLANE, &tmA, &full[s], 0, kb, mtile * 16, blk, 1);
+            for (int h = 0; h < a.nh; ++h) {
+              if (a.bshift[h] && t == 0) continue;
+              const CUtensorMap* m = h == 0 ? &tmB0 : &tmB1;
+              uint8_t* sb = st + SS_A_STAGE * (1 + h);
+              if (a.bvar[h] == 0) {
+                const int bb = blk - a.bshift[h] * a.tpw;
+                tma_load_5d(sb, m, &full[s], 0, kb, a.bcol0[h], bb, 0);
+                tma_load_5d(sb + SS_A_PLANE, m, &full[s], 0, kb, a.bcol0[h], bb, 1);
+              } else {  // row-major [plane][(window, step)][node][C]: two 64-column boxes per plane
+                const int zt = blk / a.tpw, node = nt * a.rpt + kb * 32;
+                for (int j = 0; j < 2; ++j) {
+                  tma_load_4d(sb + j * 4096, m, &full[s], a.bcol0[h] + 64 * j, node, zt, 0);
+                  tma_load_4d(sb + SS_A_PLANE + j * 4096, m, &full[s], a.bcol0[h] + 64 * j, node, zt, 1);
+                }
+              }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    const uint32_t idesc = ss_idesc(128, (uint32_t)a.afmt, (uint32_t)a.bfmt, 1, 1);
+    const uint32_t idesc1 = ss_idesc(16, (uint32_t)a.afmt, (uint32_t)a.bfmt, 1, 1);
+    const uint64_t odesc = ss_desc(smem_u32(ones), 128, 256, 0);
+    int it = 0, lt = 0;
+    bool ok = true;
+    for (int tile = blockIdx.x; tile < total && ok; tile += gridDim.x, ++lt) {
+      const int split = (tile >> 2) / a.G;
+      const int b0 = split * a.bps, b1 = min(blocks_g, b0 + a.bps);
+      if (!mbar_wait(&dempty, (lt & 1) ^ 1)) { if (lane == 0) atomicExch(a.err, 62); ok = false; break; }
+      tc_fence_after();
+      uint32_t acc[2] = {0u, 0u}, acc1 = 0u;
+      for (int b = b0; b < b1 && ok; ++b) {
+        const int t = (b / a.tpw) % a.T;
+        for (int kb = 0; kb < kb_n; ++kb, ++it) {
+          const int s = it % NST, ph = (it / NST) & 1;
+          if (!mbar_wait(&full[s], ph)) { if (lane == 0) atomicExch(a.err, 63); ok = false; break; }
+          tc_fence_after();
+          if (lane == 0) {
+            const uint32_t as = smem_u32(smem + s * STAGE);
+            const int nk16 = min(2, (a.rpt - kb * 32 + 15) / 16);
+            for (int k16 = 0; k16 < nk16; ++k16) {
+              const uint64_t ahi = ss_desc(as + k16 * 256, 128, 512, 0), alo = ss_desc(as + SS_A_PLANE + k16 * 256, 128, 512, 0);
+              for (int h = 0; h < a.nh; ++h) {
+                if (a.bshift[h] && t == 0) continue;
+                const uint32_t bs = as + SS_A_STAGE * (1 + h);
+                uint64_t bhi, blo;
+                if (a.bvar[h] == 0) { bhi = ss_desc(bs + k16 * 256, 128, 512, 0); blo = ss_desc(bs + SS_A_PLANE + k16 * 256, 128, 512, 0); }
+                else { bhi = ss_desc(bs + k16 * 2048, 4096, 1024, 2); blo = ss_desc(bs + SS_A_PLANE + k16 * 2048, 4096, 1024, 2); }
+                ss_mma(tbase + h * 128, ahi, bhi, idesc, acc[h]);
+                ss_mma(tbase + h * 128, alo, bhi, idesc, 1u);
+                ss_mma(tbase + h * 128, ahi, blo, idesc, 1u);
+                acc[h] = 1u;
+              }
+              if (a.bias_part != nullptr) {
+                ss_mma(tbase + 256, ahi, odesc, idesc1, acc1);   // row sums of dG^T: the bias gradients
+                ss_mma(tbase + 256, alo, odesc, idesc1, 1u);
+                acc1 = 1u;
+              }
+            }
+            umma_commit(&empty[s]);
+          }
+          __syncwarp();
+        }
+      }
+      if (lane == 0 && ok) umma_commit(&dfull);
+      __syncwarp();
+    }
+  } else {
+    const int q = warp & 3, row = q * 32 + lane;
+    const uint32_t tlane = tbase + ((uint32_t)(q * 32) << 16);
+    const int ncol = a.nh * 128;
+    int lt = 0;
+    for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++lt) {
+      const int mtile = tile & 3, g = (tile >> 2) % a.G, split = (tile >> 2) / a.G;
+      if (!mbar_wait(&dfull, lt & 1)) { if (lane == 0) atomicExch(a.err, 64); break; }
+      tc_fence_after();
+      float* crow = a.part + (((long long)split * a.G + g) * 512 + mtile * 128 + row) * ncol;
+      // a half whose every block of this split was skipped (step 0 of a shifted operand) never touched its accumulator
+      bool live[2] = {false, false};
+      {
+        const int b0 = split * a.bps, b1 = min(blocks_g, b0 + a.bps);
+        for (int h = 0; h < a.nh; ++h)
+          for (int b = b0; b < b1 && !live[h]; ++b) live[h] = !(a.bshift[h] && (b / a.tpw) % a.T == 0);
+      }
+#pragma unroll 1
+      for (int cc = 0; cc < ncol; cc += 32) {
+        uint32_t v[32];
+        __syncwarp();
+        tmem_ld32(tlane + cc, v);
+        tmem_wait_ld();
+        if (!live[cc >> 7]) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = 0u;
+        }
+#pragma unroll
+        for (int j = 0; j < 32; j += 4)
+          *reinterpret_cast<float4*>(crow + cc + j) = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
+                                                                  __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+      }
+      if (a.bias_part != nullptr) {
+        uint32_t v[8];
+        __syncwarp();
+        tmem_ld8(tlane + 256, v);
+        tmem_wait_ld();
+        a.bias_part[((long long)split * a.G + g) * 512 + mtile * 128 + row] = __uint_as_float(v[0]);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&dempty);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tbase, 512);
+}
+
+// dst_h[g][m][c] = sum_s part[s][g][m][h*128 + c] (fixed order); bias -> both LSTM bias gradients
+__global__ void wf_wg_reduce_kernel(const float* __restrict__ part, const float* __restrict__ bias_part, int splits, int G, int nh,
+                                    float* dst0, int ld0, int w0, float* dst1, int ld1, int w1, float* db1, float* db2,
+                                    long long gstride) {
+  // columns [0, w0) of a tile row go to dst0 (row pitch ld0), columns [w0, w0 + w1) to dst1 (row pitch ld1)
+  const int ncol = nh * 128, g = blockIdx.y;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;   // over 512 * ncol / 4 float4 + 512 bias rows
+  const int quads = 512 * ncol / 4;
+  if (i < quads) {
+    const int m = (i * 4) / ncol, c = (i * 4) - m * ncol;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int s = 0; s < splits; ++s) {
+      const float4 v = *reinterpret_cast<const float4*>(part + (((long long)s * G + g) * 512 + m) * ncol + c);
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    if (c < w0) *reinterpret_cast<float4*>(dst0 + g * gstride + (long long)m * ld0 + c) = acc;
+    else if (dst1 != nullptr && c - w0 < w1) *reinterpret_cast<float4*>(dst1 + g * gstride + (long long)m * ld1 + (c - w0)) = acc;
+  } else if (i < quads + 512 && bias_part != nullptr && db1 != nullptr) {
+    const int m = i - quads;
+    float acc = 0.f;
+    for (int s = 0; s < splits; ++s) acc += bias_part[((long long)s * G + g) * 512 + m];
+    db1[g * gstride + m] = acc;
+    if (db2) db2[g * gstride + m] = acc;
+  }
+}
+
+}  // namespace
+
+// ================================================================================= host side
+namespace {
+
+int ss_dtype(int fmt) { return fmt == 0 ? 1 : 2; }   // wf_encode_tensor_map: 1 = f16, 2 = bf16
+
+// row-major hl16 [2 planes][Z][rows][C]: K-major operand boxes {32 k, box_rows} (SWIZZLE_64B)
+int map_rows_k(CUtensorMap* m, const void* base, uint64_t C, uint64_t rows, uint64_t Z, uint64_t plane, uint32_t box_rows, int fmt) {
+  uint64_t dims[4] = {C, rows, Z, 2};
+  uint64_t str[3] = {C * 2, rows * C * 2, plane * 2};
+  uint32_t box[4] = {SS_BK, box_rows, 1, 1};
+  return wf_encode_tensor_map(m, base, 4, dims, str, box, 2, ss_dtype(fmt));
+}
+// the same tensor as an MN-major operand (rows = K): boxes {64 columns, 32 rows} (SWIZZLE_128B); also the GCN output map
+int map_rows_mn(CUtensorMap* m, const void* base, uint64_t C, uint64_t rows, uint64_t Z, uint64_t plane, int fmt) {
+  uint64_t dims[4] = {C, rows, Z, 2};
+  uint64_t str[3] = {C * 2, rows * C * 2, plane * 2};
+  uint32_t box[4] = {64, 32, 1, 1};
+  return wf_encode_tensor_map(m, base, 4, dims, str, box, 1, ss_dtype(fmt));
+}
+// TB8 [2 planes][blocks][C/8][128 rows][8]: the 128 x 8 elements of a channel group are folded as {256, 4}.
+// fold = 4, groups = 4: a K-major [128 rows][32 k] box; fold = 1, groups = 16: an MN-major [128 channels][32 rows] box
+int map_tb8(CUtensorMap* m, const void* base, uint64_t C, uint64_t blocks, uint64_t plane, uint32_t fold, uint32_t groups, int fmt) {
+  uint64_t dims[5] = {256, 4, C / 8, blocks, 2};
+  uint64_t str[4] = {512, 2048, C * 256, plane * 2};
+  uint32_t box[5] = {256, fold, groups, 1, 1};
+  return wf_encode_tensor_map(m, base, 5, dims, str, box, 0, ss_dtype(fmt));
+}
+// weights [G][N][K] (one plane): resident-B boxes {32 k, bn rows} (SWIZZLE_64B)
+int map_w(CUtensorMap* m, const void* base, uint64_t K, uint64_t N, uint64_t G, uint64_t ld, uint64_t gstride, uint32_t bn, int fmt) {
+  uint64_t dims[3] = {K, N, G};
+  uint64_t str[2] = {ld * 2, gstride * 2};
+  uint32_t box[3] = {SS_BK, bn, 1};
+  return wf_encode_tensor_map(m, base, 3, dims, str, box, 2, ss_dtype(fmt));
+}
+
+int ss_sms() {
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0)
+      sms = 148;
+  }
+  return sms;
+}
+
+template <int BN>
+int ss_launch_bn(const CUtensorMap& tmA, const CUtensorMap& tmA2, const CUtensorMap& tmBhi, const CUtensorMap& tmBlo,
+                 const CUtensorMap& tmOut, const CUtensorMap& tmOut2, SsArgs& a, cudaStream_t st) {
+  a.nst = a.epi == SS_E_HL ? 4 : 6;
+  const int smem = SS_B_BYTES + a.nst * SS_A_STAGE + (a.epi == SS_E_HL ? SS_STG_BYTES : 0) + 1024;
+  static bool configured = false;
+  if (!configured) {
+    const int mx = SS_B_BYTES + 6 * SS_A_STAGE + 1024;
+    if (cudaFuncSetAttribute(wf_ss_kernel<BN, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx) != cudaSuccess ||
+        cudaFuncSetAttribute(wf_ss_kernel<BN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx) != cudaSuccess)
+      return wf_fail(WF_ECUDA, "ss kernel: cannot raise dynamic shared memory to %d", mx);
+    configured = true;
+  }
+  const int total_mt = a.m_tiles_g * a.G;
+  int slots = ss_sms() / a.n_parts;
+  if (slots > total_mt) slots = total_mt;
+  if (slots < 1) slots = 1;
+  const int grid = slots * a.n_parts;
+  if (a.drop.rng != nullptr) wf_ss_kernel<BN, true><<<grid, SS_THREADS, smem, st>>>(tmA, tmA2, tmBhi, tmBlo, tmOut, tmOut2, a);
+  else wf_ss_kernel<BN, false><<<grid, SS_THREADS, smem, st>>>(tmA, tmA2, tmBhi, tmBlo, tmOut, tmOut2, a);
+  WF_CHECK_LAUNCH("ss_kernel");
+  return WF_OK;
+}
+
+int ss_launch(int bn, const CUtensorMap& tmA, const CUtensorMap& tmA2, const CUtensorMap& tmBhi, const CUtensorMap& tmBlo,
+              const CUtensorMap& tmOut, const CUtensorMap& tmOut2, SsArgs& a, cudaStream_t st) {
+  WF_REQUIRE((long long)bn * a.nkb * SS_BK * 4 <= SS_B_BYTES, "ss gemm: the weight slice %d x %d does not fit shared memory", bn, a.nkb * SS_BK);
+  if (bn == 64) return ss_launch_bn<64>(tmA, tmA2, tmBhi, tmBlo, tmOut, tmOut2, a, st);
+  if (bn == 128) return ss_launch_bn<128>(tmA, tmA2, tmBhi, tmBlo, tmOut, tmOut2, a, st);
+  if (bn == 256) return ss_launch_bn<256>(tmA, tmA2, tmBhi, tmBlo, tmOut, tmOut2, a, st);
+  return wf_fail(WF_EINVAL, "ss gemm: unsupported n-part width %d", bn);
+}
+
+}  // namespace
+
+// C (TB4 fp32, c_cols = Ntot channels per block) = A W^T (+ bias + bias2) per (window, step, node tile).
+// avar 0: A row-major hl16 [2][G*Bw*T][Nn][K]; 1: A TB8 hl16 [2][blocks][K/8][128][8].  W hi/lo: [G][Ntot][K] (ldb, gstride).
+int wf_ss_launch_nodes(int bn, int avar, const void* A16, long long a_plane, int K, int afmt, const void* Bhi, const void* Blo,
+                       int ldb, long long b_gstride, int Ntot, int bfmt, const float* bias, const float* bias2,
+                       long long bias_gstride, float* C, int T, int Nn, int Bw, int G, const DropCfg* drop, int* err,
+                       cudaStream_t st) {
+  WF_REQUIRE(K % SS_BK == 0 && Ntot % bn == 0 && ldb % 8 == 0, "ss_nodes: K=%d must be a multiple of 32, N=%d of %d", K, Ntot, bn);
+  WF_REQUIRE(((uintptr_t)A16 | (uintptr_t)Bhi | (uintptr_t)Blo | (uintptr_t)C) % 16 == 0, "ss_nodes: pointers must be 16-byte aligned");
+  const int tpw = wf_cdiv(Nn, 128);
+  const long long ZT = (long long)G * Bw * T;
+  CUtensorMap tmA, tmBhi, tmBlo;
+  int rc;
+  if (avar == SS_A_KT) rc = map_tb8(&tmA, A16, K, ZT * tpw, a_plane, 4, 4, afmt);
+  else rc = map_rows_k(&tmA, A16, K, Nn, ZT, a_plane, 128, afmt);
+  if (rc) return rc;
+  if ((rc = map_w(&tmBhi, Bhi, K, Ntot, G, ldb, G > 1 ? b_gstride : (long long)Ntot * ldb, bn, bfmt))) return rc;
+  if ((rc = map_w(&tmBlo, Blo, K, Ntot, G, ldb, G > 1 ? b_gstride : (long long)Ntot * ldb, bn, bfmt))) return rc;
+  SsArgs a;
+  memset(&a, 0, sizeof(a));
+  a.mode = SS_NODES; a.avar = avar; a.epi = SS_E_TB4; a.n_parts = Ntot / bn; a.m_tiles_g = Bw * T * tpw; a.G = G;
+  a.nkb = K / SS_BK; a.b_per_group = G > 1 ? 1 : 0; a.afmt = afmt; a.bfmt = bfmt;
+  a.T = T; a.Nn = Nn; a.Bw = Bw; a.tpw = tpw; a.rpt = wf_tile_rows(Nn);
+  a.C = C; a.c_cols = Ntot; a.bias = bias; a.bias2 = bias2; a.bias_gstride = bias_gstride; a.err = err;
+  if (drop != nullptr) a.drop = *drop;
+  return ss_launch(bn, tmA, tmA, tmBhi, tmBlo, tmA, tmA, a, st);
+}
+
+// Weight gradients of one LSTM layer from dG (TB8 bf16) and up to two 128-column operand halves (see wf_wg_kernel).
+// bsrc_h: base of the half's source; bvar 0: TB8 with bC channels per block, 1: row-major [2][G*Bw*T][Nn][bC].
+// Columns [0, w0) of the result go to dst0 (row pitch ld0), [w0, w0 + w1) to dst1; row sums to db1 / db2 (optional).
+int wf_ss_launch_wgrad(const void* dg16, long long dg_plane, int nh, const void* const* bsrc, const long long* bplane,
+                       const int* bvar, const int* bshift, const int* bcol0, const int* bC, int T, int Nn, int Bw, int G,
+                       float* part, size_t part_floats, float* dst0, int ld0, int w0, float* dst1, int ld1, int w1, float* db1,
+                       float* db2, long long gstride, int* err, cudaStream_t st) {
+  WF_REQUIRE(nh == 1 || nh == 2, "ss_wgrad: one or two operand halves");
+  const int tpw = wf_cdiv(Nn, 128), blocks_g = Bw * T * tpw;
+  const long long blocks = (long long)G * blocks_g, ZT = (long long)G * Bw * T;
+  CUtensorMap tmA, tmB[2];
+  int rc;
+  if ((rc = map_tb8(&tmA, dg16, 512, blocks, dg_plane, 1, 16, 1))) return rc;
+  for (int h = 0; h < nh; ++h) {
+    if (bvar[h] == 0) rc = map_tb8(&tmB[h], bsrc[h], bC[h], blocks, bplane[h], 1, 16, 1);
+    else rc = map_rows_mn(&tmB[h], bsrc[h], bC[h], Nn, ZT, bplane[h], 1);
+    if (rc) return rc;
+  }
+  if (nh == 1) tmB[1] = tmB[0];
+  // split-K over blocks: the split count that minimises (rounds of tiles over the SMs) x (blocks per tile)
+  const int ncol = nh * 128, sms = ss_sms();
+  int best = 1;
+  long long best_cost = -1;
+  for (int s = 1; s <= 40 && s <= blocks_g; ++s) {
+    if ((size_t)s * G * 512 * (ncol + 1) > part_floats) break;
+    const long long cost = (long long)wf_cdiv(4LL * G * s, sms) * wf_cdiv(blocks_g, s) * 64 + s;  // + s: prefer fewer partials on ties
+    if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = s; }
+  }
+  WF_REQUIRE((size_t)best * G * 512 * (ncol + 1) <= part_floats, "ss_wgrad: partial buffer too small");
+  WgArgs a;
+  memset(&a, 0, sizeof(a));
+  a.G = G; a.Bw = Bw; a.T = T; a.tpw = tpw; a.rpt = wf_tile_rows(Nn); a.Nn = Nn;
+  a.bps = wf_cdiv(blocks_g, best); a.splits = wf_cdiv(blocks_g, a.bps); a.nh = nh;
+  for (int h = 0; h < nh; ++h) { a.bvar[h] = bvar[h]; a.bshift[h] = bshift[h]; a.bcol0[h] = bvar[h] == 0 ? bcol0[h] / 8 : bcol0[h]; }
+  a.afmt = 1; a.bfmt = 1; a.nst = nh == 2 ? 4 : 6;   // kind::f16 takes ONE format for both operands: bf16 (dG's range)
+  a.part = part; a.bias_part = db1 != nullptr ? part + (size_t)a.splits * G * 512 * ncol : nullptr; a.err = err;
+  const int smem = a.nst * SS_A_STAGE * (1 + nh) + 1024 + 1024;
+  static bool configured = false;
+  if (!configured) {
+    if (cudaFuncSetAttribute(wf_wg_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * SS_A_STAGE * 3 + 2048) != cudaSuccess)
+      return wf_fail(WF_ECUDA, "wg kernel: cannot raise dynamic shared memory");
+    configured = true;
+  }
+  const int total = a.splits * G * 4;
+  wf_wg_kernel<<<total < sms ? total : sms, WG_THREADS, smem, st>>>(tmA, tmB[0], tmB[1], a);
+  WF_CHECK_LAUNCH("wg_kernel");
+  const int items = 512 * ncol / 4 + 512;
+  wf_wg_reduce_kernel<<<dim3(wf_cdiv(items, 256), G), 256, 0, st>>>(part, a.bias_part, a.splits, G, nh, dst0, ld0, w0, dst1, ld1, w1,
+                                                                   db1, db2, gstride);
+  WF_CHECK_LAUNCH("wg_reduce");
+  return WF_OK;
+}
+
+// ================================================================================= GCN layer on pre-split operands
+namespace {
+
+// fp32 windows [Z][R][C] (contiguous, or window z at element x_win_off[z] of a resident features tensor) -> fp16 hi / lo
+// planes [2][Z][R][C].  One thread per 4 channels.
+__global__ void wf_ss_split_windows_kernel(const float* __restrict__ X, const long long* __restrict__ x_win_off, int C, int R,
+                                           uint16_t* __restrict__ out, long long plane) {
+  const int z = blockIdx.y;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // float4 index inside the window
+  const long long n4 = (long long)R * C / 4;
+  if (i >= n4) return;
+  const float4 v = *reinterpret_cast<const float4*>(X + (x_win_off ? x_win_off[z] : (long long)z * R * C) + 4 * i);
+  uint2 hi, lo;
+  ss_split_f16(v.x, v.y, hi.x, lo.x);
+  ss_split_f16(v.z, v.w, hi.y, lo.y);
+  const long long o = (long long)z * R * C + 4 * i;
+  *reinterpret_cast<uint2*>(out + o) = hi;
+  *reinterpret_cast<uint2*>(out + plane + o) = lo;
+}
+
+// Side buffer S[z][rr][:] = sum_p val[p] * X[z][col[p]][:] for the leading agg_rows rows of every window (all rows whose
+// aggregation is not the unit self loop live there: the t = 0 slice for the reference's graphs).  Rows that
+// only have their self loop come out as copies.  X as fp32 windows (first layer) or fp16 hi/lo planes; S is fp16 hi/lo
+// [2][Z][agg_rows][C].  One warp per (row, window), 8 channels per lane and trip.
+__global__ void __launch_bounds__(256) wf_ss_agg_rows_kernel(const float* __restrict__ X32, const long long* __restrict__ x_win_off,
+                                                             const uint16_t* __restrict__ X16, long long x_plane, int C, int R,
+                                                             int Bw, int agg_rows, const int* __restrict__ rowptr,
+                                                             const int* __restrict__ col, const float* __restrict__ val,
+                                                             long long g_rowptr, long long g_csr, uint16_t* __restrict__ S,
+                                                             long long s_plane) {
+  const int z = blockIdx.y, g = z / Bw, rr = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (rr >= agg_rows || rr >= R) return;
+  const int* rp = rowptr + g * g_rowptr;
+  const int p0 = rp[rr], p1 = rp[rr + 1];
+  const long long xbase = X32 ? (x_win_off ? x_win_off[z] : (long long)z * R * C) : (long long)z * R * C;
+  for (int c8 = lane; c8 < (C >> 3); c8 += 32) {
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    for (int p = p0; p < p1; ++p) {
+      const float v = __ldg(val + g * g_csr + p);
+      const long long src = xbase + (long long)__ldg(col + g * g_csr + p) * C + 8 * c8;
+      float x[8];
+      if (X32) {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(X32 + src)), b = __ldg(reinterpret_cast<const float4*>(X32 + src + 4));
+        x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w; x[4] = b.x; x[5] = b.y; x[6] = b.z; x[7] = b.w;
+      } else {
+        const uint4 h = __ldg(reinterpret_cast<const uint4*>(X16 + src)), l = __ldg(reinterpret_cast<const uint4*>(X16 + x_plane + src));
+        const uint32_t hw[4] = {h.x, h.y, h.z, h.w}, lw[4] = {l.x, l.y, l.z, l.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 fh = __half22float2(*reinterpret_cast<const __half2*>(&hw[j]));
+          const float2 fl = __half22float2(*reinterpret_cast<const __half2*>(&lw[j]));
+          x[2 * j] = fh.x + fl.x; x[2 * j + 1] = fh.y + fl.y;
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] = fmaf(v, x[j], acc[j]);
+    }
+    uint4 hi, lo;
+    ss_split_f16(acc[0], acc[1], hi.x, lo.x); ss_split_f16(acc[2], acc[3], hi.y, lo.y);
+    ss_split_f16(acc[4], acc[5], hi.z, lo.z); ss_split_f16(acc[6], acc[7], hi.w, lo.w);
+    const long long o = ((long long)z * agg_rows + rr) * C + 8 * c8;
+    *reinterpret_cast<uint4*>(S + o) = hi;
+    *reinterpret_cast<uint4*>(S + s_plane + o) = lo;
+  }
+}
+
+}  // namespace
+
+// GCNConv + ReLU (+ train-mode dropout) on pre-split fp16 hi/lo activations (model.py:31-42, hybrid_model.py:65-75):
+// Y16 = split(dropout(relu((A_hat X) W^T + b))), Y16 / X16 as planes [2][G*Bw][R][C]; Yb16 (optional): the same values
+// as bf16 hi / lo planes (the LSTM's layer-0 weight gradient contracts them against bf16 dG).  The first layer passes the fp32
+// windows instead (X32 + x_win_off, or dense when x_win_off == NULL) and a scratch `xsplit16` [2][G*Bw][R][Cin] that
+// receives their split.  Rows whose aggregation is not the unit self loop must all lie in the leading agg_rows rows of a
+// window (a multiple of 128, or R rounded up); they are aggregated into `side16` [2][G*Bw][agg_rows][Cin] first and the
+// GEMM reads those row tiles from there.  Cin % 8 == 0, Cout % 128 == 0, W16 hi/lo = wf_split16(W, 0) shared by all groups.
+extern "C" int wf_gcn_layer_fwd_ss(const float* X32, const long long* x_win_off, const void* X16, void* xsplit16,
+                                   const void* W16_hi, const void* W16_lo, const float* bias, const int* rowptr,
+                                   const int* col, const float* val, long long rowptr_group_stride, long long csr_group_stride,
+                                   int agg_rows, void* side16, int R, int Cin, int Cout, int G, int Bw, int relu, void* Y16,
+                                   void* Yb16, float p_drop, const unsigned long long* rng, int site, int* err, void* stream) {
+  WF_REQUIRE(G > 0 && Bw > 0 && R > 0, "gcn_layer_fwd_ss: bad batch");
+  WF_REQUIRE(Cin % 8 == 0 && Cout % 128 == 0, "gcn_layer_fwd_ss: Cin=%d must be a multiple of 8, Cout=%d of 128", Cin, Cout);
+  WF_REQUIRE((X32 != nullptr) != (X16 != nullptr), "gcn_layer_fwd_ss: pass the input either as fp32 windows or as fp16 planes");
+  WF_REQUIRE(X32 == nullptr || xsplit16 != nullptr, "gcn_layer_fwd_ss: fp32 input needs the split scratch");
+  WF_REQUIRE(agg_rows >= 0 && agg_rows % 128 == 0 && (agg_rows == 0 || (rowptr != nullptr && side16 != nullptr)),
+             "gcn_layer_fwd_ss: agg_rows=%d must be a multiple of 128 and comes with the CSR and the side buffer", agg_rows);
+  WF_REQUIRE(p_drop >= 0.f && p_drop < 1.f && (p_drop == 0.f || rng != nullptr), "gcn_layer_fwd_ss: bad dropout arguments");
+  WF_REQUIRE((long long)128 * ((Cin + 31) / 32 * 32) * 4 <= SS_B_BYTES, "gcn_layer_fwd_ss: Cin=%d too wide for a resident weight slice", Cin);
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long Z = (long long)G * Bw, plane = Z * R * Cin;
+  const uint16_t* A16 = (const uint16_t*)X16;
+  if (X32 != nullptr) {
+    wf_ss_split_windows_kernel<<<dim3(wf_cdiv((long long)R * Cin / 4, 256), (unsigned)Z), 256, 0, st>>>(X32, x_win_off, Cin, R,
+                                                                                                      (uint16_t*)xsplit16, plane);
+    WF_CHECK_LAUNCH("ss_split_windows");
+    A16 = (const uint16_t*)xsplit16;
+  }
+  const int win_tiles = wf_cdiv(R, 128);
+  if (agg_rows > win_tiles * 128) agg_rows = win_tiles * 128;
+  const long long s_plane = Z * agg_rows * Cin;
+  if (agg_rows > 0) {
+    wf_ss_agg_rows_kernel<<<dim3(wf_cdiv(agg_rows, 8), (unsigned)Z), 256, 0, st>>>(X32, x_win_off, X32 ? nullptr : A16, plane, Cin, R, Bw,
+                                                                                  agg_rows, rowptr, col, val, rowptr_group_stride,
+                                                                                  csr_group_stride, (uint16_t*)side16, s_plane);
+    WF_CHECK_LAUNCH("ss_agg_rows");
+  }
+  CUtensorMap tmA, tmA2, tmBhi, tmBlo, tmOut, tmOut2;
+  int rc;
+  if ((rc = map_rows_k(&tmA, A16, Cin, R, Z, plane, 128, 0))) return rc;
+  if (agg_rows > 0) { if ((rc = map_rows_k(&tmA2, side16, Cin, agg_rows, Z, s_plane, 128, 0))) return rc; }
+  else tmA2 = tmA;
+  if ((rc = map_w(&tmBhi, W16_hi, Cin, Cout, 1, Cin, (long long)Cout * Cin, 128, 0))) return rc;
+  if ((rc = map_w(&tmBlo, W16_lo, Cin, Cout, 1, Cin, (long long)Cout * Cin, 128, 0))) return rc;
+  if ((rc = map_rows_mn(&tmOut, Y16, Cout, R, Z, Z * R * Cout, 0))) return rc;
+  if (Yb16 != nullptr) { if ((rc = map_rows_mn(&tmOut2, Yb16, Cout, R, Z, Z * R * Cout, 1))) return rc; }
+  else tmOut2 = tmOut;
+  SsArgs a;
+  memset(&a, 0, sizeof(a));
+  a.mode = SS_ROWS; a.avar = SS_A_KS; a.epi = SS_E_HL; a.n_parts = Cout / 128; a.m_tiles_g = Bw * win_tiles; a.G = G;
+  a.nkb = (Cin + SS_BK - 1) / SS_BK; a.b_per_group = 0; a.afmt = 0; a.bfmt = 0;
+  a.R = R; a.Bw = Bw; a.win_tiles = win_tiles; a.agg_tiles = agg_rows / 128;
+  a.c_cols = Cout; a.bias = bias; a.relu = relu; a.err = err;
+  a.drop = wf_drop_cfg(p_drop, rng, WF_SITE_GCN + site);
+  a.range_limit = 32768.0f;
+  a.out2 = Yb16 != nullptr ? 1 : 0;
+  return ss_launch(128, tmA, tmA2, tmBhi, tmBlo, tmOut, tmOut2, a, st);
+}
+
+// hi + lo planes -> fp32 (tests, and the drop-in module API, whose tensors are fp32): out[i] = float(hi[i]) + float(lo[i])
+static __global__ void wf_ss_join_kernel(const uint16_t* __restrict__ hi, const uint16_t* __restrict__ lo, long long n, int fmt,
+                                         float* __restrict__ out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float a, b;
+  if (fmt == 0) { a = __half2float(__ushort_as_half(hi[i])); b = __half2float(__ushort_as_half(lo[i])); }
+  else { a = __uint_as_float((uint32_t)hi[i] << 16); b = __uint_as_float((uint32_t)lo[i] << 16); }
+  out[i] = a + b;
+}
+extern "C" int wf_join16(const void* hi, const void* lo, long long n, int fmt, float* out, void* stream) {
+  WF_REQUIRE(n > 0 && (fmt == 0 || fmt == 1), "join16: bad arguments");
+  wf_ss_join_kernel<<<wf_cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>((const uint16_t*)hi, (const uint16_t*)lo, n, fmt, out);
+  WF_CHECK_LAUNCH("join16");
+  return WF_OK;
+}
+
+// ---- test entry points: the two kernels on operands given as plain 16-bit planes, so that every operand layout
+// (K-major SWIZZLE_64B / TB8 K-major / TB8 MN-major / row-major MN-major SWIZZLE_128B, fp16 and bf16) can be checked
+// against a float64 product in isolation (tests/test_gpu_ss.py).
+// C (TB4 fp32 [blocks][Ntot/4][128][4]) = A W^T: avar 0: A16 row-major planes [2][G*Bw*T][Nn][K]; 1: TB8 planes.
+extern "C" int wf_ss_nodes_gemm(int bn, int avar, const void* A16, long long a_plane, int K, int afmt, const void* W16_hi,
+                                const void* W16_lo, long long w_group_stride, int Ntot, int bfmt, const float* bias,
+                                const float* bias2, long long bias_group_stride, float* C, int T, int Nn, int Bw, int G,
+                                int* err, void* stream) {
+  return wf_ss_launch_nodes(bn, avar, A16, a_plane, K, afmt, W16_hi, W16_lo, K, w_group_stride, Ntot, bfmt, bias, bias2,
+                            bias_group_stride, C, T, Nn, Bw, G, nullptr, err, (cudaStream_t)stream);
+}
+// dst0 [G][512][w0] (+ dst1 [G][512][w1], db [G][512]) = dG^T [B0 | B1] over all blocks: dg16 TB8 bf16 planes (512 channels);
+// half h: bvar 0 TB8 fp16 planes with bC channels (bcol0: first channel), 1 row-major fp16 planes [2][G*Bw*T][Nn][bC];
+// bshift 1: the block of the previous step.  part: scratch of part_floats floats.
+extern "C" int wf_ss_wgrad(const void* dg16, long long dg_plane, int nh, const void* b0, long long b0_plane, int b0var,
+                           int b0shift, int b0col0, int b0C, const void* b1, long long b1_plane, int b1var, int b1shift,
+                           int b1col0, int b1C, int T, int Nn, int Bw, int G, float* part, long long part_floats, float* dst0,
+                           int ld0, int w0, float* dst1, int ld1, int w1, float* db, long long gstride, int* err,
+                           void* stream) {
+  const void* src[2] = {b0, b1};
+  const long long plane[2] = {b0_plane, b1_plane};
+  const int var[2] = {b0var, b1var}, shift[2] = {b0shift, b1shift}, col0[2] = {b0col0, b1col0}, ch[2] = {b0C, b1C};
+  return wf_ss_launch_wgrad(dg16, dg_plane, nh, src, plane, var, shift, col0, ch, T, Nn, Bw, G, part, (size_t)part_floats, dst0,
+                            ld0, w0, dst1, ld1, w1, db, nullptr, gstride, err, (cudaStream_t)stream);
+}

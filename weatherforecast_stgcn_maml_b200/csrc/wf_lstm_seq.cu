@@ -37,12 +37,14 @@
 
 using namespace wftc;
 
-int wf_launch_g16_nodes(int fmt, const float* A, int a_tb4, int K, const void* Whi, const void* Wlo, int ldb, long long b_gstride,
-                        int N, const float* bias, const float* bias2, long long bias_gstride, float* C, int T, int Nn, int Bw,
-                        int G, int* err, cudaStream_t st, const DropCfg* drop);
-int wf_launch_g16_wgrad(const float* AT, int M, const void* BT_hi, const void* BT_lo, int N, int R, int Bw, int G, int a_k0,
-                        int b_k0, int klen, float* dW, long long dw_gstride, int* err, cudaStream_t st, float* partials,
-                        size_t partial_floats, float* rowsum1, float* rowsum2, long long rowsum_gstride);
+int wf_ss_launch_nodes(int bn, int avar, const void* A16, long long a_plane, int K, int afmt, const void* Bhi, const void* Blo,
+                       int ldb, long long b_gstride, int Ntot, int bfmt, const float* bias, const float* bias2,
+                       long long bias_gstride, float* C, int T, int Nn, int Bw, int G, const DropCfg* drop, int* err,
+                       cudaStream_t st);
+int wf_ss_launch_wgrad(const void* dg16, long long dg_plane, int nh, const void* const* bsrc, const long long* bplane,
+                       const int* bvar, const int* bshift, const int* bcol0, const int* bC, int T, int Nn, int Bw, int G,
+                       float* part, size_t part_floats, float* dst0, int ld0, int w0, float* dst1, int ld1, int w1, float* db1,
+                       float* db2, long long gstride, int* err, cudaStream_t st);
 int wf_launch_split16(const float* src, long long src_gstride, void* hi, void* lo, long long dst_gstride, long long n, int G,
                       int fmt, cudaStream_t st);
 int wf_launch_transpose_split16(const float* in, long long in_gstride, int rows, int cols, void* out_hi, void* out_lo,
@@ -59,17 +61,19 @@ constexpr int SEQ_SMEM = 196608 + 1024;
 struct SeqArgs {
   float* XG;          // TB4, 4L channels. fwd: input projection in, activated gates out; bwd: gates in, dG out
   float* Cst;         // TB4, L channels: cell state
-  float* H;           // fwd out: row-major [Z*R, L], or TB4 (L channels) when h_tb4
-  int h_tb4;
-  __nv_bfloat16* HT;  // fwd out (optional): transposed bf16 hi / lo copies [(z)][L][RT]
-  __nv_bfloat16* HT_lo;
-  __nv_bfloat16* HTm;  // fwd out (dropout on): transposed copies of the MASKED h, the next layer's input (dW_ih of layer l+1)
-  __nv_bfloat16* HTm_lo;
-  DropCfg drop;        // fwd: inter-layer dropout on this layer's output (hybrid_model.py:47); rng == nullptr: off
-  float* DGT;         // bwd out: transposed dG [(z)][4L][RT]
+  // fwd out, all hi / lo plane pairs in the TB8 layout [2][block][L/8][128 rows][8] (optional each):
+  uint16_t* H16;      //   fp16: what the NEXT layer's input projection reads (K-major operand) -- masked when dropout is on
+  uint16_t* HB16;     //   bf16: the plain h, for dW_hh (and dW_ih of the next layer when dropout is off): MN-major operand
+  uint16_t* HB16m;    //   bf16 (dropout on): the masked h, for dW_ih of the next layer
+                      //   (tcgen05 kind::f16 wants both operands in ONE format, and dG needs bf16's exponent range)
+  long long h16_plane;  // elements between the hi and the lo plane
+  float* Hlast;       // fwd out (top layer): h of the last step, row-major [Z*Nn, L] (what the head reads)
+  DropCfg drop;       // fwd: inter-layer dropout on this layer's output (hybrid_model.py:47); rng == nullptr: off
+  uint16_t* DG16;     // bwd out: dG as bf16 hi / lo planes, TB8 [2][block][4L/8][128 rows][8]
+  long long dg16_plane;
   const float* ext;   // bwd: dL/dh from above -- TB4 (L channels), or row-major dlast [Z*Nn, L] if ext_last_only
   int ext_last_only;
-  int T, Nn, Bw, tpw, rpt, Np, RT;  // rpt: nodes per node tile (wf_tile_rows)
+  int T, Nn, Bw, tpw, rpt;  // rpt: nodes per node tile (wf_tile_rows)
   int slab0, slab_g;  // weight map z coordinate = slab0 + g * slab_g (+ rank in the backward kernel)
   int* err;
 };
@@ -318,7 +322,6 @@ wf_lstm_seq_fwd16_kernel(const __grid_constant__ CUtensorMap tmWhi, const __grid
     mdone = !(warp < 4 && t + 1 < T);
     const long long blk = ((long long)z * T + t) * a.tpw + nt;
     const long long hrow = ((long long)z * R + (long long)t * a.Nn + node) * L + u0;
-    const long long tcol = (long long)t * a.Np + node;
     // ------------------------------------------------------------ phase A: cell mathematics, h[t] out
     uint32_t acc[4][4];
     auto issue_acc = [&](int c) {
@@ -425,8 +428,11 @@ wf_lstm_seq_fwd16_kernel(const __grid_constant__ CUtensorMap tmWhi, const __grid
           xg4[xg_index(t, c, gate)] = make_float4(__uint_as_float(gt[gate][0]), __uint_as_float(gt[gate][1]),
                                                   __uint_as_float(gt[gate][2]), __uint_as_float(gt[gate][3]));
         c4[(blk * 32 + (u0 >> 2) + 4 * c) * 128 + r] = make_float4(cst[4 * c], cst[4 * c + 1], cst[4 * c + 2], cst[4 * c + 3]);
-        // Inter-layer dropout (hybrid_model.py:47): the NEXT layer reads mask * h / (1 - p); the recurrence of this layer
-        // (the A operand handed over in phase A) and dW_hh (the unmasked transposed copy below) keep the plain h.
+        // h[t] leaves as 16-bit hi/lo planes in the TB8 layout (8 bytes per plane here; the warp of the neighbouring unit
+        // group fills the other half of each 16-byte chunk).  Inter-layer dropout (hybrid_model.py:47): the NEXT layer
+        // reads mask * h / (1 - p); the recurrence of this layer (the operand handed over in phase A) and dW_hh keep h.
+        const int unit = u0 + 16 * c;
+        const long long h16o = ((blk * (L / 8) + (unit >> 3)) * 128 + r) * 8 + (unit & 7);
         float hm[4] = {hh[0], hh[1], hh[2], hh[3]};
         if (DROP) {
           float m[4];
@@ -434,34 +440,29 @@ wf_lstm_seq_fwd16_kernel(const __grid_constant__ CUtensorMap tmWhi, const __grid
 #pragma unroll
           for (int j = 0; j < 4; ++j) hm[j] *= m[j];
         }
-        if (a.h_tb4) reinterpret_cast<float4*>(a.H)[(blk * 32 + (u0 >> 2) + 4 * c) * 128 + r] = make_float4(hm[0], hm[1], hm[2], hm[3]);
-        if (!a.h_tb4) *reinterpret_cast<float4*>(a.H + hrow + 16 * c) = make_float4(hh[0], hh[1], hh[2], hh[3]);
-        if (DROP && a.HTm != nullptr) {
-          __nv_bfloat16* ht = a.HTm + ((long long)z * L + u0 + 16 * c) * a.RT + tcol;
-          __nv_bfloat16* htl = a.HTm_lo + ((long long)z * L + u0 + 16 * c) * a.RT + tcol;
-#pragma unroll
-          for (int j = 0; j < 4; j += 2) {
-            float ra, rb, d0, d1;
-            const uint32_t uh = pack_bf16(hm[j], hm[j + 1], ra, rb), ul = pack_bf16(ra, rb, d0, d1);
-            reinterpret_cast<uint16_t*>(ht)[(long long)j * a.RT] = (uint16_t)uh;
-            reinterpret_cast<uint16_t*>(ht)[(long long)(j + 1) * a.RT] = (uint16_t)(uh >> 16);
-            reinterpret_cast<uint16_t*>(htl)[(long long)j * a.RT] = (uint16_t)ul;
-            reinterpret_cast<uint16_t*>(htl)[(long long)(j + 1) * a.RT] = (uint16_t)(ul >> 16);
-          }
+        if (a.H16 != nullptr) {
+          float ra, rb, rc, rd, d0, d1;
+          const uint32_t h0 = pack_f16(hm[0], hm[1], ra, rb), h1 = pack_f16(hm[2], hm[3], rc, rd);
+          const uint32_t l0 = pack_f16(ra, rb, d0, d1), l1 = pack_f16(rc, rd, d0, d1);
+          *reinterpret_cast<uint2*>(a.H16 + h16o) = make_uint2(h0, h1);
+          *reinterpret_cast<uint2*>(a.H16 + a.h16_plane + h16o) = make_uint2(l0, l1);
         }
-        if (a.HT != nullptr) {
-          __nv_bfloat16* ht = a.HT + ((long long)z * L + u0 + 16 * c) * a.RT + tcol;
-          __nv_bfloat16* htl = a.HT_lo + ((long long)z * L + u0 + 16 * c) * a.RT + tcol;
-#pragma unroll
-          for (int j = 0; j < 4; j += 2) {
-            float ra, rb, d0, d1;
-            const uint32_t uh = pack_bf16(hh[j], hh[j + 1], ra, rb), ul = pack_bf16(ra, rb, d0, d1);
-            reinterpret_cast<uint16_t*>(ht)[(long long)j * a.RT] = (uint16_t)uh;
-            reinterpret_cast<uint16_t*>(ht)[(long long)(j + 1) * a.RT] = (uint16_t)(uh >> 16);
-            reinterpret_cast<uint16_t*>(htl)[(long long)j * a.RT] = (uint16_t)ul;
-            reinterpret_cast<uint16_t*>(htl)[(long long)(j + 1) * a.RT] = (uint16_t)(ul >> 16);
-          }
+        if (a.HB16 != nullptr) {
+          float ra, rb, rc, rd, d0, d1;
+          const uint32_t h0 = pack_bf16(hh[0], hh[1], ra, rb), h1 = pack_bf16(hh[2], hh[3], rc, rd);
+          const uint32_t l0 = pack_bf16(ra, rb, d0, d1), l1 = pack_bf16(rc, rd, d0, d1);
+          *reinterpret_cast<uint2*>(a.HB16 + h16o) = make_uint2(h0, h1);
+          *reinterpret_cast<uint2*>(a.HB16 + a.h16_plane + h16o) = make_uint2(l0, l1);
         }
+        if (DROP && a.HB16m != nullptr) {
+          float ra, rb, rc, rd, d0, d1;
+          const uint32_t h0 = pack_bf16(hm[0], hm[1], ra, rb), h1 = pack_bf16(hm[2], hm[3], rc, rd);
+          const uint32_t l0 = pack_bf16(ra, rb, d0, d1), l1 = pack_bf16(rc, rd, d0, d1);
+          *reinterpret_cast<uint2*>(a.HB16m + h16o) = make_uint2(h0, h1);
+          *reinterpret_cast<uint2*>(a.HB16m + a.h16_plane + h16o) = make_uint2(l0, l1);
+        }
+        if (a.Hlast != nullptr && t == T - 1)
+          *reinterpret_cast<float4*>(a.Hlast + ((long long)z * a.Nn + node) * L + unit) = make_float4(hh[0], hh[1], hh[2], hh[3]);
       }
     }
     WF_TR(5);
@@ -519,7 +520,7 @@ wf_lstm_seq_bwd_kernel(const __grid_constant__ CUtensorMap tmWhi, const __grid_c
     const bool valid = r < a.rpt && node < a.Nn;
     const float vm = valid ? 1.0f : 0.0f;
     const uint32_t tlane = tbase + ((uint32_t)(q * 32) << 16);
-    float4* const xg4 = reinterpret_cast<float4*>(a.XG);
+    const float4* const xg4 = reinterpret_cast<const float4*>(a.XG);
     const float4* const c4 = reinterpret_cast<const float4*>(a.Cst);
     const float4* const e4 = reinterpret_cast<const float4*>(a.ext);
     const uint32_t xr_remote0 = mapa_u32(smem_u32(&x_ready[0]), peer), xr_remote1 = mapa_u32(smem_u32(&x_ready[1]), peer);
@@ -626,7 +627,6 @@ wf_lstm_seq_bwd_kernel(const __grid_constant__ CUtensorMap tmWhi, const __grid_c
         WF_TRS(2);
       }
       const long long blk = blk_of(t);
-      const long long tcol = (long long)t * a.Np + node;
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
         // prefetch the next chunk (possibly of the next step) while this one is processed
@@ -698,10 +698,11 @@ wf_lstm_seq_bwd_kernel(const __grid_constant__ CUtensorMap tmWhi, const __grid_c
         if (warp == 0) issue_mma(s + 1, 0);  // the first half of the MMA before warp 0's own stores
         WF_TRS(8);  // warp 0 feeds the tensor core first, then stores like everybody else
       }
-      // ---- deferred stores of step t (under MMA[s+1]): dG in place (TB4) and transposed fp32 for the weight gradients
+      // ---- deferred stores of step t (under MMA[s+1]): dG leaves exactly as it sits in the TMEM operand -- bf16 hi / lo
+      // planes, TB8 layout: per (gate, 8 units) one 16-byte chunk per plane and row, 512 contiguous bytes per warp store,
+      // no arithmetic.  dX and the weight gradients read these planes directly (K-major and MN-major views of the same bytes).
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
-        float v[4][8];
         __syncwarp();
 #pragma unroll
         for (int gate = 0; gate < 4; ++gate) {
@@ -710,25 +711,10 @@ wf_lstm_seq_bwd_kernel(const __grid_constant__ CUtensorMap tmWhi, const __grid_c
           tmem_ld4(tlane + A_HI + col, hi);
           tmem_ld4(tlane + A_LO + col, lo);
           tmem_wait_ld();
-#pragma unroll
-          for (int i2 = 0; i2 < 4; ++i2) {
-            v[gate][2 * i2] = __uint_as_float(hi[i2] << 16) + __uint_as_float(lo[i2] << 16);
-            v[gate][2 * i2 + 1] = __uint_as_float(hi[i2] & 0xFFFF0000u) + __uint_as_float(lo[i2] & 0xFFFF0000u);
-          }
-        }
-        const int uq = (u0 + 8 * c) >> 2;
-        if (valid) {
-#pragma unroll
-          for (int gate = 0; gate < 4; ++gate)
-#pragma unroll
-            for (int hsel = 0; hsel < 2; ++hsel)
-              xg4[(blk * 128 + gate * 32 + uq + hsel) * 128 + r] =
-                  make_float4(v[gate][4 * hsel], v[gate][4 * hsel + 1], v[gate][4 * hsel + 2], v[gate][4 * hsel + 3]);
-#pragma unroll
-          for (int jj = 0; jj < 8; ++jj) {
-            float* base = a.DGT + ((long long)z * 4 * L + u0 + 8 * c + jj) * a.RT + tcol;
-#pragma unroll
-            for (int gate = 0; gate < 4; ++gate) base[(long long)gate * L * a.RT] = v[gate][jj];
+          if (valid) {
+            const long long o = ((blk * (4 * L / 8) + ((gate * L + u0 + 8 * c) >> 3)) * 128 + r) * 8;
+            *reinterpret_cast<uint4*>(a.DG16 + o) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+            *reinterpret_cast<uint4*>(a.DG16 + a.dg16_plane + o) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
           }
         }
         if (c == 1 && warp == 4 && s + 1 < T) issue_mma(s + 1, 1);  // the second half, between warp 4's store halves
@@ -849,21 +835,30 @@ extern "C" int wf_prep_weights_seq(const float* params, long long params_group_s
   return WF_OK;
 }
 
+// 16-bit elements of ONE plane of a TB8 buffer with `channels` values per (window, step, node): the hi and the lo plane
+// of an activation are two such planes back to back.
+extern "C" long long wf_tb8_elems(int channels, int T, int N, long long windows) {
+  return windows * T * wf_cdiv(N, 128) * (long long)channels * 128;
+}
+
 // nn.LSTM forward (hybrid_model.py:42-49, 93-105): per layer one input-projection GEMM + one persistent launch.
-//   x [G*Bw*T*N, F] row-major; params: flat fp32 weights (biases); p16 / f16 operands from wf_prep_weights_seq;
-//   gates TB4 [layers][4L ch], c TB4 [layers][L ch]; h [layers][wf_tb4_elems(L, ..)]: the top layer row-major
-//   [G*Bw*T*N, L] (read by the head), the layers below TB4 (read only by the next layer's projection);
-//   hT_hi / hT_lo optional bf16 transposed copies [layers][(G*Bw)][L][RT16] (training).
-extern "C" int wf_lstm_fwd_seq(const float* x, const float* params, const void* p16_hi, const void* p16_lo,
+//   x16: layer-0 input, fp16 hi / lo planes row-major [2][G*Bw*T*N][F] (wf_gcn_layer_fwd_ss / wf_split16);
+//   params: flat fp32 weights (biases); p16 / f16 operands from wf_prep_weights_seq;
+//   gates TB4 [layers][4L ch], c TB4 [layers][L ch];
+//   h16 [layers-1][2][wf_tb8_elems(L, ..)]: fp16 hi / lo planes of what the NEXT layer reads (masked when p_drop > 0);
+//   hb16 [layers][2][..] (optional: training): bf16 hi / lo planes of the plain h, the weight gradients' operand;
+//   hb16m [layers-1][2][..] (p_drop > 0 and training): bf16 planes of the masked h (dW_ih of the next layer).
+//   All TB8 and ZERO-INITIALISED by the caller: the padding rows of a node tile are never written and must read as zero
+//   where rows are contracted.  hlast [G*Bw*N, L] fp32: the top layer's last step (what the head reads).
+extern "C" int wf_lstm_fwd_seq(const void* x16, const float* params, const void* p16_hi, const void* p16_lo,
                                long long params_group_stride, const void* f16_hi, const void* f16_lo, int layers, int F, int L,
-                               int O, int T, int N, int G, int Bw, float* gates, float* h, float* c, void* hT_hi, void* hT_lo,
-                               float p_drop, const unsigned long long* rng, void* hTm_hi, void* hTm_lo, int* err,
-                               void* stream) {
-  WF_REQUIRE(layers >= 1 && layers <= 8 && L == 128 && F % 64 == 0, "lstm_fwd_seq: needs L == 128, F %% 64 == 0");
+                               int O, int T, int N, int G, int Bw, float* gates, void* h16, float* c, float* hlast, void* hb16,
+                               float p_drop, const unsigned long long* rng, void* hb16m, int* err, void* stream) {
+  WF_REQUIRE(layers >= 1 && layers <= 8 && L == 128 && F % 32 == 0, "lstm_fwd_seq: needs L == 128, F %% 32 == 0");
   WF_REQUIRE(T > 0 && N > 0 && G > 0 && Bw > 0, "lstm_fwd_seq: empty batch");
   WF_REQUIRE(p_drop >= 0.f && p_drop < 1.f, "lstm_fwd_seq: p_drop=%f outside [0, 1)", (double)p_drop);
-  WF_REQUIRE(p_drop == 0.f || rng != nullptr, "lstm_fwd_seq: dropout needs the rng state");
-  WF_REQUIRE(p_drop == 0.f || hT_hi == nullptr || hTm_hi != nullptr, "lstm_fwd_seq: training with dropout needs hTm");
+  WF_REQUIRE(p_drop == 0.f || layers == 1 || rng != nullptr, "lstm_fwd_seq: dropout needs the rng state");
+  WF_REQUIRE(p_drop == 0.f || layers == 1 || hb16 == nullptr || hb16m != nullptr, "lstm_fwd_seq: training with dropout needs hb16m");
   cudaStream_t st = (cudaStream_t)stream;
   static bool configured = false;
   if (!configured) {
@@ -874,30 +869,38 @@ extern "C" int wf_lstm_fwd_seq(const float* x, const float* params, const void* 
   }
   const LstmLayout P = lstm_layout(layers, F, L, O);
   const long long Z = (long long)G * Bw;
-  const int tpw = wf_cdiv(N, 128), Np = wf_np(N), RT = T * Np;
+  const int tpw = wf_cdiv(N, 128);
   const long long g_elems = wf_tb4_elems(4 * L, T, N, Z), c_elems = wf_tb4_elems(L, T, N, Z);
-  const long long tsz = Z * L * RT;
+  const long long hp = wf_tb8_elems(L, T, N, Z);   // one plane of h
   CUtensorMap tmhi, tmlo;
   int rc = seq_maps_fwd(&tmhi, &tmlo, f16_hi, f16_lo, L, G * layers);
   if (rc) return rc;
   for (int l = 0; l < layers; ++l) {
     const int kin = l == 0 ? F : L;
     float* XG = gates + l * g_elems;
-    const float* Xl = l == 0 ? x : h + (long long)(l - 1) * c_elems;
-    rc = wf_launch_g16_nodes(0, Xl, l == 0 ? 0 : 1, kin, (const uint16_t*)p16_hi + P.w_ih[l], (const uint16_t*)p16_lo + P.w_ih[l], kin,
-                             stride16(P.total), 4 * L, params + P.b_ih[l], params + P.b_hh[l], params_group_stride, XG, T, N,
-                             Bw, G, err, st, nullptr);
+    // input projection x W_ih^T + b_ih + b_hh -> the gate pre-activations' TB4 block (4L channels)
+    if (l == 0)
+      rc = wf_ss_launch_nodes(kin <= 128 ? 256 : 128, 0, x16, Z * T * N * (long long)F, kin, 0, (const uint16_t*)p16_hi + P.w_ih[l],
+                              (const uint16_t*)p16_lo + P.w_ih[l], kin, stride16(P.total), 4 * L, 0, params + P.b_ih[l],
+                              params + P.b_hh[l], params_group_stride, XG, T, N, Bw, G, nullptr, err, st);
+    else
+      rc = wf_ss_launch_nodes(256, 1, (const uint16_t*)h16 + (long long)(l - 1) * 2 * hp, hp, kin, 0,
+                              (const uint16_t*)p16_hi + P.w_ih[l], (const uint16_t*)p16_lo + P.w_ih[l], kin, stride16(P.total),
+                              4 * L, 0, params + P.b_ih[l], params + P.b_hh[l], params_group_stride, XG, T, N, Bw, G, nullptr,
+                              err, st);
     if (rc) return rc;
     SeqArgs a;
     memset(&a, 0, sizeof(a));
-    a.XG = XG; a.Cst = c + l * c_elems; a.H = h + (long long)l * c_elems; a.h_tb4 = l + 1 < layers ? 1 : 0;
-    a.HT = hT_hi ? (__nv_bfloat16*)hT_hi + l * tsz : nullptr; a.HT_lo = hT_hi ? (__nv_bfloat16*)hT_lo + l * tsz : nullptr;
-    a.T = T; a.Nn = N; a.Bw = Bw; a.tpw = tpw; a.rpt = wf_tile_rows(N); a.Np = Np; a.RT = RT;
+    a.XG = XG; a.Cst = c + l * c_elems; a.h16_plane = hp;
+    a.H16 = l + 1 < layers ? (uint16_t*)h16 + (long long)l * 2 * hp : nullptr;
+    a.HB16 = hb16 != nullptr ? (uint16_t*)hb16 + (long long)l * 2 * hp : nullptr;
+    a.Hlast = l + 1 == layers ? hlast : nullptr;
+    a.T = T; a.Nn = N; a.Bw = Bw; a.tpw = tpw; a.rpt = wf_tile_rows(N);
     a.slab0 = l; a.slab_g = layers; a.err = err;
     const bool drop = p_drop > 0.f && l + 1 < layers;  // nn.LSTM: dropout on the outputs of every layer but the last
     if (drop) {
       a.drop = wf_drop_cfg(p_drop, rng, WF_SITE_LSTM + l);
-      a.HTm = hTm_hi ? (__nv_bfloat16*)hTm_hi + l * tsz : nullptr; a.HTm_lo = hTm_hi ? (__nv_bfloat16*)hTm_lo + l * tsz : nullptr;
+      a.HB16m = hb16m != nullptr ? (uint16_t*)hb16m + (long long)l * 2 * hp : nullptr;
       wf_lstm_seq_fwd16_kernel<true><<<dim3((unsigned)(2 * Z * tpw)), 512, SEQ_SMEM, st>>>(tmhi, tmlo, a);
     } else {
       wf_lstm_seq_fwd16_kernel<false><<<dim3((unsigned)(2 * Z * tpw)), 512, SEQ_SMEM, st>>>(tmhi, tmlo, a);
@@ -908,75 +911,91 @@ extern "C" int wf_lstm_fwd_seq(const float* x, const float* params, const void* 
 }
 
 // workspace = dh between layers (TB4, L channels) + split-K partials of the weight gradients
-static size_t seq_partial_floats(int F, int L, int G) { return (size_t)8 * G * 4 * L * (F > L ? F : L) + (size_t)16 * G * 4 * L; }
+static size_t seq_partial_floats(int F, int L, int G) { return (size_t)(8 * G > 40 ? 8 * G : 40) * 4 * L * 257; }
 extern "C" size_t wf_lstm_bwd_seq_workspace_bytes(int layers, int F, int L, int T, int N, int G, int Bw) {
   (void)layers;
   return sizeof(float) * ((size_t)wf_tb4_elems(L, T, N, (long long)G * Bw) + seq_partial_floats(F, L, G)) + 256;
 }
 
-// BPTT (train_hybrid_maml_v5.py:134,169) with one persistent launch per layer.  gates / c from wf_lstm_fwd_seq
-// (gates are overwritten by dG); xT_hi / xT_lo: bf16 transposed layer-0 input [(G*Bw)][F][RT16]; hT_hi / hT_lo from
-// wf_lstm_fwd_seq; dgT: fp32 scratch [(G*Bw)][4L][RT16] with zero padding columns; pT16 / b16 operands from
-// wf_prep_weights_seq; dlast [G*Bw*N, L].
-extern "C" int wf_lstm_bwd_seq(const void* xT_hi, const void* xT_lo, const void* pT16_hi, const void* pT16_lo,
-                               const void* b16_hi, const void* b16_lo, int layers, int F, int L, int O, int T, int N, int G,
-                               int Bw, float* gates, const float* c, const void* hT_hi, const void* hT_lo, float* dgT,
-                               const float* dlast, float* grads, long long grads_group_stride, float p_drop,
-                               const unsigned long long* rng, const void* hTm_hi, const void* hTm_lo, void* workspace,
+// BPTT (train_hybrid_maml_v5.py:134,169) with one persistent launch per layer.  gates / c / hb16 (/ hb16m) from
+// wf_lstm_fwd_seq; xb16: the layer-0 input as BF16 hi / lo planes row-major [2][G*Bw*T*N][F]; dg16: scratch
+// [2][wf_tb8_elems(4L, ..)] for one layer's dG (bf16 hi / lo, ZERO-INITIALISED once by the caller: padding rows stay zero);
+// pT16 / b16 operands from wf_prep_weights_seq; dlast [G*Bw*N, L].
+extern "C" int wf_lstm_bwd_seq(const void* xb16, const void* pT16_hi, const void* pT16_lo, const void* b16_hi, const void* b16_lo,
+                               int layers, int F, int L, int O, int T, int N, int G, int Bw, const float* gates, const float* c,
+                               const void* hb16, void* dg16, const float* dlast, float* grads, long long grads_group_stride,
+                               float p_drop, const unsigned long long* rng, const void* hb16m, void* workspace,
                                size_t workspace_bytes, int* err, void* stream) {
-  WF_REQUIRE(layers >= 1 && layers <= 8 && L == 128 && F % 128 == 0, "lstm_bwd_seq: needs L == 128 and F %% 128 == 0");
+  WF_REQUIRE(layers >= 1 && layers <= 8 && L == 128 && F % 128 == 0 && F <= 256, "lstm_bwd_seq: needs L == 128 and F in {128, 256}");
   WF_REQUIRE(p_drop >= 0.f && p_drop < 1.f, "lstm_bwd_seq: p_drop=%f outside [0, 1)", (double)p_drop);
-  WF_REQUIRE(p_drop == 0.f || (rng != nullptr && hTm_hi != nullptr && hTm_lo != nullptr), "lstm_bwd_seq: dropout needs rng and hTm");
-  const bool drop = p_drop > 0.f;
-  const uint16_t *hTmh = (const uint16_t*)hTm_hi, *hTml = (const uint16_t*)hTm_lo;
+  WF_REQUIRE(p_drop == 0.f || layers == 1 || (rng != nullptr && hb16m != nullptr), "lstm_bwd_seq: dropout needs rng and hb16m");
+  WF_REQUIRE(hb16 != nullptr && xb16 != nullptr && dg16 != nullptr, "lstm_bwd_seq: missing operand planes");
   if (workspace_bytes < wf_lstm_bwd_seq_workspace_bytes(layers, F, L, T, N, G, Bw))
     return wf_fail(WF_EWORKSPACE, "lstm_bwd_seq: workspace too small");
   cudaStream_t st = (cudaStream_t)stream;
   static bool configured = false;
   if (!configured) { int rc = seq_configure(wf_lstm_seq_bwd_kernel); if (rc) return rc; configured = true; }
+  const bool drop = p_drop > 0.f && layers > 1;
   const LstmLayout P = lstm_layout(layers, F, L, O);
   const long long Z = (long long)G * Bw;
-  const int tpw = wf_cdiv(N, 128), Np = wf_np(N), RT = T * Np;
+  const int tpw = wf_cdiv(N, 128);
   const long long g_elems = wf_tb4_elems(4 * L, T, N, Z), c_elems = wf_tb4_elems(L, T, N, Z);
-  const long long tsz = Z * L * RT;
+  const long long hp = wf_tb8_elems(L, T, N, Z), dgp = wf_tb8_elems(4 * L, T, N, Z);
   float* DX = (float*)workspace;
   float* partials = DX + wf_tb4_elems(L, T, N, Z);
   const size_t partial_floats = seq_partial_floats(F, L, G);
-  const uint16_t *hTh = (const uint16_t*)hT_hi, *hTl = (const uint16_t*)hT_lo;
+  const uint16_t* H16 = (const uint16_t*)hb16;
+  const uint16_t* H16m = (const uint16_t*)hb16m;
   CUtensorMap tmhi, tmlo;
   int rc = seq_maps_bwd(&tmhi, &tmlo, b16_hi, b16_lo, L, G * layers);
   if (rc) return rc;
   for (int l = layers - 1; l >= 0; --l) {
-    const int kin = l == 0 ? F : L;
-    float* XG = gates + l * g_elems;
-    // the input of layer l >= 1 is the (masked, when dropout is on) output of layer l - 1
-    const void* XTh = l == 0 ? xT_hi : (const void*)((drop ? hTmh : hTh) + (l - 1) * tsz);
-    const void* XTl = l == 0 ? xT_lo : (const void*)((drop ? hTml : hTl) + (l - 1) * tsz);
     SeqArgs a;
     memset(&a, 0, sizeof(a));
-    a.XG = XG; a.Cst = const_cast<float*>(c) + l * c_elems; a.DGT = dgT;
+    a.XG = const_cast<float*>(gates) + l * g_elems; a.Cst = const_cast<float*>(c) + l * c_elems;
+    a.DG16 = (uint16_t*)dg16; a.dg16_plane = dgp;
     a.ext = l == layers - 1 ? dlast : DX; a.ext_last_only = l == layers - 1 ? 1 : 0;
-    a.T = T; a.Nn = N; a.Bw = Bw; a.tpw = tpw; a.rpt = wf_tile_rows(N); a.Np = Np; a.RT = RT;
+    a.T = T; a.Nn = N; a.Bw = Bw; a.tpw = tpw; a.rpt = wf_tile_rows(N);
     a.slab0 = 2 * l; a.slab_g = 2 * layers; a.err = err;
     wf_lstm_seq_bwd_kernel<<<dim3((unsigned)(2 * Z * tpw)), SEQ_THREADS, SEQ_SMEM, st>>>(tmhi, tmlo, a);
     WF_CHECK_LAUNCH("lstm_seq_bwd");
-    // dW_ih = dG^T X_l  as  (dG^T)(X_l^T)^T over all columns of every window (padding columns are zero); the bias
-    // gradients db_ih = db_hh = row sums of dG^T fall out of the same pass over dG^T
-    rc = wf_launch_g16_wgrad(dgT, 4 * L, XTh, XTl, kin, RT, Bw, G, 0, 0, RT, grads + P.w_ih[l], grads_group_stride, err, st,
-                             partials, partial_floats, grads + P.b_ih[l], grads + P.b_hh[l], grads_group_stride);
-    if (rc) return rc;
-    if (T > 1) {  // dW_hh = sum_{t>=1} dG[t]^T h[t-1]: dG^T columns [Np, RT) against h^T columns [0, RT-Np)
-      rc = wf_launch_g16_wgrad(dgT, 4 * L, hTh + l * tsz, hTl + l * tsz, L, RT, Bw, G, Np, 0, RT - Np, grads + P.w_hh[l],
-                               grads_group_stride, err, st, partials, partial_floats, nullptr, nullptr, 0);
+    // weight gradients, one pass over dG: [dW_ih | dW_hh] = dG^T [x | h(t-1)], the bias gradients = row sums of dG^T
+    const void* Hl = H16 + (long long)l * 2 * hp;
+    if (l > 0) {
+      const void* Xl = (drop ? H16m : H16) + (long long)(l - 1) * 2 * hp;   // the (masked) output of the layer below
+      const void* src[2] = {Xl, Hl};
+      const long long plane[2] = {hp, hp};
+      const int var[2] = {0, 0}, shift[2] = {0, 1}, col0[2] = {0, 0}, ch[2] = {L, L};
+      rc = wf_ss_launch_wgrad(dg16, dgp, T > 1 ? 2 : 1, src, plane, var, shift, col0, ch, T, N, Bw, G, partials, partial_floats,
+                              grads + P.w_ih[l], L, L, T > 1 ? grads + P.w_hh[l] : nullptr, L, L, grads + P.b_ih[l],
+                              grads + P.b_hh[l], grads_group_stride, err, st);
       if (rc) return rc;
     } else {
-      for (int g = 0; g < G; ++g)
-        cudaMemsetAsync(grads + g * grads_group_stride + P.w_hh[l], 0, sizeof(float) * 4 * L * L, st);
+      for (int f0 = 0; f0 < F; f0 += 256) {   // layer 0: the features are row-major planes, 256 columns per pass
+        const int w = F - f0 < 256 ? F - f0 : 256;
+        const void* src[2] = {xb16, xb16};
+        const long long plane[2] = {Z * T * N * (long long)F, Z * T * N * (long long)F};
+        const int var[2] = {1, 1}, shift[2] = {0, 0}, col0[2] = {f0, f0 + 128}, ch[2] = {F, F};
+        rc = wf_ss_launch_wgrad(dg16, dgp, w > 128 ? 2 : 1, src, plane, var, shift, col0, ch, T, N, Bw, G, partials, partial_floats,
+                                grads + P.w_ih[0] + f0, F, w, nullptr, 0, 0, f0 == 0 ? grads + P.b_ih[0] : nullptr,
+                                f0 == 0 ? grads + P.b_hh[0] : nullptr, grads_group_stride, err, st);
+        if (rc) return rc;
+      }
+      if (T > 1) {
+        const void* src[2] = {Hl, Hl};
+        const long long plane[2] = {hp, hp};
+        const int var[2] = {0, 0}, shift[2] = {1, 1}, col0[2] = {0, 0}, ch[2] = {L, L};
+        rc = wf_ss_launch_wgrad(dg16, dgp, 1, src, plane, var, shift, col0, ch, T, N, Bw, G, partials, partial_floats,
+                                grads + P.w_hh[0], L, L, nullptr, 0, 0, nullptr, nullptr, grads_group_stride, err, st);
+        if (rc) return rc;
+      }
     }
-    if (l > 0) {  // dL/d(input of layer l) = dG W_ih -> ext of layer l-1 (TB4 in, TB4 out), through layer l-1's mask
+    if (T == 1)
+      for (int g = 0; g < G; ++g) cudaMemsetAsync(grads + g * grads_group_stride + P.w_hh[l], 0, sizeof(float) * 4 * L * L, st);
+    if (l > 0) {  // dL/d(input of layer l) = dG W_ih -> ext of layer l-1 (TB4 out), through layer l-1's mask
       const DropCfg dc = wf_drop_cfg(p_drop, rng, WF_SITE_LSTM + l - 1);
-      rc = wf_launch_g16_nodes(1, XG, 1, 4 * L, (const uint16_t*)pT16_hi + P.wihT[l], (const uint16_t*)pT16_lo + P.wihT[l], 4 * L,
-                               stride16(P.totalT), L, nullptr, nullptr, 0, DX, T, N, Bw, G, err, st, drop ? &dc : nullptr);
+      rc = wf_ss_launch_nodes(64, 1, dg16, dgp, 4 * L, 1, (const uint16_t*)pT16_hi + P.wihT[l], (const uint16_t*)pT16_lo + P.wihT[l],
+                              4 * L, stride16(P.totalT), L, 1, nullptr, nullptr, 0, DX, T, N, Bw, G, drop ? &dc : nullptr, err, st);
       if (rc) return rc;
     }
   }
@@ -985,7 +1004,7 @@ extern "C" int wf_lstm_bwd_seq(const void* xT_hi, const void* xT_lo, const void*
 
 // ---- single-layer recurrence entry points: exactly the persistent launches the two functions above issue per layer,
 // exposed so that a harness can time the dominant kernels alone (bench.py roofline) or drive layers itself.
-extern "C" int wf_lstm_seq_recur_fwd(float* gates_l, float* c_l, float* h_l, void* hT_hi_l, void* hT_lo_l, const void* f16_hi,
+extern "C" int wf_lstm_seq_recur_fwd(float* gates_l, float* c_l, void* h16_l, void* hb16_l, float* hlast, const void* f16_hi,
                                      const void* f16_lo, int layer, int layers, int L, int T, int N, int G, int Bw, int* err,
                                      void* stream) {
   WF_REQUIRE(layers >= 1 && layers <= 8 && layer >= 0 && layer < layers && L == 128, "lstm_seq_recur_fwd: bad layer / L");
@@ -997,16 +1016,16 @@ extern "C" int wf_lstm_seq_recur_fwd(float* gates_l, float* c_l, float* h_l, voi
   if (rc) return rc;
   SeqArgs a;
   memset(&a, 0, sizeof(a));
-  a.XG = gates_l; a.Cst = c_l; a.H = h_l; a.h_tb4 = layer + 1 < layers ? 1 : 0;
-  a.HT = (__nv_bfloat16*)hT_hi_l; a.HT_lo = (__nv_bfloat16*)hT_lo_l;
-  a.T = T; a.Nn = N; a.Bw = Bw; a.tpw = wf_cdiv(N, 128); a.rpt = wf_tile_rows(N); a.Np = wf_np(N); a.RT = T * a.Np;
+  a.XG = gates_l; a.Cst = c_l; a.H16 = (uint16_t*)h16_l; a.HB16 = (uint16_t*)hb16_l; a.h16_plane = wf_tb8_elems(L, T, N, Z);
+  a.Hlast = hlast;
+  a.T = T; a.Nn = N; a.Bw = Bw; a.tpw = wf_cdiv(N, 128); a.rpt = wf_tile_rows(N);
   a.slab0 = layer; a.slab_g = layers; a.err = err;
   wf_lstm_seq_fwd16_kernel<false><<<dim3((unsigned)(2 * Z * a.tpw)), 512, SEQ_SMEM, (cudaStream_t)stream>>>(tmhi, tmlo, a);
   WF_CHECK_LAUNCH("lstm_seq_recur_fwd");
   return WF_OK;
 }
 
-extern "C" int wf_lstm_seq_recur_bwd(float* gates_l, const float* c_l, float* dgT, const float* ext, int ext_is_dlast,
+extern "C" int wf_lstm_seq_recur_bwd(const float* gates_l, const float* c_l, void* dg16, const float* ext, int ext_is_dlast,
                                      const void* b16_hi, const void* b16_lo, int layer, int layers, int L, int T, int N, int G,
                                      int Bw, int* err, void* stream) {
   WF_REQUIRE(layers >= 1 && layers <= 8 && layer >= 0 && layer < layers && L == 128, "lstm_seq_recur_bwd: bad layer / L");
@@ -1018,8 +1037,9 @@ extern "C" int wf_lstm_seq_recur_bwd(float* gates_l, const float* c_l, float* dg
   if (rc) return rc;
   SeqArgs a;
   memset(&a, 0, sizeof(a));
-  a.XG = gates_l; a.Cst = const_cast<float*>(c_l); a.DGT = dgT; a.ext = ext; a.ext_last_only = ext_is_dlast ? 1 : 0;
-  a.T = T; a.Nn = N; a.Bw = Bw; a.tpw = wf_cdiv(N, 128); a.rpt = wf_tile_rows(N); a.Np = wf_np(N); a.RT = T * a.Np;
+  a.XG = const_cast<float*>(gates_l); a.Cst = const_cast<float*>(c_l); a.DG16 = (uint16_t*)dg16;
+  a.dg16_plane = wf_tb8_elems(4 * L, T, N, Z); a.ext = ext; a.ext_last_only = ext_is_dlast ? 1 : 0;
+  a.T = T; a.Nn = N; a.Bw = Bw; a.tpw = wf_cdiv(N, 128); a.rpt = wf_tile_rows(N);
   a.slab0 = 2 * layer; a.slab_g = 2 * layers; a.err = err;
   wf_lstm_seq_bwd_kernel<<<dim3((unsigned)(2 * Z * a.tpw)), SEQ_THREADS, SEQ_SMEM, (cudaStream_t)stream>>>(tmhi, tmlo, a);
   WF_CHECK_LAUNCH("lstm_seq_recur_bwd");

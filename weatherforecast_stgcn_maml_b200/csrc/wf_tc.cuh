@@ -196,5 +196,6 @@ __device__ __forceinline__ void split_tf32(float v, uint32_t& hi, uint32_t& lo) 
 
 // Host side: encode a tiled tensor map without linking libcuda (driver entry point lookup).
 // dtype: 0 = f32, 1 = f16, 2 = bf16 (dims and box in elements, strides in bytes).
+// swizzle_128b: 0 = none, 1 = SWIZZLE_128B, 2 = SWIZZLE_64B, 3 = SWIZZLE_32B.
 int wf_encode_tensor_map(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                          const uint32_t* box, int swizzle_128b, int dtype = 0);

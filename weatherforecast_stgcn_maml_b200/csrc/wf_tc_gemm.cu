@@ -487,7 +487,8 @@ int wf_encode_tensor_map(CUtensorMap* out, const void* base, int rank, const uin
   const CUtensorMapDataType dt = dtype == 1 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16
                                : dtype == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
   CUresult r = fn(out, dt, (cuuint32_t)rank, const_cast<void*>(base), d, s, b, e,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_128b ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_128b == 1 ? CU_TENSOR_MAP_SWIZZLE_128B : swizzle_128b == 2 ? CU_TENSOR_MAP_SWIZZLE_64B
+                  : swizzle_128b == 3 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_NONE,
                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return wf_fail(WF_ECUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
   return WF_OK;

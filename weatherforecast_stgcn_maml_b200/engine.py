@@ -146,14 +146,35 @@ class HybridEngine:
         self.W = self.G * self.Bw
         f32 = dict(dtype=torch.float32, device=self.device)
         n_act = 4 if keep_gcn_activations else 2
-        self.act = [torch.empty(self.rows, d.hidden, **f32) for _ in range(n_act)]
+        i16 = dict(dtype=torch.int16, device=self.device)
         self.keep_gcn = keep_gcn_activations
         Ls, L = d.lstm_layers, d.lstm_hidden
+        # the GCN stack of the persistent path works on pre-split fp16 hi/lo planes (csrc/wf_gemm_ss.cu)
+        self.gcn_ss = self.seq and d.in_channels % 8 == 0
+        if self.gcn_ss:
+            self.act16 = [torch.empty(2, self.rows, d.hidden, **i16) for _ in range(n_act)]
+            self.featsb16 = torch.empty(2, self.rows, d.hidden, **i16) if self.training else None  # bf16 planes of the output
+            self.x16 = torch.empty(2, self.rows, d.in_channels, **i16)   # split of the fp32 input windows (first layer)
+            self.side16 = None                                            # aggregated leading rows, sized by the graph
+            self.act = None
+        else:
+            self.act = [torch.empty(self.rows, d.hidden, **f32) for _ in range(n_act)]
         if self.seq:  # gates / cell state in the tile-blocked TB4 layout (padded to 128-node tiles)
             self.gates = torch.empty(Ls, int(_lib.query("wf_tb4_elems", 4 * L, d.window, d.num_nodes, self.G * self.Bw)), **f32)
             self.c = torch.empty(Ls, int(_lib.query("wf_tb4_elems", L, d.window, d.num_nodes, self.G * self.Bw)), **f32)
-            # hidden states: top layer row-major (the head reads it), layers below TB4 (next layer's projection only)
-            self.h = torch.empty(Ls, self.c.shape[1], **f32)
+            # hidden states of every layer as fp16 hi/lo planes in the TB8 layout: the next layer's projection operand and
+            # both weight-gradient operands.  Zero-initialised: the padding rows of a node tile are never written and must
+            # read as zero where rows are contracted.  The head reads the top layer's last step from ``hlast`` (fp32).
+            # h16: fp16, what the next layer's projection reads (masked under dropout); hb16: bf16, the plain h for the weight
+            # gradients (one operand format per tensor-core product, and dG needs bf16's range); hb16m: bf16, masked
+            self.hp = int(_lib.query("wf_tb8_elems", L, d.window, d.num_nodes, self.G * self.Bw))
+            self.h16 = torch.zeros(max(Ls - 1, 1), 2, self.hp, **i16)
+            self.hb16 = torch.zeros(Ls, 2, self.hp, **i16) if self.training else None
+            self.hb16m = (torch.zeros(max(Ls - 1, 1), 2, self.hp, **i16)
+                          if self.training and self.dropout[1] > 0 and Ls > 1 else None)
+            self.hlast = torch.empty(self.W * d.num_nodes, L, **f32)
+            self.feats16 = None   # layer-0 input planes when the features arrive as an fp32 tensor (module API)
+            self.h = None
         else:
             self.gates = torch.empty(Ls, self.rows, 4 * L, **f32)
             self.c = torch.empty(Ls, self.rows, L, **f32)
@@ -176,7 +197,6 @@ class HybridEngine:
                  _lib.query("wf_head_workspace_bytes", L, d.O, d.num_nodes, self.G, self.Bw),
                  _lib.query("wf_optim_workspace_bytes", self.G))
         self.err = torch.zeros(1, dtype=torch.int32, device=self.device)
-        i16 = dict(dtype=torch.int16, device=self.device)
         if self.seq:
             # persistent path: 16-bit hi/lo operands everywhere (fp16 forward, bf16 for gradient operands)
             ws = max(ws, _lib.query("wf_lstm_bwd_seq_workspace_bytes", Ls, d.hidden, L, d.window, d.num_nodes, self.G,
@@ -187,20 +207,9 @@ class HybridEngine:
             s16 = [int(_lib.query("wf_param_stride16", Ls, d.hidden, L, d.O, w)) for w in (0, 1)]
             self.p16 = [torch.empty(self.G, s16[0], **i16) for _ in range(2)]   # flat params as fp16 hi/lo
             self.pT16 = [torch.empty(self.G, s16[1], **i16) for _ in range(2)]  # W_ih^T as bf16 hi/lo
-            if self.training:
-                # transposed activation copies [(G*Bw)][channels][RT16] feed the weight-gradient products;
-                # their padding columns must be zero and are never written by the kernels
-                rt = int(_lib.query("wf_transposed_pitch16", d.window, d.num_nodes))
-                self.hT = torch.zeros(Ls, self.W * L * rt, **i16)
-                self.hT_lo = torch.zeros(Ls, self.W * L * rt, **i16)
-                self.featsT = torch.zeros(self.W * d.hidden * rt, **i16)
-                self.featsT_lo = torch.zeros(self.W * d.hidden * rt, **i16)
-                self.dgT = torch.zeros(self.W * 4 * L * rt, **f32)
-                # dropout on: transposed copies of the MASKED layer outputs (the next layer's input, for its dW_ih)
-                self.hTm = torch.zeros(Ls - 1, self.W * L * rt, **i16) if p_lstm > 0 else None
-                self.hTm_lo = torch.zeros(Ls - 1, self.W * L * rt, **i16) if p_lstm > 0 else None
-            else:
-                self.hT = self.hT_lo = self.featsT = self.featsT_lo = self.dgT = self.hTm = self.hTm_lo = None
+            # one layer's dG as bf16 hi/lo planes (TB8), zero-initialised like h16
+            self.dg16 = (torch.zeros(2, int(_lib.query("wf_tb8_elems", 4 * L, d.window, d.num_nodes, self.W)), **i16)
+                         if self.training else None)
             self._gcn_lo = {}
         elif self.tc:
             ws = max(ws, _lib.query("wf_lstm_bwd_tc_workspace_bytes", Ls, d.hidden, L, d.window, d.num_nodes, self.G,
@@ -225,22 +234,39 @@ class HybridEngine:
         self.agg = None  # scratch of the GCN pre-aggregation pass (persistent path)
         self.launches = 0  # kernels enqueued by this engine (bench.py reports it)
 
-    def hidden_states(self):
-        """[layers, G*Bw*R, L] row-major copy of the LSTM hidden states, whatever layout the kernels keep them in."""
+    def _join16(self, planes, fmt=0):
+        """fp32 view (hi + lo) of a pair of 16-bit planes [2, n]."""
+        n = planes[0].numel()
+        out = torch.empty(n, dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.call("wf_join16", _lib.ptr(planes[0]), _lib.ptr(planes[1]), n, fmt, _lib.ptr(out), _lib.stream_ptr())
+        return out
+
+    def _tb8_to_rows(self, flat, channels):
+        """TB8 [window, step, node tile, channels/8, 128 rows, 8] -> row-major [G*Bw*R, channels]."""
+        d = self.dims
+        tpw = (d.num_nodes + 127) // 128
+        rpt = int(_lib.query("wf_tile_rows", d.num_nodes))  # nodes per tile; rows beyond are padding
+        t = flat.view(self.W, d.window, tpw, channels // 8, 128, 8).permute(0, 1, 2, 4, 3, 5)
+        t = t.reshape(self.W, d.window, tpw, 128, channels)[:, :, :, :rpt]
+        return t.reshape(self.W, d.window, tpw * rpt, channels)[:, :, :d.num_nodes].reshape(self.rows, channels)
+
+    def hidden_states(self, masked=False):
+        """[layers, G*Bw*R, L] row-major fp32 copy of the LSTM hidden states, whatever layout the kernels keep them in
+        (``masked``: what the next layer read when inter-layer dropout is on; layers - 1 entries)."""
         d, Ls, L = self.dims, self.dims.lstm_layers, self.dims.lstm_hidden
         if not self.seq:
-            return self.h.clone()
-        tpw = (d.num_nodes + 127) // 128
-        out = torch.empty(Ls, self.rows, L, dtype=torch.float32, device=self.device)
-        for l in range(Ls):
-            if l == Ls - 1:
-                out[l] = self.h[l, :self.rows * L].view(self.rows, L)
-            else:  # TB4: [window, step, node tile, L/4, 128 rows, 4]
-                rpt = int(_lib.query("wf_tile_rows", d.num_nodes))  # nodes per tile; rows beyond are padding
-                t = self.h[l].view(self.W, d.window, tpw, L // 4, 128, 4).permute(0, 1, 2, 4, 3, 5)
-                t = t.reshape(self.W, d.window, tpw, 128, L)[:, :, :, :rpt]
-                out[l] = t.reshape(self.W, d.window, tpw * rpt, L)[:, :, :d.num_nodes].reshape(self.rows, L)
-        return out
+            return (self.h_masked if masked else self.h).clone()
+        if masked or self.hb16 is None:  # fp16 planes of what the next layer read (layers - 1 entries)
+            return torch.stack([self._tb8_to_rows(self._join16(self.h16[l]), L) for l in range(Ls - 1)])
+        return torch.stack([self._tb8_to_rows(self._join16(self.hb16[l], 1), L) for l in range(Ls)])
+
+    def gcn_features(self, layer=None):
+        """fp32 [G*Bw*R, hidden] copy of the GCN stack's output (``layer`` 0..3 with keep_gcn_activations)."""
+        if not self.gcn_ss:
+            return (self.feats if layer is None else self.act[layer]).clone()
+        src = self.feats if layer is None else self.act16[layer]
+        return self._join16(src).view(self.rows, self.dims.hidden)
 
     def train(self, mode=True):
         """Dropout on (if any p > 0) / off, like ``nn.Module.train()``."""
@@ -302,24 +328,15 @@ class HybridEngine:
             raise ValueError(f"graph was normalised over {graphs.R} rows, engine window has {d.R}")
         src, src_ld, src_stride, src_off, cin = X, x_ld, x_win_stride, x_win_off, d.in_channels
         nlayers = len(gcn_weights)
+        if self.gcn_ss and x_ld == cin and (x_win_off is not None or x_win_stride == d.R * cin):
+            return self._gcn_forward_ss(X, x_win_off, gcn_weights, graphs, rp, cl, vl, rps, cs)
+        if self.gcn_ss:
+            raise ValueError("the persistent path reads windows as contiguous [R, in_channels] slices (dataset.py:36-37)")
         for i, (Wt, b) in enumerate(gcn_weights):
             dst = self.act[i] if self.keep_gcn else self.act[i & 1]
             dense = src_off is None and src_ld == cin and src_stride == d.R * cin
-            in_place = src_off is not None and src_ld == cin and gmax > 0  # windows read straight from the features
             p_drop = self._p(0) if i < nlayers - 1 else 0.0
-            if self.seq and (dense or in_place) and cin % 8 == 0 and (cin % 64 == 0 or src.data_ptr() % 16 == 0):
-                want_t = self.training and i == nlayers - 1
-                w16 = self._gcn_w_lo(Wt)
-                if self.agg is None:
-                    self.agg = torch.empty(self.rows, d.hidden, dtype=torch.float32, device=self.device)
-                _lib.call("wf_gcn_layer_fwd_g16", _lib.ptr(src), _lib.ptr(src_off) if in_place else None,
-                          src.numel() // cin, _lib.ptr(w16[0]), _lib.ptr(w16[1]), _lib.ptr(b),
-                          _lib.ptr(rp), _lib.ptr(cl), _lib.ptr(vl), rps, cs, _lib.ptr(gl) if gmax > 0 else None, gmax, gls,
-                          _lib.ptr(self.agg), d.R, d.num_nodes, cin, d.hidden, self.G,
-                          self.Bw, 1, _lib.ptr(dst), _lib.ptr(self.featsT) if want_t else None,
-                          _lib.ptr(self.featsT_lo) if want_t else None, p_drop, _lib.ptr(self.rng), i, _lib.ptr(self.err), st)
-                p_drop = 0.0  # fused into the epilogue
-            elif self.tc and not self.seq and dense and cin % 32 == 0:
+            if self.tc and not self.seq and dense and cin % 32 == 0:
                 want_t = self.training and i == nlayers - 1
                 _lib.call("wf_gcn_layer_fwd_tc", _lib.ptr(src), _lib.ptr(Wt), _lib.ptr(self._gcn_w_lo(Wt)), _lib.ptr(b),
                           _lib.ptr(rp), _lib.ptr(cl), _lib.ptr(vl), rps, cs, d.R, d.num_nodes, cin, d.hidden, self.G,
@@ -338,7 +355,47 @@ class HybridEngine:
         self.feats = src
         return src
 
+    def _gcn_forward_ss(self, X, x_win_off, gcn_weights, graphs, rp, cl, vl, rps, cs):
+        """The stack on pre-split fp16 hi/lo planes: per layer [split of the fp32 windows (first layer only)] + aggregation
+        of the leading rows that have neighbours + one persistent SS-mode GEMM with resident weights whose epilogue writes
+        the next layer's operand planes through TMA stores (csrc/wf_gemm_ss.cu)."""
+        d, st = self.dims, _lib.stream_ptr()
+        agg_rows = int(graphs.agg_rows)
+        if agg_rows > 0 and (self.side16 is None or self.side16.numel() < 2 * self.W * agg_rows * d.hidden):
+            self.side16 = torch.empty(2 * self.W * agg_rows * d.hidden, dtype=torch.int16, device=self.device)
+        nlayers, cin, src16 = len(gcn_weights), d.in_channels, None
+        for i, (Wt, b) in enumerate(gcn_weights):
+            dst = self.act16[i] if self.keep_gcn else self.act16[i & 1]
+            p_drop = self._p(0) if i < nlayers - 1 else 0.0
+            w16 = self._gcn_w_lo(Wt)
+            _lib.call("wf_gcn_layer_fwd_ss", _lib.ptr(X) if i == 0 else None, _lib.ptr(x_win_off) if i == 0 else None,
+                      _lib.ptr(src16) if i > 0 else None, _lib.ptr(self.x16) if i == 0 else None, _lib.ptr(w16[0]),
+                      _lib.ptr(w16[1]), _lib.ptr(b), _lib.ptr(rp), _lib.ptr(cl), _lib.ptr(vl), rps, cs, agg_rows,
+                      _lib.ptr(self.side16) if agg_rows > 0 else None, d.R, cin, d.hidden, self.G, self.Bw, 1,
+                      _lib.ptr(dst), _lib.ptr(self.featsb16) if i == nlayers - 1 else None, p_drop, _lib.ptr(self.rng), i,
+                      _lib.ptr(self.err), st)
+            self.launches += 2 + (1 if i == 0 else 0) if agg_rows > 0 else 1 + (1 if i == 0 else 0)
+            src16, cin = dst, d.hidden
+        self.feats = src16
+        self._xb16 = self.featsb16
+        return src16
+
     # ------------------------------------------------------------------ LSTM + head
+    def _seq_input_planes(self, feats):
+        """Layer-0 operand of the persistent path: the GCN stack's fp16 hi/lo planes, or -- for features that arrive as
+        an fp32 tensor (drop-in module API) -- their split into ``feats16``."""
+        d = self.dims
+        if feats.dtype == torch.int16:
+            return feats
+        if self.feats16 is None:
+            self.feats16 = torch.empty(2, 2, self.rows, d.hidden, dtype=torch.int16, device=self.device)
+        for fmt in ((0, 1) if self.training else (0,)):  # fp16 for the projection, bf16 for the weight gradient
+            _lib.call("wf_split16", _lib.ptr(feats), _lib.ptr(self.feats16[fmt, 0]), _lib.ptr(self.feats16[fmt, 1]),
+                      feats.numel(), fmt, _lib.stream_ptr())
+            self.launches += 1
+        self._xb16 = self.feats16[1]
+        return self.feats16[0]
+
     @_on_device
     def lstm_head_forward(self, params, params_stride, feats=None):
         d, st = self.dims, _lib.stream_ptr()
@@ -351,12 +408,14 @@ class HybridEngine:
             _lib.call("wf_prep_weights_seq", _lib.ptr(params), src_stride, Ls, d.hidden, L, d.O, self.G,
                       _lib.ptr(self.p16[0]), _lib.ptr(self.p16[1]), _lib.ptr(self.pT16[0]), _lib.ptr(self.pT16[1]),
                       _lib.ptr(self.w16[0]), _lib.ptr(self.w16[1]), _lib.ptr(self.w16[2]), _lib.ptr(self.w16[3]), st)
-            _lib.call("wf_lstm_fwd_seq", _lib.ptr(feats), _lib.ptr(params), _lib.ptr(self.p16[0]), _lib.ptr(self.p16[1]),
+            self._x16 = self._seq_input_planes(feats)
+            _lib.call("wf_lstm_fwd_seq", _lib.ptr(self._x16), _lib.ptr(params), _lib.ptr(self.p16[0]), _lib.ptr(self.p16[1]),
                       params_stride if self.G > 1 else self.P, _lib.ptr(self.w16[0]), _lib.ptr(self.w16[1]), Ls, d.hidden,
-                      L, d.O, d.window, d.num_nodes, self.G, self.Bw, _lib.ptr(self.gates), _lib.ptr(self.h),
-                      _lib.ptr(self.c), _lib.ptr(self.hT), _lib.ptr(self.hT_lo), p_lstm, _lib.ptr(self.rng),
-                      _lib.ptr(self.hTm), _lib.ptr(self.hTm_lo), _lib.ptr(self.err), st)
+                      L, d.O, d.window, d.num_nodes, self.G, self.Bw, _lib.ptr(self.gates), _lib.ptr(self.h16),
+                      _lib.ptr(self.c), _lib.ptr(self.hlast), _lib.ptr(self.hb16), p_lstm, _lib.ptr(self.rng),
+                      _lib.ptr(self.hb16m), _lib.ptr(self.err), st)
             self.launches += (1 + (Ls - 1) + 1) + 2 * Ls  # operand staging, then (projection + recurrence) per layer
+            h_top, t_head = self.hlast, 1   # the top layer's last step, compact: the head sees windows of ONE step
         elif self.tc:
             # operand staging for 3xTF32: lo halves and transposed copies of the current weights
             src_stride = params_stride if self.G > 1 else self.P
@@ -366,23 +425,24 @@ class HybridEngine:
                       d.hidden, L, d.O, d.window, d.num_nodes, self.G, self.Bw, _lib.ptr(self.gates), _lib.ptr(self.h),
                       _lib.ptr(self.c), _lib.ptr(self.hT), _lib.ptr(self.hT_lo), _lib.ptr(self.err), st)
             self.launches += 2 * Ls + Ls * (1 + d.window)
+            h_top, t_head = self.h[Ls - 1], d.window
         else:
             _lib.call("wf_lstm_fwd", _lib.ptr(feats), _lib.ptr(params), params_stride, Ls, d.hidden, L, d.O, d.window,
                       d.num_nodes, self.G, self.Bw, _lib.ptr(self.gates), _lib.ptr(self.h), _lib.ptr(self.c), p_lstm,
                       _lib.ptr(self.rng), _lib.ptr(self.h_masked), st)
             self.launches += Ls * (1 + d.window) + (Ls - 1 if p_lstm > 0 else 0)
+            h_top, t_head = self.h[Ls - 1], d.window
         if p_head > 0:
             # head-input dropout (hybrid_model.py:108): mask the last step of the top layer into a compact [W*N, L]
             # buffer, which the head then reads as a window of ONE step
-            _lib.call("wf_dropout_apply", _lib.ptr(self.h[Ls - 1].view(-1)[(d.window - 1) * d.num_nodes * L:]), d.R * L,
-                      d.num_nodes, L, self.W * d.num_nodes, L, p_head, _lib.ptr(self.rng), SITE_HEAD,
-                      _lib.ptr(self.hlast_m), st)
-            _lib.call("wf_head_fwd", _lib.ptr(self.hlast_m), _lib.ptr(params), params_stride, Ls, d.hidden, L, d.O,
-                      1, d.num_nodes, self.G, self.Bw, _lib.ptr(self.pred), st)
+            last = h_top.view(-1)[(t_head - 1) * d.num_nodes * L:]
+            _lib.call("wf_dropout_apply", _lib.ptr(last), t_head * d.num_nodes * L, d.num_nodes, L, self.W * d.num_nodes, L,
+                      p_head, _lib.ptr(self.rng), SITE_HEAD, _lib.ptr(self.hlast_m), st)
+            h_top, t_head = self.hlast_m, 1
             self.launches += 1
-        else:
-            _lib.call("wf_head_fwd", _lib.ptr(self.h[Ls - 1]), _lib.ptr(params), params_stride, Ls, d.hidden, L, d.O,
-                      d.window, d.num_nodes, self.G, self.Bw, _lib.ptr(self.pred), st)
+        self._h_top, self._t_head = h_top, t_head
+        _lib.call("wf_head_fwd", _lib.ptr(h_top), _lib.ptr(params), params_stride, Ls, d.hidden, L, d.O, t_head,
+                  d.num_nodes, self.G, self.Bw, _lib.ptr(self.pred), st)
         self.launches += 1
         return self.pred
 
@@ -405,28 +465,24 @@ class HybridEngine:
         dpred = self.dpred if dpred is None else dpred
         Ls, L = d.lstm_layers, d.lstm_hidden
         p_lstm, p_head = self._p(1), self._p(2)
+        # the head's input is whatever the forward pass fed it: the (masked) compact last step or the top layer's rows
+        _lib.call("wf_head_bwd", _lib.ptr(dpred), _lib.ptr(self._h_top), _lib.ptr(params), params_stride, Ls,
+                  d.hidden, L, d.O, self._t_head, d.num_nodes, self.G, self.Bw, _lib.ptr(self.dlast),
+                  _lib.ptr(self.grads), self.P, _lib.ptr(self.ws), self.ws_bytes, st)
         if p_head > 0:
-            _lib.call("wf_head_bwd", _lib.ptr(dpred), _lib.ptr(self.hlast_m), _lib.ptr(params), params_stride, Ls,
-                      d.hidden, L, d.O, 1, d.num_nodes, self.G, self.Bw, _lib.ptr(self.dlast),
-                      _lib.ptr(self.grads), self.P, _lib.ptr(self.ws), self.ws_bytes, st)
             _lib.call("wf_dropout_apply", _lib.ptr(self.dlast), 0, self.W * d.num_nodes, L, self.W * d.num_nodes, L, p_head,
                       _lib.ptr(self.rng), SITE_HEAD, _lib.ptr(self.dlast), st)
             self.launches += 1
-        else:
-            _lib.call("wf_head_bwd", _lib.ptr(dpred), _lib.ptr(self.h[Ls - 1]), _lib.ptr(params), params_stride, Ls,
-                      d.hidden, L, d.O, d.window, d.num_nodes, self.G, self.Bw, _lib.ptr(self.dlast),
-                      _lib.ptr(self.grads), self.P, _lib.ptr(self.ws), self.ws_bytes, st)
         if self.tc:
             if not self.training:
                 raise RuntimeError("engine was built with training=False")
             if self.seq:
-                _lib.call("wf_lstm_bwd_seq", _lib.ptr(self.featsT), _lib.ptr(self.featsT_lo), _lib.ptr(self.pT16[0]),
-                          _lib.ptr(self.pT16[1]), _lib.ptr(self.w16[2]), _lib.ptr(self.w16[3]), Ls, d.hidden, L, d.O,
-                          d.window, d.num_nodes, self.G, self.Bw, _lib.ptr(self.gates), _lib.ptr(self.c), _lib.ptr(self.hT),
-                          _lib.ptr(self.hT_lo), _lib.ptr(self.dgT), _lib.ptr(self.dlast), _lib.ptr(self.grads), self.P,
-                          p_lstm, _lib.ptr(self.rng), _lib.ptr(self.hTm), _lib.ptr(self.hTm_lo),
-                          _lib.ptr(self.ws), self.ws_bytes, _lib.ptr(self.err), st)
-                self.launches += 6 + Ls * 7 - 1  # head bwd + per layer: recurrence, colsum, 2 x (wgrad + split sum), dX
+                _lib.call("wf_lstm_bwd_seq", _lib.ptr(self._xb16), _lib.ptr(self.pT16[0]), _lib.ptr(self.pT16[1]),
+                          _lib.ptr(self.w16[2]), _lib.ptr(self.w16[3]), Ls, d.hidden, L, d.O, d.window, d.num_nodes, self.G,
+                          self.Bw, _lib.ptr(self.gates), _lib.ptr(self.c), _lib.ptr(self.hb16), _lib.ptr(self.dg16),
+                          _lib.ptr(self.dlast), _lib.ptr(self.grads), self.P, p_lstm, _lib.ptr(self.rng),
+                          _lib.ptr(self.hb16m), _lib.ptr(self.ws), self.ws_bytes, _lib.ptr(self.err), st)
+                self.launches += 6 + Ls * 4 + 1  # head bwd + per layer: recurrence, wgrad + reduce, dX (layer 0: two wgrads)
             else:
                 _lib.call("wf_lstm_bwd_tc", _lib.ptr(self.featsT), _lib.ptr(self.featsT_lo), _lib.ptr(self.paramsT),
                           _lib.ptr(self.paramsT_lo), Ls, d.hidden, L, d.O, d.window, d.num_nodes, self.G, self.Bw,

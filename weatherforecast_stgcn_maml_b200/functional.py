@@ -238,10 +238,6 @@ class LSTMHead(torch.autograd.Function):
             e.train(any(p > 0 for p in dropout))
             if e.stochastic:
                 e.rng.copy_(st.rng_snapshot())
-            if e.seq and need_grad:
-                # the weight gradient dG^T X of layer 0 reads X^T as bf16 hi/lo (normally written by the GCN epilogue)
-                _lib.call("wf_transpose_split16_rows", _lib.ptr(feats), d.window, d.num_nodes, d.hidden, bw,
-                          _lib.ptr(e.featsT), _lib.ptr(e.featsT_lo), _lib.stream_ptr())
             pred = e.lstm_head_forward(flat, 0, feats=feats).clone()
             st.publish_errors()
         if need_grad:

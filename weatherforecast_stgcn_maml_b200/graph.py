@@ -46,11 +46,13 @@ class RegionGraph:
                       _lib.ptr(ws), nbytes, _lib.stream_ptr())
         self._ws = ws  # keep alive until the stream has consumed it
         self._gather_rows = None
+        self._agg_rows = None
         _ = self.gather_rows  # computed eagerly (it synchronises): never inside a CUDA-graph capture
         # wf_csr_count_kernel flags an edge outside [0, R) in workspace int[4R] (csrc/wf_graph.cu); the host check above
         # makes that unreachable, but a corrupted graph must not be normalised silently
         if int(ws.view(torch.int32)[4 * self.R].item()) != 0:
             raise IndexError("wf_gcn_norm_csr: edge_index references a row outside the window")
+        _ = self.agg_rows
 
     @property
     def gather_rows(self):
@@ -63,6 +65,15 @@ class RegionGraph:
             ident = (deg == 1) & (self.col[first].long() == rows) & (self.val[first] == 1.0)
             self._gather_rows = torch.nonzero(~ident).flatten().to(torch.int32).contiguous()
         return self._gather_rows
+
+    @property
+    def agg_rows(self):
+        """Leading rows of a window that hold every row with neighbours, rounded up to the 128-row tiles of the GEMM
+        (0: the graph has no edges besides the self loops)."""
+        if self._agg_rows is None:
+            g = self.gather_rows
+            self._agg_rows = 0 if g.numel() == 0 else min((int(g.max()) + 128) // 128 * 128, (self.R + 127) // 128 * 128)
+        return self._agg_rows
 
     @property
     def nnz(self):
@@ -85,6 +96,7 @@ class StackedGraphs:
         self.val_t = torch.stack([g.val_t for g in graphs]).contiguous()
         lists = [g.gather_rows for g in graphs]
         self.gather_max = max(int(l.numel()) for l in lists)
+        self.agg_rows = max(g.agg_rows for g in graphs)
         self.gather_rows = torch.full((self.G, max(self.gather_max, 1)), -1, dtype=torch.int32, device=self.device)
         for i, l in enumerate(lists):
             self.gather_rows[i, :l.numel()] = l
