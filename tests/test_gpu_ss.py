@@ -46,10 +46,12 @@ def from_tb4(c, ZT, N, C):
 
 
 @pytest.mark.parametrize("avar", [0, 1])
-@pytest.mark.parametrize("bn,K,Ntot,fmt", [(128, 256, 512, 0), (256, 128, 512, 0), (64, 512, 128, 1), (128, 32, 256, 0),
+@pytest.mark.parametrize("bn,K,Ntot,fmt", [(128, 256, 512, 0), (256, 128, 512, 0), (64, 512, 128, 1), (128, 24, 256, 0),
                                            (256, 64, 256, 1)])
 @pytest.mark.parametrize("N,T,G,Bw", [(441, 3, 2, 2), (128, 2, 1, 1), (57, 1, 3, 1)])
 def test_ss_nodes_gemm_every_a_layout(avar, bn, K, Ntot, fmt, N, T, G, Bw):
+    if avar == 1 and K % 64:
+        pytest.skip("TB8 operands come in whole 64-wide k-blocks (LSTM widths)")
     torch.manual_seed(K + N)
     ZT = G * Bw * T
     scale = 1.0 if fmt == 0 else 1e-3

@@ -35,14 +35,17 @@ extern "C" int wf_tile_rows(int N);
 namespace {
 
 constexpr int SS_THREADS = 192;  // warp 0: TMA producer; warp 1: MMA issue + TMEM owner; warps 2-5: epilogue (lane quarters 2,3,0,1)
-constexpr int SS_BK = 32;
-constexpr int SS_A_PLANE = 128 * SS_BK * 2;   // 8 KB: one 16-bit plane of an A stage
+// One TMA tensor load costs ~0.2 us of serialised issue whatever its size (measured: tools/ss_bench.py ablations, and the
+// first generation's 4 loads per k-block = 1.3 us), so a stage is ONE load: the hi and the lo plane of a [128 x 64] operand
+// tile together (the plane is the outermost box dimension) = 32 KB.
+constexpr int SS_BK = 64;
+constexpr int SS_A_PLANE = 128 * SS_BK * 2;   // 16 KB: one 16-bit plane of an A stage
 constexpr int SS_A_STAGE = 2 * SS_A_PLANE;    // hi + lo
 constexpr int SS_B_BYTES = 131072;            // resident B: BN x K x 2 B x 2 planes
 constexpr int SS_STG_BYTES = 32768;           // GCN epilogue staging: 4 warps x (hi + lo) x 32 rows x 128 B
 constexpr int SS_MAX_STAGES = 6;
 
-enum { SS_A_KS = 0, SS_A_KT = 1 };    // A: K-major SWIZZLE_64B from row-major hl16 / K-major no-swizzle from TB8
+enum { SS_A_KS = 0, SS_A_KT = 1 };    // A: K-major SWIZZLE_128B from row-major hl16 / K-major no-swizzle from TB8
 enum { SS_E_TB4 = 0, SS_E_HL = 1 };   // epilogue: fp32 TB4 block (+bias) / row-major hl16 through TMA stores (+bias, ReLU)
 enum { SS_ROWS = 0, SS_NODES = 1 };   // row tiles: 128 rows of a window / the node tile of one (window, step)
 
@@ -50,7 +53,7 @@ struct SsArgs {
   int mode, avar, epi;
   int n_parts;          // N_total / BN
   int m_tiles_g, G;     // row tiles per group, groups
-  int nkb;              // K / 32
+  int nkb;              // K / 64 (rounded up: TMA zero-fills beyond K)
   int nst;              // A ring depth
   int b_per_group;      // weights differ per group: reload the resident B when a CTA's range crosses into the next group
   int afmt, bfmt;       // 0 fp16, 1 bf16
@@ -63,6 +66,8 @@ struct SsArgs {
   const float* bias; const float* bias2; long long bias_gstride; int relu;
   DropCfg drop; float range_limit;
   int out2;             // E_HL: also write bf16 planes through tmOut2
+  int pf;               // L2 prefetch distance in stages (0: off)
+  int debug;            // WF_SS_DEBUG (tools/ss_bench.py ablations): 1 no MMA, 2 no epilogue stores
   int* err;
 };
 
@@ -83,6 +88,14 @@ __device__ __forceinline__ void tma_load_5d(void* dst, const CUtensorMap* m, uin
   asm volatile("cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];\n"
                ::"r"(smem_u32(dst)), "l"(m), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
 }
+__device__ __forceinline__ void tma_prefetch_4d(const CUtensorMap* m, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.tile [%0, {%1, %2, %3, %4}];\n"
+               ::"l"(m), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_5d(const CUtensorMap* m, int c0, int c1, int c2, int c3, int c4) {
+  asm volatile("cp.async.bulk.prefetch.tensor.5d.L2.global.tile [%0, {%1, %2, %3, %4, %5}];\n"
+               ::"l"(m), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
+}
 __device__ __forceinline__ void tma_store_4d(const CUtensorMap* m, const void* src, int c0, int c1, int c2, int c3) {
   asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];\n"
                ::"l"(m), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
@@ -91,6 +104,29 @@ __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk
 __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;\n" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;\n" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
+
+// Bounded wait by POLLING (mbarrier.test_wait never suspends the thread).  mbarrier.try_wait parks the thread and its
+// wake-up was measured at about a microsecond per hand-over (tools/ss_bench.py): with two hand-overs per pipeline stage that,
+// not memory latency, set the stage round trip.  The waiting warps here have nothing else to do.
+__device__ __forceinline__ bool ss_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  for (uint32_t spin = 0; spin < (1u << 24); ++spin) {
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}\n"
+                 : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
+    if (ok) return true;
+  }
+  return false;
+}
+#define mbar_wait ss_wait
+
+// One elected lane of a converged warp (elect.sync): unlike `lane == 0` the compiler knows the region runs in exactly one
+// thread and feeds tcgen05.mma's uniform-register operands without a vote / broadcast loop per instruction.
+__device__ __forceinline__ bool ss_elect() {
+  uint32_t pred = 0;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.b32 %0, 1, 0, p;\n\t}\n" : "=r"(pred));
+  return pred != 0;
+}
 
 __device__ __forceinline__ void ss_split_bf16(float a, float b, uint32_t& hi, uint32_t& lo) {
   const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
@@ -105,6 +141,13 @@ __device__ __forceinline__ void ss_split_f16(float a, float b, uint32_t& hi, uin
   hi = *reinterpret_cast<const uint32_t*>(&h);
   lo = *reinterpret_cast<const uint32_t*>(&l);
 }
+
+#ifdef WF_SS_TRACE
+__device__ long long wf_ss_trace_buf[4 * 256];   // [role event][stage index], CTA 0 (tools/ss_trace.py)
+#define SS_TR(ev, i) do { if (blockIdx.x == 0 && (i) < 256) wf_ss_trace_buf[(ev) * 256 + (i)] = clock64(); } while (0)
+#else
+#define SS_TR(ev, i) do { } while (0)
+#endif
 
 struct SsTile { int g, mtg, z, mtw, zt, nt, blk, node0; bool side; };
 
@@ -137,8 +180,13 @@ __global__ void __launch_bounds__(SS_THREADS, 1)
 wf_ss_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
              const __grid_constant__ CUtensorMap tmBhi, const __grid_constant__ CUtensorMap tmBlo,
              const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmOut2, const SsArgs a) {
-  constexpr int NH = BN > 128 ? 2 : 1;          // MMA instructions per product and K step (N = 128 each, or one of N = BN)
-  constexpr int NI = BN > 128 ? 128 : BN;
+  // A tcgen05.mma that accumulates into the columns the previous one wrote waits ~150 clk for it, whatever its size
+  // (measured: 150-180 clk per instruction for N = 64 and N = 128 alike), so the products of a tile are dealt round-robin
+  // over NC independent accumulators that the epilogue adds up: N = 64: 3 chains, N = 128: 2, N = 256 (128 clk of work
+  // per instruction anyway): 1.  TMEM: 2 stages x NC x BN columns.
+  constexpr int NC = BN == 64 ? 3 : (BN == 128 ? 2 : 1);
+  constexpr int DCOLS = NC * BN;                // columns of one accumulator stage
+  constexpr int TCOLS = 512;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sB = smem;                           // [plane][k-block][BN rows][64 B]
@@ -163,12 +211,12 @@ wf_ss_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     mbar_fence_init();
     tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmBhi); tma_prefetch_desc(&tmBlo);
   }
-  if (warp == 1) tmem_alloc(&tmem_base_s, 2 * BN);   // two accumulator stages: 128 / 256 / 512 columns
+  if (warp == 1) tmem_alloc(&tmem_base_s, TCOLS);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tbase = tmem_base_s;
-  const uint32_t b_plane = (uint32_t)a.nkb * BN * 64u;   // bytes of one resident B plane
+  const uint32_t b_plane = (uint32_t)a.nkb * BN * 128u;   // bytes of one resident B plane: [k-block][BN rows][128 B]
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
@@ -181,33 +229,39 @@ wf_ss_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           if (bload > 0 && !mbar_wait(&bempty, (bload - 1) & 1)) { atomicExch(a.err, 51); break; }
           mbar_expect_tx(&bfull, 2 * b_plane);
           for (int kb = 0; kb < a.nkb; ++kb) {
-            tma_load_3d(sB + kb * BN * 64, &tmBhi, &bfull, kb * SS_BK, n0, gb);
-            tma_load_3d(sB + b_plane + kb * BN * 64, &tmBlo, &bfull, kb * SS_BK, n0, gb);
+            tma_load_3d(sB + kb * BN * 128, &tmBhi, &bfull, kb * SS_BK, n0, gb);
+            tma_load_3d(sB + b_plane + kb * BN * 128, &tmBlo, &bfull, kb * SS_BK, n0, gb);
           }
           gprev = gb; ++bload;
         }
         for (int kb = 0; kb < a.nkb; ++kb, ++it) {
           const int s = it % NST, ph = (it / NST) & 1;
           if (!mbar_wait(&empty[s], ph ^ 1)) { atomicExch(a.err, 52); mt = mt1; break; }
+          SS_TR(0, it);   // producer: slot free
           uint8_t* st = sA + s * SS_A_STAGE;
           mbar_expect_tx(&full[s], SS_A_STAGE);
-          if (a.avar == SS_A_KT) {   // TB8 block: [plane][block][K/8][128 rows][8]
-            tma_load_5d(st, &tmA, &full[s], 0, 0, kb * 4, t.blk, 0);
-            tma_load_5d(st + SS_A_PLANE, &tmA, &full[s], 0, 0, kb * 4, t.blk, 1);
-          } else if (a.mode == SS_NODES) {  // row-major [plane][(window, step)][node][K]
+          // one load per stage: both planes of the [128 rows x 64 k] tile
+          if (a.avar == SS_A_KT)            // TB8 block: [plane][block][K/8][128 rows][8]
+            tma_load_5d(st, &tmA, &full[s], 0, 0, kb * 8, t.blk, 0);
+          else if (a.mode == SS_NODES)      // row-major [plane][(window, step)][node][K]
             tma_load_4d(st, &tmA, &full[s], kb * SS_BK, t.node0, t.zt, 0);
-            tma_load_4d(st + SS_A_PLANE, &tmA, &full[s], kb * SS_BK, t.node0, t.zt, 1);
-          } else {                          // row-major [plane][window][row][K]; leading rows from the side buffer
-            const CUtensorMap* m = t.side ? &tmA2 : &tmA;
-            tma_load_4d(st, m, &full[s], kb * SS_BK, t.mtw * 128, t.z, 0);
-            tma_load_4d(st + SS_A_PLANE, m, &full[s], kb * SS_BK, t.mtw * 128, t.z, 1);
+          else                              // row-major [plane][window][row][K]; leading rows from the side buffer
+            tma_load_4d(st, t.side ? &tmA2 : &tmA, &full[s], kb * SS_BK, t.mtw * 128, t.z, 0);
+          if (a.pf > 0) {   // the ring is three loads deep and a load from DRAM takes ~2,700 clk: warm L2 `pf` stages ahead
+            const int fut = (mt - mt0) * a.nkb + kb + a.pf, fmt_ = mt0 + fut / a.nkb, fkb = fut % a.nkb;
+            if (fmt_ < mt1) {
+              const SsTile f = ss_decode(a, fmt_);
+              if (a.avar == SS_A_KT) tma_prefetch_5d(&tmA, 0, 0, fkb * 8, f.blk, 0);
+              else if (a.mode == SS_NODES) tma_prefetch_4d(&tmA, fkb * SS_BK, f.node0, f.zt, 0);
+              else tma_prefetch_4d(f.side ? &tmA2 : &tmA, fkb * SS_BK, f.mtw * 128, f.z, 0);
+            }
           }
         }
       }
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
-    const uint32_t idesc = ss_idesc(NI, (uint32_t)a.afmt, (uint32_t)a.bfmt, 0, 0);
+    const uint32_t idesc = ss_idesc(BN, (uint32_t)a.afmt, (uint32_t)a.bfmt, 0, 0);
     int it = 0, lt = 0, bload = 0, gprev = -1;
     bool ok = true;
     for (int mt = mt0; mt < mt1 && ok; ++mt, ++lt) {
@@ -220,25 +274,34 @@ wf_ss_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         gprev = gb; ++bload;
       }
       tc_fence_after();
+      uint32_t issued = 0;   // instructions of this tile so far: chain = issued % NC, the first NC overwrite
       for (int kb = 0; kb < a.nkb; ++kb, ++it) {
         const int s = it % NST, ph = (it / NST) & 1;
         if (!mbar_wait(&full[s], ph)) { if (lane == 0) atomicExch(a.err, 55); ok = false; break; }
         tc_fence_after();
-        if (lane == 0) {
-          const uint32_t ahi = smem_u32(sA + s * SS_A_STAGE), bhi = smem_u32(sB + kb * BN * 64);
+        const bool leader = ss_elect();
+        if (leader) SS_TR(1, it);   // MMA warp: data landed
+        if (leader && (a.debug & 1)) {
+          umma_commit(&empty[s]);
+          if (kb == a.nkb - 1) {
+            umma_commit(&dfull[ds]);
+            const int gnext = mt + 1 < mt1 ? (a.b_per_group ? (mt + 1) / a.m_tiles_g : 0) : -2;
+            if (gnext != gb && gnext != -2) umma_commit(&bempty);
+          }
+        } else if (leader) {
+          const uint32_t ahi = smem_u32(sA + s * SS_A_STAGE), bhi = smem_u32(sB + kb * BN * 128);
 #pragma unroll
-          for (int k16 = 0; k16 < 2; ++k16) {
+          for (int k16 = 0; k16 < 4; ++k16) {
 #pragma unroll
             for (int p = 0; p < 3; ++p) {  // A_hi B_hi, A_lo B_hi, A_hi B_lo
               const uint32_t as = ahi + (p == 1 ? SS_A_PLANE : 0), bs = bhi + (p == 2 ? b_plane : 0);
-              const uint64_t ad = a.avar == SS_A_KT ? ss_desc(as + k16 * 4096, 2048, 128, 0) : ss_desc(as + k16 * 32, 16, 512, 4);
-#pragma unroll
-              for (int h = 0; h < NH; ++h)
-                ss_mma(tbase + ds * BN + h * 128, ad, ss_desc(bs + h * 8192 + k16 * 32, 16, 512, 4), idesc,
-                       (kb | k16 | p) ? 1u : 0u);
+              const uint64_t ad = a.avar == SS_A_KT ? ss_desc(as + k16 * 4096, 2048, 128, 0) : ss_desc(as + k16 * 32, 16, 1024, 2);
+              ss_mma(tbase + ds * DCOLS + (issued % NC) * BN, ad, ss_desc(bs + k16 * 32, 16, 1024, 2), idesc, issued >= NC ? 1u : 0u);
+              ++issued;
             }
           }
           umma_commit(&empty[s]);
+          SS_TR(2, it);   // MMA warp: stage issued
           if (kb == a.nkb - 1) {
             umma_commit(&dfull[ds]);
             // last tile of this group in my range: the resident B may be replaced once these MMAs have completed
@@ -274,8 +337,16 @@ wf_ss_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         for (int cc = 0; cc < BN; cc += 32) {
           uint32_t v[32];
           __syncwarp();
-          tmem_ld32(tlane + ds * BN + cc, v);
+          tmem_ld32(tlane + ds * DCOLS + cc, v);
           tmem_wait_ld();
+#pragma unroll
+          for (int ch = 1; ch < NC; ++ch) {   // add the other accumulation chains
+            uint32_t w[32];
+            tmem_ld32(tlane + ds * DCOLS + ch * BN + cc, w);
+            tmem_wait_ld();
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(w[j]));
+          }
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
             float4 o = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
@@ -286,7 +357,7 @@ wf_ss_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
               wf_drop4(dst, e4row + (unsigned)((cc + j) >> 2), m);
               o.x *= m[0]; o.y *= m[1]; o.z *= m[2]; o.w *= m[3];
             }
-            if (row < a.rpt) cblk[(long long)((cc + j) >> 2) * 128] = o;  // rows >= rpt of a node tile are padding
+            if (row < a.rpt && !(a.debug & 2)) cblk[(long long)((cc + j) >> 2) * 128] = o;  // rows >= rpt of a node tile are padding
           }
         }
       } else {
@@ -307,8 +378,16 @@ wf_ss_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           for (int half = 0; half < 2; ++half) {
             const int cc = c64 + 32 * half;
             uint32_t v[32];
-            tmem_ld32(tlane + ds * BN + cc, v);
+            tmem_ld32(tlane + ds * DCOLS + cc, v);
             tmem_wait_ld();
+#pragma unroll
+            for (int ch = 1; ch < NC; ++ch) {
+              uint32_t w[32];
+              tmem_ld32(tlane + ds * DCOLS + ch * BN + cc, w);
+              tmem_wait_ld();
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(w[j]));
+            }
 #pragma unroll
             for (int j = 0; j < 32; j += 8) {
               uint32_t hi[4], lo[4];
@@ -358,7 +437,7 @@ wf_ss_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tbase, 2 * BN);
+  if (warp == 1) tmem_dealloc(tbase, TCOLS);
 }
 
 
@@ -366,7 +445,8 @@ wf_ss_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
 // dW[g][512 gate rows][nh * 128] = sum over the task's (window, step, node tile) blocks of dG^T [X | H_prev]
 // (loss.backward() through nn.LSTM: dW_ih = dG^T x, dW_hh = sum_{t >= 1} dG[t]^T h[t-1]; train_hybrid_maml_v5.py:134,169).
 // Both operands are read MN-major straight from the activations' own layouts -- the contraction runs over ROWS:
-//   A   = dG, TB8 bf16 hi/lo: block [64 channel groups][128 rows][8]  -> [16 groups of this m tile][32 rows][16 B] per stage
+//   A   = dG, TB8 bf16 hi/lo: block [64 channel groups][128 rows][8]  -> [plane][16 groups of this m tile][64 rows][16 B]
+//         per stage, ONE load
 //   B_h = half h of the N range, either TB8 fp16 (h of the layer below at the same step, or this layer's h one step
 //         EARLIER: `shift`; step 0 has no such term and is skipped) or row-major fp16 features (SWIZZLE_128B boxes).
 // Rows >= rpt of a block are padding: never written by any kernel, zero since allocation, so they add nothing.
@@ -398,7 +478,7 @@ wf_wg_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, NST = a.nst;
   const int blocks_g = a.Bw * a.T * a.tpw;
   const int total = a.splits * a.G * 4;
-  const int kb_n = (a.rpt + 31) / 32;          // 32-row k-blocks that hold data
+  const int kb_n = (a.rpt + 63) / 64;          // 64-row k-blocks that hold data
   if (threadIdx.x == 0) {
     for (int s = 0; s < NST; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
     mbar_init(&dfull, 1); mbar_init(&dempty, 4);
@@ -429,22 +509,22 @@ wf_wg_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             int bytes = SS_A_STAGE;
             for (int h = 0; h < a.nh; ++h) if (!(a.bshift[h] && t == 0)) bytes += SS_A_STAGE;
             mbar_expect_tx(&full[s], bytes);
-            tma_load_5d(st, &tmA, &full[s], 0, kb, mtile * 16, blk, 0);
-            tma_load_5d(st + SS_A_PLANE, &tmA, &full[s], 0, kb, mtile * 16, blk, 1);
+            tma_load_5d(st, &tmA, &full[s], 0, 2 * kb, mtile * 16, blk, 0);   // rows [64 kb, +64), both planes
+            // B region behind A.  TB8 halves: [hi half 0][hi half 1][lo half 0][lo half 1] (16 KB each), so that the hi
+            // (lo) planes of both halves form ONE 256-column operand; row-major source: per 64 columns a box
+            // [plane][64 rows][128 B], 16 KB apart
+            uint8_t* sbase = st + SS_A_STAGE;
             for (int h = 0; h < a.nh; ++h) {
               if (a.bshift[h] && t == 0) continue;
               const CUtensorMap* m = h == 0 ? &tmB0 : &tmB1;
-              uint8_t* sb = st + SS_A_STAGE * (1 + h);
               if (a.bvar[h] == 0) {
                 const int bb = blk - a.bshift[h] * a.tpw;
-                tma_load_5d(sb, m, &full[s], 0, kb, a.bcol0[h], bb, 0);
-                tma_load_5d(sb + SS_A_PLANE, m, &full[s], 0, kb, a.bcol0[h], bb, 1);
-              } else {  // row-major [plane][(window, step)][node][C]: two 64-column boxes per plane
-                const int zt = blk / a.tpw, node = nt * a.rpt + kb * 32;
-                for (int j = 0; j < 2; ++j) {
-                  tma_load_4d(sb + j * 4096, m, &full[s], a.bcol0[h] + 64 * j, node, zt, 0);
-                  tma_load_4d(sb + SS_A_PLANE + j * 4096, m, &full[s], a.bcol0[h] + 64 * j, node, zt, 1);
-                }
+                tma_load_5d(sbase + h * SS_A_PLANE, m, &full[s], 0, 2 * kb, a.bcol0[h], bb, 0);
+                tma_load_5d(sbase + (a.nh + h) * SS_A_PLANE, m, &full[s], 0, 2 * kb, a.bcol0[h], bb, 1);
+              } else {
+                const int zt = blk / a.tpw, node = nt * a.rpt + kb * 64;
+                for (int j = 0; j < 2; ++j)
+                  tma_load_4d(sbase + (2 * h + j) * SS_A_PLANE, m, &full[s], a.bcol0[h] + 64 * j, node, zt, 0);
               }
             }
           }
@@ -454,6 +534,7 @@ wf_wg_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   } else if (warp == 1) {
     const uint32_t idesc = ss_idesc(128, (uint32_t)a.afmt, (uint32_t)a.bfmt, 1, 1);
     const uint32_t idesc1 = ss_idesc(16, (uint32_t)a.afmt, (uint32_t)a.bfmt, 1, 1);
+    const uint32_t idesc2 = ss_idesc(256, (uint32_t)a.afmt, (uint32_t)a.bfmt, 1, 1);
     const uint64_t odesc = ss_desc(smem_u32(ones), 128, 256, 0);
     int it = 0, lt = 0;
     bool ok = true;
@@ -469,34 +550,58 @@ wf_wg_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           const int s = it % NST, ph = (it / NST) & 1;
           if (!mbar_wait(&full[s], ph)) { if (lane == 0) atomicExch(a.err, 63); ok = false; break; }
           tc_fence_after();
-          if (lane == 0) {
-            const uint32_t as = smem_u32(smem + s * STAGE);
-            const int nk16 = min(2, (a.rpt - kb * 32 + 15) / 16);
+          if (ss_elect()) {
+            SS_TR(1, it);
+            const uint32_t as = smem_u32(smem + s * STAGE), bs = as + SS_A_STAGE;
+            const int nk16 = min(4, (a.rpt - kb * 64 + 15) / 16);
+            // both halves in ONE 256-column instruction per product when both are present (5 instructions per K step with
+            // the bias products instead of 8): an MN-major operand costs ~145 clk per instruction whatever its width
+            const bool both = a.nh == 2 && !((a.bshift[0] || a.bshift[1]) && t == 0);
+            const int hsel = (a.nh == 2 && a.bshift[0] && t == 0) ? 1 : 0;   // the half that is present when only one is
+            const bool any = both || !(a.bshift[hsel] && t == 0);
             for (int k16 = 0; k16 < nk16; ++k16) {
-              const uint64_t ahi = ss_desc(as + k16 * 256, 128, 512, 0), alo = ss_desc(as + SS_A_PLANE + k16 * 256, 128, 512, 0);
-              for (int h = 0; h < a.nh; ++h) {
-                if (a.bshift[h] && t == 0) continue;
-                const uint32_t bs = as + SS_A_STAGE * (1 + h);
-                uint64_t bhi, blo;
-                if (a.bvar[h] == 0) { bhi = ss_desc(bs + k16 * 256, 128, 512, 0); blo = ss_desc(bs + SS_A_PLANE + k16 * 256, 128, 512, 0); }
-                else { bhi = ss_desc(bs + k16 * 2048, 4096, 1024, 2); blo = ss_desc(bs + SS_A_PLANE + k16 * 2048, 4096, 1024, 2); }
-                ss_mma(tbase + h * 128, ahi, bhi, idesc, acc[h]);
-                ss_mma(tbase + h * 128, alo, bhi, idesc, 1u);
-                ss_mma(tbase + h * 128, ahi, blo, idesc, 1u);
-                acc[h] = 1u;
+              // MN-major, no swizzle: [16 channel groups][64 rows][16 B] -> groups 1024 B apart (SBO), 8-row groups 128 B (LBO)
+              const uint64_t ahi = ss_desc(as + k16 * 256, 128, 1024, 0), alo = ss_desc(as + SS_A_PLANE + k16 * 256, 128, 1024, 0);
+              uint64_t bhi, blo;
+              if (a.bvar[0] == 0) {   // TB8: hi planes of the halves back to back, then the lo planes
+                bhi = ss_desc(bs + (both ? 0 : hsel) * SS_A_PLANE + k16 * 256, 128, 1024, 0);
+                blo = ss_desc(bs + (a.nh + (both ? 0 : hsel)) * SS_A_PLANE + k16 * 256, 128, 1024, 0);
+              } else {                // row-major source: 64-column boxes [plane][64 rows][128 B] 16 KB apart, SWIZZLE_128B
+                bhi = ss_desc(bs + (both ? 0 : 2 * hsel) * SS_A_PLANE + k16 * 2048, 16384, 1024, 2);
+                blo = ss_desc(bs + (both ? 0 : 2 * hsel) * SS_A_PLANE + 8192 + k16 * 2048, 16384, 1024, 2);
               }
-              if (a.bias_part != nullptr) {
-                ss_mma(tbase + 256, ahi, odesc, idesc1, acc1);   // row sums of dG^T: the bias gradients
+              if (any) {
+                const uint32_t d = tbase + (both ? 0 : hsel * 128), id = both ? idesc2 : idesc;
+                if (both && acc[0] == acc[1]) {
+                  ss_mma(d, ahi, bhi, id, acc[0]);
+                  acc[0] = acc[1] = 1u;
+                } else if (both) {
+                  // one half has products already, the other (skipped at step 0) must be overwritten: two instructions, once
+                  const uint64_t bh1 = a.bvar[0] == 0 ? ss_desc(bs + SS_A_PLANE + k16 * 256, 128, 1024, 0)
+                                                      : ss_desc(bs + 2 * SS_A_PLANE + k16 * 2048, 16384, 1024, 2);
+                  ss_mma(d, ahi, bhi, idesc, acc[0]);
+                  ss_mma(d + 128, ahi, bh1, idesc, acc[1]);
+                  acc[0] = acc[1] = 1u;
+                } else {
+                  ss_mma(d, ahi, bhi, id, acc[hsel]);
+                  acc[hsel] = 1u;
+                }
+                ss_mma(d, alo, bhi, id, 1u);
+                ss_mma(d, ahi, blo, id, 1u);
+              }
+              if (a.bias_part != nullptr) {   // row sums of dG^T: the bias gradients
+                ss_mma(tbase + 256, ahi, odesc, idesc1, acc1);
                 ss_mma(tbase + 256, alo, odesc, idesc1, 1u);
                 acc1 = 1u;
               }
             }
+            SS_TR(2, it);
             umma_commit(&empty[s]);
           }
           __syncwarp();
         }
       }
-      if (lane == 0 && ok) umma_commit(&dfull);
+      if (ss_elect() && ok) umma_commit(&dfull);
       __syncwarp();
     }
   } else {
@@ -581,34 +686,38 @@ namespace {
 
 int ss_dtype(int fmt) { return fmt == 0 ? 1 : 2; }   // wf_encode_tensor_map: 1 = f16, 2 = bf16
 
-// row-major hl16 [2 planes][Z][rows][C]: K-major operand boxes {32 k, box_rows} (SWIZZLE_64B)
+// row-major hl16 [2 planes][Z][rows][C]: K-major operand boxes {64 k, box_rows, both planes} (SWIZZLE_128B)
 int map_rows_k(CUtensorMap* m, const void* base, uint64_t C, uint64_t rows, uint64_t Z, uint64_t plane, uint32_t box_rows, int fmt) {
   uint64_t dims[4] = {C, rows, Z, 2};
   uint64_t str[3] = {C * 2, rows * C * 2, plane * 2};
-  uint32_t box[4] = {SS_BK, box_rows, 1, 1};
-  return wf_encode_tensor_map(m, base, 4, dims, str, box, 2, ss_dtype(fmt));
+  uint32_t box[4] = {SS_BK, box_rows, 1, 2};
+  return wf_encode_tensor_map(m, base, 4, dims, str, box, 1, ss_dtype(fmt));
 }
-// the same tensor as an MN-major operand (rows = K): boxes {64 columns, 32 rows} (SWIZZLE_128B); also the GCN output map
-int map_rows_mn(CUtensorMap* m, const void* base, uint64_t C, uint64_t rows, uint64_t Z, uint64_t plane, int fmt) {
+// the same tensor as an MN-major operand (rows = K): boxes {64 columns, box_rows, box_planes} (SWIZZLE_128B);
+// {64, 32, 1, 1} is also the GCN epilogue's store box
+int map_rows_mn(CUtensorMap* m, const void* base, uint64_t C, uint64_t rows, uint64_t Z, uint64_t plane, int fmt,
+                uint32_t box_rows = 32, uint32_t box_planes = 1) {
   uint64_t dims[4] = {C, rows, Z, 2};
   uint64_t str[3] = {C * 2, rows * C * 2, plane * 2};
-  uint32_t box[4] = {64, 32, 1, 1};
+  uint32_t box[4] = {64, box_rows, 1, box_planes};
   return wf_encode_tensor_map(m, base, 4, dims, str, box, 1, ss_dtype(fmt));
 }
 // TB8 [2 planes][blocks][C/8][128 rows][8]: the 128 x 8 elements of a channel group are folded as {256, 4}.
-// fold = 4, groups = 4: a K-major [128 rows][32 k] box; fold = 1, groups = 16: an MN-major [128 channels][32 rows] box
-int map_tb8(CUtensorMap* m, const void* base, uint64_t C, uint64_t blocks, uint64_t plane, uint32_t fold, uint32_t groups, int fmt) {
+// fold = 4, groups = 8: a K-major [128 rows][64 k] box; fold = 2, groups = 16: an MN-major [128 channels][64 rows] box;
+// both planes in one box
+int map_tb8(CUtensorMap* m, const void* base, uint64_t C, uint64_t blocks, uint64_t plane, uint32_t fold, uint32_t groups, int fmt,
+            uint32_t box_planes = 2) {
   uint64_t dims[5] = {256, 4, C / 8, blocks, 2};
   uint64_t str[4] = {512, 2048, C * 256, plane * 2};
-  uint32_t box[5] = {256, fold, groups, 1, 1};
+  uint32_t box[5] = {256, fold, groups, 1, box_planes};
   return wf_encode_tensor_map(m, base, 5, dims, str, box, 0, ss_dtype(fmt));
 }
-// weights [G][N][K] (one plane): resident-B boxes {32 k, bn rows} (SWIZZLE_64B)
+// weights [G][N][K] (one plane): resident-B boxes {64 k, bn rows} (SWIZZLE_128B)
 int map_w(CUtensorMap* m, const void* base, uint64_t K, uint64_t N, uint64_t G, uint64_t ld, uint64_t gstride, uint32_t bn, int fmt) {
   uint64_t dims[3] = {K, N, G};
   uint64_t str[2] = {ld * 2, gstride * 2};
   uint32_t box[3] = {SS_BK, bn, 1};
-  return wf_encode_tensor_map(m, base, 3, dims, str, box, 2, ss_dtype(fmt));
+  return wf_encode_tensor_map(m, base, 3, dims, str, box, 1, ss_dtype(fmt));
 }
 
 int ss_sms() {
@@ -624,11 +733,17 @@ int ss_sms() {
 template <int BN>
 int ss_launch_bn(const CUtensorMap& tmA, const CUtensorMap& tmA2, const CUtensorMap& tmBhi, const CUtensorMap& tmBlo,
                  const CUtensorMap& tmOut, const CUtensorMap& tmOut2, SsArgs& a, cudaStream_t st) {
-  a.nst = a.epi == SS_E_HL ? 4 : 6;
+  a.nst = a.epi == SS_E_HL ? 2 : 3;
+  static const int dbg = getenv("WF_SS_DEBUG") ? atoi(getenv("WF_SS_DEBUG")) : 0;
+  a.debug = dbg;
+  static const int pf_env = getenv("WF_SS_PF") ? atoi(getenv("WF_SS_PF")) : 0;
+  a.pf = pf_env;
+  static const int nst_env = getenv("WF_SS_NST") ? atoi(getenv("WF_SS_NST")) : 0;
+  if (nst_env > 0 && nst_env < a.nst) a.nst = nst_env;
   const int smem = SS_B_BYTES + a.nst * SS_A_STAGE + (a.epi == SS_E_HL ? SS_STG_BYTES : 0) + 1024;
   static bool configured = false;
   if (!configured) {
-    const int mx = SS_B_BYTES + 6 * SS_A_STAGE + 1024;
+    const int mx = SS_B_BYTES + 3 * SS_A_STAGE + 1024;
     if (cudaFuncSetAttribute(wf_ss_kernel<BN, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx) != cudaSuccess ||
         cudaFuncSetAttribute(wf_ss_kernel<BN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx) != cudaSuccess)
       return wf_fail(WF_ECUDA, "ss kernel: cannot raise dynamic shared memory to %d", mx);
@@ -662,13 +777,14 @@ int wf_ss_launch_nodes(int bn, int avar, const void* A16, long long a_plane, int
                        int ldb, long long b_gstride, int Ntot, int bfmt, const float* bias, const float* bias2,
                        long long bias_gstride, float* C, int T, int Nn, int Bw, int G, const DropCfg* drop, int* err,
                        cudaStream_t st) {
-  WF_REQUIRE(K % SS_BK == 0 && Ntot % bn == 0 && ldb % 8 == 0, "ss_nodes: K=%d must be a multiple of 32, N=%d of %d", K, Ntot, bn);
+  WF_REQUIRE(K % 8 == 0 && (avar == SS_A_KS || K % SS_BK == 0) && Ntot % bn == 0 && ldb % 8 == 0,
+             "ss_nodes: K=%d must be a multiple of 8 (64 for TB8 operands), N=%d of %d", K, Ntot, bn);
   WF_REQUIRE(((uintptr_t)A16 | (uintptr_t)Bhi | (uintptr_t)Blo | (uintptr_t)C) % 16 == 0, "ss_nodes: pointers must be 16-byte aligned");
   const int tpw = wf_cdiv(Nn, 128);
   const long long ZT = (long long)G * Bw * T;
   CUtensorMap tmA, tmBhi, tmBlo;
   int rc;
-  if (avar == SS_A_KT) rc = map_tb8(&tmA, A16, K, ZT * tpw, a_plane, 4, 4, afmt);
+  if (avar == SS_A_KT) rc = map_tb8(&tmA, A16, K, ZT * tpw, a_plane, 4, 8, afmt);
   else rc = map_rows_k(&tmA, A16, K, Nn, ZT, a_plane, 128, afmt);
   if (rc) return rc;
   if ((rc = map_w(&tmBhi, Bhi, K, Ntot, G, ldb, G > 1 ? b_gstride : (long long)Ntot * ldb, bn, bfmt))) return rc;
@@ -676,7 +792,7 @@ int wf_ss_launch_nodes(int bn, int avar, const void* A16, long long a_plane, int
   SsArgs a;
   memset(&a, 0, sizeof(a));
   a.mode = SS_NODES; a.avar = avar; a.epi = SS_E_TB4; a.n_parts = Ntot / bn; a.m_tiles_g = Bw * T * tpw; a.G = G;
-  a.nkb = K / SS_BK; a.b_per_group = G > 1 ? 1 : 0; a.afmt = afmt; a.bfmt = bfmt;
+  a.nkb = (K + SS_BK - 1) / SS_BK; a.b_per_group = G > 1 ? 1 : 0; a.afmt = afmt; a.bfmt = bfmt;
   a.T = T; a.Nn = Nn; a.Bw = Bw; a.tpw = tpw; a.rpt = wf_tile_rows(Nn);
   a.C = C; a.c_cols = Ntot; a.bias = bias; a.bias2 = bias2; a.bias_gstride = bias_gstride; a.err = err;
   if (drop != nullptr) a.drop = *drop;
@@ -695,10 +811,10 @@ int wf_ss_launch_wgrad(const void* dg16, long long dg_plane, int nh, const void*
   const long long blocks = (long long)G * blocks_g, ZT = (long long)G * Bw * T;
   CUtensorMap tmA, tmB[2];
   int rc;
-  if ((rc = map_tb8(&tmA, dg16, 512, blocks, dg_plane, 1, 16, 1))) return rc;
+  if ((rc = map_tb8(&tmA, dg16, 512, blocks, dg_plane, 2, 16, 1))) return rc;
   for (int h = 0; h < nh; ++h) {
-    if (bvar[h] == 0) rc = map_tb8(&tmB[h], bsrc[h], bC[h], blocks, bplane[h], 1, 16, 1);
-    else rc = map_rows_mn(&tmB[h], bsrc[h], bC[h], Nn, ZT, bplane[h], 1);
+    if (bvar[h] == 0) rc = map_tb8(&tmB[h], bsrc[h], bC[h], blocks, bplane[h], 2, 16, 1, 1);   // one plane per load
+    else rc = map_rows_mn(&tmB[h], bsrc[h], bC[h], Nn, ZT, bplane[h], 1, 64, 2);
     if (rc) return rc;
   }
   if (nh == 1) tmB[1] = tmB[0];
@@ -717,12 +833,12 @@ int wf_ss_launch_wgrad(const void* dg16, long long dg_plane, int nh, const void*
   a.G = G; a.Bw = Bw; a.T = T; a.tpw = tpw; a.rpt = wf_tile_rows(Nn); a.Nn = Nn;
   a.bps = wf_cdiv(blocks_g, best); a.splits = wf_cdiv(blocks_g, a.bps); a.nh = nh;
   for (int h = 0; h < nh; ++h) { a.bvar[h] = bvar[h]; a.bshift[h] = bshift[h]; a.bcol0[h] = bvar[h] == 0 ? bcol0[h] / 8 : bcol0[h]; }
-  a.afmt = 1; a.bfmt = 1; a.nst = nh == 2 ? 4 : 6;   // kind::f16 takes ONE format for both operands: bf16 (dG's range)
+  a.afmt = 1; a.bfmt = 1; a.nst = nh == 2 ? 2 : 3;   // kind::f16 takes ONE format for both operands: bf16 (dG's range)
   a.part = part; a.bias_part = db1 != nullptr ? part + (size_t)a.splits * G * 512 * ncol : nullptr; a.err = err;
   const int smem = a.nst * SS_A_STAGE * (1 + nh) + 1024 + 1024;
   static bool configured = false;
   if (!configured) {
-    if (cudaFuncSetAttribute(wf_wg_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * SS_A_STAGE * 3 + 2048) != cudaSuccess)
+    if (cudaFuncSetAttribute(wf_wg_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * SS_A_STAGE * 3 + 2048) != cudaSuccess)
       return wf_fail(WF_ECUDA, "wg kernel: cannot raise dynamic shared memory");
     configured = true;
   }
@@ -825,7 +941,7 @@ extern "C" int wf_gcn_layer_fwd_ss(const float* X32, const long long* x_win_off,
   WF_REQUIRE(agg_rows >= 0 && agg_rows % 128 == 0 && (agg_rows == 0 || (rowptr != nullptr && side16 != nullptr)),
              "gcn_layer_fwd_ss: agg_rows=%d must be a multiple of 128 and comes with the CSR and the side buffer", agg_rows);
   WF_REQUIRE(p_drop >= 0.f && p_drop < 1.f && (p_drop == 0.f || rng != nullptr), "gcn_layer_fwd_ss: bad dropout arguments");
-  WF_REQUIRE((long long)128 * ((Cin + 31) / 32 * 32) * 4 <= SS_B_BYTES, "gcn_layer_fwd_ss: Cin=%d too wide for a resident weight slice", Cin);
+  WF_REQUIRE((long long)128 * ((Cin + 63) / 64 * 64) * 4 <= SS_B_BYTES, "gcn_layer_fwd_ss: Cin=%d too wide for a resident weight slice", Cin);
   cudaStream_t st = (cudaStream_t)stream;
   const long long Z = (long long)G * Bw, plane = Z * R * Cin;
   const uint16_t* A16 = (const uint16_t*)X16;
@@ -908,3 +1024,9 @@ extern "C" int wf_ss_wgrad(const void* dg16, long long dg_plane, int nh, const v
   return wf_ss_launch_wgrad(dg16, dg_plane, nh, src, plane, var, shift, col0, ch, T, Nn, Bw, G, part, (size_t)part_floats, dst0,
                             ld0, w0, dst1, ld1, w1, db, nullptr, gstride, err, (cudaStream_t)stream);
 }
+
+#ifdef WF_SS_TRACE
+extern "C" int wf_ss_trace_read(long long* host) {
+  return (int)cudaMemcpyFromSymbol(host, wf_ss_trace_buf, sizeof(long long) * 4 * 256);
+}
+#endif
