@@ -646,7 +646,7 @@ def run_gpu(args, rank, local, world):
         sampler.start()
     ms, loss = timed_steps(tr, args.steps, args.warmup, world, sync_loss=False)
     clocks = sampler.stop() if sampler else None
-    launches_per_step = tr.launches_per_step + 2  # + sumsq + AdamW kernels outside the graph
+    launches_per_step = tr.launches_per_step + 2  # + the sumsq and AdamW kernels of the outer update (graph nodes too)
     stages = stage_breakdown(tr) if rank == 0 else None
     kernel_ms = time_recurrence_kernels(tr) if rank == 0 else None
     del tr

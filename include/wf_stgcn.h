@@ -300,7 +300,8 @@ int wf_gcn_layer_fwd_ss(const float* X32, const long long* x_win_off, const void
 /* The two SS-mode kernels on operands given as plain 16-bit planes (test / general entry points).
  * wf_ss_nodes_gemm: C (TB4 fp32: per (window, step, node tile) a block [Ntot/4][128 rows][4]) = A W^T (+ bias + bias2);
  *   avar 0: A16 row-major planes [2][G*Bw*T][Nn][K], 1: TB8 planes; W16 hi / lo [G][Ntot][K]; bn = 64 / 128 / 256 columns
- *   per CTA with bn * K <= 32768 (the weight slice is resident in shared memory); afmt / bfmt 0 fp16, 1 bf16.
+ *   per CTA with bn * K / k_parts <= 32768 (the weight slice is resident in shared memory); afmt / bfmt 0 fp16, 1 bf16;
+ *   k_parts > 1 deals the K range over that many CTAs whose partial products are added into the (cleared) output.
  * wf_ss_wgrad: dst0 [G][512][w0] (+ dst1 [G][512][w1], db [G][512]) = dG^T [B0 | B1] summed over all blocks of a group;
  *   dg16: TB8 bf16 planes with 512 channels; half h of 128 columns: bvar 0 = TB8 bf16 planes with bC channels (bcol0:
  *   first channel), 1 = row-major bf16 planes [2][G*Bw*T][Nn][bC] (bcol0: first column); bshift 1 = pair dG of step t
@@ -308,7 +309,7 @@ int wf_gcn_layer_fwd_ss(const float* X32, const long long* x_win_off, const void
 int wf_ss_nodes_gemm(int bn, int avar, const void* A16, long long a_plane, int K, int afmt, const void* W16_hi,
                      const void* W16_lo, long long w_group_stride, int Ntot, int bfmt, const float* bias,
                      const float* bias2, long long bias_group_stride, float* C, int T, int Nn, int Bw, int G,
-                     int* err, void* stream);
+                     int k_parts, int* err, void* stream);
 int wf_ss_wgrad(const void* dg16, long long dg_plane, int nh, const void* b0, long long b0_plane, int b0var,
                 int b0shift, int b0col0, int b0C, const void* b1, long long b1_plane, int b1var, int b1shift,
                 int b1col0, int b1C, int T, int Nn, int Bw, int G, float* part, long long part_floats, float* dst0,

@@ -46,10 +46,11 @@ def from_tb4(c, ZT, N, C):
 
 
 @pytest.mark.parametrize("avar", [0, 1])
-@pytest.mark.parametrize("bn,K,Ntot,fmt", [(128, 256, 512, 0), (256, 128, 512, 0), (64, 512, 128, 1), (128, 24, 256, 0),
-                                           (256, 64, 256, 1)])
+@pytest.mark.parametrize("bn,K,Ntot,fmt,kp", [(128, 256, 512, 0, 1), (256, 128, 512, 0, 1), (64, 512, 128, 1, 1), (128, 24, 256, 0, 1),
+                                              (256, 64, 256, 1, 1), (128, 512, 128, 1, 2), (128, 256, 256, 0, 2)])
 @pytest.mark.parametrize("N,T,G,Bw", [(441, 3, 2, 2), (128, 2, 1, 1), (57, 1, 3, 1)])
-def test_ss_nodes_gemm_every_a_layout(avar, bn, K, Ntot, fmt, N, T, G, Bw):
+def test_ss_nodes_gemm_every_a_layout(avar, bn, K, Ntot, fmt, kp, N, T, G, Bw):
+    """kp = 2: the K range split over two CTAs per row-tile range, partial products added into the cleared output."""
     if avar == 1 and K % 64:
         pytest.skip("TB8 operands come in whole 64-wide k-blocks (LSTM widths)")
     torch.manual_seed(K + N)
@@ -67,7 +68,7 @@ def test_ss_nodes_gemm_every_a_layout(avar, bn, K, Ntot, fmt, N, T, G, Bw):
     C = torch.full((ZT * tpw * Ntot * 128,), float("nan"), device="cuda")
     err = torch.zeros(1, dtype=torch.int32, device="cuda")
     _lib.call("wf_ss_nodes_gemm", bn, avar, _lib.ptr(a16), a16.shape[1], K, fmt, _lib.ptr(w16[0]), _lib.ptr(w16[1]), Ntot * K,
-              Ntot, fmt, _lib.ptr(b1), _lib.ptr(b2), Ntot, _lib.ptr(C), T, N, Bw, G, _lib.ptr(err), _lib.stream_ptr())
+              Ntot, fmt, _lib.ptr(b1), _lib.ptr(b2), Ntot, _lib.ptr(C), T, N, Bw, G, kp, _lib.ptr(err), _lib.stream_ptr())
     torch.cuda.synchronize()
     assert int(err.item()) == 0, f"pipeline error code {int(err.item())}"
     got = from_tb4(C, ZT, N, Ntot).double()

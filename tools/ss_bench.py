@@ -28,15 +28,17 @@ def timeit(fn, reps=10):
     return e0.elapsed_time(e1) / reps * 1e3
 
 
-def nodes(name, bn, avar, K, Ntot, fmt):
+def nodes(name, bn, avar, K, Ntot, fmt, kp=1):
     if avar == 1:
         a16 = torch.zeros(2, blocks * K * 128, dtype=torch.int16, device="cuda")
     else:
         a16 = torch.zeros(2, G * Bw * T * N * K, dtype=torch.int16, device="cuda")
     w = torch.zeros(2, G * Ntot * K, dtype=torch.int16, device="cuda")
     C = torch.empty(blocks * Ntot * 128, device="cuda")
+    bias = torch.zeros(G, 2, Ntot, device="cuda") if os.environ.get("BIAS") else None
+    b1, b2 = (_lib.ptr(bias[0, 0]), _lib.ptr(bias[0, 1])) if bias is not None else (None, None)
     us = timeit(lambda: _lib.call("wf_ss_nodes_gemm", bn, avar, _lib.ptr(a16), a16.shape[1], K, fmt, _lib.ptr(w[0]), _lib.ptr(w[1]),
-                                  Ntot * K, Ntot, fmt, None, None, 0, _lib.ptr(C), T, N, Bw, G, _lib.ptr(err), _lib.stream_ptr()))
+                                  Ntot * K, Ntot, fmt, b1, b2, 2 * Ntot, _lib.ptr(C), T, N, Bw, G, kp, _lib.ptr(err), _lib.stream_ptr()))
     rows = G * Bw * T * N
     byts = rows * (K * 4 + Ntot * 4)
     print(f"{name:28s} bn={bn:3d} K={K:3d} N={Ntot:3d}: {us:7.1f} us  {byts / us / 1e3:7.0f} GB/s algorithmic")
@@ -45,6 +47,7 @@ def nodes(name, bn, avar, K, Ntot, fmt):
 nodes("P0 (feats -> gates)", 128, 0, 256, 512, 0)
 nodes("P1 (h -> gates)", 256, 1, 128, 512, 0)
 nodes("dX (dG -> dh)", 64, 1, 512, 128, 1)
+nodes("dX, K split over 2 CTAs", 128, 1, 512, 128, 1, 2)
 # weight gradients
 dg = torch.zeros(2, blocks * 512 * 128, dtype=torch.int16, device="cuda")
 h = torch.zeros(2, blocks * 128 * 128, dtype=torch.int16, device="cuda")

@@ -24,13 +24,14 @@ if which == "wg":
                   128, T, N, Bw, G, _lib.ptr(part), part.numel(), _lib.ptr(buf), 128, 128, _lib.ptr(buf[0, 65536:]), 128, 128,
                   _lib.ptr(buf[0, 131072:]), buf.shape[1], _lib.ptr(err), _lib.stream_ptr())
 else:
-    bn, avar, K, Ntot, fmt = {"dx": (64, 1, 512, 128, 1), "p1": (256, 1, 128, 512, 0), "p0": (128, 0, 256, 512, 0)}[which]
+    bn, avar, K, Ntot, fmt, kp = {"dx": (64, 1, 512, 128, 1, 1), "dx2": (128, 1, 512, 128, 1, 2), "p1": (256, 1, 128, 512, 0, 1),
+                                  "p0": (128, 0, 256, 512, 0, 1)}[which]
     a16 = torch.zeros(2, blocks * K * 128 if avar else G * T * N * K, dtype=torch.int16, device="cuda")
     w = torch.zeros(2, G * Ntot * K, dtype=torch.int16, device="cuda")
     Cm = torch.empty(blocks * Ntot * 128, device="cuda")
     for _ in range(3):
         _lib.call("wf_ss_nodes_gemm", bn, avar, _lib.ptr(a16), a16.shape[1], K, fmt, _lib.ptr(w[0]), _lib.ptr(w[1]), Ntot * K, Ntot,
-                  fmt, None, None, 0, _lib.ptr(Cm), T, N, Bw, G, _lib.ptr(err), _lib.stream_ptr())
+                  fmt, None, None, 0, _lib.ptr(Cm), T, N, Bw, G, kp, _lib.ptr(err), _lib.stream_ptr())
 torch.cuda.synchronize()
 buf = (C.c_longlong * 1024)()
 lib.wf_ss_trace_read.argtypes = [C.c_void_p]

@@ -87,7 +87,7 @@ SIGNATURES = {
                                   c_i, c_i, c_i, c_p, c_p, c_f, c_p, c_i, c_p, c_p]),
     "wf_join16": (c_i, [c_p, c_p, c_ll, c_i, c_p, c_p]),
     "wf_ss_nodes_gemm": (c_i, [c_i, c_i, c_p, c_ll, c_i, c_i, c_p, c_p, c_ll, c_i, c_i, c_p, c_p, c_ll, c_p, c_i, c_i, c_i, c_i,
-                               c_p, c_p]),
+                               c_i, c_p, c_p]),
     "wf_ss_wgrad": (c_i, [c_p, c_ll, c_i, c_p, c_ll, c_i, c_i, c_i, c_i, c_p, c_ll, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_i,
                           c_p, c_ll, c_p, c_i, c_i, c_p, c_i, c_i, c_p, c_ll, c_p, c_p]),
 }

@@ -19,6 +19,8 @@
 //   TB8              [2 planes][block][K/8][128 rows][8]     LSTM h (fp16), dG (bf16); block = (window, step, node tile):
 //                    no-swizzle canonical layouts -- K-major for the projections / dX (rows = M), and the SAME bytes
 //                    MN-major for the weight gradients (rows = K), so nothing is ever transposed in memory.
+#include <type_traits>
+
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 
@@ -55,6 +57,8 @@ struct SsArgs {
   int m_tiles_g, G;     // row tiles per group, groups
   int nkb;              // K / 64 (rounded up: TMA zero-fills beyond K)
   int nst;              // A ring depth
+  int k_parts;          // >= 1: the K range is dealt over this many CTAs per row-tile range (nkb = k-blocks of ONE part); their
+                        // partial products meet in a zeroed TB4 output through red.global.add (two addends: order-free)
   int b_per_group;      // weights differ per group: reload the resident B when a CTA's range crosses into the next group
   int afmt, bfmt;       // 0 fp16, 1 bf16
   // ROWS: windows of R rows; the first agg_rows rows of every window come from the side buffer (aggregated rows)
@@ -184,7 +188,7 @@ wf_ss_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   // (measured: 150-180 clk per instruction for N = 64 and N = 128 alike), so the products of a tile are dealt round-robin
   // over NC independent accumulators that the epilogue adds up: N = 64: 3 chains, N = 128: 2, N = 256 (128 clk of work
   // per instruction anyway): 1.  TMEM: 2 stages x NC x BN columns.
-  constexpr int NC = BN == 64 ? 3 : (BN == 128 ? 2 : 1);
+  constexpr int NC = 1;   // (independent accumulation chains were measured neutral: the ring, not the MMA pipe, binds)
   constexpr int DCOLS = NC * BN;                // columns of one accumulator stage
   constexpr int TCOLS = 512;
   extern __shared__ uint8_t smem_raw[];
@@ -198,7 +202,9 @@ wf_ss_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   const int NST = a.nst;
 
   // this CTA: one n-part, a contiguous range of row tiles
-  const int npart = blockIdx.x % a.n_parts, slot = blockIdx.x / a.n_parts, slots = gridDim.x / a.n_parts;
+  const int parts = a.n_parts * a.k_parts, pidx = blockIdx.x % parts;
+  const int npart = pidx % a.n_parts, kpart = pidx / a.n_parts, slot = blockIdx.x / parts, slots = gridDim.x / parts;
+  const int kb0 = kpart * a.nkb;
   const int total_mt = a.m_tiles_g * a.G;
   const int per = (total_mt + slots - 1) / slots;
   const int mt0 = slot * per, mt1 = min(total_mt, mt0 + per);
@@ -229,8 +235,8 @@ wf_ss_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           if (bload > 0 && !mbar_wait(&bempty, (bload - 1) & 1)) { atomicExch(a.err, 51); break; }
           mbar_expect_tx(&bfull, 2 * b_plane);
           for (int kb = 0; kb < a.nkb; ++kb) {
-            tma_load_3d(sB + kb * BN * 128, &tmBhi, &bfull, kb * SS_BK, n0, gb);
-            tma_load_3d(sB + b_plane + kb * BN * 128, &tmBlo, &bfull, kb * SS_BK, n0, gb);
+            tma_load_3d(sB + kb * BN * 128, &tmBhi, &bfull, (kb0 + kb) * SS_BK, n0, gb);
+            tma_load_3d(sB + b_plane + kb * BN * 128, &tmBlo, &bfull, (kb0 + kb) * SS_BK, n0, gb);
           }
           gprev = gb; ++bload;
         }
@@ -242,13 +248,13 @@ wf_ss_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           mbar_expect_tx(&full[s], SS_A_STAGE);
           // one load per stage: both planes of the [128 rows x 64 k] tile
           if (a.avar == SS_A_KT)            // TB8 block: [plane][block][K/8][128 rows][8]
-            tma_load_5d(st, &tmA, &full[s], 0, 0, kb * 8, t.blk, 0);
+            tma_load_5d(st, &tmA, &full[s], 0, 0, (kb0 + kb) * 8, t.blk, 0);
           else if (a.mode == SS_NODES)      // row-major [plane][(window, step)][node][K]
-            tma_load_4d(st, &tmA, &full[s], kb * SS_BK, t.node0, t.zt, 0);
+            tma_load_4d(st, &tmA, &full[s], (kb0 + kb) * SS_BK, t.node0, t.zt, 0);
           else                              // row-major [plane][window][row][K]; leading rows from the side buffer
-            tma_load_4d(st, t.side ? &tmA2 : &tmA, &full[s], kb * SS_BK, t.mtw * 128, t.z, 0);
+            tma_load_4d(st, t.side ? &tmA2 : &tmA, &full[s], (kb0 + kb) * SS_BK, t.mtw * 128, t.z, 0);
           if (a.pf > 0) {   // the ring is three loads deep and a load from DRAM takes ~2,700 clk: warm L2 `pf` stages ahead
-            const int fut = (mt - mt0) * a.nkb + kb + a.pf, fmt_ = mt0 + fut / a.nkb, fkb = fut % a.nkb;
+            const int fut = (mt - mt0) * a.nkb + kb + a.pf, fmt_ = mt0 + fut / a.nkb, fkb = kb0 + fut % a.nkb;
             if (fmt_ < mt1) {
               const SsTile f = ss_decode(a, fmt_);
               if (a.avar == SS_A_KT) tma_prefetch_5d(&tmA, 0, 0, fkb * 8, f.blk, 0);
@@ -324,8 +330,8 @@ wf_ss_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       const int ds = lt & 1;
       if (!mbar_wait(&dfull[ds], (lt >> 1) & 1)) { if (lane == 0) atomicExch(a.err, 56); ok = false; break; }
       tc_fence_after();
-      const float* b1 = a.bias ? a.bias + t.g * a.bias_gstride + n0 : nullptr;
-      const float* b2 = a.bias2 ? a.bias2 + t.g * a.bias_gstride + n0 : nullptr;
+      const float* b1 = a.bias && kpart == 0 ? a.bias + t.g * a.bias_gstride + n0 : nullptr;
+      const float* b2 = a.bias2 && kpart == 0 ? a.bias2 + t.g * a.bias_gstride + n0 : nullptr;
       DropState dst;
       if (DROP) dst = wf_drop_state(a.drop);
       if (a.epi == SS_E_TB4) {
@@ -333,20 +339,10 @@ wf_ss_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         float4* cblk = reinterpret_cast<float4*>(a.C) + ((long long)t.blk * (a.c_cols >> 2) + (n0 >> 2)) * 128 + row;
         unsigned long long e4row = 0;
         if (DROP) e4row = (((unsigned long long)t.zt * a.Nn + (unsigned)(t.node0 + row)) * (unsigned)a.c_cols + (unsigned)n0) >> 2;
-#pragma unroll 1
-        for (int cc = 0; cc < BN; cc += 32) {
-          uint32_t v[32];
-          __syncwarp();
-          tmem_ld32(tlane + ds * DCOLS + cc, v);
-          tmem_wait_ld();
-#pragma unroll
-          for (int ch = 1; ch < NC; ++ch) {   // add the other accumulation chains
-            uint32_t w[32];
-            tmem_ld32(tlane + ds * DCOLS + ch * BN + cc, w);
-            tmem_wait_ld();
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(w[j]));
-          }
+        // (the store / reduction choice is made OUTSIDE the column loop: a branch per store splits the loop body into basic
+        // blocks and pins every bias load behind the previous store -- measured 2.5x on the projections)
+        auto emit = [&](const uint32_t (&v)[32], int cc, auto atomic_tag) {
+          constexpr bool ATOMIC = decltype(atomic_tag)::value;
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
             float4 o = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
@@ -357,9 +353,29 @@ wf_ss_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
               wf_drop4(dst, e4row + (unsigned)((cc + j) >> 2), m);
               o.x *= m[0]; o.y *= m[1]; o.z *= m[2]; o.w *= m[3];
             }
-            if (row < a.rpt && !(a.debug & 2)) cblk[(long long)((cc + j) >> 2) * 128] = o;  // rows >= rpt of a node tile are padding
+            if (row < a.rpt && !(a.debug & 2)) {  // rows >= rpt of a node tile are padding
+              float4* dstp = cblk + (long long)((cc + j) >> 2) * 128;
+              if constexpr (ATOMIC)
+                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dstp), "f"(o.x), "f"(o.y), "f"(o.z), "f"(o.w));   // no "memory" clobber: it would pin the bias loads of the next columns behind it
+              else
+                *dstp = o;
+            }
           }
-        }
+        };
+        // (keeping the next chunk's TMEM load in flight under these stores was measured neutral without bias pointers and
+        // 2x slower with them: the plain load - wait - store sequence stays)
+        auto drain = [&](auto atomic_tag) {
+#pragma unroll 1
+          for (int cc = 0; cc < BN; cc += 32) {
+            uint32_t v[32];
+            __syncwarp();
+            tmem_ld32(tlane + ds * DCOLS + cc, v);
+            tmem_wait_ld();
+            emit(v, cc, atomic_tag);
+          }
+        };
+        if (a.k_parts > 1) drain(std::true_type{});
+        else drain(std::false_type{});
       } else {
         // row-major hl16 through shared memory + TMA stores: per 64 columns and plane a [32 rows][128 B] box per warp;
         // the stores clip at the window's R rows (3-D map), so partial tiles need no masking
@@ -505,6 +521,7 @@ wf_wg_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
           for (int kb = 0; kb < kb_n; ++kb, ++it) {
             const int s = it % NST, ph = (it / NST) & 1;
             if (!mbar_wait(&empty[s], ph ^ 1)) { atomicExch(a.err, 61); tile = total; b = b1; break; }
+            SS_TR(0, it);
             uint8_t* st = smem + s * STAGE;
             int bytes = SS_A_STAGE;
             for (int h = 0; h < a.nh; ++h) if (!(a.bshift[h] && t == 0)) bytes += SS_A_STAGE;
@@ -527,6 +544,7 @@ wf_wg_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                   tma_load_4d(sbase + (2 * h + j) * SS_A_PLANE, m, &full[s], a.bcol0[h] + 64 * j, node, zt, 0);
               }
             }
+            SS_TR(3, it);
           }
         }
       }
@@ -613,7 +631,8 @@ wf_wg_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       const int mtile = tile & 3, g = (tile >> 2) % a.G, split = (tile >> 2) / a.G;
       if (!mbar_wait(&dfull, lt & 1)) { if (lane == 0) atomicExch(a.err, 64); break; }
       tc_fence_after();
-      float* crow = a.part + (((long long)split * a.G + g) * 512 + mtile * 128 + row) * ncol;
+      // partial tile = [ncol / 4 column groups][128 rows][4 floats]: a warp's float4 store covers 512 contiguous bytes
+      float4* cblk = reinterpret_cast<float4*>(a.part) + ((((long long)split * a.G + g) * 4 + mtile) * (ncol >> 2)) * 128 + row;
       // a half whose every block of this split was skipped (step 0 of a shifted operand) never touched its accumulator
       bool live[2] = {false, false};
       {
@@ -621,20 +640,23 @@ wf_wg_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         for (int h = 0; h < a.nh; ++h)
           for (int b = b0; b < b1 && !live[h]; ++b) live[h] = !(a.bshift[h] && (b / a.tpw) % a.T == 0);
       }
-#pragma unroll 1
-      for (int cc = 0; cc < ncol; cc += 32) {
-        uint32_t v[32];
-        __syncwarp();
-        tmem_ld32(tlane + cc, v);
-        tmem_wait_ld();
+      auto emit = [&](uint32_t (&v)[32], int cc) {
         if (!live[cc >> 7]) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = 0u;
         }
 #pragma unroll
         for (int j = 0; j < 32; j += 4)
-          *reinterpret_cast<float4*>(crow + cc + j) = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
-                                                                  __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+          cblk[(long long)((cc + j) >> 2) * 128] = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
+                                                                __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+      };
+#pragma unroll 1
+      for (int cc = 0; cc < ncol; cc += 32) {
+        uint32_t v[32];
+        __syncwarp();
+        tmem_ld32(tlane + cc, v);
+        tmem_wait_ld();
+        emit(v, cc);
       }
       if (a.bias_part != nullptr) {
         uint32_t v[8];
@@ -659,13 +681,13 @@ __global__ void wf_wg_reduce_kernel(const float* __restrict__ part, const float*
                                     long long gstride) {
   // columns [0, w0) of a tile row go to dst0 (row pitch ld0), columns [w0, w0 + w1) to dst1 (row pitch ld1)
   const int ncol = nh * 128, g = blockIdx.y;
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;   // over 512 * ncol / 4 float4 + 512 bias rows
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;   // over 512 * ncol / 4 float4 (rows fastest) + 512 bias rows
   const int quads = 512 * ncol / 4;
   if (i < quads) {
-    const int m = (i * 4) / ncol, c = (i * 4) - m * ncol;
+    const int m = i & 511, c = (i >> 9) * 4;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int s = 0; s < splits; ++s) {
-      const float4 v = *reinterpret_cast<const float4*>(part + (((long long)s * G + g) * 512 + m) * ncol + c);
+    for (int s = 0; s < splits; ++s) {   // partial tiles: [split][g][m tile][ncol / 4][128 rows][4]
+      const float4 v = reinterpret_cast<const float4*>(part)[((((long long)s * G + g) * 4 + (m >> 7)) * (ncol >> 2) + (c >> 2)) * 128 + (m & 127)];
       acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
     }
     if (c < w0) *reinterpret_cast<float4*>(dst0 + g * gstride + (long long)m * ld0 + c) = acc;
@@ -750,10 +772,11 @@ int ss_launch_bn(const CUtensorMap& tmA, const CUtensorMap& tmA2, const CUtensor
     configured = true;
   }
   const int total_mt = a.m_tiles_g * a.G;
-  int slots = ss_sms() / a.n_parts;
+  if (a.k_parts < 1) a.k_parts = 1;
+  int slots = ss_sms() / (a.n_parts * a.k_parts);
   if (slots > total_mt) slots = total_mt;
   if (slots < 1) slots = 1;
-  const int grid = slots * a.n_parts;
+  const int grid = slots * a.n_parts * a.k_parts;
   if (a.drop.rng != nullptr) wf_ss_kernel<BN, true><<<grid, SS_THREADS, smem, st>>>(tmA, tmA2, tmBhi, tmBlo, tmOut, tmOut2, a);
   else wf_ss_kernel<BN, false><<<grid, SS_THREADS, smem, st>>>(tmA, tmA2, tmBhi, tmBlo, tmOut, tmOut2, a);
   WF_CHECK_LAUNCH("ss_kernel");
@@ -776,7 +799,8 @@ int ss_launch(int bn, const CUtensorMap& tmA, const CUtensorMap& tmA2, const CUt
 int wf_ss_launch_nodes(int bn, int avar, const void* A16, long long a_plane, int K, int afmt, const void* Bhi, const void* Blo,
                        int ldb, long long b_gstride, int Ntot, int bfmt, const float* bias, const float* bias2,
                        long long bias_gstride, float* C, int T, int Nn, int Bw, int G, const DropCfg* drop, int* err,
-                       cudaStream_t st) {
+                       cudaStream_t st, int k_parts) {
+  WF_REQUIRE(k_parts >= 1 && K % (SS_BK * k_parts) == 0 || k_parts == 1, "ss_nodes: K=%d does not split into %d parts of 64-wide blocks", K, k_parts);
   WF_REQUIRE(K % 8 == 0 && (avar == SS_A_KS || K % SS_BK == 0) && Ntot % bn == 0 && ldb % 8 == 0,
              "ss_nodes: K=%d must be a multiple of 8 (64 for TB8 operands), N=%d of %d", K, Ntot, bn);
   WF_REQUIRE(((uintptr_t)A16 | (uintptr_t)Bhi | (uintptr_t)Blo | (uintptr_t)C) % 16 == 0, "ss_nodes: pointers must be 16-byte aligned");
@@ -792,8 +816,11 @@ int wf_ss_launch_nodes(int bn, int avar, const void* A16, long long a_plane, int
   SsArgs a;
   memset(&a, 0, sizeof(a));
   a.mode = SS_NODES; a.avar = avar; a.epi = SS_E_TB4; a.n_parts = Ntot / bn; a.m_tiles_g = Bw * T * tpw; a.G = G;
-  a.nkb = (K + SS_BK - 1) / SS_BK; a.b_per_group = G > 1 ? 1 : 0; a.afmt = afmt; a.bfmt = bfmt;
+  a.nkb = (K + SS_BK - 1) / SS_BK / k_parts; a.k_parts = k_parts; a.b_per_group = G > 1 ? 1 : 0; a.afmt = afmt; a.bfmt = bfmt;
   a.T = T; a.Nn = Nn; a.Bw = Bw; a.tpw = tpw; a.rpt = wf_tile_rows(Nn);
+  if (k_parts > 1 &&   // the parts add into C
+      cudaMemsetAsync(C, 0, (size_t)ZT * tpw * Ntot * 128 * sizeof(float), st) != cudaSuccess)
+    return wf_fail(WF_ECUDA, "ss_nodes: clearing the output failed");
   a.C = C; a.c_cols = Ntot; a.bias = bias; a.bias2 = bias2; a.bias_gstride = bias_gstride; a.err = err;
   if (drop != nullptr) a.drop = *drop;
   return ss_launch(bn, tmA, tmA, tmBhi, tmBlo, tmA, tmA, a, st);
@@ -1006,9 +1033,9 @@ extern "C" int wf_join16(const void* hi, const void* lo, long long n, int fmt, f
 extern "C" int wf_ss_nodes_gemm(int bn, int avar, const void* A16, long long a_plane, int K, int afmt, const void* W16_hi,
                                 const void* W16_lo, long long w_group_stride, int Ntot, int bfmt, const float* bias,
                                 const float* bias2, long long bias_group_stride, float* C, int T, int Nn, int Bw, int G,
-                                int* err, void* stream) {
+                                int k_parts, int* err, void* stream) {
   return wf_ss_launch_nodes(bn, avar, A16, a_plane, K, afmt, W16_hi, W16_lo, K, w_group_stride, Ntot, bfmt, bias, bias2,
-                            bias_group_stride, C, T, Nn, Bw, G, nullptr, err, (cudaStream_t)stream);
+                            bias_group_stride, C, T, Nn, Bw, G, nullptr, err, (cudaStream_t)stream, k_parts);
 }
 // dst0 [G][512][w0] (+ dst1 [G][512][w1], db [G][512]) = dG^T [B0 | B1] over all blocks: dg16 TB8 bf16 planes (512 channels);
 // half h: bvar 0 TB8 fp16 planes with bC channels (bcol0: first channel), 1 row-major fp16 planes [2][G*Bw*T][Nn][bC];

@@ -40,7 +40,7 @@ using namespace wftc;
 int wf_ss_launch_nodes(int bn, int avar, const void* A16, long long a_plane, int K, int afmt, const void* Bhi, const void* Blo,
                        int ldb, long long b_gstride, int Ntot, int bfmt, const float* bias, const float* bias2,
                        long long bias_gstride, float* C, int T, int Nn, int Bw, int G, const DropCfg* drop, int* err,
-                       cudaStream_t st);
+                       cudaStream_t st, int k_parts = 1);
 int wf_ss_launch_wgrad(const void* dg16, long long dg_plane, int nh, const void* const* bsrc, const long long* bplane,
                        const int* bvar, const int* bshift, const int* bcol0, const int* bC, int T, int Nn, int Bw, int G,
                        float* part, size_t part_floats, float* dst0, int ld0, int w0, float* dst1, int ld1, int w1, float* db1,
@@ -994,8 +994,14 @@ extern "C" int wf_lstm_bwd_seq(const void* xb16, const void* pT16_hi, const void
       for (int g = 0; g < G; ++g) cudaMemsetAsync(grads + g * grads_group_stride + P.w_hh[l], 0, sizeof(float) * 4 * L * L, st);
     if (l > 0) {  // dL/d(input of layer l) = dG W_ih -> ext of layer l-1 (TB4 out), through layer l-1's mask
       const DropCfg dc = wf_drop_cfg(p_drop, rng, WF_SITE_LSTM + l - 1);
-      rc = wf_ss_launch_nodes(64, 1, dg16, dgp, 4 * L, 1, (const uint16_t*)pT16_hi + P.wihT[l], (const uint16_t*)pT16_lo + P.wihT[l],
-                              4 * L, stride16(P.totalT), L, 1, nullptr, nullptr, 0, DX, T, N, Bw, G, drop ? &dc : nullptr, err, st);
+      // WF_DX_KPARTS=2: K = 4L split over two CTAs (each keeps its half of W_ih^T resident, issues full-width N = L
+      // instructions and reads dG once instead of once per column part; the halves meet through red.global.add in a cleared
+      // output).  Measured 115 us against 116 us for two 64-column parts -- the A ring's bytes in flight bind both -- so
+      // the plain form stays the default.
+      static const int dx_kparts = getenv("WF_DX_KPARTS") ? atoi(getenv("WF_DX_KPARTS")) : 1;
+      rc = wf_ss_launch_nodes(dx_kparts > 1 ? L : 64, 1, dg16, dgp, 4 * L, 1, (const uint16_t*)pT16_hi + P.wihT[l],
+                              (const uint16_t*)pT16_lo + P.wihT[l], 4 * L, stride16(P.totalT), L, 1, nullptr, nullptr, 0, DX, T, N, Bw,
+                              G, drop ? &dc : nullptr, err, st, dx_kparts > 1 ? dx_kparts : 1);
       if (rc) return rc;
     }
   }

@@ -550,14 +550,25 @@ class AdamState:
         self.ws = torch.empty(self.ws_bytes, dtype=torch.uint8, device=device)
 
     @_on_device
-    def step(self, theta, grad, max_norm=1.0, grad_scale=1.0):
+    def prepare(self, grad_scale=1.0):
+        """Host half of a step: count it and send {lr, betas, eps, weight decay, bias corrections, grad scale} to the
+        device block the kernel reads (async copy from a pinned slot, stream ordered).  Separate from ``apply`` so that
+        the kernel launch can live inside a captured CUDA graph while the numbers still change every step."""
         self.step_count += 1
         b1, b2 = self.betas
         slot = self.hyper_host[self.step_count % self.hyper_host.shape[0]]
         slot.copy_(torch.tensor([self.lr, b1, b2, self.eps, self.weight_decay, 1.0 - b1 ** self.step_count,
                                  1.0 - b2 ** self.step_count, grad_scale], dtype=torch.float32))
         self.hyper.copy_(slot, non_blocking=True)
+
+    @_on_device
+    def apply(self, theta, grad, max_norm=1.0):
+        """Device half: fused clip + Adam(W) with the hyper-parameters currently in ``self.hyper`` (capturable)."""
         _lib.call("wf_clip_adam_step", _lib.ptr(theta), _lib.ptr(grad), _lib.ptr(self.exp_avg),
                   _lib.ptr(self.exp_avg_sq), self.P, _lib.ptr(self.hyper), float(max_norm), int(self.decoupled),
                   _lib.ptr(self.norm), _lib.ptr(self.ws), self.ws_bytes, _lib.stream_ptr())
         return theta
+
+    def step(self, theta, grad, max_norm=1.0, grad_scale=1.0):
+        self.prepare(grad_scale)
+        return self.apply(theta, grad, max_norm)

@@ -36,6 +36,8 @@ from __future__ import annotations
 
 import copy
 
+import os
+
 import torch
 import torch.nn as nn
 
@@ -323,7 +325,8 @@ class MetaTrainer:
 
     def __init__(self, state_dict, tasks, dims: V5Dims, device="cuda", support_rows=(0, 1, 2), query_row=None,
                  inner_lr=INNER_LR, outer_lr=OUTER_LR, weight_decay=1e-4, accum=None, use_cuda_graph=True,
-                 process_group=None, distributed=None, host_staging=False, dropout=REFERENCE_DROPOUT, seed=SEED):
+                 process_group=None, distributed=None, host_staging=False, dropout=REFERENCE_DROPOUT, seed=SEED,
+                 fused_update=None):
         import torch.distributed as dist
 
         self.dims, self.device = dims, torch.device(device)
@@ -371,6 +374,11 @@ class MetaTrainer:
         self.meta = torch.zeros(self.P + 4, dtype=torch.float32, device=self.device)  # grad + packed loss
         self.adam = AdamState(self.P, self.device, outer_lr, weight_decay=weight_decay, decoupled=True)
         self.use_graph, self.cuda_graphs = bool(use_cuda_graph), [None, None]
+        # all-reduce + AdamW as nodes of the captured graph (default wherever there is a graph; WF_FUSED_UPDATE=0 keeps
+        # them as separate enqueues after the replay)
+        if fused_update is None:
+            fused_update = os.environ.get("WF_FUSED_UPDATE", "1") != "0"
+        self.fused_update = bool(fused_update) and self.use_graph
         self._copy = None
         self.launches_per_step = None
 
@@ -391,6 +399,40 @@ class MetaTrainer:
         e.launches += 1
         self.meta[self.P:self.P + 1].copy_((e.loss.sum() / self.accum).reshape(1))
         self.meta[self.P + 1:self.P + 2].copy_(e.err.to(torch.float32))  # error flag rides with the loss (summed over ranks)
+        if self.fused_update:
+            self._update()
+
+    def _update(self):
+        """The exchange step and the outer update: ONE all-reduce of [meta-gradient | loss | error flag] over the ranks,
+        then the fused clip + AdamW, identical on every rank.  With ``fused_update`` both are nodes of the captured
+        meta-step graph (NCCL collectives capture; AdamW reads its hyper-parameters from the device block that
+        ``AdamState.prepare`` refreshes before every replay), so a meta-step is one graph launch on every rank."""
+        if self.dist is not None and self.world > 1:
+            self.dist.all_reduce(self.meta, op=self.dist.ReduceOp.SUM, group=self.pg)
+        self.adam.apply(self.theta, self.meta, max_norm=1.0)
+
+    def _ensure_graph(self, k):
+        """Warm up (uncaptured, without the outer update) and capture the meta-step graph that reads staging buffer k."""
+        if self.cuda_graphs[k] is not None:
+            return
+        before = self.engine.launches
+        side = torch.cuda.Stream(self.device)
+        side.wait_stream(torch.cuda.current_stream(self.device))
+        fused, self.fused_update = self.fused_update, False
+        try:
+            with torch.cuda.stream(side):
+                self._body()  # module load, lazy allocations: outside capture, and without touching theta
+                if fused and self.dist is not None and self.world > 1:
+                    # communicator set-up must not happen inside a capture: one throw-away collective first
+                    self.dist.all_reduce(torch.zeros(8, dtype=torch.float32, device=self.device), group=self.pg)
+        finally:
+            self.fused_update = fused
+        torch.cuda.current_stream(self.device).wait_stream(side)
+        torch.cuda.synchronize(self.device)
+        self.launches_per_step = self.engine.launches - before
+        self.cuda_graphs[k] = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.cuda_graphs[k]):
+            self._body()
 
     def _run_body(self, k=0):
         """Replay (capturing on first use) the CUDA graph of the meta-step body that reads staging buffer k."""
@@ -399,22 +441,13 @@ class MetaTrainer:
             self._body()
             self.launches_per_step = self.engine.launches - before
             return
-        if self.cuda_graphs[k] is None:
-            before = self.engine.launches
-            side = torch.cuda.Stream(self.device)
-            side.wait_stream(torch.cuda.current_stream(self.device))
-            with torch.cuda.stream(side):
-                self._body()  # warm-up: module load + autotune-free, outside capture
-            torch.cuda.current_stream(self.device).wait_stream(side)
-            torch.cuda.synchronize(self.device)
-            self.launches_per_step = self.engine.launches - before
-            self.cuda_graphs[k] = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(self.cuda_graphs[k]):
-                self._body()
+        self._ensure_graph(k)
         self.cuda_graphs[k].replay()
 
     def meta_step(self):
         """Enqueue one meta-step; returns the (device) meta-loss tensor without synchronising."""
+        if self.fused_update:
+            self.adam.prepare()  # hyper-parameters of THIS step, stream-ordered before the graph that applies them
         if self.stager is None:
             self._run_body(0)
         elif not self.use_graph:
@@ -430,9 +463,8 @@ class MetaTrainer:
                 for k in (0, 1):  # first call: both buffers filled synchronously, both graphs captured
                     self.features = self.stager.upload(k)
                     torch.cuda.synchronize(self.device)
-                    if self.cuda_graphs[k] is None:
-                        self._run_body(k)
-                        torch.cuda.synchronize(self.device)
+                    self._ensure_graph(k)
+                    torch.cuda.synchronize(self.device)
             k = self._t & 1
             if self._up_done[k] is not None:
                 main.wait_event(self._up_done[k])
@@ -448,9 +480,9 @@ class MetaTrainer:
                 self._up_done[kn] = torch.cuda.Event()
                 self._up_done[kn].record(self._copy)
             self._t += 1
-        if self.dist is not None and self.world > 1:
-            self.dist.all_reduce(self.meta, op=self.dist.ReduceOp.SUM, group=self.pg)
-        self.adam.step(self.theta, self.meta, max_norm=1.0)
+        if not self.fused_update:
+            self.adam.prepare()
+            self._update()
         return self.meta[self.P]
 
     def read_loss(self):
