@@ -193,15 +193,19 @@ def test_meta_trainer_two_tasks_vs_oracle_with_and_without_graph():
         for p, k in zip(params, names):
             cur[k] = p.detach().clone()
         ref_losses.append(tot)
-    for use_graph in (False, True):
+    # eager; one graph per meta-step with the all-reduce + AdamW inside it (default) or enqueued after it; host-resident
+    # features (two graphs, double-buffered uploads: capture must not run the outer update)
+    for use_graph, fused, host in ((False, None, False), (True, True, False), (True, False, False), (True, True, True)):
         mt = MetaTrainer(sd, tasks, dims, "cuda", dropout=(0, 0, 0), support_rows=(0, 1, 2), query_row=3, accum=2,
-                         use_cuda_graph=use_graph)
+                         use_cuda_graph=use_graph, fused_update=fused, host_staging=host)
+        assert mt.fused_update == bool(use_graph and fused)
         got = [mt.meta_step().item() for _ in range(2)]
         torch.cuda.synchronize()
+        assert mt.adam.step_count == 2
         out = mt.state_dict()
-        assert np.allclose(got, ref_losses, rtol=FWD_TOL), (use_graph, got, ref_losses)
+        assert np.allclose(got, ref_losses, rtol=FWD_TOL), (use_graph, fused, host, got, ref_losses)
         for k in names:
-            assert rel_err(out[k], cur[k]) <= 1e-4, (use_graph, k)
+            assert rel_err(out[k], cur[k]) <= 1e-4, (use_graph, fused, host, k)
         for k in sd:
             if k.startswith("base_stgcn."):
                 assert torch.equal(out[k], sd[k])
