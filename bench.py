@@ -355,7 +355,9 @@ def load_ncu_traffic():
     with open(files[-1]) as fh:
         for row in csv.DictReader(fh):
             try:
-                out[row["kernel"]] = (float(row["dram_read_bytes"]) + float(row["dram_write_bytes"])) / max(1.0, float(row["launches"]))
+                per = (float(row["dram_read_bytes"]) + float(row["dram_write_bytes"])) / max(1.0, float(row["launches"]))
+                out[row["kernel"]] = per
+                out.setdefault(row["kernel"].split("<")[0], per)  # "wf_lstm_seq_fwd16_kernel<0>" -> the plain name
             except (KeyError, ValueError):
                 continue
     return out, os.path.relpath(files[-1], ROOT)
