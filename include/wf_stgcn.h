@@ -297,6 +297,20 @@ int wf_gcn_layer_fwd_ss(const float* X32, const long long* x_win_off, const void
                         int Bw, int relu, void* Y16, void* Yb16, float p_drop, const unsigned long long* rng,
                         int site, int* err, void* stream);
 
+/* loss.backward() through GCNConv + ReLU (+ Dropout) on the tensor cores (model.py:31-42 under autograd: STGCN.forward,
+ * SURVEY.md D4; replaces wf_gcn_layer_bwd where the widths allow).  X [Bw*R][Cin], Y / dY [Bw*R][Cout], W [Cout][Cin]:
+ * fp32 row-major; CSR by target of A_hat over the R rows of a window and its transpose (shared by the Bw windows).
+ * dZ = dY * mask * (Y > 0) is written once as bf16 hi/lo planes and read by both products: dW = dZ^T (A_hat X), db = dZ^T 1
+ * (weight-gradient kernel) and dX = A_hat^T (dZ W) (SS GEMM + transposed aggregation).  dX may be NULL.  Cout % 128 == 0,
+ * Cin % 8 == 0 and <= 256 (dX: Cin 128 or 256).  The mask is regenerated from (p_drop, rng = {seed, pass} of the forward
+ * call, site).  workspace: wf_gcn_layer_bwd_ss_workspace_bytes, 256-byte aligned. */
+size_t wf_gcn_layer_bwd_ss_workspace_bytes(int R, int Cin, int Cout, int Bw);
+int wf_gcn_layer_bwd_ss(const float* X, const float* Y, const float* dY, const float* W, const int* rowptr,
+                        const int* col, const float* val, const int* rowptr_t, const int* col_t, const float* val_t,
+                        int R, int Cin, int Cout, int Bw, int relu, float p_drop, const unsigned long long* rng,
+                        int site, float* dX, float* dW, float* db, void* workspace, size_t workspace_bytes, int* err,
+                        void* stream);
+
 /* The two SS-mode kernels on operands given as plain 16-bit planes (test / general entry points).
  * wf_ss_nodes_gemm: C (TB4 fp32: per (window, step, node tile) a block [Ntot/4][128 rows][4]) = A W^T (+ bias + bias2);
  *   avar 0: A16 row-major planes [2][G*Bw*T][Nn][K], 1: TB8 planes; W16 hi / lo [G][Ntot][K]; bn = 64 / 128 / 256 columns

@@ -31,6 +31,9 @@ SIGNATURES = {
     "wf_gcn_layer_fwd": (c_i, [c_p, c_i, c_ll, c_p, c_p, c_p, c_ll, c_ll, c_p, c_p, c_p, c_ll, c_ll,
                                c_i, c_i, c_i, c_i, c_i, c_i, c_p, c_p]),
     "wf_gcn_layer_bwd_workspace_bytes": (c_sz, [c_i, c_i, c_i, c_i, c_i]),
+    "wf_gcn_layer_bwd_ss_workspace_bytes": (c_sz, [c_i, c_i, c_i, c_i]),
+    "wf_gcn_layer_bwd_ss": (c_i, [c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_i, c_i, c_i, c_i, c_i, c_f, c_p, c_i,
+                                  c_p, c_p, c_p, c_p, c_sz, c_p, c_p]),
     "wf_gcn_layer_bwd": (c_i, [c_p, c_i, c_ll, c_p, c_p, c_p, c_p, c_ll, c_p, c_p, c_p, c_p, c_p, c_p,
                                c_ll, c_ll, c_i, c_i, c_i, c_i, c_i, c_i, c_p, c_p, c_p, c_ll, c_ll,
                                c_p, c_sz, c_p]),

@@ -478,7 +478,8 @@ struct WgArgs {
   int bcol0[2];                 // TB8: first channel group of the half; row-major: first column
   int afmt, bfmt;
   int nst;
-  float* part; float* bias_part;   // [splits][G][512][nh * 128], [splits][G][512]
+  float* part; float* bias_part;   // [splits][G][M][nh * 128] (tiles in TB4 order), [splits][G][M]
+  int mt;                          // M / 128 row tiles of dG's channels (4: the LSTM's 4L = 512 gate rows)
   int* err;
 };
 
@@ -493,7 +494,7 @@ wf_wg_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   __shared__ uint32_t tmem_base_s;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, NST = a.nst;
   const int blocks_g = a.Bw * a.T * a.tpw;
-  const int total = a.splits * a.G * 4;
+  const int total = a.splits * a.G * a.mt;
   const int kb_n = (a.rpt + 63) / 64;          // 64-row k-blocks that hold data
   if (threadIdx.x == 0) {
     for (int s = 0; s < NST; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
@@ -513,7 +514,7 @@ wf_wg_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     if (lane == 0) {
       int it = 0;
       for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
-        const int mtile = tile & 3, g = (tile >> 2) % a.G, split = (tile >> 2) / a.G;
+        const int mtile = tile % a.mt, g = (tile / a.mt) % a.G, split = (tile / a.mt) / a.G;
         const int b0 = split * a.bps, b1 = min(blocks_g, b0 + a.bps);
         for (int b = b0; b < b1; ++b) {
           const int t = (b / a.tpw) % a.T, nt = b % a.tpw;
@@ -557,7 +558,7 @@ wf_wg_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     int it = 0, lt = 0;
     bool ok = true;
     for (int tile = blockIdx.x; tile < total && ok; tile += gridDim.x, ++lt) {
-      const int split = (tile >> 2) / a.G;
+      const int split = (tile / a.mt) / a.G;
       const int b0 = split * a.bps, b1 = min(blocks_g, b0 + a.bps);
       if (!mbar_wait(&dempty, (lt & 1) ^ 1)) { if (lane == 0) atomicExch(a.err, 62); ok = false; break; }
       tc_fence_after();
@@ -628,11 +629,11 @@ wf_wg_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     const int ncol = a.nh * 128;
     int lt = 0;
     for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++lt) {
-      const int mtile = tile & 3, g = (tile >> 2) % a.G, split = (tile >> 2) / a.G;
+      const int mtile = tile % a.mt, g = (tile / a.mt) % a.G, split = (tile / a.mt) / a.G;
       if (!mbar_wait(&dfull, lt & 1)) { if (lane == 0) atomicExch(a.err, 64); break; }
       tc_fence_after();
       // partial tile = [ncol / 4 column groups][128 rows][4 floats]: a warp's float4 store covers 512 contiguous bytes
-      float4* cblk = reinterpret_cast<float4*>(a.part) + ((((long long)split * a.G + g) * 4 + mtile) * (ncol >> 2)) * 128 + row;
+      float4* cblk = reinterpret_cast<float4*>(a.part) + ((((long long)split * a.G + g) * a.mt + mtile) * (ncol >> 2)) * 128 + row;
       // a half whose every block of this split was skipped (step 0 of a shifted operand) never touched its accumulator
       bool live[2] = {false, false};
       {
@@ -663,7 +664,7 @@ wf_wg_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         __syncwarp();
         tmem_ld8(tlane + 256, v);
         tmem_wait_ld();
-        a.bias_part[((long long)split * a.G + g) * 512 + mtile * 128 + row] = __uint_as_float(v[0]);
+        a.bias_part[((long long)split * a.G + g) * (a.mt * 128) + mtile * 128 + row] = __uint_as_float(v[0]);
       }
       tc_fence_before();
       __syncwarp();
@@ -676,26 +677,26 @@ wf_wg_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
 }
 
 // dst_h[g][m][c] = sum_s part[s][g][m][h*128 + c] (fixed order); bias -> both LSTM bias gradients
-__global__ void wf_wg_reduce_kernel(const float* __restrict__ part, const float* __restrict__ bias_part, int splits, int G, int nh,
+__global__ void wf_wg_reduce_kernel(const float* __restrict__ part, const float* __restrict__ bias_part, int splits, int G, int nh, int M,
                                     float* dst0, int ld0, int w0, float* dst1, int ld1, int w1, float* db1, float* db2,
                                     long long gstride) {
   // columns [0, w0) of a tile row go to dst0 (row pitch ld0), columns [w0, w0 + w1) to dst1 (row pitch ld1)
   const int ncol = nh * 128, g = blockIdx.y;
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;   // over 512 * ncol / 4 float4 (rows fastest) + 512 bias rows
-  const int quads = 512 * ncol / 4;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;   // over M * ncol / 4 float4 (rows fastest) + M bias rows
+  const int quads = M * ncol / 4, mt = M >> 7;
   if (i < quads) {
-    const int m = i & 511, c = (i >> 9) * 4;
+    const int m = i % M, c = (i / M) * 4;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int s = 0; s < splits; ++s) {   // partial tiles: [split][g][m tile][ncol / 4][128 rows][4]
-      const float4 v = reinterpret_cast<const float4*>(part)[((((long long)s * G + g) * 4 + (m >> 7)) * (ncol >> 2) + (c >> 2)) * 128 + (m & 127)];
+      const float4 v = reinterpret_cast<const float4*>(part)[((((long long)s * G + g) * mt + (m >> 7)) * (ncol >> 2) + (c >> 2)) * 128 + (m & 127)];
       acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
     }
     if (c < w0) *reinterpret_cast<float4*>(dst0 + g * gstride + (long long)m * ld0 + c) = acc;
     else if (dst1 != nullptr && c - w0 < w1) *reinterpret_cast<float4*>(dst1 + g * gstride + (long long)m * ld1 + (c - w0)) = acc;
-  } else if (i < quads + 512 && bias_part != nullptr && db1 != nullptr) {
+  } else if (i < quads + M && bias_part != nullptr && db1 != nullptr) {
     const int m = i - quads;
     float acc = 0.f;
-    for (int s = 0; s < splits; ++s) acc += bias_part[((long long)s * G + g) * 512 + m];
+    for (int s = 0; s < splits; ++s) acc += bias_part[((long long)s * G + g) * M + m];
     db1[g * gstride + m] = acc;
     if (db2) db2[g * gstride + m] = acc;
   }
@@ -832,13 +833,14 @@ int wf_ss_launch_nodes(int bn, int avar, const void* A16, long long a_plane, int
 int wf_ss_launch_wgrad(const void* dg16, long long dg_plane, int nh, const void* const* bsrc, const long long* bplane,
                        const int* bvar, const int* bshift, const int* bcol0, const int* bC, int T, int Nn, int Bw, int G,
                        float* part, size_t part_floats, float* dst0, int ld0, int w0, float* dst1, int ld1, int w1, float* db1,
-                       float* db2, long long gstride, int* err, cudaStream_t st) {
+                       float* db2, long long gstride, int* err, cudaStream_t st, int M) {
   WF_REQUIRE(nh == 1 || nh == 2, "ss_wgrad: one or two operand halves");
+  WF_REQUIRE(M >= 128 && M % 128 == 0, "ss_wgrad: M=%d must be a multiple of 128", M);
   const int tpw = wf_cdiv(Nn, 128), blocks_g = Bw * T * tpw;
   const long long blocks = (long long)G * blocks_g, ZT = (long long)G * Bw * T;
   CUtensorMap tmA, tmB[2];
   int rc;
-  if ((rc = map_tb8(&tmA, dg16, 512, blocks, dg_plane, 2, 16, 1))) return rc;
+  if ((rc = map_tb8(&tmA, dg16, M, blocks, dg_plane, 2, 16, 1))) return rc;
   for (int h = 0; h < nh; ++h) {
     if (bvar[h] == 0) rc = map_tb8(&tmB[h], bsrc[h], bC[h], blocks, bplane[h], 2, 16, 1, 1);   // one plane per load
     else rc = map_rows_mn(&tmB[h], bsrc[h], bC[h], Nn, ZT, bplane[h], 1, 64, 2);
@@ -850,18 +852,19 @@ int wf_ss_launch_wgrad(const void* dg16, long long dg_plane, int nh, const void*
   int best = 1;
   long long best_cost = -1;
   for (int s = 1; s <= 40 && s <= blocks_g; ++s) {
-    if ((size_t)s * G * 512 * (ncol + 1) > part_floats) break;
-    const long long cost = (long long)wf_cdiv(4LL * G * s, sms) * wf_cdiv(blocks_g, s) * 64 + s;  // + s: prefer fewer partials on ties
+    if ((size_t)s * G * M * (ncol + 1) > part_floats) break;
+    const long long cost = (long long)wf_cdiv((long long)(M / 128) * G * s, sms) * wf_cdiv(blocks_g, s) * 64 + s;  // + s: prefer fewer partials on ties
     if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = s; }
   }
-  WF_REQUIRE((size_t)best * G * 512 * (ncol + 1) <= part_floats, "ss_wgrad: partial buffer too small");
+  WF_REQUIRE((size_t)best * G * M * (ncol + 1) <= part_floats, "ss_wgrad: partial buffer too small");
   WgArgs a;
   memset(&a, 0, sizeof(a));
   a.G = G; a.Bw = Bw; a.T = T; a.tpw = tpw; a.rpt = wf_tile_rows(Nn); a.Nn = Nn;
   a.bps = wf_cdiv(blocks_g, best); a.splits = wf_cdiv(blocks_g, a.bps); a.nh = nh;
   for (int h = 0; h < nh; ++h) { a.bvar[h] = bvar[h]; a.bshift[h] = bshift[h]; a.bcol0[h] = bvar[h] == 0 ? bcol0[h] / 8 : bcol0[h]; }
   a.afmt = 1; a.bfmt = 1; a.nst = nh == 2 ? 2 : 3;   // kind::f16 takes ONE format for both operands: bf16 (dG's range)
-  a.part = part; a.bias_part = db1 != nullptr ? part + (size_t)a.splits * G * 512 * ncol : nullptr; a.err = err;
+  a.mt = M / 128;
+  a.part = part; a.bias_part = db1 != nullptr ? part + (size_t)a.splits * G * M * ncol : nullptr; a.err = err;
   const int smem = a.nst * SS_A_STAGE * (1 + nh) + 1024 + 1024;
   static bool configured = false;
   if (!configured) {
@@ -869,11 +872,11 @@ int wf_ss_launch_wgrad(const void* dg16, long long dg_plane, int nh, const void*
       return wf_fail(WF_ECUDA, "wg kernel: cannot raise dynamic shared memory");
     configured = true;
   }
-  const int total = a.splits * G * 4;
+  const int total = a.splits * G * a.mt;
   wf_wg_kernel<<<total < sms ? total : sms, WG_THREADS, smem, st>>>(tmA, tmB[0], tmB[1], a);
   WF_CHECK_LAUNCH("wg_kernel");
-  const int items = 512 * ncol / 4 + 512;
-  wf_wg_reduce_kernel<<<dim3(wf_cdiv(items, 256), G), 256, 0, st>>>(part, a.bias_part, a.splits, G, nh, dst0, ld0, w0, dst1, ld1, w1,
+  const int items = M * ncol / 4 + M;
+  wf_wg_reduce_kernel<<<dim3(wf_cdiv(items, 256), G), 256, 0, st>>>(part, a.bias_part, a.splits, G, nh, M, dst0, ld0, w0, dst1, ld1, w1,
                                                                    db1, db2, gstride);
   WF_CHECK_LAUNCH("wg_reduce");
   return WF_OK;
@@ -1026,6 +1029,222 @@ extern "C" int wf_join16(const void* hi, const void* lo, long long n, int fmt, f
   return WF_OK;
 }
 
+// ================================================================================= GCNConv backward on the tensor cores
+// loss.backward() through Y = dropout(relu((A_hat X) W^T + b)) (model.py:31-42 under autograd -- STGCN.forward, the only
+// differentiable use of GCNConv):
+//   dZ = dY * mask * (Y > 0)                  -> TB8 bf16 hi/lo planes, block = (window, 128-row tile)     wf_ss_dz_tb8_kernel
+//   AX = A_hat X                               -> row-major bf16 hi/lo planes                               wf_ss_ax_rows_kernel
+//   dW = dZ^T AX, db = dZ^T 1                  -> wf_wg_kernel (both operands MN-major, M = Cout)
+//   P  = dZ W                                  -> wf_ss_kernel (A = the same dZ planes K-major, B = W^T bf16 hi/lo), TB4 fp32
+//   dX = A_hat^T P                             -> wf_ss_dx_finish_kernel (transposed CSR; TB4 -> row-major fp32)
+namespace {
+
+// one CTA per TB8 block, one thread per row of it; rows past the window (or past rpt) are written as zeros
+__global__ void __launch_bounds__(128) wf_ss_dz_tb8_kernel(const float* __restrict__ dY, const float* __restrict__ Y, int Cout, int R,
+                                                           int tpw, int rpt, int relu, const DropCfg drop,
+                                                           uint16_t* __restrict__ out, long long plane) {
+  const long long blk = blockIdx.x;
+  const int z = (int)(blk / tpw), nt = (int)(blk % tpw), rl = threadIdx.x;
+  const int r = nt * rpt + rl;
+  const bool valid = rl < rpt && r < R;
+  const long long grow = (long long)z * R + r;
+  DropState ds;
+  if (drop.rng != nullptr) ds = wf_drop_state(drop);
+  for (int c8 = 0; c8 < (Cout >> 3); ++c8) {
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = 0.f;
+    if (valid) {
+      const float* src = dY + grow * Cout + 8 * c8;
+      const float4 a = __ldg(reinterpret_cast<const float4*>(src)), b = __ldg(reinterpret_cast<const float4*>(src + 4));
+      v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+      if (drop.rng != nullptr) {
+        float m[8];
+        const unsigned long long e4 = (unsigned long long)(grow * Cout + 8 * c8) >> 2;
+        wf_drop4(ds, e4, m);
+        wf_drop4(ds, e4 + 1, m + 4);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] *= m[j];
+      }
+      if (relu) {
+        const float* ys = Y + grow * Cout + 8 * c8;
+        const float4 ya = __ldg(reinterpret_cast<const float4*>(ys)), yb = __ldg(reinterpret_cast<const float4*>(ys + 4));
+        const float y[8] = {ya.x, ya.y, ya.z, ya.w, yb.x, yb.y, yb.z, yb.w};
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = y[j] > 0.f ? v[j] : 0.f;
+      }
+    }
+    uint4 hi, lo;
+    ss_split_bf16(v[0], v[1], hi.x, lo.x); ss_split_bf16(v[2], v[3], hi.y, lo.y);
+    ss_split_bf16(v[4], v[5], hi.z, lo.z); ss_split_bf16(v[6], v[7], hi.w, lo.w);
+    const long long o = ((blk * (Cout >> 3) + c8) * 128 + rl) * 8;
+    *reinterpret_cast<uint4*>(out + o) = hi;
+    *reinterpret_cast<uint4*>(out + plane + o) = lo;
+  }
+}
+
+// AX[z][r][:] = sum_p val[p] X[z][col[p]][:] as bf16 hi/lo planes with row pitch CinP >= Cin (columns past Cin zero):
+// one warp per row, 8 channels per lane
+__global__ void __launch_bounds__(256) wf_ss_ax_rows_kernel(const float* __restrict__ X, int Cin, int CinP, int R, long long rows,
+                                                            const int* __restrict__ rowptr, const int* __restrict__ col,
+                                                            const float* __restrict__ val, uint16_t* __restrict__ out,
+                                                            long long plane) {
+  const long long gr = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (gr >= rows) return;
+  const long long z = gr / R;
+  const int r = (int)(gr - z * R);
+  const int p0 = __ldg(rowptr + r), p1 = __ldg(rowptr + r + 1);
+  for (int c8 = lane; c8 < (CinP >> 3); c8 += 32) {
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    if (8 * c8 < Cin) {
+      for (int p = p0; p < p1; ++p) {
+        const float w = __ldg(val + p);
+        const float* src = X + (z * R + __ldg(col + p)) * Cin + 8 * c8;
+        const float4 a = __ldg(reinterpret_cast<const float4*>(src)), b = __ldg(reinterpret_cast<const float4*>(src + 4));
+        acc[0] = fmaf(w, a.x, acc[0]); acc[1] = fmaf(w, a.y, acc[1]); acc[2] = fmaf(w, a.z, acc[2]); acc[3] = fmaf(w, a.w, acc[3]);
+        acc[4] = fmaf(w, b.x, acc[4]); acc[5] = fmaf(w, b.y, acc[5]); acc[6] = fmaf(w, b.z, acc[6]); acc[7] = fmaf(w, b.w, acc[7]);
+      }
+    }
+    uint4 hi, lo;
+    ss_split_bf16(acc[0], acc[1], hi.x, lo.x); ss_split_bf16(acc[2], acc[3], hi.y, lo.y);
+    ss_split_bf16(acc[4], acc[5], hi.z, lo.z); ss_split_bf16(acc[6], acc[7], hi.w, lo.w);
+    const long long o = gr * CinP + 8 * c8;
+    *reinterpret_cast<uint4*>(out + o) = hi;
+    *reinterpret_cast<uint4*>(out + plane + o) = lo;
+  }
+}
+
+// dX[z][r][:] = sum_p val_t[p] P[z][col_t[p]][:], P in TB4 blocks [Cin / 4][128 rows][4]; one CTA per block, one thread per row
+__global__ void __launch_bounds__(128) wf_ss_dx_finish_kernel(const float* __restrict__ P, int Cin, int R, int tpw, int rpt,
+                                                              const int* __restrict__ rowptr_t, const int* __restrict__ col_t,
+                                                              const float* __restrict__ val_t, float* __restrict__ dX) {
+  const long long blk = blockIdx.x;
+  const int z = (int)(blk / tpw), nt = (int)(blk % tpw), rl = threadIdx.x;
+  const int r = nt * rpt + rl;
+  if (rl >= rpt || r >= R) return;
+  const int p0 = __ldg(rowptr_t + r), p1 = __ldg(rowptr_t + r + 1);
+  const float4* P4 = reinterpret_cast<const float4*>(P);
+  float* dst = dX + ((long long)z * R + r) * Cin;
+  const int q = Cin >> 2;
+  if (p1 - p0 == 1 && __ldg(col_t + p0) == r) {  // the common row: its own (unit or not) self loop only
+    const float w = __ldg(val_t + p0);
+    for (int c4 = 0; c4 < q; c4 += 2) {
+      float4 a = P4[(blk * q + c4) * 128 + rl], b = P4[(blk * q + c4 + 1) * 128 + rl];
+      a.x *= w; a.y *= w; a.z *= w; a.w *= w; b.x *= w; b.y *= w; b.z *= w; b.w *= w;
+      *reinterpret_cast<float4*>(dst + 4 * c4) = a;
+      *reinterpret_cast<float4*>(dst + 4 * c4 + 4) = b;
+    }
+    return;
+  }
+  for (int c4 = 0; c4 < q; c4 += 2) {
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+    for (int p = p0; p < p1; ++p) {
+      const float w = __ldg(val_t + p);
+      const int c = __ldg(col_t + p);
+      const long long sb = (long long)z * tpw + c / rpt;
+      const int sl = c % rpt;
+      const float4 u = P4[(sb * q + c4) * 128 + sl], v = P4[(sb * q + c4 + 1) * 128 + sl];
+      a.x = fmaf(w, u.x, a.x); a.y = fmaf(w, u.y, a.y); a.z = fmaf(w, u.z, a.z); a.w = fmaf(w, u.w, a.w);
+      b.x = fmaf(w, v.x, b.x); b.y = fmaf(w, v.y, b.y); b.z = fmaf(w, v.z, b.z); b.w = fmaf(w, v.w, b.w);
+    }
+    *reinterpret_cast<float4*>(dst + 4 * c4) = a;
+    *reinterpret_cast<float4*>(dst + 4 * c4 + 4) = b;
+  }
+}
+
+// WT[n][k] = W[k][n] as bf16 hi/lo planes [2][Cin][Cout]
+__global__ void wf_ss_wt_split_kernel(const float* __restrict__ W, int Cout, int Cin, uint16_t* __restrict__ out, long long plane) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= Cout * Cin) return;
+  const int n = i / Cout, k = i - n * Cout;
+  const float w = W[(long long)k * Cin + n];
+  const __nv_bfloat16 h = __float2bfloat16_rn(w);
+  const __nv_bfloat16 l = __float2bfloat16_rn(w - __bfloat162float(h));
+  out[i] = *reinterpret_cast<const uint16_t*>(&h);
+  out[plane + i] = *reinterpret_cast<const uint16_t*>(&l);
+}
+
+struct GcnBwdWs { size_t dz, ax, p, wt, part, total; int cinp, splits_max; };
+GcnBwdWs gcn_bwd_ws(int R, int Cin, int Cout, int Bw, bool need_dx) {
+  GcnBwdWs w;
+  const long long tpw = wf_cdiv(R, 128), blocks = (long long)Bw * tpw;
+  w.cinp = Cin <= 128 ? 128 : 256;
+  w.splits_max = 40;
+  auto up = [](size_t b) { return (b + 1023) & ~(size_t)1023; };
+  w.dz = 0;
+  w.ax = w.dz + up((size_t)blocks * Cout * 128 * 2 * 2);
+  w.p = w.ax + up((size_t)Bw * R * w.cinp * 2 * 2);
+  w.wt = w.p + (need_dx ? up((size_t)blocks * Cin * 128 * 4) : 0);
+  w.part = w.wt + up((size_t)Cin * Cout * 2 * 2);
+  w.total = w.part + up((size_t)w.splits_max * Cout * (w.cinp + 1) * 4);
+  return w;
+}
+
+}  // namespace
+
+extern "C" size_t wf_gcn_layer_bwd_ss_workspace_bytes(int R, int Cin, int Cout, int Bw) {
+  return gcn_bwd_ws(R, Cin, Cout, Bw, true).total;
+}
+
+// X [Bw*R][Cin], Y / dY [Bw*R][Cout], W [Cout][Cin] fp32 row-major; CSR by target (A_hat) and its transpose over the R rows of
+// one window (shared by all windows).  dX may be NULL (input without gradient).  Cout a multiple of 128, Cin a multiple
+// of 8 up to 256 (dX additionally needs Cin = 128 or 256).  Y is read only when relu != 0.
+extern "C" int wf_gcn_layer_bwd_ss(const float* X, const float* Y, const float* dY, const float* W, const int* rowptr,
+                                   const int* col, const float* val, const int* rowptr_t, const int* col_t, const float* val_t,
+                                   int R, int Cin, int Cout, int Bw, int relu, float p_drop, const unsigned long long* rng,
+                                   int site, float* dX, float* dW, float* db, void* workspace, size_t workspace_bytes, int* err,
+                                   void* stream) {
+  WF_REQUIRE(R > 0 && Bw > 0, "gcn_layer_bwd_ss: bad batch");
+  WF_REQUIRE(Cout % 128 == 0 && Cin % 8 == 0 && Cin <= 256, "gcn_layer_bwd_ss: Cout=%d must be a multiple of 128, Cin=%d of 8 and <= 256", Cout, Cin);
+  WF_REQUIRE(dX == nullptr || Cin % 128 == 0, "gcn_layer_bwd_ss: dX needs Cin=%d to be 128 or 256", Cin);
+  WF_REQUIRE(!relu || Y != nullptr, "gcn_layer_bwd_ss: the ReLU gate needs Y");
+  WF_REQUIRE(p_drop >= 0.f && p_drop < 1.f && (p_drop == 0.f || rng != nullptr), "gcn_layer_bwd_ss: bad dropout arguments");
+  const GcnBwdWs w = gcn_bwd_ws(R, Cin, Cout, Bw, dX != nullptr);
+  WF_REQUIRE(workspace != nullptr && workspace_bytes >= w.total && (uintptr_t)workspace % 256 == 0,
+             "gcn_layer_bwd_ss: workspace too small or not 256-byte aligned (%zu < %zu)", workspace_bytes, w.total);
+  cudaStream_t st = (cudaStream_t)stream;
+  uint8_t* base = (uint8_t*)workspace;
+  const int tpw = wf_cdiv(R, 128), rpt = wf_tile_rows(R);
+  const long long blocks = (long long)Bw * tpw, rows = (long long)Bw * R;
+  uint16_t* dz16 = (uint16_t*)(base + w.dz);
+  uint16_t* ax16 = (uint16_t*)(base + w.ax);
+  float* P = (float*)(base + w.p);
+  uint16_t* wt16 = (uint16_t*)(base + w.wt);
+  float* part = (float*)(base + w.part);
+  const long long dz_plane = blocks * Cout * 128, ax_plane = rows * w.cinp;
+  const DropCfg dc = wf_drop_cfg(p_drop, rng, site);
+  wf_ss_dz_tb8_kernel<<<(unsigned)blocks, 128, 0, st>>>(dY, Y, Cout, R, tpw, rpt, relu, dc, dz16, dz_plane);
+  WF_CHECK_LAUNCH("ss_dz_tb8");
+  int rc;
+  if (dW != nullptr || db != nullptr) {
+    WF_REQUIRE(dW != nullptr, "gcn_layer_bwd_ss: db comes with dW");
+    wf_ss_ax_rows_kernel<<<(unsigned)wf_cdiv(rows, 8), 256, 0, st>>>(X, Cin, w.cinp, R, rows, rowptr, col, val, ax16, ax_plane);
+    WF_CHECK_LAUNCH("ss_ax_rows");
+    const int nh = w.cinp / 128;
+    const void* src[2] = {ax16, ax16};
+    const long long plane[2] = {ax_plane, ax_plane};
+    const int var[2] = {1, 1}, shift[2] = {0, 0}, col0[2] = {0, 128}, ch[2] = {w.cinp, w.cinp};
+    const int w0 = Cin < 128 ? Cin : 128, w1 = Cin > 128 ? Cin - 128 : 0;
+    rc = wf_ss_launch_wgrad(dz16, dz_plane, nh, src, plane, var, shift, col0, ch, 1, R, Bw, 1, part,
+                            (size_t)w.splits_max * Cout * (w.cinp + 1), dW, Cin, w0, w1 > 0 ? dW + 128 : nullptr, Cin, w1, db, nullptr, 0,
+                            err, st, Cout);
+    if (rc) return rc;
+  }
+  if (dX != nullptr) {
+    wf_ss_wt_split_kernel<<<wf_cdiv((long long)Cin * Cout, 256), 256, 0, st>>>(W, Cout, Cin, wt16, (long long)Cin * Cout);
+    WF_CHECK_LAUNCH("ss_wt_split");
+    rc = wf_ss_launch_nodes(128, SS_A_KT, dz16, dz_plane, Cout, 1, wt16, wt16 + (long long)Cin * Cout, Cout, 0, Cin, 1, nullptr, nullptr,
+                            0, P, 1, R, Bw, 1, nullptr, err, st, 1);
+    if (rc) return rc;
+    wf_ss_dx_finish_kernel<<<(unsigned)blocks, 128, 0, st>>>(P, Cin, R, tpw, rpt, rowptr_t, col_t, val_t, dX);
+    WF_CHECK_LAUNCH("ss_dx_finish");
+  }
+  return WF_OK;
+}
+
 // ---- test entry points: the two kernels on operands given as plain 16-bit planes, so that every operand layout
 // (K-major SWIZZLE_64B / TB8 K-major / TB8 MN-major / row-major MN-major SWIZZLE_128B, fp16 and bf16) can be checked
 // against a float64 product in isolation (tests/test_gpu_ss.py).
@@ -1049,7 +1268,7 @@ extern "C" int wf_ss_wgrad(const void* dg16, long long dg_plane, int nh, const v
   const long long plane[2] = {b0_plane, b1_plane};
   const int var[2] = {b0var, b1var}, shift[2] = {b0shift, b1shift}, col0[2] = {b0col0, b1col0}, ch[2] = {b0C, b1C};
   return wf_ss_launch_wgrad(dg16, dg_plane, nh, src, plane, var, shift, col0, ch, T, Nn, Bw, G, part, (size_t)part_floats, dst0,
-                            ld0, w0, dst1, ld1, w1, db, nullptr, gstride, err, (cudaStream_t)stream);
+                            ld0, w0, dst1, ld1, w1, db, nullptr, gstride, err, (cudaStream_t)stream, 512);
 }
 
 #ifdef WF_SS_TRACE

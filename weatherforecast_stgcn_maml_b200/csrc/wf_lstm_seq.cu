@@ -44,7 +44,7 @@ int wf_ss_launch_nodes(int bn, int avar, const void* A16, long long a_plane, int
 int wf_ss_launch_wgrad(const void* dg16, long long dg_plane, int nh, const void* const* bsrc, const long long* bplane,
                        const int* bvar, const int* bshift, const int* bcol0, const int* bC, int T, int Nn, int Bw, int G,
                        float* part, size_t part_floats, float* dst0, int ld0, int w0, float* dst1, int ld1, int w1, float* db1,
-                       float* db2, long long gstride, int* err, cudaStream_t st);
+                       float* db2, long long gstride, int* err, cudaStream_t st, int M = 512);
 int wf_launch_split16(const float* src, long long src_gstride, void* hi, void* lo, long long dst_gstride, long long n, int G,
                       int fmt, cudaStream_t st);
 int wf_launch_transpose_split16(const float* in, long long in_gstride, int rows, int cols, void* out_hi, void* out_lo,

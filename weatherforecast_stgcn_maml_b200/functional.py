@@ -116,7 +116,9 @@ def check(device=None):
 class GCNConvReLU(torch.autograd.Function):
     """Y = dropout([relu]((A_hat X) W^T + b)) for one or more windows sharing a graph.
 
-    forward: wf_gcn_layer_fwd_g16 (tensor cores) or wf_gcn_layer_fwd (FP32); backward: wf_gcn_layer_bwd.
+    forward: wf_gcn_layer_fwd_g16 (tensor cores) or wf_gcn_layer_fwd (FP32); backward: wf_gcn_layer_bwd_ss (tensor
+    cores: dZ written once as bf16 hi/lo planes, dW / db by the MN-major weight-gradient kernel, dX by the SS GEMM +
+    transposed aggregation) or wf_gcn_layer_bwd (FP32, and widths the tensor-core path does not cover).
     ``p_drop`` > 0 applies nn.Dropout after the ReLU (model.py:33-42) as site ``site`` (the layer index)."""
 
     @staticmethod
@@ -163,11 +165,26 @@ class GCNConvReLU(torch.autograd.Function):
         graph, bw = ctx.graph, ctx.bw
         rows, cin = x.shape
         cout = weight.shape[0]
-        dy = _f32c(dy).clone()  # overwritten with dY * mask * (Y > 0)
         need_x, need_w, need_b = ctx.needs_input_grad[0], ctx.needs_input_grad[1], ctx.needs_input_grad[2]
         dx = torch.empty_like(x) if need_x else None
         dw = torch.empty_like(weight) if need_w else None
         db = torch.empty(cout, dtype=torch.float32, device=x.device) if need_b else None
+        fast = (_PRECISION == "tf32x3" and cout % 128 == 0 and cin % 8 == 0 and cin <= 256 and (not need_x or cin % 128 == 0)
+                and (need_w or not need_b))
+        if fast:
+            dy = _f32c(dy)
+            nbytes = int(_lib.query("wf_gcn_layer_bwd_ss_workspace_bytes", graph.R, cin, cout, bw))
+            ws = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
+            with torch.cuda.device(x.device):
+                st = _state(x.device)
+                st.poll_errors()
+                _lib.call("wf_gcn_layer_bwd_ss", _lib.ptr(x), _lib.ptr(y), _lib.ptr(dy), _lib.ptr(weight), _lib.ptr(graph.rowptr),
+                          _lib.ptr(graph.col), _lib.ptr(graph.val), _lib.ptr(graph.rowptr_t), _lib.ptr(graph.col_t),
+                          _lib.ptr(graph.val_t), graph.R, cin, cout, bw, int(ctx.relu), ctx.p_drop, _lib.ptr(ctx.snap), ctx.site,
+                          _lib.ptr(dx), _lib.ptr(dw), _lib.ptr(db), _lib.ptr(ws), nbytes, _lib.ptr(st.err), _lib.stream_ptr())
+                st.publish_errors()
+            return dx, dw, db, None, None, None, None, None
+        dy = _f32c(dy).clone()  # overwritten with dY * mask * (Y > 0)
         nbytes = int(_lib.query("wf_gcn_layer_bwd_workspace_bytes", graph.R, cin, cout, 1, bw))
         ws = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
         with torch.cuda.device(x.device):
