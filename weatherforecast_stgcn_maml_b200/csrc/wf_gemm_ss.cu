@@ -198,6 +198,14 @@ wf_ss_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   uint8_t* sStg = sA + a.nst * SS_A_STAGE;
   __shared__ uint64_t full[SS_MAX_STAGES], empty[SS_MAX_STAGES], dfull[2], dempty[2], bfull, bempty;
   __shared__ uint32_t tmem_base_s;
+  // bias + bias2 of this CTA's columns for the current group, two copies (toggled per group change): every epilogue warp
+  // fills the copy itself (identical values, no CTA-wide barrier that a timed-out warp could leave hanging), and a warp
+  // is never more than two tiles ahead of the slowest one (TMEM double buffer), so the older copy is never rewritten
+  // while still being read
+  // (256-column parts only: they run two ring stages, the narrower ones have 160 bytes of shared memory left and read
+  // the bias through __ldg)
+  constexpr bool SBIAS = BN == 256;
+  __shared__ __align__(16) float sbias[2][SBIAS ? BN : 4];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int NST = a.nst;
 
@@ -323,15 +331,26 @@ wf_ss_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     const int q = warp & 3, row = q * 32 + lane;
     const uint32_t tlane = tbase + ((uint32_t)(q * 32) << 16);
     uint8_t* stg = sStg + (warp - 2) * 8192;   // [plane][32 rows][128 B], 16-byte chunks XOR-swizzled by (row & 7)
-    int lt = 0;
+    int lt = 0, gbias = -1, bsel = 1;
     bool ok = true;
+    const bool has_bias = (a.bias != nullptr || a.bias2 != nullptr) && kpart == 0;
     for (int mt = mt0; mt < mt1 && ok; ++mt, ++lt) {
       const SsTile t = ss_decode(a, mt);
       const int ds = lt & 1;
+      const float* b1 = has_bias && a.bias ? a.bias + t.g * a.bias_gstride + n0 : nullptr;
+      const float* b2 = has_bias && a.bias2 ? a.bias2 + t.g * a.bias_gstride + n0 : nullptr;
+      if (SBIAS && has_bias && t.g != gbias) {
+        // the summed bias row of this group goes to shared memory once (16 global loads per 8 stores in the column loop
+        // cost the store-bound projections 15-20 %)
+        bsel ^= 1;
+        for (int c = lane; c < BN; c += 32)
+          sbias[bsel][c] = (a.bias ? __ldg(a.bias + t.g * a.bias_gstride + n0 + c) : 0.f) +
+                           (a.bias2 ? __ldg(a.bias2 + t.g * a.bias_gstride + n0 + c) : 0.f);
+        __syncwarp();
+        gbias = t.g;
+      }
       if (!mbar_wait(&dfull[ds], (lt >> 1) & 1)) { if (lane == 0) atomicExch(a.err, 56); ok = false; break; }
       tc_fence_after();
-      const float* b1 = a.bias && kpart == 0 ? a.bias + t.g * a.bias_gstride + n0 : nullptr;
-      const float* b2 = a.bias2 && kpart == 0 ? a.bias2 + t.g * a.bias_gstride + n0 : nullptr;
       DropState dst;
       if (DROP) dst = wf_drop_state(a.drop);
       if (a.epi == SS_E_TB4) {
@@ -346,8 +365,12 @@ wf_ss_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
             float4 o = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
-            if (b1) { const float4 b = __ldg(reinterpret_cast<const float4*>(b1 + cc + j)); o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w; }
-            if (b2) { const float4 b = __ldg(reinterpret_cast<const float4*>(b2 + cc + j)); o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w; }
+            if (SBIAS) {
+              if (has_bias) { const float4 b = *reinterpret_cast<const float4*>(&sbias[bsel][cc + j]); o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w; }
+            } else {
+              if (b1) { const float4 b = __ldg(reinterpret_cast<const float4*>(b1 + cc + j)); o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w; }
+              if (b2) { const float4 b = __ldg(reinterpret_cast<const float4*>(b2 + cc + j)); o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w; }
+            }
             if (DROP) {
               float m[4];
               wf_drop4(dst, e4row + (unsigned)((cc + j) >> 2), m);
@@ -411,7 +434,11 @@ wf_ss_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
               for (int e = 0; e < 8; e += 4) {
                 float4 o = make_float4(__uint_as_float(v[j + e]), __uint_as_float(v[j + e + 1]), __uint_as_float(v[j + e + 2]),
                                        __uint_as_float(v[j + e + 3]));
-                if (b1) { const float4 b = __ldg(reinterpret_cast<const float4*>(b1 + cc + j + e)); o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w; }
+                if (SBIAS) {
+                  if (has_bias) { const float4 b = *reinterpret_cast<const float4*>(&sbias[bsel][cc + j + e]); o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w; }
+                } else if (b1) {
+                  const float4 b = __ldg(reinterpret_cast<const float4*>(b1 + cc + j + e)); o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
+                }
                 if (a.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
                 if (DROP) {
                   float m[4];
@@ -756,7 +783,10 @@ int ss_sms() {
 template <int BN>
 int ss_launch_bn(const CUtensorMap& tmA, const CUtensorMap& tmA2, const CUtensorMap& tmBhi, const CUtensorMap& tmBlo,
                  const CUtensorMap& tmOut, const CUtensorMap& tmOut2, SsArgs& a, cudaStream_t st) {
-  a.nst = a.epi == SS_E_HL ? 2 : 3;
+  // ring depth: 3 stages of 32 KB next to the resident weights, 2 where the epilogue needs the staging buffer -- and 2 for
+  // K <= 128 (two k-blocks per tile): those GEMMs are bound by their stores, and a third load in flight costs 13 %
+  // (h -> gates projection: 107.8 us with 3 stages, 93.7 us with 2; K >= 256: 141 vs 170 us the other way round)
+  a.nst = (a.epi == SS_E_HL || a.nkb <= 2) ? 2 : 3;
   static const int dbg = getenv("WF_SS_DEBUG") ? atoi(getenv("WF_SS_DEBUG")) : 0;
   a.debug = dbg;
   static const int pf_env = getenv("WF_SS_PF") ? atoi(getenv("WF_SS_PF")) : 0;
@@ -765,8 +795,10 @@ int ss_launch_bn(const CUtensorMap& tmA, const CUtensorMap& tmA2, const CUtensor
   if (nst_env > 0 && nst_env < a.nst) a.nst = nst_env;
   const int smem = SS_B_BYTES + a.nst * SS_A_STAGE + (a.epi == SS_E_HL ? SS_STG_BYTES : 0) + 1024;
   static bool configured = false;
+  // 256-column parts always run with two stages (K <= 128): their static shared memory (bias copies) is 2 KB
+  const int mx = SS_B_BYTES + (BN == 256 ? 2 : 3) * SS_A_STAGE + 1024;
+  WF_REQUIRE(smem <= mx, "ss kernel: %d bytes of shared memory for %d-column parts (limit %d)", smem, BN, mx);
   if (!configured) {
-    const int mx = SS_B_BYTES + 3 * SS_A_STAGE + 1024;
     if (cudaFuncSetAttribute(wf_ss_kernel<BN, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx) != cudaSuccess ||
         cudaFuncSetAttribute(wf_ss_kernel<BN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx) != cudaSuccess)
       return wf_fail(WF_ECUDA, "ss kernel: cannot raise dynamic shared memory to %d", mx);
