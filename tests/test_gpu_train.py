@@ -407,3 +407,65 @@ def test_meta_checkpoint_layout_and_real_resume():
     assert torch.equal(a.adam.exp_avg_sq, b.adam.exp_avg_sq)
     with pytest.raises(ValueError):
         ck.resume(b, sched_b, {**ckpt, "config": {**ckpt["config"], "window_size": 7}})
+
+
+def test_task_slots_and_epoch_driver(tmp_path):
+    """The reference's main() loop (train_hybrid_maml_v5.py:242-372): BATCH_SIZE tasks sampled per epoch out of all
+    regions, one meta-update, cosine schedule, CSV log, best / final checkpoints.  ``MetaTrainer(slots=...)`` keeps all
+    tasks resident and re-points its slots between (graph-replayed) meta-steps."""
+    from weatherforecast_stgcn_maml_b200 import checkpoint as ck
+    from weatherforecast_stgcn_maml_b200.embed_utils import KoppenEmbedding
+    from weatherforecast_stgcn_maml_b200.schedule import AdaptiveTaskSampler, CosineWarmRestarts
+    from weatherforecast_stgcn_maml_b200.train_hybrid_maml_v5 import MetaTrainer, train_meta
+
+    z, cfg, sd, feats, ei, dims = _small_cfg()
+    lats, lons = synth.region_grid(cfg["nlat"], cfg["nlon"])
+    eis = [ei, P.knn_edges_ckdtree(lats * 1.7, lons, 4), P.knn_edges_ckdtree(lats, lons * 2.3, 4), ei, ei]
+    tasks = [(synth.synth_features(feats.shape[0], feats.shape[1], 100 + i), eis[i]) for i in range(5)]
+    kw = dict(dropout=(0, 0, 0), support_rows=(0, 1, 2), query_row=3)
+    # (1) a slot trainer pointed at tasks (3, 1) is the plain trainer over those two tasks, bit for bit -- also after the
+    # graph has been captured for another assignment
+    slot = MetaTrainer(sd, tasks, dims, "cuda", slots=2, **kw)
+    assert slot.G == 2 and slot.num_tasks == 5 and slot.active == [0, 1]
+    slot.meta_step()
+    slot.read_loss()
+    slot.load_state_dict(sd)            # back to the initial weights (re-captures), fresh AdamW state
+    slot.adam.exp_avg.zero_(); slot.adam.exp_avg_sq.zero_(); slot.adam.step_count = 0
+    slot.assign([3, 1])
+    plain = MetaTrainer(sd, [tasks[3], tasks[1]], dims, "cuda", **kw)
+    for _ in range(2):
+        slot.meta_step(); plain.meta_step()
+    assert slot.read_loss() == plain.read_loss()
+    assert torch.equal(slot.theta, plain.theta)
+    with pytest.raises(ValueError):
+        slot.assign([0, 1, 2])
+    # (2) the epoch driver
+    np.random.seed(42)
+    tr = MetaTrainer(sd, tasks, dims, "cuda", slots=2, **kw)
+    out = train_meta(tr, KoppenEmbedding(8).state_dict(), num_epochs=4, batch_size=2, save_dir=str(tmp_path / "SavedModels"),
+                     log_file=str(tmp_path / "log.csv"), verbose=False)
+    np.random.seed(42)                   # the draws and the schedule, replayed on their own
+    sampler, sched, twin = AdaptiveTaskSampler(5, 2), CosineWarmRestarts(1e-3), MetaTrainer(sd, tasks, dims, "cuda", slots=2, **kw)
+    ref_opt = torch.optim.SGD([torch.nn.Parameter(torch.zeros(1))], lr=1e-3)
+    ref_sched = torch.optim.lr_scheduler.CosineAnnealingWarmRestarts(ref_opt, T_0=10, T_mult=2, eta_min=1e-6)
+    for epoch in range(4):
+        ids = sampler.sample()
+        twin.assign(ids)
+        twin.meta_step()
+        loss = twin.read_loss()
+        sampler.update(loss)
+        sched.step(); ref_opt.step(); ref_sched.step()
+        twin.set_lr(sched.get_last_lr()[0])
+        assert loss == out["losses"][epoch]
+        assert abs(out["lrs"][epoch] - ref_sched.get_last_lr()[0]) <= 1e-15
+    assert torch.equal(twin.theta, tr.theta)
+    lines = open(tmp_path / "log.csv").read().strip().splitlines()
+    assert lines[0] == "epoch,meta_loss,learning_rate" and len(lines) == 5
+    assert [float(l.split(",")[1]) for l in lines[1:]] == out["losses"]
+    best = torch.load(out["best_path"], weights_only=False)
+    final = torch.load(out["final_path"], weights_only=False)
+    assert best["best_loss"] == min(out["losses"]) == out["best_loss"] and best["epoch"] == int(np.argmin(out["losses"]))
+    assert final["epoch"] == 4 and final["final_loss"] == out["losses"][-1] and "final_loss" not in best
+    fresh, fsched = MetaTrainer(sd, tasks, dims, "cuda", slots=2, **kw), CosineWarmRestarts(1e-3)
+    epoch, best_loss = ck.resume(fresh, fsched, final)
+    assert (epoch, best_loss) == (4, out["best_loss"]) and torch.equal(fresh.theta, tr.theta) and fresh.adam.step_count == 4

@@ -237,3 +237,35 @@ def test_feature_assembly_has_no_cpu_fallback():
         feature_stats(w)
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         assemble_features(w, np.zeros((4, 4), dtype=np.float32), np.zeros(8, dtype=np.float32))
+
+
+def test_accumulation_groups_follow_the_reference_loop():
+    """train_hybrid_maml_v5.py:151-179: which tasks contribute to which optimiser step, including the reference's
+    behaviour for missing (None) tasks at boundary positions."""
+    import itertools
+
+    from weatherforecast_stgcn_maml_b200.train_hybrid_maml_v5 import reference_accumulation_groups
+
+    def reference_loop(tasks, accum):
+        steps, pending = [], []
+        for i, (support, _q, _s) in enumerate(tasks):
+            if support is None:
+                continue
+            pending.append(support)
+            if (i + 1) % accum == 0 or i == len(tasks) - 1:
+                steps.append((pending, True))
+                pending = []
+        if pending:
+            steps.append((pending, False))  # gradients computed, never applied
+        return steps
+
+    for n in range(0, 7):
+        for accum in (1, 2, 3):
+            for present in itertools.product([True, False], repeat=n):
+                tasks = [(f"s{i}" if p else None, f"q{i}", {}) for i, p in enumerate(present)]
+                got = [([t[0] for t in g], step) for g, step in reference_accumulation_groups(tasks, accum)]
+                assert got == reference_loop(tasks, accum), (present, accum)
+    # the all-present case is plain chunks of `accum` with a step after each
+    tasks = [(f"s{i}", None, {}) for i in range(5)]
+    assert [([t[0] for t in g], s) for g, s in reference_accumulation_groups(tasks, 2)] == [
+        (["s0", "s1"], True), (["s2", "s3"], True), (["s4"], True)]

@@ -101,6 +101,18 @@ class StackedGraphs:
         for i, l in enumerate(lists):
             self.gather_rows[i, :l.numel()] = l
 
+    def assign(self, slot, graph):
+        """Overwrite slot ``slot`` with another region's normalised graph, in place (the stacked tensors keep their
+        addresses, so captured CUDA graphs that read them stay valid).  Stream-ordered device copies."""
+        if graph.R != self.R or graph.cap != self.cap:
+            raise ValueError("stacked regions must share the row count and edge capacity")
+        if graph.agg_rows > self.agg_rows or int(graph.gather_rows.numel()) > self.gather_rows.shape[1]:
+            raise ValueError("the region has more rows with neighbours than the stack was built for")
+        for name in ("rowptr", "col", "val", "rowptr_t", "col_t", "val_t"):
+            getattr(self, name)[slot].copy_(getattr(graph, name), non_blocking=True)
+        self.gather_rows[slot].fill_(-1)
+        self.gather_rows[slot, :graph.gather_rows.numel()] = graph.gather_rows
+
     @property
     def rowptr_stride(self):
         return self.R + 1 if self.G > 1 else 0

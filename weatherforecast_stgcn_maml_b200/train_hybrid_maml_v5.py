@@ -194,9 +194,14 @@ def _runner(dims, G, device, dropout=(0.0, 0.0, 0.0)):
     return _RUNNERS[key]
 
 
+_STAGE_CACHE = {}   # (datasets, rows, dims, device) -> staged group; the reference revisits the same groups every epoch
+_STAGE_CACHE_MAX = 8
+
+
 def _stage_group(group, dims, device, support_steps_fn, query_pick):
-    """group: [(support_ds, query_ds)] -> stager, graphs, offset tables."""
-    task_windows, graphs, sup_rows, qry_rows = [], [], [], []
+    """group: [(support_ds, query_ds)] -> stager, graphs, offset tables.  The result (device staging buffer, stacked CSR,
+    offset tables) is memoised for the last few distinct groups: same datasets, same windows -> same buffers."""
+    task_windows, graphs, sup_rows, qry_rows, owners = [], [], [], [], []
     for support_ds, query_ds in group:
         sds, sidx = unwrap_subset(support_ds)
         qds, qidx = unwrap_subset(query_ds)
@@ -209,9 +214,15 @@ def _stage_group(group, dims, device, support_steps_fn, query_pick):
         graphs.append(_task_graph(sds, dims, device))
         sup_rows.append(srows)
         qry_rows.append(qrow)
+        owners.append(sds)
     n_steps = len(sup_rows[0])
     if any(len(r) != n_steps for r in sup_rows):
         raise ValueError("tasks of one accumulation group must take the same number of inner steps")
+    key = (tuple(id(o) for o in owners), tuple(tuple(w[1]) for w in task_windows), dims, str(torch.device(device)))
+    hit = _STAGE_CACHE.get(key)
+    if hit is not None and all(a is b for a, b in zip(hit[0], owners)):
+        _STAGE_CACHE[key] = _STAGE_CACHE.pop(key)  # most recently used last
+        return hit[1]
     stager = HostTaskStager(task_windows, dims, device)
     G = len(group)
     sup_x = torch.empty(n_steps, G, dtype=torch.long)
@@ -223,7 +234,11 @@ def _stage_group(group, dims, device, support_steps_fn, query_pick):
             sup_x[s, g], sup_t[s, g] = stager.offsets(g, row)
         qry_x[g], qry_t[g] = stager.offsets(g, qry_rows[g])
     dev = torch.device(device)
-    return stager, StackedGraphs(graphs), sup_x.to(dev), sup_t.to(dev), qry_x.to(dev), qry_t.to(dev)
+    staged = (stager, StackedGraphs(graphs), sup_x.to(dev), sup_t.to(dev), qry_x.to(dev), qry_t.to(dev))
+    _STAGE_CACHE[key] = (owners, staged)  # holds the datasets, so the ids in the key stay theirs
+    while len(_STAGE_CACHE) > _STAGE_CACHE_MAX:
+        _STAGE_CACHE.pop(next(iter(_STAGE_CACHE)))
+    return staged
 
 
 def _load_flat_into(model, flat, dims):
@@ -266,23 +281,42 @@ def inner_loop_v4(hybrid_model, koppen_embed, support_ds, device):
     return temp_model, temp_koppen
 
 
+def reference_accumulation_groups(tasks, accum=GRAD_ACCUMULATION_STEPS):
+    """[(tasks of the group, optimiser step afterwards?)] exactly as the reference's loop forms them
+    (train_hybrid_maml_v5.py:151-179): the boundary test ``(i + 1) % accum == 0 or i == len(tasks) - 1`` uses the
+    position in the ORIGINAL list and sits behind the ``continue`` of a missing task, so a ``None`` task at a boundary
+    position postpones the step to the next boundary, and gradients left over when the last task is missing are never
+    applied (the next call's ``zero_grad`` discards them)."""
+    groups, cur = [], []
+    n = len(tasks)
+    for i, t in enumerate(tasks):
+        if t[0] is None:
+            continue
+        cur.append(t)
+        if (i + 1) % accum == 0 or i == n - 1:
+            groups.append((cur, True))
+            cur = []
+    if cur:
+        groups.append((cur, False))
+    return groups
+
+
 def meta_update_v4(hybrid_model, koppen_embed, tasks, device, meta_optimizer, literal_reference=False,
                    grad_accumulation_steps=None, support_schedule=None):
     """train_hybrid_maml_v5.py:144-184 -- one meta-update over ``tasks``.
 
     ``tasks`` is the reference's list of ``(support_ds, query_ds, stats)``.  Tasks are processed
-    in accumulation groups of GRAD_ACCUMULATION_STEPS (an optimiser step after each group, as
-    at :173-179); inside a group all tasks run in lock-step on one batched engine.  Returns the
-    reference's ``meta_loss`` (sum of query_loss / GRAD_ACCUMULATION_STEPS)."""
+    in the reference's accumulation groups (``reference_accumulation_groups``: an optimiser step at the
+    positions :173-179 take one, missing tasks skipped the way the reference skips them); inside a
+    group all tasks run in lock-step on one batched engine.  Returns the reference's ``meta_loss``
+    (sum of query_loss / GRAD_ACCUMULATION_STEPS)."""
     accum = GRAD_ACCUMULATION_STEPS if grad_accumulation_steps is None else int(grad_accumulation_steps)
     schedule = reference_support_schedule if support_schedule is None else support_schedule
-    tasks = [t for t in tasks if t[0] is not None]
     meta_loss = 0.0
     meta_optimizer.zero_grad()
     named = dict(hybrid_model.named_parameters())
     all_params = list(hybrid_model.parameters()) + list(koppen_embed.parameters())
-    for start in range(0, len(tasks), accum):
-        group = tasks[start:start + accum]
+    for group, do_step in reference_accumulation_groups(list(tasks), accum):
         sds, _ = unwrap_subset(group[0][0])
         dims = _model_dims(hybrid_model, sds.num_nodes)
         sd = {k: v.detach() for k, v in hybrid_model.state_dict().items()}
@@ -301,9 +335,10 @@ def meta_update_v4(hybrid_model, koppen_embed, tasks, device, meta_optimizer, li
                 p = named[name]
                 p.grad = g.clone() if p.grad is None else p.grad + g
         meta_loss += float(loss)  # the reference's .item() sync (train_hybrid_maml_v5.py:170)
-        torch.nn.utils.clip_grad_norm_(all_params, max_norm=1.0)
-        meta_optimizer.step()
-        meta_optimizer.zero_grad()
+        if do_step:
+            torch.nn.utils.clip_grad_norm_(all_params, max_norm=1.0)
+            meta_optimizer.step()
+            meta_optimizer.zero_grad()
     return meta_loss
 
 
@@ -326,20 +361,35 @@ class MetaTrainer:
     def __init__(self, state_dict, tasks, dims: V5Dims, device="cuda", support_rows=(0, 1, 2), query_row=None,
                  inner_lr=INNER_LR, outer_lr=OUTER_LR, weight_decay=1e-4, accum=None, use_cuda_graph=True,
                  process_group=None, distributed=None, host_staging=False, dropout=REFERENCE_DROPOUT, seed=SEED,
-                 fused_update=None):
+                 fused_update=None, slots=None):
+        """``slots`` < len(tasks): every meta-step runs ``slots`` of the tasks (the reference samples BATCH_SIZE = 4 of
+        its 15 regions per meta-update, train_hybrid_maml_v5.py:262-281); all tasks' features and graphs stay resident and
+        ``assign(task_ids)`` re-points the slots between steps -- offset tables and the stacked CSR are rewritten in
+        place, outside the captured graph, which keeps replaying."""
         import torch.distributed as dist
 
         self.dims, self.device = dims, torch.device(device)
         self.dist = dist if (distributed if distributed is not None else dist.is_initialized()) else None
         self.pg = process_group
         self.world = self.dist.get_world_size(self.pg) if self.dist else 1
-        self.G = len(tasks)
+        self.num_tasks = len(tasks)
+        self.G = self.num_tasks if slots is None else int(slots)
+        if not (0 < self.G <= self.num_tasks):
+            raise ValueError(f"slots={slots} must lie in 1..{self.num_tasks}")
+        if self.G < self.num_tasks and host_staging:
+            raise ValueError("task slots need resident features (host_staging=False)")
         d = dims
         feats = [f for f, _ in tasks]
         time_rows = feats[0].shape[0]
         if any(tuple(f.shape) != (time_rows, d.num_nodes, d.in_channels) for f in feats):
             raise ValueError("all tasks of a rank must share the features shape [time, N, C]")
-        self.graphs = StackedGraphs([RegionGraph(ei, d.R, self.device) for _, ei in tasks])
+        self.task_graphs = [RegionGraph(ei, d.R, self.device) for _, ei in tasks]
+        if self.G < self.num_tasks:  # the stack must be able to hold any of the regions
+            big = max(self.task_graphs, key=lambda g: (g.agg_rows, int(g.gather_rows.numel())))
+            self.graphs = StackedGraphs([big] * self.G)
+        else:
+            self.graphs = StackedGraphs(self.task_graphs)
+        self.active = list(range(self.G))
         span = d.window + 1 + d.horizon
         if query_row is None:
             query_row = int(0.75 * min(600, time_rows - d.window - d.horizon))  # first query window (:95-102)
@@ -358,10 +408,13 @@ class MetaTrainer:
         else:
             self.features = torch.stack([f.to(self.device, torch.float32) for f in feats]).contiguous()
             per_step, per_task = d.num_nodes * d.in_channels, time_rows * d.num_nodes * d.in_channels
+            self._per_step, self._per_task, self._rows = per_step, per_task, torch.tensor(rows, dtype=torch.long)
             base = torch.arange(self.G, dtype=torch.long) * per_task
-            r = torch.tensor(rows, dtype=torch.long)
+            r = self._rows
             self.x_off = (base[None, :] + r[:, None] * per_step).to(self.device)             # [steps+1, G]
             self.t_off = (base[None, :] + (r[:, None] + d.window + 1) * per_step).to(self.device)
+            if self.G < self.num_tasks:
+                self.assign(self.active)
         self.n_inner = len(support_rows)
         self.inner_lr, self.accum = float(inner_lr), float(accum if accum is not None else self.G * self.world)
         self.sd = {k: v.detach().clone() for k, v in state_dict.items()}
@@ -381,6 +434,24 @@ class MetaTrainer:
         self.fused_update = bool(fused_update) and self.use_graph
         self._copy = None
         self.launches_per_step = None
+
+    def assign(self, task_ids):
+        """Point the G slots at ``task_ids`` (indices into the constructor's task list) for the following meta-steps."""
+        ids = [int(t) for t in task_ids]
+        if len(ids) != self.G or any(not (0 <= t < self.num_tasks) for t in ids):
+            raise ValueError(f"assign() takes {self.G} task indices in 0..{self.num_tasks - 1}")
+        if self.stager is not None:
+            raise RuntimeError("task slots need resident features (host_staging=False)")
+        d = self.dims
+        with torch.cuda.device(self.device):
+            base = torch.tensor(ids, dtype=torch.long) * self._per_task
+            r = self._rows
+            self.x_off.copy_((base[None, :] + r[:, None] * self._per_step), non_blocking=False)
+            self.t_off.copy_((base[None, :] + (r[:, None] + d.window + 1) * self._per_step), non_blocking=False)
+            for slot, t in enumerate(ids):
+                if self.G < self.num_tasks or t != slot:
+                    self.graphs.assign(slot, self.task_graphs[t])
+        self.active = ids
 
     # the captured region: no host interaction, fixed pointers
     def _body(self):
@@ -523,3 +594,61 @@ class MetaTrainer:
         if cache is not None:
             cache.clear()
         self.cuda_graphs = [None, None]                # ... which the captured graphs read: capture again
+
+
+def train_meta(trainer, koppen_state_dict, num_epochs=NUM_EPOCHS, batch_size=BATCH_SIZE, save_dir="./Out_Data/SavedModels",
+               log_file="./Out_Data/hybrid_maml_v5_log.csv", scheduler=None, start_epoch=0, best_loss=float("inf"),
+               lstm_dropout=0.2, verbose=True):
+    """The epoch loop of the reference's ``main()`` (train_hybrid_maml_v5.py:242-372) around a ``MetaTrainer``:
+
+    per epoch -- draw the meta-batch (``schedule.AdaptiveTaskSampler``: BATCH_SIZE of the tasks without replacement,
+    numpy's global RNG, the reference's degenerate difficulty weights), one meta-update, update the difficulties,
+    ``CosineAnnealingWarmRestarts(T_0=10, T_mult=2, eta_min=1e-6).step()``, append ``epoch,meta_loss,learning_rate`` to
+    the CSV log, save ``hybrid_maml_model_v5_best.pt`` when the loss improves; after the loop save
+    ``hybrid_maml_model_v5_final.pt``.  Checkpoints are the reference's dicts (``checkpoint.meta_checkpoint``), so
+    either implementation resumes from the other's files (``checkpoint.resume`` -> ``start_epoch`` / ``best_loss``).
+
+    ``trainer`` was built over ALL tasks with ``slots=min(batch_size, num_tasks)`` (or without slots when the task list
+    is no longer than the batch).  Returns ``{"losses", "lrs", "best_loss", "best_path", "final_path"}``."""
+    from . import checkpoint as CK
+    from .schedule import AdaptiveTaskSampler, CosineWarmRestarts
+
+    n = trainer.num_tasks
+    if trainer.G != min(int(batch_size), n):
+        raise ValueError(f"the trainer runs {trainer.G} tasks per meta-step, the meta-batch is {min(int(batch_size), n)}")
+    sampler = AdaptiveTaskSampler(n, batch_size)
+    sched = scheduler if scheduler is not None else CosineWarmRestarts(trainer.adam.lr)
+    os.makedirs(save_dir, exist_ok=True)
+    if log_file:
+        os.makedirs(os.path.dirname(os.path.abspath(log_file)), exist_ok=True)
+        if start_epoch == 0 or not os.path.exists(log_file):
+            with open(log_file, "w") as f:
+                f.write("epoch,meta_loss,learning_rate\n")
+    best_path = os.path.join(save_dir, "hybrid_maml_model_v5_best.pt")
+    final_path = os.path.join(save_dir, "hybrid_maml_model_v5_final.pt")
+    losses, lrs, saved_best = [], [], None
+    for epoch in range(int(start_epoch), int(num_epochs)):
+        ids = sampler.sample()
+        if ids != trainer.active:
+            trainer.assign(ids)
+        trainer.meta_step()
+        loss = trainer.read_loss()          # the reference's .item(): one sync per epoch, raises on kernel-side errors
+        sampler.update(loss)
+        sched.step()
+        lr = sched.get_last_lr()[0]
+        trainer.set_lr(lr)
+        losses.append(loss)
+        lrs.append(lr)
+        if verbose:
+            print(f"Epoch {epoch + 1}/{num_epochs} - Loss: {loss:.4f} - LR: {lr:.6f}")
+        if log_file:
+            with open(log_file, "a") as f:
+                f.write(f"{epoch + 1},{loss},{lr}\n")
+        if loss < best_loss:
+            best_loss = loss
+            torch.save(CK.meta_checkpoint(trainer, koppen_state_dict, sched, epoch, best_loss, lstm_dropout=lstm_dropout), best_path)
+            saved_best = best_path
+    final_loss = losses[-1] if losses else float("nan")
+    torch.save(CK.meta_checkpoint(trainer, koppen_state_dict, sched, int(num_epochs), best_loss, lstm_dropout=lstm_dropout,
+                                  final_loss=final_loss), final_path)
+    return {"losses": losses, "lrs": lrs, "best_loss": best_loss, "best_path": saved_best, "final_path": final_path}
