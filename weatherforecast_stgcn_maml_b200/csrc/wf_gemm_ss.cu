@@ -147,7 +147,7 @@ __device__ __forceinline__ void ss_split_f16(float a, float b, uint32_t& hi, uin
 }
 
 #ifdef WF_SS_TRACE
-__device__ long long wf_ss_trace_buf[4 * 256];   // [role event][stage index], CTA 0 (tools/ss_trace.py)
+__device__ long long wf_ss_trace_buf[6 * 256];   // [role event][stage index], CTA 0 (tools/ss_trace.py)
 #define SS_TR(ev, i) do { if (blockIdx.x == 0 && (i) < 256) wf_ss_trace_buf[(ev) * 256 + (i)] = clock64(); } while (0)
 #else
 #define SS_TR(ev, i) do { } while (0)
@@ -351,6 +351,7 @@ wf_ss_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       }
       if (!mbar_wait(&dfull[ds], (lt >> 1) & 1)) { if (lane == 0) atomicExch(a.err, 56); ok = false; break; }
       tc_fence_after();
+      if (warp == 2 && lane == 0) SS_TR(4, lt);   // epilogue: accumulator complete
       DropState dst;
       if (DROP) dst = wf_drop_state(a.drop);
       if (a.epi == SS_E_TB4) {
@@ -474,6 +475,7 @@ wf_ss_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
       }
       tc_fence_before();
       __syncwarp();
+      if (warp == 2 && lane == 0) SS_TR(5, lt);   // epilogue: tile drained
       if (lane == 0) mbar_arrive(&dempty[ds]);
     }
     if (a.epi == SS_E_HL && lane == 0) tma_store_wait_all();
@@ -1305,6 +1307,6 @@ extern "C" int wf_ss_wgrad(const void* dg16, long long dg_plane, int nh, const v
 
 #ifdef WF_SS_TRACE
 extern "C" int wf_ss_trace_read(long long* host) {
-  return (int)cudaMemcpyFromSymbol(host, wf_ss_trace_buf, sizeof(long long) * 4 * 256);
+  return (int)cudaMemcpyFromSymbol(host, wf_ss_trace_buf, sizeof(long long) * 6 * 256);
 }
 #endif
