@@ -587,6 +587,68 @@ def module_api_ms(sd, dims, reps=10):
     return e0.elapsed_time(e1) / reps
 
 
+def validation_windows_per_sec(sd, dims, windows=240, reps=3):
+    """configs[2], second half (adapt_hybrid_v5.py:216-231): eval-mode forward + MSE over the 240 validation windows of a
+    region (16 windows per launch set); device-timed, loss read back once per sweep as the reference's average is."""
+    import torch
+
+    from weatherforecast_stgcn_maml_b200 import synth
+    from weatherforecast_stgcn_maml_b200.adapt_hybrid_v5 import FineTuner
+    from weatherforecast_stgcn_maml_b200.graphBuilder import knn_edge_index_device
+
+    lats, lons, feats, _ = synth.synth_task(8, num_windows=windows + 8, nlat=NLAT, nlon=NLON)
+    ei = knn_edge_index_device(lats, lons, KNN, "cuda")
+    ft = FineTuner(sd, feats, ei, dims, "cuda", region_name="bench", max_samples=windows, train_frac=0.0, dropout=(0, 0, 0))
+    idx = list(range(windows))
+    ft.validate(idx)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        ft.validate(idx)
+    e1.record()
+    torch.cuda.synchronize()
+    return windows * reps / (e0.elapsed_time(e1) * 1e-3)
+
+
+def reference_shape_record(sd, dims, reps=2):
+    """configs[1] in the reference's own shape (train_hybrid_maml_v5.py:110-184,262-281): a meta-update
+    over BATCH_SIZE = 4 sampled tasks, each adapted by 6 epochs x 15 support windows = 90 SGD steps + 1 query pass,
+    optimiser step after every GRAD_ACCUMULATION_STEPS = 2 tasks -- two captured graphs of 2 tasks x 91 window passes."""
+    import torch
+
+    from weatherforecast_stgcn_maml_b200.train_hybrid_maml_v5 import MetaTrainer, reference_support_schedule
+
+    tasks = build_tasks(0, 1)[:4]
+    rows = tuple(reference_support_schedule(list(range(450))))
+    trs = [MetaTrainer(sd, tasks[2 * i:2 * i + 2], dims, "cuda", use_cuda_graph=True, support_rows=rows, accum=2,
+                       dropout=(0, 0, 0)) for i in range(2)]
+
+    def update():
+        for tr in trs:
+            tr.theta.copy_(trs[0].theta)   # the second pair starts from the weights the first step produced (SURVEY.md A14)
+            tr.meta_step()
+        trs[0].theta.copy_(trs[1].theta)
+
+    update()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        update()
+    e1.record()
+    torch.cuda.synchronize()
+    for tr in trs:
+        tr.check()
+    sec = e0.elapsed_time(e1) * 1e-3 / reps
+    out = {"sec_per_meta_update": sec, "meta_updates_per_sec": 1.0 / sec, "window_passes_per_sec": 4 * 91 / sec,
+           "workload": "the reference's own meta-update: 4 tasks x (90 inner SGD steps over support windows 0..14 + 1 query "
+                       "pass), optimiser step every 2 tasks; 441 nodes, k=8, dropout off"}
+    del trs
+    torch.cuda.empty_cache()
+    return out
+
+
 def finetune_windows_per_sec(sd, dims, steps=96, warmup=16, dropout=(0.0, 0.0, 0.0)):
     """configs[2] shape (regional adaptation, adapt_hybrid_v5.py:185-203): batch-1 Adam steps on one 441-node region,
     windows visited in a shuffled order; device-timed.  Sequential by construction (one optimiser step per window), so
@@ -725,8 +787,10 @@ def run_gpu(args, rank, local, world):
     }
     line["finetune"] = {"windows_per_sec": finetune_windows_per_sec(sd, dims), "unit": "windows/s",
                         "windows_per_sec_dropout_on": finetune_windows_per_sec(sd, dims, dropout=REFERENCE_DROPOUT),
+                        "validation_windows_per_sec": validation_windows_per_sec(sd, dims),
                         "workload": "configs[2]: batch-1 Adam fine-tuning steps on one 441-node region (k=8), "
-                                    "forward + MSE + backward + clip + Adam per window, 1 GPU"}
+                                    "forward + MSE + backward + clip + Adam per window; validation = eval-mode forward + "
+                                    "MSE over 240 windows, 16 per launch set; 1 GPU"}
     if config5 is not None:
         line["config5"] = config5
     if world == 1:
@@ -737,6 +801,7 @@ def run_gpu(args, rank, local, world):
                                       "autograd, same tcgen05 kernels through a leased engine) vs the task-batched engine "
                                       "(meta-step time / 60 window passes)"}
         line["config4"] = config4_record(peak, tf_peak)
+        line["config2_reference_shape"] = reference_shape_record(sd, dims)
     if world == 1 and not args.no_cpu_baseline:
         sec, cores, kind = cpu_window_pass(3, 1)
         sec_p, _ = port_window_pass_seconds(2, 1, literal=True)
