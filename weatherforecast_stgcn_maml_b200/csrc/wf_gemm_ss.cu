@@ -75,8 +75,8 @@ struct SsArgs {
   int* err;
 };
 
-__host__ __device__ constexpr uint32_t ss_idesc(int n, uint32_t afmt, uint32_t bfmt, uint32_t a_mn, uint32_t b_mn) {
-  return (1u << 4) | (afmt << 7) | (bfmt << 10) | (a_mn << 15) | (b_mn << 16) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+__host__ __device__ constexpr uint32_t ss_idesc(int n, uint32_t afmt, uint32_t bfmt, uint32_t a_mn, uint32_t b_mn, int m = 128) {
+  return (1u << 4) | (afmt << 7) | (bfmt << 10) | (a_mn << 15) | (b_mn << 16) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 // shared-memory matrix descriptor: start address, leading / stride byte offsets, layout (0 none, 2 SWIZZLE_128B, 4 SWIZZLE_64B)
 __device__ __forceinline__ uint64_t ss_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo, uint32_t layout) {
@@ -705,6 +705,229 @@ wf_wg_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
   if (warp == 1) tmem_dealloc(tbase, 512);
 }
 
+// ---- the same product on CTA PAIRS (tcgen05 cta_group::2, M = 256): the two CTAs of a cluster own two neighbouring
+// 128-row tiles of dG's channels and HALF of the B columns each -- CTA r loads its own A tile (32 KB per stage) and columns
+// [r N/2, (r + 1) N/2) of [X | H_prev] (32 KB), and every instruction, issued by the leader CTA alone, reads A from each
+// CTA's own shared memory and the two B halves from both.  The one-CTA kernel ingests 96 KB per stage and SM (the four M
+// tiles re-read the activation columns: it is bound by the ~40 B/clk an SM pulls from L2); a pair ingests 64 KB per SM for
+// the same work, and three 64 KB stages fit where two 96 KB ones did.
+//   full[s]  (leader's): expect_tx of both CTAs' bytes; both producers' TMA loads complete on it (.cta_group::2 loads may
+//            signal an mbarrier of the peer CTA)
+//   empty[s], dfull: tcgen05.commit multicast to both CTAs
+//   dempty   (leader's): 8 arrivals, the peer's epilogue warps arrive through the cluster window
+// A B half that has no term at step 0 (the shifted H operand) is loaded from a block coordinate past the tensor: the TMA
+// unit fills zeros, so every instruction covers both halves.
+__device__ __forceinline__ void ss_mma2(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+               "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
+               ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void umma_commit2(uint64_t* bar) {   // arrives on `bar` of BOTH CTAs of the pair
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n"
+               ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void tma2_load_5d(void* dst, const CUtensorMap* m, uint32_t cbar, int c0, int c1, int c2, int c3, int c4) {
+  asm volatile("cp.async.bulk.tensor.5d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];\n"
+               ::"r"(smem_u32(dst)), "l"(m), "r"(cbar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
+}
+__device__ __forceinline__ void tma2_load_4d(void* dst, const CUtensorMap* m, uint32_t cbar, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];\n"
+               ::"r"(smem_u32(dst)), "l"(m), "r"(cbar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ uint32_t ss_cluster_rank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;\n" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t ss_mapa(uint32_t saddr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;\n" : "=r"(r) : "r"(saddr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void ss_cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+}
+__device__ __forceinline__ void ss_arrive_remote(uint32_t cbar) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];\n" ::"r"(cbar) : "memory");
+}
+// bounded polling wait with a cluster-scope acquire (arrivals come from the peer CTA)
+__device__ __forceinline__ bool ss_wait_cluster(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  for (uint32_t spin = 0; spin < (1u << 24); ++spin) {
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}\n"
+                 : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
+    if (ok) return true;
+  }
+  return false;
+}
+
+constexpr int WG2_STAGE = 65536;   // [A hi 16K][A lo 16K][B: this CTA's N/2 columns, 32K]
+constexpr int WG2_NST = 3;
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(WG_THREADS, 1)
+wf_wg2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB0,
+              const __grid_constant__ CUtensorMap tmB1, const WgArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* ones = smem + WG2_NST * WG2_STAGE;   // [16 rows][8 columns] of 1.0: this CTA's half of the 16-column bias operand
+  __shared__ uint64_t full[WG2_NST], empty[WG2_NST], dfull, dempty;
+  __shared__ uint32_t tmem_base_s;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = ss_cluster_rank();
+  const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+  const int blocks_g = a.Bw * a.T * a.tpw;
+  const int mp = a.mt >> 1;                      // M tile pairs
+  const int total = a.splits * a.G * mp;
+  const int kb_n = (a.rpt + 63) / 64;
+  const int ncta = a.nh * 64;                    // B columns held by one CTA
+  const uint32_t b_bytes = (uint32_t)ncta * 64u * 2u * 2u;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < WG2_NST; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    mbar_init(&dfull, 1); mbar_init(&dempty, 8);
+    mbar_fence_init();
+    tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmB0); tma_prefetch_desc(&tmB1);
+  }
+  if (threadIdx.x < 64) reinterpret_cast<uint32_t*>(ones)[threadIdx.x] = a.bfmt == 0 ? 0x3C003C00u : 0x3F803F80u;
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(&tmem_base_s)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;\n" ::: "memory");
+  }
+  fence_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  ss_cluster_sync();   // both CTAs' barriers exist before anybody signals across
+  tc_fence_after();
+  const uint32_t tbase = tmem_base_s;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int it = 0;
+      for (int tile = pair; tile < total; tile += npairs) {
+        const int mtile = 2 * (tile % mp) + (int)rank, g = (tile / mp) % a.G, split = (tile / mp) / a.G;
+        const int b0 = split * a.bps, b1 = min(blocks_g, b0 + a.bps);
+        for (int b = b0; b < b1; ++b) {
+          const int t = (b / a.tpw) % a.T, nt = b % a.tpw;
+          const int blk = g * blocks_g + b;
+          for (int kb = 0; kb < kb_n; ++kb, ++it) {
+            const int s = it % WG2_NST, ph = (it / WG2_NST) & 1;
+            if (!mbar_wait(&empty[s], ph ^ 1)) { atomicExch(a.err, 71); tile = total; b = b1; break; }
+            uint8_t* st = smem + s * WG2_STAGE;
+            const uint32_t fbar = ss_mapa(smem_u32(&full[s]), 0);   // the leader's barrier collects both CTAs' bytes
+            if (rank == 0) mbar_expect_tx(&full[s], 2u * ((uint32_t)SS_A_STAGE + b_bytes));
+            tma2_load_5d(st, &tmA, fbar, 0, 2 * kb, mtile * 16, blk, 0);
+            uint8_t* sb = st + SS_A_STAGE;
+            // my columns of [half 0 | half 1]: with two halves CTA r holds half r, with one it holds 64 columns of it
+            const int h = a.nh == 2 ? (int)rank : 0;
+            const CUtensorMap* m = h == 0 ? &tmB0 : &tmB1;
+            const bool absent = a.bshift[h] && t == 0;   // no such term: zeros from past the end of the tensor
+            if (a.bvar[h] == 0) {
+              const int bb = absent ? a.G * blocks_g : blk - a.bshift[h] * a.tpw;
+              const int grp = a.bcol0[h] + (a.nh == 2 ? 0 : 8 * (int)rank);
+              tma2_load_5d(sb, m, fbar, 0, 2 * kb, grp, bb, 0);
+              tma2_load_5d(sb + SS_A_PLANE, m, fbar, 0, 2 * kb, grp, bb, 1);
+            } else {
+              const int zt = absent ? a.G * a.Bw * a.T : blk / a.tpw, node = nt * a.rpt + kb * 64;
+              const int col = a.bcol0[h] + (a.nh == 2 ? 0 : 64 * (int)rank);
+              for (int j = 0; j < ncta / 64; ++j) tma2_load_4d(sb + j * SS_A_PLANE, m, fbar, col + 64 * j, node, zt, 0);
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (rank == 0) {
+      const uint32_t idesc = ss_idesc(a.nh * 128, (uint32_t)a.afmt, (uint32_t)a.bfmt, 1, 1, 256);
+      const uint32_t idesc1 = ss_idesc(16, (uint32_t)a.afmt, (uint32_t)a.bfmt, 1, 1, 256);
+      const uint64_t odesc = ss_desc(smem_u32(ones), 128, 256, 0);
+      int it = 0, lt = 0;
+      bool ok = true;
+      for (int tile = pair; tile < total && ok; tile += npairs, ++lt) {
+        const int split = (tile / mp) / a.G;
+        const int b0 = split * a.bps, b1 = min(blocks_g, b0 + a.bps);
+        if (!ss_wait_cluster(&dempty, (lt & 1) ^ 1)) { if (lane == 0) atomicExch(a.err, 72); ok = false; break; }
+        tc_fence_after();
+        uint32_t acc = 0u;
+        for (int b = b0; b < b1 && ok; ++b) {
+          for (int kb = 0; kb < kb_n; ++kb, ++it) {
+            const int s = it % WG2_NST, ph = (it / WG2_NST) & 1;
+            if (!mbar_wait(&full[s], ph)) { if (lane == 0) atomicExch(a.err, 73); ok = false; break; }
+            tc_fence_after();
+            if (ss_elect()) {
+              const uint32_t as = smem_u32(smem + s * WG2_STAGE), bs = as + SS_A_STAGE;
+              const int nk16 = min(4, (a.rpt - kb * 64 + 15) / 16);
+              for (int k16 = 0; k16 < nk16; ++k16) {
+                const uint64_t ahi = ss_desc(as + k16 * 256, 128, 1024, 0), alo = ss_desc(as + SS_A_PLANE + k16 * 256, 128, 1024, 0);
+                uint64_t bhi, blo;
+                if (a.bvar[0] == 0) {   // TB8: [groups of 8 columns][64 rows][16 B], hi plane then lo plane 16 KB apart
+                  bhi = ss_desc(bs + k16 * 256, 128, 1024, 0);
+                  blo = ss_desc(bs + SS_A_PLANE + k16 * 256, 128, 1024, 0);
+                } else {                // row-major source: 64-column boxes [plane][64 rows][128 B], SWIZZLE_128B
+                  bhi = ss_desc(bs + k16 * 2048, 16384, 1024, 2);
+                  blo = ss_desc(bs + 8192 + k16 * 2048, 16384, 1024, 2);
+                }
+                ss_mma2(tbase, ahi, bhi, idesc, acc);
+                ss_mma2(tbase, alo, bhi, idesc, 1u);
+                ss_mma2(tbase, ahi, blo, idesc, 1u);
+                if (a.bias_part != nullptr) {
+                  ss_mma2(tbase + 256, ahi, odesc, idesc1, acc);
+                  ss_mma2(tbase + 256, alo, odesc, idesc1, 1u);
+                }
+                acc = 1u;
+              }
+              umma_commit2(&empty[s]);
+            }
+            __syncwarp();
+          }
+        }
+        if (ss_elect() && ok) umma_commit2(&dfull);
+        __syncwarp();
+      }
+    }
+  } else {
+    const int q = warp & 3, row = q * 32 + lane;
+    const uint32_t tlane = tbase + ((uint32_t)(q * 32) << 16);
+    const int ncol = a.nh * 128;
+    const uint32_t dempty0 = ss_mapa(smem_u32(&dempty), 0);
+    int lt = 0;
+    for (int tile = pair; tile < total; tile += npairs, ++lt) {
+      const int mtile = 2 * (tile % mp) + (int)rank, g = (tile / mp) % a.G, split = (tile / mp) / a.G;
+      if (!mbar_wait(&dfull, lt & 1)) { if (lane == 0) atomicExch(a.err, 74); break; }
+      tc_fence_after();
+      float4* cblk = reinterpret_cast<float4*>(a.part) + ((((long long)split * a.G + g) * a.mt + mtile) * (ncol >> 2)) * 128 + row;
+#pragma unroll 1
+      for (int cc = 0; cc < ncol; cc += 32) {
+        uint32_t v[32];
+        __syncwarp();
+        tmem_ld32(tlane + cc, v);
+        tmem_wait_ld();
+#pragma unroll
+        for (int j = 0; j < 32; j += 4)
+          cblk[(long long)((cc + j) >> 2) * 128] = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
+                                                                __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+      }
+      if (a.bias_part != nullptr) {
+        uint32_t v[8];
+        __syncwarp();
+        tmem_ld8(tlane + 256, v);
+        tmem_wait_ld();
+        a.bias_part[((long long)split * a.G + g) * (a.mt * 128) + mtile * 128 + row] = __uint_as_float(v[0]);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if (rank == 0) mbar_arrive(&dempty);
+        else ss_arrive_remote(dempty0);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  ss_cluster_sync();   // nobody leaves (or frees tensor memory) while the pair's instructions may still touch this CTA
+  if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;\n" ::"r"(tbase), "r"(512u) : "memory");
+}
+
 // dst_h[g][m][c] = sum_s part[s][g][m][h*128 + c] (fixed order); bias -> both LSTM bias gradients
 __global__ void wf_wg_reduce_kernel(const float* __restrict__ part, const float* __restrict__ bias_part, int splits, int G, int nh, int M,
                                     float* dst0, int ld0, int w0, float* dst1, int ld1, int w1, float* db1, float* db2,
@@ -899,6 +1122,38 @@ int wf_ss_launch_wgrad(const void* dg16, long long dg_plane, int nh, const void*
   a.afmt = 1; a.bfmt = 1; a.nst = nh == 2 ? 2 : 3;   // kind::f16 takes ONE format for both operands: bf16 (dG's range)
   a.mt = M / 128;
   a.part = part; a.bias_part = db1 != nullptr ? part + (size_t)a.splits * G * M * ncol : nullptr; a.err = err;
+  static const int use_pairs = getenv("WF_WG_PAIRS") ? atoi(getenv("WF_WG_PAIRS")) : 1;
+  if (use_pairs && a.mt % 2 == 0 && (nh == 1 || bvar[0] == bvar[1])) {
+    // CTA pairs (cta_group::2): the split count is chosen for pair tiles over sms / 2 pairs
+    const int pairs = sms / 2, mp = a.mt / 2;
+    int bestp = 1;
+    long long bestc = -1;
+    for (int s2 = 1; s2 <= 40 && s2 <= blocks_g; ++s2) {
+      if ((size_t)s2 * G * M * (ncol + 1) > part_floats) break;
+      const long long cost = (long long)wf_cdiv((long long)mp * G * s2, pairs) * (wf_cdiv(blocks_g, s2) + 1) * 64 + s2;
+      if (bestc < 0 || cost < bestc) { bestc = cost; bestp = s2; }
+    }
+    a.bps = wf_cdiv(blocks_g, bestp); a.splits = wf_cdiv(blocks_g, a.bps);
+    a.bias_part = db1 != nullptr ? part + (size_t)a.splits * G * M * ncol : nullptr;
+    CUtensorMap tmBp[2] = {tmB[0], tmB[1]};
+    if (nh == 1 && bvar[0] == 0 && (rc = map_tb8(&tmBp[0], bsrc[0], bC[0], blocks, bplane[0], 2, 8, 1, 1))) return rc;  // 64-column boxes
+    if (nh == 1) tmBp[1] = tmBp[0];
+    const int smem2 = WG2_NST * WG2_STAGE + 1024 + 1024;
+    static bool configured2 = false;
+    if (!configured2) {
+      if (cudaFuncSetAttribute(wf_wg2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2) != cudaSuccess)
+        return wf_fail(WF_ECUDA, "wg pair kernel: cannot raise dynamic shared memory");
+      configured2 = true;
+    }
+    const int total2 = a.splits * G * mp;
+    wf_wg2_kernel<<<2 * (total2 < pairs ? total2 : pairs), WG_THREADS, smem2, st>>>(tmA, tmBp[0], tmBp[1], a);
+    WF_CHECK_LAUNCH("wg2_kernel");
+    const int items2 = M * ncol / 4 + M;
+    wf_wg_reduce_kernel<<<dim3(wf_cdiv(items2, 256), G), 256, 0, st>>>(part, a.bias_part, a.splits, G, nh, M, dst0, ld0, w0, dst1, ld1, w1,
+                                                                      db1, db2, gstride);
+    WF_CHECK_LAUNCH("wg_reduce");
+    return WF_OK;
+  }
   const int smem = a.nst * SS_A_STAGE * (1 + nh) + 1024 + 1024;
   static bool configured = false;
   if (!configured) {
