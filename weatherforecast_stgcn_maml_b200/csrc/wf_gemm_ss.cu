@@ -509,6 +509,7 @@ struct WgArgs {
   int nst;
   float* part; float* bias_part;   // [splits][G][M][nh * 128] (tiles in TB4 order), [splits][G][M]
   int mt;                          // M / 128 row tiles of dG's channels (4: the LSTM's 4L = 512 gate rows)
+  int sumw;                        // pair kernel: bias gradient by the summing warps (1) or by 16-column instructions (0)
   int* err;
 };
 
@@ -751,6 +752,11 @@ __device__ __forceinline__ void ss_cluster_sync() {
 __device__ __forceinline__ void ss_arrive_remote(uint32_t cbar) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];\n" ::"r"(cbar) : "memory");
 }
+// no data of the arriving thread is published: no fence (a cluster-scope release in the MMA-issuing thread stalls it for
+// ~1.5k clk per stage)
+__device__ __forceinline__ void ss_arrive_remote_relaxed(uint32_t cbar) {
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];\n" ::"r"(cbar) : "memory");
+}
 // bounded polling wait with a cluster-scope acquire (arrivals come from the peer CTA)
 __device__ __forceinline__ bool ss_wait_cluster(uint64_t* bar, uint32_t parity) {
   const uint32_t addr = smem_u32(bar);
@@ -763,19 +769,26 @@ __device__ __forceinline__ bool ss_wait_cluster(uint64_t* bar, uint32_t parity) 
   return false;
 }
 
+// The bias gradient (column sums of dG over the rows) costs the tensor pipe as much as the products when it is a
+// 16-column instruction pair per K step: an instruction with an MN-major no-swizzle operand takes ~150 clk whatever its
+// width, 8 of the 20 per stage.  Four extra warps (6-9) add the dG tile up straight from shared memory instead (16
+// LDS.128 + 128 converts / adds per thread and stage, fp32 accumulators, one shuffle reduction per tile); they hold the
+// stage (empty[s] counts them) and learn that it has landed from the leader's MMA warp (landed[s], also across the pair).
 constexpr int WG2_STAGE = 65536;   // [A hi 16K][A lo 16K][B: this CTA's N/2 columns, 32K]
 constexpr int WG2_NST = 3;
+constexpr int WG2_THREADS = 320;
 
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(WG_THREADS, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(WG2_THREADS, 1)
 wf_wg2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB0,
               const __grid_constant__ CUtensorMap tmB1, const WgArgs a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* ones = smem + WG2_NST * WG2_STAGE;   // [16 rows][8 columns] of 1.0: this CTA's half of the 16-column bias operand
-  __shared__ uint64_t full[WG2_NST], empty[WG2_NST], dfull, dempty;
+  __shared__ uint64_t full[WG2_NST], empty[WG2_NST], landed[WG2_NST], dfull[2], dempty[2];
   __shared__ uint32_t tmem_base_s;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = ss_cluster_rank();
+  const bool sum_warps = a.bias_part != nullptr && a.afmt == 1 && a.sumw != 0;   // bias gradient by warps 6-9 (bf16 dG), else by the tensor core
   const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
   const int blocks_g = a.Bw * a.T * a.tpw;
   const int mp = a.mt >> 1;                      // M tile pairs
@@ -784,11 +797,14 @@ wf_wg2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
   const int ncta = a.nh * 64;                    // B columns held by one CTA
   const uint32_t b_bytes = (uint32_t)ncta * 64u * 2u * 2u;
   if (threadIdx.x == 0) {
-    for (int s = 0; s < WG2_NST; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    mbar_init(&dfull, 1); mbar_init(&dempty, 8);
+    for (int s = 0; s < WG2_NST; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], sum_warps ? 5 : 1); mbar_init(&landed[s], 1); }
+    for (int d = 0; d < 2; ++d) { mbar_init(&dfull[d], 1); mbar_init(&dempty[d], 8); }
     mbar_fence_init();
     tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmB0); tma_prefetch_desc(&tmB1);
   }
+  // with the bias gradient off the tensor core the accumulator is 256 columns: two of them, so that the epilogue of a
+  // tile (128 KB of partials per CTA, ~10k clk) runs under the next tile's instructions
+  const int nbuf = sum_warps ? 2 : 1;
   if (threadIdx.x < 64) reinterpret_cast<uint32_t*>(ones)[threadIdx.x] = a.bfmt == 0 ? 0x3C003C00u : 0x3F803F80u;
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(&tmem_base_s)), "r"(512u) : "memory");
@@ -813,6 +829,7 @@ wf_wg2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
           for (int kb = 0; kb < kb_n; ++kb, ++it) {
             const int s = it % WG2_NST, ph = (it / WG2_NST) & 1;
             if (!mbar_wait(&empty[s], ph ^ 1)) { atomicExch(a.err, 71); tile = total; b = b1; break; }
+            SS_TR(0, it);
             uint8_t* st = smem + s * WG2_STAGE;
             const uint32_t fbar = ss_mapa(smem_u32(&full[s]), 0);   // the leader's barrier collects both CTAs' bytes
             if (rank == 0) mbar_expect_tx(&full[s], 2u * ((uint32_t)SS_A_STAGE + b_bytes));
@@ -832,6 +849,7 @@ wf_wg2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
               const int col = a.bcol0[h] + (a.nh == 2 ? 0 : 64 * (int)rank);
               for (int j = 0; j < ncta / 64; ++j) tma2_load_4d(sb + j * SS_A_PLANE, m, fbar, col + 64 * j, node, zt, 0);
             }
+            SS_TR(3, it);
           }
         }
       }
@@ -846,7 +864,9 @@ wf_wg2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
       for (int tile = pair; tile < total && ok; tile += npairs, ++lt) {
         const int split = (tile / mp) / a.G;
         const int b0 = split * a.bps, b1 = min(blocks_g, b0 + a.bps);
-        if (!ss_wait_cluster(&dempty, (lt & 1) ^ 1)) { if (lane == 0) atomicExch(a.err, 72); ok = false; break; }
+        const int ds = lt % nbuf;
+        const uint32_t dcol = tbase + (uint32_t)ds * 256u;
+        if (!ss_wait_cluster(&dempty[ds], ((lt / nbuf) & 1) ^ 1)) { if (lane == 0) atomicExch(a.err, 72); ok = false; break; }
         tc_fence_after();
         uint32_t acc = 0u;
         for (int b = b0; b < b1 && ok; ++b) {
@@ -855,6 +875,13 @@ wf_wg2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
             if (!mbar_wait(&full[s], ph)) { if (lane == 0) atomicExch(a.err, 73); ok = false; break; }
             tc_fence_after();
             if (ss_elect()) {
+              SS_TR(1, it);
+              if (sum_warps) {   // the stage is complete in BOTH CTAs: tell the summing warps of each
+                // (the bytes were put into the peer's shared memory by its own TMA loads, complete before the transaction
+                // count reached this CTA's full[s]; this thread publishes nothing of its own)
+                mbar_arrive(&landed[s]);
+                ss_arrive_remote_relaxed(ss_mapa(smem_u32(&landed[s]), 1));
+              }
               const uint32_t as = smem_u32(smem + s * WG2_STAGE), bs = as + SS_A_STAGE;
               const int nk16 = min(4, (a.rpt - kb * 64 + 15) / 16);
               for (int k16 = 0; k16 < nk16; ++k16) {
@@ -867,47 +894,96 @@ wf_wg2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
                   bhi = ss_desc(bs + k16 * 2048, 16384, 1024, 2);
                   blo = ss_desc(bs + 8192 + k16 * 2048, 16384, 1024, 2);
                 }
-                ss_mma2(tbase, ahi, bhi, idesc, acc);
-                ss_mma2(tbase, alo, bhi, idesc, 1u);
-                ss_mma2(tbase, ahi, blo, idesc, 1u);
-                if (a.bias_part != nullptr) {
+                ss_mma2(dcol, ahi, bhi, idesc, acc);
+                ss_mma2(dcol, alo, bhi, idesc, 1u);
+                ss_mma2(dcol, ahi, blo, idesc, 1u);
+                if (a.bias_part != nullptr && !sum_warps) {
                   ss_mma2(tbase + 256, ahi, odesc, idesc1, acc);
                   ss_mma2(tbase + 256, alo, odesc, idesc1, 1u);
                 }
                 acc = 1u;
               }
               umma_commit2(&empty[s]);
+              SS_TR(2, it);
             }
             __syncwarp();
           }
         }
-        if (ss_elect() && ok) umma_commit2(&dfull);
+        if (ss_elect() && ok) umma_commit2(&dfull[ds]);
         __syncwarp();
+      }
+    }
+  } else if (warp >= 6) {
+    if (sum_warps) {
+      // column sums of my dG tile: thread (grp, rs) owns the 8 channels of group grp and rows rs, rs + 8, ... of a stage
+      const int tid2 = threadIdx.x - 192, grp = tid2 >> 3, rs = tid2 & 7;
+      int it = 0;
+      bool ok = true;
+      for (int tile = pair; tile < total && ok; tile += npairs) {
+        const int mtile = 2 * (tile % mp) + (int)rank, g = (tile / mp) % a.G, split = (tile / mp) / a.G;
+        const int b0 = split * a.bps, b1 = min(blocks_g, b0 + a.bps);
+        float acc[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+        for (int b = b0; b < b1 && ok; ++b) {
+          for (int kb = 0; kb < kb_n; ++kb, ++it) {
+            const int s = it % WG2_NST, ph = (it / WG2_NST) & 1;
+            if (!ss_wait_cluster(&landed[s], ph)) { if (lane == 0) atomicExch(a.err, 75); ok = false; break; }
+            const uint32_t as = smem_u32(smem + s * WG2_STAGE) + (uint32_t)grp * 1024u + (uint32_t)rs * 16u;
+#pragma unroll
+            for (int pl = 0; pl < 2; ++pl) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                uint4 w;
+                asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];\n" : "=r"(w.x), "=r"(w.y), "=r"(w.z), "=r"(w.w)
+                             : "r"(as + (uint32_t)pl * (uint32_t)SS_A_PLANE + (uint32_t)i * 128u));
+                acc[0] += __uint_as_float(w.x << 16); acc[1] += __uint_as_float(w.x & 0xFFFF0000u);
+                acc[2] += __uint_as_float(w.y << 16); acc[3] += __uint_as_float(w.y & 0xFFFF0000u);
+                acc[4] += __uint_as_float(w.z << 16); acc[5] += __uint_as_float(w.z & 0xFFFF0000u);
+                acc[6] += __uint_as_float(w.w << 16); acc[7] += __uint_as_float(w.w & 0xFFFF0000u);
+              }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[s]);   // my reads of the stage are done
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], 1);
+          acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], 2);
+          acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], 4);
+        }
+        if (rs == 0 && ok) {
+          float* dstb = a.bias_part + ((long long)split * a.G + g) * (a.mt * 128) + mtile * 128 + grp * 8;
+          *reinterpret_cast<float4*>(dstb) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+          *reinterpret_cast<float4*>(dstb + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
+        }
       }
     }
   } else {
     const int q = warp & 3, row = q * 32 + lane;
     const uint32_t tlane = tbase + ((uint32_t)(q * 32) << 16);
     const int ncol = a.nh * 128;
-    const uint32_t dempty0 = ss_mapa(smem_u32(&dempty), 0);
     int lt = 0;
     for (int tile = pair; tile < total; tile += npairs, ++lt) {
       const int mtile = 2 * (tile % mp) + (int)rank, g = (tile / mp) % a.G, split = (tile / mp) / a.G;
-      if (!mbar_wait(&dfull, lt & 1)) { if (lane == 0) atomicExch(a.err, 74); break; }
+      const int ds = lt % nbuf;
+      const uint32_t tl = tlane + (uint32_t)ds * 256u;
+      if (!mbar_wait(&dfull[ds], (lt / nbuf) & 1)) { if (lane == 0) atomicExch(a.err, 74); break; }
       tc_fence_after();
       float4* cblk = reinterpret_cast<float4*>(a.part) + ((((long long)split * a.G + g) * a.mt + mtile) * (ncol >> 2)) * 128 + row;
 #pragma unroll 1
       for (int cc = 0; cc < ncol; cc += 32) {
         uint32_t v[32];
         __syncwarp();
-        tmem_ld32(tlane + cc, v);
+        tmem_ld32(tl + cc, v);
         tmem_wait_ld();
 #pragma unroll
         for (int j = 0; j < 32; j += 4)
           cblk[(long long)((cc + j) >> 2) * 128] = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
                                                                 __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
       }
-      if (a.bias_part != nullptr) {
+      if (a.bias_part != nullptr && !sum_warps) {
         uint32_t v[8];
         __syncwarp();
         tmem_ld8(tlane + 256, v);
@@ -917,8 +993,8 @@ wf_wg2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
-        if (rank == 0) mbar_arrive(&dempty);
-        else ss_arrive_remote(dempty0);
+        if (rank == 0) mbar_arrive(&dempty[ds]);
+        else ss_arrive_remote(ss_mapa(smem_u32(&dempty[ds]), 0));
       }
     }
   }
@@ -1130,7 +1206,8 @@ int wf_ss_launch_wgrad(const void* dg16, long long dg_plane, int nh, const void*
     long long bestc = -1;
     for (int s2 = 1; s2 <= 40 && s2 <= blocks_g; ++s2) {
       if ((size_t)s2 * G * M * (ncol + 1) > part_floats) break;
-      const long long cost = (long long)wf_cdiv((long long)mp * G * s2, pairs) * (wf_cdiv(blocks_g, s2) + 1) * 64 + s2;
+      // rounds of pair tiles x (blocks per tile + half a block of hand-over), fewer partial tiles on ties
+      const long long cost = (long long)wf_cdiv((long long)mp * G * s2, pairs) * (wf_cdiv(blocks_g, s2) * 64 + 32) + s2;
       if (bestc < 0 || cost < bestc) { bestc = cost; bestp = s2; }
     }
     a.bps = wf_cdiv(blocks_g, bestp); a.splits = wf_cdiv(blocks_g, a.bps);
@@ -1145,8 +1222,10 @@ int wf_ss_launch_wgrad(const void* dg16, long long dg_plane, int nh, const void*
         return wf_fail(WF_ECUDA, "wg pair kernel: cannot raise dynamic shared memory");
       configured2 = true;
     }
+    static const int sumw = getenv("WF_WG_SUMWARPS") ? atoi(getenv("WF_WG_SUMWARPS")) : 1;
+    a.sumw = sumw;
     const int total2 = a.splits * G * mp;
-    wf_wg2_kernel<<<2 * (total2 < pairs ? total2 : pairs), WG_THREADS, smem2, st>>>(tmA, tmBp[0], tmBp[1], a);
+    wf_wg2_kernel<<<2 * (total2 < pairs ? total2 : pairs), WG2_THREADS, smem2, st>>>(tmA, tmBp[0], tmBp[1], a);
     WF_CHECK_LAUNCH("wg2_kernel");
     const int items2 = M * ncol / 4 + M;
     wf_wg_reduce_kernel<<<dim3(wf_cdiv(items2, 256), G), 256, 0, st>>>(part, a.bias_part, a.splits, G, nh, M, dst0, ld0, w0, dst1, ld1, w1,
