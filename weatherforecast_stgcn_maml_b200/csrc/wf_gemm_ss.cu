@@ -1004,6 +1004,178 @@ wf_wg2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
   if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;\n" ::"r"(tbase), "r"(512u) : "memory");
 }
 
+// ---- the resident-weight GEMM on CTA pairs (NODES row tiles, TB4 epilogue): the pair owns two consecutive row tiles
+// (M = 256) and BN2 output columns; each CTA keeps HALF of the weight slice resident (BN2 / 2 rows x K, hi + lo <= 128 KB),
+// streams its OWN row tile through a 3-stage ring and drains its own 128 x BN2 accumulator.  Against the one-CTA kernel:
+// twice the columns per resident byte, so A is read half as often (dX: once instead of twice; K = 256 projection: twice
+// instead of four times), and every instruction does four times the work of a 128 x 64 one for the same ~150 clk.
+template <int BN2, bool DROP>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(SS_THREADS, 1)
+wf_ss2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmBhi,
+              const __grid_constant__ CUtensorMap tmBlo, const SsArgs a) {
+  constexpr int BNH = BN2 / 2;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sB = smem;                           // [plane][k-block][BNH rows][128 B]
+  uint8_t* sA = smem + SS_B_BYTES;              // ring of A stages: [plane][128 rows x 64 k]
+  __shared__ uint64_t full[3], empty[3], dfull[2], dempty[2], bfull, bempty;
+  __shared__ uint32_t tmem_base_s;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr int NST = 3;
+  const uint32_t rank = ss_cluster_rank();
+  const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+  const int pidx = pair % a.n_parts, slot = pair / a.n_parts, slots = npairs / a.n_parts;
+  const int total_pt = (a.m_tiles_g * a.G) >> 1;            // pair tiles: row tiles (2 pt, 2 pt + 1), same group
+  const int per = (total_pt + slots - 1) / slots;
+  const int pt0 = slot * per, pt1 = min(total_pt, pt0 + per);
+  const int n0 = pidx * BN2;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < NST; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&dfull[s], 1); mbar_init(&dempty[s], 8); }
+    mbar_init(&bfull, 1); mbar_init(&bempty, 1);
+    mbar_fence_init();
+    tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmBhi); tma_prefetch_desc(&tmBlo);
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(&tmem_base_s)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;\n" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  ss_cluster_sync();
+  tc_fence_after();
+  const uint32_t tbase = tmem_base_s;
+  const uint32_t b_plane = (uint32_t)a.nkb * BNH * 128u;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int it = 0, bload = 0, gprev = -1;
+      const uint32_t bfull0 = ss_mapa(smem_u32(&bfull), 0);
+      for (int pt = pt0; pt < pt1; ++pt) {
+        const SsTile t = ss_decode(a, 2 * pt + (int)rank);
+        const int gb = a.b_per_group ? t.g : 0;
+        if (gb != gprev) {  // (re)load my half of the resident weight slice of this group
+          if (bload > 0 && !mbar_wait(&bempty, (bload - 1) & 1)) { atomicExch(a.err, 81); break; }
+          if (rank == 0) mbar_expect_tx(&bfull, 4u * b_plane);   // both CTAs' halves, both planes
+          for (int kb = 0; kb < a.nkb; ++kb) {
+            asm volatile("cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];\n"
+                         ::"r"(smem_u32(sB + kb * BNH * 128)), "l"(&tmBhi), "r"(bfull0), "r"(kb * SS_BK), "r"(n0 + (int)rank * BNH), "r"(gb) : "memory");
+            asm volatile("cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];\n"
+                         ::"r"(smem_u32(sB + b_plane + kb * BNH * 128)), "l"(&tmBlo), "r"(bfull0), "r"(kb * SS_BK), "r"(n0 + (int)rank * BNH), "r"(gb) : "memory");
+          }
+          gprev = gb; ++bload;
+        }
+        for (int kb = 0; kb < a.nkb; ++kb, ++it) {
+          const int s = it % NST, ph = (it / NST) & 1;
+          if (!mbar_wait(&empty[s], ph ^ 1)) { atomicExch(a.err, 82); pt = pt1; break; }
+          SS_TR(0, it);
+          uint8_t* st = sA + s * SS_A_STAGE;
+          const uint32_t fbar = ss_mapa(smem_u32(&full[s]), 0);
+          if (rank == 0) mbar_expect_tx(&full[s], 2u * (uint32_t)SS_A_STAGE);
+          if (a.avar == SS_A_KT) tma2_load_5d(st, &tmA, fbar, 0, 0, kb * 8, t.blk, 0);
+          else tma2_load_4d(st, &tmA, fbar, kb * SS_BK, t.node0, t.zt, 0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (rank == 0) {
+      const uint32_t idesc = ss_idesc(BN2, (uint32_t)a.afmt, (uint32_t)a.bfmt, 0, 0, 256);
+      int it = 0, lt = 0, bload = 0, gprev = -1;
+      bool ok = true;
+      for (int pt = pt0; pt < pt1 && ok; ++pt, ++lt) {
+        const int g = (2 * pt) / a.m_tiles_g;
+        const int gb = a.b_per_group ? g : 0;
+        const int ds = lt & 1;
+        if (!ss_wait_cluster(&dempty[ds], ((lt >> 1) & 1) ^ 1)) { if (lane == 0) atomicExch(a.err, 83); ok = false; break; }
+        if (gb != gprev) {
+          if (!mbar_wait(&bfull, bload & 1)) { if (lane == 0) atomicExch(a.err, 84); ok = false; break; }
+          gprev = gb; ++bload;
+        }
+        tc_fence_after();
+        uint32_t acc = 0u;
+        for (int kb = 0; kb < a.nkb; ++kb, ++it) {
+          const int s = it % NST, ph = (it / NST) & 1;
+          if (!mbar_wait(&full[s], ph)) { if (lane == 0) atomicExch(a.err, 85); ok = false; break; }
+          tc_fence_after();
+          if (ss_elect()) {
+            SS_TR(1, it);
+            const uint32_t ahi = smem_u32(sA + s * SS_A_STAGE), bhi = smem_u32(sB + kb * BNH * 128);
+#pragma unroll
+            for (int k16 = 0; k16 < 4; ++k16) {
+#pragma unroll
+              for (int p = 0; p < 3; ++p) {  // A_hi B_hi, A_lo B_hi, A_hi B_lo
+                const uint32_t as = ahi + (p == 1 ? SS_A_PLANE : 0), bs = bhi + (p == 2 ? b_plane : 0);
+                const uint64_t ad = a.avar == SS_A_KT ? ss_desc(as + k16 * 4096, 2048, 128, 0) : ss_desc(as + k16 * 32, 16, 1024, 2);
+                ss_mma2(tbase + ds * BN2, ad, ss_desc(bs + k16 * 32, 16, 1024, 2), idesc, acc);
+                acc = 1u;
+              }
+            }
+            umma_commit2(&empty[s]);
+            SS_TR(2, it);
+            if (kb == a.nkb - 1) {
+              umma_commit2(&dfull[ds]);
+              const int gnext = pt + 1 < pt1 ? (a.b_per_group ? (2 * (pt + 1)) / a.m_tiles_g : 0) : -2;
+              if (gnext != gb && gnext != -2) umma_commit2(&bempty);
+            }
+          }
+          __syncwarp();
+        }
+      }
+    }
+  } else {
+    const int q = warp & 3, row = q * 32 + lane;
+    const uint32_t tlane = tbase + ((uint32_t)(q * 32) << 16);
+    int lt = 0;
+    bool ok = true;
+    const bool has_bias = a.bias != nullptr || a.bias2 != nullptr;
+    for (int pt = pt0; pt < pt1 && ok; ++pt, ++lt) {
+      const SsTile t = ss_decode(a, 2 * pt + (int)rank);
+      const int ds = lt & 1;
+      const float* b1 = has_bias && a.bias ? a.bias + t.g * a.bias_gstride + n0 : nullptr;
+      const float* b2 = has_bias && a.bias2 ? a.bias2 + t.g * a.bias_gstride + n0 : nullptr;
+      if (!mbar_wait(&dfull[ds], (lt >> 1) & 1)) { if (lane == 0) atomicExch(a.err, 86); ok = false; break; }
+      tc_fence_after();
+      if (warp == 2 && lane == 0) SS_TR(4, lt);
+      DropState dst;
+      if (DROP) dst = wf_drop_state(a.drop);
+      float4* cblk = reinterpret_cast<float4*>(a.C) + ((long long)t.blk * (a.c_cols >> 2) + (n0 >> 2)) * 128 + row;
+      unsigned long long e4row = 0;
+      if (DROP) e4row = (((unsigned long long)t.zt * a.Nn + (unsigned)(t.node0 + row)) * (unsigned)a.c_cols + (unsigned)n0) >> 2;
+#pragma unroll 1
+      for (int cc = 0; cc < BN2; cc += 32) {
+        uint32_t v[32];
+        __syncwarp();
+        tmem_ld32(tlane + ds * BN2 + cc, v);
+        tmem_wait_ld();
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          float4 o = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+          if (b1) { const float4 b = __ldg(reinterpret_cast<const float4*>(b1 + cc + j)); o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w; }
+          if (b2) { const float4 b = __ldg(reinterpret_cast<const float4*>(b2 + cc + j)); o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w; }
+          if (DROP) {
+            float m[4];
+            wf_drop4(dst, e4row + (unsigned)((cc + j) >> 2), m);
+            o.x *= m[0]; o.y *= m[1]; o.z *= m[2]; o.w *= m[3];
+          }
+          if (row < a.rpt) cblk[(long long)((cc + j) >> 2) * 128] = o;   // rows >= rpt of a node tile are padding
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (warp == 2 && lane == 0) SS_TR(5, lt);
+      if (lane == 0) {
+        if (rank == 0) mbar_arrive(&dempty[ds]);
+        else ss_arrive_remote(ss_mapa(smem_u32(&dempty[ds]), 0));
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  ss_cluster_sync();
+  if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;\n" ::"r"(tbase), "r"(512u) : "memory");
+}
+
 // dst_h[g][m][c] = sum_s part[s][g][m][h*128 + c] (fixed order); bias -> both LSTM bias gradients
 __global__ void wf_wg_reduce_kernel(const float* __restrict__ part, const float* __restrict__ bias_part, int splits, int G, int nh, int M,
                                     float* dst0, int ld0, int w0, float* dst1, int ld1, int w1, float* db1, float* db2,
@@ -1117,6 +1289,27 @@ int ss_launch_bn(const CUtensorMap& tmA, const CUtensorMap& tmA2, const CUtensor
   return WF_OK;
 }
 
+template <int BN2>
+int ss2_launch_bn(const CUtensorMap& tmA, const CUtensorMap& tmBhi, const CUtensorMap& tmBlo, SsArgs& a, cudaStream_t st) {
+  const int smem = SS_B_BYTES + 3 * SS_A_STAGE + 1024;
+  static bool configured = false;
+  if (!configured) {
+    if (cudaFuncSetAttribute(wf_ss2_kernel<BN2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess ||
+        cudaFuncSetAttribute(wf_ss2_kernel<BN2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess)
+      return wf_fail(WF_ECUDA, "ss pair kernel: cannot raise dynamic shared memory to %d", smem);
+    configured = true;
+  }
+  const int total_pt = a.m_tiles_g * a.G / 2;
+  int slots = (ss_sms() / 2) / a.n_parts;
+  if (slots > total_pt) slots = total_pt;
+  if (slots < 1) slots = 1;
+  const int grid = 2 * slots * a.n_parts;
+  if (a.drop.rng != nullptr) wf_ss2_kernel<BN2, true><<<grid, SS_THREADS, smem, st>>>(tmA, tmBhi, tmBlo, a);
+  else wf_ss2_kernel<BN2, false><<<grid, SS_THREADS, smem, st>>>(tmA, tmBhi, tmBlo, a);
+  WF_CHECK_LAUNCH("ss2_kernel");
+  return WF_OK;
+}
+
 int ss_launch(int bn, const CUtensorMap& tmA, const CUtensorMap& tmA2, const CUtensorMap& tmBhi, const CUtensorMap& tmBlo,
               const CUtensorMap& tmOut, const CUtensorMap& tmOut2, SsArgs& a, cudaStream_t st) {
   WF_REQUIRE((long long)bn * a.nkb * SS_BK * 4 <= SS_B_BYTES, "ss gemm: the weight slice %d x %d does not fit shared memory", bn, a.nkb * SS_BK);
@@ -1157,6 +1350,18 @@ int wf_ss_launch_nodes(int bn, int avar, const void* A16, long long a_plane, int
     return wf_fail(WF_ECUDA, "ss_nodes: clearing the output failed");
   a.C = C; a.c_cols = Ntot; a.bias = bias; a.bias2 = bias2; a.bias_gstride = bias_gstride; a.err = err;
   if (drop != nullptr) a.drop = *drop;
+  // CTA pairs (cta_group::2): K >= 256 (the store-bound K = 128 projection gains nothing), an even number of row tiles per
+  // group, and a column count the pair's resident halves can cover
+  static const int use_pairs = getenv("WF_SS_PAIRS") ? atoi(getenv("WF_SS_PAIRS")) : 1;
+  const int bn2 = K >= 512 ? 128 : 256;
+  if (use_pairs && k_parts == 1 && K >= 256 && K % SS_BK == 0 && (a.m_tiles_g % 2) == 0 && Ntot % bn2 == 0 &&
+      (long long)(bn2 / 2) * K * 4 <= SS_B_BYTES) {
+    CUtensorMap tmBhi2, tmBlo2;
+    if ((rc = map_w(&tmBhi2, Bhi, K, Ntot, G, ldb, G > 1 ? b_gstride : (long long)Ntot * ldb, bn2 / 2, bfmt))) return rc;
+    if ((rc = map_w(&tmBlo2, Blo, K, Ntot, G, ldb, G > 1 ? b_gstride : (long long)Ntot * ldb, bn2 / 2, bfmt))) return rc;
+    a.n_parts = Ntot / bn2;
+    return bn2 == 128 ? ss2_launch_bn<128>(tmA, tmBhi2, tmBlo2, a, st) : ss2_launch_bn<256>(tmA, tmBhi2, tmBlo2, a, st);
+  }
   return ss_launch(bn, tmA, tmA, tmBhi, tmBlo, tmA, tmA, a, st);
 }
 
