@@ -46,7 +46,7 @@ def nodes(name, bn, avar, K, Ntot, fmt, kp=1):
 
 nodes("P0 (feats -> gates)", 128, 0, 256, 512, 0)
 nodes("P1 (h -> gates)", 256, 1, 128, 512, 0)
-nodes("dX (dG -> dh)", 64, 1, 512, 128, 1)
+nodes("dX (dG -> dh)", 64, 1, 512, 128, 1)   # CTA pairs unless WF_SS_PAIRS=0 (then two 64-column parts on one CTA each)
 nodes("dX, K split over 2 CTAs", 128, 1, 512, 128, 1, 2)
 # weight gradients
 dg = torch.zeros(2, blocks * 512 * 128, dtype=torch.int16, device="cuda")
