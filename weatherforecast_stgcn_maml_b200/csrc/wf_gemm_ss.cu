@@ -37,6 +37,8 @@ extern "C" int wf_tile_rows(int N);
 namespace {
 
 constexpr int SS_THREADS = 192;  // warp 0: TMA producer; warp 1: MMA issue + TMEM owner; warps 2-5: epilogue (lane quarters 2,3,0,1)
+constexpr int SS_THREADS_HL = 320;  // the hl16 epilogue runs on 8 warps (2-9): a warp's ~12 dependent instructions per value leave
+                                    // its scheduler idle most of the time, so two warps per scheduler each take half of the columns
 // One TMA tensor load costs ~0.2 us of serialised issue whatever its size (measured: tools/ss_bench.py ablations, and the
 // first generation's 4 loads per k-block = 1.3 us), so a stage is ONE load: the hi and the lo plane of a [128 x 64] operand
 // tile together (the plane is the outermost box dimension) = 32 KB.
@@ -44,7 +46,7 @@ constexpr int SS_BK = 64;
 constexpr int SS_A_PLANE = 128 * SS_BK * 2;   // 16 KB: one 16-bit plane of an A stage
 constexpr int SS_A_STAGE = 2 * SS_A_PLANE;    // hi + lo
 constexpr int SS_B_BYTES = 131072;            // resident B: BN x K x 2 B x 2 planes
-constexpr int SS_STG_BYTES = 32768;           // GCN epilogue staging: 4 warps x (hi + lo) x 32 rows x 128 B
+constexpr int SS_STG_BYTES = 32768;           // GCN epilogue staging: 8 warps x (hi + lo) x 32 rows x 64 B
 constexpr int SS_MAX_STAGES = 6;
 
 enum { SS_A_KS = 0, SS_A_KT = 1 };    // A: K-major SWIZZLE_128B from row-major hl16 / K-major no-swizzle from TB8
@@ -180,7 +182,7 @@ __device__ __forceinline__ SsTile ss_decode(const SsArgs& a, int mt) {
 // tmBhi / tmBlo: weights [G or 1][N_total][K] as two planes; tmOut: E_HL output [2 planes][Z][R][N_total] (fp16);
 // tmOut2 (a.out2): the same values once more as bf16 planes (the weight gradients' operand format).
 template <int BN, bool DROP>
-__global__ void __launch_bounds__(SS_THREADS, 1)
+__global__ void __launch_bounds__(SS_THREADS_HL, 1)
 wf_ss_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
              const __grid_constant__ CUtensorMap tmBhi, const __grid_constant__ CUtensorMap tmBlo,
              const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ CUtensorMap tmOut2, const SsArgs a) {
@@ -220,7 +222,7 @@ wf_ss_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < NST; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&dfull[s], 1); mbar_init(&dempty[s], 4); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&dfull[s], 1); mbar_init(&dempty[s], a.epi == SS_E_HL ? 8 : 4); }
     mbar_init(&bfull, 1); mbar_init(&bempty, 1);
     mbar_fence_init();
     tma_prefetch_desc(&tmA); tma_prefetch_desc(&tmBhi); tma_prefetch_desc(&tmBlo);
@@ -326,11 +328,12 @@ wf_ss_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         __syncwarp();
       }
     }
-  } else {
+  } else if (warp < 6 || a.epi == SS_E_HL) {
     // ------------------------------------------------------------------ epilogue
     const int q = warp & 3, row = q * 32 + lane;
     const uint32_t tlane = tbase + ((uint32_t)(q * 32) << 16);
-    uint8_t* stg = sStg + (warp - 2) * 8192;   // [plane][32 rows][128 B], 16-byte chunks XOR-swizzled by (row & 7)
+    const int chalf = (warp - 2) >> 2;         // hl16 epilogue: warps 2-5 take the first half of the columns, 6-9 the second
+    uint8_t* stg = sStg + (warp - 2) * 4096;   // [plane][32 rows][64 B], 16-byte chunks XOR-swizzled by (row >> 1) & 3 (SWIZZLE_64B)
     int lt = 0, gbias = -1, bsel = 1;
     bool ok = true;
     const bool has_bias = (a.bias != nullptr || a.bias2 != nullptr) && kpart == 0;
@@ -409,64 +412,53 @@ wf_ss_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         if (DROP) e4row = ((((unsigned long long)t.z * (unsigned)a.R) + (unsigned)grow) * (unsigned)a.c_cols + (unsigned)n0) >> 2;
         float amax = 0.f;
         const int npass = a.out2 ? 2 : 1;   // pass 1: the same values again as bf16 planes
+        const int cbase = chalf * (BN / 2);  // this warp's columns: [cbase, cbase + BN / 2), 32 at a time
 #pragma unroll 1
-        for (int c64p = 0; c64p < (BN / 64) * npass; ++c64p) {
-          const int c64 = (c64p / npass) * 64, pass = c64p % npass;
+        for (int c32p = 0; c32p < (BN / 64) * npass; ++c32p) {
+          const int cc = cbase + (c32p / npass) * 32, pass = c32p % npass;
           if (lane == 0) tma_store_wait_read();   // the previous boxes have been read out of the staging buffer
           __syncwarp();
+          uint32_t v[32];
+          tmem_ld32(tlane + ds * DCOLS + cc, v);
+          tmem_wait_ld();
 #pragma unroll
-          for (int half = 0; half < 2; ++half) {
-            const int cc = c64 + 32 * half;
-            uint32_t v[32];
-            tmem_ld32(tlane + ds * DCOLS + cc, v);
-            tmem_wait_ld();
+          for (int j = 0; j < 32; j += 8) {
+            uint32_t hi[4], lo[4];
 #pragma unroll
-            for (int ch = 1; ch < NC; ++ch) {
-              uint32_t w[32];
-              tmem_ld32(tlane + ds * DCOLS + ch * BN + cc, w);
-              tmem_wait_ld();
-#pragma unroll
-              for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(w[j]));
-            }
-#pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              uint32_t hi[4], lo[4];
-#pragma unroll
-              for (int e = 0; e < 8; e += 4) {
-                float4 o = make_float4(__uint_as_float(v[j + e]), __uint_as_float(v[j + e + 1]), __uint_as_float(v[j + e + 2]),
-                                       __uint_as_float(v[j + e + 3]));
-                if (SBIAS) {
-                  if (has_bias) { const float4 b = *reinterpret_cast<const float4*>(&sbias[bsel][cc + j + e]); o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w; }
-                } else if (b1) {
-                  const float4 b = __ldg(reinterpret_cast<const float4*>(b1 + cc + j + e)); o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
-                }
-                if (a.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
-                if (DROP) {
-                  float m[4];
-                  wf_drop4(dst, e4row + (unsigned)((cc + j + e) >> 2), m);
-                  o.x *= m[0]; o.y *= m[1]; o.z *= m[2]; o.w *= m[3];
-                }
-                if (valid) amax = fmaxf(amax, fmaxf(fmaxf(fabsf(o.x), fabsf(o.y)), fmaxf(fabsf(o.z), fabsf(o.w))));
-                if (pass == 0) {
-                  ss_split_f16(o.x, o.y, hi[e >> 1], lo[e >> 1]);
-                  ss_split_f16(o.z, o.w, hi[(e >> 1) + 1], lo[(e >> 1) + 1]);
-                } else {
-                  ss_split_bf16(o.x, o.y, hi[e >> 1], lo[e >> 1]);
-                  ss_split_bf16(o.z, o.w, hi[(e >> 1) + 1], lo[(e >> 1) + 1]);
-                }
+            for (int e = 0; e < 8; e += 4) {
+              float4 o = make_float4(__uint_as_float(v[j + e]), __uint_as_float(v[j + e + 1]), __uint_as_float(v[j + e + 2]),
+                                     __uint_as_float(v[j + e + 3]));
+              if (SBIAS) {
+                if (has_bias) { const float4 b = *reinterpret_cast<const float4*>(&sbias[bsel][cc + j + e]); o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w; }
+              } else if (b1) {
+                const float4 b = __ldg(reinterpret_cast<const float4*>(b1 + cc + j + e)); o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
               }
-              const int ch = (32 * half + j) >> 3;   // 16-byte chunk of this row's 128-byte line
-              const uint32_t off = (uint32_t)(lane * 128 + ((ch ^ (lane & 7)) << 4));
-              sts128(smem_u32(stg + off), make_uint4(hi[0], hi[1], hi[2], hi[3]));
-              sts128(smem_u32(stg + 4096 + off), make_uint4(lo[0], lo[1], lo[2], lo[3]));
+              if (a.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+              if (DROP) {
+                float m[4];
+                wf_drop4(dst, e4row + (unsigned)((cc + j + e) >> 2), m);
+                o.x *= m[0]; o.y *= m[1]; o.z *= m[2]; o.w *= m[3];
+              }
+              if (valid) amax = fmaxf(amax, fmaxf(fmaxf(fabsf(o.x), fabsf(o.y)), fmaxf(fabsf(o.z), fabsf(o.w))));
+              if (pass == 0) {
+                ss_split_f16(o.x, o.y, hi[e >> 1], lo[e >> 1]);
+                ss_split_f16(o.z, o.w, hi[(e >> 1) + 1], lo[(e >> 1) + 1]);
+              } else {
+                ss_split_bf16(o.x, o.y, hi[e >> 1], lo[e >> 1]);
+                ss_split_bf16(o.z, o.w, hi[(e >> 1) + 1], lo[(e >> 1) + 1]);
+              }
             }
+            const int ch = j >> 3;   // 16-byte chunk of this row's 64-byte line
+            const uint32_t off = (uint32_t)(lane * 64 + ((ch ^ ((lane >> 1) & 3)) << 4));
+            sts128(smem_u32(stg + off), make_uint4(hi[0], hi[1], hi[2], hi[3]));
+            sts128(smem_u32(stg + 2048 + off), make_uint4(lo[0], lo[1], lo[2], lo[3]));
           }
           fence_async_smem();
           __syncwarp();
           if (lane == 0) {
             const CUtensorMap* om = pass == 0 ? &tmOut : &tmOut2;
-            tma_store_4d(om, stg, n0 + c64, t.mtw * 128 + q * 32, t.z, 0);
-            tma_store_4d(om, stg + 4096, n0 + c64, t.mtw * 128 + q * 32, t.z, 1);
+            tma_store_4d(om, stg, n0 + cc, t.mtw * 128 + q * 32, t.z, 0);
+            tma_store_4d(om, stg + 2048, n0 + cc, t.mtw * 128 + q * 32, t.z, 1);
             tma_store_commit();
           }
         }
@@ -1225,6 +1217,13 @@ int map_rows_mn(CUtensorMap* m, const void* base, uint64_t C, uint64_t rows, uin
   uint32_t box[4] = {64, box_rows, 1, box_planes};
   return wf_encode_tensor_map(m, base, 4, dims, str, box, 1, ss_dtype(fmt));
 }
+// the hl16 epilogue's store box: {32 columns, 32 rows} of one plane, SWIZZLE_64B
+int map_rows_store(CUtensorMap* m, const void* base, uint64_t C, uint64_t rows, uint64_t Z, uint64_t plane, int fmt) {
+  uint64_t dims[4] = {C, rows, Z, 2};
+  uint64_t str[3] = {C * 2, rows * C * 2, plane * 2};
+  uint32_t box[4] = {32, 32, 1, 1};
+  return wf_encode_tensor_map(m, base, 4, dims, str, box, 2, ss_dtype(fmt));
+}
 // TB8 [2 planes][blocks][C/8][128 rows][8]: the 128 x 8 elements of a channel group are folded as {256, 4}.
 // fold = 4, groups = 8: a K-major [128 rows][64 k] box; fold = 2, groups = 16: an MN-major [128 channels][64 rows] box;
 // both planes in one box
@@ -1283,8 +1282,9 @@ int ss_launch_bn(const CUtensorMap& tmA, const CUtensorMap& tmA2, const CUtensor
   if (slots > total_mt) slots = total_mt;
   if (slots < 1) slots = 1;
   const int grid = slots * a.n_parts * a.k_parts;
-  if (a.drop.rng != nullptr) wf_ss_kernel<BN, true><<<grid, SS_THREADS, smem, st>>>(tmA, tmA2, tmBhi, tmBlo, tmOut, tmOut2, a);
-  else wf_ss_kernel<BN, false><<<grid, SS_THREADS, smem, st>>>(tmA, tmA2, tmBhi, tmBlo, tmOut, tmOut2, a);
+  const int threads = a.epi == SS_E_HL ? SS_THREADS_HL : SS_THREADS;
+  if (a.drop.rng != nullptr) wf_ss_kernel<BN, true><<<grid, threads, smem, st>>>(tmA, tmA2, tmBhi, tmBlo, tmOut, tmOut2, a);
+  else wf_ss_kernel<BN, false><<<grid, threads, smem, st>>>(tmA, tmA2, tmBhi, tmBlo, tmOut, tmOut2, a);
   WF_CHECK_LAUNCH("ss_kernel");
   return WF_OK;
 }
@@ -1570,8 +1570,8 @@ extern "C" int wf_gcn_layer_fwd_ss(const float* X32, const long long* x_win_off,
   else tmA2 = tmA;
   if ((rc = map_w(&tmBhi, W16_hi, Cin, Cout, 1, Cin, (long long)Cout * Cin, 128, 0))) return rc;
   if ((rc = map_w(&tmBlo, W16_lo, Cin, Cout, 1, Cin, (long long)Cout * Cin, 128, 0))) return rc;
-  if ((rc = map_rows_mn(&tmOut, Y16, Cout, R, Z, Z * R * Cout, 0))) return rc;
-  if (Yb16 != nullptr) { if ((rc = map_rows_mn(&tmOut2, Yb16, Cout, R, Z, Z * R * Cout, 1))) return rc; }
+  if ((rc = map_rows_store(&tmOut, Y16, Cout, R, Z, Z * R * Cout, 0))) return rc;
+  if (Yb16 != nullptr) { if ((rc = map_rows_store(&tmOut2, Yb16, Cout, R, Z, Z * R * Cout, 1))) return rc; }
   else tmOut2 = tmOut;
   SsArgs a;
   memset(&a, 0, sizeof(a));
