@@ -123,7 +123,7 @@ extern "C" int wf_head_bwd(const float* dpred, const float* h_top, const float* 
   float* part = (float*)workspace;
   size_t partf = (workspace_bytes - 256) / sizeof(float);
   RowMap dpm = make_rowmap(0, M, 0, O);
-  {
+  if (dlast) {   // (NULL: only the parameter gradients -- the two halves can run on different streams)
     GemmArgs a = {};
     a.A = dpred; a.am = dpm; a.gA = (long long)M * O;
     a.B = params + hw; a.bm = make_rowmap(0, O, 0, L); a.gB = params_group_stride;

@@ -17,6 +17,7 @@ per task (the replacement for ``copy.deepcopy(model)`` at train_hybrid_maml_v5.p
 from __future__ import annotations
 
 import functools
+import os
 from dataclasses import dataclass
 
 import torch
@@ -230,6 +231,12 @@ class HybridEngine:
             self._gcn_lo = {}
         self.ws_bytes = int(ws)
         self.ws = torch.empty(self.ws_bytes, dtype=torch.uint8, device=self.device)
+        # side stream for work that is off the critical path of a pass (weight staging next to the frozen GCN stack, the
+        # head's parameter gradients next to the LSTM backward); WF_OVERLAP=0 keeps everything on one stream
+        self.overlap = os.environ.get("WF_OVERLAP", "1") != "0"
+        self._side = torch.cuda.Stream(self.device)
+        self.ws_head = torch.empty(int(_lib.query("wf_head_workspace_bytes", L, d.O, d.num_nodes, self.G, self.Bw)),
+                                   dtype=torch.uint8, device=self.device)
         self.feats = None
         self.agg = None  # scratch of the GCN pre-aggregation pass (persistent path)
         self.launches = 0  # kernels enqueued by this engine (bench.py reports it)
@@ -397,17 +404,23 @@ class HybridEngine:
         return self.feats16[0]
 
     @_on_device
-    def lstm_head_forward(self, params, params_stride, feats=None):
+    def _prep_weights(self, params, params_stride):
+        """Operand staging of the persistent path: 16-bit hi/lo copies of the current (fast) weights, on the current stream."""
+        d = self.dims
+        src_stride = params_stride if self.G > 1 else self.P
+        _lib.call("wf_prep_weights_seq", _lib.ptr(params), src_stride, d.lstm_layers, d.hidden, d.lstm_hidden, d.O, self.G,
+                  _lib.ptr(self.p16[0]), _lib.ptr(self.p16[1]), _lib.ptr(self.pT16[0]), _lib.ptr(self.pT16[1]),
+                  _lib.ptr(self.w16[0]), _lib.ptr(self.w16[1]), _lib.ptr(self.w16[2]), _lib.ptr(self.w16[3]), _lib.stream_ptr())
+
+    @_on_device
+    def lstm_head_forward(self, params, params_stride, feats=None, prepped=False):
         d, st = self.dims, _lib.stream_ptr()
         feats = self.feats if feats is None else feats
         Ls, L = d.lstm_layers, d.lstm_hidden
         p_lstm, p_head = self._p(1), self._p(2)
         if self.seq:
-            # operand staging: 16-bit hi/lo copies of the current (fast) weights
-            src_stride = params_stride if self.G > 1 else self.P
-            _lib.call("wf_prep_weights_seq", _lib.ptr(params), src_stride, Ls, d.hidden, L, d.O, self.G,
-                      _lib.ptr(self.p16[0]), _lib.ptr(self.p16[1]), _lib.ptr(self.pT16[0]), _lib.ptr(self.pT16[1]),
-                      _lib.ptr(self.w16[0]), _lib.ptr(self.w16[1]), _lib.ptr(self.w16[2]), _lib.ptr(self.w16[3]), st)
+            if not prepped:
+                self._prep_weights(params, params_stride)
             self._x16 = self._seq_input_planes(feats)
             _lib.call("wf_lstm_fwd_seq", _lib.ptr(self._x16), _lib.ptr(params), _lib.ptr(self.p16[0]), _lib.ptr(self.p16[1]),
                       params_stride if self.G > 1 else self.P, _lib.ptr(self.w16[0]), _lib.ptr(self.w16[1]), Ls, d.hidden,
@@ -466,9 +479,19 @@ class HybridEngine:
         Ls, L = d.lstm_layers, d.lstm_hidden
         p_lstm, p_head = self._p(1), self._p(2)
         # the head's input is whatever the forward pass fed it: the (masked) compact last step or the top layer's rows
+        forked = self.seq and self.overlap
+        if forked:
+            # dW_o / db_o are needed only by the optimiser step: on the side stream, next to the LSTM backward, whose
+            # recurrence kernels leave 28 SMs idle; the BPTT chain only waits for dlast
+            main = torch.cuda.current_stream(self.device)
+            self._side.wait_stream(main)
+            with torch.cuda.stream(self._side):
+                _lib.call("wf_head_bwd", _lib.ptr(dpred), _lib.ptr(self._h_top), _lib.ptr(params), params_stride, Ls,
+                          d.hidden, L, d.O, self._t_head, d.num_nodes, self.G, self.Bw, None, _lib.ptr(self.grads), self.P,
+                          _lib.ptr(self.ws_head), self.ws_head.numel(), _lib.stream_ptr())
         _lib.call("wf_head_bwd", _lib.ptr(dpred), _lib.ptr(self._h_top), _lib.ptr(params), params_stride, Ls,
                   d.hidden, L, d.O, self._t_head, d.num_nodes, self.G, self.Bw, _lib.ptr(self.dlast),
-                  _lib.ptr(self.grads), self.P, _lib.ptr(self.ws), self.ws_bytes, st)
+                  None if forked else _lib.ptr(self.grads), self.P, _lib.ptr(self.ws), self.ws_bytes, st)
         if p_head > 0:
             _lib.call("wf_dropout_apply", _lib.ptr(self.dlast), 0, self.W * d.num_nodes, L, self.W * d.num_nodes, L, p_head,
                       _lib.ptr(self.rng), SITE_HEAD, _lib.ptr(self.dlast), st)
@@ -496,6 +519,8 @@ class HybridEngine:
                       _lib.ptr(self.dlast), _lib.ptr(self.grads), self.P, p_lstm, _lib.ptr(self.rng),
                       _lib.ptr(self.h_masked), _lib.ptr(self.ws), self.ws_bytes, st)
             self.launches += 6 + Ls * (d.window + 9) + (Ls - 1 if p_lstm > 0 else 0)
+        if forked:
+            torch.cuda.current_stream(self.device).wait_stream(self._side)
         return self.grads
 
     @_on_device
@@ -509,8 +534,19 @@ class HybridEngine:
     # ------------------------------------------------------------------ convenience
     def forward_backward(self, X, x_ld, x_win_stride, x_win_off, gcn_weights, graphs, params, params_stride,
                          y=None, feat=None, tgt_off=None, feat_ld=0, grad_scale=1.0):
-        self.gcn_forward(X, x_ld, x_win_stride, x_win_off, gcn_weights, graphs)
-        self.lstm_head_forward(params, params_stride)
+        if self.seq and self.overlap:
+            # the operand staging of the (fast) LSTM weights does not depend on the frozen GCN stack: fork it onto the side
+            # stream (also inside a captured graph: the fork / join become graph edges)
+            main = torch.cuda.current_stream(self.device)
+            self._side.wait_stream(main)
+            with torch.cuda.stream(self._side):
+                self._prep_weights(params, params_stride)
+            self.gcn_forward(X, x_ld, x_win_stride, x_win_off, gcn_weights, graphs)
+            main.wait_stream(self._side)
+            self.lstm_head_forward(params, params_stride, prepped=True)
+        else:
+            self.gcn_forward(X, x_ld, x_win_stride, x_win_off, gcn_weights, graphs)
+            self.lstm_head_forward(params, params_stride)
         self.mse(y, feat, tgt_off, feat_ld, grad_scale)
         self.backward(params, params_stride)
         if self.stochastic:
