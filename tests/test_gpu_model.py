@@ -238,3 +238,51 @@ def test_forward_rejects_cpu_tensors():
     x, _ = P.window_xy(feats, 0, cfg["T"], cfg["H"])
     with pytest.raises(RuntimeError):
         hyb(x, ei)
+
+
+def test_side_stream_overlap_is_bit_identical_to_one_stream():
+    """The engine forks the weight staging and the head's parameter gradients onto a side stream (also inside captured
+    graphs); the result must not depend on it: same bits with overlap on and off, eager and replayed from a CUDA graph."""
+    from weatherforecast_stgcn_maml_b200.engine import HybridEngine, V5Dims, flatten_trainable, gcn_weights_from_state_dict
+    from weatherforecast_stgcn_maml_b200.graph import RegionGraph, StackedGraphs
+
+    dims = V5Dims(num_nodes=35, window=6, horizon=3)
+    G, Bw, dev = 2, 2, "cuda"
+    lats, lons = synth.region_grid(5, 7)
+    ei = P.knn_edges_ckdtree(lats, lons, 4)
+    sd = synth.init_v5_state_dict(11, gcn_bias_scale=0.05, horizon=3)
+    feats = torch.stack([synth.synth_features(16, 35, 300 + g) for g in range(G)]).to(dev)
+    per, per_task = 35 * 24, 16 * 35 * 24
+    xo = torch.tensor([g * per_task + b * per for g in range(G) for b in range(Bw)], device=dev)
+    to = xo + (dims.window + 1) * per
+    theta = torch.stack([flatten_trainable(sd, dims) for _ in range(G)]).to(dev)
+    graphs = StackedGraphs([RegionGraph(ei, dims.R, dev) for _ in range(G)])
+    gw = gcn_weights_from_state_dict(sd, dev)
+    out = {}
+    for overlap in (True, False):
+        eng = HybridEngine(dims, G, Bw, dev)
+        if not eng.seq:
+            pytest.skip("persistent tensor-core path not available for this shape")
+        eng.overlap = overlap
+        run = lambda: eng.forward_backward(feats, 24, 0, xo, gw, graphs, theta, eng.P, feat=feats, tgt_off=to, feat_ld=24)
+        run()
+        torch.cuda.synchronize()
+        eng.check()
+        out[overlap, "eager"] = (eng.loss.clone(), eng.grads.clone())
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            run()
+        torch.cuda.current_stream().wait_stream(side)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            run()
+        eng.grads.zero_()
+        graph.replay()
+        torch.cuda.synchronize()
+        eng.check()
+        out[overlap, "graph"] = (eng.loss.clone(), eng.grads.clone())
+    ref = out[False, "eager"]
+    for key, val in out.items():
+        assert torch.equal(val[0], ref[0]) and torch.equal(val[1], ref[1]), key
+    assert float(ref[1].abs().max()) > 0
