@@ -16,7 +16,8 @@ steps = int(sys.argv[1]) if len(sys.argv) > 1 else 1
 dims = V5Dims(num_nodes=bench.NLAT * bench.NLON)
 sd = synth.init_v5_state_dict(42)
 tasks = bench.build_tasks(0, 1)
-tr = MetaTrainer(sd, tasks, dims, "cuda", use_cuda_graph=False, support_rows=bench.SUPPORT_ROWS, accum=15, dropout=(0, 0, 0))
+drop = (0.2, 0.2, 0.2) if os.environ.get("WF_ONE_STEP_DROPOUT") else (0, 0, 0)
+tr = MetaTrainer(sd, tasks, dims, "cuda", use_cuda_graph=False, support_rows=bench.SUPPORT_ROWS, accum=15, dropout=drop)
 for _ in range(steps):
     tr.meta_step()
 torch.cuda.synchronize()
